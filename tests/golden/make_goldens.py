@@ -1,0 +1,158 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference (under oracle/ref_shim.py).
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_goldens.py
+
+Weights and inputs are regenerated from seeds by oracle.recformer_oracle.make_* (numpy PCG64,
+platform independent), so the fixtures hold only the reference's OUTPUTS plus the case
+parameters.  The GPU box re-creates the identical inputs and compares against these.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import recformer_oracle as O  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def small_cfg(**kw):
+    base = dict(vocab_size=2000, num_hidden_layers=2, attention_window=[64, 64], max_position_embeddings=1030)
+    base.update(kw)
+    return base
+
+
+def build_ref_seqrec(ocfg, sd_seed, items):
+    ref = ref_shim.load_reference()
+    cfg = ref_shim.reference_config(ocfg)
+    cfg.item_num = items.shape[0]
+    m = ref.RecformerForSeqRec(cfg).eval()
+    sd = O.make_state_dict(ocfg, seed=sd_seed, prefix="longformer.")
+    m.load_state_dict(sd, strict=True)
+    m.init_item_embedding(items)
+    return m, sd
+
+
+def case_forward(name, cfg_kw, B, L, ragged, N, sd_seed=0, batch_seed=0, hidden_stride=1):
+    ocfg = O.OracleConfig(**cfg_kw)
+    items = O.make_item_table(N, ocfg.hidden_size, seed=1)
+    m, _ = build_ref_seqrec(ocfg, sd_seed, items)
+    batch = O.make_batch(ocfg, B, L, seed=batch_seed, ragged=ragged)
+    t = time.time()
+    with torch.no_grad():
+        out = m.longformer(**batch)
+        logits = m(**batch)
+    dt = time.time() - t
+    g = {"cfg": cfg_kw, "B": B, "L": L, "ragged": ragged, "N": N, "sd_seed": sd_seed, "batch_seed": batch_seed,
+         "hidden_stride": hidden_stride,
+         "pooler_output": out.pooler_output.clone(),
+         "last_hidden_sample": out.last_hidden_state[:, ::hidden_stride].clone(),
+         "logits": logits.clone(), "ref_seconds": dt}
+    print(f"{name}: ref fwd {dt:.2f}s logits std {logits.std():.3f}")
+    return g
+
+
+def case_train(name, cfg_kw, B, L, N, sd_seed=0, batch_seed=0):
+    """Loss + gradient fingerprints from the reference's own autograd (dropout disabled by
+    eval(): the reference's train-mode RNG stream cannot be reproduced, SURVEY.md §7 hard part 7)."""
+    ocfg = O.OracleConfig(**cfg_kw)
+    items = O.make_item_table(N, ocfg.hidden_size, seed=1)
+    m, _ = build_ref_seqrec(ocfg, sd_seed, items)
+    batch = O.make_batch(ocfg, B, L, seed=batch_seed, ragged=True)
+    labels = torch.from_numpy(__import__("numpy").random.default_rng(7).integers(0, N, size=B))
+    loss = m(**batch, labels=labels)
+    loss.backward()
+    grads = {}
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        gflat = p.grad.reshape(-1)
+        grads[k] = {"norm": gflat.norm().item(), "head": gflat[:32].clone(), "sum": gflat.double().sum().item()}
+        if gflat.numel() <= 4096:
+            grads[k]["full"] = p.grad.clone()
+    print(f"{name}: loss {loss.item():.6f}, {len(grads)} grads")
+    return {"cfg": cfg_kw, "B": B, "L": L, "N": N, "sd_seed": sd_seed, "batch_seed": batch_seed,
+            "labels": labels, "loss": loss.item(), "grads": grads}
+
+
+def case_ranker():
+    ru = ref_shim.load_reference_utils()
+    import numpy as np
+    rng = np.random.default_rng(11)
+    out = []
+    for B, N, tie in ((64, 4000, False), (32, 500, True), (16, 100, "all")):
+        s = torch.from_numpy(rng.standard_normal((B, N), dtype=np.float32))
+        if tie is True:
+            s = torch.round(s * 2) / 2
+        if tie == "all":
+            s = torch.zeros_like(s)
+        labels = torch.from_numpy(rng.integers(0, N, size=(B, 1)))
+        res = ru.Ranker([10, 50])(s, labels)
+        out.append({"B": B, "N": N, "tie": tie, "scores": s.half() if tie is False else s, "labels": labels,
+                    "metrics": res})
+        if tie is False:   # keep the fixture exact: recompute on the stored (half-rounded) scores
+            s2 = s.half().float()
+            out[-1]["metrics"] = ru.Ranker([10, 50])(s2, labels)
+    return out
+
+
+def case_tokenizer():
+    tk = ref_shim.load_reference_tokenization()
+
+    class Stub:
+        bos_token_id = 0
+        pad_token_id = 1
+
+    ocfg = O.OracleConfig()
+    stub = Stub()
+    stub.config = ocfg
+    stub.encode = lambda items, encode_item=True: tk.RecformerTokenizer.encode(stub, items, encode_item)
+    stub.padding = lambda item_batch, pad_to_max: tk.RecformerTokenizer.padding(stub, item_batch, pad_to_max)
+    import numpy as np
+    rng = np.random.default_rng(5)
+    users = []
+    for u in range(5):
+        n_items = int(rng.integers(1, 70))
+        items = []
+        for _ in range(n_items):
+            ln = int(rng.integers(3, 97))
+            items.append([[int(x) for x in rng.integers(3, 50265, size=ln)], [int(x) for x in rng.integers(1, 3, size=ln)]])
+        users.append(items)
+    import copy
+    enc = tk.RecformerTokenizer.batch_encode(stub, copy.deepcopy(users), encode_item=False, pad_to_max=False)
+    enc_max = tk.RecformerTokenizer.batch_encode(stub, copy.deepcopy(users), encode_item=False, pad_to_max=True)
+    return {"users": users, "batch": enc, "batch_pad_to_max": enc_max}
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    g = {}
+    g["fwd_small_ragged"] = case_forward("fwd_small_ragged", small_cfg(), B=3, L=200, ragged=True, N=300, hidden_stride=3)
+    g["fwd_small_dense"] = case_forward("fwd_small_dense", small_cfg(), B=2, L=256, ragged=False, N=300, hidden_stride=3)
+    g["fwd_small_short"] = case_forward("fwd_small_short", small_cfg(), B=4, L=97, ragged=True, N=64, hidden_stride=2)
+    for w in (128, 256, 512):
+        g[f"fwd_window_{w}"] = case_forward(f"fwd_window_{w}", small_cfg(num_hidden_layers=1, attention_window=[w]),
+                                            B=2, L=1024, ragged=True, N=64, hidden_stride=16)
+    g["fwd_c1_full"] = case_forward("fwd_c1_full", dict(), B=8, L=1024, ragged=False, N=1000, hidden_stride=64)
+    g["fwd_c1_ragged"] = case_forward("fwd_c1_ragged", dict(), B=4, L=1000, ragged=True, N=1000, hidden_stride=50,
+                                      batch_seed=3)
+    g["train_small"] = case_train("train_small", small_cfg(), B=3, L=200, N=50)
+    g["ranker"] = case_ranker()
+    g["tokenizer"] = case_tokenizer()
+    path = os.path.join(OUT, "reference_goldens.pt")
+    torch.save(g, path)
+    print("wrote", path, os.path.getsize(path) / 1e6, "MB")
+
+
+if __name__ == "__main__":
+    main()
