@@ -1,0 +1,239 @@
+/* recformer_b200 — C ABI of the B200-native Recformer encoder + scoring hot path.
+ *
+ * The reference (norahallqvistMK/RecFormer) is pure Python: it has no FFI/plugin layer, its
+ * boundary is the `recformer` Python class API.  This header is the C-ABI
+ * layer underneath our drop-in Python classes (`recformer_b200/models.py`): plain pointers and
+ * sizes, no torch types.  Every entry point cites the reference code whose arithmetic it
+ * replaces (`ref:` = reference repo path:line, `HF:` = transformers
+ * models/longformer/modeling_longformer.py which holds the un-vendored encoder arithmetic).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - every buffer (inputs, outputs, workspaces) is allocated and owned by the caller; the
+ *     library never allocates device memory and keeps no mutable global state apart from a
+ *     mutex-guarded cache of TMA descriptors / function attributes;
+ *   - kernels are enqueued on `stream` and never synchronise;
+ *   - return value: 0 on success, negative RF_ERR_* otherwise; rf_last_error() returns a
+ *     thread-local message.  No C++ exceptions cross the boundary;
+ *   - `bf16` buffers are raw uint16 storage of bfloat16; ids are int64 as produced by
+ *     torch.LongTensor (ref: recformer/tokenization.py:28-31).
+ */
+#ifndef RECFORMER_B200_H_
+#define RECFORMER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* rf_stream_t; /* == cudaStream_t */
+
+#define RF_OK 0
+#define RF_ERR_INVALID (-1) /* bad argument / unsupported shape */
+#define RF_ERR_CUDA (-2)    /* CUDA runtime / driver error       */
+
+const char* rf_last_error(void);
+int rf_version(void);
+/* Number of kernels launched by this library in the calling process so far (bench.py reports
+ * the per-step delta as `gpu_launches`). */
+unsigned long long rf_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense projections: C[M,N] = epilogue(A (*) B) on tcgen05 tensor cores (bf16 in, fp32 accum).
+ * Replaces every nn.Linear on the path — HF:503-505 (query/key/value), HF:1067 (attention
+ * output dense), HF:1112 (intermediate dense), HF:1126 (output dense) — and their autograd
+ * (dgrad / wgrad).
+ *   a_mn_major = 0: A is [M,K] row-major (lda = row pitch, elements); 1: A is stored [K,M].
+ *   b_mn_major = 0: B is [N,K] row-major (nn.Linear weight layout); 1: B is stored [K,N].
+ * Epilogue, applied in this order on the fp32 accumulator v(row, col):
+ *   v += bias[col]; if (col < scale_ncols) v *= scale;           (q /= sqrt(D), HF:513)
+ *   epi == RF_EPI_GELU : C  <- v (pre-activation), C2 <- gelu_erf(v)         (HF:1112-1115)
+ *   epi == RF_EPI_DGELU: v *= gelu_erf'(aux[row,col])                         (GELU backward)
+ *   dropout(drop_p, seed) on v;  v += residual[row,col];         (HF:1069-1070, 1128-1129)
+ *   out_f32 ? (accumulate ? C += v : C = v) as fp32 : C = bf16(v)
+ * split_k > 1 (fp32 output only) splits K over CTAs and accumulates with red.add; the caller
+ * zeroes C beforehand.
+ * ------------------------------------------------------------------------------------------ */
+enum { RF_EPI_NONE = 0, RF_EPI_GELU = 1, RF_EPI_DGELU = 2 };
+
+typedef struct rf_gemm_args {
+  const void* A;
+  const void* B;
+  void* C;
+  void* C2;             /* RF_EPI_GELU: activation output [M,N] bf16 (ldc) */
+  const float* bias;    /* [N] or NULL */
+  const void* residual; /* bf16 [M,N] (ldr) or NULL */
+  const void* aux;      /* RF_EPI_DGELU: bf16 pre-activation [M,N] (ldaux) */
+  int M, N, K;
+  int lda, ldb, ldc, ldr, ldaux;
+  int a_mn_major, b_mn_major;
+  int epi;
+  int out_f32;
+  int accumulate;
+  int split_k;
+  float scale;
+  int scale_ncols;
+  float drop_p;
+  uint64_t drop_seed;
+} rf_gemm_args;
+
+int rf_gemm_bf16(const rf_gemm_args* args, rf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Input preparation (ref: recformer/models.py:68-79 create_position_ids_from_input_ids,
+ * :262-272 _merge_to_attention_mask, :210-260 _pad_to_window_size, :327-329 extended mask).
+ * From the tokenizer's int64 [B,L] tensors builds, for the window-padded length Lp >= L:
+ *   pos_ids [B,Lp] int32 = cumsum(ids != pad) * (ids != pad) + pad   (pad for l >= L)
+ *   mask012 [B,Lp] uint8 = attention_mask * (global_attention_mask + 1)  (0 for l >= L)
+ * attention_mask == NULL means all ones; global_attention_mask == NULL means no global token.
+ * err_flag (int32, device) gets bit 0 set if any position other than 0 is marked global (the
+ * kernels implement the tokenizer's CLS-only layout, ref: recformer/tokenization.py:97-99).
+ * ------------------------------------------------------------------------------------------ */
+int rf_prepare_inputs(const int64_t* input_ids, const int64_t* attention_mask, const int64_t* global_attention_mask,
+                      int B, int L, int Lp, int padding_idx, int32_t* pos_ids, uint8_t* mask012, int* err_flag,
+                      rf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * RecformerEmbeddings (ref: recformer/models.py:108-138): 4-table gather-sum, LayerNorm,
+ * dropout — one kernel, one warp per token, 128-bit loads, warp-shuffle statistics.
+ *   out[t,:] = dropout(LN(word[ids[t]] + pos[pid[t]] + type[tt[t]] + item[ip[t]]))   (bf16)
+ * Tokens l in [L, Lp) are the window padding of _pad_to_window_size (ids = pad, position = pad,
+ * item position = pad (sic, models.py:244), token type = 0).  pos_ids is the int32 [B,Lp] array
+ * from rf_prepare_inputs (or caller-provided position ids).  Out-of-range ids set bit 1 of
+ * err_flag and are clamped.
+ * rf_embed_ln_bwd recomputes the sum/statistics, back-propagates LayerNorm and scatter-adds
+ * into the fp32 gradient tables (any of which may be NULL = frozen, e.g. --fix_word_embedding,
+ * ref: finetune.py:272-275) and accumulates dgamma/dbeta.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct rf_embed_args {
+  const int64_t* input_ids;          /* [B,L] */
+  const int64_t* token_type_ids;     /* [B,L] or NULL (zeros) */
+  const int64_t* item_position_ids;  /* [B,L] */
+  const int32_t* pos_ids;            /* [B,Lp] */
+  const float* word_emb;             /* [vocab,E] */
+  const float* pos_emb;              /* [max_pos,E] */
+  const float* type_emb;             /* [type_size,E] */
+  const float* item_emb;             /* [max_item,E] */
+  const float* ln_gamma;
+  const float* ln_beta;
+  int B, L, Lp, E;
+  int vocab, max_pos, type_size, max_item;
+  int padding_idx;
+  float eps;
+  float drop_p;
+  uint64_t drop_seed;
+} rf_embed_args;
+
+int rf_embed_ln_fwd(const rf_embed_args* a, void* out_bf16, int* err_flag, rf_stream_t stream);
+int rf_embed_ln_bwd(const rf_embed_args* a, const void* dout_bf16, float* d_word, float* d_pos, float* d_type,
+                    float* d_item, float* d_gamma, float* d_beta, rf_stream_t stream);
+
+/* LayerNorm over the last dim (E = 768) of a bf16 [T,E] tensor; fp32 statistics saved as
+ * stats[t] = (mean, rstd).  Replaces nn.LayerNorm at HF:1070, HF:1129.
+ * bwd: dx (bf16) from dy (bf16), pre-LN input x and stats; dgamma/dbeta accumulated (fp32,
+ * += ).  If dx_dropped != NULL it also receives dropout-masked dx (mask regenerated from
+ * drop_seed; the dense branch's gradient, HF:1069) while dx keeps the residual branch's. */
+/* out[n] += sum_t x[t,n] for a bf16 [T,N] matrix (bias gradients of the dense layers). */
+int rf_colsum_bf16(const void* x_bf16, float* out, int T, int N, int ld, rf_stream_t stream);
+int rf_layernorm_fwd(const void* x_bf16, const float* gamma, const float* beta, void* y_bf16, float* stats, int T,
+                     int E, float eps, rf_stream_t stream);
+int rf_layernorm_bwd(const void* dy_bf16, const void* x_bf16, const float* stats, const float* gamma, void* dx_bf16,
+                     void* dx_dropped_bf16, float drop_p, uint64_t drop_seed, float* d_gamma, float* d_beta, int T,
+                     int E, rf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Longformer sliding-window attention with a global CLS token (SURVEY.md §8a Spec A;
+ * HF:481-639 + helpers HF:641-961).  qkv is the fused projection output [B*L, 3*E] bf16 with
+ * q already scaled by 1/sqrt(D); mask012 is the merged mask (ref: recformer/models.py:262-272)
+ * as uint8 [B,L]: 0 padding, 1 local, 2 global.  Only position 0 may be global (the
+ * tokenizer's layout, ref: recformer/tokenization.py:97-99).  One CTA per (batch, head,
+ * 128-query tile): TMA loads, QK^T and PV on tcgen05 with TMEM accumulators, fp32 softmax.
+ *   ctx  [B*L, E] bf16: attention output of every NON-global query (row 0 of each sequence
+ *        is written by rf_global_attn_fwd); padded query rows are exactly zero (HF:578).
+ *   lse  [B,H,L] fp32: log-sum-exp of each query row (saved for backward).
+ * one_sided_window w = attention_window/2 must be a multiple of 32 and <= 256.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct rf_attn_args {
+  const void* qkv; /* bf16 [B*L, 3E] */
+  const uint8_t* mask012;
+  int B, L, H, D;
+  int w; /* one-sided window */
+  float drop_p;
+  uint64_t drop_seed;
+} rf_attn_args;
+
+int rf_band_attn_fwd(const rf_attn_args* a, void* ctx_bf16, float* lse, rf_stream_t stream);
+/* dqkv [B*L,3E] bf16 (gradient w.r.t. the UNSCALED q and k, v projections), given dctx.
+ * dkv_cls [B,H,2,D] fp32 scratch receives the CLS key/value gradient contributions and is
+ * folded into row 0 of dqkv by the kernel's final phase. */
+int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx_bf16, const float* lse, const void* dctx_bf16,
+                     void* dqkv_bf16, float* dkv_cls, rf_stream_t stream);
+
+/* Global (CLS) query row (HF:963-1056), re-associated so that key_global/value_global are
+ * never applied to all L tokens (SURVEY.md §7 hard part 3):
+ *   q_g = (Wqg x_cls + bqg)/sqrt(D);  u_h = Wkg[h]^T q_g[h];  s_j = u_h . x_j  (b_kg cancels in
+ *   the softmax);  p = softmax_{valid j}(s);  m_h = sum_j p_j x_j;  out[h] = Wvg[h] m_h + bvg[h].
+ * Writes row 0 of every sequence in ctx.  Saved for backward: qg [B,E], u [B,H,E], p [B,H,L],
+ * mvec [B,H,E], psum [B,H] = sum_j dropout(p)_j (all fp32). */
+typedef struct rf_global_args {
+  const void* x;  /* bf16 [B*L,E] layer input */
+  const uint8_t* mask012;
+  const float* Wqg; const float* bqg;
+  const float* Wkg;
+  const float* Wvg; const float* bvg;
+  int B, L, H, D;
+  float drop_p;
+  uint64_t drop_seed;
+} rf_global_args;
+
+int rf_global_attn_fwd(const rf_global_args* a, void* ctx_bf16, float* qg, float* u, float* p, float* mvec,
+                       float* psum, rf_stream_t stream);
+/* Backward of the CLS row: reads dctx row 0; accumulates (+=) fp32 dWqg,dbqg,dWkg,dWvg,dbvg and
+ * ADDS the dense gradient it sends to every token (through s_j and m_h) into dx (bf16 [B*L,E]). */
+int rf_global_attn_bwd(const rf_global_args* a, const void* dctx_bf16, const float* qg, const float* u,
+                       const float* p, const float* mvec, void* dx_bf16, float* dWqg, float* dbqg, float* dWkg,
+                       float* dWvg, float* dbvg, float* ws, rf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Scoring (SURVEY.md §8a Spec S; ref: recformer/models.py:358-369,533-545) and metrics
+ * (Spec R; ref: utils.py:76-107).
+ * ------------------------------------------------------------------------------------------ */
+/* y[n,:] = bf16(x[n,:] / max(||x[n,:]||, 1e-8)); fp32 or bf16 input. */
+int rf_normalize_rows(const void* x, int x_is_bf16, void* y_bf16, float* norms_or_null, long long N, int E,
+                      rf_stream_t stream);
+/* logits[b,n] = (xn[b] . yn[n]) / temp as fp32 [B,N] (xn, yn L2-normalised bf16). */
+int rf_cosine_logits(const void* xn_bf16, const void* yn_bf16, float* logits, int B, long long N, int E, float temp,
+                     rf_stream_t stream);
+/* Fused cosine-GEMM + temperature + per-CTA top-k: the (B,N) logits never reach HBM.
+ * Outputs per user the k best (score fp32 desc, id int32; ties -> lower id) over this table
+ * (ids offset by id_base for a shard), plus label_score[b] = logit of labels[b] if that id
+ * lies in [id_base, id_base+N), else -inf.  ws must hold rf_cosine_topk_ws_bytes(). */
+long long rf_cosine_topk_ws_bytes(int B, long long N, int k);
+int rf_cosine_topk(const void* xn_bf16, const void* yn_bf16, int B, long long N, int E, float temp, int k,
+                   int id_base, const int64_t* labels_or_null, float* topk_scores, int32_t* topk_ids,
+                   float* label_score, void* ws, rf_stream_t stream);
+/* Merge `parts` lists of k (score,id) per user (e.g. the all-gathered per-GPU top-k) into the
+ * global top-k; label scores are max-reduced over parts. */
+int rf_topk_merge(const float* scores, const int32_t* ids, const float* label_scores, int parts, int B, int k,
+                  float* out_scores, int32_t* out_ids, float* out_label_score, rf_stream_t stream);
+/* Full-softmax cross entropy over cosine logits and its gradient w.r.t. the pooled vector
+ * (ref: recformer/models.py:587-591): loss = mean_b(lse_n logit[b,n] - logit[b,label_b]). */
+int rf_cosine_ce(const void* pooled_bf16_or_f32, int pooled_is_bf16, const void* yn_bf16, const int64_t* labels,
+                 int B, long long N, int E, float temp, float* loss, float* dpooled_f32, float* ws,
+                 rf_stream_t stream);
+long long rf_cosine_ce_ws_bytes(int B, long long N, int E);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser plumbing on the flat parameter buffer: fused AdamW (ref: optimization.py:7-34 uses
+ * torch AdamW) that also refreshes the bf16 shadow weights, and a plain fp32->bf16 cast.
+ * ------------------------------------------------------------------------------------------ */
+int rf_cast_f32_to_bf16(const float* x, void* y_bf16, long long n, rf_stream_t stream);
+int rf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16_or_null,
+                  long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                  float grad_scale, rf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECFORMER_B200_H_ */

@@ -1,0 +1,316 @@
+// Banded (sliding-window) attention forward with a global CLS key column, sm_100a.
+//
+// One CTA = one (batch, head, 128-query tile).  Keys j in [i0-W, i0+127+W] (NK = 128+2W rows)
+// plus the sequence's first 16 rows (row 0 = the global CLS key) are TMA-loaded once
+// (128B-swizzled, out-of-range rows zero-filled by TMA), then
+//   S[128 x (NK+16)] = Q K^T          tcgen05.mma, fp32 accumulator in TMEM
+//   softmax over the band + CLS column in fp32, one thread per query row (tcgen05.ld); the
+//   band / padding / global masks are predicates on (row, column), never materialised
+//   P (bf16) -> shared memory in the K-major UMMA layout (aliasing the dead Q/K tiles)
+//   O[128 x 64] = P V                 tcgen05.mma (V is the MN-major B operand, no transpose)
+//   O / rowsum -> bf16 context; log-sum-exp saved for the backward pass.
+// Semantics: SURVEY.md §8a Spec A / HF:481-639.  Global keys are removed from the band and
+// re-enter through the extra column (HF:523,558-568); padded query rows produce zeros (HF:578);
+// the global query row (position 0 when mask012==2) is left to rf_global_attn_fwd (HF:963-1056).
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "rf_common.h"
+#include "rf_ptx.cuh"
+
+namespace rf {
+
+constexpr int ATT_THREADS = 128;
+constexpr int HEAD_DIM = 64;
+
+template <int W>
+struct AttnFwdCfg {
+  static constexpr int NK = 128 + 2 * W;       // band key rows
+  static constexpr int NT = NK + 16;           // + global chunk
+  static constexpr int PCH = (NT + 63) / 64;   // 64-key P chunks
+  static constexpr uint32_t Q_BYTES = 128 * 128;
+  static constexpr uint32_t KV_BYTES = NT * 128;
+  static constexpr uint32_t P_BYTES = PCH * 16384;
+  static constexpr uint32_t REGION_A = (Q_BYTES + KV_BYTES > P_BYTES) ? (Q_BYTES + KV_BYTES) : P_BYTES;
+  static constexpr uint32_t OFF_V = REGION_A;
+  static constexpr uint32_t OFF_FLAG = OFF_V + KV_BYTES;
+  static constexpr uint32_t OFF_BAR = OFF_FLAG + ((NT + 15) / 16) * 16;
+  static constexpr uint32_t TOTAL = OFF_BAR + 64 + 1024;
+  static constexpr uint32_t TMEM_COLS = (NT <= 256) ? 256 : 512;
+  static_assert(NT <= 512, "window too large for the single-shot kernel");
+  static_assert(TOTAL <= 227 * 1024, "shared memory budget");
+};
+
+struct AttnFwdParams {
+  const uint8_t* mask012;
+  __nv_bfloat16* ctx;
+  float* lse;
+  int B, L, H;
+  float drop_scale;
+  uint32_t drop_thresh;
+  uint64_t drop_seed;
+};
+
+template <int W>
+__global__ void __launch_bounds__(ATT_THREADS)
+band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
+                     const AttnFwdParams p) {
+  using C = AttnFwdCfg<W>;
+  constexpr int NK = C::NK, NT = C::NT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + C::Q_BYTES;
+  uint8_t* sP = smem;  // aliases Q/K once S has been computed
+  uint8_t* sV = smem + C::OFF_V;
+  uint8_t* kflag = smem + C::OFF_FLAG;
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* bar_mma = bar_load + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int tiles_per_seq = (p.L + 127) / 128;
+  const int tile = blockIdx.x % tiles_per_seq;
+  const int h = (blockIdx.x / tiles_per_seq) % p.H;
+  const int b = blockIdx.x / (tiles_per_seq * p.H);
+  const int i0 = tile * 128;
+  const int E = p.H * HEAD_DIM;
+  const uint8_t* mrow = p.mask012 + static_cast<size_t>(b) * p.L;
+
+  if (tid == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  for (int c = tid; c < NT; c += ATT_THREADS) {
+    uint8_t f = 0;
+    if (c < NK) {
+      const int j = i0 - W + c;
+      f = (j >= 0 && j < p.L && mrow[j] == 1) ? 1 : 0;
+    } else if (c == NK) {
+      f = (mrow[0] == 2) ? 1 : 0;
+    }
+    kflag[c] = f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_load, C::Q_BYTES + 2 * C::KV_BYTES);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) tma_load_3d(sQ + c * 8192, &tm64, bar_load, h * HEAD_DIM, i0 + c * 64, b);
+#pragma unroll
+    for (int c = 0; c < NK / 64; ++c) {
+      tma_load_3d(sK + c * 8192, &tm64, bar_load, E + h * HEAD_DIM, i0 - W + c * 64, b);
+      tma_load_3d(sV + c * 8192, &tm64, bar_load, 2 * E + h * HEAD_DIM, i0 - W + c * 64, b);
+    }
+    tma_load_3d(sK + NK * 128, &tm16, bar_load, E + h * HEAD_DIM, 0, b);
+    tma_load_3d(sV + NK * 128, &tm16, bar_load, 2 * E + h * HEAD_DIM, 0, b);
+    // ---- S = Q K^T ----
+    mbar_wait(bar_load, 0);
+    tc_fence_after();
+    const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK);
+#pragma unroll
+    for (int n0 = 0; n0 < NT; n0 += 256) {
+      const int n = (NT - n0) < 256 ? (NT - n0) : 256;
+      const uint32_t idesc = umma_idesc_bf16(128, n, false, false);
+#pragma unroll
+      for (int k = 0; k < HEAD_DIM / 16; ++k)
+        umma_bf16(tmem + n0, umma_smem_desc(aq + k * 32, 16, 1024), umma_smem_desc(ak + n0 * 128 + k * 32, 16, 1024),
+                  idesc, k > 0 ? 1u : 0u);
+    }
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+
+  // ---- softmax: thread r owns query row i0 + r (TMEM lane r) ----
+  const int r = tid;
+  const int i = i0 + r;
+  const bool row_valid = (i < p.L) && (mrow[i < p.L ? i : 0] != 0);
+  const uint32_t lane_base = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  constexpr int WIN_CH = 2 * W / 32 + 1;   // 32-column chunks that can hold this warp's band
+  const float LOG2E = 1.4426950408889634f;
+
+  float m = -INFINITY;
+  {
+#pragma unroll 1
+    for (int cc = warp; cc < warp + WIN_CH; ++cc) {
+      uint32_t v[32];
+      tmem_ld32(lane_base + cc * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = cc * 32 + j;
+        const bool ok = kflag[c] && (c >= r) && (c <= r + 2 * W);
+        m = ok ? fmaxf(m, __uint_as_float(v[j])) : m;
+      }
+    }
+  }
+  uint32_t g16[16];
+  tmem_ld16(lane_base + NK, g16);
+  tmem_ld_wait();
+  const float sg = __uint_as_float(g16[0]);
+  const bool g_ok = kflag[NK] != 0;
+  if (g_ok) m = fmaxf(m, sg);
+  if (!row_valid || m == -INFINITY) m = 0.0f;   // fully masked row: every p below is forced to 0
+  const float m2 = m * LOG2E;
+
+  float l = 0.0f;
+#pragma unroll 1
+  for (int cc = 0; cc < NK / 32; ++cc) {
+    uint4 out[4];
+    if (cc >= warp && cc < warp + WIN_CH) {   // warp-uniform
+      uint32_t v[32];
+      tmem_ld32(lane_base + cc * 32, v);
+      tmem_ld_wait();
+      float pr[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = cc * 32 + j;
+        const bool ok = row_valid && kflag[c] && (c >= r) && (c <= r + 2 * W);
+        const float e = ok ? exp2f(__uint_as_float(v[j]) * LOG2E - m2) : 0.0f;
+        l += e;
+        pr[j] = e;
+      }
+      if (p.drop_thresh != 0) {
+        // mask keyed on (row, diagonal offset d = c - r) in groups of 8 along d
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int d = cc * 32 + j - r;
+          if (d >= 0 && d <= 2 * W) {
+            const uint64_t rowid = (static_cast<uint64_t>(b) * p.H + h) * p.L + i;
+            const uint32_t keep = dropout_keep8(p.drop_seed, rowid * ((2 * W + 16) / 8) + (d >> 3), p.drop_thresh);
+            pr[j] = ((keep >> (d & 7)) & 1u) ? pr[j] * p.drop_scale : 0.0f;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        out[u].x = pack_bf16(pr[u * 8 + 0], pr[u * 8 + 1]);
+        out[u].y = pack_bf16(pr[u * 8 + 2], pr[u * 8 + 3]);
+        out[u].z = pack_bf16(pr[u * 8 + 4], pr[u * 8 + 5]);
+        out[u].w = pack_bf16(pr[u * 8 + 6], pr[u * 8 + 7]);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) out[u] = make_uint4(0, 0, 0, 0);
+    }
+    uint8_t* prow = sP + (cc >> 1) * 16384 + r * 128;
+    const int ubase = (cc & 1) * 4;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(prow + (((ubase + u) ^ (r & 7)) << 4)) = out[u];
+  }
+  {
+    float pg = (row_valid && g_ok) ? exp2f(sg * LOG2E - m2) : 0.0f;
+    l += pg;
+    if (p.drop_thresh != 0) {
+      const uint64_t rowid = (static_cast<uint64_t>(b) * p.H + h) * p.L + i;
+      const int d = 2 * W + 1;
+      const uint32_t keep = dropout_keep8(p.drop_seed, rowid * ((2 * W + 16) / 8) + (d >> 3), p.drop_thresh);
+      pg = ((keep >> (d & 7)) & 1u) ? pg * p.drop_scale : 0.0f;
+    }
+    uint8_t* prow = sP + (NK / 64) * 16384 + r * 128;
+    *reinterpret_cast<uint4*>(prow + ((0 ^ (r & 7)) << 4)) = make_uint4(pack_bf16(pg, 0.0f), 0, 0, 0);
+    *reinterpret_cast<uint4*>(prow + ((1 ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+  }
+
+  // ---- O = P V ----
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t ap = smem_u32(sP), av = smem_u32(sV);
+    constexpr uint32_t idesc2 = umma_idesc_bf16(128, HEAD_DIM, false, true);
+#pragma unroll
+    for (int ks = 0; ks < NT / 16; ++ks)
+      umma_bf16(tmem, umma_smem_desc(ap + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+                umma_smem_desc(av + ks * 2048, 8192, 1024), idesc2, ks > 0 ? 1u : 0u);
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 1);
+  tc_fence_after();
+
+  const float inv_l = l > 0.0f ? 1.0f / l : 0.0f;
+  const bool is_global_row = (i == 0) && (mrow[0] == 2);
+  const bool do_store = (i < p.L) && !is_global_row;
+  __nv_bfloat16* orow = p.ctx + (static_cast<size_t>(b) * p.L + (do_store ? i : 0)) * E + h * HEAD_DIM;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t v[32];
+    tmem_ld32(lane_base + half * 32, v);   // warp-collective: executed by every lane
+    tmem_ld_wait();
+    if (do_store) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 o;
+        o.x = pack_bf16(__uint_as_float(v[j]) * inv_l, __uint_as_float(v[j + 1]) * inv_l);
+        o.y = pack_bf16(__uint_as_float(v[j + 2]) * inv_l, __uint_as_float(v[j + 3]) * inv_l);
+        o.z = pack_bf16(__uint_as_float(v[j + 4]) * inv_l, __uint_as_float(v[j + 5]) * inv_l);
+        o.w = pack_bf16(__uint_as_float(v[j + 6]) * inv_l, __uint_as_float(v[j + 7]) * inv_l);
+        *reinterpret_cast<uint4*>(orow + half * 32 + j) = o;
+      }
+    }
+  }
+  if (i < p.L) p.lse[(static_cast<size_t>(b) * p.H + h) * p.L + i] = (l > 0.0f) ? (m + logf(l)) : 0.0f;
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, C::TMEM_COLS);
+  }
+}
+
+template <int W>
+static int launch_attn_fwd(const rf_attn_args* a, void* ctx, float* lse, cudaStream_t stream) {
+  using C = AttnFwdCfg<W>;
+  auto kern = band_attn_fwd_kernel<W>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+    attr_set = true;
+  }
+  const int E = a->H * HEAD_DIM;
+  const CUtensorMap* tm64 = get_tmap_3d(a->qkv, a->B, a->L, 3 * E, 3 * E, static_cast<uint64_t>(a->L) * 3 * E, 64);
+  const CUtensorMap* tm16 = get_tmap_3d(a->qkv, a->B, a->L, 3 * E, 3 * E, static_cast<uint64_t>(a->L) * 3 * E, 16);
+  if (!tm64 || !tm16) return RF_ERR_CUDA;
+  AttnFwdParams p;
+  p.mask012 = a->mask012;
+  p.ctx = reinterpret_cast<__nv_bfloat16*>(ctx);
+  p.lse = lse;
+  p.B = a->B; p.L = a->L; p.H = a->H;
+  p.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
+  p.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
+  p.drop_seed = a->drop_seed;
+  const int tiles = (a->L + 127) / 128;
+  kern<<<a->B * a->H * tiles, ATT_THREADS, C::TOTAL, stream>>>(*tm64, *tm16, p);
+  return check_launch("rf_band_attn_fwd");
+}
+
+}  // namespace rf
+
+extern "C" int rf_band_attn_fwd(const rf_attn_args* a, void* ctx, float* lse, rf_stream_t stream_) {
+  using namespace rf;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(a && ctx && lse, "rf_band_attn_fwd: null argument");
+  RF_REQUIRE(a->D == HEAD_DIM, "rf_band_attn_fwd: head_dim %d unsupported (64 only)", a->D);
+  RF_REQUIRE(a->B > 0 && a->L >= 16 && a->H > 0, "rf_band_attn_fwd: bad shape B=%d L=%d H=%d", a->B, a->L, a->H);
+  switch (a->w) {
+    case 32: return launch_attn_fwd<32>(a, ctx, lse, stream);
+    case 64: return launch_attn_fwd<64>(a, ctx, lse, stream);
+    case 128: return launch_attn_fwd<128>(a, ctx, lse, stream);
+    default:
+      return set_error(RF_ERR_INVALID, "rf_band_attn_fwd: one-sided window %d unsupported (32, 64, 128)", a->w);
+  }
+}

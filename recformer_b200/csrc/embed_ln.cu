@@ -1,0 +1,512 @@
+// Memory-bound row kernels: input preparation, fused embedding-sum + LayerNorm (+dropout),
+// LayerNorm forward/backward, fp32->bf16 cast and fused AdamW.  One warp per token row, 128-bit
+// coalesced accesses, warp-shuffle reductions, fp32 statistics.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "rf_common.h"
+#include "rf_ptx.cuh"
+
+namespace rf {
+
+constexpr int ROW_THREADS = 256;  // 8 warps = 8 rows per CTA pass
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// keep-mask for 4 consecutive elements (group index = element index / 4)
+__device__ __forceinline__ uint32_t dropout_keep4(uint64_t seed, uint64_t grp4, uint32_t thresh16) {
+  const uint4 r = philox4x32(seed, grp4);
+  return ((r.x & 0xFFFFu) >= thresh16 ? 1u : 0u) | ((r.x >> 16) >= thresh16 ? 2u : 0u) |
+         ((r.y & 0xFFFFu) >= thresh16 ? 4u : 0u) | ((r.y >> 16) >= thresh16 ? 8u : 0u);
+}
+
+// ----------------------------------------------------------------------------------------------
+// rf_prepare_inputs: one warp per sequence, ballot/popc scan over 32-token groups
+// ----------------------------------------------------------------------------------------------
+__global__ void prepare_inputs_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ am,
+                                      const int64_t* __restrict__ gm, int B, int L, int Lp, int pad,
+                                      int32_t* __restrict__ pos_ids, uint8_t* __restrict__ mask012, int* err_flag) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  int running = 0;
+  bool bad_global = false;
+  for (int l0 = 0; l0 < Lp; l0 += 32) {
+    const int l = l0 + lane;
+    const bool in = l < L;
+    const bool nonpad = in && ids[static_cast<size_t>(b) * L + l] != pad;
+    const uint32_t bal = __ballot_sync(0xffffffffu, nonpad);
+    const int incl = running + __popc(bal & (0xffffffffu >> (31 - lane)));
+    if (l < Lp) {
+      pos_ids[static_cast<size_t>(b) * Lp + l] = nonpad ? incl + pad : pad;
+      int m = 0;
+      if (in) {
+        const int a = am ? static_cast<int>(am[static_cast<size_t>(b) * L + l]) : 1;
+        const int g = gm ? static_cast<int>(gm[static_cast<size_t>(b) * L + l]) : 0;
+        m = a * (g + 1);
+        if (m > 1 && l != 0) bad_global = true;
+        if (m < 0 || m > 2) bad_global = true;
+      }
+      mask012[static_cast<size_t>(b) * Lp + l] = static_cast<uint8_t>(m < 0 ? 0 : (m > 2 ? 2 : m));
+    }
+    running += __popc(bal);
+  }
+  if (__any_sync(0xffffffffu, bad_global) && lane == 0) atomicOr(err_flag, 1);
+}
+
+// ----------------------------------------------------------------------------------------------
+// fused embedding sum + LayerNorm.  NV4 = E / 128 float4 per lane.
+// ----------------------------------------------------------------------------------------------
+struct EmbedDev {
+  const int64_t* ids; const int64_t* tt; const int64_t* ip; const int32_t* pos;
+  const float* word; const float* posw; const float* type; const float* item;
+  const float* gamma; const float* beta;
+  int B, L, Lp, E, vocab, max_pos, type_size, max_item, pad;
+  float eps, drop_scale; uint32_t drop_thresh; uint64_t drop_seed;
+};
+
+__device__ __forceinline__ void embed_token_ids(const EmbedDev& a, int t, int& id, int& pid, int& tt, int& ip,
+                                                bool& bad) {
+  const int b = t / a.Lp, l = t % a.Lp;
+  if (l < a.L) {
+    const size_t s = static_cast<size_t>(b) * a.L + l;
+    id = static_cast<int>(a.ids[s]);
+    tt = a.tt ? static_cast<int>(a.tt[s]) : 0;
+    ip = static_cast<int>(a.ip[s]);
+  } else {  // window padding (ref: recformer/models.py:238-258)
+    id = a.pad; tt = 0; ip = a.pad;
+  }
+  pid = a.pos[t];
+  bad = id < 0 || id >= a.vocab || pid < 0 || pid >= a.max_pos || tt < 0 || tt >= a.type_size || ip < 0 ||
+        ip >= a.max_item;
+  id = min(max(id, 0), a.vocab - 1);
+  pid = min(max(pid, 0), a.max_pos - 1);
+  tt = min(max(tt, 0), a.type_size - 1);
+  ip = min(max(ip, 0), a.max_item - 1);
+}
+
+template <int NV4>
+__device__ __forceinline__ void embed_row_stats(const EmbedDev& a, int id, int pid, int tt, int ip, int lane,
+                                                float4 (&x)[NV4], float& mean, float& rstd) {
+  const float4* w = reinterpret_cast<const float4*>(a.word + static_cast<size_t>(id) * a.E);
+  const float4* pw = reinterpret_cast<const float4*>(a.posw + static_cast<size_t>(pid) * a.E);
+  const float4* tw = reinterpret_cast<const float4*>(a.type + static_cast<size_t>(tt) * a.E);
+  const float4* iw = reinterpret_cast<const float4*>(a.item + static_cast<size_t>(ip) * a.E);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV4; ++k) {
+    const int v = k * 32 + lane;
+    const float4 a0 = __ldg(w + v), a1 = __ldg(pw + v), a2 = __ldg(tw + v), a3 = __ldg(iw + v);
+    // same association order as the reference: ((word + pos) + type) + item
+    x[k].x = ((a0.x + a1.x) + a2.x) + a3.x;
+    x[k].y = ((a0.y + a1.y) + a2.y) + a3.y;
+    x[k].z = ((a0.z + a1.z) + a2.z) + a3.z;
+    x[k].w = ((a0.w + a1.w) + a2.w) + a3.w;
+    s += (x[k].x + x[k].y) + (x[k].z + x[k].w);
+  }
+  mean = warp_sum(s) / a.E;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV4; ++k) {
+    const float dx = x[k].x - mean, dy = x[k].y - mean, dz = x[k].z - mean, dw = x[k].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+  rstd = rsqrtf(warp_sum(q) / a.E + a.eps);
+}
+
+template <int NV4>
+__global__ void __launch_bounds__(ROW_THREADS) embed_ln_fwd_kernel(const EmbedDev a, __nv_bfloat16* __restrict__ out,
+                                                                   int* err_flag) {
+  const int lane = threadIdx.x & 31;
+  const int T = a.B * a.Lp;
+  for (int t = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); t < T; t += gridDim.x * (ROW_THREADS / 32)) {
+    int id, pid, tt, ip;
+    bool bad;
+    embed_token_ids(a, t, id, pid, tt, ip, bad);
+    if (bad && lane == 0 && err_flag) atomicOr(err_flag, 2);
+    float4 x[NV4];
+    float mean, rstd;
+    embed_row_stats<NV4>(a, id, pid, tt, ip, lane, x, mean, rstd);
+    const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(a.beta);
+    uint2* o2 = reinterpret_cast<uint2*>(out + static_cast<size_t>(t) * a.E);
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) {
+      const int v = k * 32 + lane;
+      const float4 g = __ldg(g4 + v), be = __ldg(b4 + v);
+      float y0 = (x[k].x - mean) * rstd * g.x + be.x, y1 = (x[k].y - mean) * rstd * g.y + be.y;
+      float y2 = (x[k].z - mean) * rstd * g.z + be.z, y3 = (x[k].w - mean) * rstd * g.w + be.w;
+      if (a.drop_thresh != 0) {
+        const uint32_t keep = dropout_keep4(a.drop_seed, static_cast<uint64_t>(t) * (a.E / 4) + v, a.drop_thresh);
+        y0 = (keep & 1u) ? y0 * a.drop_scale : 0.f; y1 = (keep & 2u) ? y1 * a.drop_scale : 0.f;
+        y2 = (keep & 4u) ? y2 * a.drop_scale : 0.f; y3 = (keep & 8u) ? y3 * a.drop_scale : 0.f;
+      }
+      o2[v] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+    }
+  }
+}
+
+template <int NV4>
+__global__ void __launch_bounds__(ROW_THREADS)
+embed_ln_bwd_kernel(const EmbedDev a, const __nv_bfloat16* __restrict__ dout, float* d_word, float* d_pos,
+                    float* d_type, float* d_item, float* d_gamma, float* d_beta) {
+  const int lane = threadIdx.x & 31;
+  const int T = a.B * a.Lp;
+  float4 dg[NV4], db[NV4];
+#pragma unroll
+  for (int k = 0; k < NV4; ++k) dg[k] = db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); t < T; t += gridDim.x * (ROW_THREADS / 32)) {
+    int id, pid, tt, ip;
+    bool bad;
+    embed_token_ids(a, t, id, pid, tt, ip, bad);
+    float4 x[NV4];
+    float mean, rstd;
+    embed_row_stats<NV4>(a, id, pid, tt, ip, lane, x, mean, rstd);
+    const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
+    const uint2* d2 = reinterpret_cast<const uint2*>(dout + static_cast<size_t>(t) * a.E);
+    float4 gy[NV4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) {
+      const int v = k * 32 + lane;
+      const uint2 raw = d2[v];
+      float2 lo = unpack_bf16(raw.x), hi = unpack_bf16(raw.y);
+      float4 dy = make_float4(lo.x, lo.y, hi.x, hi.y);
+      if (a.drop_thresh != 0) {
+        const uint32_t keep = dropout_keep4(a.drop_seed, static_cast<uint64_t>(t) * (a.E / 4) + v, a.drop_thresh);
+        dy.x = (keep & 1u) ? dy.x * a.drop_scale : 0.f; dy.y = (keep & 2u) ? dy.y * a.drop_scale : 0.f;
+        dy.z = (keep & 4u) ? dy.z * a.drop_scale : 0.f; dy.w = (keep & 8u) ? dy.w * a.drop_scale : 0.f;
+      }
+      const float4 xh = make_float4((x[k].x - mean) * rstd, (x[k].y - mean) * rstd, (x[k].z - mean) * rstd,
+                                    (x[k].w - mean) * rstd);
+      x[k] = xh;
+      dg[k].x += dy.x * xh.x; dg[k].y += dy.y * xh.y; dg[k].z += dy.z * xh.z; dg[k].w += dy.w * xh.w;
+      db[k].x += dy.x; db[k].y += dy.y; db[k].z += dy.z; db[k].w += dy.w;
+      const float4 g = __ldg(g4 + v);
+      gy[k] = make_float4(dy.x * g.x, dy.y * g.y, dy.z * g.z, dy.w * g.w);
+      s1 += (gy[k].x + gy[k].y) + (gy[k].z + gy[k].w);
+      s2 += (gy[k].x * xh.x + gy[k].y * xh.y) + (gy[k].z * xh.z + gy[k].w * xh.w);
+    }
+    s1 = warp_sum(s1) / a.E;
+    s2 = warp_sum(s2) / a.E;
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) {
+      const int v = k * 32 + lane;
+      const float dx0 = rstd * (gy[k].x - s1 - x[k].x * s2), dx1 = rstd * (gy[k].y - s1 - x[k].y * s2);
+      const float dx2 = rstd * (gy[k].z - s1 - x[k].z * s2), dx3 = rstd * (gy[k].w - s1 - x[k].w * s2);
+      if (d_word) red_add_v4(d_word + static_cast<size_t>(id) * a.E + v * 4, dx0, dx1, dx2, dx3);
+      if (d_pos) red_add_v4(d_pos + static_cast<size_t>(pid) * a.E + v * 4, dx0, dx1, dx2, dx3);
+      if (d_type) red_add_v4(d_type + static_cast<size_t>(tt) * a.E + v * 4, dx0, dx1, dx2, dx3);
+      if (d_item) red_add_v4(d_item + static_cast<size_t>(ip) * a.E + v * 4, dx0, dx1, dx2, dx3);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NV4; ++k) {
+    const int v = k * 32 + lane;
+    if (d_gamma) red_add_v4(d_gamma + v * 4, dg[k].x, dg[k].y, dg[k].z, dg[k].w);
+    if (d_beta) red_add_v4(d_beta + v * 4, db[k].x, db[k].y, db[k].z, db[k].w);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// LayerNorm on bf16 rows.  NV8 = E / 256 uint4 (8 x bf16) per lane.
+// ----------------------------------------------------------------------------------------------
+template <int NV8>
+__global__ void __launch_bounds__(ROW_THREADS)
+layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ stats, int T,
+                     float eps) {
+  constexpr int E = NV8 * 256;
+  const int lane = threadIdx.x & 31;
+  for (int t = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); t < T; t += gridDim.x * (ROW_THREADS / 32)) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * E);
+    float v[NV8][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV8; ++k) {
+      const uint4 raw = xr[k * 32 + lane];
+      const float2 a0 = unpack_bf16(raw.x), a1 = unpack_bf16(raw.y), a2 = unpack_bf16(raw.z), a3 = unpack_bf16(raw.w);
+      v[k][0] = a0.x; v[k][1] = a0.y; v[k][2] = a1.x; v[k][3] = a1.y;
+      v[k][4] = a2.x; v[k][5] = a2.y; v[k][6] = a3.x; v[k][7] = a3.y;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[k][e];
+    }
+    const float mean = warp_sum(s) / E;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV8; ++k)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = v[k][e] - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) / E + eps);
+    if (lane == 0 && stats) { stats[2 * t] = mean; stats[2 * t + 1] = rstd; }
+    uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(t) * E);
+#pragma unroll
+    for (int k = 0; k < NV8; ++k) {
+      const int c = (k * 32 + lane) * 8;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+      uint4 o;
+      o.x = pack_bf16((v[k][0] - mean) * rstd * g0.x + b0.x, (v[k][1] - mean) * rstd * g0.y + b0.y);
+      o.y = pack_bf16((v[k][2] - mean) * rstd * g0.z + b0.z, (v[k][3] - mean) * rstd * g0.w + b0.w);
+      o.z = pack_bf16((v[k][4] - mean) * rstd * g1.x + b1.x, (v[k][5] - mean) * rstd * g1.y + b1.y);
+      o.w = pack_bf16((v[k][6] - mean) * rstd * g1.z + b1.z, (v[k][7] - mean) * rstd * g1.w + b1.w);
+      yr[k * 32 + lane] = o;
+    }
+  }
+}
+
+template <int NV8>
+__global__ void __launch_bounds__(ROW_THREADS)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                     const float* __restrict__ stats, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
+                     __nv_bfloat16* __restrict__ dx_dropped, float drop_scale, uint32_t drop_thresh,
+                     uint64_t drop_seed, float* d_gamma, float* d_beta, int T) {
+  constexpr int E = NV8 * 256;
+  const int lane = threadIdx.x & 31;
+  float dg[NV8][8], db[NV8][8];
+#pragma unroll
+  for (int k = 0; k < NV8; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dg[k][e] = db[k][e] = 0.f;
+  for (int t = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); t < T; t += gridDim.x * (ROW_THREADS / 32)) {
+    const float mean = stats[2 * t], rstd = stats[2 * t + 1];
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * E);
+    const uint4* dr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(t) * E);
+    float xh[NV8][8], gy[NV8][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV8; ++k) {
+      const int c = (k * 32 + lane) * 8;
+      const uint4 xraw = xr[k * 32 + lane], draw = dr[k * 32 + lane];
+      const float2 a0 = unpack_bf16(xraw.x), a1 = unpack_bf16(xraw.y), a2 = unpack_bf16(xraw.z), a3 = unpack_bf16(xraw.w);
+      const float2 d0 = unpack_bf16(draw.x), d1 = unpack_bf16(draw.y), d2 = unpack_bf16(draw.z), d3 = unpack_bf16(draw.w);
+      const float xv[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+      const float dv[8] = {d0.x, d0.y, d1.x, d1.y, d2.x, d2.y, d3.x, d3.y};
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        xh[k][e] = (xv[e] - mean) * rstd;
+        dg[k][e] += dv[e] * xh[k][e];
+        db[k][e] += dv[e];
+        gy[k][e] = dv[e] * gv[e];
+        s1 += gy[k][e];
+        s2 += gy[k][e] * xh[k][e];
+      }
+    }
+    s1 = warp_sum(s1) / E;
+    s2 = warp_sum(s2) / E;
+    uint4* oxr = reinterpret_cast<uint4*>(dx + static_cast<size_t>(t) * E);
+#pragma unroll
+    for (int k = 0; k < NV8; ++k) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = rstd * (gy[k][e] - s1 - xh[k][e] * s2);
+      uint4 ov;
+      ov.x = pack_bf16(o[0], o[1]); ov.y = pack_bf16(o[2], o[3]); ov.z = pack_bf16(o[4], o[5]); ov.w = pack_bf16(o[6], o[7]);
+      oxr[k * 32 + lane] = ov;
+      if (dx_dropped != nullptr) {
+        const uint64_t grp = (static_cast<uint64_t>(t) * E + (k * 32 + lane) * 8) >> 3;
+        const uint32_t keep = drop_thresh ? dropout_keep8(drop_seed, grp, drop_thresh) : 0xFFu;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = ((keep >> e) & 1u) ? o[e] * drop_scale : 0.f;
+        ov.x = pack_bf16(o[0], o[1]); ov.y = pack_bf16(o[2], o[3]); ov.z = pack_bf16(o[4], o[5]); ov.w = pack_bf16(o[6], o[7]);
+        reinterpret_cast<uint4*>(dx_dropped + static_cast<size_t>(t) * E)[k * 32 + lane] = ov;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NV8; ++k) {
+    const int c = (k * 32 + lane) * 8;
+    if (d_gamma) {
+      red_add_v4(d_gamma + c, dg[k][0], dg[k][1], dg[k][2], dg[k][3]);
+      red_add_v4(d_gamma + c + 4, dg[k][4], dg[k][5], dg[k][6], dg[k][7]);
+    }
+    if (d_beta) {
+      red_add_v4(d_beta + c, db[k][0], db[k][1], db[k][2], db[k][3]);
+      red_add_v4(d_beta + c + 4, db[k][4], db[k][5], db[k][6], db[k][7]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// column sums of a bf16 [T,N] matrix (bias gradients): out[n] += sum_t x[t,n]
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* out, int T, int N,
+                                                          int ld, int rows_per_cta) {
+  // thread handles 8 consecutive columns; CTA covers 2048 columns-slab x rows_per_cta rows
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (c >= N) return;
+  const int t0 = blockIdx.y * rows_per_cta;
+  const int t1 = min(T, t0 + rows_per_cta);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int t = t0; t < t1; ++t) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * ld + c);
+    const float2 a0 = unpack_bf16(raw.x), a1 = unpack_bf16(raw.y), a2 = unpack_bf16(raw.z), a3 = unpack_bf16(raw.w);
+    acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y;
+    acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
+  }
+  red_add_v4(out + c, acc[0], acc[1], acc[2], acc[3]);
+  red_add_v4(out + c + 4, acc[4], acc[5], acc[6], acc[7]);
+}
+
+// ----------------------------------------------------------------------------------------------
+// cast + AdamW on the flat parameter buffer
+// ----------------------------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ y, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    y[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+__global__ void adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                             float4* __restrict__ v, uint2* __restrict__ shadow, long long n4, float lr, float b1,
+                             float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+    float* pa = reinterpret_cast<float*>(&pp); float* ga = reinterpret_cast<float*>(&gg);
+    float* ma = reinterpret_cast<float*>(&mm); float* va = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gr = ga[e] * gscale;
+      pa[e] *= (1.f - lr * wd);                      // decoupled weight decay (torch.optim.AdamW)
+      ma[e] = b1 * ma[e] + (1.f - b1) * gr;
+      va[e] = b2 * va[e] + (1.f - b2) * gr * gr;
+      const float denom = sqrtf(va[e]) / bc2_sqrt + eps;
+      pa[e] -= (lr / bc1) * (ma[e] / denom);
+    }
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    if (shadow) shadow[i] = make_uint2(pack_bf16(pa[0], pa[1]), pack_bf16(pa[2], pa[3]));
+  }
+}
+
+static EmbedDev make_embed_dev(const rf_embed_args* a) {
+  EmbedDev d;
+  d.ids = a->input_ids; d.tt = a->token_type_ids; d.ip = a->item_position_ids; d.pos = a->pos_ids;
+  d.word = a->word_emb; d.posw = a->pos_emb; d.type = a->type_emb; d.item = a->item_emb;
+  d.gamma = a->ln_gamma; d.beta = a->ln_beta;
+  d.B = a->B; d.L = a->L; d.Lp = a->Lp; d.E = a->E; d.vocab = a->vocab; d.max_pos = a->max_pos;
+  d.type_size = a->type_size; d.max_item = a->max_item; d.pad = a->padding_idx; d.eps = a->eps;
+  d.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
+  d.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
+  d.drop_seed = a->drop_seed;
+  return d;
+}
+
+static int row_grid(int T) {
+  const int need = (T + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32);
+  const int cap = sm_count() * 8;
+  return need < cap ? (need > 0 ? need : 1) : cap;
+}
+
+}  // namespace rf
+
+using namespace rf;
+
+extern "C" int rf_prepare_inputs(const int64_t* input_ids, const int64_t* attention_mask,
+                                 const int64_t* global_attention_mask, int B, int L, int Lp, int padding_idx,
+                                 int32_t* pos_ids, uint8_t* mask012, int* err_flag, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(input_ids && pos_ids && mask012 && err_flag, "rf_prepare_inputs: null argument");
+  RF_REQUIRE(B > 0 && L > 0 && Lp >= L, "rf_prepare_inputs: bad shape B=%d L=%d Lp=%d", B, L, Lp);
+  const int warps = 4;
+  prepare_inputs_kernel<<<(B + warps - 1) / warps, warps * 32, 0, stream>>>(input_ids, attention_mask,
+                                                                          global_attention_mask, B, L, Lp, padding_idx,
+                                                                          pos_ids, mask012, err_flag);
+  return check_launch("rf_prepare_inputs");
+}
+
+extern "C" int rf_embed_ln_fwd(const rf_embed_args* a, void* out, int* err_flag, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(a && out, "rf_embed_ln_fwd: null argument");
+  RF_REQUIRE(a->E == 768, "rf_embed_ln_fwd: hidden size %d unsupported (768)", a->E);
+  RF_REQUIRE(a->B > 0 && a->L > 0 && a->Lp >= a->L, "rf_embed_ln_fwd: bad shape");
+  const EmbedDev d = make_embed_dev(a);
+  embed_ln_fwd_kernel<6><<<row_grid(a->B * a->Lp), ROW_THREADS, 0, stream>>>(d, reinterpret_cast<__nv_bfloat16*>(out),
+                                                                           err_flag);
+  return check_launch("rf_embed_ln_fwd");
+}
+
+extern "C" int rf_embed_ln_bwd(const rf_embed_args* a, const void* dout, float* d_word, float* d_pos, float* d_type,
+                               float* d_item, float* d_gamma, float* d_beta, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(a && dout, "rf_embed_ln_bwd: null argument");
+  RF_REQUIRE(a->E == 768, "rf_embed_ln_bwd: hidden size %d unsupported (768)", a->E);
+  const EmbedDev d = make_embed_dev(a);
+  const int grid = min(row_grid(a->B * a->Lp), sm_count() * 2);
+  embed_ln_bwd_kernel<6><<<grid, ROW_THREADS, 0, stream>>>(d, reinterpret_cast<const __nv_bfloat16*>(dout), d_word,
+                                                          d_pos, d_type, d_item, d_gamma, d_beta);
+  return check_launch("rf_embed_ln_bwd");
+}
+
+extern "C" int rf_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats, int T,
+                                int E, float eps, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(x && gamma && beta && y, "rf_layernorm_fwd: null argument");
+  RF_REQUIRE(E == 768, "rf_layernorm_fwd: hidden size %d unsupported (768)", E);
+  RF_REQUIRE(T > 0, "rf_layernorm_fwd: T=%d", T);
+  layernorm_fwd_kernel<3><<<row_grid(T), ROW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma,
+                                                                  beta, reinterpret_cast<__nv_bfloat16*>(y), stats, T,
+                                                                  eps);
+  return check_launch("rf_layernorm_fwd");
+}
+
+extern "C" int rf_layernorm_bwd(const void* dy, const void* x, const float* stats, const float* gamma, void* dx,
+                                void* dx_dropped, float drop_p, uint64_t drop_seed, float* d_gamma, float* d_beta,
+                                int T, int E, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(dy && x && stats && gamma && dx, "rf_layernorm_bwd: null argument");
+  RF_REQUIRE(E == 768, "rf_layernorm_bwd: hidden size %d unsupported (768)", E);
+  const uint32_t thresh = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 65536.0f) : 0u;
+  const float scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  const int grid = min(row_grid(T), sm_count() * 2);
+  layernorm_bwd_kernel<3><<<grid, ROW_THREADS, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), stats, gamma,
+      reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(dx_dropped), scale, thresh, drop_seed,
+      d_gamma, d_beta, T);
+  return check_launch("rf_layernorm_bwd");
+}
+
+extern "C" int rf_colsum_bf16(const void* x, float* out, int T, int N, int ld, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(x && out && T > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0, "rf_colsum_bf16: bad argument");
+  const int gx = (N / 8 + 255) / 256;
+  int gy = (sm_count() * 4) / gx;
+  if (gy < 1) gy = 1;
+  if (gy > T) gy = T;
+  const int rows = (T + gy - 1) / gy;
+  gy = (T + rows - 1) / rows;
+  colsum_bf16_kernel<<<dim3(gx, gy), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, T, N, ld, rows);
+  return check_launch("rf_colsum_bf16");
+}
+
+extern "C" int rf_cast_f32_to_bf16(const float* x, void* y, long long n, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(x && y && n > 0 && n % 4 == 0, "rf_cast_f32_to_bf16: n=%lld must be a positive multiple of 4", n);
+  const long long n4 = n / 4;
+  long long grid = (n4 + 255) / 256;
+  if (grid > sm_count() * 16) grid = sm_count() * 16;
+  cast_f32_bf16_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(reinterpret_cast<const float4*>(x),
+                                                                  reinterpret_cast<uint2*>(y), n4);
+  return check_launch("rf_cast_f32_to_bf16");
+}
+
+extern "C" int rf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow,
+                             long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                             float grad_scale, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && n % 4 == 0 && step >= 1, "rf_adamw_step: bad argument");
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  const long long n4 = n / 4;
+  long long grid = (n4 + 255) / 256;
+  if (grid > sm_count() * 16) grid = sm_count() * 16;
+  adamw_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(
+      reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad), reinterpret_cast<float4*>(exp_avg),
+      reinterpret_cast<float4*>(exp_avg_sq), reinterpret_cast<uint2*>(shadow), n4, lr, beta1, beta2, eps, weight_decay,
+      bc1, sqrtf(bc2), grad_scale);
+  return check_launch("rf_adamw_step");
+}

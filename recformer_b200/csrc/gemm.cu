@@ -1,0 +1,377 @@
+// Persistent warp-specialised bf16 GEMM on tcgen05 tensor cores for sm_100a.
+//
+//   C[M,N] = epilogue( A (*) B ),  fp32 accumulation in TMEM.
+//
+// One CTA per SM loops over 128 x BN output tiles (x split-K slices).  Roles:
+//   warp 0      TMA producer: streams 128x64 A and BNx64 B slabs (128B swizzle) through a
+//               STAGES-deep shared-memory ring, mbarrier complete_tx signalling;
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases ring
+//               slots and publishes finished accumulators;
+//   warps 2..5  epilogue: tcgen05.ld the accumulator (double-buffered in TMEM so the next
+//               tile's MMAs overlap), apply bias / scale / GELU / GELU' / dropout / residual,
+//               store bf16 or fp32 (plain, += or red.add for split-K).
+// Operand layouts (template): K-major (row = M/N index, K contiguous: activations and
+// nn.Linear weights) or MN-major (row = K index: used by dgrad for W and by wgrad for both
+// operands, so no transposed copies of weights or activations are ever materialised).
+#include <cuda_bf16.h>
+
+#include "rf_common.h"
+#include "rf_ptx.cuh"
+
+namespace rf {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+  void* C;
+  void* C2;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  const __nv_bfloat16* aux;
+  int M, N, K;
+  int ldc, ldr, ldaux;
+  int accumulate;
+  int split_k;
+  float scale;
+  int scale_ncols;
+  float drop_scale;       // 1/(1-p)
+  uint32_t drop_thresh;   // p * 65536, 0 = no dropout
+  uint64_t drop_seed;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t TILE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr uint32_t BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr uint32_t TOTAL = TILE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu_erf(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using S = GemmSmem<BN>;
+  constexpr int STAGES = S::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int k_blocks_total = (p.K + BK - 1) / BK;
+  const int k_per_split = (k_blocks_total + p.split_k - 1) / p.split_k;
+  const int total_tiles = m_tiles * n_tiles * p.split_k;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile % m_tiles;
+        const int rest = tile / m_tiles;
+        const int nt = rest % n_tiles;
+        const int sp = rest / n_tiles;
+        const int m0 = mt * BM, n0 = nt * BN;
+        const int kb0 = sp * k_per_split;
+        const int kb1 = min(kb0 + k_per_split, k_blocks_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);            // box (64 k, 128 rows)
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c)                                   // box (64 m, 64 k-rows)
+              tma_load_2d(sa + c * 8192, &tmA, &full_bar[stage], m0 + c * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);            // box (64 k, BN rows)
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sb + c * 8192, &tmB, &full_bar[stage], n0 + c * 64, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int sp = (tile / m_tiles) / n_tiles;
+      const int kb0 = sp * k_per_split;
+      const int kb1 = min(kb0 + k_per_split, k_blocks_total);
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? umma_smem_desc(sa + k * 2048, 8192, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_smem_desc(sb + k * 2048, 8192, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                 // slot reusable once these MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (kb1 <= kb0 && lane == 0) umma_commit(&tfull_bar[acc]);  // empty K slice (never for sane shapes)
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile % m_tiles;
+      const int rest = tile / m_tiles;
+      const int nt = rest % n_tiles;
+      const int m0 = mt * BM, n0 = nt * BN;
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col0 + j);
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        }
+        if (col0 < p.scale_ncols) {  // scale_ncols is a multiple of 32
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= p.scale;
+        }
+        if (row_ok) {
+          const size_t off = static_cast<size_t>(row) * p.ldc + col0;
+          if (EPI == RF_EPI_GELU) {
+            __nv_bfloat16* c1 = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
+            __nv_bfloat16* c2 = reinterpret_cast<__nv_bfloat16*>(p.C2) + off;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u, g;
+              u.x = pack_bf16(v[j], v[j + 1]); u.y = pack_bf16(v[j + 2], v[j + 3]);
+              u.z = pack_bf16(v[j + 4], v[j + 5]); u.w = pack_bf16(v[j + 6], v[j + 7]);
+              // activation of the bf16-rounded pre-activation, so that backward (which only
+              // sees the stored bf16 u) differentiates exactly the function forward applied
+              float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
+              g.x = pack_bf16(gelu_erf(a0.x), gelu_erf(a0.y)); g.y = pack_bf16(gelu_erf(a1.x), gelu_erf(a1.y));
+              g.z = pack_bf16(gelu_erf(a2.x), gelu_erf(a2.y)); g.w = pack_bf16(gelu_erf(a3.x), gelu_erf(a3.y));
+              *reinterpret_cast<uint4*>(c1 + j) = u;
+              *reinterpret_cast<uint4*>(c2 + j) = g;
+            }
+          } else {
+            if (EPI == RF_EPI_DGELU) {
+              const __nv_bfloat16* ax = p.aux + static_cast<size_t>(row) * p.ldaux + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 a = *reinterpret_cast<const uint4*>(ax + j);
+                float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+                v[j] *= dgelu_erf(a0.x); v[j + 1] *= dgelu_erf(a0.y); v[j + 2] *= dgelu_erf(a1.x);
+                v[j + 3] *= dgelu_erf(a1.y); v[j + 4] *= dgelu_erf(a2.x); v[j + 5] *= dgelu_erf(a2.y);
+                v[j + 6] *= dgelu_erf(a3.x); v[j + 7] *= dgelu_erf(a3.y);
+              }
+            }
+            if (p.drop_thresh != 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint64_t grp = (static_cast<uint64_t>(row) * p.N + col0 + j) >> 3;
+                const uint32_t keep = dropout_keep8(p.drop_seed, grp, p.drop_thresh);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[j + e] = ((keep >> e) & 1u) ? v[j + e] * p.drop_scale : 0.0f;
+              }
+            }
+            if (p.residual != nullptr) {
+              const __nv_bfloat16* rs = p.residual + static_cast<size_t>(row) * p.ldr + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 a = *reinterpret_cast<const uint4*>(rs + j);
+                float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+                v[j] += a0.x; v[j + 1] += a0.y; v[j + 2] += a1.x; v[j + 3] += a1.y;
+                v[j + 4] += a2.x; v[j + 5] += a2.y; v[j + 6] += a3.x; v[j + 7] += a3.y;
+              }
+            }
+            if (OUT_F32) {
+              float* cf = reinterpret_cast<float*>(p.C) + off;
+              if (p.split_k > 1) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cf + j), "f"(v[j]), "f"(v[j + 1]),
+                               "f"(v[j + 2]), "f"(v[j + 3])
+                               : "memory");
+              } else if (p.accumulate) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 o = *reinterpret_cast<float4*>(cf + j);
+                  o.x += v[j]; o.y += v[j + 1]; o.z += v[j + 2]; o.w += v[j + 3];
+                  *reinterpret_cast<float4*>(cf + j) = o;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(cf + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              }
+            } else {
+              __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 o;
+                o.x = pack_bf16(v[j], v[j + 1]); o.y = pack_bf16(v[j + 2], v[j + 3]);
+                o.z = pack_bf16(v[j + 4], v[j + 5]); o.w = pack_bf16(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(cb + j) = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32>
+static int launch_gemm(const rf_gemm_args* a, cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, OUT_F32>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  const CUtensorMap* tmA = A_MN ? get_tmap_2d(a->A, a->K, a->M, a->lda, 64) : get_tmap_2d(a->A, a->M, a->K, a->lda, BM);
+  if (!tmA) return RF_ERR_CUDA;
+  const CUtensorMap* tmB = B_MN ? get_tmap_2d(a->B, a->K, a->N, a->ldb, 64) : get_tmap_2d(a->B, a->N, a->K, a->ldb, BN);
+  if (!tmB) return RF_ERR_CUDA;
+  GemmParams p;
+  p.C = a->C; p.C2 = a->C2; p.bias = a->bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+  p.aux = reinterpret_cast<const __nv_bfloat16*>(a->aux);
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.ldc = a->ldc; p.ldr = a->ldr; p.ldaux = a->ldaux;
+  p.accumulate = a->accumulate;
+  p.split_k = a->split_k > 1 ? a->split_k : 1;
+  p.scale = a->scale; p.scale_ncols = a->scale_ncols;
+  p.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
+  p.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
+  p.drop_seed = a->drop_seed;
+  const int m_tiles = (a->M + BM - 1) / BM, n_tiles = (a->N + BN - 1) / BN;
+  const int total = m_tiles * n_tiles * p.split_k;
+  const int grid = total < sm_count() ? total : sm_count();
+  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(*tmA, *tmB, p);
+  return check_launch("rf_gemm_bf16");
+}
+
+}  // namespace rf
+
+extern "C" int rf_gemm_bf16(const rf_gemm_args* a, rf_stream_t stream_) {
+  using namespace rf;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(a != nullptr, "rf_gemm_bf16: null args");
+  RF_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "rf_gemm_bf16: empty problem M=%d N=%d K=%d", a->M, a->N, a->K);
+  RF_REQUIRE(a->N % 32 == 0, "rf_gemm_bf16: N=%d must be a multiple of 32", a->N);
+  RF_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "rf_gemm_bf16: lda/ldb must be multiples of 8 (TMA 16B strides)");
+  RF_REQUIRE(a->ldc % 8 == 0, "rf_gemm_bf16: ldc must be a multiple of 8");
+  RF_REQUIRE((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(a->C) & 15) == 0,
+             "rf_gemm_bf16: A/B/C must be 16-byte aligned");
+  RF_REQUIRE(a->scale_ncols % 32 == 0, "rf_gemm_bf16: scale_ncols must be a multiple of 32");
+  RF_REQUIRE(a->split_k <= 1 || a->out_f32, "rf_gemm_bf16: split_k needs fp32 output");
+  RF_REQUIRE(a->epi != RF_EPI_GELU || (a->C2 != nullptr && !a->out_f32), "rf_gemm_bf16: GELU epilogue needs C2, bf16");
+  RF_REQUIRE(a->epi != RF_EPI_DGELU || a->aux != nullptr, "rf_gemm_bf16: DGELU epilogue needs aux");
+  const int layout = (a->a_mn_major ? 2 : 0) | (a->b_mn_major ? 1 : 0);
+  // Tile width: 256 for the big projections; 128 where that fills the machine better.
+  if (layout == 0) {
+    if (a->epi == RF_EPI_GELU) return launch_gemm<256, false, false, RF_EPI_GELU, false>(a, stream);
+    RF_REQUIRE(a->epi == RF_EPI_NONE, "rf_gemm_bf16: epilogue %d unsupported for K-major x K-major", a->epi);
+    if (a->out_f32) return launch_gemm<128, false, false, RF_EPI_NONE, true>(a, stream);
+    return launch_gemm<256, false, false, RF_EPI_NONE, false>(a, stream);
+  }
+  if (layout == 1) {  // dgrad: dY[M,K] (K-major) x W stored [K,N]
+    RF_REQUIRE(!a->out_f32, "rf_gemm_bf16: fp32 output unsupported for the dgrad layout");
+    if (a->epi == RF_EPI_DGELU) return launch_gemm<256, false, true, RF_EPI_DGELU, false>(a, stream);
+    RF_REQUIRE(a->epi == RF_EPI_NONE, "rf_gemm_bf16: epilogue %d unsupported for the dgrad layout", a->epi);
+    return launch_gemm<256, false, true, RF_EPI_NONE, false>(a, stream);
+  }
+  if (layout == 3) {  // wgrad: dY^T x X, both stored [K, *]
+    RF_REQUIRE(a->out_f32 && a->epi == RF_EPI_NONE, "rf_gemm_bf16: the wgrad layout writes fp32 without epilogue");
+    return launch_gemm<128, true, true, RF_EPI_NONE, true>(a, stream);
+  }
+  return set_error(RF_ERR_INVALID, "rf_gemm_bf16: layout a_mn_major=1,b_mn_major=0 is not instantiated");
+}

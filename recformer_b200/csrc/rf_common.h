@@ -1,0 +1,39 @@
+// Host-side helpers shared by the translation units of librecformer_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/recformer_b200.h"
+
+namespace rf {
+
+// Error channel of the C ABI: every entry point returns 0 or a negative code and leaves a
+// human-readable message retrievable with rf_last_error() (thread local).
+int set_error(int code, const char* fmt, ...);
+int check_launch(const char* what);  // cudaGetLastError() -> rf error
+
+#define RF_REQUIRE(cond, ...)                                  \
+  do {                                                         \
+    if (!(cond)) return ::rf::set_error(RF_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define RF_CUDA(call)                                                                        \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return ::rf::set_error(RF_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));  \
+  } while (0)
+
+// bf16 2-D row-major tensor map with 128B swizzle; box = (64 elements, box_rows).  Cached per
+// (ptr, shape, box).  Returns nullptr on failure (error already set).
+const CUtensorMap* get_tmap_2d(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
+                               uint32_t box_cols = 64);
+// bf16 3-D (batch, rows, cols) map: box = (64 cols, box_rows rows, 1 batch); out-of-range rows
+// (negative or >= rows) are zero-filled, which the band kernels rely on at sequence edges.
+const CUtensorMap* get_tmap_3d(const void* ptr, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                               uint64_t batch_stride_elems, uint32_t box_rows);
+
+int sm_count();
+
+}  // namespace rf

@@ -1,0 +1,495 @@
+// Full-catalogue cosine scoring (SURVEY.md §8a Spec S; ref: recformer/models.py:358-369,539-545):
+//   logit[b,n] = (x_b / |x_b|) . (y_n / |y_n|) / temp
+// as a bf16 tcgen05 GEMM over a pre-normalised item table with fused epilogues:
+//   TOPK : temperature scaling + streaming per-thread top-k (one thread = one user row of the
+//          128-row tile), logits never written; label score picked out of the same accumulator
+//          so that Spec R's strict `>` rank count is exact;
+//   DENSE: fp32 logits [B,N] (the (B,N) score tensor RecformerForSeqRec.forward returns, and the
+//          training cross-entropy input, ref: recformer/models.py:583-591).
+// Scheduling: CTA = (user m-tile, item slice s); slice s sweeps item tiles s, s+S, ... so all
+// m-tiles advance through the table in lock-step and each 256-item tile is fetched from HBM once
+// and re-read from L2 by the other m-tiles.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "rf_common.h"
+#include "rf_ptx.cuh"
+
+namespace rf {
+
+constexpr int SC_BM = 128, SC_BN = 256, SC_BK = 64, SC_STAGES = 4, SC_THREADS = 192;
+constexpr int SC_MAXK = 16;
+constexpr uint32_t SC_A_BYTES = SC_BM * SC_BK * 2, SC_B_BYTES = SC_BN * SC_BK * 2;
+constexpr uint32_t SC_STAGE_BYTES = SC_A_BYTES + SC_B_BYTES;
+constexpr uint32_t SC_SMEM = SC_STAGES * SC_STAGE_BYTES + (2 * SC_STAGES + 4) * 8 + 16 + 1024;
+
+struct ScoreParams {
+  int B; long long N; int K;      // users, items, hidden
+  float inv_temp;
+  int k;                          // top-k
+  int id_base;
+  int slices;                     // S
+  const int64_t* labels;
+  float* ws_scores;               // [S][B][k]
+  int32_t* ws_ids;                // [S][B][k]
+  float* ws_label;                // [S][B]
+  float* logits;                  // DENSE: [B][N]
+};
+
+enum { SC_TOPK = 0, SC_DENSE = 1 };
+
+template <int MODE>
+__global__ void __launch_bounds__(SC_THREADS, 1)
+cosine_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const ScoreParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SC_STAGES * SC_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + SC_STAGES;
+  uint64_t* tfull_bar = empty_bar + SC_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x / p.slices;
+  const int slice = blockIdx.x % p.slices;
+  const int m0 = mt * SC_BM;
+  const int n_tiles = static_cast<int>((p.N + SC_BN - 1) / SC_BN);
+  const int k_blocks = (p.K + SC_BK - 1) / SC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 2 * SC_BN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0; uint32_t phase = 0;
+      for (int nt = slice; nt < n_tiles; nt += p.slices) {
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], SC_STAGE_BYTES);
+          uint8_t* sa = smem + stage * SC_STAGE_BYTES;
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * SC_BK, m0);
+          tma_load_2d(sa + SC_A_BYTES, &tmB, &full_bar[stage], kb * SC_BK, nt * SC_BN);
+          if (++stage == SC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(SC_BM, SC_BN, false, false);
+    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+    for (int nt = slice; nt < n_tiles; nt += p.slices) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * SC_STAGE_BYTES), sb = sa + SC_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < SC_BK / 16; ++k)
+            umma_bf16(tmem_base + acc * SC_BN, umma_smem_desc(sa + k * 32, 16, 1024),
+                      umma_smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == SC_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = m0 + quad * 32 + lane;
+    const bool row_ok = row < p.B;
+    float ts[SC_MAXK]; int ti[SC_MAXK];
+#pragma unroll
+    for (int i = 0; i < SC_MAXK; ++i) { ts[i] = -INFINITY; ti[i] = 0x7fffffff; }
+    float thr = -INFINITY;   // current k-th best
+    float label_score = -INFINITY;
+    long long label_local = -1;
+    if (MODE == SC_TOPK && p.labels != nullptr && row_ok) label_local = p.labels[row] - p.id_base;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int nt = slice; nt < n_tiles; nt += p.slices) {
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const long long n0 = static_cast<long long>(nt) * SC_BN;
+#pragma unroll 1
+      for (int c = 0; c < SC_BN / 32; ++c) {
+        const long long col0 = n0 + c * 32;
+        if (col0 >= p.N) break;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * SC_BN + c * 32, r);
+        tmem_ld_wait();
+        if (MODE == SC_DENSE) {
+          if (row_ok) {
+            float* out = p.logits + static_cast<size_t>(row) * p.N + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) out[j] = __uint_as_float(r[j]) * p.inv_temp;
+          }
+        } else {
+          const int nvalid = (p.N - col0) < 32 ? static_cast<int>(p.N - col0) : 32;
+          const long long rel = label_local - col0;
+          if (rel >= 0 && rel < nvalid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j == rel) label_score = __uint_as_float(r[j]) * p.inv_temp;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float s = __uint_as_float(r[j]) * p.inv_temp;
+            if (s > thr && j < nvalid) {
+              // insert (s, id) into the descending list; strict '>' keeps the lower id on ties
+              const int id = p.id_base + static_cast<int>(col0) + j;
+              float cs = s; int ci = id;
+#pragma unroll
+              for (int q = 0; q < SC_MAXK; ++q) {
+                if (q < p.k) {
+                  const bool sw = cs > ts[q];
+                  const float t_s = ts[q]; const int t_i = ti[q];
+                  ts[q] = sw ? cs : t_s; ti[q] = sw ? ci : t_i;
+                  cs = sw ? t_s : cs; ci = sw ? t_i : ci;
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < SC_MAXK; ++q) if (q == p.k - 1) thr = ts[q];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (MODE == SC_TOPK && row_ok) {
+      float* os = p.ws_scores + (static_cast<size_t>(slice) * p.B + row) * p.k;
+      int32_t* oi = p.ws_ids + (static_cast<size_t>(slice) * p.B + row) * p.k;
+#pragma unroll
+      for (int q = 0; q < SC_MAXK; ++q)
+        if (q < p.k) { os[q] = ts[q]; oi[q] = ti[q]; }
+      p.ws_label[static_cast<size_t>(slice) * p.B + row] = label_score;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * SC_BN); }
+}
+
+// Merge `parts` sorted lists of k (score, id) per user -> global top-k (score desc, id asc).
+__global__ void topk_merge_kernel(const float* __restrict__ scores, const int32_t* __restrict__ ids,
+                                  const float* __restrict__ label_scores, int parts, int B, int k,
+                                  float* __restrict__ out_scores, int32_t* __restrict__ out_ids,
+                                  float* __restrict__ out_label) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float ts[SC_MAXK]; int ti[SC_MAXK];
+#pragma unroll
+  for (int i = 0; i < SC_MAXK; ++i) { ts[i] = -INFINITY; ti[i] = 0x7fffffff; }
+  float lab = -INFINITY;
+  for (int s = 0; s < parts; ++s) {
+    const float* ps = scores + (static_cast<size_t>(s) * B + b) * k;
+    const int32_t* pi = ids + (static_cast<size_t>(s) * B + b) * k;
+    if (label_scores) lab = fmaxf(lab, label_scores[static_cast<size_t>(s) * B + b]);
+    for (int q0 = 0; q0 < k; ++q0) {
+      float cs = ps[q0]; int ci = pi[q0];
+      if (cs == -INFINITY) break;
+#pragma unroll
+      for (int q = 0; q < SC_MAXK; ++q) {
+        if (q < k) {
+          const bool sw = (cs > ts[q]) || (cs == ts[q] && ci < ti[q]);
+          const float t_s = ts[q]; const int t_i = ti[q];
+          ts[q] = sw ? cs : t_s; ti[q] = sw ? ci : t_i;
+          cs = sw ? t_s : cs; ci = sw ? t_i : ci;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < SC_MAXK; ++q)
+    if (q < k) { out_scores[static_cast<size_t>(b) * k + q] = ts[q]; out_ids[static_cast<size_t>(b) * k + q] = ti[q]; }
+  if (out_label) out_label[b] = lab;
+}
+
+// y[n,:] = x[n,:] / max(|x[n,:]|, 1e-8) as bf16; one warp per row (E = 768).
+template <bool IN_BF16>
+__global__ void __launch_bounds__(256)
+normalize_rows_kernel(const void* __restrict__ x_, __nv_bfloat16* __restrict__ y, float* __restrict__ norms,
+                      long long N) {
+  constexpr int E = 768;
+  const int lane = threadIdx.x & 31;
+  for (long long n = blockIdx.x * 8ll + (threadIdx.x >> 5); n < N; n += gridDim.x * 8ll) {
+    float v[24];
+    if (IN_BF16) {
+      const uint2* xr = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x_) + n * E);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const uint2 raw = xr[k * 32 + lane];
+        const float2 a = unpack_bf16(raw.x), b = unpack_bf16(raw.y);
+        v[k * 4] = a.x; v[k * 4 + 1] = a.y; v[k * 4 + 2] = b.x; v[k * 4 + 3] = b.y;
+      }
+    } else {
+      const float4* xr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x_) + n * E);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const float4 a = xr[k * 32 + lane];
+        v[k * 4] = a.x; v[k * 4 + 1] = a.y; v[k * 4 + 2] = a.z; v[k * 4 + 3] = a.w;
+      }
+    }
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) q += v[i] * v[i];
+    const float nrm = sqrtf(warp_sum(q));
+    const float inv = 1.0f / fmaxf(nrm, 1e-8f);
+    if (norms && lane == 0) norms[n] = nrm;
+    uint2* yr = reinterpret_cast<uint2*>(y + n * E);
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      yr[k * 32 + lane] = make_uint2(pack_bf16(v[k * 4] * inv, v[k * 4 + 1] * inv),
+                                     pack_bf16(v[k * 4 + 2] * inv, v[k * 4 + 3] * inv));
+  }
+}
+
+// ---- cross entropy over dense logits + gradient w.r.t. the (un-normalised) pooled vector ----
+// ce_row_kernel: grid (B): loss_b, and dlogits (in place) = (softmax - onehot) / B
+__global__ void __launch_bounds__(256)
+ce_row_kernel(float* __restrict__ logits, const int64_t* __restrict__ labels, int B, long long N,
+              float* __restrict__ loss) {
+  const int b = blockIdx.x;
+  float* row = logits + static_cast<size_t>(b) * N;
+  __shared__ float red[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float m = -INFINITY;
+  for (long long n = tid; n < N; n += 256) m = fmaxf(m, row[n]);
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float l = 0.f;
+  for (long long n = tid; n < N; n += 256) l += expf(row[n] - m);
+  l = warp_sum(l);
+  if (lane == 0) red[warp] = l;
+  __syncthreads();
+  l = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) l += red[w];
+  const long long lab = labels[b];
+  const float lse = m + logf(l);
+  if (tid == 0) atomicAdd(loss, (lse - row[lab]) / B);
+  __syncthreads();
+  const float invB = 1.0f / B;
+  for (long long n = tid; n < N; n += 256) {
+    const float pr = expf(row[n] - lse);
+    row[n] = (pr - (n == lab ? 1.f : 0.f)) * invB;
+  }
+}
+
+// dxn[b,:] += inv_temp * sum_{n in chunk} dlogit[b,n] * yn[n,:]   grid (chunks, B), 256 threads
+__global__ void __launch_bounds__(256)
+ce_dxn_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ yn, long long N, int chunk,
+              float inv_temp, float* __restrict__ dxn) {
+  const int b = blockIdx.y;
+  const long long n0 = static_cast<long long>(blockIdx.x) * chunk;
+  const long long n1 = (n0 + chunk < N) ? n0 + chunk : N;
+  const int tid = threadIdx.x;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const float* dl = dlogits + static_cast<size_t>(b) * N;
+  for (long long n = n0; n < n1; ++n) {
+    const float g = dl[n];
+    const uint32_t* yr = reinterpret_cast<const uint32_t*>(yn + n * 768);
+    const float2 v0 = unpack_bf16(yr[tid]);
+    a0 += g * v0.x; a1 += g * v0.y;
+    if (tid < 128) {
+      const float2 v1 = unpack_bf16(yr[256 + tid]);
+      a2 += g * v1.x; a3 += g * v1.y;
+    }
+  }
+  float* o = dxn + static_cast<size_t>(b) * 768;
+  atomicAdd(o + tid * 2, a0 * inv_temp);
+  atomicAdd(o + tid * 2 + 1, a1 * inv_temp);
+  if (tid < 128) {
+    atomicAdd(o + 512 + tid * 2, a2 * inv_temp);
+    atomicAdd(o + 512 + tid * 2 + 1, a3 * inv_temp);
+  }
+}
+
+// dx = (dxn - xh (xh . dxn)) / max(|x|, eps);  grid (B), 256 threads (3 elements each)
+template <bool IN_BF16>
+__global__ void __launch_bounds__(256)
+ce_norm_bwd_kernel(const void* __restrict__ x_, const float* __restrict__ dxn, float* __restrict__ dx) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ float red[2][8];
+  float xv[3], gv[3];
+  float q = 0.f, d = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int e = k * 256 + tid;
+    xv[k] = IN_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x_)[static_cast<size_t>(b) * 768 + e])
+                    : reinterpret_cast<const float*>(x_)[static_cast<size_t>(b) * 768 + e];
+    gv[k] = dxn[static_cast<size_t>(b) * 768 + e];
+    q += xv[k] * xv[k];
+    d += xv[k] * gv[k];
+  }
+  q = warp_sum(q); d = warp_sum(d);
+  if (lane == 0) { red[0][warp] = q; red[1][warp] = d; }
+  __syncthreads();
+  q = 0.f; d = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { q += red[0][w]; d += red[1][w]; }
+  const float nrm = fmaxf(sqrtf(q), 1e-8f);
+  const float inv = 1.f / nrm;
+  // xh = x*inv; xh.dxn = d*inv
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int e = k * 256 + tid;
+    dx[static_cast<size_t>(b) * 768 + e] = (gv[k] - xv[k] * inv * (d * inv)) * inv;
+  }
+}
+
+static int launch_cosine(int mode, const void* xn, const void* yn, ScoreParams& p, cudaStream_t stream) {
+  const CUtensorMap* tmA = get_tmap_2d(xn, p.B, p.K, p.K, SC_BM);
+  const CUtensorMap* tmB = get_tmap_2d(yn, static_cast<uint64_t>(p.N), p.K, p.K, SC_BN);
+  if (!tmA || !tmB) return RF_ERR_CUDA;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RF_CUDA(cudaFuncSetAttribute(cosine_mma_kernel<SC_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+    RF_CUDA(cudaFuncSetAttribute(cosine_mma_kernel<SC_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+    attr_set = true;
+  }
+  const int m_tiles = (p.B + SC_BM - 1) / SC_BM;
+  const int grid = m_tiles * p.slices;
+  if (mode == SC_TOPK)
+    cosine_mma_kernel<SC_TOPK><<<grid, SC_THREADS, SC_SMEM, stream>>>(*tmA, *tmB, p);
+  else
+    cosine_mma_kernel<SC_DENSE><<<grid, SC_THREADS, SC_SMEM, stream>>>(*tmA, *tmB, p);
+  return check_launch("cosine_mma_kernel");
+}
+
+static int pick_slices(int B, long long N) {
+  const int m_tiles = (B + SC_BM - 1) / SC_BM;
+  const long long n_tiles = (N + SC_BN - 1) / SC_BN;
+  long long s = sm_count() / m_tiles;
+  if (s < 1) s = 1;
+  if (s > n_tiles) s = n_tiles;
+  return static_cast<int>(s);
+}
+
+}  // namespace rf
+
+using namespace rf;
+
+extern "C" int rf_normalize_rows(const void* x, int x_is_bf16, void* y, float* norms, long long N, int E,
+                                 rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(x && y && N > 0, "rf_normalize_rows: bad argument");
+  RF_REQUIRE(E == 768, "rf_normalize_rows: hidden size %d unsupported (768)", E);
+  long long grid = (N + 7) / 8;
+  if (grid > sm_count() * 16) grid = sm_count() * 16;
+  if (x_is_bf16)
+    normalize_rows_kernel<true><<<static_cast<int>(grid), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), norms, N);
+  else
+    normalize_rows_kernel<false><<<static_cast<int>(grid), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), norms, N);
+  return check_launch("rf_normalize_rows");
+}
+
+extern "C" int rf_cosine_logits(const void* xn, const void* yn, float* logits, int B, long long N, int E, float temp,
+                                rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(xn && yn && logits && B > 0 && N > 0, "rf_cosine_logits: bad argument");
+  RF_REQUIRE(E % 8 == 0, "rf_cosine_logits: E must be a multiple of 8");
+  ScoreParams p{};
+  p.B = B; p.N = N; p.K = E; p.inv_temp = 1.0f / temp; p.k = 0; p.id_base = 0;
+  p.slices = pick_slices(B, N);
+  p.logits = logits;
+  return launch_cosine(SC_DENSE, xn, yn, p, stream);
+}
+
+extern "C" long long rf_cosine_topk_ws_bytes(int B, long long N, int k) {
+  const long long s = pick_slices(B, N);
+  return s * B * (static_cast<long long>(k) * 8 + 4) + 256;
+}
+
+extern "C" int rf_cosine_topk(const void* xn, const void* yn, int B, long long N, int E, float temp, int k,
+                              int id_base, const int64_t* labels, float* topk_scores, int32_t* topk_ids,
+                              float* label_score, void* ws, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(xn && yn && topk_scores && topk_ids && ws && B > 0 && N > 0, "rf_cosine_topk: bad argument");
+  RF_REQUIRE(k >= 1 && k <= SC_MAXK, "rf_cosine_topk: k=%d out of range [1,%d]", k, SC_MAXK);
+  RF_REQUIRE(E % 8 == 0, "rf_cosine_topk: E must be a multiple of 8");
+  RF_REQUIRE(N + id_base < 2147483647ll, "rf_cosine_topk: item ids must fit int32");
+  ScoreParams p{};
+  p.B = B; p.N = N; p.K = E; p.inv_temp = 1.0f / temp; p.k = k; p.id_base = id_base;
+  p.slices = pick_slices(B, N);
+  p.labels = labels;
+  const size_t cnt = static_cast<size_t>(p.slices) * B * k;
+  p.ws_scores = reinterpret_cast<float*>(ws);
+  p.ws_ids = reinterpret_cast<int32_t*>(p.ws_scores + cnt);
+  p.ws_label = reinterpret_cast<float*>(p.ws_ids + cnt);
+  int rc = launch_cosine(SC_TOPK, xn, yn, p, stream);
+  if (rc) return rc;
+  topk_merge_kernel<<<(B + 127) / 128, 128, 0, stream>>>(p.ws_scores, p.ws_ids, p.ws_label, p.slices, B, k,
+                                                        topk_scores, topk_ids, label_score);
+  return check_launch("rf_cosine_topk/merge");
+}
+
+extern "C" int rf_topk_merge(const float* scores, const int32_t* ids, const float* label_scores, int parts, int B,
+                             int k, float* out_scores, int32_t* out_ids, float* out_label_score,
+                             rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(scores && ids && out_scores && out_ids && parts > 0 && B > 0, "rf_topk_merge: bad argument");
+  RF_REQUIRE(k >= 1 && k <= SC_MAXK, "rf_topk_merge: k=%d out of range [1,%d]", k, SC_MAXK);
+  topk_merge_kernel<<<(B + 127) / 128, 128, 0, stream>>>(scores, ids, label_scores, parts, B, k, out_scores, out_ids,
+                                                        out_label_score);
+  return check_launch("rf_topk_merge");
+}
+
+extern "C" long long rf_cosine_ce_ws_bytes(int B, long long N, int E) {
+  return static_cast<long long>(B) * N * 4 + static_cast<long long>(B) * E * (2 + 4) + 256;
+}
+
+// ws layout: [B*E bf16 xn][B*N fp32 logits][B*E fp32 dxn]
+extern "C" int rf_cosine_ce(const void* pooled, int pooled_is_bf16, const void* yn, const int64_t* labels, int B,
+                            long long N, int E, float temp, float* loss, float* dpooled, float* ws_,
+                            rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(pooled && yn && labels && loss && ws_ && B > 0 && N > 0, "rf_cosine_ce: bad argument");
+  RF_REQUIRE(E == 768, "rf_cosine_ce: hidden size %d unsupported (768)", E);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(ws_);
+  __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(ws);
+  size_t off = (static_cast<size_t>(B) * E * 2 + 255) & ~size_t(255);
+  float* logits = reinterpret_cast<float*>(ws + off);
+  off += (static_cast<size_t>(B) * N * 4 + 255) & ~size_t(255);
+  float* dxn = reinterpret_cast<float*>(ws + off);
+  int rc = rf_normalize_rows(pooled, pooled_is_bf16, xn, nullptr, B, E, stream_);
+  if (rc) return rc;
+  rc = rf_cosine_logits(xn, yn, logits, B, N, E, temp, stream_);
+  if (rc) return rc;
+  RF_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), stream));
+  ce_row_kernel<<<B, 256, 0, stream>>>(logits, labels, B, N, loss);
+  rc = check_launch("rf_cosine_ce/row");
+  if (rc || dpooled == nullptr) return rc;
+  RF_CUDA(cudaMemsetAsync(dxn, 0, static_cast<size_t>(B) * E * 4, stream));
+  const int chunk = 128;
+  ce_dxn_kernel<<<dim3(static_cast<unsigned>((N + chunk - 1) / chunk), B), 256, 0, stream>>>(
+      logits, reinterpret_cast<const __nv_bfloat16*>(yn), N, chunk, 1.0f / temp, dxn);
+  rc = check_launch("rf_cosine_ce/dxn");
+  if (rc) return rc;
+  if (pooled_is_bf16)
+    ce_norm_bwd_kernel<true><<<B, 256, 0, stream>>>(pooled, dxn, dpooled);
+  else
+    ce_norm_bwd_kernel<false><<<B, 256, 0, stream>>>(pooled, dxn, dpooled);
+  return check_launch("rf_cosine_ce/norm_bwd");
+}

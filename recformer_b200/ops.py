@@ -1,0 +1,283 @@
+"""torch-tensor wrappers over the C ABI (include/recformer_b200.h).
+
+PyTorch is used for device memory and streams only; every computation below is a call into
+librecformer_b200.so.  All wrappers launch on the current torch CUDA stream."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import AttnArgs, EmbedArgs, GemmArgs, GlobalArgs, check
+
+EPI_NONE, EPI_GELU, EPI_DGELU = 0, 1, 2
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, dtype, name):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (recformer_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def launch_count() -> int:
+    return int(_lib.lib().rf_launch_count())
+
+
+# ---------------------------------------------------------------------------------------------
+def gemm(A, B, out=None, *, bias=None, residual=None, aux=None, out2=None, a_mn_major=False, b_mn_major=False,
+         epi=EPI_NONE, out_dtype=torch.bfloat16, accumulate=False, split_k=1, scale=1.0, scale_ncols=0,
+         drop_p=0.0, drop_seed=0, M=None, N=None, K=None):
+    """C[M,N] = epilogue(A (*) B).  A: [M,K] (or [K,M] if a_mn_major), B: [N,K] (or [K,N] if b_mn_major)."""
+    _req(A, torch.bfloat16, "A"), _req(B, torch.bfloat16, "B")
+    if M is None:
+        M, K_a = (A.shape[1], A.shape[0]) if a_mn_major else (A.shape[0], A.shape[1])
+        N, K_b = (B.shape[1], B.shape[0]) if b_mn_major else (B.shape[0], B.shape[1])
+        if K_a != K_b:
+            raise ValueError(f"gemm: inner dimensions differ ({K_a} vs {K_b})")
+        K = K_a
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=A.device)
+    a = GemmArgs()
+    a.A, a.B, a.C, a.C2 = A.data_ptr(), B.data_ptr(), out.data_ptr(), _ptr(out2)
+    a.bias, a.residual, a.aux = _ptr(bias), _ptr(residual), _ptr(aux)
+    a.M, a.N, a.K = M, N, K
+    a.lda, a.ldb, a.ldc = A.stride(0), B.stride(0), out.stride(0)
+    a.ldr = residual.stride(0) if residual is not None else 0
+    a.ldaux = aux.stride(0) if aux is not None else 0
+    a.a_mn_major, a.b_mn_major, a.epi = int(a_mn_major), int(b_mn_major), epi
+    a.out_f32 = int(out.dtype == torch.float32)
+    a.accumulate, a.split_k = int(accumulate), split_k
+    a.scale, a.scale_ncols = scale, scale_ncols
+    a.drop_p, a.drop_seed = drop_p, drop_seed
+    check(_lib.lib().rf_gemm_bf16(C.byref(a), _stream()), "rf_gemm_bf16")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+def prepare_inputs(input_ids, attention_mask, global_attention_mask, Lp, padding_idx, err_flag):
+    _req(input_ids, torch.int64, "input_ids")
+    B, L = input_ids.shape
+    if attention_mask is not None:
+        _req(attention_mask, torch.int64, "attention_mask")
+    if global_attention_mask is not None:
+        _req(global_attention_mask, torch.int64, "global_attention_mask")
+    pos = torch.empty(B, Lp, dtype=torch.int32, device=input_ids.device)
+    mask = torch.empty(B, Lp, dtype=torch.uint8, device=input_ids.device)
+    check(_lib.lib().rf_prepare_inputs(input_ids.data_ptr(), _ptr(attention_mask), _ptr(global_attention_mask), B, L,
+                                       Lp, padding_idx, pos.data_ptr(), mask.data_ptr(), err_flag.data_ptr(),
+                                       _stream()), "rf_prepare_inputs")
+    return pos, mask
+
+
+def _embed_args(input_ids, token_type_ids, item_position_ids, pos_ids, word, posw, typew, itemw, gamma, beta, Lp,
+                padding_idx, eps, drop_p, drop_seed):
+    B, L = input_ids.shape
+    a = EmbedArgs()
+    a.input_ids, a.token_type_ids = input_ids.data_ptr(), _ptr(token_type_ids)
+    a.item_position_ids, a.pos_ids = item_position_ids.data_ptr(), pos_ids.data_ptr()
+    a.word_emb, a.pos_emb, a.type_emb, a.item_emb = word.data_ptr(), posw.data_ptr(), typew.data_ptr(), itemw.data_ptr()
+    a.ln_gamma, a.ln_beta = gamma.data_ptr(), beta.data_ptr()
+    a.B, a.L, a.Lp, a.E = B, L, Lp, word.shape[1]
+    a.vocab, a.max_pos, a.type_size, a.max_item = word.shape[0], posw.shape[0], typew.shape[0], itemw.shape[0]
+    a.padding_idx, a.eps, a.drop_p, a.drop_seed = padding_idx, eps, drop_p, drop_seed
+    return a
+
+
+def embed_ln_fwd(input_ids, token_type_ids, item_position_ids, pos_ids, word, posw, typew, itemw, gamma, beta, Lp,
+                 padding_idx, eps, err_flag, drop_p=0.0, drop_seed=0, out=None):
+    for t, n in ((word, "word"), (posw, "pos"), (typew, "type"), (itemw, "item"), (gamma, "gamma"), (beta, "beta")):
+        _req(t, torch.float32, n)
+    B = input_ids.shape[0]
+    a = _embed_args(input_ids, token_type_ids, item_position_ids, pos_ids, word, posw, typew, itemw, gamma, beta, Lp,
+                    padding_idx, eps, drop_p, drop_seed)
+    if out is None:
+        out = torch.empty(B * Lp, word.shape[1], dtype=torch.bfloat16, device=word.device)
+    check(_lib.lib().rf_embed_ln_fwd(C.byref(a), out.data_ptr(), _ptr(err_flag), _stream()), "rf_embed_ln_fwd")
+    return out
+
+
+def embed_ln_bwd(dout, input_ids, token_type_ids, item_position_ids, pos_ids, word, posw, typew, itemw, gamma, beta,
+                 Lp, padding_idx, eps, d_word, d_pos, d_type, d_item, d_gamma, d_beta, drop_p=0.0, drop_seed=0):
+    a = _embed_args(input_ids, token_type_ids, item_position_ids, pos_ids, word, posw, typew, itemw, gamma, beta, Lp,
+                    padding_idx, eps, drop_p, drop_seed)
+    check(_lib.lib().rf_embed_ln_bwd(C.byref(a), dout.data_ptr(), _ptr(d_word), _ptr(d_pos), _ptr(d_type),
+                                     _ptr(d_item), _ptr(d_gamma), _ptr(d_beta), _stream()), "rf_embed_ln_bwd")
+
+
+def layernorm_fwd(x, gamma, beta, eps, out=None, stats=None):
+    _req(x, torch.bfloat16, "x")
+    T, E = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.lib().rf_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), _ptr(stats), T,
+                                      E, eps, _stream()), "rf_layernorm_fwd")
+    return out
+
+
+def layernorm_bwd(dy, x, stats, gamma, d_gamma, d_beta, dx=None, dx_dropped=None, drop_p=0.0, drop_seed=0):
+    T, E = x.shape
+    if dx is None:
+        dx = torch.empty_like(x)
+    check(_lib.lib().rf_layernorm_bwd(dy.data_ptr(), x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), dx.data_ptr(),
+                                      _ptr(dx_dropped), drop_p, drop_seed, _ptr(d_gamma), _ptr(d_beta), T, E,
+                                      _stream()), "rf_layernorm_bwd")
+    return dx
+
+
+def colsum(x, out):
+    T, N = x.shape
+    check(_lib.lib().rf_colsum_bf16(x.data_ptr(), out.data_ptr(), T, N, x.stride(0), _stream()), "rf_colsum_bf16")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+def _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed):
+    a = AttnArgs()
+    a.qkv, a.mask012 = qkv.data_ptr(), mask012.data_ptr()
+    a.B, a.L, a.H, a.D, a.w = B, L, H, 64, w
+    a.drop_p, a.drop_seed = drop_p, drop_seed
+    return a
+
+
+def band_attn_fwd(qkv, mask012, B, L, H, w, ctx=None, lse=None, drop_p=0.0, drop_seed=0):
+    _req(qkv, torch.bfloat16, "qkv"), _req(mask012, torch.uint8, "mask012")
+    if ctx is None:
+        ctx = torch.empty(B * L, H * 64, dtype=torch.bfloat16, device=qkv.device)
+    if lse is None:
+        lse = torch.empty(B, H, L, dtype=torch.float32, device=qkv.device)
+    a = _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed)
+    check(_lib.lib().rf_band_attn_fwd(C.byref(a), ctx.data_ptr(), lse.data_ptr(), _stream()), "rf_band_attn_fwd")
+    return ctx, lse
+
+
+def band_attn_bwd(qkv, mask012, B, L, H, w, ctx, lse, dctx, dqkv, dkv_cls, drop_p=0.0, drop_seed=0):
+    a = _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed)
+    check(_lib.lib().rf_band_attn_bwd(C.byref(a), ctx.data_ptr(), lse.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(),
+                                      dkv_cls.data_ptr(), _stream()), "rf_band_attn_bwd")
+    return dqkv
+
+
+def _global_args(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, drop_p, drop_seed):
+    a = GlobalArgs()
+    a.x, a.mask012 = x.data_ptr(), mask012.data_ptr()
+    a.Wqg, a.bqg, a.Wkg, a.Wvg, a.bvg = Wqg.data_ptr(), bqg.data_ptr(), Wkg.data_ptr(), Wvg.data_ptr(), bvg.data_ptr()
+    a.B, a.L, a.H, a.D = B, L, H, 64
+    a.drop_p, a.drop_seed = drop_p, drop_seed
+    return a
+
+
+def global_attn_fwd(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, ctx, saved=None, drop_p=0.0, drop_seed=0):
+    """Writes row 0 of every sequence of ctx; returns the tensors saved for backward."""
+    E = H * 64
+    dev = x.device
+    if saved is None:
+        saved = {"qg": torch.empty(B, E, dtype=torch.float32, device=dev),
+                 "u": torch.empty(B, H, E, dtype=torch.float32, device=dev),
+                 "p": torch.empty(B, H, L, dtype=torch.float32, device=dev),
+                 "mvec": torch.empty(B, H, E, dtype=torch.float32, device=dev),
+                 "psum": torch.empty(B, H, dtype=torch.float32, device=dev)}
+    a = _global_args(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, drop_p, drop_seed)
+    check(_lib.lib().rf_global_attn_fwd(C.byref(a), ctx.data_ptr(), saved["qg"].data_ptr(), saved["u"].data_ptr(),
+                                        saved["p"].data_ptr(), saved["mvec"].data_ptr(), saved["psum"].data_ptr(),
+                                        _stream()), "rf_global_attn_fwd")
+    return saved
+
+
+# ---------------------------------------------------------------------------------------------
+def normalize_rows(x, out=None, norms=None):
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("normalize_rows: fp32 or bf16 input")
+    if not x.is_cuda or not x.is_contiguous():
+        raise ValueError("normalize_rows: contiguous CUDA tensor required")
+    N, E = x.shape
+    if out is None:
+        out = torch.empty(N, E, dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().rf_normalize_rows(x.data_ptr(), int(x.dtype == torch.bfloat16), out.data_ptr(), _ptr(norms), N, E,
+                                       _stream()), "rf_normalize_rows")
+    return out
+
+
+def cosine_logits(xn, yn, temp, out=None):
+    _req(xn, torch.bfloat16, "xn"), _req(yn, torch.bfloat16, "yn")
+    B, E = xn.shape
+    N = yn.shape[0]
+    if out is None:
+        out = torch.empty(B, N, dtype=torch.float32, device=xn.device)
+    check(_lib.lib().rf_cosine_logits(xn.data_ptr(), yn.data_ptr(), out.data_ptr(), B, N, E, temp, _stream()),
+          "rf_cosine_logits")
+    return out
+
+
+def cosine_topk(xn, yn, temp, k=10, id_base=0, labels=None, ws=None):
+    _req(xn, torch.bfloat16, "xn"), _req(yn, torch.bfloat16, "yn")
+    B, E = xn.shape
+    N = yn.shape[0]
+    dev = xn.device
+    nbytes = int(_lib.lib().rf_cosine_topk_ws_bytes(B, N, k))
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    scores = torch.empty(B, k, dtype=torch.float32, device=dev)
+    ids = torch.empty(B, k, dtype=torch.int32, device=dev)
+    label_score = torch.empty(B, dtype=torch.float32, device=dev)
+    if labels is not None:
+        _req(labels, torch.int64, "labels")
+    check(_lib.lib().rf_cosine_topk(xn.data_ptr(), yn.data_ptr(), B, N, E, temp, k, id_base, _ptr(labels),
+                                    scores.data_ptr(), ids.data_ptr(), label_score.data_ptr(), ws.data_ptr(),
+                                    _stream()), "rf_cosine_topk")
+    return scores, ids, label_score
+
+
+def topk_merge(scores, ids, label_scores=None):
+    """scores/ids: [parts, B, k]; label_scores: [parts, B] or None."""
+    parts, B, k = scores.shape
+    dev = scores.device
+    out_s = torch.empty(B, k, dtype=torch.float32, device=dev)
+    out_i = torch.empty(B, k, dtype=torch.int32, device=dev)
+    out_l = torch.empty(B, dtype=torch.float32, device=dev) if label_scores is not None else None
+    check(_lib.lib().rf_topk_merge(scores.data_ptr(), ids.data_ptr(), _ptr(label_scores), parts, B, k,
+                                   out_s.data_ptr(), out_i.data_ptr(), _ptr(out_l), _stream()), "rf_topk_merge")
+    return out_s, out_i, out_l
+
+
+def cosine_ce(pooled, yn, labels, temp, want_grad=True, ws=None):
+    """Full-softmax CE over cosine logits; returns (loss[1] fp32, dpooled [B,E] fp32 or None)."""
+    B, E = pooled.shape
+    N = yn.shape[0]
+    dev = pooled.device
+    nbytes = int(_lib.lib().rf_cosine_ce_ws_bytes(B, N, E)) + 1024
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dpooled = torch.empty(B, E, dtype=torch.float32, device=dev) if want_grad else None
+    check(_lib.lib().rf_cosine_ce(pooled.data_ptr(), int(pooled.dtype == torch.bfloat16), yn.data_ptr(),
+                                  labels.data_ptr(), B, N, E, temp, loss.data_ptr(), _ptr(dpooled), ws.data_ptr(),
+                                  _stream()), "rf_cosine_ce")
+    return loss, dpooled
+
+
+def cast_bf16(x, out=None):
+    _req(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().rf_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "rf_cast_f32_to_bf16")
+    return out
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    check(_lib.lib().rf_adamw_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                   _ptr(shadow), param.numel(), lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                                   _stream()), "rf_adamw_step")

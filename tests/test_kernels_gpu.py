@@ -1,0 +1,306 @@
+"""Per-kernel parity tests (B200 only): every C-ABI kernel against a plain fp32 PyTorch
+restatement of the same arithmetic on the same (bf16-rounded) inputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from recformer_b200 import ops
+
+DEV = "cuda"
+
+
+def rnd(*shape, scale=1.0, seed=0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def relerr(a, b):
+    return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12)).item()
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 256, 128), (200, 768, 768), (1024, 2304, 768),
+                                   (512, 768, 3072), (64, 3072, 768)])
+def test_gemm_tn_bias(M, N, K):
+    A, B = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    out = ops.gemm(A, B, bias=bias)
+    ref = A.float() @ B.float().T + bias
+    assert relerr(out, ref) < 1e-2
+    out32 = ops.gemm(A, B, bias=bias, out_dtype=torch.float32)
+    assert relerr(out32, ref) < 1e-4
+
+
+def test_gemm_q_scale_residual():
+    M, N, K = 384, 2304, 768
+    A, B = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    out = ops.gemm(A, B, bias=bias, scale=0.125, scale_ncols=768)
+    ref = A.float() @ B.float().T + bias
+    ref[:, :768] *= 0.125
+    assert relerr(out, ref) < 1e-2
+    res = rnd(M, 768, seed=5)
+    out = ops.gemm(A, B[:768].contiguous(), bias=bias[:768].contiguous(), residual=res)
+    ref = A.float() @ B[:768].float().T + bias[:768] + res.float()
+    assert relerr(out, ref) < 1e-2
+
+
+def test_gemm_gelu_dual_and_dgelu():
+    M, N, K = 256, 3072, 768
+    A, B = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    g = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    u = ops.gemm(A, B, bias=bias, epi=ops.EPI_GELU, out2=g)
+    uref = A.float() @ B.float().T + bias
+    assert relerr(u, uref) < 1e-2
+    assert relerr(g, torch.nn.functional.gelu(u.float())) < 1e-2
+    # dgrad with GELU': dU = (dY @ W) * gelu'(u); W stored [K=768(out), N=3072(in)] i.e. nn.Linear weight of the down proj
+    dY = rnd(M, 768, seed=7)
+    W2 = rnd(768, 3072, seed=8, scale=0.05)
+    dU = ops.gemm(dY, W2, b_mn_major=True, epi=ops.EPI_DGELU, aux=u)
+    uf = u.float().requires_grad_(True)
+    torch.nn.functional.gelu(uf).backward(dY.float() @ W2.float())
+    assert relerr(dU, uf.grad) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (384, 768, 2304), (200, 3072, 768)])
+def test_gemm_dgrad_layout(M, N, K):
+    # dX[M,N] = dY[M,K] @ W[K,N]  with W stored row-major [K,N] (nn.Linear weight [out,in])
+    dY, W = rnd(M, K, seed=1), rnd(K, N, seed=2, scale=0.05)
+    res = rnd(M, N, seed=3)
+    out = ops.gemm(dY, W, b_mn_major=True, residual=res)
+    ref = dY.float() @ W.float() + res.float()
+    assert relerr(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("T,No,Ki,split", [(64, 128, 128, 1), (1024, 768, 768, 1), (2048, 2304, 768, 4),
+                                           (1000 // 8 * 8, 768, 3072, 3)])
+def test_gemm_wgrad_layout(T, No, Ki, split):
+    # dW[No,Ki] = dY[T,No]^T @ X[T,Ki]; both operands stored [T, *]
+    dY, X = rnd(T, No, seed=1), rnd(T, Ki, seed=2)
+    out = torch.zeros(No, Ki, dtype=torch.float32, device=DEV)
+    ops.gemm(dY, X, out=out, a_mn_major=True, b_mn_major=True, split_k=split)
+    ref = dY.float().T @ X.float()
+    assert relerr(out, ref) < 1e-4
+    ops.gemm(dY, X, out=out, a_mn_major=True, b_mn_major=True, accumulate=True)
+    assert relerr(out, 2 * ref) < 1e-4
+
+
+def test_gemm_dropout_statistics_and_determinism():
+    M, N, K = 256, 768, 768
+    A, B = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05)
+    o1 = ops.gemm(A, B, drop_p=0.1, drop_seed=1234)
+    o2 = ops.gemm(A, B, drop_p=0.1, drop_seed=1234)
+    o0 = ops.gemm(A, B)
+    assert torch.equal(o1, o2)
+    zero_frac = (o1 == 0).float().mean().item()
+    assert 0.08 < zero_frac < 0.12
+    kept = o1 != 0
+    assert relerr(o1[kept], o0[kept].float() / 0.9) < 1e-2
+
+
+# ------------------------------------------------------------------------------- embeddings / LN
+def test_prepare_and_embed_ln():
+    from oracle import recformer_oracle as O
+    cfg = O.OracleConfig(vocab_size=3000, num_hidden_layers=1, attention_window=[64], max_position_embeddings=600)
+    sd = {k: v.to(DEV) for k, v in O.make_state_dict(cfg, seed=3).items()}
+    batch = O.make_batch(cfg, 5, 200, seed=1, ragged=True)
+    Lp = 256
+    dbatch = {k: v.to(DEV) for k, v in batch.items()}
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    pos, mask = ops.prepare_inputs(dbatch["input_ids"], dbatch["attention_mask"], dbatch["global_attention_mask"], Lp,
+                                   1, err)
+    ref_pos = O.create_position_ids_from_input_ids(batch["input_ids"], 1)
+    assert torch.equal(pos[:, :200].cpu().long(), ref_pos)
+    assert (pos[:, 200:] == 1).all()
+    ref_mask = O.merge_to_attention_mask(batch["attention_mask"], batch["global_attention_mask"])
+    assert torch.equal(mask[:, :200].cpu().long(), ref_mask) and (mask[:, 200:] == 0).all()
+    p = "embeddings."
+    out = ops.embed_ln_fwd(dbatch["input_ids"], dbatch["token_type_ids"], dbatch["item_position_ids"], pos,
+                           sd[p + "word_embeddings.weight"], sd[p + "position_embeddings.weight"],
+                           sd[p + "token_type_embeddings.weight"], sd[p + "item_position_embeddings.weight"],
+                           sd[p + "LayerNorm.weight"], sd[p + "LayerNorm.bias"], Lp, 1, 1e-5, err)
+    assert err.item() == 0
+    _, ids, am, tt, pids, ip = O.pad_to_window_size(
+        O.OracleConfig(num_hidden_layers=1, attention_window=[256]), batch["input_ids"], batch["attention_mask"],
+        batch["token_type_ids"], None, batch["item_position_ids"])
+    sd_cpu = {k: v.cpu() for k, v in sd.items()}
+    ref = O.embeddings_forward(sd_cpu, cfg, ids, tt, ip)
+    assert (out.view(5, Lp, 768).float().cpu() - ref).abs().max() < 0.03   # bf16 output rounding
+    # bad global mask is flagged
+    gm = dbatch["global_attention_mask"].clone()
+    gm[0, 5] = 1
+    ops.prepare_inputs(dbatch["input_ids"], dbatch["attention_mask"], gm, Lp, 1, err)
+    assert err.item() & 1
+
+
+def test_layernorm_fwd_bwd():
+    T, E = 1000, 768
+    x = rnd(T, E, seed=1, scale=2.0)
+    gamma = 1 + rnd(E, seed=2, scale=0.1, dtype=torch.float32)
+    beta = rnd(E, seed=3, scale=0.1, dtype=torch.float32)
+    stats = torch.empty(T, 2, dtype=torch.float32, device=DEV)
+    y = ops.layernorm_fwd(x, gamma, beta, 1e-5, stats=stats)
+    xf = x.float().requires_grad_(True)
+    gf, bf = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xf, (E,), gf, bf, 1e-5)
+    assert (y.float() - ref).abs().max() < 0.03
+    assert (stats[:, 0] - xf.mean(-1)).abs().max() < 1e-4
+    dy = rnd(T, E, seed=4)
+    ref.backward(dy.float())
+    dg = torch.zeros(E, dtype=torch.float32, device=DEV)
+    db = torch.zeros(E, dtype=torch.float32, device=DEV)
+    dx = ops.layernorm_bwd(dy, x, stats, gamma, dg, db)
+    assert relerr(dx, xf.grad) < 1e-2
+    assert relerr(dg, gf.grad) < 1e-3 and relerr(db, bf.grad) < 1e-3
+    cs = torch.zeros(E, dtype=torch.float32, device=DEV)
+    ops.colsum(dy, cs)
+    assert relerr(cs, dy.float().sum(0)) < 1e-4
+
+
+# ----------------------------------------------------------------------------------- attention
+def dense_band_reference(qkv, mask012, B, L, H, w):
+    """Spec A on already-projected q (scaled), k, v: returns ctx (B,L,E) and lse (B,H,L)."""
+    E = H * 64
+    q, k, v = qkv.float().view(B, L, 3, H, 64).permute(2, 0, 3, 1, 4)   # (3,B,H,L,D)
+    valid, glob = mask012 > 0, mask012 > 1
+    idx = torch.arange(L, device=qkv.device)
+    band = (idx[:, None] - idx[None, :]).abs() <= w
+    allowed = (band[None] & (valid & ~glob)[:, None, :]) | glob[:, None, :]
+    s = (q @ k.transpose(-1, -2)).masked_fill(~allowed[:, None], float("-inf"))
+    lse = torch.logsumexp(s, dim=-1)
+    p = torch.nan_to_num(torch.softmax(s, dim=-1), nan=0.0).masked_fill(~valid[:, None, :, None], 0.0)
+    ctx = (p @ v).transpose(1, 2).reshape(B, L, E)
+    return ctx, lse
+
+
+@pytest.mark.parametrize("B,L,w,ragged", [(2, 256, 32, False), (3, 1024, 32, True), (2, 128, 32, True),
+                                          (2, 192, 32, True), (2, 512, 64, True), (1, 1024, 128, True)])
+def test_band_attention_fwd(B, L, w, ragged):
+    H = 12
+    qkv = rnd(B * L, 3 * H * 64, seed=L + w, scale=1.0)
+    qkv[:, : H * 64] *= 0.35   # q pre-scaled
+    mask = torch.ones(B, L, dtype=torch.uint8, device=DEV)
+    mask[:, 0] = 2
+    if ragged:
+        for b in range(1, B):
+            mask[b, L - 37 * b - 5:] = 0
+        if B == 1:
+            mask[0, L - 100:] = 0
+    ctx, lse = ops.band_attn_fwd(qkv, mask, B, L, H, w)
+    ref_ctx, ref_lse = dense_band_reference(qkv, mask.long(), B, L, H, w)
+    ctx = ctx.view(B, L, -1).float()
+    err = (ctx[:, 1:] - ref_ctx[:, 1:]).abs().max().item()
+    assert err < 2e-2, err
+    validq = mask[:, 1:] > 0
+    lerr = (lse[:, :, 1:] - ref_lse[:, :, 1:]).abs()[validq[:, None, :].expand(-1, H, -1)].max().item()
+    assert lerr < 1e-3, lerr
+    # padded query rows are exactly zero (HF:578)
+    if ragged:
+        assert (ctx[:, 1:][~validq] == 0).all()
+
+
+def test_band_attention_no_global():
+    B, L, H, w = 2, 256, 12, 32
+    qkv = rnd(B * L, 3 * H * 64, seed=11)
+    qkv[:, : H * 64] *= 0.35
+    mask = torch.ones(B, L, dtype=torch.uint8, device=DEV)
+    mask[1, 200:] = 0
+    ctx, _ = ops.band_attn_fwd(qkv, mask, B, L, H, w)
+    ref_ctx, _ = dense_band_reference(qkv, mask.long(), B, L, H, w)
+    assert (ctx.view(B, L, -1).float() - ref_ctx).abs().max() < 2e-2
+
+
+def test_global_attention_fwd():
+    B, L, H = 3, 320, 12
+    E = H * 64
+    x = rnd(B * L, E, seed=1)
+    Wq, Wk, Wv = (rnd(E, E, seed=s, scale=0.03, dtype=torch.float32) for s in (2, 3, 4))
+    bq, bk, bv = (rnd(E, seed=s, scale=0.1, dtype=torch.float32) for s in (5, 6, 7))
+    mask = torch.ones(B, L, dtype=torch.uint8, device=DEV)
+    mask[:, 0] = 2
+    mask[1, 250:] = 0
+    mask[2, 100:] = 0
+    ctx = torch.zeros(B * L, E, dtype=torch.bfloat16, device=DEV)
+    saved = ops.global_attn_fwd(x, mask, Wq, bq, Wk, Wv, bv, B, L, H, ctx)
+    xf = x.float().view(B, L, E)
+    qg = ((xf[:, 0] @ Wq.T + bq) / 8).view(B, H, 1, 64)
+    kg = (xf @ Wk.T + bk).view(B, L, H, 64).transpose(1, 2)
+    vg = (xf @ Wv.T + bv).view(B, L, H, 64).transpose(1, 2)
+    s = (qg @ kg.transpose(-1, -2)).masked_fill((mask == 0)[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, -1)
+    ref = (p @ vg).reshape(B, E)
+    got = ctx.view(B, L, E)[:, 0].float()
+    assert (got - ref).abs().max() < 1e-2
+    assert (saved["p"] - p[:, :, 0]).abs().max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------- scoring
+def test_normalize_and_logits_and_topk():
+    B, N, E = 200, 5000, 768
+    x = rnd(B, E, seed=1, dtype=torch.float32)
+    y = rnd(N, E, seed=2, dtype=torch.float32)
+    xn, yn = ops.normalize_rows(x), ops.normalize_rows(y)
+    ref_xn = x / x.norm(dim=-1, keepdim=True)
+    assert (xn.float() - ref_xn).abs().max() < 1e-3
+    logits = ops.cosine_logits(xn, yn, 0.05)
+    ref = (xn.float() @ yn.float().T) / 0.05
+    assert (logits - ref).abs().max() < 1e-3
+    labels = torch.randint(0, N, (B,), device=DEV)
+    ts, ti, ls = ops.cosine_topk(xn, yn, 0.05, k=10, labels=labels)
+    rs, ri = torch.topk(logits, 10, dim=-1)
+    assert torch.equal(ts, rs)
+    assert torch.equal(ti.long(), ri)
+    assert torch.equal(ls, logits[torch.arange(B, device=DEV), labels])
+
+
+def test_topk_sharded_merge_matches_unsharded():
+    B, N, E, S = 130, 4096 + 77, 768, 4
+    xn = ops.normalize_rows(rnd(B, E, seed=1, dtype=torch.float32))
+    yn = ops.normalize_rows(rnd(N, E, seed=2, dtype=torch.float32))
+    labels = torch.randint(0, N, (B,), device=DEV)
+    ts, ti, ls = ops.cosine_topk(xn, yn, 0.05, k=10, labels=labels)
+    bounds = [0, 1000, 2048, 3000, N]
+    ps, pi, pl = [], [], []
+    for s in range(S):
+        a, b = bounds[s], bounds[s + 1]
+        s_, i_, l_ = ops.cosine_topk(xn, yn[a:b].contiguous(), 0.05, k=10, id_base=a, labels=labels)
+        ps.append(s_), pi.append(i_), pl.append(l_)
+    ms, mi, ml = ops.topk_merge(torch.stack(ps), torch.stack(pi), torch.stack(pl))
+    assert torch.equal(ms, ts) and torch.equal(mi, ti) and torch.equal(ml, ls)
+
+
+def test_cosine_ce_loss_and_grad():
+    B, N, E = 16, 5000, 768
+    pooled = rnd(B, E, seed=1)
+    yn = ops.normalize_rows(rnd(N, E, seed=2, dtype=torch.float32))
+    labels = torch.randint(0, N, (B,), device=DEV)
+    loss, dp = ops.cosine_ce(pooled, yn, labels, 0.05)
+    pf = pooled.float().requires_grad_(True)
+    logits = (pf / pf.norm(dim=-1, keepdim=True).clamp_min(1e-8)) @ yn.float().T / 0.05
+    ref = torch.nn.functional.cross_entropy(logits, labels)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 5e-3
+    assert relerr(dp, pf.grad) < 2e-2
+
+
+def test_cast_and_adamw():
+    n = 4096 * 3
+    p = rnd(n, seed=1, dtype=torch.float32)
+    g = rnd(n, seed=2, dtype=torch.float32)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    shadow = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    pt = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pt], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    for step in (1, 2, 3):
+        pt.grad = g.clone()
+        opt.step()
+        ops.adamw_step(p, g, m, v, shadow, 1e-3, 0.9, 0.999, 1e-8, 0.01, step)
+    assert (p - pt.detach()).abs().max() < 1e-6
+    assert torch.equal(shadow, p.to(torch.bfloat16))
+    assert torch.equal(ops.cast_bf16(p), p.to(torch.bfloat16))
