@@ -165,10 +165,11 @@ typedef struct rf_attn_args {
 
 int rf_band_attn_fwd(const rf_attn_args* a, void* ctx_bf16, float* lse, rf_stream_t stream);
 /* dqkv [B*L,3E] bf16 (gradient w.r.t. the UNSCALED q and k, v projections), given dctx.
- * dkv_cls [B,H,2,D] fp32 scratch receives the CLS key/value gradient contributions and is
- * folded into row 0 of dqkv by the kernel's final phase. */
+ * dkv_scratch: fp32 [B*L, 2E] workspace (zeroed by the call) in which the K/V gradients of
+ * overlapping tiles and of the CLS key are accumulated before being folded into dqkv.
+ * Round 1: one-sided window 32 (attention_window 64) only. */
 int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx_bf16, const float* lse, const void* dctx_bf16,
-                     void* dqkv_bf16, float* dkv_cls, rf_stream_t stream);
+                     void* dqkv_bf16, float* dkv_scratch, rf_stream_t stream);
 
 /* Global (CLS) query row (HF:963-1056), re-associated so that key_global/value_global are
  * never applied to all L tokens (SURVEY.md §7 hard part 3):
@@ -189,11 +190,13 @@ typedef struct rf_global_args {
 
 int rf_global_attn_fwd(const rf_global_args* a, void* ctx_bf16, float* qg, float* u, float* p, float* mvec,
                        float* psum, rf_stream_t stream);
-/* Backward of the CLS row: reads dctx row 0; accumulates (+=) fp32 dWqg,dbqg,dWkg,dWvg,dbvg and
- * ADDS the dense gradient it sends to every token (through s_j and m_h) into dx (bf16 [B*L,E]). */
+/* Backward of the CLS row: reads dctx row 0; accumulates (+=) fp32 dWqg,dbqg,dWkg,dWvg,dbvg (any
+ * may be NULL; dbkg is identically zero) and ADDS the dense gradient the row sends to every
+ * token (through s_j and m_h) into dx (bf16 [B*L,E]).  ws: rf_global_attn_bwd_ws_bytes(). */
+long long rf_global_attn_bwd_ws_bytes(int B, int L, int H);
 int rf_global_attn_bwd(const rf_global_args* a, const void* dctx_bf16, const float* qg, const float* u,
-                       const float* p, const float* mvec, void* dx_bf16, float* dWqg, float* dbqg, float* dWkg,
-                       float* dWvg, float* dbvg, float* ws, rf_stream_t stream);
+                       const float* p, const float* mvec, const float* psum, void* dx_bf16, float* dWqg, float* dbqg,
+                       float* dWkg, float* dWvg, float* dbvg, float* ws, rf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Scoring (SURVEY.md §8a Spec S; ref: recformer/models.py:358-369,533-545) and metrics

@@ -136,16 +136,3 @@ const char* rf_last_error(void) { return rf::g_err; }
 int rf_version(void) { return 100; }
 unsigned long long rf_launch_count(void) { return rf::g_launches.load(); }
 }
-
-// ---- entry points that are declared in the header but implemented in a later translation unit
-// get a loud "not implemented" here only while RF_STUB_BWD is defined at build time ----
-#ifdef RF_STUB_BWD
-extern "C" int rf_band_attn_bwd(const rf_attn_args*, const void*, const float*, const void*, void*, float*,
-                                rf_stream_t) {
-  return rf::set_error(RF_ERR_INVALID, "rf_band_attn_bwd: not implemented in this build");
-}
-extern "C" int rf_global_attn_bwd(const rf_global_args*, const void*, const float*, const float*, const float*,
-                                  const float*, void*, float*, float*, float*, float*, float*, float*, rf_stream_t) {
-  return rf::set_error(RF_ERR_INVALID, "rf_global_attn_bwd: not implemented in this build");
-}
-#endif

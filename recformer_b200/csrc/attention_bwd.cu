@@ -1,0 +1,386 @@
+// Banded attention backward (one-sided window W = 32, i.e. attention_window 64), sm_100a.
+//
+// One CTA = one (batch, head, 128-query tile), the same tiling as the forward kernel:
+//   S  = Q K^T,  dP = dO V^T                      tcgen05.mma -> TMEM (2 x 208 columns)
+//   P  = exp(S - lse),  delta = sum_j P dP,  dS = P (dP - delta)        fp32, thread = query row
+//   P, dS (bf16) -> shared memory (128B-swizzled, rows = queries)
+//   dQ = dS K          A = dS (K-major),   B = K  (MN-major view of the K tile)
+//   dV = P^T dO        A = P  (MN-major view of the same P buffer), B = dO (MN-major)
+//   dK = dS^T Q        A = dS (MN-major view),                       B = Q  (MN-major)
+// so no operand is ever transposed in memory.  dQ (scaled back by 1/sqrt(D)) is written as bf16
+// into dqkv; dK/dV tiles (keys of neighbouring tiles overlap, and every tile contributes to the
+// CLS key) are accumulated with red.add.f32 into an fp32 scratch [B*L, 2E] that a small kernel
+// then folds into the K/V columns of dqkv.  The global query row receives no band gradient (its
+// band output is overwritten by the global row, HF:615-626).
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "rf_common.h"
+#include "rf_ptx.cuh"
+
+namespace rf {
+
+constexpr int AB_THREADS = 128;
+constexpr int AB_W = 32;
+constexpr int AB_NK = 128 + 2 * AB_W;   // 192
+constexpr int AB_NT = AB_NK + 16;       // 208
+constexpr int AB_D = 64;
+constexpr uint32_t AB_Q_BYTES = 128 * 128, AB_KV_BYTES = AB_NT * 128, AB_P_BYTES = 4 * 16384;
+constexpr uint32_t AB_OFF_Q = 0;
+constexpr uint32_t AB_OFF_DO = AB_OFF_Q + AB_Q_BYTES;
+constexpr uint32_t AB_OFF_K = AB_OFF_DO + AB_Q_BYTES;
+constexpr uint32_t AB_OFF_V = AB_OFF_K + AB_KV_BYTES;          // 26624 = 26 KiB: stays 1024-aligned
+constexpr uint32_t AB_OFF_P = AB_OFF_V + AB_KV_BYTES;
+constexpr uint32_t AB_OFF_DS = AB_OFF_P + AB_P_BYTES;
+constexpr uint32_t AB_OFF_FLAG = AB_OFF_DS + AB_P_BYTES;
+constexpr uint32_t AB_OFF_BAR = AB_OFF_FLAG + 208;
+constexpr uint32_t AB_SMEM = AB_OFF_BAR + 64 + 1024;
+static_assert(AB_OFF_V % 1024 == 0 && AB_OFF_P % 1024 == 0, "swizzled tiles need 1024B alignment");
+static_assert(AB_SMEM <= 227 * 1024, "shared memory budget");
+
+struct AttnBwdParams {
+  const uint8_t* mask012;
+  const float* lse;
+  __nv_bfloat16* dqkv;
+  float* dkv;   // fp32 scratch [B*L, 2E]
+  int B, L, H;
+  float drop_scale;
+  uint32_t drop_thresh;
+  uint64_t drop_seed;
+};
+
+__global__ void __launch_bounds__(AB_THREADS)
+band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_constant__ CUtensorMap tmQKV16,
+                     const __grid_constant__ CUtensorMap tmDO, const AttnBwdParams p) {
+  constexpr int W = AB_W, NK = AB_NK, NT = AB_NT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + AB_OFF_Q;
+  uint8_t* sDO = smem + AB_OFF_DO;
+  uint8_t* sK = smem + AB_OFF_K;
+  uint8_t* sV = smem + AB_OFF_V;
+  uint8_t* sP = smem + AB_OFF_P;
+  uint8_t* sDS = smem + AB_OFF_DS;
+  uint8_t* kflag = smem + AB_OFF_FLAG;
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + AB_OFF_BAR);
+  uint64_t* bar_mma = bar_load + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tiles_per_seq = (p.L + 127) / 128;
+  const int tile = blockIdx.x % tiles_per_seq;
+  const int h = (blockIdx.x / tiles_per_seq) % p.H;
+  const int b = blockIdx.x / (tiles_per_seq * p.H);
+  const int i0 = tile * 128;
+  const int E = p.H * AB_D;
+  const uint8_t* mrow = p.mask012 + static_cast<size_t>(b) * p.L;
+
+  if (tid == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  for (int c = tid; c < NT; c += AB_THREADS) {
+    uint8_t f = 0;
+    if (c < NK) {
+      const int j = i0 - W + c;
+      f = (j >= 0 && j < p.L && mrow[j] == 1) ? 1 : 0;
+    } else if (c == NK) {
+      f = (mrow[0] == 2) ? 1 : 0;
+    }
+    kflag[c] = f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t TM_S = 0, TM_DP = 256;                       // phase 1
+  constexpr uint32_t TM_DQ = 0, TM_DV = 64, TM_DK = 192;          // phase 2 (dV: 2 x 64, dK: 2 x 64)
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_load, 2 * AB_Q_BYTES + 2 * AB_KV_BYTES);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      tma_load_3d(sQ + c * 8192, &tmQKV64, bar_load, h * AB_D, i0 + c * 64, b);
+      tma_load_3d(sDO + c * 8192, &tmDO, bar_load, h * AB_D, i0 + c * 64, b);
+    }
+#pragma unroll
+    for (int c = 0; c < NK / 64; ++c) {
+      tma_load_3d(sK + c * 8192, &tmQKV64, bar_load, E + h * AB_D, i0 - W + c * 64, b);
+      tma_load_3d(sV + c * 8192, &tmQKV64, bar_load, 2 * E + h * AB_D, i0 - W + c * 64, b);
+    }
+    tma_load_3d(sK + NK * 128, &tmQKV16, bar_load, E + h * AB_D, 0, b);
+    tma_load_3d(sV + NK * 128, &tmQKV16, bar_load, 2 * E + h * AB_D, 0, b);
+    mbar_wait(bar_load, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc_bf16(128, NT, false, false);
+    const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK), ado = smem_u32(sDO), av = smem_u32(sV);
+#pragma unroll
+    for (int k = 0; k < AB_D / 16; ++k)
+      umma_bf16(tmem + TM_S, umma_smem_desc(aq + k * 32, 16, 1024), umma_smem_desc(ak + k * 32, 16, 1024), idesc,
+                k > 0 ? 1u : 0u);
+#pragma unroll
+    for (int k = 0; k < AB_D / 16; ++k)
+      umma_bf16(tmem + TM_DP, umma_smem_desc(ado + k * 32, 16, 1024), umma_smem_desc(av + k * 32, 16, 1024), idesc,
+                k > 0 ? 1u : 0u);
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+
+  const int r = tid;
+  const int i = i0 + r;
+  const bool in_seq = i < p.L;
+  const bool is_global_row = (i == 0) && (mrow[0] == 2);
+  const bool row_valid = in_seq && (mrow[in_seq ? i : 0] != 0) && !is_global_row;
+  const float lse = in_seq ? p.lse[(static_cast<size_t>(b) * p.H + h) * p.L + i] : 0.f;
+  const uint32_t lane_base = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  constexpr int WIN_CH = 2 * W / 32 + 1;
+  const float LOG2E = 1.4426950408889634f;
+  const float lse2 = lse * LOG2E;
+  const uint64_t rowid = (static_cast<uint64_t>(b) * p.H + h) * p.L + (in_seq ? i : 0);
+  constexpr int DGRP = (2 * W + 16) / 8;
+  const bool g_ok = kflag[NK] != 0;
+
+  // ---- pass A: delta = sum_c P'_c dP_c (P' = dropout(P)) ----
+  float delta = 0.f;
+#pragma unroll 1
+  for (int cc = warp; cc < warp + WIN_CH; ++cc) {
+    uint32_t sv[32], dv[32];
+    tmem_ld32(lane_base + TM_S + cc * 32, sv);
+    tmem_ld32(lane_base + TM_DP + cc * 32, dv);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int c = cc * 32 + j;
+      const bool ok = row_valid && kflag[c] && (c >= r) && (c <= r + 2 * W);
+      float pr = ok ? exp2f(__uint_as_float(sv[j]) * LOG2E - lse2) : 0.f;
+      if (p.drop_thresh != 0 && ok) {
+        const int d = c - r;
+        const uint32_t keep = dropout_keep8(p.drop_seed, rowid * DGRP + (d >> 3), p.drop_thresh);
+        pr = ((keep >> (d & 7)) & 1u) ? pr * p.drop_scale : 0.f;
+      }
+      delta += pr * __uint_as_float(dv[j]);
+    }
+  }
+  uint32_t gs[16], gd[16];
+  tmem_ld16(lane_base + TM_S + NK, gs);
+  tmem_ld16(lane_base + TM_DP + NK, gd);
+  tmem_ld_wait();
+  float pg = (row_valid && g_ok) ? exp2f(__uint_as_float(gs[0]) * LOG2E - lse2) : 0.f;   // undropped
+  float pg_d = pg;                                                                         // dropped
+  float keep_g = 1.f;
+  if (p.drop_thresh != 0) {
+    const int d = 2 * W + 1;
+    const uint32_t keep = dropout_keep8(p.drop_seed, rowid * DGRP + (d >> 3), p.drop_thresh);
+    keep_g = ((keep >> (d & 7)) & 1u) ? p.drop_scale : 0.f;
+    pg_d = pg * keep_g;
+  }
+  const float dpg = __uint_as_float(gd[0]);
+  delta += pg_d * dpg;
+
+  // ---- pass B: P' and dS -> shared memory ----
+#pragma unroll 1
+  for (int cc = 0; cc < NK / 32; ++cc) {
+    uint4 po[4], so[4];
+    if (cc >= warp && cc < warp + WIN_CH) {
+      uint32_t sv[32], dv[32];
+      tmem_ld32(lane_base + TM_S + cc * 32, sv);
+      tmem_ld32(lane_base + TM_DP + cc * 32, dv);
+      tmem_ld_wait();
+      float pr[32], ds[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = cc * 32 + j;
+        const bool ok = row_valid && kflag[c] && (c >= r) && (c <= r + 2 * W);
+        const float pu = ok ? exp2f(__uint_as_float(sv[j]) * LOG2E - lse2) : 0.f;
+        float kp = 1.f;
+        if (p.drop_thresh != 0 && ok) {
+          const int d = c - r;
+          const uint32_t keep = dropout_keep8(p.drop_seed, rowid * DGRP + (d >> 3), p.drop_thresh);
+          kp = ((keep >> (d & 7)) & 1u) ? p.drop_scale : 0.f;
+        }
+        pr[j] = pu * kp;                                           // P' feeds dV
+        ds[j] = pu * (kp * __uint_as_float(dv[j]) - delta);        // softmax backward
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        po[u] = make_uint4(pack_bf16(pr[u * 8], pr[u * 8 + 1]), pack_bf16(pr[u * 8 + 2], pr[u * 8 + 3]),
+                           pack_bf16(pr[u * 8 + 4], pr[u * 8 + 5]), pack_bf16(pr[u * 8 + 6], pr[u * 8 + 7]));
+        so[u] = make_uint4(pack_bf16(ds[u * 8], ds[u * 8 + 1]), pack_bf16(ds[u * 8 + 2], ds[u * 8 + 3]),
+                           pack_bf16(ds[u * 8 + 4], ds[u * 8 + 5]), pack_bf16(ds[u * 8 + 6], ds[u * 8 + 7]));
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) po[u] = so[u] = make_uint4(0, 0, 0, 0);
+    }
+    const uint32_t roff = (cc >> 1) * 16384 + r * 128;
+    const int ubase = (cc & 1) * 4;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t o = roff + (((ubase + u) ^ (r & 7)) << 4);
+      *reinterpret_cast<uint4*>(sP + o) = po[u];
+      *reinterpret_cast<uint4*>(sDS + o) = so[u];
+    }
+  }
+  {
+    // global chunk = P/dS chunk 3 (columns 192..255): column 192 holds the CLS key, the rest is zero
+    const float dsg = pg * (keep_g * dpg - delta);
+    const uint32_t roff = 3 * 16384 + r * 128;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t o = roff + ((u ^ (r & 7)) << 4);
+      *reinterpret_cast<uint4*>(sP + o) = (u == 0) ? make_uint4(pack_bf16(pg_d, 0.f), 0, 0, 0) : make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sDS + o) = (u == 0) ? make_uint4(pack_bf16(dsg, 0.f), 0, 0, 0) : make_uint4(0, 0, 0, 0);
+    }
+  }
+
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK), ado = smem_u32(sDO), ap = smem_u32(sP), ads = smem_u32(sDS);
+    // dQ[128 x 64] = dS[128 x 208] K[208 x 64]
+    constexpr uint32_t idesc_q = umma_idesc_bf16(128, AB_D, false, true);
+#pragma unroll
+    for (int ks = 0; ks < NT / 16; ++ks)
+      umma_bf16(tmem + TM_DQ, umma_smem_desc(ads + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+                umma_smem_desc(ak + ks * 2048, 8192, 1024), idesc_q, ks > 0 ? 1u : 0u);
+    // dV[keys x 64] = P^T dO,  dK[keys x 64] = dS^T Q   (two 128-key halves each)
+    constexpr uint32_t idesc_kv = umma_idesc_bf16(128, AB_D, true, true);
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+      for (int ks = 0; ks < 128 / 16; ++ks) {
+        umma_bf16(tmem + TM_DV + hh * 64, umma_smem_desc(ap + hh * 32768 + ks * 2048, 16384, 1024),
+                  umma_smem_desc(ado + ks * 2048, 8192, 1024), idesc_kv, ks > 0 ? 1u : 0u);
+        umma_bf16(tmem + TM_DK + hh * 64, umma_smem_desc(ads + hh * 32768 + ks * 2048, 16384, 1024),
+                  umma_smem_desc(aq + ks * 2048, 8192, 1024), idesc_kv, ks > 0 ? 1u : 0u);
+      }
+    }
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 1);
+  tc_fence_after();
+
+  // ---- dQ (x 1/sqrt(D): gradient w.r.t. the unscaled projection) ----
+  {
+    __nv_bfloat16* orow = p.dqkv + (static_cast<size_t>(b) * p.L + (in_seq ? i : 0)) * 3 * E + h * AB_D;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[32];
+      tmem_ld32(lane_base + TM_DQ + half * 32, v);
+      tmem_ld_wait();
+      if (in_seq) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(v[j]) * 0.125f, __uint_as_float(v[j + 1]) * 0.125f);
+          o.y = pack_bf16(__uint_as_float(v[j + 2]) * 0.125f, __uint_as_float(v[j + 3]) * 0.125f);
+          o.z = pack_bf16(__uint_as_float(v[j + 4]) * 0.125f, __uint_as_float(v[j + 5]) * 0.125f);
+          o.w = pack_bf16(__uint_as_float(v[j + 6]) * 0.125f, __uint_as_float(v[j + 7]) * 0.125f);
+          *reinterpret_cast<uint4*>(orow + half * 32 + j) = o;
+        }
+      }
+    }
+  }
+  // ---- dK / dV: thread r owns key column c = hh*128 + r of the tile ----
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int c = hh * 128 + r;
+    int j = -1;
+    if (c < NK) j = i0 - W + c;
+    else if (c == NK) j = 0;
+    const bool key_ok = (j >= 0 && j < p.L) && kflag[c < NT ? c : 0] && (c <= NK);
+    float* base = p.dkv + (static_cast<size_t>(b) * p.L + (key_ok ? j : 0)) * 2 * E + h * AB_D;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {   // 0: dK, 1: dV
+      const uint32_t tcol = (which == 0 ? TM_DK : TM_DV) + hh * 64;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(lane_base + tcol + half * 32, v);
+        tmem_ld_wait();
+        if (key_ok) {
+          float* dst = base + which * E + half * 32;
+#pragma unroll
+          for (int q = 0; q < 32; q += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q), "f"(__uint_as_float(v[q])),
+                         "f"(__uint_as_float(v[q + 1])), "f"(__uint_as_float(v[q + 2])), "f"(__uint_as_float(v[q + 3]))
+                         : "memory");
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// dqkv[:, E:3E] = bf16(dkv)   (fold the fp32 K/V gradient scratch into the fused gradient)
+__global__ void fold_dkv_kernel(const float4* __restrict__ dkv, __nv_bfloat16* __restrict__ dqkv, long long T, int E) {
+  const int per_row = 2 * E / 4;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < T * per_row;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long t = idx / per_row;
+    const int c4 = static_cast<int>(idx % per_row);
+    const float4 v = dkv[idx];
+    *reinterpret_cast<uint2*>(dqkv + t * 3 * E + E + c4 * 4) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+}  // namespace rf
+
+using namespace rf;
+
+extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const float* lse, const void* dctx,
+                                void* dqkv, float* dkv_scratch, rf_stream_t stream_) {
+  (void)ctx;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(a && lse && dctx && dqkv && dkv_scratch, "rf_band_attn_bwd: null argument");
+  RF_REQUIRE(a->D == AB_D, "rf_band_attn_bwd: head_dim %d unsupported (64 only)", a->D);
+  RF_REQUIRE(a->w == AB_W, "rf_band_attn_bwd: one-sided window %d unsupported (32 only, i.e. attention_window 64)",
+             a->w);
+  RF_REQUIRE(a->B > 0 && a->L >= 16 && a->H > 0, "rf_band_attn_bwd: bad shape");
+  static bool attr_set = false;
+  if (!attr_set) {
+    RF_CUDA(cudaFuncSetAttribute(band_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    attr_set = true;
+  }
+  const int E = a->H * AB_D;
+  const uint64_t L = a->L, B = a->B;
+  const CUtensorMap* tm64 = get_tmap_3d(a->qkv, B, L, 3 * E, 3 * E, L * 3 * E, 64);
+  const CUtensorMap* tm16 = get_tmap_3d(a->qkv, B, L, 3 * E, 3 * E, L * 3 * E, 16);
+  const CUtensorMap* tmdo = get_tmap_3d(dctx, B, L, E, E, L * E, 64);
+  if (!tm64 || !tm16 || !tmdo) return RF_ERR_CUDA;
+  RF_CUDA(cudaMemsetAsync(dkv_scratch, 0, static_cast<size_t>(B) * L * 2 * E * sizeof(float), stream));
+  AttnBwdParams p;
+  p.mask012 = a->mask012; p.lse = lse;
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  p.dkv = dkv_scratch;
+  p.B = a->B; p.L = a->L; p.H = a->H;
+  p.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
+  p.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
+  p.drop_seed = a->drop_seed;
+  const int tiles = (a->L + 127) / 128;
+  band_attn_bwd_kernel<<<a->B * a->H * tiles, AB_THREADS, AB_SMEM, stream>>>(*tm64, *tm16, *tmdo, p);
+  int rc = check_launch("rf_band_attn_bwd");
+  if (rc) return rc;
+  const long long T = static_cast<long long>(B) * L;
+  long long grid = (T * (2 * E / 4) + 255) / 256;
+  if (grid > sm_count() * 16) grid = sm_count() * 16;
+  fold_dkv_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(reinterpret_cast<const float4*>(dkv_scratch),
+                                                             reinterpret_cast<__nv_bfloat16*>(dqkv), T, E);
+  return check_launch("rf_band_attn_bwd/fold");
+}

@@ -196,8 +196,10 @@ embed_ln_bwd_kernel(const EmbedDev a, const __nv_bfloat16* __restrict__ dout, fl
       const int v = k * 32 + lane;
       const float dx0 = rstd * (gy[k].x - s1 - x[k].x * s2), dx1 = rstd * (gy[k].y - s1 - x[k].y * s2);
       const float dx2 = rstd * (gy[k].z - s1 - x[k].z * s2), dx3 = rstd * (gy[k].w - s1 - x[k].w * s2);
-      if (d_word) red_add_v4(d_word + static_cast<size_t>(id) * a.E + v * 4, dx0, dx1, dx2, dx3);
-      if (d_pos) red_add_v4(d_pos + static_cast<size_t>(pid) * a.E + v * 4, dx0, dx1, dx2, dx3);
+      // nn.Embedding(padding_idx=pad) never accumulates a gradient into the pad row
+      // (ref: recformer/models.py:89,104-106)
+      if (d_word && id != a.pad) red_add_v4(d_word + static_cast<size_t>(id) * a.E + v * 4, dx0, dx1, dx2, dx3);
+      if (d_pos && pid != a.pad) red_add_v4(d_pos + static_cast<size_t>(pid) * a.E + v * 4, dx0, dx1, dx2, dx3);
       if (d_type) red_add_v4(d_type + static_cast<size_t>(tt) * a.E + v * 4, dx0, dx1, dx2, dx3);
       if (d_item) red_add_v4(d_item + static_cast<size_t>(ip) * a.E + v * 4, dx0, dx1, dx2, dx3);
     }

@@ -209,6 +209,235 @@ global_out_kernel(const float* __restrict__ mvec, const float* __restrict__ psum
   }
 }
 
+
+// =============================== backward of the CLS row ===================================
+// GB1: dm[b,h,:] = Wvg[h]^T dout_h, dpsum = bvg[h].dout_h; dWvg += dout_h (x) m_h; dbvg += dout_h psum.
+//      Also zeroes du and dxcls.  grid (H, B), 256 threads.
+__global__ void __launch_bounds__(256)
+global_bwd_dm_kernel(const __nv_bfloat16* __restrict__ dctx, const uint8_t* __restrict__ mask,
+                     const float* __restrict__ Wvg, const float* __restrict__ bvg, const float* __restrict__ mvec,
+                     const float* __restrict__ psum, int L, float* __restrict__ dm, float* __restrict__ dpsum,
+                     float* __restrict__ du, float* __restrict__ dxcls, float* dWvg, float* dbvg) {
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  __shared__ float dout[GD];
+  const bool on = mask[static_cast<size_t>(b) * L] == 2;
+  if (tid < GD) dout[tid] = on ? __bfloat162float(dctx[static_cast<size_t>(b) * L * GE + h * GD + tid]) : 0.f;
+  for (int e = tid; e < GE; e += 256) du[(static_cast<size_t>(b) * GH + h) * GE + e] = 0.f;
+  if (h == 0) for (int e = tid; e < GE; e += 256) dxcls[static_cast<size_t>(b) * GE + e] = 0.f;
+  __syncthreads();
+  const float ps = psum[b * GH + h];
+  const float* mb = mvec + (static_cast<size_t>(b) * GH + h) * GE;
+  for (int e = tid; e < GE; e += 256) {
+    float acc = 0.f;
+    const float me = mb[e];
+#pragma unroll 8
+    for (int d = 0; d < GD; ++d) {
+      const float g = dout[d];
+      acc += Wvg[static_cast<size_t>(h * GD + d) * GE + e] * g;
+      if (on && dWvg) red_add_f32(dWvg + static_cast<size_t>(h * GD + d) * GE + e, g * me);
+    }
+    dm[(static_cast<size_t>(b) * GH + h) * GE + e] = acc;
+  }
+  if (tid < GD && on && dbvg) red_add_f32(dbvg + h * GD + tid, dout[tid] * ps);
+  if (tid == 0) {
+    float t = 0.f;
+    for (int d = 0; d < GD; ++d) t += bvg[h * GD + d] * dout[d];
+    dpsum[b * GH + h] = t;
+  }
+}
+
+// GB2: dp[b,h,j] = keep_j * scale * (dm_h . x_j + dpsum_h)   (0 for padded keys).  grid (L/64, B)
+__global__ void __launch_bounds__(256)
+global_bwd_dp_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict__ mask,
+                     const float* __restrict__ dm, const float* __restrict__ dpsum, int L, float drop_scale,
+                     uint32_t drop_thresh, uint64_t drop_seed, float* __restrict__ dp) {
+  const int b = blockIdx.y, j0 = blockIdx.x * TOK_PER_CTA;
+  extern __shared__ float us[];   // [GH][GE]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* ub = dm + static_cast<size_t>(b) * GH * GE;
+  for (int i = tid; i < GH * GE; i += 256) us[i] = ub[i];
+  __syncthreads();
+  for (int jj = warp; jj < TOK_PER_CTA; jj += 8) {
+    const int j = j0 + jj;
+    if (j >= L) break;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (static_cast<size_t>(b) * L + j) * GE);
+    float xv[24];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const uint4 raw = xr[k * 32 + lane];
+      const float2 a0 = unpack_bf16(raw.x), a1 = unpack_bf16(raw.y), a2 = unpack_bf16(raw.z), a3 = unpack_bf16(raw.w);
+      xv[k * 8 + 0] = a0.x; xv[k * 8 + 1] = a0.y; xv[k * 8 + 2] = a1.x; xv[k * 8 + 3] = a1.y;
+      xv[k * 8 + 4] = a2.x; xv[k * 8 + 5] = a2.y; xv[k * 8 + 6] = a3.x; xv[k * 8 + 7] = a3.y;
+    }
+    const bool valid = mask[static_cast<size_t>(b) * L + j] != 0;
+#pragma unroll
+    for (int h = 0; h < GH; ++h) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float* up = us + h * GE + (k * 32 + lane) * 8;
+        const float4 u0 = *reinterpret_cast<const float4*>(up), u1 = *reinterpret_cast<const float4*>(up + 4);
+        acc += xv[k * 8 + 0] * u0.x + xv[k * 8 + 1] * u0.y + xv[k * 8 + 2] * u0.z + xv[k * 8 + 3] * u0.w +
+               xv[k * 8 + 4] * u1.x + xv[k * 8 + 5] * u1.y + xv[k * 8 + 6] * u1.z + xv[k * 8 + 7] * u1.w;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        float v = valid ? acc + dpsum[b * GH + h] : 0.f;
+        if (drop_thresh != 0) {
+          const uint64_t idx = (static_cast<uint64_t>(b) * GH + h) * L + j;
+          const uint32_t keep = dropout_keep8(drop_seed, idx >> 3, drop_thresh);
+          v = ((keep >> (idx & 7)) & 1u) ? v * drop_scale : 0.f;
+        }
+        dp[(static_cast<size_t>(b) * GH + h) * L + j] = v;
+      }
+    }
+  }
+}
+
+// GB3: ds_j = p_j (dp_j - sum_k p_k dp_k), in place over dp.  grid (B*H), 256 threads
+__global__ void __launch_bounds__(256) global_bwd_ds_kernel(const float* __restrict__ p, float* __restrict__ dp, int L) {
+  const float* pr = p + static_cast<size_t>(blockIdx.x) * L;
+  float* dr = dp + static_cast<size_t>(blockIdx.x) * L;
+  __shared__ float red[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float t = 0.f;
+  for (int j = tid; j < L; j += 256) t += pr[j] * dr[j];
+  t = warp_sum(t);
+  if (lane == 0) red[warp] = t;
+  __syncthreads();
+  t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];
+  for (int j = tid; j < L; j += 256) dr[j] = pr[j] * (dr[j] - t);
+}
+
+// GB4: du[b,h,:] += sum_j ds_hj x_j ;  dx_j += sum_h (p'_hj dm_h + ds_hj u_h).  grid (L/64, B), 256 threads
+__global__ void __launch_bounds__(256)
+global_bwd_dx_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ p, const float* __restrict__ ds,
+                     const float* __restrict__ dm, const float* __restrict__ u, int L, float drop_scale,
+                     uint32_t drop_thresh, uint64_t drop_seed, float* __restrict__ du, __nv_bfloat16* __restrict__ dx) {
+  const int b = blockIdx.y, j0 = blockIdx.x * TOK_PER_CTA;
+  __shared__ float cp[GH][TOK_PER_CTA];   // p'
+  __shared__ float cs[GH][TOK_PER_CTA];   // ds
+  const int tid = threadIdx.x;
+  for (int i = tid; i < GH * TOK_PER_CTA; i += 256) {
+    const int h = i / TOK_PER_CTA, jj = i % TOK_PER_CTA;
+    const int j = j0 + jj;
+    float v = 0.f, s = 0.f;
+    if (j < L) {
+      const uint64_t idx = (static_cast<uint64_t>(b) * GH + h) * L + j;
+      v = p[idx];
+      s = ds[idx];
+      if (drop_thresh != 0) {
+        const uint32_t keep = dropout_keep8(drop_seed, idx >> 3, drop_thresh);
+        v = ((keep >> (idx & 7)) & 1u) ? v * drop_scale : 0.f;
+      }
+    }
+    cp[h][jj] = v;
+    cs[h][jj] = s;
+  }
+  // per-thread columns: pair tid (cols 2tid,2tid+1) and, for tid < 128, pair 256+tid
+  float dmr[GH][4], ur[GH][4], acc[GH][4];
+  const bool second = tid < 128;
+#pragma unroll
+  for (int h = 0; h < GH; ++h) {
+    const float* dmb = dm + (static_cast<size_t>(b) * GH + h) * GE;
+    const float* ub = u + (static_cast<size_t>(b) * GH + h) * GE;
+    dmr[h][0] = dmb[tid * 2]; dmr[h][1] = dmb[tid * 2 + 1];
+    ur[h][0] = ub[tid * 2]; ur[h][1] = ub[tid * 2 + 1];
+    dmr[h][2] = second ? dmb[512 + tid * 2] : 0.f; dmr[h][3] = second ? dmb[512 + tid * 2 + 1] : 0.f;
+    ur[h][2] = second ? ub[512 + tid * 2] : 0.f; ur[h][3] = second ? ub[512 + tid * 2 + 1] : 0.f;
+    acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
+  }
+  __syncthreads();
+  const int n = min(TOK_PER_CTA, L - j0);
+  for (int jj = 0; jj < n; ++jj) {
+    const size_t rowoff = (static_cast<size_t>(b) * L + j0 + jj) * GE;
+    const uint32_t* xr = reinterpret_cast<const uint32_t*>(x + rowoff);
+    uint32_t* dxr = reinterpret_cast<uint32_t*>(dx + rowoff);
+    const float2 x0 = unpack_bf16(xr[tid]);
+    const float2 x1 = second ? unpack_bf16(xr[256 + tid]) : make_float2(0.f, 0.f);
+    float2 g0 = unpack_bf16(dxr[tid]);
+    float2 g1 = second ? unpack_bf16(dxr[256 + tid]) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < GH; ++h) {
+      const float a = cp[h][jj], s = cs[h][jj];
+      g0.x += a * dmr[h][0] + s * ur[h][0]; g0.y += a * dmr[h][1] + s * ur[h][1];
+      g1.x += a * dmr[h][2] + s * ur[h][2]; g1.y += a * dmr[h][3] + s * ur[h][3];
+      acc[h][0] += s * x0.x; acc[h][1] += s * x0.y; acc[h][2] += s * x1.x; acc[h][3] += s * x1.y;
+    }
+    dxr[tid] = pack_bf16(g0.x, g0.y);
+    if (second) dxr[256 + tid] = pack_bf16(g1.x, g1.y);
+  }
+#pragma unroll
+  for (int h = 0; h < GH; ++h) {
+    float* dub = du + (static_cast<size_t>(b) * GH + h) * GE;
+    red_add_f32(dub + tid * 2, acc[h][0]);
+    red_add_f32(dub + tid * 2 + 1, acc[h][1]);
+    if (second) {
+      red_add_f32(dub + 512 + tid * 2, acc[h][2]);
+      red_add_f32(dub + 512 + tid * 2 + 1, acc[h][3]);
+    }
+  }
+}
+
+// GB5: dqg = Wkg[h] du_h; dWkg += qg_h (x) du_h; dWqg += dqg/8 (x) xcls; dbqg += dqg/8;
+//      dxcls += Wqg[h]^T dqg/8.   grid (H, B), 256 threads
+__global__ void __launch_bounds__(256)
+global_bwd_q_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict__ mask,
+                    const float* __restrict__ Wqg, const float* __restrict__ Wkg, const float* __restrict__ qg,
+                    const float* __restrict__ du, int L, float* dWqg, float* dbqg, float* dWkg,
+                    float* __restrict__ dxcls) {
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (mask[static_cast<size_t>(b) * L] != 2) return;
+  __shared__ float dus[GE];
+  __shared__ float xs[GE];
+  __shared__ float dq[GD];
+  __shared__ float qs[GD];
+  const float* dub = du + (static_cast<size_t>(b) * GH + h) * GE;
+  for (int e = tid; e < GE; e += 256) {
+    dus[e] = dub[e];
+    xs[e] = __bfloat162float(x[static_cast<size_t>(b) * L * GE + e]);
+  }
+  if (tid < GD) qs[tid] = qg[static_cast<size_t>(b) * GE + h * GD + tid];
+  __syncthreads();
+  for (int d = warp; d < GD; d += 8) {
+    const float* wr = Wkg + static_cast<size_t>(h * GD + d) * GE;
+    float acc = 0.f;
+    for (int e = lane; e < GE; e += 32) acc += wr[e] * dus[e];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      dq[d] = acc * 0.125f;   // gradient w.r.t. (Wqg x + bqg)
+      if (dbqg) red_add_f32(dbqg + h * GD + d, acc * 0.125f);
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < GE; e += 256) {
+    float acc = 0.f;
+    const float due = dus[e], xe = xs[e];
+#pragma unroll 8
+    for (int d = 0; d < GD; ++d) {
+      const size_t w = static_cast<size_t>(h * GD + d) * GE + e;
+      acc += Wqg[w] * dq[d];
+      if (dWkg) red_add_f32(dWkg + w, qs[d] * due);
+      if (dWqg) red_add_f32(dWqg + w, dq[d] * xe);
+    }
+    red_add_f32(dxcls + static_cast<size_t>(b) * GE + e, acc);
+  }
+}
+
+// GB6: dx[b,0,:] += dxcls[b,:].  grid (B), 256 threads
+__global__ void __launch_bounds__(256)
+global_bwd_cls_kernel(const float* __restrict__ dxcls, const uint8_t* __restrict__ mask, int L,
+                      __nv_bfloat16* __restrict__ dx) {
+  const int b = blockIdx.x;
+  if (mask[static_cast<size_t>(b) * L] != 2) return;
+  for (int e = threadIdx.x; e < GE; e += 256) {
+    __nv_bfloat16* d = dx + static_cast<size_t>(b) * L * GE + e;
+    *d = __float2bfloat16(__bfloat162float(*d) + dxcls[static_cast<size_t>(b) * GE + e]);
+  }
+}
+
 }  // namespace rf
 
 using namespace rf;
@@ -243,4 +472,53 @@ extern "C" int rf_global_attn_fwd(const rf_global_args* a, void* ctx, float* qg,
   global_out_kernel<<<dim3(GH, a->B), 256, 0, stream>>>(mvec, psum, a->Wvg, a->bvg, a->mask012, a->L,
                                                        reinterpret_cast<__nv_bfloat16*>(ctx));
   return check_launch("rf_global_attn_fwd/out");
+}
+
+extern "C" long long rf_global_attn_bwd_ws_bytes(int B, int L, int H) {
+  const long long E = static_cast<long long>(H) * GD;
+  return 4ll * (2ll * B * H * E + B * H + static_cast<long long>(B) * H * L + B * E) + 256;
+}
+
+extern "C" int rf_global_attn_bwd(const rf_global_args* a, const void* dctx, const float* qg, const float* u,
+                                  const float* p, const float* mvec, const float* psum, void* dx, float* dWqg,
+                                  float* dbqg, float* dWkg, float* dWvg, float* dbvg, float* ws, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(a && dctx && qg && u && p && mvec && psum && dx && ws, "rf_global_attn_bwd: null argument");
+  RF_REQUIRE(a->H == GH && a->D == GD, "rf_global_attn_bwd: only H=12, D=64 supported (got %d, %d)", a->H, a->D);
+  const int B = a->B, L = a->L;
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a->x);
+  float* dm = ws;
+  float* du = dm + static_cast<size_t>(B) * GH * GE;
+  float* dpsum = du + static_cast<size_t>(B) * GH * GE;
+  float* dp = dpsum + static_cast<size_t>(B) * GH;
+  float* dxcls = dp + static_cast<size_t>(B) * GH * L;
+  const int chunks = (L + TOK_PER_CTA - 1) / TOK_PER_CTA;
+  const uint32_t thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
+  const float scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RF_CUDA(cudaFuncSetAttribute(global_bwd_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GH * GE * 4));
+    attr_set = true;
+  }
+  global_bwd_dm_kernel<<<dim3(GH, B), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dctx), a->mask012,
+                                                       a->Wvg, a->bvg, mvec, psum, L, dm, dpsum, du, dxcls, dWvg, dbvg);
+  int rc = check_launch("rf_global_attn_bwd/dm");
+  if (rc) return rc;
+  global_bwd_dp_kernel<<<dim3(chunks, B), 256, GH * GE * 4, stream>>>(x, a->mask012, dm, dpsum, L, scale, thresh,
+                                                                     a->drop_seed, dp);
+  rc = check_launch("rf_global_attn_bwd/dp");
+  if (rc) return rc;
+  global_bwd_ds_kernel<<<B * GH, 256, 0, stream>>>(p, dp, L);
+  rc = check_launch("rf_global_attn_bwd/ds");
+  if (rc) return rc;
+  global_bwd_dx_kernel<<<dim3(chunks, B), 256, 0, stream>>>(x, p, dp, dm, u, L, scale, thresh, a->drop_seed, du,
+                                                           reinterpret_cast<__nv_bfloat16*>(dx));
+  rc = check_launch("rf_global_attn_bwd/dx");
+  if (rc) return rc;
+  global_bwd_q_kernel<<<dim3(GH, B), 256, 0, stream>>>(x, a->mask012, a->Wqg, a->Wkg, qg, du, L, dWqg, dbqg, dWkg,
+                                                      dxcls);
+  rc = check_launch("rf_global_attn_bwd/q");
+  if (rc) return rc;
+  global_bwd_cls_kernel<<<B, 256, 0, stream>>>(dxcls, a->mask012, L, reinterpret_cast<__nv_bfloat16*>(dx));
+  return check_launch("rf_global_attn_bwd/cls");
 }

@@ -1,0 +1,428 @@
+"""Host-side engine of the B200 encoder: flat parameter storage, activation workspaces and the
+forward / backward launch schedules over the C-ABI kernels.
+
+Data layout in HBM
+  * parameters live in ONE flat fp32 buffer (the nn.Parameters of the reference-compatible module
+    tree are views into it), ordered so that query/key/value weights of a layer are contiguous
+    (= the fused [3E,E] QKV weight) and so that AdamW can run as two launches (decay / no-decay);
+  * the dense encoder weights additionally have a bf16 shadow in the same order (TMA/tcgen05
+    operands); gradients live in a flat fp32 buffer with the same offsets, `.grad`s are views;
+  * activations are bf16 [B*Lp, *] row-major, statistics (LN mean/rstd, attention LSE) fp32.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+
+def _pick_split(M: int, N: int, K: int, sms: int = 148) -> int:
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    kb = (K + 63) // 64
+    best, best_eff = 1, 0.0
+    for s in range(1, 9):
+        if kb // s < 4 and s > 1:
+            break
+        total = tiles * s
+        eff = total / (((total + sms - 1) // sms) * sms)
+        if eff > best_eff + 0.02:
+            best, best_eff = s, eff
+    return best
+
+
+class FlatParams:
+    """Flat fp32 parameter / gradient buffers + bf16 shadow of the dense encoder weights."""
+
+    def __init__(self, model):
+        self.model = model
+        self.flat: Optional[torch.Tensor] = None
+        self.grad: Optional[torch.Tensor] = None
+        self.shadow: Optional[torch.Tensor] = None
+        self.offsets: Dict[str, int] = {}
+        self.n_dense = 0
+        self.n_decay = 0
+        self.n_total = 0
+        self._order: List[str] = []
+        self._sentinel = None
+        self._shadow_sig = None
+        self._plan()
+
+    def _plan(self):
+        m = self.model
+        named = dict(m.named_parameters())
+        dense, other, nodecay = [], [], []
+        nl = m.config.num_hidden_layers
+        for i in range(nl):
+            p = f"encoder.layer.{i}."
+            dense += [p + "attention.self.query.weight", p + "attention.self.key.weight",
+                      p + "attention.self.value.weight", p + "attention.output.dense.weight",
+                      p + "intermediate.dense.weight", p + "output.dense.weight"]
+            other += [p + "attention.self.query_global.weight", p + "attention.self.key_global.weight",
+                      p + "attention.self.value_global.weight"]
+            nodecay += [p + "attention.self.query.bias", p + "attention.self.key.bias", p + "attention.self.value.bias",
+                        p + "attention.self.query_global.bias", p + "attention.self.key_global.bias",
+                        p + "attention.self.value_global.bias", p + "attention.output.dense.bias",
+                        p + "attention.output.LayerNorm.weight", p + "attention.output.LayerNorm.bias",
+                        p + "intermediate.dense.bias", p + "output.dense.bias",
+                        p + "output.LayerNorm.weight", p + "output.LayerNorm.bias"]
+        other = ["embeddings.word_embeddings.weight", "embeddings.position_embeddings.weight",
+                 "embeddings.token_type_embeddings.weight", "embeddings.item_position_embeddings.weight"] + other
+        nodecay += ["embeddings.LayerNorm.weight", "embeddings.LayerNorm.bias"]
+        order = dense + other + nodecay
+        assert set(order) == set(named), (set(named) ^ set(order))
+        off = 0
+        for k in order:
+            n = named[k].numel()
+            assert n % 8 == 0, (k, n)
+            self.offsets[k] = off
+            off += n
+            if k == dense[-1]:
+                self.n_dense = off
+            if k == other[-1]:
+                self.n_decay = off
+        self.n_total = off
+        self._order = order
+        self._named = named
+
+    # -- storage -------------------------------------------------------------------------------
+    def ensure(self, device) -> None:
+        first = self._named[self._order[0]]
+        if (self.flat is not None and self.flat.device == first.device == torch.device(device)
+                and first.data_ptr() == self.flat.data_ptr()
+                and self._named[self._order[-1]].data_ptr() ==
+                self.flat.data_ptr() + 4 * self.offsets[self._order[-1]]):
+            return
+        if first.device != torch.device(device):
+            raise RuntimeError(f"recformer_b200: parameters are on {first.device}, inputs on {device}")
+        if first.device.type != "cuda":
+            raise RuntimeError("recformer_b200 runs on CUDA only: move the model with .cuda() / .to('cuda') "
+                               "(there is no CPU path)")
+        flat = torch.empty(self.n_total, dtype=torch.float32, device=device)
+        with torch.no_grad():
+            for k in self._order:
+                p = self._named[k]
+                o = self.offsets[k]
+                view = flat[o:o + p.numel()].view(p.shape)
+                view.copy_(p.detach().to(torch.float32))
+                p.data = view
+                p.grad = None
+        self.flat = flat
+        self.grad = None
+        self.shadow = torch.empty(self.n_dense, dtype=torch.bfloat16, device=device)
+        self._shadow_sig = None
+
+    def view(self, key: str, flat: Optional[torch.Tensor] = None, shape=None) -> torch.Tensor:
+        p = self._named[key]
+        o = self.offsets[key]
+        base = self.flat if flat is None else flat
+        return base[o:o + p.numel()].view(p.shape if shape is None else shape)
+
+    def fused(self, first_key: str, n_params: int, base: torch.Tensor, shape) -> torch.Tensor:
+        """View spanning `n_params` consecutive parameters starting at `first_key` (fused QKV)."""
+        o = self.offsets[first_key]
+        n = 1
+        for s in shape:
+            n *= s
+        return base[o:o + n].view(shape)
+
+    def refresh_shadow(self, force: bool = False) -> None:
+        sig = sum(self._named[k]._version for k in self._order[: 6 * self.model.config.num_hidden_layers])
+        if force or sig != self._shadow_sig:
+            ops.cast_bf16(self.flat[: self.n_dense], self.shadow)
+            self._shadow_sig = sig
+
+    def mark_shadow_fresh(self) -> None:
+        self._shadow_sig = sum(self._named[k]._version for k in self._order[: 6 * self.model.config.num_hidden_layers])
+
+    def prepare_grads(self) -> None:
+        """Make every trainable parameter's .grad a view of the flat gradient buffer.  If no
+        parameter currently has a gradient (optimizer.zero_grad(set_to_none=True)) the whole
+        buffer is zeroed with one memset; existing view-gradients are accumulated into."""
+        if self.grad is None:
+            self.grad = torch.zeros(self.n_total, dtype=torch.float32, device=self.flat.device)
+            fresh = True
+        else:
+            fresh = False
+        params = [(k, self._named[k]) for k in self._order]
+        if all(p.grad is None for _, p in params):
+            if not fresh:
+                self.grad.zero_()
+            for k, p in params:
+                if p.requires_grad:
+                    p.grad = self.view(k, self.grad)
+            return
+        for k, p in params:
+            if not p.requires_grad:
+                continue
+            gv = self.view(k, self.grad)
+            if p.grad is None:
+                gv.zero_()
+                p.grad = gv
+            elif p.grad.data_ptr() != gv.data_ptr():
+                gv.copy_(p.grad)      # foreign gradient tensor: adopt its value, then accumulate in place
+                p.grad = gv
+
+
+class SavedActivations:
+    """Everything one forward pass keeps for its backward (or, in eval, reusable scratch)."""
+
+    def __init__(self, B: int, Lp: int, cfg, device, per_layer: bool):
+        E, F, H = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
+        T = B * Lp
+        nl = cfg.num_hidden_layers
+        n = nl if per_layer else 1
+        bf = dict(dtype=torch.bfloat16, device=device)
+        f32 = dict(dtype=torch.float32, device=device)
+        self.B, self.Lp, self.per_layer = B, Lp, per_layer
+        self.x = [torch.empty(T, E, **bf) for _ in range(nl + 1 if per_layer else 2)]
+        self.qkv = [torch.empty(T, 3 * E, **bf) for _ in range(n)]
+        self.lse = [torch.empty(B, H, Lp, **f32) for _ in range(n)]
+        self.ctx = [torch.empty(T, E, **bf) for _ in range(n)]
+        self.pre1 = [torch.empty(T, E, **bf) for _ in range(n)]
+        self.stats1 = [torch.empty(T, 2, **f32) for _ in range(n)]
+        self.h1 = [torch.empty(T, E, **bf) for _ in range(n)]
+        self.u = [torch.empty(T, F, **bf) for _ in range(n)]
+        self.g = [torch.empty(T, F, **bf) for _ in range(n)]
+        self.pre2 = [torch.empty(T, E, **bf) for _ in range(n)]
+        self.stats2 = [torch.empty(T, 2, **f32) for _ in range(n)]
+        self.glob = [{"qg": torch.empty(B, E, **f32), "u": torch.empty(B, H, E, **f32),
+                      "p": torch.empty(B, H, Lp, **f32), "mvec": torch.empty(B, H, E, **f32),
+                      "psum": torch.empty(B, H, **f32)} for _ in range(n)]
+        self.pos_ids = None
+        self.mask012 = None
+        self.inputs = None
+        self.seed = 0
+        self.drop_hidden = 0.0
+        self.drop_attn = 0.0
+
+    def idx(self, layer: int) -> int:
+        return layer if self.per_layer else 0
+
+    def xin(self, layer: int) -> torch.Tensor:
+        return self.x[layer] if self.per_layer else self.x[layer % 2]
+
+    def xout(self, layer: int) -> torch.Tensor:
+        return self.x[layer + 1] if self.per_layer else self.x[(layer + 1) % 2]
+
+
+class BackwardScratch:
+    def __init__(self, B: int, Lp: int, cfg, device):
+        E, F, H = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
+        T = B * Lp
+        bf = dict(dtype=torch.bfloat16, device=device)
+        self.d_pre = torch.empty(T, E, **bf)
+        self.d_pre_drop = torch.empty(T, E, **bf)
+        self.dU = torch.empty(T, F, **bf)
+        self.dh1 = torch.empty(T, E, **bf)
+        self.dctx = torch.empty(T, E, **bf)
+        self.dqkv = torch.empty(T, 3 * E, **bf)
+        self.dx = [torch.empty(T, E, **bf) for _ in range(2)]
+        self.dkv = torch.empty(T, 2 * E, dtype=torch.float32, device=device)
+        self.gws = None
+
+
+class EncoderEngine:
+    def __init__(self, model):
+        self.model = model
+        self.cfg = model.config
+        self.params = FlatParams(model)
+        self._free: Dict[tuple, List[SavedActivations]] = {}
+        self._bwd: Dict[tuple, BackwardScratch] = {}
+        self._err = None
+        self._call = 0
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _acquire(self, B, Lp, device, per_layer) -> SavedActivations:
+        key = (B, Lp, str(device), per_layer)
+        pool = self._free.setdefault(key, [])
+        return pool.pop() if pool else SavedActivations(B, Lp, self.cfg, device, per_layer)
+
+    def release(self, sv: SavedActivations) -> None:
+        key = (sv.B, sv.Lp, str(sv.x[0].device), sv.per_layer)
+        pool = self._free.setdefault(key, [])
+        if len(pool) < 4:
+            pool.append(sv)
+
+    def err_flag(self, device) -> torch.Tensor:
+        if self._err is None or self._err.device != torch.device(device):
+            self._err = torch.zeros(1, dtype=torch.int32, device=device)
+        return self._err
+
+    def check_errors(self) -> None:
+        """Synchronising check of the device-side input validation flags."""
+        if self._err is None:
+            return
+        v = int(self._err.item())
+        if v:
+            self._err.zero_()
+            msgs = []
+            if v & 1:
+                msgs.append("global_attention_mask marks a position other than 0 (only the tokenizer's CLS-global "
+                            "layout is supported, ref: recformer/tokenization.py:97-99)")
+            if v & 2:
+                msgs.append("an input / token-type / item-position / position id is out of range")
+            raise ValueError("recformer_b200: " + "; ".join(msgs))
+
+    def window_pad(self, L: int) -> int:
+        aw = self.cfg.attention_window
+        w = aw if isinstance(aw, int) else max(aw)
+        return (L + w - 1) // w * w
+
+    def _layer_weights(self, i: int):
+        P = self.params
+        E, F = self.cfg.hidden_size, self.cfg.intermediate_size
+        p = f"encoder.layer.{i}."
+        sh, fl = P.shadow, P.flat
+        return {
+            "Wqkv": P.fused(p + "attention.self.query.weight", 3, sh, (3 * E, E)),
+            "bqkv": P.fused(p + "attention.self.query.bias", 3, fl, (3 * E,)),
+            "Wo": P.view(p + "attention.output.dense.weight", sh), "bo": P.view(p + "attention.output.dense.bias"),
+            "W1": P.view(p + "intermediate.dense.weight", sh), "b1": P.view(p + "intermediate.dense.bias"),
+            "W2": P.view(p + "output.dense.weight", sh), "b2": P.view(p + "output.dense.bias"),
+            "ln1w": P.view(p + "attention.output.LayerNorm.weight"), "ln1b": P.view(p + "attention.output.LayerNorm.bias"),
+            "ln2w": P.view(p + "output.LayerNorm.weight"), "ln2b": P.view(p + "output.LayerNorm.bias"),
+            "Wqg": P.view(p + "attention.self.query_global.weight"), "bqg": P.view(p + "attention.self.query_global.bias"),
+            "Wkg": P.view(p + "attention.self.key_global.weight"),
+            "Wvg": P.view(p + "attention.self.value_global.weight"), "bvg": P.view(p + "attention.self.value_global.bias"),
+        }
+
+    def _layer_grads(self, i: int):
+        P = self.params
+        E = self.cfg.hidden_size
+        p = f"encoder.layer.{i}."
+        g = P.grad
+        return {
+            "Wqkv": P.fused(p + "attention.self.query.weight", 3, g, (3 * E, E)),
+            "bqkv": P.fused(p + "attention.self.query.bias", 3, g, (3 * E,)),
+            "Wo": P.view(p + "attention.output.dense.weight", g), "bo": P.view(p + "attention.output.dense.bias", g),
+            "W1": P.view(p + "intermediate.dense.weight", g), "b1": P.view(p + "intermediate.dense.bias", g),
+            "W2": P.view(p + "output.dense.weight", g), "b2": P.view(p + "output.dense.bias", g),
+            "ln1w": P.view(p + "attention.output.LayerNorm.weight", g), "ln1b": P.view(p + "attention.output.LayerNorm.bias", g),
+            "ln2w": P.view(p + "output.LayerNorm.weight", g), "ln2b": P.view(p + "output.LayerNorm.bias", g),
+            "Wqg": P.view(p + "attention.self.query_global.weight", g), "bqg": P.view(p + "attention.self.query_global.bias", g),
+            "Wkg": P.view(p + "attention.self.key_global.weight", g),
+            "Wvg": P.view(p + "attention.self.value_global.weight", g), "bvg": P.view(p + "attention.self.value_global.bias", g),
+        }
+
+    def _seed(self, sv: SavedActivations, layer: int, site: int) -> int:
+        return (sv.seed + 1000003 * (layer + 1) + 7919 * site) & 0x7FFFFFFFFFFFFFFF
+
+    # -- forward -------------------------------------------------------------------------------
+    def forward(self, input_ids, attention_mask, global_attention_mask, token_type_ids, item_position_ids,
+                position_ids=None, training: bool = False, save: bool = False) -> SavedActivations:
+        cfg, P = self.cfg, self.params
+        device = input_ids.device
+        P.ensure(device)
+        P.refresh_shadow(force=training and save)
+        B, L = input_ids.shape
+        Lp = self.window_pad(L)
+        E, H = cfg.hidden_size, cfg.num_attention_heads
+        sv = self._acquire(B, Lp, device, save)
+        sv.drop_hidden = float(cfg.hidden_dropout_prob) if training else 0.0
+        sv.drop_attn = float(cfg.attention_probs_dropout_prob) if training else 0.0
+        self._call += 1
+        sv.seed = (torch.initial_seed() * 2654435761 + self._call * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
+        err = self.err_flag(device)
+        pos, mask = ops.prepare_inputs(input_ids, attention_mask, global_attention_mask, Lp, cfg.pad_token_id, err)
+        if position_ids is not None:
+            pos = torch.nn.functional.pad(position_ids.to(torch.int32), (0, Lp - L), value=cfg.pad_token_id).contiguous()
+        sv.pos_ids, sv.mask012 = pos, mask
+        sv.inputs = (input_ids, token_type_ids, item_position_ids)
+        e = "embeddings."
+        ops.embed_ln_fwd(input_ids, token_type_ids, item_position_ids, pos,
+                         P.view(e + "word_embeddings.weight"), P.view(e + "position_embeddings.weight"),
+                         P.view(e + "token_type_embeddings.weight"), P.view(e + "item_position_embeddings.weight"),
+                         P.view(e + "LayerNorm.weight"), P.view(e + "LayerNorm.bias"), Lp, cfg.pad_token_id,
+                         cfg.layer_norm_eps, err, drop_p=sv.drop_hidden, drop_seed=self._seed(sv, -1, 0),
+                         out=sv.xin(0))
+        aw = cfg.attention_window
+        for i in range(cfg.num_hidden_layers):
+            W = self._layer_weights(i)
+            k = sv.idx(i)
+            x = sv.xin(i)
+            w_one = (aw if isinstance(aw, int) else aw[i]) // 2
+            ops.gemm(x, W["Wqkv"], out=sv.qkv[k], bias=W["bqkv"], scale=0.125, scale_ncols=E)
+            ops.band_attn_fwd(sv.qkv[k], mask, B, Lp, H, w_one, ctx=sv.ctx[k], lse=sv.lse[k], drop_p=sv.drop_attn,
+                              drop_seed=self._seed(sv, i, 1))
+            ops.global_attn_fwd(x, mask, W["Wqg"], W["bqg"], W["Wkg"], W["Wvg"], W["bvg"], B, Lp, H, sv.ctx[k],
+                                saved=sv.glob[k], drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 2))
+            ops.gemm(sv.ctx[k], W["Wo"], out=sv.pre1[k], bias=W["bo"], residual=x, drop_p=sv.drop_hidden,
+                     drop_seed=self._seed(sv, i, 3))
+            ops.layernorm_fwd(sv.pre1[k], W["ln1w"], W["ln1b"], cfg.layer_norm_eps, out=sv.h1[k], stats=sv.stats1[k])
+            ops.gemm(sv.h1[k], W["W1"], out=sv.u[k], bias=W["b1"], epi=ops.EPI_GELU, out2=sv.g[k])
+            ops.gemm(sv.g[k], W["W2"], out=sv.pre2[k], bias=W["b2"], residual=sv.h1[k], drop_p=sv.drop_hidden,
+                     drop_seed=self._seed(sv, i, 4))
+            ops.layernorm_fwd(sv.pre2[k], W["ln2w"], W["ln2b"], cfg.layer_norm_eps, out=sv.xout(i), stats=sv.stats2[k])
+        return sv
+
+    def hidden(self, sv: SavedActivations) -> torch.Tensor:
+        nl = self.cfg.num_hidden_layers
+        return sv.x[nl] if sv.per_layer else sv.x[nl % 2]
+
+    # -- backward ------------------------------------------------------------------------------
+    def backward(self, sv: SavedActivations, dout: torch.Tensor) -> None:
+        """dout: bf16 [B*Lp, E] gradient w.r.t. the final hidden states.  Accumulates into .grad."""
+        cfg, P = self.cfg, self.params
+        assert sv.per_layer, "forward was not run with save=True"
+        B, Lp = sv.B, sv.Lp
+        E, F, H = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
+        T = B * Lp
+        device = dout.device
+        P.prepare_grads()
+        key = (B, Lp, str(device))
+        sc = self._bwd.get(key)
+        if sc is None:
+            sc = self._bwd[key] = BackwardScratch(B, Lp, cfg, device)
+        mask = sv.mask012
+        pd = sv.drop_hidden
+        aw = cfg.attention_window
+        d_out = dout
+        for i in reversed(range(cfg.num_hidden_layers)):
+            W, G = self._layer_weights(i), self._layer_grads(i)
+            x = sv.x[i]
+            w_one = (aw if isinstance(aw, int) else aw[i]) // 2
+            # ---- output block: LN2 <- dense(W2) <- gelu <- dense(W1) ----
+            dpd = sc.d_pre_drop if pd > 0 else None
+            ops.layernorm_bwd(d_out, sv.pre2[i], sv.stats2[i], W["ln2w"], G["ln2w"], G["ln2b"], dx=sc.d_pre,
+                              dx_dropped=dpd, drop_p=pd, drop_seed=self._seed(sv, i, 4))
+            dY = sc.d_pre_drop if pd > 0 else sc.d_pre
+            ops.colsum(dY, G["b2"])
+            ops.gemm(dY, sv.g[i], out=G["W2"], a_mn_major=True, b_mn_major=True, accumulate=True,
+                     split_k=_pick_split(E, F, T))
+            ops.gemm(dY, W["W2"], out=sc.dU, b_mn_major=True, epi=ops.EPI_DGELU, aux=sv.u[i])
+            ops.colsum(sc.dU, G["b1"])
+            ops.gemm(sc.dU, sv.h1[i], out=G["W1"], a_mn_major=True, b_mn_major=True, accumulate=True,
+                     split_k=_pick_split(F, E, T))
+            ops.gemm(sc.dU, W["W1"], out=sc.dh1, b_mn_major=True, residual=sc.d_pre)
+            # ---- attention block: LN1 <- dense(Wo) <- attention <- dense(Wqkv) ----
+            ops.layernorm_bwd(sc.dh1, sv.pre1[i], sv.stats1[i], W["ln1w"], G["ln1w"], G["ln1b"], dx=sc.d_pre,
+                              dx_dropped=dpd, drop_p=pd, drop_seed=self._seed(sv, i, 3))
+            ops.colsum(dY, G["bo"])
+            ops.gemm(dY, sv.ctx[i], out=G["Wo"], a_mn_major=True, b_mn_major=True, accumulate=True,
+                     split_k=_pick_split(E, E, T))
+            ops.gemm(dY, W["Wo"], out=sc.dctx, b_mn_major=True)
+            ops.band_attn_bwd(sv.qkv[i], mask, B, Lp, H, w_one, sv.ctx[i], sv.lse[i], sc.dctx, sc.dqkv, sc.dkv,
+                              drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 1))
+            ops.colsum(sc.dqkv, G["bqkv"])
+            ops.gemm(sc.dqkv, x, out=G["Wqkv"], a_mn_major=True, b_mn_major=True, accumulate=True,
+                     split_k=_pick_split(3 * E, E, T))
+            dx = sc.dx[i % 2]
+            ops.gemm(sc.dqkv, W["Wqkv"], out=dx, b_mn_major=True, residual=sc.d_pre)
+            sc.gws = ops.global_attn_bwd(x, mask, W["Wqg"], W["bqg"], W["Wkg"], W["Wvg"], W["bvg"], B, Lp, H, sc.dctx,
+                                         sv.glob[i], dx, G["Wqg"], G["bqg"], G["Wkg"], G["Wvg"], G["bvg"], ws=sc.gws,
+                                         drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 2))
+            d_out = dx
+        e = "embeddings."
+        named = P._named
+        gview = lambda k: P.view(k, P.grad) if named[k].requires_grad else None
+        input_ids, token_type_ids, item_position_ids = sv.inputs
+        ops.embed_ln_bwd(d_out, input_ids, token_type_ids, item_position_ids, sv.pos_ids,
+                         P.view(e + "word_embeddings.weight"), P.view(e + "position_embeddings.weight"),
+                         P.view(e + "token_type_embeddings.weight"), P.view(e + "item_position_embeddings.weight"),
+                         P.view(e + "LayerNorm.weight"), P.view(e + "LayerNorm.bias"), Lp, cfg.pad_token_id,
+                         cfg.layer_norm_eps, gview(e + "word_embeddings.weight"),
+                         gview(e + "position_embeddings.weight"), gview(e + "token_type_embeddings.weight"),
+                         gview(e + "item_position_embeddings.weight"), gview(e + "LayerNorm.weight"),
+                         gview(e + "LayerNorm.bias"), drop_p=sv.drop_hidden, drop_seed=self._seed(sv, -1, 0))

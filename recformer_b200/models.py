@@ -1,0 +1,379 @@
+"""Drop-in replacements for the reference's hot-path classes (ref: recformer/models.py):
+RecformerModel (:174-356), RecformerForSeqRec (:524-599), Similarity (:358-369), with the same
+constructor, forward kwargs, outputs and `state_dict` keys, executed by the
+B200 kernels behind the C ABI (include/recformer_b200.h).  The module tree below only CARRIES
+parameters under the reference's names; all arithmetic is in recformer_b200/engine.py + csrc/.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .config import RecformerConfig
+from .engine import EncoderEngine
+
+
+# --------------------------------------------------------------------------------------------
+# output container (ref returns transformers' LongformerBaseModelOutputWithPooling)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class RecformerModelOutput:
+    last_hidden_state: torch.Tensor = None
+    pooler_output: torch.Tensor = None
+    hidden_states: Optional[Tuple[torch.Tensor]] = None
+    attentions: Optional[Tuple[torch.Tensor]] = None
+    global_attentions: Optional[Tuple[torch.Tensor]] = None
+
+    def to_tuple(self):
+        return tuple(v for v in (self.last_hidden_state, self.pooler_output, self.hidden_states, self.attentions,
+                                 self.global_attentions) if v is not None)
+
+    def __getitem__(self, k):
+        if isinstance(k, str):
+            return getattr(self, k)
+        return self.to_tuple()[k]
+
+
+# --------------------------------------------------------------------------------------------
+# parameter containers mirroring the reference / HF module names
+# --------------------------------------------------------------------------------------------
+class RecformerEmbeddings(nn.Module):
+    """ref: recformer/models.py:82-106 (forward is fused into rf_embed_ln_fwd)."""
+
+    def __init__(self, config: RecformerConfig):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(config.vocab_size, config.hidden_size, padding_idx=config.pad_token_id)
+        self.position_embeddings = nn.Embedding(config.max_position_embeddings, config.hidden_size,
+                                                padding_idx=config.pad_token_id)
+        self.token_type_embeddings = nn.Embedding(config.token_type_size, config.hidden_size)
+        self.item_position_embeddings = nn.Embedding(config.max_item_embeddings, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        self.register_buffer("position_ids", torch.arange(config.max_position_embeddings).expand((1, -1)))
+        self.padding_idx = config.pad_token_id
+
+
+class _SelfAttention(nn.Module):   # HF:445-466
+    def __init__(self, config):
+        super().__init__()
+        E = config.hidden_size
+        self.query, self.key, self.value = nn.Linear(E, E), nn.Linear(E, E), nn.Linear(E, E)
+        self.query_global, self.key_global, self.value_global = nn.Linear(E, E), nn.Linear(E, E), nn.Linear(E, E)
+
+
+class _SelfOutput(nn.Module):      # HF:1060-1066
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+
+
+class _Attention(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.self = _SelfAttention(config)
+        self.output = _SelfOutput(config)
+
+
+class _Intermediate(nn.Module):    # HF:1103-1111
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.intermediate_size)
+
+
+class _Output(nn.Module):          # HF:1119-1125
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.intermediate_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+
+
+class _Layer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.attention = _Attention(config)
+        self.intermediate = _Intermediate(config)
+        self.output = _Output(config)
+
+
+class _Encoder(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.layer = nn.ModuleList([_Layer(config) for _ in range(config.num_hidden_layers)])
+
+
+class RecformerPooler(nn.Module):
+    """ref: recformer/models.py:155-171."""
+
+    def __init__(self, config: RecformerConfig):
+        super().__init__()
+        self.pooler_type = config.pooler_type
+
+    def forward(self, attention_mask: torch.Tensor, hidden_states: torch.Tensor) -> torch.Tensor:
+        if self.pooler_type == "cls":
+            return hidden_states[:, 0]
+        if self.pooler_type == "avg":
+            am = attention_mask[:, : hidden_states.shape[1]].to(hidden_states.dtype)
+            return (hidden_states * am.unsqueeze(-1)).sum(1) / am.sum(-1).unsqueeze(-1)
+        raise NotImplementedError
+
+
+def _init_weights(module: nn.Module, std: float):
+    """HF PreTrainedModel._init_weights for the module kinds used here."""
+    if isinstance(module, nn.Linear):
+        module.weight.data.normal_(mean=0.0, std=std)
+        if module.bias is not None:
+            module.bias.data.zero_()
+    elif isinstance(module, nn.Embedding):
+        module.weight.data.normal_(mean=0.0, std=std)
+        if module.padding_idx is not None:
+            module.weight.data[module.padding_idx].zero_()
+    elif isinstance(module, nn.LayerNorm):
+        module.bias.data.zero_()
+        module.weight.data.fill_(1.0)
+
+
+# --------------------------------------------------------------------------------------------
+# autograd bridge: one Function for the whole encoder
+# --------------------------------------------------------------------------------------------
+class _EncoderFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hook, model, L, inputs):
+        eng = model._engine
+        sv = eng.forward(*inputs, training=model.training, save=True)
+        B, Lp, E = sv.B, sv.Lp, model.config.hidden_size
+        hidden = eng.hidden(sv).view(B, Lp, E)[:, :L].float()
+        ctx.model, ctx.sv, ctx.L = model, sv, L
+        return hidden
+
+    @staticmethod
+    def backward(ctx, d_hidden):
+        model, sv = ctx.model, ctx.sv
+        eng = model._engine
+        B, Lp, E = sv.B, sv.Lp, model.config.hidden_size
+        dout = torch.zeros(B, Lp, E, dtype=torch.bfloat16, device=d_hidden.device)
+        dout[:, : ctx.L] = d_hidden
+        eng.backward(sv, dout.view(B * Lp, E))
+        eng.release(sv)
+        ctx.sv = None
+        return None, None, None, None
+
+
+class RecformerModel(nn.Module):
+    """ref: recformer/models.py:174-356 — same constructor checks, forward kwargs and outputs."""
+
+    def __init__(self, config: RecformerConfig):
+        super().__init__()
+        self.config = config
+        if isinstance(config.attention_window, int):
+            assert config.attention_window % 2 == 0, "`config.attention_window` has to be an even value"
+            assert config.attention_window > 0, "`config.attention_window` has to be positive"
+            config.attention_window = [config.attention_window] * config.num_hidden_layers
+        else:
+            assert len(config.attention_window) == config.num_hidden_layers, (
+                "`len(config.attention_window)` should equal `config.num_hidden_layers`. "
+                f"Expected {config.num_hidden_layers}, given {len(config.attention_window)}")
+        if config.hidden_size != 768 or config.num_attention_heads != 12:
+            raise NotImplementedError("recformer_b200 kernels are built for the longformer-base shape "
+                                      "(hidden 768, 12 heads of 64)")
+        self.embeddings = RecformerEmbeddings(config)
+        self.encoder = _Encoder(config)
+        self.pooler = RecformerPooler(config)
+        self.apply(lambda m: _init_weights(m, config.initializer_range))
+        # not parameters / buffers: the engine and the autograd hook stay out of state_dict
+        object.__setattr__(self, "_engine", EncoderEngine(self))
+        object.__setattr__(self, "_hook", None)
+        self.strict_checks = True
+
+    # HF-compatible accessors used by the reference scripts (finetune.py:272-275)
+    def get_input_embeddings(self):
+        return self.embeddings.word_embeddings
+
+    def set_input_embeddings(self, value):
+        self.embeddings.word_embeddings = value
+
+    def named_parameters(self, *a, **kw):   # engine views must see the module's own parameters
+        return super().named_parameters(*a, **kw)
+
+    def _grad_hook(self, device):
+        if self._hook is None or self._hook.device != torch.device(device):
+            object.__setattr__(self, "_hook", torch.zeros(1, device=device, requires_grad=True))
+        return self._hook
+
+    def forward(self,
+                input_ids: Optional[torch.Tensor] = None,
+                attention_mask: Optional[torch.Tensor] = None,
+                global_attention_mask: Optional[torch.Tensor] = None,
+                head_mask: Optional[torch.Tensor] = None,
+                token_type_ids: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.Tensor] = None,
+                item_position_ids: Optional[torch.Tensor] = None,
+                inputs_embeds: Optional[torch.Tensor] = None,
+                output_attentions: Optional[bool] = None,
+                output_hidden_states: Optional[bool] = None,
+                return_dict: Optional[bool] = None):
+        return_dict = return_dict if return_dict is not None else self.config.use_return_dict
+        if input_ids is not None and inputs_embeds is not None:
+            raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
+        if input_ids is None and inputs_embeds is None:
+            raise ValueError("You have to specify either input_ids or inputs_embeds")
+        if inputs_embeds is not None:
+            raise NotImplementedError("recformer_b200: inputs_embeds is not on the accelerated path")
+        if head_mask is not None:
+            raise NotImplementedError("recformer_b200: head_mask is not supported (the reference never sets it)")
+        if output_attentions or output_hidden_states:
+            raise NotImplementedError("recformer_b200: attention maps / per-layer states are never materialised")
+        if not input_ids.is_cuda:
+            raise RuntimeError("recformer_b200 runs on CUDA only (no CPU fallback): move inputs to the GPU")
+        B, L = input_ids.shape
+        if item_position_ids is None:
+            raise ValueError("item_position_ids is required (ref: recformer/models.py:132 indexes it unconditionally)")
+        to64 = lambda t: None if t is None else t.to(torch.int64).contiguous()
+        inputs = (to64(input_ids), to64(attention_mask), to64(global_attention_mask), to64(token_type_ids),
+                  to64(item_position_ids), to64(position_ids))
+        eng = self._engine
+        E = self.config.hidden_size
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if needs_grad:
+            hidden = _EncoderFunction.apply(self._grad_hook(input_ids.device), self, L, inputs)
+        else:
+            sv = eng.forward(*inputs, training=self.training, save=False)
+            hidden = eng.hidden(sv).view(B, sv.Lp, E)[:, :L].float()
+            eng.release(sv)
+        if self.strict_checks:
+            eng.check_errors()
+        merged = None
+        if self.pooler.pooler_type != "cls":
+            am = attention_mask if attention_mask is not None else torch.ones_like(input_ids)
+            merged = am * (global_attention_mask + 1) if global_attention_mask is not None else am
+        pooled = self.pooler(merged, hidden)
+        if not return_dict:
+            return (hidden, pooled)
+        return RecformerModelOutput(last_hidden_state=hidden, pooler_output=pooled)
+
+    # raw bf16 access for fused consumers (scoring) that do not need fp32 copies
+    def encode_pooled_bf16(self, **batch) -> torch.Tensor:
+        """CLS vectors as bf16 [B,E] without materialising fp32 hidden states (inference only)."""
+        eng = self._engine
+        to64 = lambda t: None if t is None else t.to(torch.int64).contiguous()
+        ids = batch["input_ids"]
+        sv = eng.forward(to64(ids), to64(batch.get("attention_mask")), to64(batch.get("global_attention_mask")),
+                         to64(batch.get("token_type_ids")), to64(batch["item_position_ids"]),
+                         to64(batch.get("position_ids")), training=False, save=False)
+        pooled = eng.hidden(sv).view(sv.B, sv.Lp, -1)[:, 0].contiguous()
+        eng.release(sv)
+        return pooled
+
+
+# --------------------------------------------------------------------------------------------
+# scoring
+# --------------------------------------------------------------------------------------------
+class _CosineCEFunction(torch.autograd.Function):
+    """loss = CE(cos(pooled, items)/temp, labels) with the table pre-normalised (Spec S)."""
+
+    @staticmethod
+    def forward(ctx, pooled, yn, labels, temp):
+        loss, dpooled = ops.cosine_ce(pooled.contiguous(), yn, labels, temp, want_grad=True)
+        ctx.save_for_backward(dpooled)
+        return loss.squeeze(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dpooled,) = ctx.saved_tensors
+        return dpooled * g, None, None, None
+
+
+class Similarity(nn.Module):
+    """ref: recformer/models.py:358-369 — cos(x, y) / temp on broadcastable (B,1,E) x (1|B,N,E)."""
+
+    def __init__(self, config: RecformerConfig):
+        super().__init__()
+        self.temp = config.temp
+
+    def forward(self, x, y):
+        if x.dim() == 3 and x.shape[1] == 1 and y.dim() == 3 and y.shape[0] == 1:
+            xn = ops.normalize_rows(x[:, 0].contiguous())
+            yn = ops.normalize_rows(y[0].contiguous())
+            return ops.cosine_logits(xn, yn, self.temp)
+        xn = x / x.norm(dim=-1, keepdim=True).clamp_min(1e-8)
+        yn = y / y.norm(dim=-1, keepdim=True).clamp_min(1e-8)
+        return (xn * yn).sum(-1) / self.temp
+
+
+class RecformerForSeqRec(nn.Module):
+    """ref: recformer/models.py:524-599."""
+
+    def __init__(self, config: RecformerConfig):
+        super().__init__()
+        self.config = config
+        self.longformer = RecformerModel(config)
+        self.sim = Similarity(config)
+        object.__setattr__(self, "_yn", None)      # cached L2-normalised bf16 table
+        object.__setattr__(self, "_yn_sig", None)
+
+    def init_item_embedding(self, embeddings: Optional[torch.Tensor] = None):
+        self.item_embedding = nn.Embedding(num_embeddings=self.config.item_num, embedding_dim=self.config.hidden_size)
+        if embeddings is not None:
+            self.item_embedding = nn.Embedding.from_pretrained(embeddings, freeze=True)
+            print("Initalize item embeddings from vectors.")
+        object.__setattr__(self, "_yn_sig", None)
+
+    def normalized_items(self) -> torch.Tensor:
+        """bf16 L2-normalised copy of the (frozen) item table, rebuilt only when the table changes."""
+        w = self.item_embedding.weight
+        sig = (w.data_ptr(), w._version, tuple(w.shape), str(w.device))
+        if self._yn is None or self._yn_sig != sig:
+            object.__setattr__(self, "_yn", ops.normalize_rows(w.detach().contiguous()))
+            object.__setattr__(self, "_yn_sig", sig)
+        return self._yn
+
+    def similarity_score(self, pooler_output, candidates=None):
+        if candidates is None:
+            xn = ops.normalize_rows(pooler_output.detach().contiguous())
+            return ops.cosine_logits(xn, self.normalized_items(), self.config.temp)
+        candidate_embeddings = self.item_embedding(candidates)       # (B, C, E) gather (torch plumbing)
+        return self.sim(pooler_output.unsqueeze(1), candidate_embeddings)
+
+    @torch.no_grad()
+    def topk(self, pooler_output, k: int = 10, labels: Optional[torch.Tensor] = None, id_base: int = 0):
+        """Fused full-catalogue scoring + top-k (the (B,N) logits are never written)."""
+        xn = ops.normalize_rows(pooler_output.contiguous())
+        return ops.cosine_topk(xn, self.normalized_items(), self.config.temp, k=k, id_base=id_base, labels=labels)
+
+    def forward(self,
+                input_ids: Optional[torch.Tensor] = None,
+                attention_mask: Optional[torch.Tensor] = None,
+                global_attention_mask: Optional[torch.Tensor] = None,
+                head_mask: Optional[torch.Tensor] = None,
+                token_type_ids: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.Tensor] = None,
+                item_position_ids: Optional[torch.Tensor] = None,
+                inputs_embeds: Optional[torch.Tensor] = None,
+                output_attentions: Optional[bool] = None,
+                output_hidden_states: Optional[bool] = None,
+                return_dict: Optional[bool] = None,
+                candidates: Optional[torch.Tensor] = None,
+                labels: Optional[torch.Tensor] = None):
+        batch_size = input_ids.size(0)
+        outputs = self.longformer(input_ids, attention_mask=attention_mask,
+                                  global_attention_mask=global_attention_mask, head_mask=head_mask,
+                                  token_type_ids=token_type_ids, position_ids=position_ids,
+                                  item_position_ids=item_position_ids, inputs_embeds=inputs_embeds,
+                                  output_attentions=output_attentions, output_hidden_states=output_hidden_states,
+                                  return_dict=True)
+        pooler_output = outputs.pooler_output
+        if labels is None:
+            return self.similarity_score(pooler_output, candidates)
+        if self.config.finetune_negative_sample_size <= 0:      # full softmax
+            return _CosineCEFunction.apply(pooler_output, self.normalized_items(), labels.to(torch.int64).contiguous(),
+                                           self.config.temp)
+        # sampled softmax (ref: :593-597) — negatives drawn on the device instead of CPU + H2D
+        neg = torch.randint(0, self.config.item_num, (batch_size, self.config.finetune_negative_sample_size),
+                            device=labels.device)
+        cand = torch.cat((labels.unsqueeze(-1), neg), dim=-1)
+        logits = self.similarity_score(pooler_output, cand)
+        return nn.functional.cross_entropy(logits, torch.zeros_like(labels))

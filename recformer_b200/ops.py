@@ -281,3 +281,17 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, shadow, lr, beta1, beta2, eps, 
     check(_lib.lib().rf_adamw_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                    _ptr(shadow), param.numel(), lr, beta1, beta2, eps, weight_decay, step, grad_scale,
                                    _stream()), "rf_adamw_step")
+
+
+def global_attn_bwd(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, dctx, saved, dx, dWqg, dbqg, dWkg, dWvg, dbvg,
+                    ws=None, drop_p=0.0, drop_seed=0):
+    """Adds the CLS row's dense gradient into dx (bf16 [B*L,E]) and accumulates the *_global weight grads."""
+    nbytes = int(_lib.lib().rf_global_attn_bwd_ws_bytes(B, L, H))
+    if ws is None or ws.numel() * ws.element_size() < nbytes:
+        ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=x.device)
+    a = _global_args(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, drop_p, drop_seed)
+    check(_lib.lib().rf_global_attn_bwd(C.byref(a), dctx.data_ptr(), saved["qg"].data_ptr(), saved["u"].data_ptr(),
+                                        saved["p"].data_ptr(), saved["mvec"].data_ptr(), saved["psum"].data_ptr(),
+                                        dx.data_ptr(), _ptr(dWqg), _ptr(dbqg), _ptr(dWkg), _ptr(dWvg), _ptr(dbvg),
+                                        ws.data_ptr(), _stream()), "rf_global_attn_bwd")
+    return ws

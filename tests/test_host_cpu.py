@@ -1,0 +1,158 @@
+"""CPU-only tests of the host-side logic and of the C-ABI boundary (no compute calls)."""
+import copy
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import recformer_b200 as rb
+from recformer_b200 import _lib
+from recformer_b200.engine import FlatParams, _pick_split
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "recformer_b200.h")).read()
+    declared = set(re.findall(r"\b(rf_[a-z0-9_]+)\s*\(", header))
+    declared -= {"rf_stream_t"}
+    assert len(declared) >= 24
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(handle, name), f"{name} declared in include/recformer_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    lib = _lib.lib()
+    assert lib.rf_version() >= 100
+    assert lib.rf_launch_count() == 0
+
+
+def test_argument_validation_errors_without_gpu():
+    lib = _lib.lib()
+    a = _lib.GemmArgs()
+    assert lib.rf_gemm_bf16(ctypes.byref(a), None) == -1
+    assert b"empty problem" in lib.rf_last_error()
+    assert lib.rf_normalize_rows(None, 0, None, None, 10, 768, None) == -1
+    assert lib.rf_cosine_topk(None, None, 1, 1, 768, 0.05, 10, 0, None, None, None, None, None, None) == -1
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/librecformer_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.lib()
+
+
+def test_cpu_inputs_are_rejected_not_emulated():
+    cfg = rb.RecformerConfig(attention_window=[64], vocab_size=100, num_hidden_layers=1, max_position_embeddings=80)
+    m = rb.RecformerModel(cfg)
+    ids = torch.zeros(1, 8, dtype=torch.long)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(input_ids=ids, item_position_ids=ids)
+
+
+def test_config_defaults_match_reference():
+    cfg = rb.RecformerConfig()
+    # ref: recformer/models.py:26-38
+    assert (cfg.token_type_size, cfg.max_token_num, cfg.max_item_embeddings, cfg.max_attr_num, cfg.max_attr_length,
+            cfg.pooler_type, cfg.temp, cfg.mlm_weight, cfg.item_num, cfg.finetune_negative_sample_size) == \
+           (4, 2048, 32, 12, 8, "cls", 0.05, 0.1, 0, 0)
+    base = rb.RecformerConfig.from_pretrained("allenai/longformer-base-4096")
+    assert (base.vocab_size, base.hidden_size, base.num_hidden_layers, base.max_position_embeddings) == (50265, 768, 12, 4098)
+    assert base.attention_window == [512] * 12
+    with pytest.raises(OSError):
+        rb.RecformerConfig.from_pretrained("some/unknown-model")
+
+
+def test_config_roundtrip(tmp_path):
+    cfg = rb.RecformerConfig(attention_window=[64] * 12, max_token_num=1024, max_item_embeddings=51)
+    cfg.save_pretrained(str(tmp_path))
+    back = rb.RecformerConfig.from_pretrained(str(tmp_path))
+    assert back.attention_window == [64] * 12 and back.max_token_num == 1024 and back.max_item_embeddings == 51
+
+
+def test_constructor_asserts_like_reference():
+    with pytest.raises(AssertionError):
+        rb.RecformerModel(rb.RecformerConfig(attention_window=[64, 64], num_hidden_layers=3, vocab_size=50,
+                                             max_position_embeddings=70))
+    with pytest.raises(AssertionError):
+        rb.RecformerModel(rb.RecformerConfig(attention_window=63, num_hidden_layers=1, vocab_size=50,
+                                             max_position_embeddings=70))
+    cfg = rb.RecformerConfig(attention_window=64, num_hidden_layers=2, vocab_size=50, max_position_embeddings=70)
+    rb.RecformerModel(cfg)
+    assert cfg.attention_window == [64, 64]
+    m = rb.RecformerModel(rb.RecformerConfig(attention_window=64, num_hidden_layers=1, vocab_size=50,
+                                             max_position_embeddings=70, pooler_type="max"))
+    with pytest.raises(NotImplementedError):
+        m.pooler(None, torch.zeros(1, 2, 768))
+
+
+def test_state_dict_keys_match_reference_layout():
+    from oracle import recformer_oracle as O
+    ocfg = O.OracleConfig(vocab_size=60, num_hidden_layers=2, attention_window=[64, 64], max_position_embeddings=70)
+    cfg = rb.RecformerConfig(attention_window=[64, 64], vocab_size=60, num_hidden_layers=2, max_position_embeddings=70,
+                             max_item_embeddings=51)
+    m = rb.RecformerForSeqRec(cfg)
+    want = {k for k, _, _ in O.state_dict_keys(ocfg, "longformer.")} | {"longformer.embeddings.position_ids"}
+    assert set(m.state_dict().keys()) == want
+    m.init_item_embedding(torch.zeros(5, 768))
+    assert "item_embedding.weight" in m.state_dict() and not m.item_embedding.weight.requires_grad
+    # padding rows are zero-initialised like HF's _init_weights
+    assert m.longformer.embeddings.word_embeddings.weight[1].abs().sum() == 0
+    assert m.longformer.get_input_embeddings() is m.longformer.embeddings.word_embeddings
+
+
+def test_flat_parameter_plan():
+    cfg = rb.RecformerConfig(attention_window=[64, 64], vocab_size=60, num_hidden_layers=2, max_position_embeddings=70,
+                             max_item_embeddings=51)
+    m = rb.RecformerModel(cfg)
+    fp: FlatParams = m._engine.params
+    assert fp.n_total == sum(p.numel() for p in m.parameters())
+    o = fp.offsets
+    p = "encoder.layer.1.attention.self."
+    assert o[p + "key.weight"] - o[p + "query.weight"] == 768 * 768          # fused QKV weight is contiguous
+    assert o[p + "value.weight"] - o[p + "key.weight"] == 768 * 768
+    assert o[p + "key.bias"] - o[p + "query.bias"] == 768
+    assert fp.n_dense == 2 * (4 * 768 * 768 + 2 * 768 * 3072) and fp.n_dense < fp.n_decay < fp.n_total
+    assert all(v % 8 == 0 for v in o.values())
+
+
+def test_split_k_heuristic():
+    assert _pick_split(2304, 768, 16384) >= 2       # 108 tiles on 148 SMs -> split
+    assert _pick_split(768, 768, 128) == 1           # too few K blocks to split
+    assert 1 <= _pick_split(3072, 768, 16384) <= 8
+
+
+def test_tokenizer_layout_matches_reference(goldens):
+    g = goldens["tokenizer"]
+    cfg = rb.RecformerConfig(max_token_num=1024, max_item_embeddings=51, max_attr_num=3, max_attr_length=32)
+    tok = rb.RecformerTokenizer.from_pretrained("allenai/longformer-base-4096", cfg)
+    assert tok.batch_encode(copy.deepcopy(g["users"]), encode_item=False, pad_to_max=False) == g["batch"]
+    assert tok.batch_encode(copy.deepcopy(g["users"]), encode_item=False, pad_to_max=True) == g["batch_pad_to_max"]
+    # SURVEY §8a example
+    tok2 = rb.RecformerTokenizer(rb.RecformerConfig(max_token_num=1024, max_item_embeddings=51))
+    out = tok2.batch_encode([[([10, 11, 12, 13], [1, 2, 2, 2]), ([20, 21, 22], [1, 2, 2])], [([30, 31], [1, 2])]],
+                            encode_item=False)
+    assert out["input_ids"] == [[0, 20, 21, 22, 10, 11, 12, 13], [0, 30, 31, 1, 1, 1, 1, 1]]
+    assert out["item_position_ids"] == [[0, 1, 1, 1, 2, 2, 2, 2], [0, 1, 1, 50, 50, 50, 50, 50]]
+    assert out["global_attention_mask"][0] == [1, 0, 0, 0, 0, 0, 0, 0]
+    # attribute text path with a pluggable text tokenizer (ref: tokenization.py:38-61)
+    tok3 = rb.RecformerTokenizer(rb.RecformerConfig(max_attr_num=2, max_attr_length=3),
+                                 text_tokenizer=lambda s: [ord(c) for c in s])
+    ids, tts = tok3.encode_item({"ab": "cde", "f": "g", "dropped": "x"})
+    assert ids == [97, 98, 99, 102, 103] and tts == [1, 1, 2, 1, 2]
+    t = tok3([[{"a": "b"}], [{"c": "de"}, {"f": "g"}]], return_tensor=True)   # __call__ encodes item dicts
+    assert t["input_ids"].dtype == torch.int64 and t["input_ids"].tolist() == [[0, 97, 98, 1, 1, 1], [0, 102, 103, 99, 100, 101]]
+
+
+def test_ranker_and_topk_ranker_match_reference(goldens):
+    for g in goldens["ranker"]:
+        s = g["scores"].float()
+        got = rb.Ranker([10, 50])(s, g["labels"])
+        assert np.allclose(got, g["metrics"], atol=1e-6)
+        lab = g["labels"].reshape(-1)
+        top = torch.topk(s, 50, dim=-1).values
+        tk = rb.TopKRanker([10, 50])(top, s[torch.arange(s.shape[0]), lab])
+        assert np.allclose(tk, g["metrics"][:4], atol=1e-6)

@@ -1,0 +1,174 @@
+"""Model-level parity on a B200: the drop-in classes against the golden fixtures produced by the
+unmodified reference, and against the CPU oracle (forward, loss and gradients)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import recformer_oracle as O
+
+if torch.cuda.is_available():
+    import recformer_b200 as rb
+
+DEV = "cuda"
+LOGIT_TOL = 2e-2     # north_star: logits within 2e-2 max-abs (bf16 path vs fp32 reference)
+
+
+def build(cfg_kw, sd_seed=0, N=None, seqrec=True):
+    ocfg = O.OracleConfig(**cfg_kw)
+    kw = dict(vocab_size=ocfg.vocab_size, num_hidden_layers=ocfg.num_hidden_layers,
+              max_position_embeddings=ocfg.max_position_embeddings, max_token_num=ocfg.max_token_num,
+              max_item_embeddings=ocfg.max_item_embeddings, max_attr_num=3, max_attr_length=32)
+    cfg = rb.RecformerConfig(attention_window=list(ocfg.attention_window), **kw)
+    sd = O.make_state_dict(ocfg, seed=sd_seed, prefix="longformer." if seqrec else "")
+    model = rb.RecformerForSeqRec(cfg) if seqrec else rb.RecformerModel(cfg)
+    missing, unexpected = model.load_state_dict(sd, strict=True) if True else (None, None)
+    model = model.to(DEV)
+    return ocfg, cfg, model, sd
+
+
+FWD = ["fwd_small_ragged", "fwd_small_dense", "fwd_small_short", "fwd_window_128", "fwd_window_256", "fwd_c1_full",
+       "fwd_c1_ragged"]
+
+
+@pytest.mark.parametrize("name", FWD)
+def test_forward_matches_reference_goldens(goldens, name):
+    g = goldens[name]
+    ocfg, cfg, model, sd = build(g["cfg"], g["sd_seed"])
+    model.eval()
+    batch = {k: v.to(DEV) for k, v in O.make_batch(ocfg, g["B"], g["L"], seed=g["batch_seed"], ragged=g["ragged"]).items()}
+    items = O.make_item_table(g["N"], 768, seed=1).to(DEV)
+    cfg.item_num = g["N"]
+    model.init_item_embedding(items)
+    with torch.no_grad():
+        out = model.longformer(**batch)
+        logits = model(**batch)
+    assert out.last_hidden_state.shape == (g["B"], g["L"], 768)
+    herr = (out.last_hidden_state[:, :: g["hidden_stride"]].cpu() - g["last_hidden_sample"]).abs().max().item()
+    perr = (out.pooler_output.cpu() - g["pooler_output"]).abs().max().item()
+    lerr = (logits.cpu() - g["logits"]).abs().max().item()
+    print(f"{name}: hidden {herr:.4f} pooled {perr:.4f} logits {lerr:.4f}")
+    assert lerr < LOGIT_TOL, lerr
+    assert perr < 0.1 and herr < 0.15
+    # top-10 ids bit-exact wherever the reference's score gap exceeds the tolerance
+    ref = g["logits"]
+    rs, ri = torch.topk(ref, 11, dim=-1)
+    ts, ti, _ = model.topk(out.pooler_output, k=10)
+    ti = ti.cpu().long()
+    for b in range(ref.shape[0]):
+        for r in range(10):
+            gap_ok = (r == 0 or rs[b, r - 1] - rs[b, r] > 2 * LOGIT_TOL) and rs[b, r] - rs[b, r + 1] > 2 * LOGIT_TOL
+            if gap_ok:
+                assert ti[b, r] == ri[b, r], (b, r)
+
+
+def test_recall_ndcg_match_reference_ranker(goldens):
+    g = goldens["fwd_c1_full"]
+    ocfg, cfg, model, sd = build(g["cfg"], g["sd_seed"])
+    model.eval()
+    batch = {k: v.to(DEV) for k, v in O.make_batch(ocfg, g["B"], g["L"], seed=g["batch_seed"], ragged=g["ragged"]).items()}
+    items = O.make_item_table(g["N"], 768, seed=1).to(DEV)
+    model.init_item_embedding(items)
+    ref = g["logits"]
+    # labels chosen inside the reference's own top-20 so that the metrics are non-trivial
+    labels = torch.topk(ref, 20, dim=-1).indices[torch.arange(ref.shape[0]), torch.arange(ref.shape[0]) * 2 % 20]
+    want = O.ranker(ref, labels, ks=(10,))
+    with torch.no_grad():
+        pooled = model.longformer(**batch).pooler_output
+        ts, ti, ls = model.topk(pooled, k=10, labels=labels.to(DEV))
+    got = rb.TopKRanker([10])(ts, ls)
+    assert round(got[0], 4) == round(want[0], 4) and round(got[1], 4) == round(want[1], 4), (got, want[:2])
+
+
+def test_train_step_matches_reference_gradients(goldens):
+    g = goldens["train_small"]
+    ocfg, cfg, model, sd = build(g["cfg"], g["sd_seed"])
+    cfg.hidden_dropout_prob = 0.0
+    cfg.attention_probs_dropout_prob = 0.0
+    model.train()
+    batch = {k: v.to(DEV) for k, v in O.make_batch(ocfg, g["B"], g["L"], seed=g["batch_seed"], ragged=True).items()}
+    items = O.make_item_table(g["N"], 768, seed=1).to(DEV)
+    model.init_item_embedding(items)
+    loss = model(**batch, labels=g["labels"].to(DEV))
+    assert abs(loss.item() - g["loss"]) < 2e-2, (loss.item(), g["loss"])
+    loss.backward()
+    named = dict(model.named_parameters())
+    worst = 0.0
+    for k, ref in g["grads"].items():
+        p = named[k]
+        if ref["norm"] < 1e-6:
+            continue
+        assert p.grad is not None, k
+        gn = p.grad.norm().item()
+        rel = abs(gn - ref["norm"]) / ref["norm"]
+        head = (p.grad.reshape(-1)[:32].cpu() - ref["head"]).abs().max().item() / (ref["head"].abs().max().item() + 1e-6 * ref["norm"] + 1e-12)
+        worst = max(worst, rel)
+        assert rel < 0.05, (k, gn, ref["norm"])
+        if "full" in ref:
+            err = (p.grad.cpu() - ref["full"]).abs().max().item() / (ref["full"].abs().max().item() + 1e-12)
+            assert err < 0.08, (k, err)
+    print("worst relative grad-norm error", worst)
+
+
+def test_train_gradients_match_oracle_autograd_dense():
+    """Full gradient tensors against the oracle's autograd (1 layer, every parameter)."""
+    cfg_kw = dict(vocab_size=1500, num_hidden_layers=1, attention_window=[64], max_position_embeddings=600)
+    ocfg, cfg, model, sd = build(cfg_kw, sd_seed=5)
+    cfg.hidden_dropout_prob = 0.0
+    cfg.attention_probs_dropout_prob = 0.0
+    model.train()
+    B, L, N = 3, 300, 40
+    batch = O.make_batch(ocfg, B, L, seed=2, ragged=True)
+    items = O.make_item_table(N, 768, seed=1)
+    labels = torch.tensor([3, 17, 39])
+    for v in sd.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    ref_loss = O.seqrec_forward(sd, ocfg, batch, items, labels=labels)
+    ref_loss.backward()
+    model.init_item_embedding(items.to(DEV))
+    loss = model(**{k: v.to(DEV) for k, v in batch.items()}, labels=labels.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 2e-2
+    named = dict(model.named_parameters())
+    for k, p in named.items():
+        if k == "item_embedding.weight":
+            continue
+        rg = sd[k].grad
+        if rg is None or rg.abs().max() < 1e-9:
+            continue
+        err = (p.grad.cpu() - rg).abs().max().item() / rg.abs().max().item()
+        assert err < 0.06, (k, err)
+
+
+def test_state_dict_keys_and_api_errors():
+    ocfg, cfg, model, sd = build(dict(vocab_size=1500, num_hidden_layers=1, attention_window=[64],
+                                      max_position_embeddings=600), seqrec=False)
+    keys = set(model.state_dict().keys())
+    assert keys == set(sd.keys())
+    with pytest.raises(ValueError):
+        model(input_ids=None)
+    ids = torch.zeros(1, 8, dtype=torch.long, device=DEV)
+    with pytest.raises(ValueError):
+        model(input_ids=ids, inputs_embeds=torch.zeros(1, 8, 768, device=DEV))
+    gm = torch.zeros(1, 64, dtype=torch.long, device=DEV)
+    gm[0, 3] = 1
+    ids = torch.full((1, 64), 5, dtype=torch.long, device=DEV)
+    with pytest.raises(ValueError):
+        model(input_ids=ids, attention_mask=torch.ones_like(ids), global_attention_mask=gm,
+              token_type_ids=torch.zeros_like(ids), item_position_ids=torch.zeros_like(ids))
+
+
+def test_dropout_training_runs_and_is_stochastic():
+    ocfg, cfg, model, sd = build(dict(vocab_size=1500, num_hidden_layers=2, attention_window=[64, 64],
+                                      max_position_embeddings=600))
+    model.train()
+    batch = {k: v.to(DEV) for k, v in O.make_batch(ocfg, 2, 256, seed=2, ragged=True).items()}
+    model.init_item_embedding(O.make_item_table(50, 768, seed=1).to(DEV))
+    labels = torch.tensor([1, 2], device=DEV)
+    l1 = model(**batch, labels=labels)
+    l1.backward()
+    l2 = model(**batch, labels=labels)
+    assert torch.isfinite(l1) and torch.isfinite(l2) and l1.item() != l2.item()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
