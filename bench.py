@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Headline benchmark of the Recformer encoder + scoring hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workloads (BASELINE.json):
+  * primary line = configs[1], the finetune step: RecformerForSeqRec fwd + full-softmax CE over
+    5k items + bwd + AdamW on B=16/GPU Industrial-shaped ragged sequences of 1024 tokens,
+    train mode (dropout 0.1), bf16 tensor-core operands.  metric: train seqs/sec.
+  * "secondary" object in the same JSON line = configs[3], full-catalogue eval: 4096 users x 1M
+    items (sharded over the N GPUs), fused cosine top-10 + all-gather merge.  metric: users/sec.
+`--impl reference` times the CPU oracle port of the reference (the reference is pure Python and
+cannot travel to the GPU box) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "train seqs/sec fwd+bwd @1024 tok"
+UNIT = "seqs/s"
+B_PER_GPU = 16
+SEQ_LEN = 1024
+N_ITEMS = 5000
+EVAL_USERS = 4096
+EVAL_ITEMS = 1_000_000
+E, NL, F = 768, 12, 3072
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d["bf16_tflops_sustained"], "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def algorithmic_gemm_flops_per_seq(L=SEQ_LEN):
+    """Dense projections only (Q,K,V,out,FFN), fwd + dgrad + wgrad = 3x fwd; the reference's
+    key_global/value_global GEMMs are re-associated away and not counted."""
+    per_token_layer = 2 * E * E * 4 + 2 * 2 * E * F
+    return 3 * per_token_layer * NL * L
+
+
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_finetune_step_rate(n_seqs: int, steps: int, warmup: int):
+    """Oracle (CPU port of the reference) finetune step on `n_seqs` sequences of the C2 workload."""
+    from oracle import recformer_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    ocfg = O.OracleConfig()
+    sd = O.make_state_dict(ocfg, seed=0, prefix="longformer.")
+    params = [v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point()]
+    opt = torch.optim.AdamW(params, lr=5e-5)
+    items = O.make_item_table(N_ITEMS, E, seed=1)
+    times = []
+    for it in range(warmup + steps):
+        batch = O.make_batch(ocfg, n_seqs, SEQ_LEN, seed=100 + it, ragged=True)
+        labels = torch.randint(0, N_ITEMS, (n_seqs,))
+        t0 = time.perf_counter()
+        loss = O.seqrec_forward(sd, ocfg, batch, items, labels=labels)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return n_seqs * len(times) / total, 1000.0 * total / len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 1 if (args.steps + args.warmup) > 12 else 2
+    rate, ms, cores = cpu_finetune_step_rate(n, args.steps, args.warmup)
+    sample = f"{n} of {B_PER_GPU} sequences x {SEQ_LEN} tokens per step, fwd+CE(5k items)+bwd+AdamW, fp32 torch CPU"
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "finetune step (BASELINE configs[1]): RecformerForSeqRec longformer-base shape, "
+                                   "B=16/GPU x 1024 tok ragged, window 64, CE over 5k items, AdamW",
+                       "reference_arm": "CPU oracle port of the reference (oracle/recformer_oracle.py); the Python "
+                                        "reference itself cannot travel to the GPU box"},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def build_model(device):
+    import recformer_b200 as rb
+    from oracle import recformer_oracle as O   # synthetic weights / batches only (shared generators)
+    cfg = rb.RecformerConfig(attention_window=[64] * NL, max_token_num=SEQ_LEN, max_item_embeddings=51,
+                             max_attr_num=3, max_attr_length=32, item_num=N_ITEMS)
+    model = rb.RecformerForSeqRec(cfg)
+    sd = O.make_state_dict(O.OracleConfig(), seed=0, prefix="longformer.")
+    model.load_state_dict(sd, strict=True)
+    model = model.to(device)
+    model.init_item_embedding(O.make_item_table(N_ITEMS, E, seed=1).to(device))
+    model.longformer.strict_checks = False     # device-side input validation stays on; no per-step host sync
+    return model, cfg
+
+
+def make_batches(n, device, rank):
+    from oracle import recformer_oracle as O
+    ocfg = O.OracleConfig()
+    host, dev = [], []
+    g = torch.Generator().manual_seed(1234 + rank)
+    for i in range(n):
+        b = O.make_batch(ocfg, B_PER_GPU, SEQ_LEN, seed=1000 * rank + i, ragged=True)
+        b["labels"] = torch.randint(0, N_ITEMS, (B_PER_GPU,), generator=g)
+        host.append({k: v.pin_memory() for k, v in b.items()})
+        dev.append({k: v.to(device) for k, v in b.items()})
+    return host, dev
+
+
+def train_step(model, opt, batch, world):
+    from recformer_b200 import dist as rdist
+    loss = model(**batch)
+    opt.zero_grad()
+    loss.backward()
+    if world > 1:
+        rdist.allreduce_gradients(model)
+    opt.step()
+    return loss
+
+
+def time_region(fn, steps, world):
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(steps):
+        fn(i)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def gemm_profile(model, opt, batch, world):
+    """Device time of the dominant kernel (the tcgen05 GEMM) inside one step, via CUDA events around
+    every rf_gemm_bf16 launch on the launching stream."""
+    from recformer_b200 import ops
+    real = ops.gemm
+    evs = []
+
+    def timed(*a, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = real(*a, **kw)
+        e1.record()
+        evs.append((e0, e1))
+        return out
+
+    ops.gemm = timed
+    import recformer_b200.engine as eng
+    eng.ops.gemm = timed
+    try:
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        train_step(model, opt, batch, world)
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = real
+        eng.ops.gemm = real
+    gemm_ms = sum(a.elapsed_time(b) for a, b in evs)
+    return gemm_ms, len(evs), e0.elapsed_time(e1)
+
+
+def eval_topk_bench(device, rank, world, steps, warmup):
+    """configs[3]: 4096 users x 1M items sharded by item id over the ranks, fused top-10."""
+    from recformer_b200 import dist as rdist
+    from recformer_b200 import ops
+    lo, hi = rdist.shard_bounds(EVAL_ITEMS, world, rank)
+    g = torch.Generator(device=device).manual_seed(2)
+    table = torch.empty(hi - lo, E, dtype=torch.bfloat16, device=device)
+    chunk = 125_000
+    for a in range(0, hi - lo, chunk):       # N(0,1) rows, L2-normalised, bf16 (pre-normalised table, Spec S)
+        b = min(hi - lo, a + chunk)
+        ops.normalize_rows(torch.randn(b - a, E, device=device, generator=g), out=table[a:b])
+    users = ops.normalize_rows(torch.randn(EVAL_USERS, E, device=device, generator=torch.Generator(device=device).manual_seed(3)))
+    labels = torch.randint(0, EVAL_ITEMS, (EVAL_USERS,), device=device, generator=torch.Generator(device=device).manual_seed(4))
+
+    def one(_):
+        s, i, l = ops.cosine_topk(users, table, 0.05, k=10, id_base=lo, labels=labels)
+        if world > 1:
+            gs, gi, gl = rdist.all_gather_topk(s, i, l)
+            s, i, l = ops.topk_merge(gs, gi, gl)
+        return s, i, l
+
+    for w in range(max(3, warmup)):
+        one(w)
+    ms = time_region(one, steps, world)
+    # kernel-only time of the fused scorer on this rank
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        ops.cosine_topk(users, table, 0.05, k=10, id_base=lo, labels=labels)
+    e1.record()
+    torch.cuda.synchronize()
+    k_ms = e0.elapsed_time(e1) / 3
+    flops = 2.0 * EVAL_USERS * (hi - lo) * E
+    _, burst, _, src = peaks()
+    return {"metric": "eval users/sec top-10 over 1M items", "value": EVAL_USERS * steps / (ms / 1e3), "unit": "users/s",
+            "ms_per_pass": ms / steps, "config": {"workload": "BASELINE configs[3]: 4096 users x 1M items bf16 table "
+                                                  f"sharded over {world} GPU(s), cosine top-10 + all-gather merge"},
+            "roofline": {"bound": "tensor", "achieved": flops / (k_ms / 1e3) / 1e12, "peak": burst, "unit": "TFLOP/s",
+                         "frac": flops / (k_ms / 1e3) / 1e12 / burst, "traffic": None, "peak_source": src,
+                         "kernel": "cosine_mma_kernel<TOPK>", "flops_per_launch": flops, "ms_per_launch": k_ms}}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from recformer_b200 import ops
+    from recformer_b200.optim import FusedAdamW
+
+    model, cfg = build_model(device)
+    model.train()
+    opt = FusedAdamW(model, lr=5e-5, weight_decay=0.01)
+    nb = 4
+    host, dev = make_batches(nb, device, rank)
+
+    for w in range(max(3, args.warmup)):
+        train_step(model, opt, dev[w % nb], world)
+    torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM -------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.__enter__()
+    l0 = ops.launch_count()
+    ms = time_region(lambda i: train_step(model, opt, dev[i % nb], world), args.steps, world)
+    launches = (ops.launch_count() - l0) // args.steps
+    # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region ----------
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    last = {}
+
+    def e2e_step(i):
+        b = {k: v.to(device, non_blocking=True) for k, v in host[i % nb].items()}
+        loss = train_step(model, opt, b, world)
+        last["loss"] = float(loss.item())      # device -> host read of the step's result
+
+    ms_e2e = time_region(e2e_step, args.steps, world)
+    if sampler:
+        sampler.__exit__()
+    # ---- roofline of the dominant kernel (tcgen05 GEMM) --------------------------------------
+    gemm_ms, n_gemm, step_ms_prof = gemm_profile(model, opt, dev[0], world)
+    hbm, burst, sustained, src = peaks()
+    flops_step = algorithmic_gemm_flops_per_seq() * B_PER_GPU
+    achieved = flops_step / (gemm_ms / 1e3) / 1e12
+    roof = {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
+            "traffic": None, "peak_source": f"{src} (sustained: kernel timed inside a long step)",
+            "kernel": "gemm_kernel (tcgen05, all fwd/dgrad/wgrad launches of one step)",
+            "flops_per_launch": flops_step / n_gemm, "launches_per_step": n_gemm, "ms_per_launch": gemm_ms / n_gemm,
+            "gemm_share_of_step": gemm_ms / step_ms_prof,
+            "step_tensor_frac": (flops_step + 3 * 4 * 66 * E * NL * SEQ_LEN * B_PER_GPU) / (ms / args.steps / 1e3) / 1e12 / sustained}
+    secondary = None
+    try:
+        del model, opt
+        torch.cuda.empty_cache()
+        secondary = eval_topk_bench(device, rank, world, max(3, min(args.steps, 10)), args.warmup)
+    except Exception as ex:  # the primary line must still print
+        secondary = {"metric": "eval users/sec top-10 over 1M items", "error": repr(ex)[:300]}
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, cms, cores = cpu_finetune_step_rate(2, 2, 1)
+        cpu_base = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"2 of {B_PER_GPU} sequences x {SEQ_LEN} tokens per step, 2 timed steps after 1 warm-up, "
+                              "fwd+CE(5k items)+bwd+AdamW, fp32 torch CPU oracle"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": world * B_PER_GPU * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": "finetune step (BASELINE configs[1]): RecformerForSeqRec longformer-base shape "
+                                       "(12 layers, d=768, window 64, random init), B=16/GPU x 1024 tok ragged "
+                                       "Industrial-shaped sequences, full-softmax CE over 5k items, fwd+bwd+AdamW, "
+                                       "train mode dropout 0.1",
+                           "global_batch": world * B_PER_GPU, "seq_len": SEQ_LEN, "parallelism": f"dp{world}",
+                           "l2": "per-step working set ~6 GB (activations + weights) >> 126 MB L2; 4 rotating batches"},
+                "e2e": {"value": world * B_PER_GPU * args.steps / (ms_e2e / 1e3), "unit": UNIT,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                        "last_loss": last.get("loss")},
+                "gpu_launches": int(launches),
+                "clocks": sampler.summary() if sampler else None,
+                "roofline": roof, "cpu_baseline": cpu_base, "secondary": secondary}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback); "
+                             "use --impl reference for the CPU arm")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

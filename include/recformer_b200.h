@@ -63,7 +63,7 @@ typedef struct rf_gemm_args {
   void* C;
   void* C2;             /* RF_EPI_GELU: activation output [M,N] bf16 (ldc) */
   const float* bias;    /* [N] or NULL */
-  const void* residual; /* bf16 [M,N] (ldr) or NULL */
+  const void* residual; /* [M,N] (ldr) bf16, or fp32 when residual_f32 != 0; or NULL */
   const void* aux;      /* RF_EPI_DGELU: bf16 pre-activation [M,N] (ldaux) */
   int M, N, K;
   int lda, ldb, ldc, ldr, ldaux;
@@ -76,6 +76,7 @@ typedef struct rf_gemm_args {
   int scale_ncols;
   float drop_p;
   uint64_t drop_seed;
+  int residual_f32;
 } rf_gemm_args;
 
 int rf_gemm_bf16(const rf_gemm_args* args, rf_stream_t stream);
@@ -125,20 +126,23 @@ typedef struct rf_embed_args {
   uint64_t drop_seed;
 } rf_embed_args;
 
-int rf_embed_ln_fwd(const rf_embed_args* a, void* out_bf16, int* err_flag, rf_stream_t stream);
+int rf_embed_ln_fwd(const rf_embed_args* a, void* out_bf16, float* out_f32_or_null, int* err_flag,
+                    rf_stream_t stream);
 int rf_embed_ln_bwd(const rf_embed_args* a, const void* dout_bf16, float* d_word, float* d_pos, float* d_type,
                     float* d_item, float* d_gamma, float* d_beta, rf_stream_t stream);
 
-/* LayerNorm over the last dim (E = 768) of a bf16 [T,E] tensor; fp32 statistics saved as
- * stats[t] = (mean, rstd).  Replaces nn.LayerNorm at HF:1070, HF:1129.
- * bwd: dx (bf16) from dy (bf16), pre-LN input x and stats; dgamma/dbeta accumulated (fp32,
- * += ).  If dx_dropped != NULL it also receives dropout-masked dx (mask regenerated from
+/* LayerNorm over the last dim (E = 768) of the fp32 residual stream [T,E]; replaces nn.LayerNorm
+ * at HF:1070, HF:1129.  The residual stream (pre-LN sums and LN outputs) is kept in fp32 and only
+ * rounded to bf16 where it becomes a tensor-core operand: y_bf16 is that operand copy, y_f32 the
+ * residual copy (either may be NULL); stats[t] = (mean, rstd) are saved for backward.
+ * bwd: dx (bf16) from dy (bf16), the fp32 pre-LN input x and stats; dgamma/dbeta accumulated
+ * (fp32, +=).  If dx_dropped != NULL it also receives dropout-masked dx (mask regenerated from
  * drop_seed; the dense branch's gradient, HF:1069) while dx keeps the residual branch's. */
 /* out[n] += sum_t x[t,n] for a bf16 [T,N] matrix (bias gradients of the dense layers). */
 int rf_colsum_bf16(const void* x_bf16, float* out, int T, int N, int ld, rf_stream_t stream);
-int rf_layernorm_fwd(const void* x_bf16, const float* gamma, const float* beta, void* y_bf16, float* stats, int T,
-                     int E, float eps, rf_stream_t stream);
-int rf_layernorm_bwd(const void* dy_bf16, const void* x_bf16, const float* stats, const float* gamma, void* dx_bf16,
+int rf_layernorm_fwd(const float* x_f32, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                     float* stats, int T, int E, float eps, rf_stream_t stream);
+int rf_layernorm_bwd(const void* dy_bf16, const float* x_f32, const float* stats, const float* gamma, void* dx_bf16,
                      void* dx_dropped_bf16, float drop_p, uint64_t drop_seed, float* d_gamma, float* d_beta, int T,
                      int E, rf_stream_t stream);
 

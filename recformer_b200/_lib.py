@@ -20,7 +20,7 @@ class GemmArgs(C.Structure):
                 ("lda", c_int), ("ldb", c_int), ("ldc", c_int), ("ldr", c_int), ("ldaux", c_int),
                 ("a_mn_major", c_int), ("b_mn_major", c_int), ("epi", c_int), ("out_f32", c_int),
                 ("accumulate", c_int), ("split_k", c_int), ("scale", c_float), ("scale_ncols", c_int),
-                ("drop_p", c_float), ("drop_seed", c_u64)]
+                ("drop_p", c_float), ("drop_seed", c_u64), ("residual_f32", c_int)]
 
 
 class EmbedArgs(C.Structure):
@@ -51,11 +51,12 @@ _SIGS = {
     "rf_gemm_bf16": (c_int, [P(GemmArgs), c_void_p]),
     "rf_prepare_inputs": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
-    "rf_embed_ln_fwd": (c_int, [P(EmbedArgs), c_void_p, c_void_p, c_void_p]),
+    "rf_embed_ln_fwd": (c_int, [P(EmbedArgs), c_void_p, c_void_p, c_void_p, c_void_p]),
     "rf_embed_ln_bwd": (c_int, [P(EmbedArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
     "rf_colsum_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "rf_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "rf_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+                                 c_void_p]),
     "rf_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_u64,
                                  c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "rf_band_attn_fwd": (c_int, [P(AttnArgs), c_void_p, c_void_p, c_void_p]),

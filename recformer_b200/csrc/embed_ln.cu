@@ -118,7 +118,7 @@ __device__ __forceinline__ void embed_row_stats(const EmbedDev& a, int id, int p
 
 template <int NV4>
 __global__ void __launch_bounds__(ROW_THREADS) embed_ln_fwd_kernel(const EmbedDev a, __nv_bfloat16* __restrict__ out,
-                                                                   int* err_flag) {
+                                                                   float* __restrict__ out32, int* err_flag) {
   const int lane = threadIdx.x & 31;
   const int T = a.B * a.Lp;
   for (int t = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); t < T; t += gridDim.x * (ROW_THREADS / 32)) {
@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_ln_fwd_kernel(const EmbedDe
         y0 = (keep & 1u) ? y0 * a.drop_scale : 0.f; y1 = (keep & 2u) ? y1 * a.drop_scale : 0.f;
         y2 = (keep & 4u) ? y2 * a.drop_scale : 0.f; y3 = (keep & 8u) ? y3 * a.drop_scale : 0.f;
       }
-      o2[v] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+      if (out) o2[v] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+      if (out32) reinterpret_cast<float4*>(out32 + static_cast<size_t>(t) * a.E)[v] = make_float4(y0, y1, y2, y3);
     }
   }
 }
@@ -216,25 +217,31 @@ embed_ln_bwd_kernel(const EmbedDev a, const __nv_bfloat16* __restrict__ dout, fl
 // LayerNorm on bf16 rows.  NV8 = E / 256 uint4 (8 x bf16) per lane.
 // ----------------------------------------------------------------------------------------------
 template <int NV8>
+__device__ __forceinline__ void load_row_f32(const float* __restrict__ xr, int lane, float (&v)[NV8][8]) {
+#pragma unroll
+  for (int k = 0; k < NV8; ++k) {
+    const float4 a = *reinterpret_cast<const float4*>(xr + (k * 32 + lane) * 8);
+    const float4 b = *reinterpret_cast<const float4*>(xr + (k * 32 + lane) * 8 + 4);
+    v[k][0] = a.x; v[k][1] = a.y; v[k][2] = a.z; v[k][3] = a.w;
+    v[k][4] = b.x; v[k][5] = b.y; v[k][6] = b.z; v[k][7] = b.w;
+  }
+}
+
+template <int NV8>
 __global__ void __launch_bounds__(ROW_THREADS)
-layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ stats, int T,
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     __nv_bfloat16* __restrict__ y, float* __restrict__ y32, float* __restrict__ stats, int T,
                      float eps) {
   constexpr int E = NV8 * 256;
   const int lane = threadIdx.x & 31;
   for (int t = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); t < T; t += gridDim.x * (ROW_THREADS / 32)) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * E);
     float v[NV8][8];
+    load_row_f32<NV8>(x + static_cast<size_t>(t) * E, lane, v);
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < NV8; ++k) {
-      const uint4 raw = xr[k * 32 + lane];
-      const float2 a0 = unpack_bf16(raw.x), a1 = unpack_bf16(raw.y), a2 = unpack_bf16(raw.z), a3 = unpack_bf16(raw.w);
-      v[k][0] = a0.x; v[k][1] = a0.y; v[k][2] = a1.x; v[k][3] = a1.y;
-      v[k][4] = a2.x; v[k][5] = a2.y; v[k][6] = a3.x; v[k][7] = a3.y;
+    for (int k = 0; k < NV8; ++k)
 #pragma unroll
       for (int e = 0; e < 8; ++e) s += v[k][e];
-    }
     const float mean = warp_sum(s) / E;
     float q = 0.f;
 #pragma unroll
@@ -243,25 +250,33 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
       for (int e = 0; e < 8; ++e) { const float d = v[k][e] - mean; q += d * d; }
     const float rstd = rsqrtf(warp_sum(q) / E + eps);
     if (lane == 0 && stats) { stats[2 * t] = mean; stats[2 * t + 1] = rstd; }
-    uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(t) * E);
 #pragma unroll
     for (int k = 0; k < NV8; ++k) {
       const int c = (k * 32 + lane) * 8;
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
-      uint4 o;
-      o.x = pack_bf16((v[k][0] - mean) * rstd * g0.x + b0.x, (v[k][1] - mean) * rstd * g0.y + b0.y);
-      o.y = pack_bf16((v[k][2] - mean) * rstd * g0.z + b0.z, (v[k][3] - mean) * rstd * g0.w + b0.w);
-      o.z = pack_bf16((v[k][4] - mean) * rstd * g1.x + b1.x, (v[k][5] - mean) * rstd * g1.y + b1.y);
-      o.w = pack_bf16((v[k][6] - mean) * rstd * g1.z + b1.z, (v[k][7] - mean) * rstd * g1.w + b1.w);
-      yr[k * 32 + lane] = o;
+      float o[8];
+      o[0] = (v[k][0] - mean) * rstd * g0.x + b0.x; o[1] = (v[k][1] - mean) * rstd * g0.y + b0.y;
+      o[2] = (v[k][2] - mean) * rstd * g0.z + b0.z; o[3] = (v[k][3] - mean) * rstd * g0.w + b0.w;
+      o[4] = (v[k][4] - mean) * rstd * g1.x + b1.x; o[5] = (v[k][5] - mean) * rstd * g1.y + b1.y;
+      o[6] = (v[k][6] - mean) * rstd * g1.z + b1.z; o[7] = (v[k][7] - mean) * rstd * g1.w + b1.w;
+      if (y) {
+        uint4 ov;
+        ov.x = pack_bf16(o[0], o[1]); ov.y = pack_bf16(o[2], o[3]); ov.z = pack_bf16(o[4], o[5]); ov.w = pack_bf16(o[6], o[7]);
+        reinterpret_cast<uint4*>(y + static_cast<size_t>(t) * E)[k * 32 + lane] = ov;
+      }
+      if (y32) {
+        float* yr = y32 + static_cast<size_t>(t) * E + c;
+        *reinterpret_cast<float4*>(yr) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(yr + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
     }
   }
 }
 
 template <int NV8>
 __global__ void __launch_bounds__(ROW_THREADS)
-layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
                      const float* __restrict__ stats, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
                      __nv_bfloat16* __restrict__ dx_dropped, float drop_scale, uint32_t drop_thresh,
                      uint64_t drop_seed, float* d_gamma, float* d_beta, int T) {
@@ -274,23 +289,21 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     for (int e = 0; e < 8; ++e) dg[k][e] = db[k][e] = 0.f;
   for (int t = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); t < T; t += gridDim.x * (ROW_THREADS / 32)) {
     const float mean = stats[2 * t], rstd = stats[2 * t + 1];
-    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * E);
     const uint4* dr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(t) * E);
     float xh[NV8][8], gy[NV8][8];
+    load_row_f32<NV8>(x + static_cast<size_t>(t) * E, lane, xh);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < NV8; ++k) {
       const int c = (k * 32 + lane) * 8;
-      const uint4 xraw = xr[k * 32 + lane], draw = dr[k * 32 + lane];
-      const float2 a0 = unpack_bf16(xraw.x), a1 = unpack_bf16(xraw.y), a2 = unpack_bf16(xraw.z), a3 = unpack_bf16(xraw.w);
+      const uint4 draw = dr[k * 32 + lane];
       const float2 d0 = unpack_bf16(draw.x), d1 = unpack_bf16(draw.y), d2 = unpack_bf16(draw.z), d3 = unpack_bf16(draw.w);
-      const float xv[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
       const float dv[8] = {d0.x, d0.y, d1.x, d1.y, d2.x, d2.y, d3.x, d3.y};
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
       const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        xh[k][e] = (xv[e] - mean) * rstd;
+        xh[k][e] = (xh[k][e] - mean) * rstd;
         dg[k][e] += dv[e] * xh[k][e];
         db[k][e] += dv[e];
         gy[k][e] = dv[e] * gv[e];
@@ -421,14 +434,14 @@ extern "C" int rf_prepare_inputs(const int64_t* input_ids, const int64_t* attent
   return check_launch("rf_prepare_inputs");
 }
 
-extern "C" int rf_embed_ln_fwd(const rf_embed_args* a, void* out, int* err_flag, rf_stream_t stream_) {
+extern "C" int rf_embed_ln_fwd(const rf_embed_args* a, void* out, float* out32, int* err_flag, rf_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  RF_REQUIRE(a && out, "rf_embed_ln_fwd: null argument");
+  RF_REQUIRE(a && (out || out32), "rf_embed_ln_fwd: null argument");
   RF_REQUIRE(a->E == 768, "rf_embed_ln_fwd: hidden size %d unsupported (768)", a->E);
   RF_REQUIRE(a->B > 0 && a->L > 0 && a->Lp >= a->L, "rf_embed_ln_fwd: bad shape");
   const EmbedDev d = make_embed_dev(a);
   embed_ln_fwd_kernel<6><<<row_grid(a->B * a->Lp), ROW_THREADS, 0, stream>>>(d, reinterpret_cast<__nv_bfloat16*>(out),
-                                                                           err_flag);
+                                                                           out32, err_flag);
   return check_launch("rf_embed_ln_fwd");
 }
 
@@ -444,19 +457,18 @@ extern "C" int rf_embed_ln_bwd(const rf_embed_args* a, const void* dout, float* 
   return check_launch("rf_embed_ln_bwd");
 }
 
-extern "C" int rf_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats, int T,
-                                int E, float eps, rf_stream_t stream_) {
+extern "C" int rf_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, float* y32,
+                                float* stats, int T, int E, float eps, rf_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  RF_REQUIRE(x && gamma && beta && y, "rf_layernorm_fwd: null argument");
+  RF_REQUIRE(x && gamma && beta && (y || y32), "rf_layernorm_fwd: null argument");
   RF_REQUIRE(E == 768, "rf_layernorm_fwd: hidden size %d unsupported (768)", E);
   RF_REQUIRE(T > 0, "rf_layernorm_fwd: T=%d", T);
-  layernorm_fwd_kernel<3><<<row_grid(T), ROW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma,
-                                                                  beta, reinterpret_cast<__nv_bfloat16*>(y), stats, T,
-                                                                  eps);
+  layernorm_fwd_kernel<3><<<row_grid(T), ROW_THREADS, 0, stream>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y),
+                                                                  y32, stats, T, eps);
   return check_launch("rf_layernorm_fwd");
 }
 
-extern "C" int rf_layernorm_bwd(const void* dy, const void* x, const float* stats, const float* gamma, void* dx,
+extern "C" int rf_layernorm_bwd(const void* dy, const float* x, const float* stats, const float* gamma, void* dx,
                                 void* dx_dropped, float drop_p, uint64_t drop_seed, float* d_gamma, float* d_beta,
                                 int T, int E, rf_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -466,7 +478,7 @@ extern "C" int rf_layernorm_bwd(const void* dy, const void* x, const float* stat
   const float scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   const int grid = min(row_grid(T), sm_count() * 2);
   layernorm_bwd_kernel<3><<<grid, ROW_THREADS, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), stats, gamma,
+      reinterpret_cast<const __nv_bfloat16*>(dy), x, stats, gamma,
       reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(dx_dropped), scale, thresh, drop_seed,
       d_gamma, d_beta, T);
   return check_launch("rf_layernorm_bwd");

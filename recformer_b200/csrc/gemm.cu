@@ -28,7 +28,8 @@ struct GemmParams {
   void* C;
   void* C2;
   const float* bias;
-  const __nv_bfloat16* residual;
+  const void* residual;     // bf16 or fp32 (residual_f32)
+  int residual_f32;
   const __nv_bfloat16* aux;
   int M, N, K;
   int ldc, ldr, ldaux;
@@ -249,13 +250,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
             if (p.residual != nullptr) {
-              const __nv_bfloat16* rs = p.residual + static_cast<size_t>(row) * p.ldr + col0;
+              if (p.residual_f32) {
+                const float* rs = reinterpret_cast<const float*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 a = *reinterpret_cast<const uint4*>(rs + j);
-                float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
-                v[j] += a0.x; v[j + 1] += a0.y; v[j + 2] += a1.x; v[j + 3] += a1.y;
-                v[j + 4] += a2.x; v[j + 5] += a2.y; v[j + 6] += a3.x; v[j + 7] += a3.y;
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 a = *reinterpret_cast<const float4*>(rs + j);
+                  v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
+                }
+              } else {
+                const __nv_bfloat16* rs =
+                    reinterpret_cast<const __nv_bfloat16*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  const uint4 a = *reinterpret_cast<const uint4*>(rs + j);
+                  float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+                  v[j] += a0.x; v[j + 1] += a0.y; v[j + 2] += a1.x; v[j + 3] += a1.y;
+                  v[j + 4] += a2.x; v[j + 5] += a2.y; v[j + 6] += a3.x; v[j + 7] += a3.y;
+                }
               }
             }
             if (OUT_F32) {
@@ -321,12 +332,20 @@ static int launch_gemm(const rf_gemm_args* a, cudaStream_t stream) {
   if (!tmB) return RF_ERR_CUDA;
   GemmParams p;
   p.C = a->C; p.C2 = a->C2; p.bias = a->bias;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+  p.residual = a->residual;
+  p.residual_f32 = a->residual_f32;
   p.aux = reinterpret_cast<const __nv_bfloat16*>(a->aux);
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.ldc = a->ldc; p.ldr = a->ldr; p.ldaux = a->ldaux;
   p.accumulate = a->accumulate;
-  p.split_k = a->split_k > 1 ? a->split_k : 1;
+  {
+    // every K slice must be non-empty: recompute the slice count from the per-slice block count
+    const int kb = (a->K + BK - 1) / BK;
+    int sk = a->split_k > 1 ? a->split_k : 1;
+    if (sk > kb) sk = kb;
+    const int per = (kb + sk - 1) / sk;
+    p.split_k = (kb + per - 1) / per;
+  }
   p.scale = a->scale; p.scale_ncols = a->scale_ncols;
   p.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   p.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;

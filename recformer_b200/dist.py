@@ -1,0 +1,83 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed over NCCL; gloo for CPU tests).
+
+The hot path shards in two ways:
+  * full-catalogue scoring: the item table is sharded by contiguous item-id ranges; each rank
+    runs the fused cosine-GEMM + top-k on its shard and the per-rank (k scores, k ids, label
+    score) are exchanged with ONE all-gather, then merged locally (rf_topk_merge);
+  * data-parallel training: replicas; the flat fp32 gradient buffer is all-reduced in one call.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous id range [lo, hi) owned by `rank` (remainder spread over the first ranks)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_topk(scores: torch.Tensor, ids: torch.Tensor, label_score: torch.Tensor) -> torch.Tensor:
+    """(B,k) fp32, (B,k) int32, (B,) fp32 -> one (B, 2k+1) fp32 buffer (ids bit-cast) so that the
+    exchange is a single collective."""
+    return torch.cat([scores, ids.view(torch.float32), label_score[:, None]], dim=1).contiguous()
+
+
+def unpack_topk(buf: torch.Tensor, k: int):
+    """(W, B, 2k+1) -> scores (W,B,k) fp32, ids (W,B,k) int32, label scores (W,B) fp32."""
+    return (buf[..., :k].contiguous(), buf[..., k:2 * k].contiguous().view(torch.int32), buf[..., 2 * k].contiguous())
+
+
+def merge_topk_reference(scores: torch.Tensor, ids: torch.Tensor, label_scores: torch.Tensor, k: int):
+    """Host/torch restatement of rf_topk_merge used by the CPU (gloo) tests: global top-k over W
+    lists of k with ties broken towards the lower id; label score = max over ranks."""
+    W, B, _ = scores.shape
+    s = scores.permute(1, 0, 2).reshape(B, W * k)
+    i = ids.permute(1, 0, 2).reshape(B, W * k).to(torch.int64)
+    order = torch.argsort(i, dim=1, stable=True)                 # ids ascending first ...
+    s, i = torch.gather(s, 1, order), torch.gather(i, 1, order)
+    order = torch.argsort(s, dim=1, descending=True, stable=True)  # ... then stable by score
+    s, i = torch.gather(s, 1, order)[:, :k], torch.gather(i, 1, order)[:, :k]
+    return s, i.to(torch.int32), label_scores.max(dim=0).values
+
+
+def all_gather_topk(scores, ids, label_score, group=None):
+    """All-gather the packed per-rank top-k; returns (W,B,k) scores, (W,B,k) ids, (W,B) labels."""
+    k = scores.shape[1]
+    packed = pack_topk(scores, ids, label_score)
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out.view(-1), packed.view(-1), group=group)
+    return unpack_topk(out, k)
+
+
+def sharded_topk(model, pooled: torch.Tensor, k: int = 10, labels: Optional[torch.Tensor] = None,
+                 id_base: int = 0, group=None):
+    """Global top-k when `model.item_embedding` holds only this rank's shard (ids offset by
+    id_base).  One all-gather + local merge; identical on every rank."""
+    from . import ops
+    s, i, l = model.topk(pooled, k=k, labels=labels, id_base=id_base)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return s, i, l
+    gs, gi, gl = all_gather_topk(s, i, l, group)
+    return ops.topk_merge(gs, gi, gl)
+
+
+def allreduce_gradients(model, group=None, average: bool = True) -> None:
+    """Data-parallel gradient sync: one all-reduce over the flat fp32 gradient buffer."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    enc = getattr(model, "longformer", model)
+    g = enc._engine.params.grad
+    if g is None:
+        raise RuntimeError("allreduce_gradients: no gradients (run backward first)")
+    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        g.mul_(1.0 / world)

@@ -146,7 +146,7 @@ class _EncoderFunction(torch.autograd.Function):
         eng = model._engine
         sv = eng.forward(*inputs, training=model.training, save=True)
         B, Lp, E = sv.B, sv.Lp, model.config.hidden_size
-        hidden = eng.hidden(sv).view(B, Lp, E)[:, :L].float()
+        hidden = eng.hidden(sv).view(B, Lp, E)[:, :L].clone()   # fp32 residual stream of the last layer
         ctx.model, ctx.sv, ctx.L = model, sv, L
         return hidden
 
@@ -242,7 +242,7 @@ class RecformerModel(nn.Module):
             hidden = _EncoderFunction.apply(self._grad_hook(input_ids.device), self, L, inputs)
         else:
             sv = eng.forward(*inputs, training=self.training, save=False)
-            hidden = eng.hidden(sv).view(B, sv.Lp, E)[:, :L].float()
+            hidden = eng.hidden(sv).view(B, sv.Lp, E)[:, :L].clone()
             eng.release(sv)
         if self.strict_checks:
             eng.check_errors()
@@ -264,7 +264,7 @@ class RecformerModel(nn.Module):
         sv = eng.forward(to64(ids), to64(batch.get("attention_mask")), to64(batch.get("global_attention_mask")),
                          to64(batch.get("token_type_ids")), to64(batch["item_position_ids"]),
                          to64(batch.get("position_ids")), training=False, save=False)
-        pooled = eng.hidden(sv).view(sv.B, sv.Lp, -1)[:, 0].contiguous()
+        pooled = eng.hidden_bf16(sv).view(sv.B, sv.Lp, -1)[:, 0].contiguous()
         eng.release(sv)
         return pooled
 

@@ -57,6 +57,7 @@ def gemm(A, B, out=None, *, bias=None, residual=None, aux=None, out2=None, a_mn_
     a.M, a.N, a.K = M, N, K
     a.lda, a.ldb, a.ldc = A.stride(0), B.stride(0), out.stride(0)
     a.ldr = residual.stride(0) if residual is not None else 0
+    a.residual_f32 = int(residual is not None and residual.dtype == torch.float32)
     a.ldaux = aux.stride(0) if aux is not None else 0
     a.a_mn_major, a.b_mn_major, a.epi = int(a_mn_major), int(b_mn_major), epi
     a.out_f32 = int(out.dtype == torch.float32)
@@ -98,16 +99,17 @@ def _embed_args(input_ids, token_type_ids, item_position_ids, pos_ids, word, pos
 
 
 def embed_ln_fwd(input_ids, token_type_ids, item_position_ids, pos_ids, word, posw, typew, itemw, gamma, beta, Lp,
-                 padding_idx, eps, err_flag, drop_p=0.0, drop_seed=0, out=None):
+                 padding_idx, eps, err_flag, drop_p=0.0, drop_seed=0, out=None, out32=None):
     for t, n in ((word, "word"), (posw, "pos"), (typew, "type"), (itemw, "item"), (gamma, "gamma"), (beta, "beta")):
         _req(t, torch.float32, n)
     B = input_ids.shape[0]
     a = _embed_args(input_ids, token_type_ids, item_position_ids, pos_ids, word, posw, typew, itemw, gamma, beta, Lp,
                     padding_idx, eps, drop_p, drop_seed)
-    if out is None:
+    if out is None and out32 is None:
         out = torch.empty(B * Lp, word.shape[1], dtype=torch.bfloat16, device=word.device)
-    check(_lib.lib().rf_embed_ln_fwd(C.byref(a), out.data_ptr(), _ptr(err_flag), _stream()), "rf_embed_ln_fwd")
-    return out
+    check(_lib.lib().rf_embed_ln_fwd(C.byref(a), _ptr(out), _ptr(out32), _ptr(err_flag), _stream()),
+          "rf_embed_ln_fwd")
+    return out if out is not None else out32
 
 
 def embed_ln_bwd(dout, input_ids, token_type_ids, item_position_ids, pos_ids, word, posw, typew, itemw, gamma, beta,
@@ -118,20 +120,22 @@ def embed_ln_bwd(dout, input_ids, token_type_ids, item_position_ids, pos_ids, wo
                                      _ptr(d_item), _ptr(d_gamma), _ptr(d_beta), _stream()), "rf_embed_ln_bwd")
 
 
-def layernorm_fwd(x, gamma, beta, eps, out=None, stats=None):
-    _req(x, torch.bfloat16, "x")
+def layernorm_fwd(x, gamma, beta, eps, out=None, out32=None, stats=None):
+    """x: fp32 [T,E] (the residual stream); out: bf16 operand copy, out32: fp32 residual copy."""
+    _req(x, torch.float32, "x")
     T, E = x.shape
-    if out is None:
-        out = torch.empty_like(x)
-    check(_lib.lib().rf_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), _ptr(stats), T,
-                                      E, eps, _stream()), "rf_layernorm_fwd")
-    return out
+    if out is None and out32 is None:
+        out = torch.empty(T, E, dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().rf_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(out), _ptr(out32),
+                                      _ptr(stats), T, E, eps, _stream()), "rf_layernorm_fwd")
+    return out if out is not None else out32
 
 
 def layernorm_bwd(dy, x, stats, gamma, d_gamma, d_beta, dx=None, dx_dropped=None, drop_p=0.0, drop_seed=0):
+    _req(x, torch.float32, "x")
     T, E = x.shape
     if dx is None:
-        dx = torch.empty_like(x)
+        dx = torch.empty(T, E, dtype=torch.bfloat16, device=x.device)
     check(_lib.lib().rf_layernorm_bwd(dy.data_ptr(), x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), dx.data_ptr(),
                                       _ptr(dx_dropped), drop_p, drop_seed, _ptr(d_gamma), _ptr(d_beta), T, E,
                                       _stream()), "rf_layernorm_bwd")

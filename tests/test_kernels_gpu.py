@@ -47,6 +47,10 @@ def test_gemm_q_scale_residual():
     out = ops.gemm(A, B[:768].contiguous(), bias=bias[:768].contiguous(), residual=res)
     ref = A.float() @ B[:768].float().T + bias[:768] + res.float()
     assert relerr(out, ref) < 1e-2
+    res32 = rnd(M, 768, seed=6, dtype=torch.float32)      # fp32 residual stream in, fp32 pre-LN sum out
+    out32 = ops.gemm(A, B[:768].contiguous(), bias=bias[:768].contiguous(), residual=res32, out_dtype=torch.float32)
+    ref = A.float() @ B[:768].float().T + bias[:768] + res32
+    assert relerr(out32, ref) < 1e-4
 
 
 def test_gemm_gelu_dual_and_dgelu():
@@ -124,6 +128,11 @@ def test_prepare_and_embed_ln():
                            sd[p + "word_embeddings.weight"], sd[p + "position_embeddings.weight"],
                            sd[p + "token_type_embeddings.weight"], sd[p + "item_position_embeddings.weight"],
                            sd[p + "LayerNorm.weight"], sd[p + "LayerNorm.bias"], Lp, 1, 1e-5, err)
+    out32 = torch.empty(5 * Lp, 768, dtype=torch.float32, device=DEV)
+    ops.embed_ln_fwd(dbatch["input_ids"], dbatch["token_type_ids"], dbatch["item_position_ids"], pos,
+                     sd[p + "word_embeddings.weight"], sd[p + "position_embeddings.weight"],
+                     sd[p + "token_type_embeddings.weight"], sd[p + "item_position_embeddings.weight"],
+                     sd[p + "LayerNorm.weight"], sd[p + "LayerNorm.bias"], Lp, 1, 1e-5, err, out=out, out32=out32)
     assert err.item() == 0
     _, ids, am, tt, pids, ip = O.pad_to_window_size(
         O.OracleConfig(num_hidden_layers=1, attention_window=[256]), batch["input_ids"], batch["attention_mask"],
@@ -131,6 +140,7 @@ def test_prepare_and_embed_ln():
     sd_cpu = {k: v.cpu() for k, v in sd.items()}
     ref = O.embeddings_forward(sd_cpu, cfg, ids, tt, ip)
     assert (out.view(5, Lp, 768).float().cpu() - ref).abs().max() < 0.03   # bf16 output rounding
+    assert (out32.view(5, Lp, 768).cpu() - ref).abs().max() < 1e-4
     # bad global mask is flagged
     gm = dbatch["global_attention_mask"].clone()
     gm[0, 5] = 1
@@ -140,15 +150,18 @@ def test_prepare_and_embed_ln():
 
 def test_layernorm_fwd_bwd():
     T, E = 1000, 768
-    x = rnd(T, E, seed=1, scale=2.0)
+    x = rnd(T, E, seed=1, scale=2.0, dtype=torch.float32)
     gamma = 1 + rnd(E, seed=2, scale=0.1, dtype=torch.float32)
     beta = rnd(E, seed=3, scale=0.1, dtype=torch.float32)
     stats = torch.empty(T, 2, dtype=torch.float32, device=DEV)
-    y = ops.layernorm_fwd(x, gamma, beta, 1e-5, stats=stats)
-    xf = x.float().requires_grad_(True)
+    y32 = torch.empty(T, E, dtype=torch.float32, device=DEV)
+    y = torch.empty(T, E, dtype=torch.bfloat16, device=DEV)
+    ops.layernorm_fwd(x, gamma, beta, 1e-5, out=y, out32=y32, stats=stats)
+    xf = x.clone().requires_grad_(True)
     gf, bf = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     ref = torch.nn.functional.layer_norm(xf, (E,), gf, bf, 1e-5)
     assert (y.float() - ref).abs().max() < 0.03
+    assert (y32 - ref).abs().max() < 1e-4 and torch.equal(y, y32.to(torch.bfloat16))
     assert (stats[:, 0] - xf.mean(-1)).abs().max() < 1e-4
     dy = rnd(T, E, seed=4)
     ref.backward(dy.float())

@@ -71,8 +71,13 @@ def test_recall_ndcg_match_reference_ranker(goldens):
     items = O.make_item_table(g["N"], 768, seed=1).to(DEV)
     model.init_item_embedding(items)
     ref = g["logits"]
-    # labels chosen inside the reference's own top-20 so that the metrics are non-trivial
-    labels = torch.topk(ref, 20, dim=-1).indices[torch.arange(ref.shape[0]), torch.arange(ref.shape[0]) * 2 % 20]
+    # labels chosen inside the reference's own top-20 (non-trivial metrics), at the rank whose score is
+    # best separated from its neighbours: the contract is exactness where gaps exceed the tolerance
+    top = torch.topk(ref, 21, dim=-1)
+    gaps = torch.minimum(top.values[:, :-2] - top.values[:, 1:-1], top.values[:, 1:-1] - top.values[:, 2:])   # ranks 1..19
+    pick = gaps.argmax(-1) + 1
+    assert (gaps.max(-1).values > 2 * LOGIT_TOL).all()
+    labels = top.indices[torch.arange(ref.shape[0]), pick]
     want = O.ranker(ref, labels, ks=(10,))
     with torch.no_grad():
         pooled = model.longformer(**batch).pooler_output
