@@ -326,6 +326,8 @@ def run_ours(args):
             "step_tensor_frac": (flops_step + 3 * 4 * 66 * E * NL * SEQ_LEN * B_PER_GPU) / (ms / args.steps / 1e3) / 1e12 / sustained}
     secondary = None
     try:
+        if args.no_secondary:
+            raise RuntimeError("skipped (--no-secondary)")
         del model, opt
         torch.cuda.empty_cache()
         secondary = eval_topk_bench(device, rank, world, max(3, min(args.steps, 10)), args.warmup)
@@ -367,6 +369,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the 1M-item eval leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
