@@ -137,14 +137,16 @@ int rf_embed_ln_bwd(const rf_embed_args* a, const void* dout_bf16, float* d_word
  * residual copy (either may be NULL); stats[t] = (mean, rstd) are saved for backward.
  * bwd: dx (bf16) from dy (bf16), the fp32 pre-LN input x and stats; dgamma/dbeta accumulated
  * (fp32, +=).  If dx_dropped != NULL it also receives dropout-masked dx (mask regenerated from
- * drop_seed; the dense branch's gradient, HF:1069) while dx keeps the residual branch's. */
+ * drop_seed; the dense branch's gradient, HF:1069) while dx keeps the residual branch's.
+ * d_bias (optional, +=) receives the column sums of that dense-branch gradient, i.e. the bias
+ * gradient of the nn.Linear in front of the LayerNorm. */
 /* out[n] += sum_t x[t,n] for a bf16 [T,N] matrix (bias gradients of the dense layers). */
 int rf_colsum_bf16(const void* x_bf16, float* out, int T, int N, int ld, rf_stream_t stream);
 int rf_layernorm_fwd(const float* x_f32, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
                      float* stats, int T, int E, float eps, rf_stream_t stream);
 int rf_layernorm_bwd(const void* dy_bf16, const float* x_f32, const float* stats, const float* gamma, void* dx_bf16,
-                     void* dx_dropped_bf16, float drop_p, uint64_t drop_seed, float* d_gamma, float* d_beta, int T,
-                     int E, rf_stream_t stream);
+                     void* dx_dropped_bf16, float drop_p, uint64_t drop_seed, float* d_gamma, float* d_beta,
+                     float* d_bias, int T, int E, rf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Longformer sliding-window attention with a global CLS token (SURVEY.md §8a Spec A;

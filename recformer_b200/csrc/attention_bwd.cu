@@ -144,7 +144,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   const float LOG2E = 1.4426950408889634f;
   const float lse2 = lse * LOG2E;
   const uint64_t rowid = (static_cast<uint64_t>(b) * p.H + h) * p.L + (in_seq ? i : 0);
-  constexpr int DGRP = (2 * W + 16) / 8;
+  constexpr int DGRP = NT / 8;
   const bool g_ok = kflag[NK] != 0;
 
   // ---- pass A: delta = sum_c P'_c dP_c (P' = dropout(P)) ----
@@ -155,19 +155,25 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     tmem_ld32(lane_base + TM_S + cc * 32, sv);
     tmem_ld32(lane_base + TM_DP + cc * 32, dv);
     tmem_ld_wait();
+    uint32_t keepm = 0xFFFFFFFFu;
+    if (p.drop_thresh != 0) {
+      keepm = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c0 = cc * 32 + u * 8;
+        if (c0 + 7 >= r && c0 <= r + 2 * W)
+          keepm |= dropout_keep8(p.drop_seed, rowid * DGRP + (c0 >> 3), p.drop_thresh) << (u * 8);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int c = cc * 32 + j;
-      const bool ok = row_valid && kflag[c] && (c >= r) && (c <= r + 2 * W);
-      float pr = ok ? exp2f(__uint_as_float(sv[j]) * LOG2E - lse2) : 0.f;
-      if (p.drop_thresh != 0 && ok) {
-        const int d = c - r;
-        const uint32_t keep = dropout_keep8(p.drop_seed, rowid * DGRP + (d >> 3), p.drop_thresh);
-        pr = ((keep >> (d & 7)) & 1u) ? pr * p.drop_scale : 0.f;
-      }
+      const bool ok = row_valid && kflag[c] && (c >= r) && (c <= r + 2 * W) && ((keepm >> j) & 1u);
+      const float pr = ok ? exp2f(__uint_as_float(sv[j]) * LOG2E - lse2) : 0.f;
       delta += pr * __uint_as_float(dv[j]);
     }
   }
+  delta *= p.drop_scale;
   uint32_t gs[16], gd[16];
   tmem_ld16(lane_base + TM_S + NK, gs);
   tmem_ld16(lane_base + TM_DP + NK, gd);
@@ -176,9 +182,8 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   float pg_d = pg;                                                                         // dropped
   float keep_g = 1.f;
   if (p.drop_thresh != 0) {
-    const int d = 2 * W + 1;
-    const uint32_t keep = dropout_keep8(p.drop_seed, rowid * DGRP + (d >> 3), p.drop_thresh);
-    keep_g = ((keep >> (d & 7)) & 1u) ? p.drop_scale : 0.f;
+    const uint32_t keep = dropout_keep8(p.drop_seed, rowid * DGRP + (NK >> 3), p.drop_thresh);
+    keep_g = (keep & 1u) ? p.drop_scale : 0.f;
     pg_d = pg * keep_g;
   }
   const float dpg = __uint_as_float(gd[0]);
@@ -193,18 +198,23 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
       tmem_ld32(lane_base + TM_S + cc * 32, sv);
       tmem_ld32(lane_base + TM_DP + cc * 32, dv);
       tmem_ld_wait();
+      uint32_t keepm = 0xFFFFFFFFu;
+      if (p.drop_thresh != 0) {
+        keepm = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c0 = cc * 32 + u * 8;
+          if (c0 + 7 >= r && c0 <= r + 2 * W)
+            keepm |= dropout_keep8(p.drop_seed, rowid * DGRP + (c0 >> 3), p.drop_thresh) << (u * 8);
+        }
+      }
       float pr[32], ds[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int c = cc * 32 + j;
         const bool ok = row_valid && kflag[c] && (c >= r) && (c <= r + 2 * W);
         const float pu = ok ? exp2f(__uint_as_float(sv[j]) * LOG2E - lse2) : 0.f;
-        float kp = 1.f;
-        if (p.drop_thresh != 0 && ok) {
-          const int d = c - r;
-          const uint32_t keep = dropout_keep8(p.drop_seed, rowid * DGRP + (d >> 3), p.drop_thresh);
-          kp = ((keep >> (d & 7)) & 1u) ? p.drop_scale : 0.f;
-        }
+        const float kp = ((keepm >> j) & 1u) ? p.drop_scale : 0.f;
         pr[j] = pu * kp;                                           // P' feeds dV
         ds[j] = pu * (kp * __uint_as_float(dv[j]) - delta);        // softmax backward
       }

@@ -182,14 +182,15 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
         pr[j] = e;
       }
       if (p.drop_thresh != 0) {
-        // mask keyed on (row, diagonal offset d = c - r) in groups of 8 along d
+        // keep-mask keyed on (row, 8-column group of the tile): one Philox call per 8 probabilities
+        const uint64_t rowid = (static_cast<uint64_t>(b) * p.H + h) * p.L + i;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int d = cc * 32 + j - r;
-          if (d >= 0 && d <= 2 * W) {
-            const uint64_t rowid = (static_cast<uint64_t>(b) * p.H + h) * p.L + i;
-            const uint32_t keep = dropout_keep8(p.drop_seed, rowid * ((2 * W + 16) / 8) + (d >> 3), p.drop_thresh);
-            pr[j] = ((keep >> (d & 7)) & 1u) ? pr[j] * p.drop_scale : 0.0f;
+        for (int u = 0; u < 4; ++u) {
+          const int c0 = cc * 32 + u * 8;
+          if (c0 + 7 >= r && c0 <= r + 2 * W) {
+            const uint32_t keep = dropout_keep8(p.drop_seed, rowid * (NT / 8) + (c0 >> 3), p.drop_thresh);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pr[u * 8 + e] = ((keep >> e) & 1u) ? pr[u * 8 + e] * p.drop_scale : 0.0f;
           }
         }
       }
@@ -214,9 +215,8 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
     l += pg;
     if (p.drop_thresh != 0) {
       const uint64_t rowid = (static_cast<uint64_t>(b) * p.H + h) * p.L + i;
-      const int d = 2 * W + 1;
-      const uint32_t keep = dropout_keep8(p.drop_seed, rowid * ((2 * W + 16) / 8) + (d >> 3), p.drop_thresh);
-      pg = ((keep >> (d & 7)) & 1u) ? pg * p.drop_scale : 0.0f;
+      const uint32_t keep = dropout_keep8(p.drop_seed, rowid * (NT / 8) + (NK >> 3), p.drop_thresh);
+      pg = (keep & 1u) ? pg * p.drop_scale : 0.0f;
     }
     uint8_t* prow = sP + (NK / 64) * 16384 + r * 128;
     *reinterpret_cast<uint4*>(prow + ((0 ^ (r & 7)) << 4)) = make_uint4(pack_bf16(pg, 0.0f), 0, 0, 0);

@@ -279,14 +279,15 @@ __global__ void __launch_bounds__(ROW_THREADS)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
                      const float* __restrict__ stats, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
                      __nv_bfloat16* __restrict__ dx_dropped, float drop_scale, uint32_t drop_thresh,
-                     uint64_t drop_seed, float* d_gamma, float* d_beta, int T) {
+                     uint64_t drop_seed, float* d_gamma, float* d_beta, float* d_bias, int T) {
   constexpr int E = NV8 * 256;
   const int lane = threadIdx.x & 31;
-  float dg[NV8][8], db[NV8][8];
+  __shared__ float red[ROW_THREADS / 32][E];
+  float dg[NV8][8], db[NV8][8], dbias[NV8][8];
 #pragma unroll
   for (int k = 0; k < NV8; ++k)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) dg[k][e] = db[k][e] = 0.f;
+    for (int e = 0; e < 8; ++e) dg[k][e] = db[k][e] = dbias[k][e] = 0.f;
   for (int t = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); t < T; t += gridDim.x * (ROW_THREADS / 32)) {
     const float mean = stats[2 * t], rstd = stats[2 * t + 1];
     const uint4* dr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(t) * E);
@@ -330,18 +331,29 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
         ov.x = pack_bf16(o[0], o[1]); ov.y = pack_bf16(o[2], o[3]); ov.z = pack_bf16(o[4], o[5]); ov.w = pack_bf16(o[6], o[7]);
         reinterpret_cast<uint4*>(dx_dropped + static_cast<size_t>(t) * E)[k * 32 + lane] = ov;
       }
+      // column sums of the gradient that reaches the preceding dense layer (its bias gradient)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dbias[k][e] += o[e];
     }
   }
+  // CTA-level reduction (8 warps -> 1) in shared memory, then one red.add per column per CTA
+  const int warp = threadIdx.x >> 5;
+#pragma unroll 1
+  for (int which = 0; which < 3; ++which) {
+    float* dst = which == 0 ? d_gamma : (which == 1 ? d_beta : d_bias);
+    if (dst == nullptr) continue;   // uniform across the CTA
+    __syncthreads();
 #pragma unroll
-  for (int k = 0; k < NV8; ++k) {
-    const int c = (k * 32 + lane) * 8;
-    if (d_gamma) {
-      red_add_v4(d_gamma + c, dg[k][0], dg[k][1], dg[k][2], dg[k][3]);
-      red_add_v4(d_gamma + c + 4, dg[k][4], dg[k][5], dg[k][6], dg[k][7]);
-    }
-    if (d_beta) {
-      red_add_v4(d_beta + c, db[k][0], db[k][1], db[k][2], db[k][3]);
-      red_add_v4(d_beta + c + 4, db[k][4], db[k][5], db[k][6], db[k][7]);
+    for (int k = 0; k < NV8; ++k)
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        red[warp][(k * 32 + lane) * 8 + e] = which == 0 ? dg[k][e] : (which == 1 ? db[k][e] : dbias[k][e]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < E; c += ROW_THREADS) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < ROW_THREADS / 32; ++w) t += red[w][c];
+      atomicAdd(dst + c, t);
     }
   }
 }
@@ -351,20 +363,44 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* out, int T, int N,
                                                           int ld, int rows_per_cta) {
-  // thread handles 8 consecutive columns; CTA covers 2048 columns-slab x rows_per_cta rows
-  const int c = (blockIdx.x * 256 + threadIdx.x) * 8;
-  if (c >= N) return;
+  // CTA = one 256-column slab (lane -> 8 columns) x rows_per_cta rows (warp w takes rows w, w+8, ...);
+  // warps are reduced in shared memory, then one red.add per column per CTA.
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
   const int t0 = blockIdx.y * rows_per_cta;
   const int t1 = min(T, t0 + rows_per_cta);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int t = t0; t < t1; ++t) {
-    const uint4 raw = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * ld + c);
-    const float2 a0 = unpack_bf16(raw.x), a1 = unpack_bf16(raw.y), a2 = unpack_bf16(raw.z), a3 = unpack_bf16(raw.w);
-    acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y;
-    acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
+  if (c < N) {
+    int t = t0 + warp;
+    for (; t + 24 < t1; t += 32) {   // 4 independent loads in flight
+      uint4 raw[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) raw[q] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(t + q * 8) * ld + c);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 a0 = unpack_bf16(raw[q].x), a1 = unpack_bf16(raw[q].y), a2 = unpack_bf16(raw[q].z), a3 = unpack_bf16(raw[q].w);
+        acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y;
+        acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
+      }
+    }
+    for (; t < t1; t += 8) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * ld + c);
+      const float2 a0 = unpack_bf16(raw.x), a1 = unpack_bf16(raw.y), a2 = unpack_bf16(raw.z), a3 = unpack_bf16(raw.w);
+      acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y;
+      acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
+    }
   }
-  red_add_v4(out + c, acc[0], acc[1], acc[2], acc[3]);
-  red_add_v4(out + c + 4, acc[4], acc[5], acc[6], acc[7]);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = acc[e];
+  __syncthreads();
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(out + col, t);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -470,24 +506,24 @@ extern "C" int rf_layernorm_fwd(const float* x, const float* gamma, const float*
 
 extern "C" int rf_layernorm_bwd(const void* dy, const float* x, const float* stats, const float* gamma, void* dx,
                                 void* dx_dropped, float drop_p, uint64_t drop_seed, float* d_gamma, float* d_beta,
-                                int T, int E, rf_stream_t stream_) {
+                                float* d_bias, int T, int E, rf_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   RF_REQUIRE(dy && x && stats && gamma && dx, "rf_layernorm_bwd: null argument");
   RF_REQUIRE(E == 768, "rf_layernorm_bwd: hidden size %d unsupported (768)", E);
   const uint32_t thresh = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 65536.0f) : 0u;
   const float scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
-  const int grid = min(row_grid(T), sm_count() * 2);
+  const int grid = min(row_grid(T), sm_count());
   layernorm_bwd_kernel<3><<<grid, ROW_THREADS, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), x, stats, gamma,
       reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(dx_dropped), scale, thresh, drop_seed,
-      d_gamma, d_beta, T);
+      d_gamma, d_beta, d_bias, T);
   return check_launch("rf_layernorm_bwd");
 }
 
 extern "C" int rf_colsum_bf16(const void* x, float* out, int T, int N, int ld, rf_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   RF_REQUIRE(x && out && T > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0, "rf_colsum_bf16: bad argument");
-  const int gx = (N / 8 + 255) / 256;
+  const int gx = (N + 255) / 256;
   int gy = (sm_count() * 4) / gx;
   if (gy < 1) gy = 1;
   if (gy > T) gy = T;

@@ -398,9 +398,8 @@ class EncoderEngine:
             # ---- output block: LN2 <- dense(W2) <- gelu <- dense(W1) ----
             dpd = sc.d_pre_drop if pd > 0 else None
             ops.layernorm_bwd(d_out, sv.pre2[i], sv.stats2[i], W["ln2w"], G["ln2w"], G["ln2b"], dx=sc.d_pre,
-                              dx_dropped=dpd, drop_p=pd, drop_seed=self._seed(sv, i, 4))
+                              dx_dropped=dpd, drop_p=pd, drop_seed=self._seed(sv, i, 4), d_bias=G["b2"])
             dY = sc.d_pre_drop if pd > 0 else sc.d_pre
-            ops.colsum(dY, G["b2"])
             ops.gemm(dY, sv.g[i], out=G["W2"], a_mn_major=True, b_mn_major=True, accumulate=True,
                      split_k=_pick_split(E, F, T))
             ops.gemm(dY, W["W2"], out=sc.dU, b_mn_major=True, epi=ops.EPI_DGELU, aux=sv.u[i])
@@ -410,8 +409,7 @@ class EncoderEngine:
             ops.gemm(sc.dU, W["W1"], out=sc.dh1, b_mn_major=True, residual=sc.d_pre)
             # ---- attention block: LN1 <- dense(Wo) <- attention <- dense(Wqkv) ----
             ops.layernorm_bwd(sc.dh1, sv.pre1[i], sv.stats1[i], W["ln1w"], G["ln1w"], G["ln1b"], dx=sc.d_pre,
-                              dx_dropped=dpd, drop_p=pd, drop_seed=self._seed(sv, i, 3))
-            ops.colsum(dY, G["bo"])
+                              dx_dropped=dpd, drop_p=pd, drop_seed=self._seed(sv, i, 3), d_bias=G["bo"])
             ops.gemm(dY, sv.ctx[i], out=G["Wo"], a_mn_major=True, b_mn_major=True, accumulate=True,
                      split_k=_pick_split(E, E, T))
             ops.gemm(dY, W["Wo"], out=sc.dctx, b_mn_major=True)

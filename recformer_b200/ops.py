@@ -131,14 +131,15 @@ def layernorm_fwd(x, gamma, beta, eps, out=None, out32=None, stats=None):
     return out if out is not None else out32
 
 
-def layernorm_bwd(dy, x, stats, gamma, d_gamma, d_beta, dx=None, dx_dropped=None, drop_p=0.0, drop_seed=0):
+def layernorm_bwd(dy, x, stats, gamma, d_gamma, d_beta, dx=None, dx_dropped=None, drop_p=0.0, drop_seed=0,
+                  d_bias=None):
     _req(x, torch.float32, "x")
     T, E = x.shape
     if dx is None:
         dx = torch.empty(T, E, dtype=torch.bfloat16, device=x.device)
     check(_lib.lib().rf_layernorm_bwd(dy.data_ptr(), x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), dx.data_ptr(),
-                                      _ptr(dx_dropped), drop_p, drop_seed, _ptr(d_gamma), _ptr(d_beta), T, E,
-                                      _stream()), "rf_layernorm_bwd")
+                                      _ptr(dx_dropped), drop_p, drop_seed, _ptr(d_gamma), _ptr(d_beta), _ptr(d_bias),
+                                      T, E, _stream()), "rf_layernorm_bwd")
     return dx
 
 

@@ -167,12 +167,18 @@ def test_layernorm_fwd_bwd():
     ref.backward(dy.float())
     dg = torch.zeros(E, dtype=torch.float32, device=DEV)
     db = torch.zeros(E, dtype=torch.float32, device=DEV)
-    dx = ops.layernorm_bwd(dy, x, stats, gamma, dg, db)
+    dbias = torch.zeros(E, dtype=torch.float32, device=DEV)
+    dx = ops.layernorm_bwd(dy, x, stats, gamma, dg, db, d_bias=dbias)
     assert relerr(dx, xf.grad) < 1e-2
+    assert relerr(dbias, dx.float().sum(0)) < 1e-3
     assert relerr(dg, gf.grad) < 1e-3 and relerr(db, bf.grad) < 1e-3
     cs = torch.zeros(E, dtype=torch.float32, device=DEV)
     ops.colsum(dy, cs)
     assert relerr(cs, dy.float().sum(0)) < 1e-4
+    wide = rnd(777, 2304, seed=9)
+    cs2 = torch.zeros(2304, dtype=torch.float32, device=DEV)
+    ops.colsum(wide, cs2)
+    assert relerr(cs2, wide.float().sum(0)) < 1e-4
 
 
 # ----------------------------------------------------------------------------------- attention

@@ -1,0 +1,74 @@
+"""Micro-driver for ncu: launches each hot kernel once (after one warm-up pass) at the C2 shapes
+(B=16, L=1024, T=16384) and prints CUDA-event timings (3 timed repetitions)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from recformer_b200 import ops
+
+dev = "cuda"
+B, L, H, E, F = 16, 1024, 12, 768, 3072
+T = B * L
+g = torch.Generator(device=dev).manual_seed(0)
+rb = lambda *s, sc=1.0: (torch.randn(*s, device=dev, generator=g) * sc).to(torch.bfloat16)
+rf = lambda *s, sc=1.0: torch.randn(*s, device=dev, generator=g) * sc
+x, Wqkv, bqkv = rb(T, E), rb(3 * E, E, sc=0.02), rf(3 * E, sc=0.02)
+W1, b1, W2, b2 = rb(F, E, sc=0.02), rf(F, sc=0.02), rb(E, F, sc=0.02), rf(E, sc=0.02)
+qkv = torch.empty(T, 3 * E, dtype=torch.bfloat16, device=dev)
+u = torch.empty(T, F, dtype=torch.bfloat16, device=dev); gl = torch.empty_like(u)
+res32 = rf(T, E); pre = torch.empty(T, E, dtype=torch.float32, device=dev)
+dY = rb(T, E, sc=0.01); dU = torch.empty(T, F, dtype=torch.bfloat16, device=dev)
+dW1 = torch.zeros(F, E, dtype=torch.float32, device=dev); dWqkv = torch.zeros(3 * E, E, dtype=torch.float32, device=dev)
+mask = torch.ones(B, L, dtype=torch.uint8, device=dev); mask[:, 0] = 2
+for b in range(1, B):
+    mask[b, L - 31 * b:] = 0
+ctx = torch.empty(T, E, dtype=torch.bfloat16, device=dev); lse = torch.empty(B, H, L, device=dev)
+dctx = rb(T, E, sc=0.01); dqkv = torch.empty(T, 3 * E, dtype=torch.bfloat16, device=dev)
+scratch = torch.empty(T, 2 * E, dtype=torch.float32, device=dev)
+gamma, beta = 1 + rf(E, sc=0.1), rf(E, sc=0.1)
+stats = torch.empty(T, 2, device=dev); dg = torch.zeros(E, device=dev); db = torch.zeros(E, device=dev); dbias = torch.zeros(E, device=dev)
+h1 = torch.empty(T, E, dtype=torch.bfloat16, device=dev); h32 = torch.empty(T, E, device=dev)
+dpre = torch.empty(T, E, dtype=torch.bfloat16, device=dev); dpre2 = torch.empty_like(dpre)
+Wg = [rf(E, E, sc=0.03) for _ in range(3)]; bg = [rf(E, sc=0.1) for _ in range(2)]
+gW = [torch.zeros(E, E, device=dev) for _ in range(3)]; gb = [torch.zeros(E, device=dev) for _ in range(2)]
+dx = rb(T, E, sc=0.01)
+cs = torch.zeros(F, device=dev)
+state = {}
+
+CASES = {
+    "gemm_qkv": lambda: ops.gemm(x, Wqkv, out=qkv, bias=bqkv, scale=0.125, scale_ncols=E),
+    "gemm_up_gelu": lambda: ops.gemm(x, W1, out=u, bias=b1, epi=ops.EPI_GELU, out2=gl),
+    "gemm_down_res": lambda: ops.gemm(gl, W2, out=pre, bias=b2, residual=res32, drop_p=0.1, drop_seed=1),
+    "gemm_dgrad_dgelu": lambda: ops.gemm(dY, W2, out=dU, b_mn_major=True, epi=ops.EPI_DGELU, aux=u),
+    "gemm_wgrad_up": lambda: ops.gemm(dU, x, out=dW1, a_mn_major=True, b_mn_major=True, accumulate=True, split_k=2),
+    "gemm_wgrad_qkv": lambda: ops.gemm(qkv, x, out=dWqkv, a_mn_major=True, b_mn_major=True, accumulate=True, split_k=4),
+    "attn_fwd": lambda: ops.band_attn_fwd(qkv, mask, B, L, H, 32, ctx=ctx, lse=lse, drop_p=0.1, drop_seed=3),
+    "attn_bwd": lambda: ops.band_attn_bwd(qkv, mask, B, L, H, 32, ctx, lse, dctx, dqkv, scratch, drop_p=0.1, drop_seed=3),
+    "ln_fwd": lambda: ops.layernorm_fwd(pre, gamma, beta, 1e-5, out=h1, out32=h32, stats=stats),
+    "ln_bwd": lambda: ops.layernorm_bwd(dY, pre, stats, gamma, dg, db, dx=dpre, dx_dropped=dpre2, drop_p=0.1, drop_seed=5, d_bias=dbias),
+    "colsum_3072": lambda: ops.colsum(dU, cs),
+    "global_fwd": lambda: state.__setitem__("sv", ops.global_attn_fwd(x, mask, Wg[0], bg[0], Wg[1], Wg[2], bg[1], B, L, H, ctx, saved=state.get("sv"), drop_p=0.1, drop_seed=7)),
+    "global_bwd": lambda: state.__setitem__("ws", ops.global_attn_bwd(x, mask, Wg[0], bg[0], Wg[1], Wg[2], bg[1], B, L, H, dctx, state["sv"], dx, gW[0], gb[0], gW[1], gW[2], gb[1], ws=state.get("ws"), drop_p=0.1, drop_seed=7)),
+}
+FLOPS = {"gemm_qkv": 2 * T * 3 * E * E, "gemm_up_gelu": 2 * T * F * E, "gemm_down_res": 2 * T * F * E,
+         "gemm_dgrad_dgelu": 2 * T * F * E, "gemm_wgrad_up": 2 * T * F * E, "gemm_wgrad_qkv": 2 * T * 3 * E * E}
+BYTES = {"attn_fwd": T * 4 * E * 2, "attn_bwd": T * 8 * E * 2, "ln_fwd": T * E * (4 + 2 + 4), "ln_bwd": T * E * (2 + 4 + 2 + 2),
+         "colsum_3072": T * F * 2}
+only = sys.argv[1:] or list(CASES)
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+for name in only:
+    CASES[name]()
+torch.cuda.synchronize()
+for name in only:
+    ts = []
+    for _ in range(3):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); CASES[name](); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = min(ts)
+    extra = ""
+    if name in FLOPS:
+        extra = f"  {FLOPS[name] / ms / 1e9:8.1f} TFLOP/s"
+    if name in BYTES:
+        extra = f"  {BYTES[name] / ms / 1e6:8.1f} GB/s (algorithmic)"
+    print(f"{name:18s} {ms * 1e3:9.1f} us{extra}")
