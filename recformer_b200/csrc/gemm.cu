@@ -22,7 +22,8 @@ namespace rf {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;      // TMA warp + MMA warp + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
 
 struct GemmParams {
   void* C;
@@ -50,7 +51,8 @@ struct GemmSmem {
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TILE_BYTES = STAGES * STAGE_BYTES;
   static constexpr uint32_t BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr uint32_t TOTAL = TILE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr uint32_t BIAS_BYTES = 2 * BN * 4;                // per-accumulator-stage bias slab
+  static constexpr uint32_t TOTAL = TILE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;  // + alignment slack
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -72,6 +74,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + S::TILE_BYTES + S::BAR_BYTES);   // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,7 +92,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -110,10 +113,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile % m_tiles;
-        const int rest = tile / m_tiles;
-        const int nt = rest % n_tiles;
-        const int sp = rest / n_tiles;
+        const int nt = tile % n_tiles;
+        const int rest = tile / n_tiles;
+        const int mt = rest % m_tiles;
+        const int sp = rest / m_tiles;
         const int m0 = mt * BM, n0 = nt * BN;
         const int kb0 = sp * k_per_split;
         const int kb1 = min(kb0 + k_per_split, k_blocks_total);
@@ -148,7 +151,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int sp = (tile / m_tiles) / n_tiles;
+      const int sp = (tile / n_tiles) / m_tiles;
       const int kb0 = sp * k_per_split;
       const int kb1 = min(kb0 + k_per_split, k_blocks_total);
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -177,32 +180,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ================= epilogue warps =================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // warp (2..9): TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 2) / 4
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int etid = threadIdx.x - 64;          // 0..255 among the epilogue threads
+    constexpr int CH = BN / 2 / 32;             // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile % m_tiles;
-      const int rest = tile / m_tiles;
-      const int nt = rest % n_tiles;
+      const int nt = tile % n_tiles;
+      const int mt = (tile / n_tiles) % m_tiles;
       const int m0 = mt * BM, n0 = nt * BN;
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < p.M;
+      // stage this tile's bias slab in shared memory (global-load latency off the critical path)
+      float* sb = s_bias + acc * BN;
+      if (p.bias != nullptr && etid < BN) sb[etid] = (n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c * 32, r);
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
+      uint32_t rbuf[2][32];
+      tmem_ld32(tbase, rbuf[0]);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
         tmem_ld_wait();
+        if (c + 1 < CH) {
+          tmem_ld32(tbase + (c + 1) * 32, rbuf[(c + 1) & 1]);   // prefetch the next chunk
+        } else {
+          // accumulator fully read: hand the TMEM stage back to the MMA warp before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        const int lcol = half * (BN / 2) + c * 32;
+        const int col0 = n0 + lcol;
+        if (col0 >= p.N) continue;  // warp-uniform
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rbuf[c & 1][j]);
         if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col0 + j);
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + lcol + j);
             v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
           }
         }
@@ -231,9 +251,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
             if (EPI == RF_EPI_DGELU) {
               const __nv_bfloat16* ax = p.aux + static_cast<size_t>(row) * p.ldaux + col0;
+              uint4 araw[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) araw[j] = *reinterpret_cast<const uint4*>(ax + j * 8);
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
-                const uint4 a = *reinterpret_cast<const uint4*>(ax + j);
+                const uint4 a = araw[j >> 3];
                 float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
                 v[j] *= dgelu_erf(a0.x); v[j + 1] *= dgelu_erf(a0.y); v[j + 2] *= dgelu_erf(a1.x);
                 v[j + 3] *= dgelu_erf(a1.y); v[j + 4] *= dgelu_erf(a2.x); v[j + 5] *= dgelu_erf(a2.y);
@@ -252,17 +275,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (p.residual != nullptr) {
               if (p.residual_f32) {
                 const float* rs = reinterpret_cast<const float*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
+                float4 rr[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rr[j] = *reinterpret_cast<const float4*>(rs + j * 4);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                  const float4 a = *reinterpret_cast<const float4*>(rs + j);
-                  v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
+                  v[j] += rr[j >> 2].x; v[j + 1] += rr[j >> 2].y; v[j + 2] += rr[j >> 2].z; v[j + 3] += rr[j >> 2].w;
                 }
               } else {
                 const __nv_bfloat16* rs =
                     reinterpret_cast<const __nv_bfloat16*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
+                uint4 rr[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(rs + j * 8);
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
-                  const uint4 a = *reinterpret_cast<const uint4*>(rs + j);
+                  const uint4 a = rr[j >> 3];
                   float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
                   v[j] += a0.x; v[j + 1] += a0.y; v[j + 2] += a1.x; v[j + 3] += a1.y;
                   v[j + 4] += a2.x; v[j + 5] += a2.y; v[j + 6] += a3.x; v[j + 7] += a3.y;
@@ -278,11 +306,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                "f"(v[j + 2]), "f"(v[j + 3])
                                : "memory");
               } else if (p.accumulate) {
+                float4 o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = *reinterpret_cast<float4*>(cf + j * 4);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                  float4 o = *reinterpret_cast<float4*>(cf + j);
-                  o.x += v[j]; o.y += v[j + 1]; o.z += v[j + 2]; o.w += v[j + 3];
-                  *reinterpret_cast<float4*>(cf + j) = o;
+                  float4 t = o[j >> 2];
+                  t.x += v[j]; t.y += v[j + 1]; t.z += v[j + 2]; t.w += v[j + 3];
+                  *reinterpret_cast<float4*>(cf + j) = t;
                 }
               } else {
 #pragma unroll
@@ -302,9 +333,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
