@@ -55,11 +55,147 @@ struct GemmSmem {
   static constexpr uint32_t TOTAL = TILE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;  // + alignment slack
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution): one MUFU.RCP, one
+// MUFU.EX2 and 6 FMAs instead of libdevice's branchy erff in the epilogue's critical path.
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float y = 1.0f - poly * t * __expf(-ax * ax);
+  return copysignf(y, x);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float dgelu_erf(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
   const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
+}
+
+
+// Epilogue of one 32-column chunk of one accumulator row (thread = row): bias / scale / GELU /
+// GELU' / dropout / residual, then the store.  `sb` is the tile's bias slab in shared memory.
+template <int EPI, bool OUT_F32>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const GemmParams& p, const float* sb,
+                                               int lcol, int row, bool row_ok, int col0) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + lcol + j);
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        }
+        if (col0 < p.scale_ncols) {  // scale_ncols is a multiple of 32
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= p.scale;
+        }
+        if (row_ok) {
+          const size_t off = static_cast<size_t>(row) * p.ldc + col0;
+          if (EPI == RF_EPI_GELU) {
+            __nv_bfloat16* c1 = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
+            __nv_bfloat16* c2 = reinterpret_cast<__nv_bfloat16*>(p.C2) + off;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u, g;
+              u.x = pack_bf16(v[j], v[j + 1]); u.y = pack_bf16(v[j + 2], v[j + 3]);
+              u.z = pack_bf16(v[j + 4], v[j + 5]); u.w = pack_bf16(v[j + 6], v[j + 7]);
+              // activation of the bf16-rounded pre-activation, so that backward (which only
+              // sees the stored bf16 u) differentiates exactly the function forward applied
+              float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
+              g.x = pack_bf16(gelu_erf(a0.x), gelu_erf(a0.y)); g.y = pack_bf16(gelu_erf(a1.x), gelu_erf(a1.y));
+              g.z = pack_bf16(gelu_erf(a2.x), gelu_erf(a2.y)); g.w = pack_bf16(gelu_erf(a3.x), gelu_erf(a3.y));
+              *reinterpret_cast<uint4*>(c1 + j) = u;
+              *reinterpret_cast<uint4*>(c2 + j) = g;
+            }
+          } else {
+            if (EPI == RF_EPI_DGELU) {
+              const __nv_bfloat16* ax = p.aux + static_cast<size_t>(row) * p.ldaux + col0;
+              uint4 araw[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) araw[j] = *reinterpret_cast<const uint4*>(ax + j * 8);
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 a = araw[j >> 3];
+                float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+                v[j] *= dgelu_erf(a0.x); v[j + 1] *= dgelu_erf(a0.y); v[j + 2] *= dgelu_erf(a1.x);
+                v[j + 3] *= dgelu_erf(a1.y); v[j + 4] *= dgelu_erf(a2.x); v[j + 5] *= dgelu_erf(a2.y);
+                v[j + 6] *= dgelu_erf(a3.x); v[j + 7] *= dgelu_erf(a3.y);
+              }
+            }
+            if (p.drop_thresh != 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint64_t grp = (static_cast<uint64_t>(row) * p.N + col0 + j) >> 3;
+                const uint32_t keep = dropout_keep8(p.drop_seed, grp, p.drop_thresh);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[j + e] = ((keep >> e) & 1u) ? v[j + e] * p.drop_scale : 0.0f;
+              }
+            }
+            if (p.residual != nullptr) {
+              if (p.residual_f32) {
+                const float* rs = reinterpret_cast<const float*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
+                float4 rr[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rr[j] = *reinterpret_cast<const float4*>(rs + j * 4);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  v[j] += rr[j >> 2].x; v[j + 1] += rr[j >> 2].y; v[j + 2] += rr[j >> 2].z; v[j + 3] += rr[j >> 2].w;
+                }
+              } else {
+                const __nv_bfloat16* rs =
+                    reinterpret_cast<const __nv_bfloat16*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
+                uint4 rr[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(rs + j * 8);
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  const uint4 a = rr[j >> 3];
+                  float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+                  v[j] += a0.x; v[j + 1] += a0.y; v[j + 2] += a1.x; v[j + 3] += a1.y;
+                  v[j + 4] += a2.x; v[j + 5] += a2.y; v[j + 6] += a3.x; v[j + 7] += a3.y;
+                }
+              }
+            }
+            if (OUT_F32) {
+              float* cf = reinterpret_cast<float*>(p.C) + off;
+              if (p.split_k > 1) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cf + j), "f"(v[j]), "f"(v[j + 1]),
+                               "f"(v[j + 2]), "f"(v[j + 3])
+                               : "memory");
+              } else if (p.accumulate) {
+                float4 o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = *reinterpret_cast<float4*>(cf + j * 4);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 t = o[j >> 2];
+                  t.x += v[j]; t.y += v[j + 1]; t.z += v[j + 2]; t.w += v[j + 3];
+                  *reinterpret_cast<float4*>(cf + j) = t;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(cf + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              }
+            } else {
+              __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 o;
+                o.x = pack_bf16(v[j], v[j + 1]); o.y = pack_bf16(v[j + 2], v[j + 3]);
+                o.z = pack_bf16(v[j + 4], v[j + 5]); o.w = pack_bf16(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(cb + j) = o;
+              }
+            }
+          }
+        }
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32>
@@ -216,122 +352,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int lcol = half * (BN / 2) + c * 32;
         const int col0 = n0 + lcol;
         if (col0 >= p.N) continue;  // warp-uniform
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rbuf[c & 1][j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sb + lcol + j);
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-          }
-        }
-        if (col0 < p.scale_ncols) {  // scale_ncols is a multiple of 32
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= p.scale;
-        }
-        if (row_ok) {
-          const size_t off = static_cast<size_t>(row) * p.ldc + col0;
-          if (EPI == RF_EPI_GELU) {
-            __nv_bfloat16* c1 = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
-            __nv_bfloat16* c2 = reinterpret_cast<__nv_bfloat16*>(p.C2) + off;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u, g;
-              u.x = pack_bf16(v[j], v[j + 1]); u.y = pack_bf16(v[j + 2], v[j + 3]);
-              u.z = pack_bf16(v[j + 4], v[j + 5]); u.w = pack_bf16(v[j + 6], v[j + 7]);
-              // activation of the bf16-rounded pre-activation, so that backward (which only
-              // sees the stored bf16 u) differentiates exactly the function forward applied
-              float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
-              g.x = pack_bf16(gelu_erf(a0.x), gelu_erf(a0.y)); g.y = pack_bf16(gelu_erf(a1.x), gelu_erf(a1.y));
-              g.z = pack_bf16(gelu_erf(a2.x), gelu_erf(a2.y)); g.w = pack_bf16(gelu_erf(a3.x), gelu_erf(a3.y));
-              *reinterpret_cast<uint4*>(c1 + j) = u;
-              *reinterpret_cast<uint4*>(c2 + j) = g;
-            }
-          } else {
-            if (EPI == RF_EPI_DGELU) {
-              const __nv_bfloat16* ax = p.aux + static_cast<size_t>(row) * p.ldaux + col0;
-              uint4 araw[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) araw[j] = *reinterpret_cast<const uint4*>(ax + j * 8);
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 a = araw[j >> 3];
-                float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
-                v[j] *= dgelu_erf(a0.x); v[j + 1] *= dgelu_erf(a0.y); v[j + 2] *= dgelu_erf(a1.x);
-                v[j + 3] *= dgelu_erf(a1.y); v[j + 4] *= dgelu_erf(a2.x); v[j + 5] *= dgelu_erf(a2.y);
-                v[j + 6] *= dgelu_erf(a3.x); v[j + 7] *= dgelu_erf(a3.y);
-              }
-            }
-            if (p.drop_thresh != 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint64_t grp = (static_cast<uint64_t>(row) * p.N + col0 + j) >> 3;
-                const uint32_t keep = dropout_keep8(p.drop_seed, grp, p.drop_thresh);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[j + e] = ((keep >> e) & 1u) ? v[j + e] * p.drop_scale : 0.0f;
-              }
-            }
-            if (p.residual != nullptr) {
-              if (p.residual_f32) {
-                const float* rs = reinterpret_cast<const float*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
-                float4 rr[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) rr[j] = *reinterpret_cast<const float4*>(rs + j * 4);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  v[j] += rr[j >> 2].x; v[j + 1] += rr[j >> 2].y; v[j + 2] += rr[j >> 2].z; v[j + 3] += rr[j >> 2].w;
-                }
-              } else {
-                const __nv_bfloat16* rs =
-                    reinterpret_cast<const __nv_bfloat16*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
-                uint4 rr[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(rs + j * 8);
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  const uint4 a = rr[j >> 3];
-                  float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
-                  v[j] += a0.x; v[j + 1] += a0.y; v[j + 2] += a1.x; v[j + 3] += a1.y;
-                  v[j + 4] += a2.x; v[j + 5] += a2.y; v[j + 6] += a3.x; v[j + 7] += a3.y;
-                }
-              }
-            }
-            if (OUT_F32) {
-              float* cf = reinterpret_cast<float*>(p.C) + off;
-              if (p.split_k > 1) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cf + j), "f"(v[j]), "f"(v[j + 1]),
-                               "f"(v[j + 2]), "f"(v[j + 3])
-                               : "memory");
-              } else if (p.accumulate) {
-                float4 o[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = *reinterpret_cast<float4*>(cf + j * 4);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  float4 t = o[j >> 2];
-                  t.x += v[j]; t.y += v[j + 1]; t.z += v[j + 2]; t.w += v[j + 3];
-                  *reinterpret_cast<float4*>(cf + j) = t;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(cf + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              }
-            } else {
-              __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 o;
-                o.x = pack_bf16(v[j], v[j + 1]); o.y = pack_bf16(v[j + 2], v[j + 3]);
-                o.z = pack_bf16(v[j + 4], v[j + 5]); o.w = pack_bf16(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(cb + j) = o;
-              }
-            }
-          }
-        }
+        epilogue_chunk<EPI, OUT_F32>(rbuf[c & 1], p, sb, lcol, row, row_ok, col0);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -345,20 +366,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32>
-static int launch_gemm(const rf_gemm_args* a, cudaStream_t stream) {
-  using S = GemmSmem<BN>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, OUT_F32>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
-  }
-  const CUtensorMap* tmA = A_MN ? get_tmap_2d(a->A, a->K, a->M, a->lda, 64) : get_tmap_2d(a->A, a->M, a->K, a->lda, BM);
-  if (!tmA) return RF_ERR_CUDA;
-  const CUtensorMap* tmB = B_MN ? get_tmap_2d(a->B, a->K, a->N, a->ldb, 64) : get_tmap_2d(a->B, a->N, a->K, a->ldb, BN);
-  if (!tmB) return RF_ERR_CUDA;
-  GemmParams p;
+
+
+static void fill_params(const rf_gemm_args* a, GemmParams& p) {
   p.C = a->C; p.C2 = a->C2; p.bias = a->bias;
   p.residual = a->residual;
   p.residual_f32 = a->residual_f32;
@@ -378,6 +388,225 @@ static int launch_gemm(const rf_gemm_args* a, cudaStream_t stream) {
   p.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   p.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
   p.drop_seed = a->drop_seed;
+}
+
+// ==============================================================================================
+// CTA-pair kernel: a 2-CTA cluster computes one 256 x 256 tile with tcgen05.mma.cta_group::2.
+// Each CTA stages its own 128 rows of A and its own 128-row half of B (32 KB per 64-wide K slab
+// instead of 48 KB), so the per-SM L2->SM ingest that bounds the single-CTA kernel drops by a third
+// and 6 ring stages fit.  The leader CTA's MMA thread issues for both; tcgen05.commit multicasts
+// the "slot free" / "accumulator ready" arrivals to both CTAs; both epilogues report "accumulator
+// drained" to the leader.
+// ==============================================================================================
+constexpr int P_BN = 256;        // pair tile N
+constexpr int P_STAGES = 6;
+constexpr uint32_t P_A_BYTES = 128 * BK * 2, P_B_BYTES = 128 * BK * 2, P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
+constexpr uint32_t P_TILE_BYTES = P_STAGES * P_STAGE_BYTES;
+constexpr uint32_t P_BAR_BYTES = (2 * P_STAGES + 4) * 8 + 16;
+constexpr uint32_t P_SMEM = P_TILE_BYTES + P_BAR_BYTES + 2 * P_BN * 4 + 1024;
+
+template <bool A_MN, bool B_MN, int EPI, bool OUT_F32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P_TILE_BYTES);
+  uint64_t* empty_bar = full_bar + P_STAGES;
+  uint64_t* tfull_bar = empty_bar + P_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + P_TILE_BYTES + P_BAR_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  const int m_tiles = (p.M + 255) / 256;
+  const int n_tiles = (p.N + P_BN - 1) / P_BN;
+  const int k_blocks_total = (p.K + BK - 1) / BK;
+  const int k_per_split = (k_blocks_total + p.split_k - 1) / p.split_k;
+  const int total_tiles = m_tiles * n_tiles * p.split_k;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);     // leader's copy is the live one: expect_tx covers both CTAs' slabs
+      mbar_init(&empty_bar[s], 1);    // multicast tcgen05.commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);                // multicast tcgen05.commit
+      mbar_init(&tempty_bar[s], 2 * EPI_WARPS);   // leader's copy: epilogue warps of both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs) =================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        const int nt = tile % n_tiles;
+        const int rest = tile / n_tiles;
+        const int mt = rest % m_tiles;
+        const int sp = rest / m_tiles;
+        const int m0 = mt * 256 + static_cast<int>(rank) * 128;       // this CTA's 128 rows of A / of the output
+        const int n0 = nt * P_BN + static_cast<int>(rank) * 128;      // this CTA's half of the B tile
+        const int kb0 = sp * k_per_split;
+        const int kb1 = min(kb0 + k_per_split, k_blocks_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * P_STAGE_BYTES);
+          const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's barrier
+          uint8_t* sa = smem + stage * P_STAGE_BYTES;
+          uint8_t* sb = sa + P_A_BYTES;
+          if (!A_MN) {
+            tma_load_2d_pair(sa, &tmA, fb, kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_2d_pair(sa + c * 8192, &tmA, fb, m0 + c * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d_pair(sb, &tmB, fb, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_2d_pair(sb + c * 8192, &tmB, fb, n0 + c * 64, kb * BK);
+          }
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, P_BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        const int sp = (tile / n_tiles) / m_tiles;
+        const int kb0 = sp * k_per_split;
+        const int kb1 = min(kb0 + k_per_split, k_blocks_total);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * P_BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * P_STAGE_BYTES);
+            const uint32_t sb = sa + P_A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t adesc = A_MN ? umma_smem_desc(sa + k * 2048, 8192, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
+              const uint64_t bdesc = B_MN ? umma_smem_desc(sb + k * 2048, 8192, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
+              umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[acc]);
+          }
+          __syncwarp();
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue warps (both CTAs, each on its own 128 accumulator rows) =================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int etid = threadIdx.x - 64;
+    constexpr int CH = P_BN / 2 / 32;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs) {
+      const int nt = tile % n_tiles;
+      const int mt = (tile / n_tiles) % m_tiles;
+      const int m0 = mt * 256 + static_cast<int>(rank) * 128, n0 = nt * P_BN;
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      float* sb = s_bias + acc * P_BN;
+      if (p.bias != nullptr && etid < P_BN) sb[etid] = (n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * P_BN + half * (P_BN / 2);
+      uint32_t rbuf[2][32];
+      tmem_ld32(tbase, rbuf[0]);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        tmem_ld_wait();
+        if (c + 1 < CH) {
+          tmem_ld32(tbase + (c + 1) * 32, rbuf[(c + 1) & 1]);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));   // leader's barrier
+        }
+        const int lcol = half * (P_BN / 2) + c * 32;
+        const int col0 = n0 + lcol;
+        if (col0 >= p.N) continue;
+        epilogue_chunk<EPI, OUT_F32>(rbuf[c & 1], p, sb, lcol, row, row_ok, col0);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();     // neither CTA may exit (or free TMEM) while its peer still uses its smem / barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+template <bool A_MN, bool B_MN, int EPI, bool OUT_F32>
+static int launch_gemm_pair(const rf_gemm_args* a, cudaStream_t stream) {
+  auto kern = gemm_pair_kernel<A_MN, B_MN, EPI, OUT_F32>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+    attr_set = true;
+  }
+  const CUtensorMap* tmA = A_MN ? get_tmap_2d(a->A, a->K, a->M, a->lda, 64) : get_tmap_2d(a->A, a->M, a->K, a->lda, 128);
+  if (!tmA) return RF_ERR_CUDA;
+  const CUtensorMap* tmB = B_MN ? get_tmap_2d(a->B, a->K, a->N, a->ldb, 64) : get_tmap_2d(a->B, a->N, a->K, a->ldb, 128);
+  if (!tmB) return RF_ERR_CUDA;
+  GemmParams p;
+  fill_params(a, p);
+  const int m_tiles = (a->M + 255) / 256, n_tiles = (a->N + P_BN - 1) / P_BN;
+  const int total = m_tiles * n_tiles * p.split_k;
+  const int pairs = total < sm_count() / 2 ? total : sm_count() / 2;
+  kern<<<2 * pairs, GEMM_THREADS, P_SMEM, stream>>>(*tmA, *tmB, p);
+  return check_launch("rf_gemm_bf16(pair)");
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32>
+static int launch_gemm(const rf_gemm_args* a, cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, OUT_F32>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  const CUtensorMap* tmA = A_MN ? get_tmap_2d(a->A, a->K, a->M, a->lda, 64) : get_tmap_2d(a->A, a->M, a->K, a->lda, BM);
+  if (!tmA) return RF_ERR_CUDA;
+  const CUtensorMap* tmB = B_MN ? get_tmap_2d(a->B, a->K, a->N, a->ldb, 64) : get_tmap_2d(a->B, a->N, a->K, a->ldb, BN);
+  if (!tmB) return RF_ERR_CUDA;
+  GemmParams p;
+  fill_params(a, p);
   const int m_tiles = (a->M + BM - 1) / BM, n_tiles = (a->N + BN - 1) / BN;
   const int total = m_tiles * n_tiles * p.split_k;
   const int grid = total < sm_count() ? total : sm_count();
@@ -403,22 +632,33 @@ extern "C" int rf_gemm_bf16(const rf_gemm_args* a, rf_stream_t stream_) {
   RF_REQUIRE(a->epi != RF_EPI_GELU || (a->C2 != nullptr && !a->out_f32), "rf_gemm_bf16: GELU epilogue needs C2, bf16");
   RF_REQUIRE(a->epi != RF_EPI_DGELU || a->aux != nullptr, "rf_gemm_bf16: DGELU epilogue needs aux");
   const int layout = (a->a_mn_major ? 2 : 0) | (a->b_mn_major ? 1 : 0);
-  // Tile width: 256 for the big projections; 128 where that fills the machine better.
+  // CTA-pair kernel (256 x 256 tiles) whenever there is more than one 128-row slab of output;
+  // the single-CTA kernel covers small problems (e.g. one short sequence).
+  const bool pair = a->M > 128 && a->N >= 128;
   if (layout == 0) {
-    if (a->epi == RF_EPI_GELU) return launch_gemm<256, false, false, RF_EPI_GELU, false>(a, stream);
+    if (a->epi == RF_EPI_GELU)
+      return pair ? launch_gemm_pair<false, false, RF_EPI_GELU, false>(a, stream)
+                  : launch_gemm<256, false, false, RF_EPI_GELU, false>(a, stream);
     RF_REQUIRE(a->epi == RF_EPI_NONE, "rf_gemm_bf16: epilogue %d unsupported for K-major x K-major", a->epi);
-    if (a->out_f32) return launch_gemm<128, false, false, RF_EPI_NONE, true>(a, stream);
-    return launch_gemm<256, false, false, RF_EPI_NONE, false>(a, stream);
+    if (a->out_f32)
+      return pair ? launch_gemm_pair<false, false, RF_EPI_NONE, true>(a, stream)
+                  : launch_gemm<128, false, false, RF_EPI_NONE, true>(a, stream);
+    return pair ? launch_gemm_pair<false, false, RF_EPI_NONE, false>(a, stream)
+                : launch_gemm<256, false, false, RF_EPI_NONE, false>(a, stream);
   }
   if (layout == 1) {  // dgrad: dY[M,K] (K-major) x W stored [K,N]
     RF_REQUIRE(!a->out_f32, "rf_gemm_bf16: fp32 output unsupported for the dgrad layout");
-    if (a->epi == RF_EPI_DGELU) return launch_gemm<256, false, true, RF_EPI_DGELU, false>(a, stream);
+    if (a->epi == RF_EPI_DGELU)
+      return pair ? launch_gemm_pair<false, true, RF_EPI_DGELU, false>(a, stream)
+                  : launch_gemm<256, false, true, RF_EPI_DGELU, false>(a, stream);
     RF_REQUIRE(a->epi == RF_EPI_NONE, "rf_gemm_bf16: epilogue %d unsupported for the dgrad layout", a->epi);
-    return launch_gemm<256, false, true, RF_EPI_NONE, false>(a, stream);
+    return pair ? launch_gemm_pair<false, true, RF_EPI_NONE, false>(a, stream)
+                : launch_gemm<256, false, true, RF_EPI_NONE, false>(a, stream);
   }
   if (layout == 3) {  // wgrad: dY^T x X, both stored [K, *]
     RF_REQUIRE(a->out_f32 && a->epi == RF_EPI_NONE, "rf_gemm_bf16: the wgrad layout writes fp32 without epilogue");
-    return launch_gemm<128, true, true, RF_EPI_NONE, true>(a, stream);
+    return pair ? launch_gemm_pair<true, true, RF_EPI_NONE, true>(a, stream)
+                : launch_gemm<128, true, true, RF_EPI_NONE, true>(a, stream);
   }
   return set_error(RF_ERR_INVALID, "rf_gemm_bf16: layout a_mn_major=1,b_mn_major=0 is not instantiated");
 }

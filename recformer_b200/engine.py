@@ -23,14 +23,17 @@ from . import ops
 
 
 def _pick_split(M: int, N: int, K: int, sms: int = 148) -> int:
-    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    """Split-K factor for a weight-gradient GEMM (K = tokens): fill the 74 CTA pairs that each own
+    a 256 x 256 output tile, keeping at least 8 K-blocks (512 tokens) per slice."""
+    tiles = ((M + 255) // 256) * ((N + 255) // 256)
+    pairs = sms // 2
     kb = (K + 63) // 64
     best, best_eff = 1, 0.0
-    for s in range(1, 9):
-        if kb // s < 4 and s > 1:
+    for s in range(1, 17):
+        if s > 1 and kb // s < 8:
             break
         total = tiles * s
-        eff = total / (((total + sms - 1) // sms) * sms)
+        eff = total / (((total + pairs - 1) // pairs) * pairs)
         if eff > best_eff + 0.02:
             best, best_eff = s, eff
     return best

@@ -120,7 +120,7 @@ def test_flat_parameter_plan():
 
 
 def test_split_k_heuristic():
-    assert _pick_split(2304, 768, 16384) >= 2       # 108 tiles on 148 SMs -> split
+    assert _pick_split(2304, 768, 16384) >= 2       # 27 pair-tiles on 74 CTA pairs -> split
     assert _pick_split(768, 768, 128) == 1           # too few K blocks to split
     assert 1 <= _pick_split(3072, 768, 16384) <= 8
 
