@@ -20,7 +20,7 @@
 
 namespace rf {
 
-constexpr int AB_THREADS = 128;
+constexpr int AB_THREADS = 256;
 constexpr int AB_W = 32;
 constexpr int AB_NK = 128 + 2 * AB_W;   // 192
 constexpr int AB_NT = AB_NK + 16;       // 208
@@ -34,7 +34,8 @@ constexpr uint32_t AB_OFF_P = AB_OFF_V + AB_KV_BYTES;
 constexpr uint32_t AB_OFF_DS = AB_OFF_P + AB_P_BYTES;
 constexpr uint32_t AB_OFF_FLAG = AB_OFF_DS + AB_P_BYTES;
 constexpr uint32_t AB_OFF_BAR = AB_OFF_FLAG + 208;
-constexpr uint32_t AB_SMEM = AB_OFF_BAR + 64 + 1024;
+constexpr uint32_t AB_OFF_DELTA = AB_OFF_BAR + 64;
+constexpr uint32_t AB_SMEM = AB_OFF_DELTA + 2 * 128 * 4 + 1024;
 static_assert(AB_OFF_V % 1024 == 0 && AB_OFF_P % 1024 == 0, "swizzled tiles need 1024B alignment");
 static_assert(AB_SMEM <= 227 * 1024, "shared memory budget");
 
@@ -65,8 +66,12 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + AB_OFF_BAR);
   uint64_t* bar_mma = bar_load + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
+  float* s_delta = reinterpret_cast<float*>(smem + AB_OFF_DELTA);   // [2][128] partial row sums
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  // 8 warps: TMEM lane quadrant = warp % 4 (rows 32*quad..), `part` = warp / 4 splits every row's
+  // columns between two threads so that 8 warps (not 4) cover the softmax-backward arithmetic.
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, part = warp >> 2;
   const int tiles_per_seq = (p.L + 127) / 128;
   const int tile = blockIdx.x % tiles_per_seq;
   const int h = (blockIdx.x / tiles_per_seq) % p.H;
@@ -133,38 +138,43 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   mbar_wait(bar_mma, 0);
   tc_fence_after();
 
-  const int r = tid;
+  const int r = quad * 32 + lane;       // query row of the tile == TMEM lane
   const int i = i0 + r;
   const bool in_seq = i < p.L;
   const bool is_global_row = (i == 0) && (mrow[0] == 2);
   const bool row_valid = in_seq && (mrow[in_seq ? i : 0] != 0) && !is_global_row;
   const float lse = in_seq ? p.lse[(static_cast<size_t>(b) * p.H + h) * p.L + i] : 0.f;
-  const uint32_t lane_base = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  constexpr int WIN_CH = 2 * W / 32 + 1;
+  const uint32_t lane_base = tmem + (static_cast<uint32_t>(quad * 32) << 16);
   const float LOG2E = 1.4426950408889634f;
   const float lse2 = lse * LOG2E;
   const uint64_t rowid = (static_cast<uint64_t>(b) * p.H + h) * p.L + (in_seq ? i : 0);
   constexpr int DGRP = NT / 8;
   const bool g_ok = kflag[NK] != 0;
+  // window chunks of this row block: quad, quad+1 (part 0) and quad+2 + the CLS column (part 1)
+  const int cc_lo = quad + (part == 0 ? 0 : 2);
+  const int cc_hi = quad + (part == 0 ? 2 : 3);
 
-  // ---- pass A: delta = sum_c P'_c dP_c (P' = dropout(P)) ----
+  auto chunk_keep = [&](int cc) -> uint32_t {
+    if (p.drop_thresh == 0) return 0xFFFFFFFFu;
+    uint32_t km = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c0 = cc * 32 + u * 8;
+      if (c0 + 7 >= r && c0 <= r + 2 * W)
+        km |= dropout_keep8(p.drop_seed, rowid * DGRP + (c0 >> 3), p.drop_thresh) << (u * 8);
+    }
+    return km;
+  };
+
+  // ---- pass A: delta = sum_c P'_c dP_c (P' = dropout(P)); each part sums its own columns ----
   float delta = 0.f;
 #pragma unroll 1
-  for (int cc = warp; cc < warp + WIN_CH; ++cc) {
+  for (int cc = cc_lo; cc < cc_hi; ++cc) {
     uint32_t sv[32], dv[32];
     tmem_ld32(lane_base + TM_S + cc * 32, sv);
     tmem_ld32(lane_base + TM_DP + cc * 32, dv);
     tmem_ld_wait();
-    uint32_t keepm = 0xFFFFFFFFu;
-    if (p.drop_thresh != 0) {
-      keepm = 0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c0 = cc * 32 + u * 8;
-        if (c0 + 7 >= r && c0 <= r + 2 * W)
-          keepm |= dropout_keep8(p.drop_seed, rowid * DGRP + (c0 >> 3), p.drop_thresh) << (u * 8);
-      }
-    }
+    const uint32_t keepm = chunk_keep(cc);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int c = cc * 32 + j;
@@ -174,40 +184,40 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     }
   }
   delta *= p.drop_scale;
-  uint32_t gs[16], gd[16];
-  tmem_ld16(lane_base + TM_S + NK, gs);
-  tmem_ld16(lane_base + TM_DP + NK, gd);
-  tmem_ld_wait();
-  float pg = (row_valid && g_ok) ? exp2f(__uint_as_float(gs[0]) * LOG2E - lse2) : 0.f;   // undropped
-  float pg_d = pg;                                                                         // dropped
-  float keep_g = 1.f;
-  if (p.drop_thresh != 0) {
-    const uint32_t keep = dropout_keep8(p.drop_seed, rowid * DGRP + (NK >> 3), p.drop_thresh);
-    keep_g = (keep & 1u) ? p.drop_scale : 0.f;
-    pg_d = pg * keep_g;
+  float pg = 0.f, pg_d = 0.f, keep_g = 1.f, dpg = 0.f;
+  if (part == 1) {   // warp-uniform
+    uint32_t gs[16], gd[16];
+    tmem_ld16(lane_base + TM_S + NK, gs);
+    tmem_ld16(lane_base + TM_DP + NK, gd);
+    tmem_ld_wait();
+    pg = (row_valid && g_ok) ? exp2f(__uint_as_float(gs[0]) * LOG2E - lse2) : 0.f;   // undropped
+    pg_d = pg;
+    if (p.drop_thresh != 0) {
+      const uint32_t keep = dropout_keep8(p.drop_seed, rowid * DGRP + (NK >> 3), p.drop_thresh);
+      keep_g = (keep & 1u) ? p.drop_scale : 0.f;
+      pg_d = pg * keep_g;
+    }
+    dpg = __uint_as_float(gd[0]);
+    delta += pg_d * dpg;
   }
-  const float dpg = __uint_as_float(gd[0]);
-  delta += pg_d * dpg;
+  s_delta[part * 128 + r] = delta;
+  __syncthreads();
+  delta = s_delta[r] + s_delta[128 + r];
 
-  // ---- pass B: P' and dS -> shared memory ----
+  // ---- pass B: P' and dS -> shared memory (window chunks as in pass A; the remaining all-zero
+  //      chunks are split by parity) ----
 #pragma unroll 1
   for (int cc = 0; cc < NK / 32; ++cc) {
+    const bool in_win = cc >= quad && cc < quad + 3;
+    const bool mine = in_win ? (cc >= cc_lo && cc < cc_hi) : ((cc & 1) == part);
+    if (!mine) continue;   // warp-uniform
     uint4 po[4], so[4];
-    if (cc >= warp && cc < warp + WIN_CH) {
+    if (in_win) {
       uint32_t sv[32], dv[32];
       tmem_ld32(lane_base + TM_S + cc * 32, sv);
       tmem_ld32(lane_base + TM_DP + cc * 32, dv);
       tmem_ld_wait();
-      uint32_t keepm = 0xFFFFFFFFu;
-      if (p.drop_thresh != 0) {
-        keepm = 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c0 = cc * 32 + u * 8;
-          if (c0 + 7 >= r && c0 <= r + 2 * W)
-            keepm |= dropout_keep8(p.drop_seed, rowid * DGRP + (c0 >> 3), p.drop_thresh) << (u * 8);
-        }
-      }
+      const uint32_t keepm = chunk_keep(cc);
       float pr[32], ds[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -239,11 +249,13 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     }
   }
   {
-    // global chunk = P/dS chunk 3 (columns 192..255): column 192 holds the CLS key, the rest is zero
+    // global chunk = P/dS chunk 3 (columns 192..255): column 192 holds the CLS key, the rest is zero;
+    // part 1 (which owns pg) writes units 0..3, part 0 units 4..7
     const float dsg = pg * (keep_g * dpg - delta);
     const uint32_t roff = 3 * 16384 + r * 128;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int uu = 0; uu < 4; ++uu) {
+      const int u = part == 1 ? uu : uu + 4;
       const uint32_t o = roff + ((u ^ (r & 7)) << 4);
       *reinterpret_cast<uint4*>(sP + o) = (u == 0) ? make_uint4(pack_bf16(pg_d, 0.f), 0, 0, 0) : make_uint4(0, 0, 0, 0);
       *reinterpret_cast<uint4*>(sDS + o) = (u == 0) ? make_uint4(pack_bf16(dsg, 0.f), 0, 0, 0) : make_uint4(0, 0, 0, 0);
@@ -279,55 +291,61 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   __syncwarp();
   mbar_wait(bar_mma, 1);
   tc_fence_after();
+  // every shared-memory operand is dead now: the P region becomes 8 per-warp 4 KB transpose slabs
+  uint8_t* slab = sP + warp * 4096;
 
-  // ---- dQ (x 1/sqrt(D): gradient w.r.t. the unscaled projection) ----
+  // ---- dQ (x 1/sqrt(D): gradient w.r.t. the unscaled projection); part p owns columns 32p..32p+31 ----
   {
-    __nv_bfloat16* orow = p.dqkv + (static_cast<size_t>(b) * p.L + (in_seq ? i : 0)) * 3 * E + h * AB_D;
+    uint32_t v[32];
+    tmem_ld32(lane_base + TM_DQ + part * 32, v);
+    tmem_ld_wait();
+    if (in_seq) {
+      __nv_bfloat16* orow = p.dqkv + (static_cast<size_t>(b) * p.L + i) * 3 * E + h * AB_D + part * 32;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t v[32];
-      tmem_ld32(lane_base + TM_DQ + half * 32, v);
-      tmem_ld_wait();
-      if (in_seq) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 o;
-          o.x = pack_bf16(__uint_as_float(v[j]) * 0.125f, __uint_as_float(v[j + 1]) * 0.125f);
-          o.y = pack_bf16(__uint_as_float(v[j + 2]) * 0.125f, __uint_as_float(v[j + 3]) * 0.125f);
-          o.z = pack_bf16(__uint_as_float(v[j + 4]) * 0.125f, __uint_as_float(v[j + 5]) * 0.125f);
-          o.w = pack_bf16(__uint_as_float(v[j + 6]) * 0.125f, __uint_as_float(v[j + 7]) * 0.125f);
-          *reinterpret_cast<uint4*>(orow + half * 32 + j) = o;
-        }
+      for (int j = 0; j < 32; j += 8) {
+        uint4 o;
+        o.x = pack_bf16(__uint_as_float(v[j]) * 0.125f, __uint_as_float(v[j + 1]) * 0.125f);
+        o.y = pack_bf16(__uint_as_float(v[j + 2]) * 0.125f, __uint_as_float(v[j + 3]) * 0.125f);
+        o.z = pack_bf16(__uint_as_float(v[j + 4]) * 0.125f, __uint_as_float(v[j + 5]) * 0.125f);
+        o.w = pack_bf16(__uint_as_float(v[j + 6]) * 0.125f, __uint_as_float(v[j + 7]) * 0.125f);
+        *reinterpret_cast<uint4*>(orow + j) = o;
       }
     }
   }
-  // ---- dK / dV: thread r owns key column c = hh*128 + r of the tile ----
+  // ---- dK / dV: TMEM lane = key column c = hh*128 + r of the tile.  Each 32-key x 32-dim chunk is
+  //      transposed through the warp's slab so that one red.add.v4 instruction covers 4 key rows x
+  //      128 contiguous bytes (4 LSU wavefronts) instead of 32 rows x 16 bytes. ----
+#pragma unroll 1
+  for (int t = 0; t < 4; ++t) {       // (hh, which) : which = 0 -> dK, 1 -> dV
+    const int hh = t >> 1, which = t & 1;
+    const uint32_t tcol = (which == 0 ? TM_DK : TM_DV) + hh * 64 + part * 32;
+    uint32_t v[32];
+    tmem_ld32(lane_base + tcol, v);
+    tmem_ld_wait();
+    {
+      uint8_t* srow = slab + lane * 128;
 #pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    const int c = hh * 128 + r;
-    int j = -1;
-    if (c < NK) j = i0 - W + c;
-    else if (c == NK) j = 0;
-    const bool key_ok = (j >= 0 && j < p.L) && kflag[c < NT ? c : 0] && (c <= NK);
-    float* base = p.dkv + (static_cast<size_t>(b) * p.L + (key_ok ? j : 0)) * 2 * E + h * AB_D;
+      for (int u = 0; u < 8; ++u)
+        *reinterpret_cast<uint4*>(srow + ((u ^ (lane & 7)) << 4)) = make_uint4(v[u * 4], v[u * 4 + 1], v[u * 4 + 2], v[u * 4 + 3]);
+    }
+    __syncwarp();
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {   // 0: dK, 1: dV
-      const uint32_t tcol = (which == 0 ? TM_DK : TM_DV) + hh * 64;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t v[32];
-        tmem_ld32(lane_base + tcol + half * 32, v);
-        tmem_ld_wait();
-        if (key_ok) {
-          float* dst = base + which * E + half * 32;
-#pragma unroll
-          for (int q = 0; q < 32; q += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q), "f"(__uint_as_float(v[q])),
-                         "f"(__uint_as_float(v[q + 1])), "f"(__uint_as_float(v[q + 2])), "f"(__uint_as_float(v[q + 3]))
-                         : "memory");
-        }
+    for (int s2 = 0; s2 < 8; ++s2) {
+      const int rl = s2 * 4 + (lane >> 3);          // key row within this warp's 32
+      const int u = lane & 7;                       // 16B unit = 4 floats of the 32-dim chunk
+      const int c = hh * 128 + quad * 32 + rl;      // key column of the tile
+      int j = -1;
+      if (c < NK) j = i0 - W + c;
+      else if (c == NK) j = 0;
+      const bool key_ok = (j >= 0 && j < p.L) && (c <= NK) && kflag[c <= NK ? c : 0];
+      const float4 x = *reinterpret_cast<const float4*>(slab + rl * 128 + ((u ^ (rl & 7)) << 4));
+      if (key_ok) {
+        float* dst = p.dkv + (static_cast<size_t>(b) * p.L + j) * 2 * E + which * E + h * AB_D + part * 32 + u * 4;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
+                     : "memory");
       }
     }
+    __syncwarp();
   }
 
   tc_fence_before();

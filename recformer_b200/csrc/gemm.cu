@@ -45,14 +45,15 @@ struct GemmParams {
 
 template <int BN>
 struct GemmSmem {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256) ? 3 : 5;
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TILE_BYTES = STAGES * STAGE_BYTES;
   static constexpr uint32_t BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
   static constexpr uint32_t BIAS_BYTES = 2 * BN * 4;                // per-accumulator-stage bias slab
-  static constexpr uint32_t TOTAL = TILE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;  // + alignment slack
+  static constexpr uint32_t EPI_STAGE_BYTES = EPI_WARPS * 4096;     // per-warp transpose slab
+  static constexpr uint32_t TOTAL = TILE_BYTES + EPI_STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;  // + alignment slack
 };
 
 // erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution): one MUFU.RCP, one
@@ -75,127 +76,110 @@ __device__ __forceinline__ float dgelu_erf(float x) {
 }
 
 
-// Epilogue of one 32-column chunk of one accumulator row (thread = row): bias / scale / GELU /
-// GELU' / dropout / residual, then the store.  `sb` is the tile's bias slab in shared memory.
+// Epilogue of one 32-row x 32-column accumulator chunk held by a warp (thread = row, as read from
+// TMEM).  The raw fp32 accumulators are first transposed through a 4 KB 128B-swizzled staging slab
+// in shared memory so that every global access of the epilogue is coalesced: in the second phase
+// lane l owns 8 consecutive columns ((l % 4) * 8) of row 8*s + l/4 for s = 0..3, i.e. each warp
+// instruction touches 8 rows x 64..128 contiguous bytes instead of 32 rows x 16 bytes (the
+// row-per-thread pattern costs 32 LSU wavefronts per instruction and bounded the epilogue).
+// Then: bias / scale / GELU / GELU' / dropout / residual, and the store.
 template <int EPI, bool OUT_F32>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const GemmParams& p, const float* sb,
-                                               int lcol, int row, bool row_ok, int col0) {
-        float v[32];
+                                               uint8_t* stage, int lane, int lcol, int row_base, int col0) {
+  // ---- phase 1: thread (= row `lane`) writes its 32 fp32 values, 16B units XOR-swizzled by row ----
+  {
+    uint8_t* srow = stage + lane * 128;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr) {
+    for (int u = 0; u < 8; ++u)
+      *reinterpret_cast<uint4*>(srow + ((u ^ (lane & 7)) << 4)) = make_uint4(r[u * 4], r[u * 4 + 1], r[u * 4 + 2], r[u * 4 + 3]);
+  }
+  __syncwarp();
+  // ---- phase 2: coalesced layout ----
+  const int cq = lane & 3;               // which 8-column group of the chunk
+  const int c8 = col0 + cq * 8;          // first global column owned by this lane
+  float bias8[8];
+  if (p.bias != nullptr) {
+    const float4 b0 = *reinterpret_cast<const float4*>(sb + lcol + cq * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(sb + lcol + cq * 8 + 4);
+    bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
+    bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
+  } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sb + lcol + j);
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-          }
-        }
-        if (col0 < p.scale_ncols) {  // scale_ncols is a multiple of 32
+    for (int e = 0; e < 8; ++e) bias8[e] = 0.f;
+  }
+  const float sc = (col0 < p.scale_ncols) ? p.scale : 1.0f;   // scale_ncols is a multiple of 32
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= p.scale;
-        }
-        if (row_ok) {
-          const size_t off = static_cast<size_t>(row) * p.ldc + col0;
-          if (EPI == RF_EPI_GELU) {
-            __nv_bfloat16* c1 = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
-            __nv_bfloat16* c2 = reinterpret_cast<__nv_bfloat16*>(p.C2) + off;
+  for (int s = 0; s < 4; ++s) {
+    const int rl = s * 8 + (lane >> 2);
+    const int row = row_base + rl;
+    const uint8_t* srow = stage + rl * 128;
+    const float4 x0 = *reinterpret_cast<const float4*>(srow + (((2 * cq) ^ (rl & 7)) << 4));
+    const float4 x1 = *reinterpret_cast<const float4*>(srow + (((2 * cq + 1) ^ (rl & 7)) << 4));
+    if (row >= p.M) continue;
+    float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u, g;
-              u.x = pack_bf16(v[j], v[j + 1]); u.y = pack_bf16(v[j + 2], v[j + 3]);
-              u.z = pack_bf16(v[j + 4], v[j + 5]); u.w = pack_bf16(v[j + 6], v[j + 7]);
-              // activation of the bf16-rounded pre-activation, so that backward (which only
-              // sees the stored bf16 u) differentiates exactly the function forward applied
-              float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
-              g.x = pack_bf16(gelu_erf(a0.x), gelu_erf(a0.y)); g.y = pack_bf16(gelu_erf(a1.x), gelu_erf(a1.y));
-              g.z = pack_bf16(gelu_erf(a2.x), gelu_erf(a2.y)); g.w = pack_bf16(gelu_erf(a3.x), gelu_erf(a3.y));
-              *reinterpret_cast<uint4*>(c1 + j) = u;
-              *reinterpret_cast<uint4*>(c2 + j) = g;
-            }
-          } else {
-            if (EPI == RF_EPI_DGELU) {
-              const __nv_bfloat16* ax = p.aux + static_cast<size_t>(row) * p.ldaux + col0;
-              uint4 araw[4];
+    for (int e = 0; e < 8; ++e) v[e] = (v[e] + bias8[e]) * sc;
+    const size_t off = static_cast<size_t>(row) * p.ldc + c8;
+    if (EPI == RF_EPI_GELU) {
+      uint4 u, g;
+      u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+      // activation of the bf16-rounded pre-activation, so that backward (which only sees the
+      // stored bf16 u) differentiates exactly the function forward applied
+      const float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
+      g.x = pack_bf16(gelu_erf(a0.x), gelu_erf(a0.y)); g.y = pack_bf16(gelu_erf(a1.x), gelu_erf(a1.y));
+      g.z = pack_bf16(gelu_erf(a2.x), gelu_erf(a2.y)); g.w = pack_bf16(gelu_erf(a3.x), gelu_erf(a3.y));
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = u;
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + off) = g;
+      continue;
+    }
+    if (EPI == RF_EPI_DGELU) {
+      const uint4 a = *reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.ldaux + c8);
+      const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+      v[0] *= dgelu_erf(a0.x); v[1] *= dgelu_erf(a0.y); v[2] *= dgelu_erf(a1.x); v[3] *= dgelu_erf(a1.y);
+      v[4] *= dgelu_erf(a2.x); v[5] *= dgelu_erf(a2.y); v[6] *= dgelu_erf(a3.x); v[7] *= dgelu_erf(a3.y);
+    }
+    if (p.drop_thresh != 0) {
+      const uint64_t grp = (static_cast<uint64_t>(row) * p.N + c8) >> 3;
+      const uint32_t keep = dropout_keep8(p.drop_seed, grp, p.drop_thresh);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) araw[j] = *reinterpret_cast<const uint4*>(ax + j * 8);
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 a = araw[j >> 3];
-                float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
-                v[j] *= dgelu_erf(a0.x); v[j + 1] *= dgelu_erf(a0.y); v[j + 2] *= dgelu_erf(a1.x);
-                v[j + 3] *= dgelu_erf(a1.y); v[j + 4] *= dgelu_erf(a2.x); v[j + 5] *= dgelu_erf(a2.y);
-                v[j + 6] *= dgelu_erf(a3.x); v[j + 7] *= dgelu_erf(a3.y);
-              }
-            }
-            if (p.drop_thresh != 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint64_t grp = (static_cast<uint64_t>(row) * p.N + col0 + j) >> 3;
-                const uint32_t keep = dropout_keep8(p.drop_seed, grp, p.drop_thresh);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[j + e] = ((keep >> e) & 1u) ? v[j + e] * p.drop_scale : 0.0f;
-              }
-            }
-            if (p.residual != nullptr) {
-              if (p.residual_f32) {
-                const float* rs = reinterpret_cast<const float*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
-                float4 rr[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) rr[j] = *reinterpret_cast<const float4*>(rs + j * 4);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  v[j] += rr[j >> 2].x; v[j + 1] += rr[j >> 2].y; v[j + 2] += rr[j >> 2].z; v[j + 3] += rr[j >> 2].w;
-                }
-              } else {
-                const __nv_bfloat16* rs =
-                    reinterpret_cast<const __nv_bfloat16*>(p.residual) + static_cast<size_t>(row) * p.ldr + col0;
-                uint4 rr[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(rs + j * 8);
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  const uint4 a = rr[j >> 3];
-                  float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
-                  v[j] += a0.x; v[j + 1] += a0.y; v[j + 2] += a1.x; v[j + 3] += a1.y;
-                  v[j + 4] += a2.x; v[j + 5] += a2.y; v[j + 6] += a3.x; v[j + 7] += a3.y;
-                }
-              }
-            }
-            if (OUT_F32) {
-              float* cf = reinterpret_cast<float*>(p.C) + off;
-              if (p.split_k > 1) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cf + j), "f"(v[j]), "f"(v[j + 1]),
-                               "f"(v[j + 2]), "f"(v[j + 3])
-                               : "memory");
-              } else if (p.accumulate) {
-                float4 o[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = *reinterpret_cast<float4*>(cf + j * 4);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  float4 t = o[j >> 2];
-                  t.x += v[j]; t.y += v[j + 1]; t.z += v[j + 2]; t.w += v[j + 3];
-                  *reinterpret_cast<float4*>(cf + j) = t;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(cf + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              }
-            } else {
-              __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 o;
-                o.x = pack_bf16(v[j], v[j + 1]); o.y = pack_bf16(v[j + 2], v[j + 3]);
-                o.z = pack_bf16(v[j + 4], v[j + 5]); o.w = pack_bf16(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(cb + j) = o;
-              }
-            }
-          }
-        }
+      for (int e = 0; e < 8; ++e) v[e] = ((keep >> e) & 1u) ? v[e] * p.drop_scale : 0.0f;
+    }
+    if (p.residual != nullptr) {
+      if (p.residual_f32) {
+        const float* rs = reinterpret_cast<const float*>(p.residual) + static_cast<size_t>(row) * p.ldr + c8;
+        const float4 r0 = *reinterpret_cast<const float4*>(rs), r1 = *reinterpret_cast<const float4*>(rs + 4);
+        v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+      } else {
+        const uint4 a = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                                       static_cast<size_t>(row) * p.ldr + c8);
+        const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+        v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y; v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
+      }
+    }
+    if (OUT_F32) {
+      float* cf = reinterpret_cast<float*>(p.C) + off;
+      if (p.split_k > 1) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cf), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+                     : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cf + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
+                     "f"(v[7])
+                     : "memory");
+      } else if (p.accumulate) {
+        float4 o0 = *reinterpret_cast<float4*>(cf), o1 = *reinterpret_cast<float4*>(cf + 4);
+        o0.x += v[0]; o0.y += v[1]; o0.z += v[2]; o0.w += v[3]; o1.x += v[4]; o1.y += v[5]; o1.z += v[6]; o1.w += v[7];
+        *reinterpret_cast<float4*>(cf) = o0;
+        *reinterpret_cast<float4*>(cf + 4) = o1;
+      } else {
+        *reinterpret_cast<float4*>(cf) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(cf + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    } else {
+      uint4 o;
+      o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = o;
+    }
+  }
+  __syncwarp();   // the staging slab is rewritten by the next chunk
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32>
@@ -205,12 +189,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int STAGES = S::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES);
+  uint8_t* s_stage = smem + S::TILE_BYTES;    // [EPI_WARPS][4096] epilogue transpose slabs
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES + S::EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_bias = reinterpret_cast<float*>(smem + S::TILE_BYTES + S::BAR_BYTES);   // [2][BN]
+  float* s_bias = reinterpret_cast<float*>(smem + S::TILE_BYTES + S::EPI_STAGE_BYTES + S::BAR_BYTES);   // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -327,8 +312,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int nt = tile % n_tiles;
       const int mt = (tile / n_tiles) % m_tiles;
       const int m0 = mt * BM, n0 = nt * BN;
-      const int row = m0 + quad * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row_base = m0 + quad * 32;
+      uint8_t* my_stage = s_stage + (warp - 2) * 4096;
       // stage this tile's bias slab in shared memory (global-load latency off the critical path)
       float* sb = s_bias + acc * BN;
       if (p.bias != nullptr && etid < BN) sb[etid] = (n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
@@ -352,7 +337,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int lcol = half * (BN / 2) + c * 32;
         const int col0 = n0 + lcol;
         if (col0 >= p.N) continue;  // warp-uniform
-        epilogue_chunk<EPI, OUT_F32>(rbuf[c & 1], p, sb, lcol, row, row_ok, col0);
+        epilogue_chunk<EPI, OUT_F32>(rbuf[c & 1], p, sb, my_stage, lane, lcol, row_base, col0);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -399,23 +384,25 @@ static void fill_params(const rf_gemm_args* a, GemmParams& p) {
 // drained" to the leader.
 // ==============================================================================================
 constexpr int P_BN = 256;        // pair tile N
-constexpr int P_STAGES = 6;
+constexpr int P_STAGES = 5;
 constexpr uint32_t P_A_BYTES = 128 * BK * 2, P_B_BYTES = 128 * BK * 2, P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
 constexpr uint32_t P_TILE_BYTES = P_STAGES * P_STAGE_BYTES;
 constexpr uint32_t P_BAR_BYTES = (2 * P_STAGES + 4) * 8 + 16;
-constexpr uint32_t P_SMEM = P_TILE_BYTES + P_BAR_BYTES + 2 * P_BN * 4 + 1024;
+constexpr uint32_t P_EPI_STAGE_BYTES = EPI_WARPS * 4096;
+constexpr uint32_t P_SMEM = P_TILE_BYTES + P_EPI_STAGE_BYTES + P_BAR_BYTES + 2 * P_BN * 4 + 1024;
 
 template <bool A_MN, bool B_MN, int EPI, bool OUT_F32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P_TILE_BYTES);
+  uint8_t* s_stage = smem + P_TILE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P_TILE_BYTES + P_EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + P_STAGES;
   uint64_t* tfull_bar = empty_bar + P_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_bias = reinterpret_cast<float*>(smem + P_TILE_BYTES + P_BAR_BYTES);
+  float* s_bias = reinterpret_cast<float*>(smem + P_TILE_BYTES + P_EPI_STAGE_BYTES + P_BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -534,8 +521,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int nt = tile % n_tiles;
       const int mt = (tile / n_tiles) % m_tiles;
       const int m0 = mt * 256 + static_cast<int>(rank) * 128, n0 = nt * P_BN;
-      const int row = m0 + quad * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row_base = m0 + quad * 32;
+      uint8_t* my_stage = s_stage + (warp - 2) * 4096;
       float* sb = s_bias + acc * P_BN;
       if (p.bias != nullptr && etid < P_BN) sb[etid] = (n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -557,7 +544,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int lcol = half * (P_BN / 2) + c * 32;
         const int col0 = n0 + lcol;
         if (col0 >= p.N) continue;
-        epilogue_chunk<EPI, OUT_F32>(rbuf[c & 1], p, sb, lcol, row, row_ok, col0);
+        epilogue_chunk<EPI, OUT_F32>(rbuf[c & 1], p, sb, my_stage, lane, lcol, row_base, col0);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
