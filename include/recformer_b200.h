@@ -48,8 +48,8 @@ unsigned long long rf_launch_count(void);
  *   b_mn_major = 0: B is [N,K] row-major (nn.Linear weight layout); 1: B is stored [K,N].
  * Epilogue, applied in this order on the fp32 accumulator v(row, col):
  *   v += bias[col]; if (col < scale_ncols) v *= scale;           (q /= sqrt(D), HF:513)
- *   epi == RF_EPI_GELU : C  <- v (pre-activation), C2 <- gelu_erf(v)         (HF:1112-1115)
- *   epi == RF_EPI_DGELU: v *= gelu_erf'(aux[row,col])                         (GELU backward)
+ *   epi == RF_EPI_GELU : C2 <- gelu_erf(v), C <- gelu_erf'(v) (saved for backward) (HF:1112-1115)
+ *   epi == RF_EPI_DGELU: v *= aux[row,col]   (aux = the gelu' tensor saved by RF_EPI_GELU)
  *   dropout(drop_p, seed) on v;  v += residual[row,col];         (HF:1069-1070, 1128-1129)
  *   out_f32 ? (accumulate ? C += v : C = v) as fp32 : C = bf16(v)
  * split_k > 1 (fp32 output only) splits K over CTAs and accumulates with red.add; the caller
@@ -64,7 +64,7 @@ typedef struct rf_gemm_args {
   void* C2;             /* RF_EPI_GELU: activation output [M,N] bf16 (ldc) */
   const float* bias;    /* [N] or NULL */
   const void* residual; /* [M,N] (ldr) bf16, or fp32 when residual_f32 != 0; or NULL */
-  const void* aux;      /* RF_EPI_DGELU: bf16 pre-activation [M,N] (ldaux) */
+  const void* aux;      /* RF_EPI_DGELU: bf16 gelu'(pre-activation) [M,N] (ldaux) */
   int M, N, K;
   int lda, ldb, ldc, ldr, ldaux;
   int a_mn_major, b_mn_major;

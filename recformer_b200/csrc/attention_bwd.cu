@@ -14,6 +14,7 @@
 // band output is overwritten by the global row, HF:615-626).
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "rf_common.h"
 #include "rf_ptx.cuh"
@@ -339,7 +340,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
       else if (c == NK) j = 0;
       const bool key_ok = (j >= 0 && j < p.L) && (c <= NK) && kflag[c <= NK ? c : 0];
       const float4 x = *reinterpret_cast<const float4*>(slab + rl * 128 + ((u ^ (rl & 7)) << 4));
-      if (key_ok) {
+      if (key_ok && p.dkv != nullptr) {
         float* dst = p.dkv + (static_cast<size_t>(b) * p.L + j) * 2 * E + which * E + h * AB_D + part * 32 + u * 4;
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
                      : "memory");
@@ -397,6 +398,12 @@ extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const fl
   p.mask012 = a->mask012; p.lse = lse;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   p.dkv = dkv_scratch;
+  {
+    // profiling aid only: RF_DEBUG_NO_DKV_ATOMICS=1 drops the dK/dV accumulation (wrong results) so
+    // that the cost of the red.add traffic can be measured in isolation
+    static const bool no_atomics = getenv("RF_DEBUG_NO_DKV_ATOMICS") != nullptr;
+    if (no_atomics) p.dkv = nullptr;
+  }
   p.B = a->B; p.L = a->L; p.H = a->H;
   p.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   p.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;

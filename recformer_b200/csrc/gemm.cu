@@ -56,25 +56,24 @@ struct GemmSmem {
   static constexpr uint32_t TOTAL = TILE_BYTES + EPI_STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;  // + alignment slack
 };
 
-// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution): one MUFU.RCP, one
-// MUFU.EX2 and 6 FMAs instead of libdevice's branchy erff in the epilogue's critical path.
-__device__ __forceinline__ float erf_fast(float x) {
-  const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+// GELU (erf form, HF ACT2FN["gelu"]) and its derivative from ONE exponential and one reciprocal:
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution),
+//   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2),  t = 1/(1 + p z),  z = |x|/sqrt(2),
+// and exp(-z^2) = exp(-x^2/2) is also the Gaussian of gelu'(x) = Phi(x) + x phi(x).  Two MUFU ops
+// per element (MUFU is 16/clk/SM and is what bounds this epilogue), the rest FMAs.
+__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float y = 1.0f - poly * t * __expf(-ax * ax);
-  return copysignf(y, x);
+  const float e = exp2f(-0.72134752044448170f * x * x);      // exp(-x^2/2)
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  const float cdf = fmaf(0.5f, copysignf(erf_abs, x), 0.5f);
+  g = x * cdf;
+  dg = fmaf(x * 0.39894228040143268f, e, cdf);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float dgelu_erf(float x) {
-  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
-}
-
 
 // Epilogue of one 32-row x 32-column accumulator chunk held by a warp (thread = row, as read from
 // TMEM).  The raw fp32 accumulators are first transposed through a 4 KB 128B-swizzled staging slab
@@ -86,6 +85,30 @@ __device__ __forceinline__ float dgelu_erf(float x) {
 template <int EPI, bool OUT_F32>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const GemmParams& p, const float* sb,
                                                uint8_t* stage, int lane, int lcol, int row_base, int col0) {
+  // ---- phase 0: issue the epilogue's global loads (residual / gelu' tile) for all four row steps
+  //      now, so their latency overlaps the shared-memory transposition ----
+  uint4 aux_pf[4];
+  float4 res_pf[4][2];
+  {
+    const int c8p = col0 + (lane & 3) * 8;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int row = row_base + s * 8 + (lane >> 2);
+      const bool ok = row < p.M;
+      if (EPI == RF_EPI_DGELU)
+        aux_pf[s] = ok ? *reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.ldaux + c8p) : make_uint4(0, 0, 0, 0);
+      if (EPI != RF_EPI_GELU && p.residual != nullptr && ok) {
+        if (p.residual_f32) {
+          const float* rs = reinterpret_cast<const float*>(p.residual) + static_cast<size_t>(row) * p.ldr + c8p;
+          res_pf[s][0] = *reinterpret_cast<const float4*>(rs);
+          res_pf[s][1] = *reinterpret_cast<const float4*>(rs + 4);
+        } else {
+          res_pf[s][0] = *reinterpret_cast<const float4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                                          static_cast<size_t>(row) * p.ldr + c8p);
+        }
+      }
+    }
+  }
   // ---- phase 1: thread (= row `lane`) writes its 32 fp32 values, 16B units XOR-swizzled by row ----
   {
     uint8_t* srow = stage + lane * 128;
@@ -121,22 +144,21 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ge
     for (int e = 0; e < 8; ++e) v[e] = (v[e] + bias8[e]) * sc;
     const size_t off = static_cast<size_t>(row) * p.ldc + c8;
     if (EPI == RF_EPI_GELU) {
-      uint4 u, g;
-      u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
-      // activation of the bf16-rounded pre-activation, so that backward (which only sees the
-      // stored bf16 u) differentiates exactly the function forward applied
-      const float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
-      g.x = pack_bf16(gelu_erf(a0.x), gelu_erf(a0.y)); g.y = pack_bf16(gelu_erf(a1.x), gelu_erf(a1.y));
-      g.z = pack_bf16(gelu_erf(a2.x), gelu_erf(a2.y)); g.w = pack_bf16(gelu_erf(a3.x), gelu_erf(a3.y));
-      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = u;
-      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + off) = g;
+      // C2 <- gelu(u) (operand of the next GEMM); C <- gelu'(u) (all the backward pass needs of u)
+      float g[8], d[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gelu_and_grad(v[e], g[e], d[e]);
+      uint4 dv, gv;
+      dv.x = pack_bf16(d[0], d[1]); dv.y = pack_bf16(d[2], d[3]); dv.z = pack_bf16(d[4], d[5]); dv.w = pack_bf16(d[6], d[7]);
+      gv.x = pack_bf16(g[0], g[1]); gv.y = pack_bf16(g[2], g[3]); gv.z = pack_bf16(g[4], g[5]); gv.w = pack_bf16(g[6], g[7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = dv;
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + off) = gv;
       continue;
     }
-    if (EPI == RF_EPI_DGELU) {
-      const uint4 a = *reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.ldaux + c8);
+    if (EPI == RF_EPI_DGELU) {   // aux holds gelu'(u) saved by the forward epilogue
+      const uint4 a = aux_pf[s];
       const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
-      v[0] *= dgelu_erf(a0.x); v[1] *= dgelu_erf(a0.y); v[2] *= dgelu_erf(a1.x); v[3] *= dgelu_erf(a1.y);
-      v[4] *= dgelu_erf(a2.x); v[5] *= dgelu_erf(a2.y); v[6] *= dgelu_erf(a3.x); v[7] *= dgelu_erf(a3.y);
+      v[0] *= a0.x; v[1] *= a0.y; v[2] *= a1.x; v[3] *= a1.y; v[4] *= a2.x; v[5] *= a2.y; v[6] *= a3.x; v[7] *= a3.y;
     }
     if (p.drop_thresh != 0) {
       const uint64_t grp = (static_cast<uint64_t>(row) * p.N + c8) >> 3;
@@ -146,13 +168,12 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ge
     }
     if (p.residual != nullptr) {
       if (p.residual_f32) {
-        const float* rs = reinterpret_cast<const float*>(p.residual) + static_cast<size_t>(row) * p.ldr + c8;
-        const float4 r0 = *reinterpret_cast<const float4*>(rs), r1 = *reinterpret_cast<const float4*>(rs + 4);
+        const float4 r0 = res_pf[s][0], r1 = res_pf[s][1];
         v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
       } else {
-        const uint4 a = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
-                                                       static_cast<size_t>(row) * p.ldr + c8);
-        const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+        const float4 raw = res_pf[s][0];
+        const float2 a0 = unpack_bf16(__float_as_uint(raw.x)), a1 = unpack_bf16(__float_as_uint(raw.y));
+        const float2 a2 = unpack_bf16(__float_as_uint(raw.z)), a3 = unpack_bf16(__float_as_uint(raw.w));
         v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y; v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
       }
     }

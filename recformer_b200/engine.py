@@ -192,7 +192,7 @@ class SavedActivations:
         self.pre1 = [torch.empty(T, E, **f32) for _ in range(n)]
         self.stats1 = [torch.empty(T, 2, **f32) for _ in range(n)]
         self.h1 = [torch.empty(T, E, **bf) for _ in range(n)]
-        self.u = [torch.empty(T, F, **bf) for _ in range(n)]
+        self.u = [torch.empty(T, F, **bf) for _ in range(n)]       # gelu'(pre-activation), saved for backward
         self.g = [torch.empty(T, F, **bf) for _ in range(n)]
         self.pre2 = [torch.empty(T, E, **f32) for _ in range(n)]
         self.stats2 = [torch.empty(T, 2, **f32) for _ in range(n)]

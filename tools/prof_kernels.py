@@ -53,6 +53,9 @@ FLOPS = {"gemm_qkv": 2 * T * 3 * E * E, "gemm_up_gelu": 2 * T * F * E, "gemm_dow
          "gemm_dgrad_dgelu": 2 * T * F * E, "gemm_wgrad_up": 2 * T * F * E, "gemm_wgrad_qkv": 2 * T * 3 * E * E}
 BYTES = {"attn_fwd": T * 4 * E * 2, "attn_bwd": T * 8 * E * 2, "ln_fwd": T * E * (4 + 2 + 4), "ln_bwd": T * E * (2 + 4 + 2 + 2),
          "colsum_3072": T * F * 2}
+CASES["attn_bwd_nodrop"] = lambda: ops.band_attn_bwd(qkv, mask, B, L, H, 32, ctx, lse, dctx, dqkv, scratch)
+CASES["attn_fwd_nodrop"] = lambda: ops.band_attn_fwd(qkv, mask, B, L, H, 32, ctx=ctx, lse=lse)
+BYTES["attn_bwd_nodrop"] = BYTES["attn_bwd"]; BYTES["attn_fwd_nodrop"] = BYTES["attn_fwd"]
 only = sys.argv[1:] or list(CASES)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 for name in only:
