@@ -1,0 +1,113 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: the packed top-k
+all-gather + merge of sharded scoring, and the flat-gradient all-reduce of data-parallel training.
+The per-shard scores come from the CPU oracle (Spec S); the CUDA kernels themselves are covered by
+the `-m gpu` tests, here only the exchange / merge / bookkeeping runs."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, fn, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ret[rank] = fn(rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn, world=2):
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, fn, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0, f"worker exited with {p.exitcode}"
+    return [ret[r] for r in range(world)]
+
+
+def _sharded_topk_job(rank, world):
+    from oracle import recformer_oracle as O
+    from recformer_b200 import dist as rdist
+    from recformer_b200.metrics import Ranker, TopKRanker
+    N, B, E, k = 4001, 37, 768, 10          # N not divisible by the world size: uneven shards
+    items = O.make_item_table(N, E, seed=1)
+    users = torch.randn(B, E, generator=torch.Generator().manual_seed(3))
+    labels = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(4))
+    full = O.similarity_score(users, items, 0.05)                     # (B, N) oracle logits
+    full[:, 7] = full[:, 1900]                                    # a cross-shard tie: lower id must win
+    lo, hi = rdist.shard_bounds(N, world, rank)
+    local = full[:, lo:hi]
+    s, i = torch.topk(local, k, dim=1)
+    i = (i + lo).to(torch.int32)
+    own = (labels >= lo) & (labels < hi)
+    lab = torch.where(own, full[torch.arange(B), labels], torch.full((B,), float("-inf")))
+    gs, gi, gl = rdist.all_gather_topk(s.contiguous(), i.contiguous(), lab)
+    ms, mi, ml = rdist.merge_topk_reference(gs, gi, gl, k)
+    # reference: unsharded top-k with ties towards the lower id, and the reference Ranker
+    order = torch.argsort(full, dim=1, descending=True, stable=True)[:, :k]
+    ref_s = torch.gather(full, 1, order)
+    assert torch.equal(ms, ref_s)
+    assert torch.equal(mi.to(torch.int64), order)
+    assert torch.equal(ml, full[torch.arange(B), labels])
+    dense = Ranker([10])(full, labels[:, None])
+    fused = TopKRanker([10])(ms, ml)
+    assert abs(dense[0] - fused[0]) < 1e-6 and abs(dense[1] - fused[1]) < 1e-6      # NDCG@10, Recall@10
+    return mi.tolist()
+
+
+def test_sharded_topk_allgather_merge_world2():
+    out = _run(_sharded_topk_job)
+    assert out[0] == out[1]           # identical result on every rank
+
+
+def _shard_bounds_job(rank, world):
+    from recformer_b200 import dist as rdist
+    covered = []
+    for r in range(world):
+        covered += list(range(*rdist.shard_bounds(1_000_003, world, r)))[:: 100_000]
+    lo, hi = rdist.shard_bounds(1_000_003, world, rank)
+    t = torch.tensor([hi - lo])
+    dist.all_reduce(t)
+    return int(t.item())
+
+
+def test_shard_bounds_cover_table_world2():
+    assert _run(_shard_bounds_job) == [1_000_003, 1_000_003]
+
+
+def _grad_allreduce_job(rank, world):
+    """allreduce_gradients averages the engine's flat fp32 gradient buffer across ranks."""
+    import recformer_b200 as rb
+    from recformer_b200 import dist as rdist
+    cfg = rb.RecformerConfig(attention_window=[64], vocab_size=120, num_hidden_layers=1, max_position_embeddings=80)
+    model = rb.RecformerForSeqRec(cfg)
+    P = model.longformer._engine.params
+    P.grad = torch.full((P.n_total,), float(rank + 1))             # stand-in for a backward pass on this rank
+    rdist.allreduce_gradients(model)
+    return float(P.grad[0]), float(P.grad[-1]), P.n_total
+
+
+def test_flat_gradient_allreduce_world2():
+    out = _run(_grad_allreduce_job)
+    assert out[0][:2] == (1.5, 1.5) and out[1][:2] == (1.5, 1.5)

@@ -56,6 +56,15 @@ BYTES = {"attn_fwd": T * 4 * E * 2, "attn_bwd": T * 8 * E * 2, "ln_fwd": T * E *
 CASES["attn_bwd_nodrop"] = lambda: ops.band_attn_bwd(qkv, mask, B, L, H, 32, ctx, lse, dctx, dqkv, scratch)
 CASES["attn_fwd_nodrop"] = lambda: ops.band_attn_fwd(qkv, mask, B, L, H, 32, ctx=ctx, lse=lse)
 BYTES["attn_bwd_nodrop"] = BYTES["attn_bwd"]; BYTES["attn_fwd_nodrop"] = BYTES["attn_fwd"]
+if any(a.startswith("score") for a in sys.argv[1:]):
+    NU, NI = 4096, int(os.environ.get("RF_PROF_ITEMS", "1000000"))
+    tab = torch.empty(NI, E, dtype=torch.bfloat16, device=dev)
+    for a0 in range(0, NI, 125000):
+        ops.normalize_rows(torch.randn(min(125000, NI - a0), E, device=dev, generator=g), out=tab[a0:a0 + 125000])
+    usr = ops.normalize_rows(torch.randn(NU, E, device=dev, generator=g))
+    lab = torch.randint(0, NI, (NU,), device=dev, generator=g)
+    CASES["score_topk"] = lambda: ops.cosine_topk(usr, tab, 0.05, k=10, labels=lab)
+    FLOPS["score_topk"] = 2 * NU * NI * E
 only = sys.argv[1:] or list(CASES)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 for name in only:
