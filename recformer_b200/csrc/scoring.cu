@@ -1,14 +1,18 @@
 // Full-catalogue cosine scoring (SURVEY.md §8a Spec S; ref: recformer/models.py:358-369,539-545):
 //   logit[b,n] = (x_b / |x_b|) . (y_n / |y_n|) / temp
 // as a bf16 tcgen05 GEMM over a pre-normalised item table with fused epilogues:
-//   TOPK : temperature scaling + streaming per-thread top-k (one thread = one user row of the
-//          128-row tile), logits never written; label score picked out of the same accumulator
-//          so that Spec R's strict `>` rank count is exact;
+//   TOPK : temperature scaling + streaming per-row top-k, logits never written.  Each epilogue
+//          thread owns one user row x one 128-column half of the tile; its sorted k-list lives in
+//          shared memory and only the k-th best score is kept in a register, so a 32-column
+//          accumulator chunk that cannot enter the list costs one max per column + one warp vote;
+//          the label score is picked out of the same accumulator so that Spec R's strict `>`
+//          rank count is exact;
 //   DENSE: fp32 logits [B,N] (the (B,N) score tensor RecformerForSeqRec.forward returns, and the
 //          training cross-entropy input, ref: recformer/models.py:583-591).
 // Scheduling: CTA = (user m-tile, item slice s); slice s sweeps item tiles s, s+S, ... so all
 // m-tiles advance through the table in lock-step and each 256-item tile is fetched from HBM once
-// and re-read from L2 by the other m-tiles.
+// and re-read from L2 by the other m-tiles.  More than 128 users: CTA pairs (cta_group::2) on
+// 256 x 256 tiles; otherwise single CTAs on 128 x 256 tiles.
 #include <cuda_bf16.h>
 #include <math.h>
 
@@ -17,34 +21,130 @@
 
 namespace rf {
 
-constexpr int SC_BM = 128, SC_BN = 256, SC_BK = 64, SC_STAGES = 4, SC_THREADS = 192;
+constexpr int SC_BM = 128, SC_BN = 256, SC_BK = 64, SC_STAGES = 4;
+constexpr int SC_EPI_WARPS = 8, SC_THREADS = 64 + 32 * SC_EPI_WARPS;
 constexpr int SC_MAXK = 16;
 constexpr uint32_t SC_A_BYTES = SC_BM * SC_BK * 2, SC_B_BYTES = SC_BN * SC_BK * 2;
 constexpr uint32_t SC_STAGE_BYTES = SC_A_BYTES + SC_B_BYTES;
-constexpr uint32_t SC_SMEM = SC_STAGES * SC_STAGE_BYTES + (2 * SC_STAGES + 4) * 8 + 16 + 1024;
+constexpr uint32_t SC_LIST_BYTES = SC_MAXK * SC_EPI_WARPS * 32 * 8;   // per-thread top-k lists: [q][thread] score + id
+constexpr uint32_t SC_SMEM = SC_STAGES * SC_STAGE_BYTES + SC_LIST_BYTES + (2 * SC_STAGES + 4) * 8 + 16 + 1024;
+// CTA-pair variant: 256 users x 256 items per tile, each CTA stages its 128 user rows and its
+// 128-item half of the table slab (32 KB per 64-wide K slab), 5 ring stages
+constexpr int SP_STAGES = 5;
+constexpr uint32_t SP_STAGE_BYTES = 2 * 128 * SC_BK * 2;
+constexpr uint32_t SP_SMEM = SP_STAGES * SP_STAGE_BYTES + SC_LIST_BYTES + (2 * SP_STAGES + 4) * 8 + 16 + 1024;
 
 struct ScoreParams {
   int B; long long N; int K;      // users, items, hidden
   float inv_temp;
   int k;                          // top-k
   int id_base;
-  int slices;                     // S
+  int slices;                     // S: item-tile slices per user tile
   const int64_t* labels;
-  float* ws_scores;               // [S][B][k]
-  int32_t* ws_ids;                // [S][B][k]
-  float* ws_label;                // [S][B]
+  float* ws_scores;               // [2S][B][k]   (part = slice * 2 + column half)
+  int32_t* ws_ids;                // [2S][B][k]
+  float* ws_label;                // [2S][B]
   float* logits;                  // DENSE: [B][N]
 };
 
 enum { SC_TOPK = 0, SC_DENSE = 1 };
 
+// Per-thread (= per user row) streaming top-k state.  The sorted list lives in shared memory
+// ([q][thread], conflict-free); only the current k-th best score (`thr`) is kept in a register, so
+// the common case — no column of a 32-column accumulator chunk beats thr — costs one max per
+// column and a single warp vote.
+struct TopkState {
+  float* ts;        // &list_scores[0][thread]
+  int* ti;          // &list_ids[0][thread]
+  float thr;
+  float label_score;
+  long long label_local;   // label id relative to this table shard, or -1
+};
+
+constexpr int SC_LIST_STRIDE = SC_EPI_WARPS * 32;
+
+__device__ __noinline__ float topk_insert(float* ts, int* ti, int k, float s, int id) {
+  // descending insertion; strict '>' keeps the earlier (lower) id ahead on equal scores
+  int q = k - 1;
+  while (q > 0 && s > ts[(q - 1) * SC_LIST_STRIDE]) {
+    ts[q * SC_LIST_STRIDE] = ts[(q - 1) * SC_LIST_STRIDE];
+    ti[q * SC_LIST_STRIDE] = ti[(q - 1) * SC_LIST_STRIDE];
+    --q;
+  }
+  ts[q * SC_LIST_STRIDE] = s;
+  ti[q * SC_LIST_STRIDE] = id;
+  return ts[(k - 1) * SC_LIST_STRIDE];
+}
+
+// One 32-row x 32-column accumulator chunk (thread = user row) of the TOPK epilogue.
+__device__ __forceinline__ void topk_chunk(const uint32_t (&r)[32], TopkState& st, const ScoreParams& p,
+                                           long long col0) {
+  // fast reject: max over the chunk (4 independent chains), one multiply, one vote
+  float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
+#pragma unroll
+  for (int j = 4; j < 32; j += 4) {
+    m0 = fmaxf(m0, __uint_as_float(r[j]));
+    m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
+    m2 = fmaxf(m2, __uint_as_float(r[j + 2]));
+    m3 = fmaxf(m3, __uint_as_float(r[j + 3]));
+  }
+  const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * p.inv_temp;   // == max_j (r[j] * inv_temp): rounding is monotonic
+  const long long rel = st.label_local - col0;
+  const bool partial = col0 + 32 > p.N;                                // warp-uniform
+  const bool mine = (mx > st.thr) || (rel >= 0 && rel < 32) || partial;
+  if (!__any_sync(0xffffffffu, mine)) return;
+  if (mine) {
+    const int nvalid = partial ? static_cast<int>(p.N - col0) : 32;
+    const int id0 = p.id_base + static_cast<int>(col0);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float s = __uint_as_float(r[j]) * p.inv_temp;
+      if (j == rel && j < nvalid) st.label_score = s;
+      if (s > st.thr && j < nvalid) st.thr = topk_insert(st.ts, st.ti, p.k, s, id0 + j);
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void dense_chunk(const uint32_t (&r)[32], const ScoreParams& p, int row, bool row_ok,
+                                            long long col0) {
+  if (!row_ok) return;
+  float* out = p.logits + static_cast<size_t>(row) * p.N + col0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (col0 + j < p.N) out[j] = __uint_as_float(r[j]) * p.inv_temp;
+}
+
+__device__ __forceinline__ void topk_state_init(TopkState& st, uint8_t* list_smem, int etid, const ScoreParams& p, int row,
+                                                bool row_ok) {
+  st.ts = reinterpret_cast<float*>(list_smem) + etid;
+  st.ti = reinterpret_cast<int*>(list_smem + SC_MAXK * SC_LIST_STRIDE * 4) + etid;
+  for (int q = 0; q < SC_MAXK; ++q) { st.ts[q * SC_LIST_STRIDE] = -INFINITY; st.ti[q * SC_LIST_STRIDE] = 0x7fffffff; }
+  st.thr = -INFINITY;
+  st.label_score = -INFINITY;
+  st.label_local = -1;
+  if (p.labels != nullptr && row_ok) {
+    const long long l = p.labels[row] - p.id_base;
+    st.label_local = (l >= 0 && l < p.N) ? l : -1;
+  }
+}
+
+__device__ __forceinline__ void topk_state_flush(const TopkState& st, const ScoreParams& p, int part, int row) {
+  float* os = p.ws_scores + (static_cast<size_t>(part) * p.B + row) * p.k;
+  int32_t* oi = p.ws_ids + (static_cast<size_t>(part) * p.B + row) * p.k;
+  for (int q = 0; q < p.k; ++q) { os[q] = st.ts[q * SC_LIST_STRIDE]; oi[q] = st.ti[q * SC_LIST_STRIDE]; }
+  p.ws_label[static_cast<size_t>(part) * p.B + row] = st.label_score;
+}
+
+// ---- single-CTA kernel (<= 128 users per tile): small user batches ----
 template <int MODE>
 __global__ void __launch_bounds__(SC_THREADS, 1)
 cosine_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const ScoreParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SC_STAGES * SC_STAGE_BYTES);
+  uint8_t* s_list = smem + SC_STAGES * SC_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_list + SC_LIST_BYTES);
   uint64_t* empty_bar = full_bar + SC_STAGES;
   uint64_t* tfull_bar = empty_bar + SC_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -59,7 +159,7 @@ cosine_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], SC_EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 2 * SC_BN); tmem_relinquish(); }
@@ -108,82 +208,161 @@ cosine_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    const int quad = warp & 3;
+    // epilogue warps 2..9: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4
+    const int quad = warp & 3, half = (warp - 2) >> 2;
     const int row = m0 + quad * 32 + lane;
     const bool row_ok = row < p.B;
-    float ts[SC_MAXK]; int ti[SC_MAXK];
-#pragma unroll
-    for (int i = 0; i < SC_MAXK; ++i) { ts[i] = -INFINITY; ti[i] = 0x7fffffff; }
-    float thr = -INFINITY;   // current k-th best
-    float label_score = -INFINITY;
-    long long label_local = -1;
-    if (MODE == SC_TOPK && p.labels != nullptr && row_ok) label_local = p.labels[row] - p.id_base;
+    TopkState st;
+    if (MODE == SC_TOPK) topk_state_init(st, s_list, threadIdx.x - 64, p, row, row_ok);
     int acc = 0; uint32_t acc_phase = 0;
     for (int nt = slice; nt < n_tiles; nt += p.slices) {
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const long long n0 = static_cast<long long>(nt) * SC_BN;
-#pragma unroll 1
-      for (int c = 0; c < SC_BN / 32; ++c) {
-        const long long col0 = n0 + c * 32;
-        if (col0 >= p.N) break;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * SC_BN + c * 32, r);
+      const long long n0 = static_cast<long long>(nt) * SC_BN + half * (SC_BN / 2);
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * SC_BN + half * (SC_BN / 2);
+      uint32_t rbuf[2][32];
+      tmem_ld32(tbase, rbuf[0]);
+#pragma unroll
+      for (int c = 0; c < SC_BN / 2 / 32; ++c) {
         tmem_ld_wait();
-        if (MODE == SC_DENSE) {
-          if (row_ok) {
-            float* out = p.logits + static_cast<size_t>(row) * p.N + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) out[j] = __uint_as_float(r[j]) * p.inv_temp;
-          }
+        if (c + 1 < SC_BN / 2 / 32) {
+          tmem_ld32(tbase + (c + 1) * 32, rbuf[(c + 1) & 1]);
         } else {
-          const int nvalid = (p.N - col0) < 32 ? static_cast<int>(p.N - col0) : 32;
-          const long long rel = label_local - col0;
-          if (rel >= 0 && rel < nvalid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j == rel) label_score = __uint_as_float(r[j]) * p.inv_temp;
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float s = __uint_as_float(r[j]) * p.inv_temp;
-            if (s > thr && j < nvalid) {
-              // insert (s, id) into the descending list; strict '>' keeps the lower id on ties
-              const int id = p.id_base + static_cast<int>(col0) + j;
-              float cs = s; int ci = id;
-#pragma unroll
-              for (int q = 0; q < SC_MAXK; ++q) {
-                if (q < p.k) {
-                  const bool sw = cs > ts[q];
-                  const float t_s = ts[q]; const int t_i = ti[q];
-                  ts[q] = sw ? cs : t_s; ti[q] = sw ? ci : t_i;
-                  cs = sw ? t_s : cs; ci = sw ? t_i : ci;
-                }
-              }
-#pragma unroll
-              for (int q = 0; q < SC_MAXK; ++q) if (q == p.k - 1) thr = ts[q];
-            }
-          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
+        const long long col0 = n0 + c * 32;
+        if (col0 >= p.N) continue;
+        if (MODE == SC_DENSE) dense_chunk(rbuf[c & 1], p, row, row_ok, col0);
+        else topk_chunk(rbuf[c & 1], st, p, col0);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (MODE == SC_TOPK && row_ok) {
-      float* os = p.ws_scores + (static_cast<size_t>(slice) * p.B + row) * p.k;
-      int32_t* oi = p.ws_ids + (static_cast<size_t>(slice) * p.B + row) * p.k;
-#pragma unroll
-      for (int q = 0; q < SC_MAXK; ++q)
-        if (q < p.k) { os[q] = ts[q]; oi[q] = ti[q]; }
-      p.ws_label[static_cast<size_t>(slice) * p.B + row] = label_score;
-    }
+    if (MODE == SC_TOPK && row_ok) topk_state_flush(st, p, slice * 2 + half, row);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * SC_BN); }
+}
+
+// ---- CTA-pair kernel: 256 users x 256 items per tile with tcgen05.mma.cta_group::2 ----
+// Same protocol as gemm_pair_kernel (gemm.cu): both CTAs stream their halves of the operands, the
+// leader's MMA thread issues for both, commits are multicast; each CTA's 8 epilogue warps scan its own
+// 128 accumulator rows.  L2 -> SM traffic per FLOP is 2/3 of the single-CTA kernel's.
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SC_THREADS, 1)
+cosine_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const ScoreParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_list = smem + SP_STAGES * SP_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_list + SC_LIST_BYTES);
+  uint64_t* empty_bar = full_bar + SP_STAGES;
+  uint64_t* tfull_bar = empty_bar + SP_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int mt = pair / p.slices;
+  const int slice = pair % p.slices;
+  const int m0 = mt * 256 + static_cast<int>(rank) * 128;
+  const int n_tiles = static_cast<int>((p.N + SC_BN - 1) / SC_BN);
+  const int k_blocks = (p.K + SC_BK - 1) / SC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SP_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * SC_EPI_WARPS); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0; uint32_t phase = 0;
+      for (int nt = slice; nt < n_tiles; nt += p.slices) {
+        const int n0 = nt * SC_BN + static_cast<int>(rank) * 128;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * SP_STAGE_BYTES);
+          const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sa = smem + stage * SP_STAGE_BYTES;
+          tma_load_2d_pair(sa, &tmA, fb, kb * SC_BK, m0);
+          tma_load_2d_pair(sa + SP_STAGE_BYTES / 2, &tmB, fb, kb * SC_BK, n0);
+          if (++stage == SP_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, SC_BN, false, false);
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      for (int nt = slice; nt < n_tiles; nt += p.slices) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * SP_STAGE_BYTES), sb = sa + SP_STAGE_BYTES / 2;
+#pragma unroll
+            for (int k = 0; k < SC_BK / 16; ++k)
+              umma_bf16_pair(tmem_base + acc * SC_BN, umma_smem_desc(sa + k * 32, 16, 1024),
+                             umma_smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == k_blocks - 1) umma_commit_pair(&tfull_bar[acc]);
+          }
+          __syncwarp();
+          if (++stage == SP_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int row = m0 + quad * 32 + lane;
+    const bool row_ok = row < p.B;
+    TopkState st;
+    if (MODE == SC_TOPK) topk_state_init(st, s_list, threadIdx.x - 64, p, row, row_ok);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int nt = slice; nt < n_tiles; nt += p.slices) {
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const long long n0 = static_cast<long long>(nt) * SC_BN + half * (SC_BN / 2);
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * SC_BN + half * (SC_BN / 2);
+      uint32_t rbuf[2][32];
+      tmem_ld32(tbase, rbuf[0]);
+#pragma unroll
+      for (int c = 0; c < SC_BN / 2 / 32; ++c) {
+        tmem_ld_wait();
+        if (c + 1 < SC_BN / 2 / 32) {
+          tmem_ld32(tbase + (c + 1) * 32, rbuf[(c + 1) & 1]);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        }
+        const long long col0 = n0 + c * 32;
+        if (col0 >= p.N) continue;
+        if (MODE == SC_DENSE) dense_chunk(rbuf[c & 1], p, row, row_ok, col0);
+        else topk_chunk(rbuf[c & 1], st, p, col0);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (MODE == SC_TOPK && row_ok) topk_state_flush(st, p, slice * 2 + half, row);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
 }
 
 // Merge `parts` sorted lists of k (score, id) per user -> global top-k (score desc, id asc).
@@ -359,32 +538,47 @@ ce_norm_bwd_kernel(const void* __restrict__ x_, const float* __restrict__ dxn, f
   }
 }
 
+static bool use_pair(int B) { return B > SC_BM; }
+
+static int pick_slices(int B, long long N) {
+  const long long n_tiles = (N + SC_BN - 1) / SC_BN;
+  long long s;
+  if (use_pair(B)) s = (sm_count() / 2) / ((B + 255) / 256);
+  else s = sm_count() / ((B + SC_BM - 1) / SC_BM);
+  if (s < 1) s = 1;
+  if (s > n_tiles) s = n_tiles;
+  return static_cast<int>(s);
+}
+
 static int launch_cosine(int mode, const void* xn, const void* yn, ScoreParams& p, cudaStream_t stream) {
-  const CUtensorMap* tmA = get_tmap_2d(xn, p.B, p.K, p.K, SC_BM);
-  const CUtensorMap* tmB = get_tmap_2d(yn, static_cast<uint64_t>(p.N), p.K, p.K, SC_BN);
-  if (!tmA || !tmB) return RF_ERR_CUDA;
   static bool attr_set = false;
   if (!attr_set) {
     RF_CUDA(cudaFuncSetAttribute(cosine_mma_kernel<SC_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
     RF_CUDA(cudaFuncSetAttribute(cosine_mma_kernel<SC_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+    RF_CUDA(cudaFuncSetAttribute(cosine_pair_kernel<SC_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+    RF_CUDA(cudaFuncSetAttribute(cosine_pair_kernel<SC_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
     attr_set = true;
   }
-  const int m_tiles = (p.B + SC_BM - 1) / SC_BM;
-  const int grid = m_tiles * p.slices;
+  if (use_pair(p.B)) {
+    const CUtensorMap* tmA = get_tmap_2d(xn, p.B, p.K, p.K, 128);
+    const CUtensorMap* tmB = get_tmap_2d(yn, static_cast<uint64_t>(p.N), p.K, p.K, 128);
+    if (!tmA || !tmB) return RF_ERR_CUDA;
+    const int grid = 2 * ((p.B + 255) / 256) * p.slices;
+    if (mode == SC_TOPK)
+      cosine_pair_kernel<SC_TOPK><<<grid, SC_THREADS, SP_SMEM, stream>>>(*tmA, *tmB, p);
+    else
+      cosine_pair_kernel<SC_DENSE><<<grid, SC_THREADS, SP_SMEM, stream>>>(*tmA, *tmB, p);
+    return check_launch("cosine_pair_kernel");
+  }
+  const CUtensorMap* tmA = get_tmap_2d(xn, p.B, p.K, p.K, SC_BM);
+  const CUtensorMap* tmB = get_tmap_2d(yn, static_cast<uint64_t>(p.N), p.K, p.K, SC_BN);
+  if (!tmA || !tmB) return RF_ERR_CUDA;
+  const int grid = ((p.B + SC_BM - 1) / SC_BM) * p.slices;
   if (mode == SC_TOPK)
     cosine_mma_kernel<SC_TOPK><<<grid, SC_THREADS, SC_SMEM, stream>>>(*tmA, *tmB, p);
   else
     cosine_mma_kernel<SC_DENSE><<<grid, SC_THREADS, SC_SMEM, stream>>>(*tmA, *tmB, p);
   return check_launch("cosine_mma_kernel");
-}
-
-static int pick_slices(int B, long long N) {
-  const int m_tiles = (B + SC_BM - 1) / SC_BM;
-  const long long n_tiles = (N + SC_BN - 1) / SC_BN;
-  long long s = sm_count() / m_tiles;
-  if (s < 1) s = 1;
-  if (s > n_tiles) s = n_tiles;
-  return static_cast<int>(s);
 }
 
 }  // namespace rf
@@ -418,8 +612,8 @@ extern "C" int rf_cosine_logits(const void* xn, const void* yn, float* logits, i
 }
 
 extern "C" long long rf_cosine_topk_ws_bytes(int B, long long N, int k) {
-  const long long s = pick_slices(B, N);
-  return s * B * (static_cast<long long>(k) * 8 + 4) + 256;
+  const long long parts = 2ll * pick_slices(B, N);
+  return parts * B * (static_cast<long long>(k) * 8 + 4) + 256;
 }
 
 extern "C" int rf_cosine_topk(const void* xn, const void* yn, int B, long long N, int E, float temp, int k,
@@ -434,13 +628,14 @@ extern "C" int rf_cosine_topk(const void* xn, const void* yn, int B, long long N
   p.B = B; p.N = N; p.K = E; p.inv_temp = 1.0f / temp; p.k = k; p.id_base = id_base;
   p.slices = pick_slices(B, N);
   p.labels = labels;
-  const size_t cnt = static_cast<size_t>(p.slices) * B * k;
+  const int parts = 2 * p.slices;   // every (slice, 128-column half) keeps its own list
+  const size_t cnt = static_cast<size_t>(parts) * B * k;
   p.ws_scores = reinterpret_cast<float*>(ws);
   p.ws_ids = reinterpret_cast<int32_t*>(p.ws_scores + cnt);
   p.ws_label = reinterpret_cast<float*>(p.ws_ids + cnt);
   int rc = launch_cosine(SC_TOPK, xn, yn, p, stream);
   if (rc) return rc;
-  topk_merge_kernel<<<(B + 127) / 128, 128, 0, stream>>>(p.ws_scores, p.ws_ids, p.ws_label, p.slices, B, k,
+  topk_merge_kernel<<<(B + 127) / 128, 128, 0, stream>>>(p.ws_scores, p.ws_ids, p.ws_label, parts, B, k,
                                                         topk_scores, topk_ids, label_score);
   return check_launch("rf_cosine_topk/merge");
 }
