@@ -15,6 +15,7 @@
 // 256 x 256 tiles; otherwise single CTAs on 128 x 256 tiles.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "rf_common.h"
 #include "rf_ptx.cuh"
@@ -39,11 +40,15 @@ struct ScoreParams {
   float inv_temp;
   int k;                          // top-k
   int id_base;
-  int slices;                     // S: item-tile slices per user tile
+  int slices;                     // S: item-tile slices per user tile (lock-step CTAs / pairs)
+  int extra;                      // pair kernel: leftover pairs (SM pairs not divisible by the user tiles)
+  int main_tiles;                 // item tiles [0, main_tiles) belong to the lock-step pairs
+  int extra_tiles;                // item tiles [main_tiles, main_tiles + extra_tiles) belong to the leftover pairs
+  int extra_steps;                // (user tile, item tile) steps per leftover pair
   const int64_t* labels;
-  float* ws_scores;               // [2S][B][k]   (part = slice * 2 + column half)
-  int32_t* ws_ids;                // [2S][B][k]
-  float* ws_label;                // [2S][B]
+  float* ws_scores;               // [parts][B][k]   part = (slice or S + extra pair) * 2 + column half
+  int32_t* ws_ids;                // [parts][B][k]
+  float* ws_label;                // [parts][B]
   float* logits;                  // DENSE: [B][N]
 };
 
@@ -267,11 +272,38 @@ cosine_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
-  const int mt = pair / p.slices;
-  const int slice = pair % p.slices;
-  const int m0 = mt * 256 + static_cast<int>(rank) * 128;
+  const int m_tiles = (p.B + 255) / 256;
   const int n_tiles = static_cast<int>((p.N + SC_BN - 1) / SC_BN);
   const int k_blocks = (p.K + SC_BK - 1) / SC_BK;
+  // Work of this pair = a list of segments (user tile, item-tile range).  Lock-step pairs own one user
+  // tile and every S-th item tile of [0, main_tiles): all user tiles advance through the table together,
+  // so a table tile is fetched from HBM once and re-read from L2.  The leftover pairs (SM pairs not
+  // divisible by the user tiles) split the (user tile x item tile) rectangle over the remaining item
+  // tiles into equal contiguous runs in user-tile-major order: few, long segments per pair (every new
+  // segment restarts its top-k list, and a young list inserts often).
+  const int n_main = m_tiles * p.slices;
+  const bool is_extra = pair >= n_main;
+  const int part = is_extra ? p.slices + (pair - n_main) : pair % p.slices;
+  const long long f_lo = is_extra ? static_cast<long long>(pair - n_main) * p.extra_steps : 0;
+  const long long f_end = static_cast<long long>(p.extra_tiles) * m_tiles;
+  const long long f_hi = is_extra ? (f_lo + p.extra_steps < f_end ? f_lo + p.extra_steps : f_end) : 0;
+  struct Seg { int mt, lo, hi, step; };
+  auto first_seg = [&](long long& f) -> bool { f = f_lo; return is_extra ? f < f_hi : true; };
+  auto get_seg = [&](long long f) -> Seg {
+    if (!is_extra) return Seg{pair / p.slices, pair % p.slices, p.main_tiles, p.slices};
+    const int mt = static_cast<int>(f / p.extra_tiles), r0 = static_cast<int>(f % p.extra_tiles);
+    const long long left = f_hi - f;
+    const int r1 = (p.extra_tiles - r0 < left) ? p.extra_tiles : r0 + static_cast<int>(left);
+    return Seg{mt, p.main_tiles + r0, p.main_tiles + r1, 1};
+  };
+  auto next_seg = [&](long long& f, const Seg& sg) -> bool {
+    if (!is_extra) return false;
+    f += sg.hi - sg.lo;
+    return f < f_hi;
+  };
+  const long long my_tiles = is_extra ? (f_hi > f_lo ? f_hi - f_lo : 0)
+                                      : (p.main_tiles > pair % p.slices
+                                             ? (p.main_tiles - pair % p.slices + p.slices - 1) / p.slices : 0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SP_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -289,24 +321,30 @@ cosine_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
       int stage = 0; uint32_t phase = 0;
-      for (int nt = slice; nt < n_tiles; nt += p.slices) {
-        const int n0 = nt * SC_BN + static_cast<int>(rank) * 128;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * SP_STAGE_BYTES);
-          const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
-          uint8_t* sa = smem + stage * SP_STAGE_BYTES;
-          tma_load_2d_pair(sa, &tmA, fb, kb * SC_BK, m0);
-          tma_load_2d_pair(sa + SP_STAGE_BYTES / 2, &tmB, fb, kb * SC_BK, n0);
-          if (++stage == SP_STAGES) { stage = 0; phase ^= 1; }
+      long long f;
+      for (bool more = first_seg(f); more;) {
+        const Seg sg = get_seg(f);
+        const int m0 = sg.mt * 256 + static_cast<int>(rank) * 128;
+        for (int nt = sg.lo; nt < sg.hi; nt += sg.step) {
+          const int n0 = nt * SC_BN + static_cast<int>(rank) * 128;
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * SP_STAGE_BYTES);
+            const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            uint8_t* sa = smem + stage * SP_STAGE_BYTES;
+            tma_load_2d_pair(sa, &tmA, fb, kb * SC_BK, m0);
+            tma_load_2d_pair(sa + SP_STAGE_BYTES / 2, &tmB, fb, kb * SC_BK, n0);
+            if (++stage == SP_STAGES) { stage = 0; phase ^= 1; }
+          }
         }
+        more = next_seg(f, sg);
       }
     }
   } else if (warp == 1) {
     if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, SC_BN, false, false);
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-      for (int nt = slice; nt < n_tiles; nt += p.slices) {
+      for (long long t = 0; t < my_tiles; ++t) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < k_blocks; ++kb) {
@@ -329,36 +367,41 @@ cosine_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else {
     const int quad = warp & 3, half = (warp - 2) >> 2;
-    const int row = m0 + quad * 32 + lane;
-    const bool row_ok = row < p.B;
-    TopkState st;
-    if (MODE == SC_TOPK) topk_state_init(st, s_list, threadIdx.x - 64, p, row, row_ok);
     int acc = 0; uint32_t acc_phase = 0;
-    for (int nt = slice; nt < n_tiles; nt += p.slices) {
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const long long n0 = static_cast<long long>(nt) * SC_BN + half * (SC_BN / 2);
-      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * SC_BN + half * (SC_BN / 2);
-      uint32_t rbuf[2][32];
-      tmem_ld32(tbase, rbuf[0]);
+    long long f;
+    for (bool more = first_seg(f); more;) {
+      const Seg sg = get_seg(f);
+      const int row = sg.mt * 256 + static_cast<int>(rank) * 128 + quad * 32 + lane;
+      const bool row_ok = row < p.B;
+      TopkState st;
+      if (MODE == SC_TOPK) topk_state_init(st, s_list, threadIdx.x - 64, p, row, row_ok);
+      for (int nt = sg.lo; nt < sg.hi; nt += sg.step) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const long long n0 = static_cast<long long>(nt) * SC_BN + half * (SC_BN / 2);
+        const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * SC_BN + half * (SC_BN / 2);
+        uint32_t rbuf[2][32];
+        tmem_ld32(tbase, rbuf[0]);
 #pragma unroll
-      for (int c = 0; c < SC_BN / 2 / 32; ++c) {
-        tmem_ld_wait();
-        if (c + 1 < SC_BN / 2 / 32) {
-          tmem_ld32(tbase + (c + 1) * 32, rbuf[(c + 1) & 1]);
-        } else {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        for (int c = 0; c < SC_BN / 2 / 32; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < SC_BN / 2 / 32) {
+            tmem_ld32(tbase + (c + 1) * 32, rbuf[(c + 1) & 1]);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+          }
+          const long long col0 = n0 + c * 32;
+          if (col0 >= p.N) continue;
+          if (MODE == SC_DENSE) dense_chunk(rbuf[c & 1], p, row, row_ok, col0);
+          else topk_chunk(rbuf[c & 1], st, p, col0);
         }
-        const long long col0 = n0 + c * 32;
-        if (col0 >= p.N) continue;
-        if (MODE == SC_DENSE) dense_chunk(rbuf[c & 1], p, row, row_ok, col0);
-        else topk_chunk(rbuf[c & 1], st, p, col0);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (MODE == SC_TOPK && row_ok) topk_state_flush(st, p, part * 2 + half, row);
+      more = next_seg(f, sg);
     }
-    if (MODE == SC_TOPK && row_ok) topk_state_flush(st, p, slice * 2 + half, row);
   }
   tc_fence_before();
   cluster_sync_all();
@@ -382,7 +425,7 @@ __global__ void topk_merge_kernel(const float* __restrict__ scores, const int32_
     if (label_scores) lab = fmaxf(lab, label_scores[static_cast<size_t>(s) * B + b]);
     for (int q0 = 0; q0 < k; ++q0) {
       float cs = ps[q0]; int ci = pi[q0];
-      if (cs == -INFINITY) break;
+      if (!(cs > -INFINITY)) break;   // -inf = list not full, NaN = part never written for this row
 #pragma unroll
       for (int q = 0; q < SC_MAXK; ++q) {
         if (q < k) {
@@ -540,14 +583,41 @@ ce_norm_bwd_kernel(const void* __restrict__ x_, const float* __restrict__ dxn, f
 
 static bool use_pair(int B) { return B > SC_BM; }
 
-static int pick_slices(int B, long long N) {
+// Fills slices / extra / main_tiles / extra_tiles; returns the number of (slice | leftover pair) parts.
+static int plan_schedule(int B, long long N, ScoreParams* p) {
   const long long n_tiles = (N + SC_BN - 1) / SC_BN;
   long long s;
-  if (use_pair(B)) s = (sm_count() / 2) / ((B + 255) / 256);
-  else s = sm_count() / ((B + SC_BM - 1) / SC_BM);
-  if (s < 1) s = 1;
-  if (s > n_tiles) s = n_tiles;
-  return static_cast<int>(s);
+  int extra = 0;
+  long long main_tiles = n_tiles, extra_tiles = 0, extra_steps = 0;
+  if (use_pair(B)) {
+    const int pairs = sm_count() / 2, m_tiles = (B + 255) / 256;
+    s = pairs / m_tiles;
+    if (s < 1) s = 1;
+    if (s > n_tiles) s = n_tiles;
+    extra = pairs - static_cast<int>(s) * m_tiles;
+    if (extra > 0 && n_tiles >= 8ll * pairs) {
+      // a leftover pair restarts its top-k list at every segment and so spends more time inserting than a
+      // lock-step pair: it also streams its table range from HBM rather than L2.  Measured (4096 x 1M): giving it 60 % of a
+      // lock-step pair's steps minimises the pass time
+      static const int pct = getenv("RF_SCORE_EXTRA_PCT") ? atoi(getenv("RF_SCORE_EXTRA_PCT")) : 60;   // tuning aid
+      extra_tiles = n_tiles * extra * pct / (100ll * pairs);
+      if (extra_tiles == 0) extra = 0;
+      main_tiles = n_tiles - extra_tiles;
+      extra_steps = (extra_tiles * m_tiles + extra - 1) / extra;
+    } else {
+      extra = 0;
+    }
+  } else {
+    s = sm_count() / ((B + SC_BM - 1) / SC_BM);
+    if (s < 1) s = 1;
+    if (s > n_tiles) s = n_tiles;
+  }
+  if (p) {
+    p->slices = static_cast<int>(s); p->extra = extra;
+    p->main_tiles = static_cast<int>(main_tiles); p->extra_tiles = static_cast<int>(extra_tiles);
+    p->extra_steps = static_cast<int>(extra_steps);
+  }
+  return static_cast<int>(s) + extra;
 }
 
 static int launch_cosine(int mode, const void* xn, const void* yn, ScoreParams& p, cudaStream_t stream) {
@@ -563,7 +633,7 @@ static int launch_cosine(int mode, const void* xn, const void* yn, ScoreParams& 
     const CUtensorMap* tmA = get_tmap_2d(xn, p.B, p.K, p.K, 128);
     const CUtensorMap* tmB = get_tmap_2d(yn, static_cast<uint64_t>(p.N), p.K, p.K, 128);
     if (!tmA || !tmB) return RF_ERR_CUDA;
-    const int grid = 2 * ((p.B + 255) / 256) * p.slices;
+    const int grid = 2 * (((p.B + 255) / 256) * p.slices + p.extra);
     if (mode == SC_TOPK)
       cosine_pair_kernel<SC_TOPK><<<grid, SC_THREADS, SP_SMEM, stream>>>(*tmA, *tmB, p);
     else
@@ -606,13 +676,13 @@ extern "C" int rf_cosine_logits(const void* xn, const void* yn, float* logits, i
   RF_REQUIRE(E % 8 == 0, "rf_cosine_logits: E must be a multiple of 8");
   ScoreParams p{};
   p.B = B; p.N = N; p.K = E; p.inv_temp = 1.0f / temp; p.k = 0; p.id_base = 0;
-  p.slices = pick_slices(B, N);
+  plan_schedule(B, N, &p);
   p.logits = logits;
   return launch_cosine(SC_DENSE, xn, yn, p, stream);
 }
 
 extern "C" long long rf_cosine_topk_ws_bytes(int B, long long N, int k) {
-  const long long parts = 2ll * pick_slices(B, N);
+  const long long parts = 2ll * plan_schedule(B, N, nullptr);
   return parts * B * (static_cast<long long>(k) * 8 + 4) + 256;
 }
 
@@ -626,13 +696,15 @@ extern "C" int rf_cosine_topk(const void* xn, const void* yn, int B, long long N
   RF_REQUIRE(N + id_base < 2147483647ll, "rf_cosine_topk: item ids must fit int32");
   ScoreParams p{};
   p.B = B; p.N = N; p.K = E; p.inv_temp = 1.0f / temp; p.k = k; p.id_base = id_base;
-  p.slices = pick_slices(B, N);
+  const int parts = 2 * plan_schedule(B, N, &p);   // every (slice | leftover pair, 128-column half) keeps its own list
   p.labels = labels;
-  const int parts = 2 * p.slices;   // every (slice, 128-column half) keeps its own list
   const size_t cnt = static_cast<size_t>(parts) * B * k;
   p.ws_scores = reinterpret_cast<float*>(ws);
   p.ws_ids = reinterpret_cast<int32_t*>(p.ws_scores + cnt);
   p.ws_label = reinterpret_cast<float*>(p.ws_ids + cnt);
+  // a leftover pair only writes the rows of the user tiles it visited: every other (part, row) slot keeps
+  // this NaN pattern, which the merge skips
+  RF_CUDA(cudaMemsetAsync(ws, 0xFF, cnt * 8 + static_cast<size_t>(parts) * B * 4, stream));
   int rc = launch_cosine(SC_TOPK, xn, yn, p, stream);
   if (rc) return rc;
   topk_merge_kernel<<<(B + 127) / 128, 128, 0, stream>>>(p.ws_scores, p.ws_ids, p.ws_label, parts, B, k,

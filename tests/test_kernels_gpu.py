@@ -277,6 +277,25 @@ def test_normalize_and_logits_and_topk():
     assert torch.equal(ls, logits[torch.arange(B, device=DEV), labels])
 
 
+def test_topk_large_catalogue_leftover_pairs_and_ties():
+    """Big enough (>= 8 item tiles per SM pair, 3 user tiles) that the CTA-pair scheduler also uses its
+    leftover pairs (private item range swept over all user tiles); duplicated rows create exact ties that
+    must resolve towards the lower id; N is not a multiple of the 256-item tile."""
+    B, N, E = 700, 160_000 + 37, 768
+    xn = ops.normalize_rows(rnd(B, E, seed=1, dtype=torch.float32))
+    yn = ops.normalize_rows(rnd(N, E, seed=2, dtype=torch.float32))
+    yn[N - 5] = yn[17]           # same score at two ids far apart (different tiles / parts)
+    yn[90_000] = yn[155_000]
+    labels = torch.randint(0, N, (B,), device=DEV)
+    labels[:3] = torch.tensor([17, N - 5, N - 1], device=DEV)
+    ts, ti, ls = ops.cosine_topk(xn, yn, 0.05, k=10, labels=labels)
+    logits = ops.cosine_logits(xn, yn, 0.05)
+    order = torch.argsort(logits, dim=1, descending=True, stable=True)[:, :10]
+    assert torch.equal(ti.long(), order)
+    assert torch.equal(ts, torch.gather(logits, 1, order))
+    assert torch.equal(ls, logits[torch.arange(B, device=DEV), labels])
+
+
 def test_topk_sharded_merge_matches_unsharded():
     B, N, E, S = 130, 4096 + 77, 768, 4
     xn = ops.normalize_rows(rnd(B, E, seed=1, dtype=torch.float32))
