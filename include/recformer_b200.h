@@ -182,7 +182,8 @@ int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx_bf16, const float* l
  *   q_g = (Wqg x_cls + bqg)/sqrt(D);  u_h = Wkg[h]^T q_g[h];  s_j = u_h . x_j  (b_kg cancels in
  *   the softmax);  p = softmax_{valid j}(s);  m_h = sum_j p_j x_j;  out[h] = Wvg[h] m_h + bvg[h].
  * Writes row 0 of every sequence in ctx.  Saved for backward: qg [B,E], u [B,H,E], p [B,H,L],
- * mvec [B,H,E], psum [B,H] = sum_j dropout(p)_j (all fp32). */
+ * pt [B,L,16] = dropout(p) transposed (token-major, 12 heads + 4 pad; 16-byte aligned), mvec [B,H,E],
+ * psum [B,H] = sum_j dropout(p)_j (all fp32). */
 typedef struct rf_global_args {
   const void* x;  /* bf16 [B*L,E] layer input */
   const uint8_t* mask012;
@@ -194,15 +195,20 @@ typedef struct rf_global_args {
   uint64_t drop_seed;
 } rf_global_args;
 
-int rf_global_attn_fwd(const rf_global_args* a, void* ctx_bf16, float* qg, float* u, float* p, float* mvec,
+int rf_global_attn_fwd(const rf_global_args* a, void* ctx_bf16, float* qg, float* u, float* p, float* pt, float* mvec,
                        float* psum, rf_stream_t stream);
 /* Backward of the CLS row: reads dctx row 0; accumulates (+=) fp32 dWqg,dbqg,dWkg,dWvg,dbvg (any
  * may be NULL; dbkg is identically zero) and ADDS the dense gradient the row sends to every
- * token (through s_j and m_h) into dx (bf16 [B*L,E]).  ws: rf_global_attn_bwd_ws_bytes(). */
+ * token (through s_j and m_h) into dx (bf16 [B*L,E]).  ws: rf_global_attn_bwd_ws_bytes().
+ * With dx == NULL only the weight-gradient part runs (it needs dctx but not dx, so it can overlap
+ * the band-attention backward on another stream); rf_global_attn_bwd_dx then adds the token
+ * gradients into dx from the workspace that call left behind. */
 long long rf_global_attn_bwd_ws_bytes(int B, int L, int H);
 int rf_global_attn_bwd(const rf_global_args* a, const void* dctx_bf16, const float* qg, const float* u,
-                       const float* p, const float* mvec, const float* psum, void* dx_bf16, float* dWqg, float* dbqg,
-                       float* dWkg, float* dWvg, float* dbvg, float* ws, rf_stream_t stream);
+                       const float* p, const float* pt, const float* mvec, const float* psum, void* dx_bf16,
+                       float* dWqg, float* dbqg, float* dWkg, float* dWvg, float* dbvg, float* ws, rf_stream_t stream);
+int rf_global_attn_bwd_dx(const rf_global_args* a, const float* u, const float* pt, void* dx_bf16, const float* ws,
+                          rf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Scoring (SURVEY.md §8a Spec S; ref: recformer/models.py:358-369,533-545) and metrics

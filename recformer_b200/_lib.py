@@ -62,10 +62,12 @@ _SIGS = {
     "rf_band_attn_fwd": (c_int, [P(AttnArgs), c_void_p, c_void_p, c_void_p]),
     "rf_band_attn_bwd": (c_int, [P(AttnArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rf_global_attn_fwd": (c_int, [P(GlobalArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                   c_void_p]),
+                                   c_void_p, c_void_p]),
     "rf_global_attn_bwd_ws_bytes": (c_ll, [c_int, c_int, c_int]),
     "rf_global_attn_bwd": (c_int, [P(GlobalArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p]),
+    "rf_global_attn_bwd_dx": (c_int, [P(GlobalArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rf_normalize_rows": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "rf_cosine_logits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_void_p]),
     "rf_cosine_topk_ws_bytes": (c_ll, [c_int, c_ll, c_int]),

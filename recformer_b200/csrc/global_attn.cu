@@ -9,9 +9,14 @@
 //   m_h   = sum_j p'_hj x_j        (p' = dropout(p))                 [E]
 //   out_h = Wvg[h] m_h + bvg[h] * sum_j p'_hj                        [D]
 //
-// Per sequence this is 2*H*L*E MACs instead of 2*L*E*E: 64x less work than the two full GEMMs,
-// so plain CUDA-core kernels (coalesced, warp-shuffle reductions) are sufficient; they are
-// bound by reading x (L x E bf16) twice from L2/HBM.
+// Per sequence this is 2*H*L*E MACs instead of 2*L*E*E: 64x less work than the two full GEMMs, and
+// it is memory-bound (x, [B*L, E] bf16, is streamed once per pass), so it runs on CUDA cores:
+//   * token-parallel "dots" kernel (s_hj, and dp_hj in backward): the 12 per-sequence vectors sit in
+//     registers (3 heads per warp), x rows are streamed with 128-bit loads, 4 tokens x 3 heads are
+//     reduced with one 16-value reduce-scatter (16 shuffles instead of 60);
+//   * column-sliced "mix" kernels (m_h, and du_h / dx in backward): a CTA owns 32 columns of one
+//     sequence and walks all its tokens, so every output element has ONE writer — no atomics;
+//   * the 768x768 *_global weight products are batched over the sequences (weights read once).
 #include <cuda_bf16.h>
 #include <math.h>
 
@@ -23,143 +28,322 @@ namespace rf {
 constexpr int GH = 12;    // heads
 constexpr int GE = 768;   // hidden
 constexpr int GD = 64;    // head dim
-constexpr int TOK = 32;   // tokens per CTA in the token-parallel kernels (4 per warp)
+constexpr int GBB = 16;   // sequences per batch-block of the weight-product kernels
 
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 
-__device__ __forceinline__ void load_row24(const __nv_bfloat16* __restrict__ row, int lane, float (&xv)[24]) {
-  const uint4* xr = reinterpret_cast<const uint4*>(row);
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const uint4 raw = xr[k * 32 + lane];
-    const float2 a0 = unpack_bf16(raw.x), a1 = unpack_bf16(raw.y), a2 = unpack_bf16(raw.z), a3 = unpack_bf16(raw.w);
-    xv[k * 8 + 0] = a0.x; xv[k * 8 + 1] = a0.y; xv[k * 8 + 2] = a1.x; xv[k * 8 + 3] = a1.y;
-    xv[k * 8 + 4] = a2.x; xv[k * 8 + 5] = a2.y; xv[k * 8 + 6] = a3.x; xv[k * 8 + 7] = a3.y;
-  }
+__device__ __forceinline__ bool seq_has_global(const uint8_t* mask, int b, int L) {
+  return mask[static_cast<size_t>(b) * L] == 2;
 }
 
-// dot of a weight row (fp32, global) with a vector in shared memory; one warp, float4 loads
-__device__ __forceinline__ float warp_dot768(const float* __restrict__ w, const float* xs, int lane) {
-  float acc = 0.f;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(w) + k * 32 + lane);
-    const float4 b = *reinterpret_cast<const float4*>(xs + (k * 32 + lane) * 4);
-    acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
-  }
-  return warp_sum(acc);
+// keep (scaled) / drop factor of probability (b,h,j): the same counter-based mask in every kernel
+__device__ __forceinline__ float drop_factor(uint64_t seed, uint32_t thresh, float scale, uint64_t idx) {
+  if (thresh == 0) return 1.0f;
+  const uint32_t keep = dropout_keep8(seed, idx >> 3, thresh);
+  return ((keep >> (idx & 7)) & 1u) ? scale : 0.0f;
 }
 
-// ---- G1: q_g and u_h; also zeroes the m / psum accumulators.  grid (H, B), 256 threads ----
-__global__ void __launch_bounds__(256)
-global_qu_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ Wqg, const float* __restrict__ bqg,
-                 const float* __restrict__ Wkg, int L, float* __restrict__ qg, float* __restrict__ u,
-                 float* __restrict__ mvec, float* __restrict__ psum) {
-  const int h = blockIdx.x, b = blockIdx.y;
-  __shared__ __align__(16) float xs[GE];
-  __shared__ float qs[GD];
+// ---------------------------------------------------------------------------------------------
+// Weight products, batched over sequences.
+//
+// rowdot: out[b, r] = W[r, :] . V_b(r)        one warp per weight row r, V staged in shared memory
+//   MODE_Q  : V = x_cls[b] (bf16);               q_g = (dot + bqg[r]) / 8                -> qg
+//   MODE_OUT: V = m[b, h(r), :];                 ctx[b, 0, r] = dot + bvg[r] * psum[b,h]  (if global)
+//   MODE_DQ : V = du[b, h(r), :];                dq = dot / 8 (0 if no global) -> dqf; dbqg[r] += sum_b dq
+// grid (E / 8, ceil(B / 16)), 256 threads (8 rows of the same head per CTA).
+// ---------------------------------------------------------------------------------------------
+enum { MODE_Q = 0, MODE_OUT = 1, MODE_DQ = 2 };
+
+struct RowdotParams {
+  const float* W;             // [E, E]
+  const float* bias;          // [E] or null
+  const __nv_bfloat16* x;     // MODE_Q: layer input [B*L, E]
+  const float* V;             // MODE_OUT / MODE_DQ: [B, H, E]
+  const float* psum;          // MODE_OUT: [B, H]
+  const uint8_t* mask;
+  float* out_f32;             // MODE_Q: qg [B,E]; MODE_DQ: dqf [B,E]
+  __nv_bfloat16* ctx;         // MODE_OUT: [B*L, E]
+  float* dbias;               // MODE_DQ: dbqg (+=) or null
+  int B, L;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) global_rowdot_kernel(const RowdotParams p) {
+  __shared__ __align__(16) float vs[GBB][GE];   // 48 KB
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const __nv_bfloat16* xc = x + static_cast<size_t>(b) * L * GE;   // row 0 of the sequence
-  for (int e = tid; e < GE; e += 256) {
-    xs[e] = __bfloat162float(xc[e]);
-    mvec[(static_cast<size_t>(b) * GH + h) * GE + e] = 0.f;
+  const int r = blockIdx.x * 8 + warp;
+  const int h = (blockIdx.x * 8) / GD;
+  const int b0 = blockIdx.y * GBB;
+  const int nb = min(GBB, p.B - b0);
+  for (int i = tid; i < nb * (GE / 4); i += 256) {
+    const int bb = i / (GE / 4), c4 = i % (GE / 4);
+    float4 v;
+    if (MODE == MODE_Q) {
+      const uint2 raw = *reinterpret_cast<const uint2*>(p.x + static_cast<size_t>(b0 + bb) * p.L * GE + c4 * 4);
+      const float2 a = unpack_bf16(raw.x), c = unpack_bf16(raw.y);
+      v = make_float4(a.x, a.y, c.x, c.y);
+    } else {
+      v = *reinterpret_cast<const float4*>(p.V + (static_cast<size_t>(b0 + bb) * GH + h) * GE + c4 * 4);
+    }
+    *reinterpret_cast<float4*>(&vs[bb][c4 * 4]) = v;
   }
-  if (tid == 0) psum[b * GH + h] = 0.f;
+  float4 w[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) w[k] = __ldg(reinterpret_cast<const float4*>(p.W + static_cast<size_t>(r) * GE) + k * 32 + lane);
   __syncthreads();
-#pragma unroll 2
-  for (int d = warp; d < GD; d += 8) {
-    const float acc = warp_dot768(Wqg + static_cast<size_t>(h * GD + d) * GE, xs, lane);
-    if (lane == 0) {
-      const float q = (acc + bqg[h * GD + d]) * 0.125f;
-      qs[d] = q;
-      qg[static_cast<size_t>(b) * GE + h * GD + d] = q;
+  float mine = 0.f;      // lane bb keeps the result of sequence b0 + bb
+  for (int bb = 0; bb < nb; ++bb) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float4 v = *reinterpret_cast<const float4*>(&vs[bb][(k * 32 + lane) * 4]);
+      acc += w[k].x * v.x + w[k].y * v.y + w[k].z * v.z + w[k].w * v.w;
+    }
+    acc = warp_sum(acc);
+    if (lane == bb) mine = acc;
+  }
+  const int b = b0 + lane;
+  const bool have = lane < nb;
+  if (MODE == MODE_Q) {
+    if (have) p.out_f32[static_cast<size_t>(b) * GE + r] = (mine + p.bias[r]) * 0.125f;
+  } else if (MODE == MODE_OUT) {
+    if (have && seq_has_global(p.mask, b, p.L))
+      p.ctx[static_cast<size_t>(b) * p.L * GE + r] = __float2bfloat16(mine + p.bias[r] * p.psum[b * GH + h]);
+  } else {
+    float g = 0.f;
+    if (have) {
+      g = seq_has_global(p.mask, b, p.L) ? mine * 0.125f : 0.f;   // gradient w.r.t. (Wqg x + bqg)
+      p.out_f32[static_cast<size_t>(b) * GE + r] = g;
+    }
+    if (p.dbias != nullptr) {
+      g = warp_sum(g);
+      if (lane == 0) red_add_f32(p.dbias + r, g);
+    }
+  }
+}
+
+// colmix: out[b, h, e] = sum_d W[h*64 + d, e] * A[b, h*64 + d]     (W^T applied per head)
+//   u  = colmix(Wkg, q_g),  dm = colmix(Wvg, dout)
+// grid (E / 64, H, ceil(B / 16)), 64 threads; thread = column e, 16 sequences in registers.
+// Also, for the dm call, produces dpsum[b,h] = bvg[h] . dout_h, dbvg += dout_h psum, and the fp32 copy
+// of dout (zero for sequences without a global token).
+struct ColmixParams {
+  const float* W;
+  const float* A;                 // [B, E] fp32, or null when A is read from dctx
+  const __nv_bfloat16* dctx;      // A = row 0 of dctx for sequences with a global token
+  const uint8_t* mask;
+  float* out;                     // [B, H, E]
+  // dm extras (null otherwise)
+  const float* bvg; const float* psum; float* dpsum; float* dbvg; float* doutf;
+  int B, L;
+};
+
+__global__ void __launch_bounds__(64) global_colmix_kernel(const ColmixParams p) {
+  __shared__ __align__(16) float as[GD][GBB];
+  const int tid = threadIdx.x;
+  const int e = blockIdx.x * 64 + tid, h = blockIdx.y, b0 = blockIdx.z * GBB;
+  const int nb = min(GBB, p.B - b0);
+  // all 64 weight loads of this thread's column are issued before anything waits on memory
+  float w[GD];
+  const float* wp = p.W + static_cast<size_t>(h) * GD * GE + e;
+#pragma unroll
+  for (int d = 0; d < GD; ++d) w[d] = __ldg(wp + static_cast<size_t>(d) * GE);
+  for (int i = tid; i < GD * GBB; i += 64) {
+    const int d = i / GBB, bb = i % GBB;
+    float v = 0.f;
+    if (bb < nb) {
+      const int b = b0 + bb;
+      if (p.A != nullptr) v = p.A[static_cast<size_t>(b) * GE + h * GD + d];
+      else if (seq_has_global(p.mask, b, p.L)) v = __bfloat162float(p.dctx[static_cast<size_t>(b) * p.L * GE + h * GD + d]);
+    }
+    as[d][bb] = v;
+  }
+  __syncthreads();
+  if (p.dpsum != nullptr && blockIdx.x == 0) {   // the extras of the dm call: once per (h, batch block)
+    {
+      float gsum = 0.f;
+      for (int bb = 0; bb < nb; ++bb) {
+        const float g = as[tid][bb];
+        p.doutf[static_cast<size_t>(b0 + bb) * GE + h * GD + tid] = g;
+        gsum += g * p.psum[(b0 + bb) * GH + h];
+      }
+      if (p.dbvg != nullptr) red_add_f32(p.dbvg + h * GD + tid, gsum);
+    }
+    if (tid < nb) {
+      float t = 0.f;
+      for (int d = 0; d < GD; ++d) t += p.bvg[h * GD + d] * as[d][tid];
+      p.dpsum[(b0 + tid) * GH + h] = t;
+    }
+  }
+  float acc[GBB];
+#pragma unroll
+  for (int bb = 0; bb < GBB; ++bb) acc[bb] = 0.f;
+#pragma unroll
+  for (int d = 0; d < GD; ++d) {
+#pragma unroll
+    for (int q = 0; q < GBB / 4; ++q) {
+      const float4 a = *reinterpret_cast<const float4*>(&as[d][q * 4]);
+      acc[q * 4 + 0] += w[d] * a.x; acc[q * 4 + 1] += w[d] * a.y; acc[q * 4 + 2] += w[d] * a.z; acc[q * 4 + 3] += w[d] * a.w;
+    }
+  }
+#pragma unroll
+  for (int bb = 0; bb < GBB; ++bb)
+    if (bb < nb) p.out[(static_cast<size_t>(b0 + bb) * GH + h) * GE + e] = acc[bb];
+}
+
+// dxcls: dx[b, 0, e] += sum_r Wqg[r, e] * dq[b, r]   (all 768 rows: the CLS token's own input gradient)
+// grid (E / 64, ceil(B / 16)), 768 threads = 64 columns x 12 heads; heads reduced through shared memory.
+__global__ void __launch_bounds__(768)
+global_dxcls_kernel(const float* __restrict__ Wqg, const float* __restrict__ dqf, const uint8_t* __restrict__ mask,
+                    int B, int L, __nv_bfloat16* __restrict__ dx) {
+  __shared__ __align__(16) float as[GE][GBB];        // 48 KB: dq of 16 sequences
+  const int tid = threadIdx.x, c = tid & 63, h = tid >> 6;
+  const int e = blockIdx.x * 64 + c, b0 = blockIdx.y * GBB;
+  const int nb = min(GBB, B - b0);
+  float w[GD];     // this thread's 64 weights (head h, column e): loads issued before the staging below
+  {
+    const float* wp = Wqg + static_cast<size_t>(h) * GD * GE + e;
+#pragma unroll
+    for (int d = 0; d < GD; ++d) w[d] = __ldg(wp + static_cast<size_t>(d) * GE);
+  }
+  for (int i = tid; i < GE * GBB; i += 768) {
+    const int r = i / GBB, bb = i % GBB;
+    as[r][bb] = bb < nb ? dqf[static_cast<size_t>(b0 + bb) * GE + r] : 0.f;
+  }
+  __syncthreads();
+  float acc[GBB];
+#pragma unroll
+  for (int bb = 0; bb < GBB; ++bb) acc[bb] = 0.f;
+#pragma unroll
+  for (int d = 0; d < GD; ++d) {
+#pragma unroll
+    for (int q = 0; q < GBB / 4; ++q) {
+      const float4 a = *reinterpret_cast<const float4*>(&as[h * GD + d][q * 4]);
+      acc[q * 4 + 0] += w[d] * a.x; acc[q * 4 + 1] += w[d] * a.y; acc[q * 4 + 2] += w[d] * a.z; acc[q * 4 + 3] += w[d] * a.w;
     }
   }
   __syncthreads();
-  for (int e = tid; e < GE; e += 256) {
-    float acc = 0.f;
-#pragma unroll 16
-    for (int d = 0; d < GD; ++d) acc += __ldg(Wkg + static_cast<size_t>(h * GD + d) * GE + e) * qs[d];
-    u[(static_cast<size_t>(b) * GH + h) * GE + e] = acc;
+  float* red = &as[0][0];                             // reuse: [12][16][64]
+#pragma unroll
+  for (int bb = 0; bb < GBB; ++bb) red[(h * GBB + bb) * 64 + c] = acc[bb];
+  __syncthreads();
+  for (int i = tid; i < nb * 64; i += 768) {
+    const int bb = i / 64, cc = i % 64;
+    if (!seq_has_global(mask, b0 + bb, L)) continue;
+    float t = 0.f;
+#pragma unroll
+    for (int hh = 0; hh < GH; ++hh) t += red[(hh * GBB + bb) * 64 + cc];
+    __nv_bfloat16* d = dx + static_cast<size_t>(b0 + bb) * L * GE + blockIdx.x * 64 + cc;
+    *d = __float2bfloat16(__bfloat162float(*d) + t);
   }
 }
 
-// ---- G2 / GB2: per-token dot products against 12 per-sequence vectors.  grid (L/32, B) ----
-//   MODE 0: s[b,h,j] = u_h . x_j                       (-inf for padded keys)
-//   MODE 1: dp[b,h,j] = keep_j*scale*(dm_h . x_j + dpsum_h)   (0 for padded keys)
+// ---------------------------------------------------------------------------------------------
+// dots: per-token dot products against the 12 per-sequence vectors.  grid (ceil(L/64), B), 256 thr.
+//   MODE 0: s[b,h,j]  = u_h . x_j                              (-inf for padded keys)
+//   MODE 1: dp[b,h,j] = keep_j * scale * (dm_h . x_j + dpsum_h)   (0 for padded keys)
+// warp = (head group hg = warp & 3 -> heads 3hg..3hg+2, token half warp >> 2 -> 32 tokens); the
+// warp's 3 vectors live in registers (lane holds the 24 columns of its three 16-byte x units).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4 raw, float (&v)[8]) {
+  const float2 a0 = unpack_bf16(raw.x), a1 = unpack_bf16(raw.y), a2 = unpack_bf16(raw.z), a3 = unpack_bf16(raw.w);
+  v[0] = a0.x; v[1] = a0.y; v[2] = a1.x; v[3] = a1.y; v[4] = a2.x; v[5] = a2.y; v[6] = a3.x; v[7] = a3.y;
+}
+
+// 16 values per lane -> lane l ends with the 32-lane sum of value ((l >> 1) & 15)
+__device__ __forceinline__ float reduce_scatter16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    const int n = 8 >> step;              // values kept after this step
+    const int bit = 16 >> step;           // lane bit that selects the kept half
+    const bool hi = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < n) {
+        const float send = hi ? v[i] : v[i + n];
+        const float keep = hi ? v[i + n] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+      }
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
 global_dots_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict__ mask,
                    const float* __restrict__ vecs, const float* __restrict__ dpsum, int L, float drop_scale,
                    uint32_t drop_thresh, uint64_t drop_seed, float* __restrict__ out) {
-  const int b = blockIdx.y, j0 = blockIdx.x * TOK;
-  extern __shared__ __align__(16) float us[];   // [GH][GE]
+  const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float4* ub = reinterpret_cast<const float4*>(vecs + static_cast<size_t>(b) * GH * GE);
-  for (int i = tid; i < GH * GE / 4; i += 256) reinterpret_cast<float4*>(us)[i] = __ldg(ub + i);
-  __syncthreads();
-#pragma unroll 1
-  for (int pair = 0; pair < 2; ++pair) {
-    const int ja = j0 + warp * 4 + pair * 2, jb = ja + 1;
-    if (ja >= L) break;
-    const bool has_b = jb < L;
-    float xa[24], xb[24];
-    load_row24(x + (static_cast<size_t>(b) * L + ja) * GE, lane, xa);
-    load_row24(x + (static_cast<size_t>(b) * L + (has_b ? jb : ja)) * GE, lane, xb);
-    float ra[GH], rb[GH];
+  const int hg = warp & 3;
+  const int j_begin = blockIdx.x * 64 + (warp >> 2) * 32;
+  float u[3][24];
 #pragma unroll
-    for (int h = 0; h < GH; ++h) {
-      float sa = 0.f, sb = 0.f;
+  for (int hh = 0; hh < 3; ++hh) {
+    const float4* up = reinterpret_cast<const float4*>(vecs + (static_cast<size_t>(b) * GH + hg * 3 + hh) * GE);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float4 a = __ldg(up + (k * 32 + lane) * 2), c = __ldg(up + (k * 32 + lane) * 2 + 1);
+      u[hh][k * 8 + 0] = a.x; u[hh][k * 8 + 1] = a.y; u[hh][k * 8 + 2] = a.z; u[hh][k * 8 + 3] = a.w;
+      u[hh][k * 8 + 4] = c.x; u[hh][k * 8 + 5] = c.y; u[hh][k * 8 + 6] = c.z; u[hh][k * 8 + 7] = c.w;
+    }
+  }
+  // lane l receives (after the reduce-scatter) value index (l >> 1) & 15 = t * 3 + hh for t < 4
+  const int vi = (lane >> 1) & 15;
+  const int my_t = vi / 3, my_h = hg * 3 + vi % 3;
+  const float my_dpsum = (MODE == 1 && vi < 12) ? dpsum[b * GH + my_h] : 0.f;
+#pragma unroll 1
+  for (int j0 = j_begin; j0 < j_begin + 32 && j0 < L; j0 += 4) {
+    uint4 raw[4][3];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = min(j0 + t, L - 1);
+      const uint4* xr = reinterpret_cast<const uint4*>(x + (static_cast<size_t>(b) * L + j) * GE);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) raw[t][k] = xr[k * 32 + lane];
+    }
+    float v[16];
+#pragma unroll
+    for (int i = 12; i < 16; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const float* up = us + h * GE + (k * 32 + lane) * 8;
-        const float4 u0 = *reinterpret_cast<const float4*>(up), u1 = *reinterpret_cast<const float4*>(up + 4);
-        sa += xa[k * 8 + 0] * u0.x + xa[k * 8 + 1] * u0.y + xa[k * 8 + 2] * u0.z + xa[k * 8 + 3] * u0.w +
-              xa[k * 8 + 4] * u1.x + xa[k * 8 + 5] * u1.y + xa[k * 8 + 6] * u1.z + xa[k * 8 + 7] * u1.w;
-        sb += xb[k * 8 + 0] * u0.x + xb[k * 8 + 1] * u0.y + xb[k * 8 + 2] * u0.z + xb[k * 8 + 3] * u0.w +
-              xb[k * 8 + 4] * u1.x + xb[k * 8 + 5] * u1.y + xb[k * 8 + 6] * u1.z + xb[k * 8 + 7] * u1.w;
-      }
-      ra[h] = sa; rb[h] = sb;
-    }
+        float xv[8];
+        unpack8(raw[t][k], xv);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int h = 0; h < GH; ++h) {
-        ra[h] += __shfl_xor_sync(0xffffffffu, ra[h], o);
-        rb[h] += __shfl_xor_sync(0xffffffffu, rb[h], o);
-      }
-    }
-    if (lane < GH) {
-      const int h = lane;
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int j = t == 0 ? ja : jb;
-        if (j >= L) break;
-        float v = 0.f;
-#pragma unroll
-        for (int hh = 0; hh < GH; ++hh) if (hh == h) v = (t == 0) ? ra[hh] : rb[hh];
-        const bool valid = mask[static_cast<size_t>(b) * L + j] != 0;
-        if (MODE == 0) {
-          v = valid ? v : -INFINITY;
-        } else {
-          v = valid ? v + dpsum[b * GH + h] : 0.f;
-          if (drop_thresh != 0) {
-            const uint64_t idx = (static_cast<uint64_t>(b) * GH + h) * L + j;
-            const uint32_t keep = dropout_keep8(drop_seed, idx >> 3, drop_thresh);
-            v = ((keep >> (idx & 7)) & 1u) ? v * drop_scale : 0.f;
-          }
+        for (int i = 0; i < 8; ++i) {
+          a0 += xv[i] * u[0][k * 8 + i];
+          a1 += xv[i] * u[1][k * 8 + i];
+          a2 += xv[i] * u[2][k * 8 + i];
         }
-        out[(static_cast<size_t>(b) * GH + h) * L + j] = v;
       }
+      v[t * 3 + 0] = a0; v[t * 3 + 1] = a1; v[t * 3 + 2] = a2;
+    }
+    float r = reduce_scatter16(v, lane);
+    const int j = j0 + my_t;
+    if ((lane & 1) == 0 && vi < 12 && j < L) {
+      const bool valid = mask[static_cast<size_t>(b) * L + j] != 0;
+      const uint64_t idx = (static_cast<uint64_t>(b) * GH + my_h) * L + j;
+      if (MODE == 0) r = valid ? r : -INFINITY;
+      else r = valid ? (r + my_dpsum) * drop_factor(drop_seed, drop_thresh, drop_scale, idx) : 0.f;
+      out[idx] = r;
     }
   }
 }
 
-// ---- G2b: in-place softmax over j for each (b,h).  grid (B*H), 256 threads ----
-__global__ void __launch_bounds__(256) global_softmax_kernel(float* __restrict__ s, int L) {
+// ---- softmax over j for each (b,h), in place (p is saved for backward); also writes the dropped,
+//      transposed copy pt[b, j, h] = p'_hj (the coefficient layout of the mix kernels) and
+//      psum[b,h] = sum_j p'_hj.  grid (B*H), 256 threads ----
+__global__ void __launch_bounds__(256)
+global_softmax_kernel(float* __restrict__ s, int L, float drop_scale, uint32_t drop_thresh, uint64_t drop_seed,
+                      float* __restrict__ pt, float* __restrict__ psum) {
   float* row = s + static_cast<size_t>(blockIdx.x) * L;
+  const int b = blockIdx.x / GH, h = blockIdx.x % GH;
   __shared__ float red[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float m = -INFINITY;
@@ -180,142 +364,33 @@ __global__ void __launch_bounds__(256) global_softmax_kernel(float* __restrict__
   l = 0.f;
 #pragma unroll
   for (int w = 0; w < 8; ++w) l += red[w];
+  __syncthreads();
   const float inv = l > 0.f ? 1.f / l : 0.f;
-  for (int j = tid; j < L; j += 256) row[j] = __expf(row[j] - m) * inv;
-}
-
-// coefficient tile loader shared by mix / dx: cp[h][jj] = dropout(p)[b,h,j0+jj] (and cs = ds)
-__device__ __forceinline__ void load_coefs(const float* __restrict__ p, const float* __restrict__ ds, int b, int j0,
-                                           int L, float drop_scale, uint32_t drop_thresh, uint64_t drop_seed,
-                                           float (*cp)[TOK], float (*cs)[TOK]) {
-  for (int i = threadIdx.x; i < GH * TOK; i += 256) {
-    const int h = i / TOK, jj = i % TOK;
-    const int j = j0 + jj;
-    float v = 0.f, s = 0.f;
-    if (j < L) {
-      const uint64_t idx = (static_cast<uint64_t>(b) * GH + h) * L + j;
-      v = p[idx];
-      if (ds) s = ds[idx];
-      if (drop_thresh != 0) {
-        const uint32_t keep = dropout_keep8(drop_seed, idx >> 3, drop_thresh);
-        v = ((keep >> (idx & 7)) & 1u) ? v * drop_scale : 0.f;
-      }
-    }
-    cp[h][jj] = v;
-    if (cs) cs[h][jj] = s;
+  float ps = 0.f;
+  for (int j = tid; j < L; j += 256) {
+    const float pr = __expf(row[j] - m) * inv;
+    row[j] = pr;
+    const float pd = pr * drop_factor(drop_seed, drop_thresh, drop_scale, static_cast<uint64_t>(blockIdx.x) * L + j);
+    pt[(static_cast<size_t>(b) * L + j) * 16 + h] = pd;
+    ps += pd;
   }
-}
-
-// ---- G3: m[b,h,:] += sum_{j in chunk} p'[b,h,j] x[b,j,:].  grid (L/32, B), 256 threads ----
-// thread owns column pair `tid` (cols 2tid, 2tid+1) and, for tid < 128, pair 256+tid
-__global__ void __launch_bounds__(256)
-global_mix_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ p, int L, float drop_scale,
-                  uint32_t drop_thresh, uint64_t drop_seed, float* __restrict__ mvec, float* __restrict__ psum) {
-  const int b = blockIdx.y, j0 = blockIdx.x * TOK;
-  __shared__ float ps[GH][TOK];
-  const int tid = threadIdx.x;
-  load_coefs(p, nullptr, b, j0, L, drop_scale, drop_thresh, drop_seed, ps, nullptr);
+  ps = warp_sum(ps);
+  if (lane == 0) red[warp] = ps;
   __syncthreads();
-  if (tid < GH) {   // sum of (dropped) probabilities: multiplies the value bias
-    float t = 0.f;
-    for (int jj = 0; jj < TOK; ++jj) t += ps[tid][jj];
-    red_add_f32(psum + b * GH + tid, t);
-  }
-  const bool second = tid < 128;
-  float acc[GH][4];
-#pragma unroll
-  for (int h = 0; h < GH; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
-  const int n = min(TOK, L - j0);
-  for (int jj = 0; jj < n; jj += 4) {
-    uint32_t r0[4], r1[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int j = min(jj + t, n - 1);
-      const uint32_t* xr = reinterpret_cast<const uint32_t*>(x + (static_cast<size_t>(b) * L + j0 + j) * GE);
-      r0[t] = xr[tid];
-      r1[t] = second ? xr[256 + tid] : 0u;
-    }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (jj + t < n) {
-        const float2 v0 = unpack_bf16(r0[t]), v1 = unpack_bf16(r1[t]);
-#pragma unroll
-        for (int h = 0; h < GH; ++h) {
-          const float pw = ps[h][jj + t];
-          acc[h][0] += pw * v0.x; acc[h][1] += pw * v0.y; acc[h][2] += pw * v1.x; acc[h][3] += pw * v1.y;
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int h = 0; h < GH; ++h) {
-    float* mb = mvec + (static_cast<size_t>(b) * GH + h) * GE;
-    red_add_f32(mb + tid * 2, acc[h][0]);
-    red_add_f32(mb + tid * 2 + 1, acc[h][1]);
-    if (second) {
-      red_add_f32(mb + 512 + tid * 2, acc[h][2]);
-      red_add_f32(mb + 512 + tid * 2 + 1, acc[h][3]);
-    }
-  }
-}
-
-// ---- G4: out[b, h*64+d] = Wvg[h*64+d,:] . m[b,h,:] + bvg * psum -> ctx row 0.  grid (H, B) ----
-__global__ void __launch_bounds__(256)
-global_out_kernel(const float* __restrict__ mvec, const float* __restrict__ psum, const float* __restrict__ Wvg,
-                  const float* __restrict__ bvg, const uint8_t* __restrict__ mask, int L,
-                  __nv_bfloat16* __restrict__ ctx) {
-  const int h = blockIdx.x, b = blockIdx.y;
-  if (mask[static_cast<size_t>(b) * L] != 2) return;   // no global token in this sequence
-  __shared__ __align__(16) float ms[GE];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* mb = mvec + (static_cast<size_t>(b) * GH + h) * GE;
-  for (int e = tid; e < GE; e += 256) ms[e] = mb[e];
-  __syncthreads();
-  const float ps = psum[b * GH + h];
-#pragma unroll 2
-  for (int d = warp; d < GD; d += 8) {
-    const float acc = warp_dot768(Wvg + static_cast<size_t>(h * GD + d) * GE, ms, lane);
-    if (lane == 0) ctx[static_cast<size_t>(b) * L * GE + h * GD + d] = __float2bfloat16(acc + bvg[h * GD + d] * ps);
-  }
-}
-
-// =============================== backward of the CLS row ===================================
-// GB1: dm[b,h,:] = Wvg[h]^T dout_h, dpsum = bvg[h].dout_h, dbvg += dout_h psum; keeps an fp32 copy
-//      of dout (zero for sequences without a global token); zeroes du and dxcls.  grid (H, B)
-__global__ void __launch_bounds__(256)
-global_bwd_dm_kernel(const __nv_bfloat16* __restrict__ dctx, const uint8_t* __restrict__ mask,
-                     const float* __restrict__ Wvg, const float* __restrict__ bvg, const float* __restrict__ psum,
-                     int L, float* __restrict__ dm, float* __restrict__ dpsum, float* __restrict__ du,
-                     float* __restrict__ dxcls, float* __restrict__ doutf, float* dbvg) {
-  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  __shared__ float dout[GD];
-  const bool on = mask[static_cast<size_t>(b) * L] == 2;
-  if (tid < GD) {
-    const float g = on ? __bfloat162float(dctx[static_cast<size_t>(b) * L * GE + h * GD + tid]) : 0.f;
-    dout[tid] = g;
-    doutf[static_cast<size_t>(b) * GE + h * GD + tid] = g;
-  }
-  for (int e = tid; e < GE; e += 256) du[(static_cast<size_t>(b) * GH + h) * GE + e] = 0.f;
-  if (h == 0) for (int e = tid; e < GE; e += 256) dxcls[static_cast<size_t>(b) * GE + e] = 0.f;
-  __syncthreads();
-  for (int e = tid; e < GE; e += 256) {
-    float acc = 0.f;
-#pragma unroll 16
-    for (int d = 0; d < GD; ++d) acc += __ldg(Wvg + static_cast<size_t>(h * GD + d) * GE + e) * dout[d];
-    dm[(static_cast<size_t>(b) * GH + h) * GE + e] = acc;
-  }
-  if (tid < GD && on && dbvg) red_add_f32(dbvg + h * GD + tid, dout[tid] * psum[b * GH + h]);
   if (tid == 0) {
     float t = 0.f;
-    for (int d = 0; d < GD; ++d) t += bvg[h * GD + d] * dout[d];
-    dpsum[b * GH + h] = t;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    psum[blockIdx.x] = t;
   }
 }
 
-// GB3: ds_j = p_j (dp_j - sum_k p_k dp_k), in place over dp.  grid (B*H), 256 threads
-__global__ void __launch_bounds__(256) global_bwd_ds_kernel(const float* __restrict__ p, float* __restrict__ dp, int L) {
+// ds_j = p_j (dp_j - sum_k p_k dp_k), written transposed: dst[b, j, h].  grid (B*H), 256 threads
+__global__ void __launch_bounds__(256)
+global_bwd_ds_kernel(const float* __restrict__ p, const float* __restrict__ dp, int L, float* __restrict__ dst) {
   const float* pr = p + static_cast<size_t>(blockIdx.x) * L;
-  float* dr = dp + static_cast<size_t>(blockIdx.x) * L;
+  const float* dr = dp + static_cast<size_t>(blockIdx.x) * L;
+  const int b = blockIdx.x / GH, h = blockIdx.x % GH;
   __shared__ float red[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float t = 0.f;
@@ -326,122 +401,161 @@ __global__ void __launch_bounds__(256) global_bwd_ds_kernel(const float* __restr
   t = 0.f;
 #pragma unroll
   for (int w = 0; w < 8; ++w) t += red[w];
-  for (int j = tid; j < L; j += 256) dr[j] = pr[j] * (dr[j] - t);
+  for (int j = tid; j < L; j += 256) dst[(static_cast<size_t>(b) * L + j) * 16 + h] = pr[j] * (dr[j] - t);
 }
 
-// GB4: du[b,h,:] += sum_j ds_hj x_j ;  dx_j += sum_h (p'_hj dm_h + ds_hj u_h).  grid (L/32, B)
-__global__ void __launch_bounds__(256)
-global_bwd_dx_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ p, const float* __restrict__ ds,
-                     const float* __restrict__ dm, const float* __restrict__ u, int L, float drop_scale,
-                     uint32_t drop_thresh, uint64_t drop_seed, float* __restrict__ du, __nv_bfloat16* __restrict__ dx) {
-  const int b = blockIdx.y, j0 = blockIdx.x * TOK;
-  __shared__ float cp[GH][TOK];   // p'
-  __shared__ float cs[GH][TOK];   // ds
-  const int tid = threadIdx.x;
-  load_coefs(p, ds, b, j0, L, drop_scale, drop_thresh, drop_seed, cp, cs);
-  float dmr[GH][4], ur[GH][4], acc[GH][4];
-  const bool second = tid < 128;
-#pragma unroll
-  for (int h = 0; h < GH; ++h) {
-    const float* dmb = dm + (static_cast<size_t>(b) * GH + h) * GE;
-    const float* ub = u + (static_cast<size_t>(b) * GH + h) * GE;
-    const float2 d0 = *reinterpret_cast<const float2*>(dmb + tid * 2), u0 = *reinterpret_cast<const float2*>(ub + tid * 2);
-    dmr[h][0] = d0.x; dmr[h][1] = d0.y; ur[h][0] = u0.x; ur[h][1] = u0.y;
-    if (second) {
-      const float2 d1 = *reinterpret_cast<const float2*>(dmb + 512 + tid * 2);
-      const float2 u1 = *reinterpret_cast<const float2*>(ub + 512 + tid * 2);
-      dmr[h][2] = d1.x; dmr[h][3] = d1.y; ur[h][2] = u1.x; ur[h][3] = u1.y;
-    } else {
-      dmr[h][2] = dmr[h][3] = ur[h][2] = ur[h][3] = 0.f;
-    }
-    acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
+// ---------------------------------------------------------------------------------------------
+// Token walks over 64-column slices, fed by TMA (MIX_ACC: m and du;  MIX_DX: the dx update).  Work item = (sequence, 64-column slice, token
+// block); the persistent CTAs take contiguous runs of items (token block fastest), so a CTA
+// changes (sequence, slice) at most a couple of times and flushes its per-(head, column) partial
+// sums with red.add into the zeroed output.  A producer warp streams, per stage, the x tile
+// [TOK tokens x 64 cols] (3-D tensor map, 128B swizzle), the coefficient rows pt / dst
+// [TOK x 16 fp32] (1-D bulk copies) and, in backward, the dx tile; 8 consumer warps (lane = column
+// pair, warp = token mod 8) do the FMAs from shared memory.
+//   MIX_ACC: out[b,h,c] += sum_j coef[b,j,h] x[b,j,c]      (coef = p' -> m;  coef = ds -> du)
+//   MIX_DX : dx[b,j,c]  += sum_h p'_hj dm[b,h,c] + ds_hj u[b,h,c]     (tile = dx itself, no flush)
+// ---------------------------------------------------------------------------------------------
+enum { MIX_ACC = 0, MIX_DX = 1 };
+
+template <int MODE>
+struct MixCfg {
+  static constexpr bool DX = MODE == MIX_DX;
+  static constexpr int TOK = DX ? 64 : 128;
+  static constexpr int STAGES = 3;
+  static constexpr uint32_t X_BYTES = TOK * 128;
+  static constexpr uint32_t C_BYTES = TOK * 64;
+  // MIX_ACC: x tile + one coefficient block;  MIX_DX: dx tile + two coefficient blocks (p', ds)
+  static constexpr uint32_t STAGE_BYTES = X_BYTES + (DX ? 2 : 1) * C_BYTES;
+  static constexpr uint32_t RED_BYTES = DX ? 0 : 8 * GH * 64 * 4;
+  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + RED_BYTES + 2 * STAGES * 8 + 1024;
+};
+
+struct MixParams {
+  const float* pt;    // [B, L, 16] coefficient rows (MIX_ACC: p' or ds;  MIX_DX: p')
+  const float* dst;   // MIX_DX: [B, L, 16] ds
+  const float* dm;    // MIX_DX: [B, H, E]
+  const float* u;     // MIX_DX: [B, H, E]
+  float* out;         // MIX_ACC: [B, H, E] (zeroed by the caller): m or du
+  __nv_bfloat16* dx;  // MIX_DX
+  int B, L, nblk, items;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(288, 2)
+global_mix_kernel(const __grid_constant__ CUtensorMap tmX, const MixParams p) {
+  using C = MixCfg<MODE>;
+  constexpr bool DX = C::DX;
+  constexpr int TOK = C::TOK, STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* red = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);                 // [8][GH][64] (MIX_ACC)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + C::RED_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int it0 = static_cast<int>(static_cast<long long>(blockIdx.x) * p.items / gridDim.x);
+  const int it1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.items / gridDim.x);
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 8); }
+    fence_mbar_init();
   }
   __syncthreads();
-  const int n = min(TOK, L - j0);
-  for (int jj = 0; jj < n; jj += 4) {
-    uint32_t xr0[4], xr1[4], gr0[4], gr1[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int j = min(jj + t, n - 1);
-      const size_t rowoff = (static_cast<size_t>(b) * L + j0 + j) * GE;
-      const uint32_t* xr = reinterpret_cast<const uint32_t*>(x + rowoff);
-      const uint32_t* dxr = reinterpret_cast<const uint32_t*>(dx + rowoff);
-      xr0[t] = xr[tid]; gr0[t] = dxr[tid];
-      xr1[t] = second ? xr[256 + tid] : 0u;
-      gr1[t] = second ? dxr[256 + tid] : 0u;
-    }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (jj + t < n) {
-        const float2 x0 = unpack_bf16(xr0[t]), x1 = unpack_bf16(xr1[t]);
-        float2 g0 = unpack_bf16(gr0[t]), g1 = unpack_bf16(gr1[t]);
-#pragma unroll
-        for (int h = 0; h < GH; ++h) {
-          const float a = cp[h][jj + t], s = cs[h][jj + t];
-          g0.x += a * dmr[h][0] + s * ur[h][0]; g0.y += a * dmr[h][1] + s * ur[h][1];
-          g1.x += a * dmr[h][2] + s * ur[h][2]; g1.y += a * dmr[h][3] + s * ur[h][3];
-          acc[h][0] += s * x0.x; acc[h][1] += s * x0.y; acc[h][2] += s * x1.x; acc[h][3] += s * x1.y;
-        }
-        uint32_t* dxw = reinterpret_cast<uint32_t*>(dx + (static_cast<size_t>(b) * L + j0 + jj + t) * GE);
-        dxw[tid] = pack_bf16(g0.x, g0.y);
-        if (second) dxw[256 + tid] = pack_bf16(g1.x, g1.y);
+  // stage layout: [x (MIX_ACC) or dx (MIX_DX) tile][coefficient rows 0][coefficient rows 1 (MIX_DX)]
+  constexpr uint32_t OFF_C0 = C::X_BYTES, OFF_C1 = OFF_C0 + C::C_BYTES;
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmX);
+      int stage = 0; uint32_t phase = 0;
+      for (int it = it0; it < it1; ++it) {
+        const int blk = it % p.nblk, slice = (it / p.nblk) % GH, b = it / (p.nblk * GH);
+        const int j0 = blk * TOK;
+        const int nt = min(TOK, p.L - j0);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * C::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], C::X_BYTES + (DX ? 2u : 1u) * static_cast<uint32_t>(nt) * 64);
+        tma_load_3d(st, &tmX, &full_bar[stage], slice * 64, j0, b);
+        bulk_load_1d(st + OFF_C0, p.pt + (static_cast<size_t>(b) * p.L + j0) * 16, nt * 64, &full_bar[stage]);
+        if (DX) bulk_load_1d(st + OFF_C1, p.dst + (static_cast<size_t>(b) * p.L + j0) * 16, nt * 64, &full_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    return;
   }
+  // ---- consumers ----
+  float acc[DX ? 1 : GH][2], dmr[DX ? GH : 1][2], ur[DX ? GH : 1][2];
+  if (!DX) {
 #pragma unroll
-  for (int h = 0; h < GH; ++h) {
-    float* dub = du + (static_cast<size_t>(b) * GH + h) * GE;
-    red_add_f32(dub + tid * 2, acc[h][0]);
-    red_add_f32(dub + tid * 2 + 1, acc[h][1]);
-    if (second) {
-      red_add_f32(dub + 512 + tid * 2, acc[h][2]);
-      red_add_f32(dub + 512 + tid * 2 + 1, acc[h][3]);
-    }
+    for (int h = 0; h < GH; ++h) acc[h][0] = acc[h][1] = 0.f;
   }
-}
-
-// GB5: dq = Wkg[h] du_h / 8 (fp32 copy kept), dbqg += dq, dxcls += Wqg[h]^T dq.  grid (H, B)
-__global__ void __launch_bounds__(256)
-global_bwd_q_kernel(const uint8_t* __restrict__ mask, const float* __restrict__ Wqg, const float* __restrict__ Wkg,
-                    const float* __restrict__ du, int L, float* __restrict__ dqf, float* dbqg,
-                    float* __restrict__ dxcls) {
-  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool on = mask[static_cast<size_t>(b) * L] == 2;
-  __shared__ __align__(16) float dus[GE];
-  __shared__ float dq[GD];
-  const float* dub = du + (static_cast<size_t>(b) * GH + h) * GE;
-  for (int e = tid; e < GE; e += 256) dus[e] = dub[e];
-  __syncthreads();
+  int cur_key = -1;    // b * GH + slice of the partial sums held in acc / of the vectors held in dmr, ur
+  auto flush = [&](int key) {
+    if (DX) return;
+    const int b = key / GH, slice = key % GH;
+#pragma unroll
+    for (int h = 0; h < (DX ? 1 : GH); ++h) {
+      *reinterpret_cast<float2*>(&red[(warp * GH + h) * 64 + lane * 2]) = make_float2(acc[h][0], acc[h][1]);
+      acc[h][0] = acc[h][1] = 0.f;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int i = tid; i < GH * 64; i += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w * GH * 64 + i];
+      red_add_f32(p.out + (static_cast<size_t>(b) * GH + i / 64) * GE + slice * 64 + (i & 63), t);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+  };
+  int stage = 0; uint32_t phase = 0;
+  for (int it = it0; it < it1; ++it) {
+    const int blk = it % p.nblk, slice = (it / p.nblk) % GH, b = it / (p.nblk * GH);
+    const int key = b * GH + slice;
+    if (key != cur_key) {
+      if (cur_key >= 0) flush(cur_key);
+      cur_key = key;
+      if (DX) {
+#pragma unroll
+        for (int h = 0; h < GH; ++h) {
+          const size_t o = (static_cast<size_t>(b) * GH + h) * GE + slice * 64 + lane * 2;
+          const float2 d = *reinterpret_cast<const float2*>(p.dm + o), w = *reinterpret_cast<const float2*>(p.u + o);
+          dmr[h][0] = d.x; dmr[h][1] = d.y; ur[h][0] = w.x; ur[h][1] = w.y;
+        }
+      }
+    }
+    const int j0 = blk * TOK;
+    const int nt = min(TOK, p.L - j0);
+    mbar_wait(&full_bar[stage], phase);
+    const uint8_t* st = smem + stage * C::STAGE_BYTES;
 #pragma unroll 2
-  for (int d = warp; d < GD; d += 8) {
-    const float acc = warp_dot768(Wkg + static_cast<size_t>(h * GD + d) * GE, dus, lane);
-    if (lane == 0) {
-      const float g = on ? acc * 0.125f : 0.f;   // gradient w.r.t. (Wqg x + bqg)
-      dq[d] = g;
-      dqf[static_cast<size_t>(b) * GE + h * GD + d] = g;
-      if (on && dbqg) red_add_f32(dbqg + h * GD + d, g);
+    for (int t = warp; t < nt; t += 8) {
+      const uint32_t xo = t * 128 + ((((lane >> 2) ^ (t & 7))) << 4) + (lane & 3) * 4;
+      float2 xv = unpack_bf16(*reinterpret_cast<const uint32_t*>(st + xo));      // x (MIX_ACC) or dx (MIX_DX)
+      float pv[GH], sv[DX ? GH : 1];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 a = *reinterpret_cast<const float4*>(st + OFF_C0 + t * 64 + q * 16);
+        pv[q * 4] = a.x; pv[q * 4 + 1] = a.y; pv[q * 4 + 2] = a.z; pv[q * 4 + 3] = a.w;
+        if (DX) {
+          const float4 c = *reinterpret_cast<const float4*>(st + OFF_C1 + t * 64 + q * 16);
+          sv[q * 4] = c.x; sv[q * 4 + 1] = c.y; sv[q * 4 + 2] = c.z; sv[q * 4 + 3] = c.w;
+        }
+      }
+      if (!DX) {
+#pragma unroll
+        for (int h = 0; h < GH; ++h) { acc[DX ? 0 : h][0] += pv[h] * xv.x; acc[DX ? 0 : h][1] += pv[h] * xv.y; }
+      } else {
+#pragma unroll
+        for (int h = 0; h < GH; ++h) {
+          xv.x += pv[h] * dmr[DX ? h : 0][0] + sv[DX ? h : 0] * ur[DX ? h : 0][0];
+          xv.y += pv[h] * dmr[DX ? h : 0][1] + sv[DX ? h : 0] * ur[DX ? h : 0][1];
+        }
+        *reinterpret_cast<uint32_t*>(p.dx + (static_cast<size_t>(b) * p.L + j0 + t) * GE + slice * 64 + lane * 2) =
+            pack_bf16(xv.x, xv.y);
+      }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    if (++stage == STAGES) { stage = 0; phase ^= 1; }
   }
-  __syncthreads();
-  if (!on) return;
-  for (int e = tid; e < GE; e += 256) {
-    float acc = 0.f;
-#pragma unroll 16
-    for (int d = 0; d < GD; ++d) acc += __ldg(Wqg + static_cast<size_t>(h * GD + d) * GE + e) * dq[d];
-    red_add_f32(dxcls + static_cast<size_t>(b) * GE + e, acc);
-  }
-}
-
-// GB6: dx[b,0,:] += dxcls[b,:].  grid (B), 256 threads
-__global__ void __launch_bounds__(256)
-global_bwd_cls_kernel(const float* __restrict__ dxcls, const uint8_t* __restrict__ mask, int L,
-                      __nv_bfloat16* __restrict__ dx) {
-  const int b = blockIdx.x;
-  if (mask[static_cast<size_t>(b) * L] != 2) return;
-  for (int e = threadIdx.x; e < GE; e += 256) {
-    __nv_bfloat16* d = dx + static_cast<size_t>(b) * L * GE + e;
-    *d = __float2bfloat16(__bfloat162float(*d) + dxcls[static_cast<size_t>(b) * GE + e]);
-  }
+  if (cur_key >= 0) flush(cur_key);
 }
 
 // GBW: batch-reduced outer products into the *_global weight gradients, no atomics:
@@ -470,14 +584,20 @@ global_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restri
       as[bb][d] = on ? A[static_cast<size_t>(b0 + bb) * GE + h * GD + d] : 0.f;
     }
     __syncthreads();
-    for (int bb = 0; bb < nb; ++bb) {
-      const int b = b0 + bb;
-      float v;
-      if (z == 0) v = mvec[(static_cast<size_t>(b) * GH + h) * GE + e];
-      else if (z == 1) v = du[(static_cast<size_t>(b) * GH + h) * GE + e];
-      else v = __bfloat162float(x[static_cast<size_t>(b) * L * GE + e]);
+    float v[16];
 #pragma unroll
-      for (int d = 0; d < GD; ++d) acc[d] += as[bb][d] * v;
+    for (int bb = 0; bb < 16; ++bb) {
+      const int b = min(b0 + bb, B - 1);
+      if (z == 0) v[bb] = mvec[(static_cast<size_t>(b) * GH + h) * GE + e];
+      else if (z == 1) v[bb] = du[(static_cast<size_t>(b) * GH + h) * GE + e];
+      else v[bb] = __bfloat162float(x[static_cast<size_t>(b) * L * GE + e]);
+    }
+#pragma unroll
+    for (int bb = 0; bb < 16; ++bb) {
+      if (bb < nb) {
+#pragma unroll
+        for (int d = 0; d < GD; ++d) acc[d] += as[bb][d] * v[bb];
+      }
     }
   }
 #pragma unroll
@@ -488,91 +608,157 @@ global_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restri
 
 using namespace rf;
 
-extern "C" int rf_global_attn_fwd(const rf_global_args* a, void* ctx, float* qg, float* u, float* p, float* mvec,
-                                  float* psum, rf_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  RF_REQUIRE(a && ctx && qg && u && p && mvec && psum, "rf_global_attn_fwd: null argument");
-  RF_REQUIRE(a->H == GH && a->D == GD, "rf_global_attn_fwd: only H=12, D=64 supported (got %d, %d)", a->H, a->D);
-  RF_REQUIRE(a->B > 0 && a->L > 0, "rf_global_attn_fwd: bad shape");
-  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a->x);
-  const int chunks = (a->L + TOK - 1) / TOK;
+template <int MODE>
+static int launch_mix(const __nv_bfloat16* tile_src, MixParams& p, cudaStream_t stream, const char* what) {
+  using C = MixCfg<MODE>;
+  auto kern = global_mix_kernel<MODE>;
   static bool attr_set = false;
   if (!attr_set) {
-    RF_CUDA(cudaFuncSetAttribute(global_dots_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GH * GE * 4));
-    RF_CUDA(cudaFuncSetAttribute(global_dots_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GH * GE * 4));
+    RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr_set = true;
   }
+  const uint64_t B = p.B, L = p.L;
+  const CUtensorMap* tmx = get_tmap_3d(tile_src, B, L, GE, GE, L * GE, C::TOK);
+  if (!tmx) return RF_ERR_CUDA;
+  p.nblk = (p.L + C::TOK - 1) / C::TOK;
+  p.items = p.B * GH * p.nblk;
+  const int grid = p.items < 2 * sm_count() ? p.items : 2 * sm_count();
+  kern<<<grid, 288, C::SMEM, stream>>>(*tmx, p);
+  return check_launch(what);
+}
+
+extern "C" int rf_global_attn_fwd(const rf_global_args* a, void* ctx, float* qg, float* u, float* p, float* pt,
+                                  float* mvec, float* psum, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(a && ctx && qg && u && p && pt && mvec && psum, "rf_global_attn_fwd: null argument");
+  RF_REQUIRE(a->H == GH && a->D == GD, "rf_global_attn_fwd: only H=12, D=64 supported (got %d, %d)", a->H, a->D);
+  RF_REQUIRE(a->B > 0 && a->L > 0, "rf_global_attn_fwd: bad shape");
+  RF_REQUIRE((reinterpret_cast<uintptr_t>(pt) & 15) == 0, "rf_global_attn_fwd: pt must be 16-byte aligned");
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a->x);
+  const int B = a->B, L = a->L;
+  const int bblocks = (B + GBB - 1) / GBB;
   const uint32_t thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   const float scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
-  global_qu_kernel<<<dim3(GH, a->B), 256, 0, stream>>>(x, a->Wqg, a->bqg, a->Wkg, a->L, qg, u, mvec, psum);
-  int rc = check_launch("rf_global_attn_fwd/qu");
-  if (rc) return rc;
-  global_dots_kernel<0><<<dim3(chunks, a->B), 256, GH * GE * 4, stream>>>(x, a->mask012, u, nullptr, a->L, scale,
-                                                                        thresh, a->drop_seed, p);
-  rc = check_launch("rf_global_attn_fwd/scores");
-  if (rc) return rc;
-  global_softmax_kernel<<<a->B * GH, 256, 0, stream>>>(p, a->L);
-  rc = check_launch("rf_global_attn_fwd/softmax");
-  if (rc) return rc;
-  global_mix_kernel<<<dim3(chunks, a->B), 256, 0, stream>>>(x, p, a->L, scale, thresh, a->drop_seed, mvec, psum);
-  rc = check_launch("rf_global_attn_fwd/mix");
-  if (rc) return rc;
-  global_out_kernel<<<dim3(GH, a->B), 256, 0, stream>>>(mvec, psum, a->Wvg, a->bvg, a->mask012, a->L,
-                                                       reinterpret_cast<__nv_bfloat16*>(ctx));
+  int rc;
+  RF_CUDA(cudaMemsetAsync(mvec, 0, static_cast<size_t>(B) * GH * GE * sizeof(float), stream));
+  {
+    RowdotParams r{};
+    r.W = a->Wqg; r.bias = a->bqg; r.x = x; r.mask = a->mask012; r.out_f32 = qg; r.B = B; r.L = L;
+    global_rowdot_kernel<MODE_Q><<<dim3(GE / 8, bblocks), 256, 0, stream>>>(r);
+    if ((rc = check_launch("rf_global_attn_fwd/q"))) return rc;
+  }
+  {
+    ColmixParams c{};
+    c.W = a->Wkg; c.A = qg; c.mask = a->mask012; c.out = u; c.B = B; c.L = L;
+    global_colmix_kernel<<<dim3(GE / 64, GH, bblocks), 64, 0, stream>>>(c);
+    if ((rc = check_launch("rf_global_attn_fwd/u"))) return rc;
+  }
+  global_dots_kernel<0><<<dim3((L + 63) / 64, B), 256, 0, stream>>>(x, a->mask012, u, nullptr, L, scale, thresh,
+                                                                   a->drop_seed, p);
+  if ((rc = check_launch("rf_global_attn_fwd/scores"))) return rc;
+  global_softmax_kernel<<<B * GH, 256, 0, stream>>>(p, L, scale, thresh, a->drop_seed, pt, psum);
+  if ((rc = check_launch("rf_global_attn_fwd/softmax"))) return rc;
+  {
+    MixParams m{};
+    m.pt = pt; m.out = mvec; m.B = B; m.L = L;
+    if ((rc = launch_mix<MIX_ACC>(x, m, stream, "rf_global_attn_fwd/mix"))) return rc;
+  }
+  {
+    RowdotParams r{};
+    r.W = a->Wvg; r.bias = a->bvg; r.V = mvec; r.psum = psum; r.mask = a->mask012;
+    r.ctx = reinterpret_cast<__nv_bfloat16*>(ctx); r.B = B; r.L = L;
+    global_rowdot_kernel<MODE_OUT><<<dim3(GE / 8, bblocks), 256, 0, stream>>>(r);
+  }
   return check_launch("rf_global_attn_fwd/out");
 }
 
 extern "C" long long rf_global_attn_bwd_ws_bytes(int B, int L, int H) {
   const long long E = static_cast<long long>(H) * GD;
-  return 4ll * (2ll * B * H * E + B * H + static_cast<long long>(B) * H * L + 3ll * B * E) + 256;
+  return 4ll * (2ll * B * H * E + B * H + static_cast<long long>(B) * H * L + 2ll * B * E + 16ll * B * L) + 256;
+}
+
+namespace {
+struct BwdWs {
+  float *dm, *du, *dst, *dp, *dpsum, *doutf, *dqf;
+  BwdWs(float* ws, int B, int L) {
+    dm = ws;
+    du = dm + static_cast<size_t>(B) * GH * GE;
+    dst = du + static_cast<size_t>(B) * GH * GE;          // [B, L, 16] (64-byte rows: bulk-copy source)
+    dp = dst + static_cast<size_t>(B) * L * 16;
+    dpsum = dp + static_cast<size_t>(B) * GH * L;
+    doutf = dpsum + static_cast<size_t>(B) * GH;
+    dqf = doutf + static_cast<size_t>(B) * GE;
+  }
+};
+}  // namespace
+
+// Part B of the backward: the gradient the CLS row sends to every token, added into dx; needs the
+// workspace left by rf_global_attn_bwd (dm, ds, dq).  Separate so that part A can run on a side
+// stream while dx is still being produced by the QKV dgrad GEMM.
+extern "C" int rf_global_attn_bwd_dx(const rf_global_args* a, const float* u, const float* pt, void* dx,
+                                     const float* ws, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(a && u && pt && dx && ws, "rf_global_attn_bwd_dx: null argument");
+  RF_REQUIRE(a->H == GH && a->D == GD, "rf_global_attn_bwd_dx: only H=12, D=64 supported (got %d, %d)", a->H, a->D);
+  const int B = a->B, L = a->L;
+  const BwdWs w(const_cast<float*>(ws), B, L);
+  int rc;
+  {
+    MixParams m{};
+    m.pt = pt; m.dst = w.dst; m.dm = w.dm; m.u = u; m.dx = reinterpret_cast<__nv_bfloat16*>(dx); m.B = B; m.L = L;
+    if ((rc = launch_mix<MIX_DX>(m.dx, m, stream, "rf_global_attn_bwd_dx/dx"))) return rc;
+  }
+  global_dxcls_kernel<<<dim3(GE / 64, (B + GBB - 1) / GBB), 768, 0, stream>>>(a->Wqg, w.dqf, a->mask012, B, L,
+                                                                             reinterpret_cast<__nv_bfloat16*>(dx));
+  return check_launch("rf_global_attn_bwd_dx/dxcls");
 }
 
 extern "C" int rf_global_attn_bwd(const rf_global_args* a, const void* dctx, const float* qg, const float* u,
-                                  const float* p, const float* mvec, const float* psum, void* dx, float* dWqg,
-                                  float* dbqg, float* dWkg, float* dWvg, float* dbvg, float* ws, rf_stream_t stream_) {
+                                  const float* p, const float* pt, const float* mvec, const float* psum, void* dx,
+                                  float* dWqg, float* dbqg, float* dWkg, float* dWvg, float* dbvg, float* ws,
+                                  rf_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  RF_REQUIRE(a && dctx && qg && u && p && mvec && psum && dx && ws, "rf_global_attn_bwd: null argument");
+  RF_REQUIRE(a && dctx && qg && u && p && pt && mvec && psum && ws, "rf_global_attn_bwd: null argument");
   RF_REQUIRE(a->H == GH && a->D == GD, "rf_global_attn_bwd: only H=12, D=64 supported (got %d, %d)", a->H, a->D);
   const int B = a->B, L = a->L;
+  const int bblocks = (B + GBB - 1) / GBB;
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a->x);
-  float* dm = ws;
-  float* du = dm + static_cast<size_t>(B) * GH * GE;
-  float* dpsum = du + static_cast<size_t>(B) * GH * GE;
-  float* dp = dpsum + static_cast<size_t>(B) * GH;
-  float* dxcls = dp + static_cast<size_t>(B) * GH * L;
-  float* doutf = dxcls + static_cast<size_t>(B) * GE;
-  float* dqf = doutf + static_cast<size_t>(B) * GE;
-  const int chunks = (L + TOK - 1) / TOK;
+  const BwdWs w(ws, B, L);
+  RF_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0 && (reinterpret_cast<uintptr_t>(pt) & 15) == 0,
+             "rf_global_attn_bwd: ws and pt must be 16-byte aligned");
   const uint32_t thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   const float scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RF_CUDA(cudaFuncSetAttribute(global_dots_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GH * GE * 4));
-    RF_CUDA(cudaFuncSetAttribute(global_dots_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GH * GE * 4));
-    attr_set = true;
+  int rc;
+  RF_CUDA(cudaMemsetAsync(w.du, 0, static_cast<size_t>(B) * GH * GE * sizeof(float), stream));
+  {
+    // dm[b,h,:] = Wvg[h]^T dout_h; dpsum = bvg[h].dout_h; dbvg += dout_h psum; fp32 copy of dout
+    ColmixParams c{};
+    c.W = a->Wvg; c.A = nullptr; c.dctx = reinterpret_cast<const __nv_bfloat16*>(dctx); c.mask = a->mask012; c.out = w.dm;
+    c.bvg = a->bvg; c.psum = psum; c.dpsum = w.dpsum; c.dbvg = dbvg; c.doutf = w.doutf; c.B = B; c.L = L;
+    global_colmix_kernel<<<dim3(GE / 64, GH, bblocks), 64, 0, stream>>>(c);
+    if ((rc = check_launch("rf_global_attn_bwd/dm"))) return rc;
   }
-  global_bwd_dm_kernel<<<dim3(GH, B), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dctx), a->mask012,
-                                                       a->Wvg, a->bvg, psum, L, dm, dpsum, du, dxcls, doutf, dbvg);
-  int rc = check_launch("rf_global_attn_bwd/dm");
-  if (rc) return rc;
-  global_dots_kernel<1><<<dim3(chunks, B), 256, GH * GE * 4, stream>>>(x, a->mask012, dm, dpsum, L, scale, thresh,
-                                                                     a->drop_seed, dp);
-  rc = check_launch("rf_global_attn_bwd/dp");
-  if (rc) return rc;
-  global_bwd_ds_kernel<<<B * GH, 256, 0, stream>>>(p, dp, L);
-  rc = check_launch("rf_global_attn_bwd/ds");
-  if (rc) return rc;
-  global_bwd_dx_kernel<<<dim3(chunks, B), 256, 0, stream>>>(x, p, dp, dm, u, L, scale, thresh, a->drop_seed, du,
-                                                           reinterpret_cast<__nv_bfloat16*>(dx));
-  rc = check_launch("rf_global_attn_bwd/dx");
-  if (rc) return rc;
-  global_bwd_q_kernel<<<dim3(GH, B), 256, 0, stream>>>(a->mask012, a->Wqg, a->Wkg, du, L, dqf, dbqg, dxcls);
-  rc = check_launch("rf_global_attn_bwd/q");
-  if (rc) return rc;
-  global_bwd_cls_kernel<<<B, 256, 0, stream>>>(dxcls, a->mask012, L, reinterpret_cast<__nv_bfloat16*>(dx));
-  rc = check_launch("rf_global_attn_bwd/cls");
-  if (rc) return rc;
-  global_wgrad_kernel<<<dim3(GH, 3, 3), 256, 0, stream>>>(x, a->mask012, B, L, doutf, mvec, qg, du, dqf, dWvg, dWkg,
-                                                         dWqg);
-  return check_launch("rf_global_attn_bwd/wgrad");
+  global_dots_kernel<1><<<dim3((L + 63) / 64, B), 256, 0, stream>>>(x, a->mask012, w.dm, w.dpsum, L, scale, thresh,
+                                                                   a->drop_seed, w.dp);
+  if ((rc = check_launch("rf_global_attn_bwd/dp"))) return rc;
+  global_bwd_ds_kernel<<<B * GH, 256, 0, stream>>>(p, w.dp, L, w.dst);
+  if ((rc = check_launch("rf_global_attn_bwd/ds"))) return rc;
+  {
+    // du[b,h,:] = sum_j ds_hj x_j
+    MixParams m{};
+    m.pt = w.dst; m.out = w.du; m.B = B; m.L = L;
+    if ((rc = launch_mix<MIX_ACC>(x, m, stream, "rf_global_attn_bwd/du"))) return rc;
+  }
+  {
+    // dq = Wkg[h] du_h / 8 (fp32 copy kept), dbqg += dq
+    RowdotParams r{};
+    r.W = a->Wkg; r.V = w.du; r.mask = a->mask012; r.out_f32 = w.dqf; r.dbias = dbqg; r.B = B; r.L = L;
+    global_rowdot_kernel<MODE_DQ><<<dim3(GE / 8, bblocks), 256, 0, stream>>>(r);
+    if ((rc = check_launch("rf_global_attn_bwd/dq"))) return rc;
+  }
+  global_wgrad_kernel<<<dim3(GH, 3, 3), 256, 0, stream>>>(x, a->mask012, B, L, w.doutf, mvec, qg, w.du, w.dqf, dWvg,
+                                                         dWkg, dWqg);
+  if ((rc = check_launch("rf_global_attn_bwd/wgrad"))) return rc;
+  if (dx != nullptr) return rf_global_attn_bwd_dx(a, u, pt, dx, ws, stream_);
+  return RF_OK;
 }

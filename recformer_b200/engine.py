@@ -197,7 +197,8 @@ class SavedActivations:
         self.pre2 = [torch.empty(T, E, **f32) for _ in range(n)]
         self.stats2 = [torch.empty(T, 2, **f32) for _ in range(n)]
         self.glob = [{"qg": torch.empty(B, E, **f32), "u": torch.empty(B, H, E, **f32),
-                      "p": torch.empty(B, H, Lp, **f32), "mvec": torch.empty(B, H, E, **f32),
+                      "p": torch.empty(B, H, Lp, **f32), "pt": torch.empty(B, Lp, 16, **f32),
+                      "mvec": torch.empty(B, H, E, **f32),
                       "psum": torch.empty(B, H, **f32)} for _ in range(n)]
         self.pos_ids = None
         self.mask012 = None
@@ -229,7 +230,7 @@ class BackwardScratch:
         self.dqkv = torch.empty(T, 3 * E, **bf)
         self.dx = [torch.empty(T, E, **bf) for _ in range(2)]
         self.dkv = torch.empty(T, 2 * E, dtype=torch.float32, device=device)
-        self.gws = None
+        self.gws = ops.global_attn_bwd_ws(B, Lp, H, device)
 
 
 class EncoderEngine:
@@ -241,6 +242,11 @@ class EncoderEngine:
         self._bwd: Dict[tuple, BackwardScratch] = {}
         self._err = None
         self._call = 0
+        # The global (CLS) row only depends on the layer input (forward) / on dctx (backward) and is made
+        # of small latency-bound kernels: it runs on a side stream next to the QKV GEMM + band attention.
+        self._side: Dict[str, torch.cuda.Stream] = {}
+        self._events: Dict[tuple, torch.cuda.Event] = {}
+        self.overlap_global = True
 
     # -- helpers -------------------------------------------------------------------------------
     def _acquire(self, B, Lp, device, per_layer) -> SavedActivations:
@@ -253,6 +259,19 @@ class EncoderEngine:
         pool = self._free.setdefault(key, [])
         if len(pool) < 4:
             pool.append(sv)
+
+    def side_stream(self, device) -> torch.cuda.Stream:
+        key = str(device)
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(device=device)
+        return self._side[key]
+
+    def event(self, device, name: str, layer: int) -> torch.cuda.Event:
+        key = (str(device), name, layer)
+        ev = self._events.get(key)
+        if ev is None:
+            ev = self._events[key] = torch.cuda.Event()
+        return ev
 
     def err_flag(self, device) -> torch.Tensor:
         if self._err is None or self._err.device != torch.device(device):
@@ -352,11 +371,25 @@ class EncoderEngine:
             k = sv.idx(i)
             x = sv.xin(i)
             w_one = (aw if isinstance(aw, int) else aw[i]) // 2
+            if self.overlap_global:
+                # global row (writes ctx row 0 of every sequence) on the side stream, concurrently with the
+                # QKV projection + band attention (which never touch that row when position 0 is global)
+                main, side = torch.cuda.current_stream(device), self.side_stream(device)
+                ev_x, ev_g = self.event(device, "x", i), self.event(device, "g", i)
+                ev_x.record(main)
+                side.wait_event(ev_x)
+                with torch.cuda.stream(side):
+                    ops.global_attn_fwd(x, mask, W["Wqg"], W["bqg"], W["Wkg"], W["Wvg"], W["bvg"], B, Lp, H, sv.ctx[k],
+                                        saved=sv.glob[k], drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 2))
+                    ev_g.record(side)
             ops.gemm(x, W["Wqkv"], out=sv.qkv[k], bias=W["bqkv"], scale=0.125, scale_ncols=E)
             ops.band_attn_fwd(sv.qkv[k], mask, B, Lp, H, w_one, ctx=sv.ctx[k], lse=sv.lse[k], drop_p=sv.drop_attn,
                               drop_seed=self._seed(sv, i, 1))
-            ops.global_attn_fwd(x, mask, W["Wqg"], W["bqg"], W["Wkg"], W["Wvg"], W["bvg"], B, Lp, H, sv.ctx[k],
-                                saved=sv.glob[k], drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 2))
+            if self.overlap_global:
+                main.wait_event(ev_g)
+            else:
+                ops.global_attn_fwd(x, mask, W["Wqg"], W["bqg"], W["Wkg"], W["Wvg"], W["bvg"], B, Lp, H, sv.ctx[k],
+                                    saved=sv.glob[k], drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 2))
             ops.gemm(sv.ctx[k], W["Wo"], out=sv.pre1[k], bias=W["bo"], residual=sv.x32[i % 2],
                      drop_p=sv.drop_hidden, drop_seed=self._seed(sv, i, 3))
             ops.layernorm_fwd(sv.pre1[k], W["ln1w"], W["ln1b"], cfg.layer_norm_eps, out=sv.h1[k], out32=sv.h1_32,
@@ -416,6 +449,18 @@ class EncoderEngine:
             ops.gemm(dY, sv.ctx[i], out=G["Wo"], a_mn_major=True, b_mn_major=True, accumulate=True,
                      split_k=_pick_split(E, E, T))
             ops.gemm(dY, W["Wo"], out=sc.dctx, b_mn_major=True)
+            gargs = (x, mask, W["Wqg"], W["bqg"], W["Wkg"], W["Wvg"], W["bvg"], B, Lp, H)
+            if self.overlap_global:
+                # weight-gradient half of the global row's backward (needs dctx, not dx) on the side stream,
+                # concurrently with the band-attention backward and the QKV wgrad / dgrad GEMMs
+                main, side = torch.cuda.current_stream(device), self.side_stream(device)
+                ev_d, ev_a = self.event(device, "dctx", i), self.event(device, "gA", i)
+                ev_d.record(main)
+                side.wait_event(ev_d)
+                with torch.cuda.stream(side):
+                    ops.global_attn_bwd(*gargs, sc.dctx, sv.glob[i], None, G["Wqg"], G["bqg"], G["Wkg"], G["Wvg"],
+                                        G["bvg"], ws=sc.gws, drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 2))
+                    ev_a.record(side)
             ops.band_attn_bwd(sv.qkv[i], mask, B, Lp, H, w_one, sv.ctx[i], sv.lse[i], sc.dctx, sc.dqkv, sc.dkv,
                               drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 1))
             ops.colsum(sc.dqkv, G["bqkv"])
@@ -423,9 +468,13 @@ class EncoderEngine:
                      split_k=_pick_split(3 * E, E, T))
             dx = sc.dx[i % 2]
             ops.gemm(sc.dqkv, W["Wqkv"], out=dx, b_mn_major=True, residual=sc.d_pre)
-            sc.gws = ops.global_attn_bwd(x, mask, W["Wqg"], W["bqg"], W["Wkg"], W["Wvg"], W["bvg"], B, Lp, H, sc.dctx,
-                                         sv.glob[i], dx, G["Wqg"], G["bqg"], G["Wkg"], G["Wvg"], G["bvg"], ws=sc.gws,
-                                         drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 2))
+            if self.overlap_global:
+                main.wait_event(ev_a)
+                ops.global_attn_bwd_dx(*gargs, sv.glob[i], dx, sc.gws, drop_p=sv.drop_attn,
+                                       drop_seed=self._seed(sv, i, 2))
+            else:
+                ops.global_attn_bwd(*gargs, sc.dctx, sv.glob[i], dx, G["Wqg"], G["bqg"], G["Wkg"], G["Wvg"], G["bvg"],
+                                    ws=sc.gws, drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 2))
             d_out = dx
         e = "embeddings."
         named = P._named

@@ -193,12 +193,13 @@ def global_attn_fwd(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, ctx, saved=Non
         saved = {"qg": torch.empty(B, E, dtype=torch.float32, device=dev),
                  "u": torch.empty(B, H, E, dtype=torch.float32, device=dev),
                  "p": torch.empty(B, H, L, dtype=torch.float32, device=dev),
+                 "pt": torch.empty(B, L, 16, dtype=torch.float32, device=dev),
                  "mvec": torch.empty(B, H, E, dtype=torch.float32, device=dev),
                  "psum": torch.empty(B, H, dtype=torch.float32, device=dev)}
     a = _global_args(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, drop_p, drop_seed)
     check(_lib.lib().rf_global_attn_fwd(C.byref(a), ctx.data_ptr(), saved["qg"].data_ptr(), saved["u"].data_ptr(),
-                                        saved["p"].data_ptr(), saved["mvec"].data_ptr(), saved["psum"].data_ptr(),
-                                        _stream()), "rf_global_attn_fwd")
+                                        saved["p"].data_ptr(), saved["pt"].data_ptr(), saved["mvec"].data_ptr(),
+                                        saved["psum"].data_ptr(), _stream()), "rf_global_attn_fwd")
     return saved
 
 
@@ -288,15 +289,28 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, shadow, lr, beta1, beta2, eps, 
                                    _stream()), "rf_adamw_step")
 
 
+def global_attn_bwd_ws(B, L, H, device):
+    nbytes = int(_lib.lib().rf_global_attn_bwd_ws_bytes(B, L, H))
+    return torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+
+
 def global_attn_bwd(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, dctx, saved, dx, dWqg, dbqg, dWkg, dWvg, dbvg,
                     ws=None, drop_p=0.0, drop_seed=0):
-    """Adds the CLS row's dense gradient into dx (bf16 [B*L,E]) and accumulates the *_global weight grads."""
+    """Accumulates the *_global weight grads and, if dx is given, adds the CLS row's dense gradient into dx
+    (bf16 [B*L,E]).  With dx=None call global_attn_bwd_dx afterwards (same ws)."""
     nbytes = int(_lib.lib().rf_global_attn_bwd_ws_bytes(B, L, H))
     if ws is None or ws.numel() * ws.element_size() < nbytes:
-        ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=x.device)
+        ws = global_attn_bwd_ws(B, L, H, x.device)
     a = _global_args(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, drop_p, drop_seed)
     check(_lib.lib().rf_global_attn_bwd(C.byref(a), dctx.data_ptr(), saved["qg"].data_ptr(), saved["u"].data_ptr(),
-                                        saved["p"].data_ptr(), saved["mvec"].data_ptr(), saved["psum"].data_ptr(),
-                                        dx.data_ptr(), _ptr(dWqg), _ptr(dbqg), _ptr(dWkg), _ptr(dWvg), _ptr(dbvg),
-                                        ws.data_ptr(), _stream()), "rf_global_attn_bwd")
+                                        saved["p"].data_ptr(), saved["pt"].data_ptr(), saved["mvec"].data_ptr(),
+                                        saved["psum"].data_ptr(), _ptr(dx), _ptr(dWqg), _ptr(dbqg), _ptr(dWkg),
+                                        _ptr(dWvg), _ptr(dbvg), ws.data_ptr(), _stream()), "rf_global_attn_bwd")
     return ws
+
+
+def global_attn_bwd_dx(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, saved, dx, ws, drop_p=0.0, drop_seed=0):
+    """Second half of global_attn_bwd(dx=None): adds the token gradients into dx from the workspace."""
+    a = _global_args(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, drop_p, drop_seed)
+    check(_lib.lib().rf_global_attn_bwd_dx(C.byref(a), saved["u"].data_ptr(), saved["pt"].data_ptr(), dx.data_ptr(),
+                                           ws.data_ptr(), _stream()), "rf_global_attn_bwd_dx")

@@ -234,15 +234,16 @@ def test_band_attention_no_global():
     assert (ctx.view(B, L, -1).float() - ref_ctx).abs().max() < 2e-2
 
 
-def test_global_attention_fwd():
-    B, L, H = 3, 320, 12
+@pytest.mark.parametrize("B,L", [(3, 320), (18, 192)])
+def test_global_attention_fwd(B, L):
+    H = 12
     E = H * 64
     x = rnd(B * L, E, seed=1)
     Wq, Wk, Wv = (rnd(E, E, seed=s, scale=0.03, dtype=torch.float32) for s in (2, 3, 4))
     bq, bk, bv = (rnd(E, seed=s, scale=0.1, dtype=torch.float32) for s in (5, 6, 7))
     mask = torch.ones(B, L, dtype=torch.uint8, device=DEV)
     mask[:, 0] = 2
-    mask[1, 250:] = 0
+    mask[1, L - 70:] = 0
     mask[2, 100:] = 0
     ctx = torch.zeros(B * L, E, dtype=torch.bfloat16, device=DEV)
     saved = ops.global_attn_fwd(x, mask, Wq, bq, Wk, Wv, bv, B, L, H, ctx)
@@ -375,15 +376,16 @@ def test_band_attention_bwd(B, L, ragged):
         assert err < 2e-2, (name, err)
 
 
-def test_global_attention_bwd():
-    B, L, H = 3, 320, 12
+@pytest.mark.parametrize("B,L", [(3, 320), (18, 192)])
+def test_global_attention_bwd(B, L):
+    H = 12
     E = H * 64
     x = rnd(B * L, E, seed=1)
     Wq, Wk, Wv = (rnd(E, E, seed=s, scale=0.03, dtype=torch.float32) for s in (2, 3, 4))
     bq, bk, bv = (rnd(E, seed=s, scale=0.1, dtype=torch.float32) for s in (5, 6, 7))
     mask = torch.ones(B, L, dtype=torch.uint8, device=DEV)
     mask[:, 0] = 2
-    mask[1, 250:] = 0
+    mask[1, L - 70:] = 0
     mask[2, 100:] = 0
     ctx = torch.zeros(B * L, E, dtype=torch.bfloat16, device=DEV)
     saved = ops.global_attn_fwd(x, mask, Wq, bq, Wk, Wv, bv, B, L, H, ctx)
