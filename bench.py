@@ -167,14 +167,21 @@ def make_batches(n, device, rank):
     return host, dev
 
 
+_SYNC = {}
+
+
 def train_step(model, opt, batch, world):
-    from recformer_b200 import dist as rdist
+    """One data-parallel finetune step: fwd + CE + bwd (gradient all-reduce overlapped with the backward,
+    per layer) + fused AdamW on the averaged gradients."""
     loss = model(**batch)
     opt.zero_grad()
+    if world > 1 and id(model) not in _SYNC:
+        from recformer_b200 import dist as rdist
+        _SYNC[id(model)] = rdist.GradSync(model)
     loss.backward()
     if world > 1:
-        rdist.allreduce_gradients(model)
-    opt.step()
+        _SYNC[id(model)].finish()
+    opt.step(grad_scale=1.0 / world)
     return loss
 
 

@@ -81,3 +81,62 @@ def allreduce_gradients(model, group=None, average: bool = True) -> None:
     dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
     if average:
         g.mul_(1.0 / world)
+
+
+class GradSync:
+    """Data-parallel gradient all-reduce overlapped with the backward pass.
+
+    The engine calls `on_layer(i)` as soon as layer i's backward has been enqueued; the layer's two
+    contiguous gradient ranges in the flat fp32 buffer (the six dense weights, the three *_global weights)
+    are all-reduced asynchronously — NCCL orders the collective after the kernels already enqueued on the
+    current stream and runs it on its own stream, next to the remaining backward kernels.  `finish()`
+    reduces what is left (embedding tables, biases, LayerNorm vectors), and makes the current stream wait
+    for every collective.  Gradients are SUMMED; pass `grad_scale=1/world` to `FusedAdamW.step()`.
+    """
+
+    def __init__(self, model, group=None):
+        enc = getattr(model, "longformer", model)
+        self.engine = enc._engine
+        self.group = group
+        self._works = []
+        self._covered = []
+        self.engine.grad_hook = self.on_layer
+
+    def _active(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def layer_ranges(self, layer: int):
+        P = self.engine.params
+        p = f"encoder.layer.{layer}."
+        named = P._named
+        d0 = P.offsets[p + "attention.self.query.weight"]
+        d1 = P.offsets[p + "output.dense.weight"] + named[p + "output.dense.weight"].numel()
+        g0 = P.offsets[p + "attention.self.query_global.weight"]
+        g1 = P.offsets[p + "attention.self.value_global.weight"] + named[p + "attention.self.value_global.weight"].numel()
+        return [(d0, d1), (g0, g1)]
+
+    def on_layer(self, layer: int) -> None:
+        if not self._active():
+            return
+        g = self.engine.params.grad
+        for a, b in self.layer_ranges(layer):
+            self._works.append(dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._covered.append((a, b))
+
+    def finish(self) -> None:
+        if not self._active():
+            self._covered.clear()
+            return
+        P = self.engine.params
+        g = P.grad
+        if g is None:
+            raise RuntimeError("GradSync.finish: no gradients (run backward first)")
+        pos = 0
+        for a, b in sorted(self._covered) + [(P.n_total, P.n_total)]:
+            if a > pos:
+                self._works.append(dist.all_reduce(g[pos:a], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            pos = max(pos, b)
+        for w in self._works:
+            w.wait()
+        self._works.clear()
+        self._covered.clear()

@@ -247,6 +247,7 @@ class EncoderEngine:
         self._side: Dict[str, torch.cuda.Stream] = {}
         self._events: Dict[tuple, torch.cuda.Event] = {}
         self.overlap_global = True
+        self.grad_hook = None      # callable(layer): that layer's gradients are final (dist.GradSync)
 
     # -- helpers -------------------------------------------------------------------------------
     def _acquire(self, B, Lp, device, per_layer) -> SavedActivations:
@@ -476,6 +477,8 @@ class EncoderEngine:
                 ops.global_attn_bwd(*gargs, sc.dctx, sv.glob[i], dx, G["Wqg"], G["bqg"], G["Wkg"], G["Wvg"], G["bvg"],
                                     ws=sc.gws, drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 2))
             d_out = dx
+            if self.grad_hook is not None:
+                self.grad_hook(i)
         e = "embeddings."
         named = P._named
         gview = lambda k: P.view(k, P.grad) if named[k].requires_grad else None

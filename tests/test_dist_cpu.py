@@ -111,3 +111,27 @@ def _grad_allreduce_job(rank, world):
 def test_flat_gradient_allreduce_world2():
     out = _run(_grad_allreduce_job)
     assert out[0][:2] == (1.5, 1.5) and out[1][:2] == (1.5, 1.5)
+
+
+def _grad_sync_job(rank, world):
+    """GradSync: per-layer async all-reduces + finish() cover the flat gradient buffer exactly once."""
+    import recformer_b200 as rb
+    from recformer_b200 import dist as rdist
+    cfg = rb.RecformerConfig(attention_window=[64, 64, 64], vocab_size=120, num_hidden_layers=3,
+                             max_position_embeddings=80)
+    model = rb.RecformerForSeqRec(cfg)
+    eng = model.longformer._engine
+    P = eng.params
+    P.grad = torch.arange(P.n_total, dtype=torch.float32) % 7 + rank      # rank-dependent stand-in gradients
+    expect = (torch.arange(P.n_total, dtype=torch.float32) % 7) * world + sum(range(world))
+    sync = rdist.GradSync(model)
+    assert eng.grad_hook is not None
+    for layer in reversed(range(3)):           # what engine.backward() does as each layer finishes
+        eng.grad_hook(layer)
+    assert len(sync._covered) == 6
+    sync.finish()
+    return bool(torch.equal(P.grad, expect)), len(sync._works)
+
+
+def test_overlapped_grad_sync_covers_buffer_once_world2():
+    assert _run(_grad_sync_job) == [(True, 0), (True, 0)]
