@@ -53,26 +53,49 @@ def algorithmic_gemm_flops_per_seq(L=SEQ_LEN):
 
 
 class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (NVML; nvidia-smi as fallback)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
     def __init__(self, index: int):
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
-    def _run(self):
+    def _sample_nvml(self):
+        n = self.nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        for name, bit in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                              str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+        f = [x.strip() for x in out.split(",")]
+        self.samples.append(float(f[0]))
+        self.max_mhz = float(f[1])
+        for n, v in zip(names, f[2:6]):
+            if v.lower().startswith("active"):
+                self.reasons.add(n)
+
+    def _run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                f = [x.strip() for x in out.split(",")]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
-                for n, v in zip(names, f[2:6]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(n)
+                self._sample_nvml() if self.nvml is not None else self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.01 if self.nvml is not None else 0.2)
 
     def __enter__(self):
         self.t = threading.Thread(target=self._run, daemon=True)
@@ -86,7 +109,7 @@ class ClockSampler:
     def summary(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -276,7 +299,7 @@ def eval_topk_bench(device, rank, world, steps, warmup):
                                                   f"sharded over {world} GPU(s), cosine top-10 + all-gather merge"},
             "roofline": {"bound": "tensor", "achieved": flops / (k_ms / 1e3) / 1e12, "peak": burst, "unit": "TFLOP/s",
                          "frac": flops / (k_ms / 1e3) / 1e12 / burst, "traffic": None, "peak_source": src,
-                         "kernel": "cosine_mma_kernel<TOPK>", "flops_per_launch": flops, "ms_per_launch": k_ms}}
+                         "kernel": "cosine_pair_kernel<TOPK> (tcgen05 cta_group::2, fused top-k epilogue)", "flops_per_launch": flops, "ms_per_launch": k_ms}}
 
 
 def run_ours(args):

@@ -2,7 +2,8 @@
 //
 // One CTA = one (batch, head, 128-query tile), the same tiling as the forward kernel:
 //   S  = Q K^T,  dP = dO V^T                      tcgen05.mma -> TMEM (2 x 208 columns)
-//   P  = exp(S - lse),  delta = sum_j P dP,  dS = P (dP - delta)        fp32, thread = query row
+//   delta = rowsum(dO o O) (= sum_j P'_j dP_j, taken from the saved context instead of a first pass
+//   over the probabilities),  P = exp(S - lse),  dS = P (dP - delta)    fp32, thread = query row
 //   P, dS (bf16) -> shared memory (128B-swizzled, rows = queries)
 //   dQ = dS K          A = dS (K-major),   B = K  (MN-major view of the K tile)
 //   dV = P^T dO        A = P  (MN-major view of the same P buffer), B = dO (MN-major)
@@ -42,6 +43,7 @@ static_assert(AB_SMEM <= 227 * 1024, "shared memory budget");
 
 struct AttnBwdParams {
   const uint8_t* mask012;
+  const __nv_bfloat16* ctx;   // forward output O (bf16 [B*L, E])
   const float* lse;
   __nv_bfloat16* dqkv;
   float* dkv;   // fp32 scratch [B*L, 2E]
@@ -135,13 +137,21 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
                 k > 0 ? 1u : 0u);
     umma_commit(bar_mma);
   }
+  const int r = quad * 32 + lane;       // query row of the tile == TMEM lane
+  const int i = i0 + r;
+  const bool in_seq = i < p.L;
+  // this thread's half (32 of 64 dims) of the saved context row: loaded while TMA / the first MMAs run
+  uint4 o_raw[4];
+  {
+    const uint4* op = reinterpret_cast<const uint4*>(p.ctx + (static_cast<size_t>(b) * p.L + (in_seq ? i : 0)) * E +
+                                                     h * AB_D + part * 32);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) o_raw[u] = in_seq ? op[u] : make_uint4(0, 0, 0, 0);
+  }
   __syncwarp();
   mbar_wait(bar_mma, 0);
   tc_fence_after();
 
-  const int r = quad * 32 + lane;       // query row of the tile == TMEM lane
-  const int i = i0 + r;
-  const bool in_seq = i < p.L;
   const bool is_global_row = (i == 0) && (mrow[0] == 2);
   const bool row_valid = in_seq && (mrow[in_seq ? i : 0] != 0) && !is_global_row;
   const float lse = in_seq ? p.lse[(static_cast<size_t>(b) * p.H + h) * p.L + i] : 0.f;
@@ -167,24 +177,21 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     return km;
   };
 
-  // ---- pass A: delta = sum_c P'_c dP_c (P' = dropout(P)); each part sums its own columns ----
+  // ---- delta_i = sum_j P'_ij dP_ij = dO_i . O_i  (O = sum_j P'_ij V_j is the saved forward output):
+  //      each part dots its 32 dims (dO from the swizzled shared-memory tile, O from registers) ----
   float delta = 0.f;
-#pragma unroll 1
-  for (int cc = cc_lo; cc < cc_hi; ++cc) {
-    uint32_t sv[32], dv[32];
-    tmem_ld32(lane_base + TM_S + cc * 32, sv);
-    tmem_ld32(lane_base + TM_DP + cc * 32, dv);
-    tmem_ld_wait();
-    const uint32_t keepm = chunk_keep(cc);
+  {
+    const uint8_t* drow = sDO + (r >> 6) * 8192 + (r & 63) * 128;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int c = cc * 32 + j;
-      const bool ok = row_valid && kflag[c] && (c >= r) && (c <= r + 2 * W) && ((keepm >> j) & 1u);
-      const float pr = ok ? exp2f(__uint_as_float(sv[j]) * LOG2E - lse2) : 0.f;
-      delta += pr * __uint_as_float(dv[j]);
+    for (int u = 0; u < 4; ++u) {
+      const uint4 d = *reinterpret_cast<const uint4*>(drow + (((part * 4 + u) ^ (r & 7)) << 4));
+      const uint4 o = o_raw[u];
+      const float2 d0 = unpack_bf16(d.x), d1 = unpack_bf16(d.y), d2 = unpack_bf16(d.z), d3 = unpack_bf16(d.w);
+      const float2 o0 = unpack_bf16(o.x), o1 = unpack_bf16(o.y), o2 = unpack_bf16(o.z), o3 = unpack_bf16(o.w);
+      delta += d0.x * o0.x + d0.y * o0.y + d1.x * o1.x + d1.y * o1.y + d2.x * o2.x + d2.y * o2.y + d3.x * o3.x +
+               d3.y * o3.y;
     }
   }
-  delta *= p.drop_scale;
   float pg = 0.f, pg_d = 0.f, keep_g = 1.f, dpg = 0.f;
   if (part == 1) {   // warp-uniform
     uint32_t gs[16], gd[16];
@@ -199,11 +206,10 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
       pg_d = pg * keep_g;
     }
     dpg = __uint_as_float(gd[0]);
-    delta += pg_d * dpg;
   }
   s_delta[part * 128 + r] = delta;
   __syncthreads();
-  delta = s_delta[r] + s_delta[128 + r];
+  delta = row_valid ? s_delta[r] + s_delta[128 + r] : 0.f;   // masked rows may hold non-finite garbage in O / dO
 
   // ---- pass B: P' and dS -> shared memory (window chunks as in pass A; the remaining all-zero
   //      chunks are split by parity) ----
@@ -375,9 +381,8 @@ using namespace rf;
 
 extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const float* lse, const void* dctx,
                                 void* dqkv, float* dkv_scratch, rf_stream_t stream_) {
-  (void)ctx;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  RF_REQUIRE(a && lse && dctx && dqkv && dkv_scratch, "rf_band_attn_bwd: null argument");
+  RF_REQUIRE(a && ctx && lse && dctx && dqkv && dkv_scratch, "rf_band_attn_bwd: null argument");
   RF_REQUIRE(a->D == AB_D, "rf_band_attn_bwd: head_dim %d unsupported (64 only)", a->D);
   RF_REQUIRE(a->w == AB_W, "rf_band_attn_bwd: one-sided window %d unsupported (32 only, i.e. attention_window 64)",
              a->w);
@@ -396,6 +401,7 @@ extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const fl
   RF_CUDA(cudaMemsetAsync(dkv_scratch, 0, static_cast<size_t>(B) * L * 2 * E * sizeof(float), stream));
   AttnBwdParams p;
   p.mask012 = a->mask012; p.lse = lse;
+  p.ctx = reinterpret_cast<const __nv_bfloat16*>(ctx);
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   p.dkv = dkv_scratch;
   {
