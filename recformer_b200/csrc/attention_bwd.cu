@@ -58,7 +58,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
                      const __grid_constant__ CUtensorMap tmDO, const AttnBwdParams p) {
   constexpr int W = AB_W, NK = AB_NK, NT = AB_NT;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sQ = smem + AB_OFF_Q;
   uint8_t* sDO = smem + AB_OFF_DO;
   uint8_t* sK = smem + AB_OFF_K;

@@ -58,7 +58,7 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
   using C = AttnFwdCfg<W>;
   constexpr int NK = C::NK, NT = C::NT;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sQ = smem;
   uint8_t* sK = smem + C::Q_BYTES;
   uint8_t* sP = smem;  // aliases Q/K once S has been computed

@@ -14,6 +14,7 @@
 // nn.Linear weights) or MN-major (row = K index: used by dgrad for W and by wgrad for both
 // operands, so no transposed copies of weights or activations are ever materialised).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "rf_common.h"
 #include "rf_ptx.cuh"
@@ -38,6 +39,7 @@ struct GemmParams {
   int split_k;
   float scale;
   int scale_ncols;
+  int debug_skip_epilogue;   // profiling aid (RF_DEBUG_GEMM_NOEPI=1): accumulators are drained but nothing is stored
   float drop_scale;       // 1/(1-p)
   uint32_t drop_thresh;   // p * 65536, 0 = no dropout
   uint64_t drop_seed;
@@ -110,7 +112,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ge
     }
   }
   // ---- phase 1: thread (= row `lane`) writes its 32 fp32 values, 16B units XOR-swizzled by row ----
-  {
+  if (!(p.debug_skip_epilogue & 8)) {
     uint8_t* srow = stage + lane * 128;
 #pragma unroll
     for (int u = 0; u < 8; ++u)
@@ -136,8 +138,14 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ge
     const int rl = s * 8 + (lane >> 2);
     const int row = row_base + rl;
     const uint8_t* srow = stage + rl * 128;
-    const float4 x0 = *reinterpret_cast<const float4*>(srow + (((2 * cq) ^ (rl & 7)) << 4));
-    const float4 x1 = *reinterpret_cast<const float4*>(srow + (((2 * cq + 1) ^ (rl & 7)) << 4));
+    float4 x0, x1;
+    if (p.debug_skip_epilogue & 8) {
+      x0 = make_float4(__uint_as_float(r[s * 8]), __uint_as_float(r[s * 8 + 1]), __uint_as_float(r[s * 8 + 2]), __uint_as_float(r[s * 8 + 3]));
+      x1 = make_float4(__uint_as_float(r[s * 8 + 4]), __uint_as_float(r[s * 8 + 5]), __uint_as_float(r[s * 8 + 6]), __uint_as_float(r[s * 8 + 7]));
+    } else {
+      x0 = *reinterpret_cast<const float4*>(srow + (((2 * cq) ^ (rl & 7)) << 4));
+      x1 = *reinterpret_cast<const float4*>(srow + (((2 * cq + 1) ^ (rl & 7)) << 4));
+    }
     if (row >= p.M) continue;
     float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
@@ -147,10 +155,14 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ge
       // C2 <- gelu(u) (operand of the next GEMM); C <- gelu'(u) (all the backward pass needs of u)
       float g[8], d[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) gelu_and_grad(v[e], g[e], d[e]);
+      for (int e = 0; e < 8; ++e) {
+        if (p.debug_skip_epilogue & 4) { g[e] = v[e]; d[e] = v[e]; }
+        else gelu_and_grad(v[e], g[e], d[e]);
+      }
       uint4 dv, gv;
       dv.x = pack_bf16(d[0], d[1]); dv.y = pack_bf16(d[2], d[3]); dv.z = pack_bf16(d[4], d[5]); dv.w = pack_bf16(d[6], d[7]);
       gv.x = pack_bf16(g[0], g[1]); gv.y = pack_bf16(g[2], g[3]); gv.z = pack_bf16(g[4], g[5]); gv.w = pack_bf16(g[6], g[7]);
+      if ((p.debug_skip_epilogue & 2) && dv.x != 0x12345678u) continue;
       *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = dv;
       *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + off) = gv;
       continue;
@@ -197,6 +209,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ge
     } else {
       uint4 o;
       o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+      if ((p.debug_skip_epilogue & 2) && o.x != 0x12345678u) continue;
       *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = o;
     }
   }
@@ -209,7 +222,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   using S = GemmSmem<BN>;
   constexpr int STAGES = S::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* s_stage = smem + S::TILE_BYTES;    // [EPI_WARPS][4096] epilogue transpose slabs
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES + S::EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -288,6 +301,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == 1) {
     // ================= MMA issuer =================
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    const bool elected = elect_one();
+    const uint32_t smem_base = smem_u32(smem);
+    const uint64_t adesc0 = A_MN ? umma_smem_desc(smem_base, 8192, 1024) : umma_smem_desc(smem_base, 16, 1024);
+    const uint64_t bdesc0 = B_MN ? umma_smem_desc(smem_base + S::A_BYTES, 8192, 1024)
+                                 : umma_smem_desc(smem_base + S::A_BYTES, 16, 1024);
+    constexpr uint32_t A_KSTEP = (A_MN ? 2048u : 32u) >> 4, B_KSTEP = (B_MN ? 2048u : 32u) >> 4;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -302,22 +321,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint32_t sb = sa + S::A_BYTES;
+        const uint32_t soff = static_cast<uint32_t>(stage) * (S::STAGE_BYTES >> 4);
+        const uint64_t ad = adesc0 + soff, bd = bdesc0 + soff;
+        if (elected) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = A_MN ? umma_smem_desc(sa + k * 2048, 8192, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? umma_smem_desc(sb + k * 2048, 8192, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(d_tmem, ad + k * A_KSTEP, bd + k * B_KSTEP, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);                 // slot reusable once these MMAs retire
           if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (kb1 <= kb0 && lane == 0) umma_commit(&tfull_bar[acc]);  // empty K slice (never for sane shapes)
+      if (kb1 <= kb0 && elected) umma_commit(&tfull_bar[acc]);  // empty K slice (never for sane shapes)
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
@@ -394,6 +410,8 @@ static void fill_params(const rf_gemm_args* a, GemmParams& p) {
   p.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   p.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
   p.drop_seed = a->drop_seed;
+  static const int noepi = getenv("RF_DEBUG_GEMM_NOEPI") ? atoi(getenv("RF_DEBUG_GEMM_NOEPI")) : 0;
+  p.debug_skip_epilogue = noepi;
 }
 
 // ==============================================================================================
@@ -416,7 +434,7 @@ template <bool A_MN, bool B_MN, int EPI, bool OUT_F32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* s_stage = smem + P_TILE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P_TILE_BYTES + P_EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + P_STAGES;
@@ -496,8 +514,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
+    // The whole warp stays converged; descriptors are warp-uniform values (base + stage / k offsets in
+    // the 16-byte-granular address field) and only the tcgen05 instructions themselves are predicated on
+    // the elected lane, which keeps the per-k-block issue sequence short.
     if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, P_BN, A_MN, B_MN);
+      const bool elected = elect_one();
+      const uint32_t smem_base = smem_u32(smem);
+      const uint64_t adesc0 = A_MN ? umma_smem_desc(smem_base, 8192, 1024) : umma_smem_desc(smem_base, 16, 1024);
+      const uint64_t bdesc0 = B_MN ? umma_smem_desc(smem_base + P_A_BYTES, 8192, 1024)
+                                   : umma_smem_desc(smem_base + P_A_BYTES, 16, 1024);
+      constexpr uint32_t A_KSTEP = (A_MN ? 2048u : 32u) >> 4, B_KSTEP = (B_MN ? 2048u : 32u) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -512,15 +539,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = smem_u32(smem + stage * P_STAGE_BYTES);
-            const uint32_t sb = sa + P_A_BYTES;
+          const uint32_t soff = static_cast<uint32_t>(stage) * (P_STAGE_BYTES >> 4);
+          const uint64_t ad = adesc0 + soff, bd = bdesc0 + soff;
+          if (elected) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t adesc = A_MN ? umma_smem_desc(sa + k * 2048, 8192, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
-              const uint64_t bdesc = B_MN ? umma_smem_desc(sb + k * 2048, 8192, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
-              umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_pair(d_tmem, ad + k * A_KSTEP, bd + k * B_KSTEP, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             umma_commit_pair(&empty_bar[stage]);
             if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[acc]);
           }
@@ -564,7 +588,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         const int lcol = half * (P_BN / 2) + c * 32;
         const int col0 = n0 + lcol;
-        if (col0 >= p.N) continue;
+        if (col0 >= p.N || (p.debug_skip_epilogue & 1)) continue;
         epilogue_chunk<EPI, OUT_F32>(rbuf[c & 1], p, sb, my_stage, lane, lcol, row_base, col0);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }

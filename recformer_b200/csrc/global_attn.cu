@@ -447,7 +447,7 @@ global_mix_kernel(const __grid_constant__ CUtensorMap tmX, const MixParams p) {
   constexpr bool DX = C::DX;
   constexpr int TOK = C::TOK, STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   float* red = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);                 // [8][GH][64] (MIX_ACC)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + C::RED_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;

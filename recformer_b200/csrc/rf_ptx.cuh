@@ -14,6 +14,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// 1024-byte aligned start inside the dynamic shared-memory array (swizzled TMA / UMMA tiles need it).
+// Done as an OFFSET on the __shared__ array, not through a uintptr_t round trip: the latter makes the
+// compiler forget the address space and emit generic LD/ST (slower, long-scoreboard) for every access.
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* smem_raw) {
+  const uint32_t base = smem_u32(smem_raw);
+  return smem_raw + ((1024u - (base & 1023u)) & 1023u);
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -44,14 +52,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// suspend-time hint of try_wait: the waiting thread is parked by the hardware (no issue slots burnt) until
+// the phase completes or this many nanoseconds pass; a spinning waiter otherwise competes with the
+// epilogue warps that share its scheduler
+constexpr uint32_t MBAR_SUSPEND_HINT_NS = 200000u;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS)
       : "memory");
   return ok != 0;
 }
@@ -161,8 +173,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// Remote arrive with the default (.release.cta) semantics: a cluster-scope release would first drain every
+// outstanding global store of the thread (measured: the largest stall of the GEMM epilogue), and the
+// accumulator hand-over only needs the tcgen05.ld's to have completed (tcgen05.wait::ld + fence before).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion bytes are credited to an mbarrier that may live in the peer CTA
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,

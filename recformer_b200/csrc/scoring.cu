@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1)
 cosine_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const ScoreParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* s_list = smem + SC_STAGES * SC_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_list + SC_LIST_BYTES);
   uint64_t* empty_bar = full_bar + SC_STAGES;
@@ -191,6 +191,9 @@ cosine_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = umma_idesc_bf16(SC_BM, SC_BN, false, false);
+    const bool elected = elect_one();
+    const uint64_t adesc0 = umma_smem_desc(smem_u32(smem), 16, 1024);
+    const uint64_t bdesc0 = umma_smem_desc(smem_u32(smem) + SC_A_BYTES, 16, 1024);
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
     for (int nt = slice; nt < n_tiles; nt += p.slices) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -198,12 +201,11 @@ cosine_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * SC_STAGE_BYTES), sb = sa + SC_A_BYTES;
+        const uint32_t soff = static_cast<uint32_t>(stage) * (SC_STAGE_BYTES >> 4);
+        if (elected) {
 #pragma unroll
           for (int k = 0; k < SC_BK / 16; ++k)
-            umma_bf16(tmem_base + acc * SC_BN, umma_smem_desc(sa + k * 32, 16, 1024),
-                      umma_smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) ? 1u : 0u);
+            umma_bf16(tmem_base + acc * SC_BN, adesc0 + soff + k * 2, bdesc0 + soff + k * 2, idesc, (kb | k) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]);
         }
@@ -260,7 +262,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SC_THREADS, 1)
 cosine_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const ScoreParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* s_list = smem + SP_STAGES * SP_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_list + SC_LIST_BYTES);
   uint64_t* empty_bar = full_bar + SP_STAGES;
@@ -343,6 +345,9 @@ cosine_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, SC_BN, false, false);
+      const bool elected = elect_one();
+      const uint64_t adesc0 = umma_smem_desc(smem_u32(smem), 16, 1024);
+      const uint64_t bdesc0 = umma_smem_desc(smem_u32(smem) + SP_STAGE_BYTES / 2, 16, 1024);
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
       for (long long t = 0; t < my_tiles; ++t) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -350,12 +355,12 @@ cosine_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = smem_u32(smem + stage * SP_STAGE_BYTES), sb = sa + SP_STAGE_BYTES / 2;
+          const uint32_t soff = static_cast<uint32_t>(stage) * (SP_STAGE_BYTES >> 4);
+          if (elected) {
 #pragma unroll
             for (int k = 0; k < SC_BK / 16; ++k)
-              umma_bf16_pair(tmem_base + acc * SC_BN, umma_smem_desc(sa + k * 32, 16, 1024),
-                             umma_smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) ? 1u : 0u);
+              umma_bf16_pair(tmem_base + acc * SC_BN, adesc0 + soff + k * 2, bdesc0 + soff + k * 2, idesc,
+                             (kb | k) ? 1u : 0u);
             umma_commit_pair(&empty_bar[stage]);
             if (kb == k_blocks - 1) umma_commit_pair(&tfull_bar[acc]);
           }
