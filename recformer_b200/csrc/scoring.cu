@@ -22,12 +22,13 @@
 
 namespace rf {
 
-constexpr int SC_BM = 128, SC_BN = 256, SC_BK = 64, SC_STAGES = 4;
+constexpr int SC_BM = 128, SC_BN = 256, SC_BK = 64, SC_STAGES = 3;
 constexpr int SC_EPI_WARPS = 8, SC_THREADS = 64 + 32 * SC_EPI_WARPS;
 constexpr int SC_MAXK = 16;
 constexpr uint32_t SC_A_BYTES = SC_BM * SC_BK * 2, SC_B_BYTES = SC_BN * SC_BK * 2;
 constexpr uint32_t SC_STAGE_BYTES = SC_A_BYTES + SC_B_BYTES;
-constexpr uint32_t SC_LIST_BYTES = SC_MAXK * SC_EPI_WARPS * 32 * 8;   // per-thread top-k lists: [q][thread] score + id
+constexpr uint32_t SC_LIST_ONLY_BYTES = SC_MAXK * SC_EPI_WARPS * 32 * 8;   // per-thread top-k lists: [q][thread] score + id
+constexpr uint32_t SC_LIST_BYTES = SC_LIST_ONLY_BYTES + SC_EPI_WARPS * 4096;   // + per-warp [32 cols][32 rows] fp32 chunk slab
 constexpr uint32_t SC_SMEM = SC_STAGES * SC_STAGE_BYTES + SC_LIST_BYTES + (2 * SC_STAGES + 4) * 8 + 16 + 1024;
 // CTA-pair variant: 256 users x 256 items per tile, each CTA stages its 128 user rows and its
 // 128-item half of the table slab (32 KB per 64-wide K slab), 5 ring stages
@@ -59,6 +60,7 @@ enum { SC_TOPK = 0, SC_DENSE = 1 };
 // the common case — no column of a 32-column accumulator chunk beats thr — costs one max per
 // column and a single warp vote.
 struct TopkState {
+  float* scratch;   // this thread's column of its warp's [32][32] fp32 chunk slab
   float* ts;        // &list_scores[0][thread]
   int* ti;          // &list_ids[0][thread]
   float thr;
@@ -68,7 +70,7 @@ struct TopkState {
 
 constexpr int SC_LIST_STRIDE = SC_EPI_WARPS * 32;
 
-__device__ __noinline__ float topk_insert(float* ts, int* ti, int k, float s, int id) {
+__device__ __forceinline__ float topk_insert(float* ts, int* ti, int k, float s, int id) {
   // descending insertion; strict '>' keeps the earlier (lower) id ahead on equal scores
   int q = k - 1;
   while (q > 0 && s > ts[(q - 1) * SC_LIST_STRIDE]) {
@@ -98,14 +100,29 @@ __device__ __forceinline__ void topk_chunk(const uint32_t (&r)[32], TopkState& s
   const bool partial = col0 + 32 > p.N;                                // warp-uniform
   const bool mine = (mx > st.thr) || (rel >= 0 && rel < 32) || partial;
   if (!__any_sync(0xffffffffu, mine)) return;
+  // slow path: bit mask of the columns that beat the current k-th best, then one insertion per set bit
+  // (a straight-line predicated insert per column costs ~10x more: the threshold only moves on a hit)
+  const int nvalid = partial ? static_cast<int>(p.N - col0) : 32;
+  uint32_t hits = 0;
   if (mine) {
-    const int nvalid = partial ? static_cast<int>(p.N - col0) : 32;
-    const int id0 = p.id_base + static_cast<int>(col0);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float s = __uint_as_float(r[j]) * p.inv_temp;
       if (j == rel && j < nvalid) st.label_score = s;
-      if (s > st.thr && j < nvalid) st.thr = topk_insert(st.ts, st.ti, p.k, s, id0 + j);
+      hits |= (s > st.thr && j < nvalid) ? (1u << j) : 0u;
+    }
+  }
+  if (__any_sync(0xffffffffu, hits != 0)) {
+    // the chunk's values go through this thread's column of the warp's scratch slab so that a hit can be
+    // fetched by its (dynamic) column index
+#pragma unroll
+    for (int j = 0; j < 32; ++j) st.scratch[j * 32] = __uint_as_float(r[j]);
+    const int id0 = p.id_base + static_cast<int>(col0);
+    while (hits != 0) {
+      const int j = __ffs(hits) - 1;
+      hits &= hits - 1;
+      const float s = st.scratch[j * 32] * p.inv_temp;
+      if (s > st.thr) st.thr = topk_insert(st.ts, st.ti, p.k, s, id0 + j);   // thr may have risen since the mask was built
     }
   }
   __syncwarp();
@@ -122,6 +139,7 @@ __device__ __forceinline__ void dense_chunk(const uint32_t (&r)[32], const Score
 
 __device__ __forceinline__ void topk_state_init(TopkState& st, uint8_t* list_smem, int etid, const ScoreParams& p, int row,
                                                 bool row_ok) {
+  st.scratch = reinterpret_cast<float*>(list_smem + SC_LIST_ONLY_BYTES) + (etid >> 5) * 1024 + (etid & 31);
   st.ts = reinterpret_cast<float*>(list_smem) + etid;
   st.ti = reinterpret_cast<int*>(list_smem + SC_MAXK * SC_LIST_STRIDE * 4) + etid;
   for (int q = 0; q < SC_MAXK; ++q) { st.ts[q * SC_LIST_STRIDE] = -INFINITY; st.ti[q * SC_LIST_STRIDE] = 0x7fffffff; }
