@@ -45,6 +45,22 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+def profiled_traffic(kernel_substr):
+    """Mean DRAM bytes per launch of the kernels whose name contains `kernel_substr`, from the newest committed
+    ncu --set full capture (profiles/*_traffic.json, written by tools/make_profiles.py); None if absent."""
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        files = sorted(f for f in os.listdir(pdir) if f.endswith("_traffic.json"))
+        d = json.load(open(os.path.join(pdir, files[-1])))
+        sel = [v for k, v in d.items() if kernel_substr in k]
+        if not sel:
+            return None, None
+        n = sum(v["n"] for v in sel)
+        return sum(v["dram_bytes"] * v["n"] for v in sel) / n, files[-1]
+    except Exception:
+        return None, None
+
+
 def algorithmic_gemm_flops_per_seq(L=SEQ_LEN):
     """Dense projections only (Q,K,V,out,FFN), fwd + dgrad + wgrad = 3x fwd; the reference's
     key_global/value_global GEMMs are re-associated away and not counted."""
@@ -348,8 +364,12 @@ def run_ours(args):
     hbm, burst, sustained, src = peaks()
     flops_step = algorithmic_gemm_flops_per_seq() * B_PER_GPU
     achieved = flops_step / (gemm_ms / 1e3) / 1e12
+    traffic, traffic_src = profiled_traffic("gemm_pair_kernel")
     roof = {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
-            "traffic": None, "peak_source": f"{src} (sustained: kernel timed inside a long step)",
+            "traffic": traffic, "traffic_source": (f"profiles/{traffic_src}: mean dram read+write bytes per launch over the "
+                                                   "captured gemm_pair_kernel launches (fwd QKV / GELU / down / dGELU / wgrad)"
+                                                   if traffic_src else None),
+            "peak_source": f"{src} (sustained: kernel timed inside a long step)",
             "kernel": "gemm_kernel (tcgen05, all fwd/dgrad/wgrad launches of one step)",
             "flops_per_launch": flops_step / n_gemm, "launches_per_step": n_gemm, "ms_per_launch": gemm_ms / n_gemm,
             "gemm_share_of_step": gemm_ms / step_ms_prof,
