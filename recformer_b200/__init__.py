@@ -2,7 +2,7 @@
 
 Mirrors the reference `recformer` package's public names (ref: recformer/__init__.py:1-3) for
 the hot path: RecformerConfig, RecformerModel, RecformerForSeqRec, RecformerTokenizer."""
-__all__ = ["RecformerConfig", "RecformerModel", "RecformerForSeqRec", "RecformerTokenizer", "Ranker"]
+__all__ = ["RecformerConfig", "RecformerModel", "RecformerForSeqRec", "RecformerTokenizer", "Ranker", "encode_all_items"]
 
 
 def __getattr__(name):
@@ -15,4 +15,7 @@ def __getattr__(name):
     if name in ("Ranker", "TopKRanker"):
         from . import metrics
         return getattr(metrics, name)
+    if name == "encode_all_items":
+        from .items import encode_all_items
+        return encode_all_items
     raise AttributeError(name)

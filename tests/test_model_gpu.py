@@ -177,3 +177,40 @@ def test_dropout_training_runs_and_is_stochastic():
     l2 = model(**batch, labels=labels)
     assert torch.isfinite(l1) and torch.isfinite(l2) and l1.item() != l2.item()
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+
+
+def test_encode_all_items_matches_oracle():
+    """Item-table build (ref: finetune.py:38-63): one-item sequences of 20..96 tokens, padded to the batch max
+    (so L is not a multiple of 64), CLS pooled; also the fused normalised-shard output and the id_range shard."""
+    import recformer_b200 as rb
+    from recformer_b200.items import encode_all_items
+    ocfg = O.OracleConfig(vocab_size=1200, num_hidden_layers=2, attention_window=[64, 64], max_position_embeddings=600)
+    cfg = rb.RecformerConfig(attention_window=[64, 64], vocab_size=1200, num_hidden_layers=2, max_position_embeddings=600,
+                             max_item_embeddings=51)
+    model = rb.RecformerModel(cfg)
+    sd = O.make_state_dict(ocfg, seed=0)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    tok = rb.RecformerTokenizer(cfg)
+    g = torch.Generator().manual_seed(5)
+    items = {}
+    for item_id in range(37):
+        n = int(torch.randint(20, 97, (1,), generator=g))
+        items[item_id * 3 + 1] = [torch.randint(3, 1200, (n,), generator=g).tolist(),
+                                  torch.randint(1, 3, (n,), generator=g).tolist()]
+    norm = torch.empty(len(items), 768, dtype=torch.bfloat16, device="cuda")
+    table = encode_all_items(model, tok, items, batch_size=16, normalized_out=norm)
+    ids = sorted(items)
+    ref_rows = []
+    for a in range(0, len(ids), 16):
+        batch = {k: torch.tensor(v) for k, v in O.tokenizer_batch_encode(ocfg, [[items[i]] for i in ids[a:a + 16]]).items()}
+        ref_rows.append(O.model_forward(sd, ocfg, **batch)[1])
+    ref = torch.cat(ref_rows)
+    assert table.shape == ref.shape
+    assert (table.cpu() - ref).abs().max() < 2e-2
+    refn = ref / ref.norm(dim=-1, keepdim=True)
+    assert (norm.float().cpu() - refn).abs().max() < 1e-2
+    shard = encode_all_items(model, tok, items, batch_size=16, id_range=(30, 70))
+    sel = [k for k, i in enumerate(ids) if 30 <= i < 70]
+    assert shard.shape[0] == len(sel)
+    assert (shard.cpu() - ref[sel]).abs().max() < 2e-2
