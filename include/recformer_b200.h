@@ -158,7 +158,7 @@ int rf_layernorm_bwd(const void* dy_bf16, const float* x_f32, const float* stats
  *   ctx  [B*L, E] bf16: attention output of every NON-global query (row 0 of each sequence
  *        is written by rf_global_attn_fwd); padded query rows are exactly zero (HF:578).
  *   lse  [B,H,L] fp32: log-sum-exp of each query row (saved for backward).
- * one_sided_window w = attention_window/2 must be a multiple of 32 and <= 256.
+ * one_sided_window w = attention_window/2 must be a multiple of 32 and <= 256 (attention_window 64..512).
  * ------------------------------------------------------------------------------------------ */
 typedef struct rf_attn_args {
   const void* qkv; /* bf16 [B*L, 3E] */
@@ -167,13 +167,18 @@ typedef struct rf_attn_args {
   int w; /* one-sided window */
   float drop_p;
   uint64_t drop_seed;
+  void* ws; /* workspace of rf_band_attn_ws_bytes() bytes; required when w > 32, else may be NULL */
 } rf_attn_args;
+
+/* Workspace for windows wider than attention_window 64 (w > 32): the band is covered by ceil((2w+1)/65)
+ * launches of the 65-key kernels on shifted keys whose partial outputs are merged through their
+ * log-sum-exps (exact); the backward accumulates dQ over the same segments.  0 for w == 32. */
+long long rf_band_attn_ws_bytes(int B, int L, int H, int w);
 
 int rf_band_attn_fwd(const rf_attn_args* a, void* ctx_bf16, float* lse, rf_stream_t stream);
 /* dqkv [B*L,3E] bf16 (gradient w.r.t. the UNSCALED q and k, v projections), given dctx.
  * dkv_scratch: fp32 [B*L, 2E] workspace (zeroed by the call) in which the K/V gradients of
- * overlapping tiles and of the CLS key are accumulated before being folded into dqkv.
- * Round 1: one-sided window 32 (attention_window 64) only. */
+ * overlapping tiles and of the CLS key are accumulated before being folded into dqkv. */
 int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx_bf16, const float* lse, const void* dctx_bf16,
                      void* dqkv_bf16, float* dkv_scratch, rf_stream_t stream);
 

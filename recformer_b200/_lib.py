@@ -34,7 +34,7 @@ class EmbedArgs(C.Structure):
 
 class AttnArgs(C.Structure):
     _fields_ = [("qkv", c_void_p), ("mask012", c_void_p), ("B", c_int), ("L", c_int), ("H", c_int), ("D", c_int),
-                ("w", c_int), ("drop_p", c_float), ("drop_seed", c_u64)]
+                ("w", c_int), ("drop_p", c_float), ("drop_seed", c_u64), ("ws", c_void_p)]
 
 
 class GlobalArgs(C.Structure):
@@ -59,6 +59,7 @@ _SIGS = {
                                  c_void_p]),
     "rf_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_u64,
                                  c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "rf_band_attn_ws_bytes": (c_ll, [c_int, c_int, c_int, c_int]),
     "rf_band_attn_fwd": (c_int, [P(AttnArgs), c_void_p, c_void_p, c_void_p]),
     "rf_band_attn_bwd": (c_int, [P(AttnArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rf_global_attn_fwd": (c_int, [P(GlobalArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -1,4 +1,6 @@
-// Banded attention backward (one-sided window W = 32, i.e. attention_window 64), sm_100a.
+// Banded attention backward, sm_100a.  The kernel covers 65 key offsets per query (one-sided window 32 =
+// attention_window 64); wider windows run it once per window segment (shifted keys, see attention_fwd.cu)
+// with the FINAL log-sum-exp / context of the merged forward, accumulating dQ in an fp32 scratch.
 //
 // One CTA = one (batch, head, 128-query tile), the same tiling as the forward kernel:
 //   S  = Q K^T,  dP = dO V^T                      tcgen05.mma -> TMEM (2 x 208 columns)
@@ -47,7 +49,9 @@ struct AttnBwdParams {
   const float* lse;
   __nv_bfloat16* dqkv;
   float* dkv;   // fp32 scratch [B*L, 2E]
+  float* dq32;  // fp32 dQ scratch [B*L, E] (wide windows: dQ is accumulated over the window segments) or null
   int B, L, H;
+  int shift, hi_cut, use_cls;   // window segment (see attention_fwd.cu)
   float drop_scale;
   uint32_t drop_thresh;
   uint64_t drop_seed;
@@ -95,10 +99,10 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   for (int c = tid; c < NT; c += AB_THREADS) {
     uint8_t f = 0;
     if (c < NK) {
-      const int j = i0 - W + c;
+      const int j = i0 - W + p.shift + c;
       f = (j >= 0 && j < p.L && mrow[j] == 1) ? 1 : 0;
     } else if (c == NK) {
-      f = (mrow[0] == 2) ? 1 : 0;
+      f = (p.use_cls && mrow[0] == 2) ? 1 : 0;
     }
     kflag[c] = f;
   }
@@ -118,8 +122,8 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     }
 #pragma unroll
     for (int c = 0; c < NK / 64; ++c) {
-      tma_load_3d(sK + c * 8192, &tmQKV64, bar_load, E + h * AB_D, i0 - W + c * 64, b);
-      tma_load_3d(sV + c * 8192, &tmQKV64, bar_load, 2 * E + h * AB_D, i0 - W + c * 64, b);
+      tma_load_3d(sK + c * 8192, &tmQKV64, bar_load, E + h * AB_D, i0 - W + p.shift + c * 64, b);
+      tma_load_3d(sV + c * 8192, &tmQKV64, bar_load, 2 * E + h * AB_D, i0 - W + p.shift + c * 64, b);
     }
     tma_load_3d(sK + NK * 128, &tmQKV16, bar_load, E + h * AB_D, 0, b);
     tma_load_3d(sV + NK * 128, &tmQKV16, bar_load, 2 * E + h * AB_D, 0, b);
@@ -229,7 +233,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int c = cc * 32 + j;
-        const bool ok = row_valid && kflag[c] && (c >= r) && (c <= r + 2 * W);
+        const bool ok = row_valid && kflag[c] && (c >= r) && (c <= r + 2 * W - p.hi_cut);
         const float pu = ok ? exp2f(__uint_as_float(sv[j]) * LOG2E - lse2) : 0.f;
         const float kp = ((keepm >> j) & 1u) ? p.drop_scale : 0.f;
         pr[j] = pu * kp;                                           // P' feeds dV
@@ -306,7 +310,15 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     uint32_t v[32];
     tmem_ld32(lane_base + TM_DQ + part * 32, v);
     tmem_ld_wait();
-    if (in_seq) {
+    if (in_seq && p.dq32 != nullptr) {
+      float* orow = p.dq32 + (static_cast<size_t>(b) * p.L + i) * E + h * AB_D + part * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + j), "f"(__uint_as_float(v[j]) * 0.125f),
+                     "f"(__uint_as_float(v[j + 1]) * 0.125f), "f"(__uint_as_float(v[j + 2]) * 0.125f),
+                     "f"(__uint_as_float(v[j + 3]) * 0.125f)
+                     : "memory");
+    } else if (in_seq) {
       __nv_bfloat16* orow = p.dqkv + (static_cast<size_t>(b) * p.L + i) * 3 * E + h * AB_D + part * 32;
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
@@ -342,7 +354,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
       const int u = lane & 7;                       // 16B unit = 4 floats of the 32-dim chunk
       const int c = hh * 128 + quad * 32 + rl;      // key column of the tile
       int j = -1;
-      if (c < NK) j = i0 - W + c;
+      if (c < NK) j = i0 - W + p.shift + c;
       else if (c == NK) j = 0;
       const bool key_ok = (j >= 0 && j < p.L) && (c <= NK) && kflag[c <= NK ? c : 0];
       const float4 x = *reinterpret_cast<const float4*>(slab + rl * 128 + ((u ^ (rl & 7)) << 4));
@@ -360,6 +372,18 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
+  }
+}
+
+// dqkv[:, 0:E] = bf16(dq32)   (wide windows only)
+__global__ void fold_dq_kernel(const float4* __restrict__ dq, __nv_bfloat16* __restrict__ dqkv, long long T, int E) {
+  const int per_row = E / 4;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < T * per_row;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long t = idx / per_row;
+    const int c4 = static_cast<int>(idx % per_row);
+    const float4 v = dq[idx];
+    *reinterpret_cast<uint2*>(dqkv + t * 3 * E + c4 * 4) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
   }
 }
 
@@ -384,8 +408,8 @@ extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const fl
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   RF_REQUIRE(a && ctx && lse && dctx && dqkv && dkv_scratch, "rf_band_attn_bwd: null argument");
   RF_REQUIRE(a->D == AB_D, "rf_band_attn_bwd: head_dim %d unsupported (64 only)", a->D);
-  RF_REQUIRE(a->w == AB_W, "rf_band_attn_bwd: one-sided window %d unsupported (32 only, i.e. attention_window 64)",
-             a->w);
+  RF_REQUIRE(a->w >= 32 && a->w % 32 == 0 && a->w <= 256,
+             "rf_band_attn_bwd: one-sided window %d unsupported (multiples of 32 up to 256)", a->w);
   RF_REQUIRE(a->B > 0 && a->L >= 16 && a->H > 0, "rf_band_attn_bwd: bad shape");
   static bool attr_set = false;
   if (!attr_set) {
@@ -394,16 +418,23 @@ extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const fl
   }
   const int E = a->H * AB_D;
   const uint64_t L = a->L, B = a->B;
+  const long long T = static_cast<long long>(B) * L;
   const CUtensorMap* tm64 = get_tmap_3d(a->qkv, B, L, 3 * E, 3 * E, L * 3 * E, 64);
   const CUtensorMap* tm16 = get_tmap_3d(a->qkv, B, L, 3 * E, 3 * E, L * 3 * E, 16);
   const CUtensorMap* tmdo = get_tmap_3d(dctx, B, L, E, E, L * E, 64);
   if (!tm64 || !tm16 || !tmdo) return RF_ERR_CUDA;
-  RF_CUDA(cudaMemsetAsync(dkv_scratch, 0, static_cast<size_t>(B) * L * 2 * E * sizeof(float), stream));
+  // window segments: the same decomposition (and per-segment dropout seeds) as the forward pass
+  const int nseg = (2 * a->w + 1 + 64) / 65;
+  RF_REQUIRE(nseg == 1 || a->ws != nullptr, "rf_band_attn_bwd: windows wider than 64 need a workspace");
+  float* dq32 = nseg > 1 ? reinterpret_cast<float*>(a->ws) : nullptr;
+  RF_CUDA(cudaMemsetAsync(dkv_scratch, 0, static_cast<size_t>(T) * 2 * E * sizeof(float), stream));
+  if (dq32) RF_CUDA(cudaMemsetAsync(dq32, 0, static_cast<size_t>(T) * E * sizeof(float), stream));
   AttnBwdParams p;
   p.mask012 = a->mask012; p.lse = lse;
   p.ctx = reinterpret_cast<const __nv_bfloat16*>(ctx);
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   p.dkv = dkv_scratch;
+  p.dq32 = dq32;
   {
     // profiling aid only: RF_DEBUG_NO_DKV_ATOMICS=1 drops the dK/dV accumulation (wrong results) so
     // that the cost of the red.add traffic can be measured in isolation
@@ -413,15 +444,24 @@ extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const fl
   p.B = a->B; p.L = a->L; p.H = a->H;
   p.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   p.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
-  p.drop_seed = a->drop_seed;
   const int tiles = (a->L + 127) / 128;
-  band_attn_bwd_kernel<<<a->B * a->H * tiles, AB_THREADS, AB_SMEM, stream>>>(*tm64, *tm16, *tmdo, p);
-  int rc = check_launch("rf_band_attn_bwd");
-  if (rc) return rc;
-  const long long T = static_cast<long long>(B) * L;
+  for (int k = 0; k < nseg; ++k) {
+    const int lo = -a->w + 65 * k, hi = lo + 64;
+    p.shift = lo + 32;
+    p.hi_cut = hi > a->w ? hi - a->w : 0;
+    p.use_cls = k == 0;
+    p.drop_seed = nseg == 1 ? a->drop_seed : a->drop_seed + 0x9E3779B97F4A7C15ull * k;
+    band_attn_bwd_kernel<<<a->B * a->H * tiles, AB_THREADS, AB_SMEM, stream>>>(*tm64, *tm16, *tmdo, p);
+    int rc = check_launch("rf_band_attn_bwd");
+    if (rc) return rc;
+  }
   long long grid = (T * (2 * E / 4) + 255) / 256;
   if (grid > sm_count() * 16) grid = sm_count() * 16;
   fold_dkv_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(reinterpret_cast<const float4*>(dkv_scratch),
                                                              reinterpret_cast<__nv_bfloat16*>(dqkv), T, E);
-  return check_launch("rf_band_attn_bwd/fold");
+  int rc = check_launch("rf_band_attn_bwd/fold");
+  if (rc || !dq32) return rc;
+  fold_dq_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(reinterpret_cast<const float4*>(dq32),
+                                                            reinterpret_cast<__nv_bfloat16*>(dqkv), T, E);
+  return check_launch("rf_band_attn_bwd/fold_dq");
 }

@@ -46,6 +46,10 @@ struct AttnFwdParams {
   __nv_bfloat16* ctx;
   float* lse;
   int B, L, H;
+  // window segment (windows wider than 2*W+1 keys are covered by several launches whose outputs are merged
+  // through their log-sum-exps): keys are shifted by `shift` rows, the top `hi_cut` offsets of the band are
+  // cut, the CLS column is only part of segment 0, and an empty row reports lse = -inf instead of 0
+  int shift, hi_cut, use_cls, lse_neg_inf;
   float drop_scale;
   uint32_t drop_thresh;
   uint64_t drop_seed;
@@ -90,10 +94,10 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
   for (int c = tid; c < NT; c += ATT_THREADS) {
     uint8_t f = 0;
     if (c < NK) {
-      const int j = i0 - W + c;
+      const int j = i0 - W + p.shift + c;
       f = (j >= 0 && j < p.L && mrow[j] == 1) ? 1 : 0;
     } else if (c == NK) {
-      f = (mrow[0] == 2) ? 1 : 0;
+      f = (p.use_cls && mrow[0] == 2) ? 1 : 0;
     }
     kflag[c] = f;
   }
@@ -101,6 +105,7 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const int band_hi = 2 * W - p.hi_cut;   // last in-band column offset of a row
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_load, C::Q_BYTES + 2 * C::KV_BYTES);
@@ -108,8 +113,8 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
     for (int c = 0; c < 2; ++c) tma_load_3d(sQ + c * 8192, &tm64, bar_load, h * HEAD_DIM, i0 + c * 64, b);
 #pragma unroll
     for (int c = 0; c < NK / 64; ++c) {
-      tma_load_3d(sK + c * 8192, &tm64, bar_load, E + h * HEAD_DIM, i0 - W + c * 64, b);
-      tma_load_3d(sV + c * 8192, &tm64, bar_load, 2 * E + h * HEAD_DIM, i0 - W + c * 64, b);
+      tma_load_3d(sK + c * 8192, &tm64, bar_load, E + h * HEAD_DIM, i0 - W + p.shift + c * 64, b);
+      tma_load_3d(sV + c * 8192, &tm64, bar_load, 2 * E + h * HEAD_DIM, i0 - W + p.shift + c * 64, b);
     }
     tma_load_3d(sK + NK * 128, &tm16, bar_load, E + h * HEAD_DIM, 0, b);
     tma_load_3d(sV + NK * 128, &tm16, bar_load, 2 * E + h * HEAD_DIM, 0, b);
@@ -150,7 +155,7 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int c = cc * 32 + j;
-        const bool ok = kflag[c] && (c >= r) && (c <= r + 2 * W);
+        const bool ok = kflag[c] && (c >= r) && (c <= r + band_hi);
         m = ok ? fmaxf(m, __uint_as_float(v[j])) : m;
       }
     }
@@ -176,7 +181,7 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int c = cc * 32 + j;
-        const bool ok = row_valid && kflag[c] && (c >= r) && (c <= r + 2 * W);
+        const bool ok = row_valid && kflag[c] && (c >= r) && (c <= r + band_hi);
         const float e = ok ? exp2f(__uint_as_float(v[j]) * LOG2E - m2) : 0.0f;
         l += e;
         pr[j] = e;
@@ -262,7 +267,8 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
       }
     }
   }
-  if (i < p.L) p.lse[(static_cast<size_t>(b) * p.H + h) * p.L + i] = (l > 0.0f) ? (m + logf(l)) : 0.0f;
+  if (i < p.L)
+    p.lse[(static_cast<size_t>(b) * p.H + h) * p.L + i] = (l > 0.0f) ? (m + logf(l)) : (p.lse_neg_inf ? -INFINITY : 0.0f);
 
   tc_fence_before();
   __syncthreads();
@@ -272,8 +278,78 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
   }
 }
 
-template <int W>
-static int launch_attn_fwd(const rf_attn_args* a, void* ctx, float* lse, cudaStream_t stream) {
+// Running merge of window segments: acc / lse_acc hold the softmax-weighted output and log-sum-exp of the
+// segments seen so far; (part, lse_part) is the next one.  grid over (token, head, 8-dim group).
+__global__ void __launch_bounds__(256)
+attn_merge_kernel(float* __restrict__ acc, float* __restrict__ lse_acc, const __nv_bfloat16* __restrict__ part,
+                  const float* __restrict__ lse_part, const uint8_t* __restrict__ mask012, __nv_bfloat16* __restrict__ ctx,
+                  float* __restrict__ lse_out, int B, int L, int H, int first, int last) {
+  const long long idx = blockIdx.x * 256ll + threadIdx.x;
+  const long long total = static_cast<long long>(B) * L * H * 8;
+  if (idx >= total) return;
+  const int g = static_cast<int>(idx & 7);
+  const int h = static_cast<int>((idx >> 3) % H);
+  const long long t = idx / (8ll * H);            // token index b * L + i
+  const int b = static_cast<int>(t / L), i = static_cast<int>(t % L);
+  if (i == 0 && mask012[static_cast<size_t>(b) * L] == 2) return;   // global row: written by rf_global_attn_fwd
+  const int E = H * HEAD_DIM;
+  const size_t o = static_cast<size_t>(t) * E + h * HEAD_DIM + g * 8;
+  const size_t lo = (static_cast<size_t>(b) * H + h) * L + i;
+  const float lp = lse_part[lo];
+  const uint4 raw = *reinterpret_cast<const uint4*>(part + o);
+  float v[8];
+  {
+    const float2 a0 = unpack_bf16(raw.x), a1 = unpack_bf16(raw.y), a2 = unpack_bf16(raw.z), a3 = unpack_bf16(raw.w);
+    v[0] = a0.x; v[1] = a0.y; v[2] = a1.x; v[3] = a1.y; v[4] = a2.x; v[5] = a2.y; v[6] = a3.x; v[7] = a3.y;
+  }
+  float la = first ? -INFINITY : lse_acc[lo];
+  const float mx = fmaxf(la, lp);
+  float wa = 0.f, wp = 0.f, ln = -INFINITY;
+  if (mx > -INFINITY) {
+    const float ea = __expf(la - mx), ep = __expf(lp - mx);
+    ln = mx + __logf(ea + ep);
+    wa = ea / (ea + ep); wp = ep / (ea + ep);
+  }
+  float r[8];
+  if (first) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = wp * v[e];
+  } else {
+    const float4 c0 = *reinterpret_cast<const float4*>(acc + o), c1 = *reinterpret_cast<const float4*>(acc + o + 4);
+    const float a[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = wa * a[e] + wp * v[e];
+  }
+  if (last) {
+    uint4 out;
+    out.x = pack_bf16(r[0], r[1]); out.y = pack_bf16(r[2], r[3]); out.z = pack_bf16(r[4], r[5]); out.w = pack_bf16(r[6], r[7]);
+    *reinterpret_cast<uint4*>(ctx + o) = out;
+    if (g == 0) lse_out[lo] = (ln > -INFINITY) ? ln : 0.0f;
+  } else {
+    *reinterpret_cast<float4*>(acc + o) = make_float4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<float4*>(acc + o + 4) = make_float4(r[4], r[5], r[6], r[7]);
+    if (g == 0) lse_acc[lo] = ln;
+  }
+}
+
+struct AttnSegment { int shift, hi_cut, use_cls; };
+
+// Segments of a band of half-width w for the W = 32 kernels (65 key offsets each): offsets [-w + 65k, -w + 65k + 64]
+// clipped to [-w, w]; the kernel's own band is centred, so segment k is run with keys shifted by its centre.
+static int attn_segments(int w, AttnSegment* seg) {
+  const int n = (2 * w + 1 + 64) / 65;
+  for (int k = 0; k < n; ++k) {
+    const int lo = -w + 65 * k, hi = lo + 64;
+    seg[k].shift = lo + 32;
+    seg[k].hi_cut = hi > w ? hi - w : 0;
+    seg[k].use_cls = k == 0;
+  }
+  return n;
+}
+
+static int launch_attn_fwd32(const rf_attn_args* a, void* ctx, float* lse, const AttnSegment& sg, int lse_neg_inf,
+                             uint64_t seed, cudaStream_t stream) {
+  constexpr int W = 32;
   using C = AttnFwdCfg<W>;
   auto kern = band_attn_fwd_kernel<W>;
   static bool attr_set = false;
@@ -290,9 +366,10 @@ static int launch_attn_fwd(const rf_attn_args* a, void* ctx, float* lse, cudaStr
   p.ctx = reinterpret_cast<__nv_bfloat16*>(ctx);
   p.lse = lse;
   p.B = a->B; p.L = a->L; p.H = a->H;
+  p.shift = sg.shift; p.hi_cut = sg.hi_cut; p.use_cls = sg.use_cls; p.lse_neg_inf = lse_neg_inf;
   p.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   p.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
-  p.drop_seed = a->drop_seed;
+  p.drop_seed = seed;
   const int tiles = (a->L + 127) / 128;
   kern<<<a->B * a->H * tiles, ATT_THREADS, C::TOTAL, stream>>>(*tm64, *tm16, p);
   return check_launch("rf_band_attn_fwd");
@@ -300,17 +377,40 @@ static int launch_attn_fwd(const rf_attn_args* a, void* ctx, float* lse, cudaStr
 
 }  // namespace rf
 
+extern "C" long long rf_band_attn_ws_bytes(int B, int L, int H, int w) {
+  if (w <= 32) return 0;
+  const long long T = static_cast<long long>(B) * L, E = static_cast<long long>(H) * rf::HEAD_DIM;
+  // forward: fp32 accumulator [T,E] + bf16 segment output [T,E] + 2 x lse [B,H,L];  backward: fp32 dQ scratch [T,E]
+  return T * E * 4 + T * E * 2 + 2ll * B * H * L * 4 + 256;
+}
+
 extern "C" int rf_band_attn_fwd(const rf_attn_args* a, void* ctx, float* lse, rf_stream_t stream_) {
   using namespace rf;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   RF_REQUIRE(a && ctx && lse, "rf_band_attn_fwd: null argument");
   RF_REQUIRE(a->D == HEAD_DIM, "rf_band_attn_fwd: head_dim %d unsupported (64 only)", a->D);
   RF_REQUIRE(a->B > 0 && a->L >= 16 && a->H > 0, "rf_band_attn_fwd: bad shape B=%d L=%d H=%d", a->B, a->L, a->H);
-  switch (a->w) {
-    case 32: return launch_attn_fwd<32>(a, ctx, lse, stream);
-    case 64: return launch_attn_fwd<64>(a, ctx, lse, stream);
-    case 128: return launch_attn_fwd<128>(a, ctx, lse, stream);
-    default:
-      return set_error(RF_ERR_INVALID, "rf_band_attn_fwd: one-sided window %d unsupported (32, 64, 128)", a->w);
+  RF_REQUIRE(a->w >= 32 && a->w % 32 == 0 && a->w <= 256,
+             "rf_band_attn_fwd: one-sided window %d unsupported (multiples of 32 up to 256)", a->w);
+  AttnSegment seg[16];
+  const int nseg = attn_segments(a->w, seg);
+  if (nseg == 1) return launch_attn_fwd32(a, ctx, lse, seg[0], 0, a->drop_seed, stream);
+  RF_REQUIRE(a->ws != nullptr, "rf_band_attn_fwd: windows wider than 64 need a workspace (rf_band_attn_ws_bytes)");
+  const size_t T = static_cast<size_t>(a->B) * a->L, E = static_cast<size_t>(a->H) * HEAD_DIM;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(a->ws);
+  float* acc = reinterpret_cast<float*>(ws);
+  __nv_bfloat16* part = reinterpret_cast<__nv_bfloat16*>(ws + T * E * 4);
+  float* lse_part = reinterpret_cast<float*>(ws + T * E * 6);
+  float* lse_acc = lse_part + static_cast<size_t>(a->B) * a->H * a->L;
+  const long long total = static_cast<long long>(T) * a->H * 8;
+  for (int k = 0; k < nseg; ++k) {
+    int rc = launch_attn_fwd32(a, part, lse_part, seg[k], 1, a->drop_seed + 0x9E3779B97F4A7C15ull * k, stream);
+    if (rc) return rc;
+    attn_merge_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        acc, lse_acc, part, lse_part, a->mask012, reinterpret_cast<__nv_bfloat16*>(ctx), lse, a->B, a->L, a->H, k == 0,
+        k == nseg - 1);
+    rc = check_launch("rf_band_attn_fwd/merge");
+    if (rc) return rc;
   }
+  return RF_OK;
 }

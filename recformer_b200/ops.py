@@ -150,11 +150,28 @@ def colsum(x, out):
 
 
 # ---------------------------------------------------------------------------------------------
+_ATTN_WS = {}
+
+
+def band_attn_ws(B, L, H, w, device):
+    """Workspace for windows wider than attention_window 64 (cached per shape; None for w == 32)."""
+    nbytes = int(_lib.lib().rf_band_attn_ws_bytes(B, L, H, w))
+    if nbytes == 0:
+        return None
+    key = (B, L, H, w, str(device))
+    ws = _ATTN_WS.get(key)
+    if ws is None:
+        _ATTN_WS.clear()
+        ws = _ATTN_WS[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return ws
+
+
 def _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed):
     a = AttnArgs()
     a.qkv, a.mask012 = qkv.data_ptr(), mask012.data_ptr()
     a.B, a.L, a.H, a.D, a.w = B, L, H, 64, w
     a.drop_p, a.drop_seed = drop_p, drop_seed
+    a.ws = _ptr(band_attn_ws(B, L, H, w, qkv.device))
     return a
 
 

@@ -198,7 +198,8 @@ def dense_band_reference(qkv, mask012, B, L, H, w):
 
 
 @pytest.mark.parametrize("B,L,w,ragged", [(2, 256, 32, False), (3, 1024, 32, True), (2, 128, 32, True),
-                                          (2, 192, 32, True), (2, 512, 64, True), (1, 1024, 128, True)])
+                                          (2, 192, 32, True), (2, 512, 64, True), (1, 1024, 128, True),
+                                          (2, 1024, 256, True), (2, 320, 96, True), (1, 256, 256, False)])
 def test_band_attention_fwd(B, L, w, ragged):
     H = 12
     qkv = rnd(B * L, 3 * H * 64, seed=L + w, scale=1.0)
@@ -346,9 +347,11 @@ def test_cast_and_adamw():
 
 
 # ------------------------------------------------------------------------- attention backward
-@pytest.mark.parametrize("B,L,ragged", [(2, 256, False), (3, 1024, True), (2, 192, True), (2, 128, True)])
-def test_band_attention_bwd(B, L, ragged):
-    H, w = 12, 32
+@pytest.mark.parametrize("B,L,ragged,w", [(2, 256, False, 32), (3, 1024, True, 32), (2, 192, True, 32), (2, 128, True, 32),
+                                          (2, 512, True, 64), (2, 1024, True, 128), (2, 1024, True, 256),
+                                          (2, 320, True, 96)])
+def test_band_attention_bwd(B, L, ragged, w):
+    H = 12
     E = H * 64
     qkv = rnd(B * L, 3 * E, seed=L, scale=1.0)
     qkv[:, :E] *= 0.35
