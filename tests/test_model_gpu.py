@@ -116,14 +116,17 @@ def test_train_step_matches_reference_gradients(goldens):
     print("worst relative grad-norm error", worst)
 
 
-def test_train_gradients_match_oracle_autograd_dense():
-    """Full gradient tensors against the oracle's autograd (1 layer, every parameter)."""
-    cfg_kw = dict(vocab_size=1500, num_hidden_layers=1, attention_window=[64], max_position_embeddings=600)
+@pytest.mark.parametrize("windows,L", [([64], 300), ([128, 256], 700), ([512], 1100)])
+def test_train_gradients_match_oracle_autograd_dense(windows, L):
+    """Full gradient tensors against the oracle's autograd (every parameter); also the wide attention
+    windows of BASELINE config 5 (attention_window 128 / 256 / 512, window-segment kernels)."""
+    cfg_kw = dict(vocab_size=1500, num_hidden_layers=len(windows), attention_window=list(windows),
+                  max_position_embeddings=1200)
     ocfg, cfg, model, sd = build(cfg_kw, sd_seed=5)
     cfg.hidden_dropout_prob = 0.0
     cfg.attention_probs_dropout_prob = 0.0
     model.train()
-    B, L, N = 3, 300, 40
+    B, N = 3, 40
     batch = O.make_batch(ocfg, B, L, seed=2, ragged=True)
     items = O.make_item_table(N, 768, seed=1)
     labels = torch.tensor([3, 17, 39])
