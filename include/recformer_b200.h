@@ -243,6 +243,13 @@ int rf_cosine_ce(const void* pooled_bf16_or_f32, int pooled_is_bf16, const void*
                  int B, long long N, int E, float temp, float* loss, float* dpooled_f32, float* ws,
                  rf_stream_t stream);
 long long rf_cosine_ce_ws_bytes(int B, long long N, int E);
+/* Masked-LM cross entropy of the pretraining head (ref: recformer/models.py:499-510, CrossEntropyLoss with
+ * ignore_index -100 over lm_head scores): logits fp32 [M, ld] (vocabulary V <= ld, ld % 8 == 0; padded columns
+ * ignored), labels int64 [M]; loss (1 float) = mean over the rows with a valid label of (lse - logit[label]);
+ * dlogits (bf16 [M, ld]) = (softmax - onehot) / count, zero for ignored rows / padded columns.  `count` is a
+ * device scalar holding the number of valid rows. */
+int rf_mlm_ce(const float* logits, const int64_t* labels, int M, int V, long long ld, const float* count, float* loss,
+              void* dlogits_bf16, rf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimiser plumbing on the flat parameter buffer: fused AdamW (ref: optimization.py:7-34 uses

@@ -362,6 +362,99 @@ def seqrec_forward(sd, cfg: OracleConfig, batch: Dict[str, Tensor], item_embeddi
 
 
 # ----------------------------------------------------------------------------------------------
+# pretraining step (ref: recformer/models.py:372-520; LM head = HF:1264-1283 LongformerLMHead)
+# ----------------------------------------------------------------------------------------------
+MASK_TOKEN_ID = 50264      # <mask> of the roberta/longformer vocabulary
+
+
+def lm_head_keys(cfg: "OracleConfig") -> List[tuple]:
+    E, V = cfg.hidden_size, cfg.vocab_size
+    return [("lm_head.bias", (V,), "b"), ("lm_head.dense.weight", (E, E), "w"), ("lm_head.dense.bias", (E,), "b"),
+            ("lm_head.layer_norm.weight", (E,), "ln_w"), ("lm_head.layer_norm.bias", (E,), "ln_b"),
+            ("lm_head.decoder.weight", (V, E), "w"), ("lm_head.decoder.bias", (V,), "b")]
+
+
+def make_pretrain_state_dict(cfg: "OracleConfig", seed: int = 0) -> Dict[str, Tensor]:
+    """Encoder weights under `longformer.` + seeded LM-head weights (same conventions as make_state_dict)."""
+    sd = make_state_dict(cfg, seed=seed, prefix="longformer.")
+    rng = np.random.default_rng(seed + 4000)
+    for key, shape, kind in lm_head_keys(cfg):
+        if kind == "w":
+            t = torch.from_numpy(rng.standard_normal(shape, dtype=np.float32) * np.float32(0.02))
+        elif kind == "b":
+            t = torch.from_numpy(rng.standard_normal(shape, dtype=np.float32) * np.float32(0.02))
+        elif kind == "ln_w":
+            t = 1.0 + torch.from_numpy(rng.standard_normal(shape, dtype=np.float32) * np.float32(0.1))
+        else:
+            t = torch.from_numpy(rng.standard_normal(shape, dtype=np.float32) * np.float32(0.1))
+        sd[key] = t
+    return sd
+
+
+def make_pretrain_batch(cfg: "OracleConfig", B: int, La: int, Lb: int, seed: int = 0, mlm_prob: float = 0.15,
+                        mask_token_id: Optional[int] = None) -> Dict[str, Tensor]:
+    """Synthetic batch of LitWrapper.training_step's layout (ref: recformer/models.py:382-405, collator.py:11-242):
+    sequence a (history, ragged, <= La tokens), sequence b (the target item, <= Lb tokens), and their MLM copies
+    (15 % of the real non-CLS tokens replaced by <mask>, labels = original id there, -100 elsewhere)."""
+    a = make_batch(cfg, B, La, seed=seed, ragged=True)
+    b = make_batch(cfg, B, Lb, seed=seed + 7, ragged=True, min_frac=0.25)
+    rng = np.random.default_rng(seed + 3000)
+    mid = min(MASK_TOKEN_ID, cfg.vocab_size - 1) if mask_token_id is None else mask_token_id
+    out = {}
+    for tag, d in (("a", a), ("b", b)):
+        ids = d["input_ids"].numpy()
+        real = d["attention_mask"].numpy().astype(bool)
+        real[:, 0] = False
+        pick = (rng.random(ids.shape) < mlm_prob) & real
+        mlm_ids = np.where(pick, mid, ids)
+        labels = np.where(pick, ids, -100)
+        for k, v in d.items():
+            out[f"{k}_{tag}"] = v
+        out[f"mlm_input_ids_{tag}"] = torch.from_numpy(mlm_ids)
+        out[f"mlm_labels_{tag}"] = torch.from_numpy(labels)
+    return out
+
+
+def lm_head_forward(sd: Dict[str, Tensor], cfg: "OracleConfig", features: Tensor) -> Tensor:
+    """HF:1275-1283: decoder(layer_norm(gelu_erf(dense(x)))); the decoder has its own bias (`lm_head.bias` is
+    an unused parameter in transformers 5.5.0's copy)."""
+    x = F.linear(features, sd["lm_head.dense.weight"], sd["lm_head.dense.bias"])
+    x = gelu_erf(x)
+    x = F.layer_norm(x, (cfg.hidden_size,), sd["lm_head.layer_norm.weight"], sd["lm_head.layer_norm.bias"],
+                     cfg.layer_norm_eps)
+    return F.linear(x, sd["lm_head.decoder.weight"], sd["lm_head.decoder.bias"])
+
+
+def pretrain_forward(sd: Dict[str, Tensor], cfg: "OracleConfig", batch: Dict[str, Tensor], mlm_weight: float = 0.1,
+                     gathered_z: Optional[tuple] = None):
+    """ref: recformer/models.py:382-520 (single process; `gathered_z` = (z1_all, z2_all, rank) emulates the
+    dist.all_gather branch :475-490 with this rank's slot replaced by the live tensors).
+    Returns (loss, cos_sim, correct_num)."""
+    enc = lambda tag, ids: model_forward(
+        sd, cfg, ids, attention_mask=batch[f"attention_mask_{tag}"],
+        global_attention_mask=batch[f"global_attention_mask_{tag}"], token_type_ids=batch[f"token_type_ids_{tag}"],
+        item_position_ids=batch[f"item_position_ids_{tag}"], prefix="longformer.")
+    _, z1 = enc("a", batch["input_ids_a"])
+    _, z2 = enc("b", batch["input_ids_b"])
+    if gathered_z is not None:
+        z1_all, z2_all, rank = gathered_z
+        B = z1.shape[0]
+        z1 = torch.cat([z1_all[: rank * B], z1, z1_all[(rank + 1) * B:]], 0)
+        z2 = torch.cat([z2_all[: rank * B], z2, z2_all[(rank + 1) * B:]], 0)
+    cos_sim = similarity(z1.unsqueeze(1), z2.unsqueeze(0), cfg.temp)
+    labels = torch.arange(cos_sim.shape[0])
+    loss = F.cross_entropy(cos_sim, labels)
+    correct = (cos_sim.argmax(1) == labels).sum()
+    for tag in ("a", "b"):
+        if batch.get(f"mlm_input_ids_{tag}") is not None:
+            hidden, _ = enc(tag, batch[f"mlm_input_ids_{tag}"])
+            scores = lm_head_forward(sd, cfg, hidden)
+            loss = loss + mlm_weight * F.cross_entropy(scores.view(-1, cfg.vocab_size),
+                                                       batch[f"mlm_labels_{tag}"].reshape(-1))
+    return loss, cos_sim, correct
+
+
+# ----------------------------------------------------------------------------------------------
 # metrics (SURVEY.md §8a Spec R; ref: utils.py:76-107)
 # ----------------------------------------------------------------------------------------------
 MAX_VAL = 1e4

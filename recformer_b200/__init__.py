@@ -2,11 +2,11 @@
 
 Mirrors the reference `recformer` package's public names (ref: recformer/__init__.py:1-3) for
 the hot path: RecformerConfig, RecformerModel, RecformerForSeqRec, RecformerTokenizer."""
-__all__ = ["RecformerConfig", "RecformerModel", "RecformerForSeqRec", "RecformerTokenizer", "Ranker", "encode_all_items"]
+__all__ = ["RecformerConfig", "RecformerModel", "RecformerForSeqRec", "RecformerForPretraining", "RecformerTokenizer", "Ranker", "encode_all_items"]
 
 
 def __getattr__(name):
-    if name in ("RecformerConfig", "RecformerModel", "RecformerForSeqRec", "Similarity"):
+    if name in ("RecformerConfig", "RecformerModel", "RecformerForSeqRec", "RecformerForPretraining", "Similarity"):
         from . import models
         return getattr(models, name)
     if name == "RecformerTokenizer":

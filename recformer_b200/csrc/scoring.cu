@@ -542,6 +542,55 @@ ce_row_kernel(float* __restrict__ logits, const int64_t* __restrict__ labels, in
   }
 }
 
+// Masked-LM cross entropy over dense logits [M, ld] fp32 (vocab V <= ld, padded columns ignored):
+//   loss += (lse_row - logit[row, label]) / count   for rows with label >= 0 (ignore_index -100 otherwise)
+//   dlogits[row, :] = (softmax - onehot) / count as bf16 (zero for ignored rows and for padded columns)
+// count = number of rows with a valid label (device scalar).  grid (M), 256 threads, 3 passes over the row.
+__global__ void __launch_bounds__(256)
+mlm_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int V, long long ld,
+              const float* __restrict__ count, float* __restrict__ loss, __nv_bfloat16* __restrict__ dlogits) {
+  const long long row_off = static_cast<long long>(blockIdx.x) * ld;
+  const float* row = logits + row_off;
+  __nv_bfloat16* drow = dlogits + row_off;
+  const long long lab = labels[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (lab < 0 || lab >= V) {   // ignored row
+    for (long long n = tid * 8; n < ld; n += 256 * 8) *reinterpret_cast<uint4*>(drow + n) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  __shared__ float red[8];
+  float m = -INFINITY;
+  for (int n = tid; n < V; n += 256) m = fmaxf(m, row[n]);
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float l = 0.f;
+  for (int n = tid; n < V; n += 256) l += __expf(row[n] - m);
+  l = warp_sum(l);
+  if (lane == 0) red[warp] = l;
+  __syncthreads();
+  l = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) l += red[w];
+  const float lse = m + logf(l);
+  const float inv = 1.0f / fmaxf(*count, 1.0f);
+  if (tid == 0) atomicAdd(loss, (lse - row[lab]) * inv);
+  for (long long n0 = tid * 8; n0 < ld; n0 += 256 * 8) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const long long n = n0 + e;
+      v[e] = n < V ? (__expf(row[n] - lse) - (n == lab ? 1.f : 0.f)) * inv : 0.f;
+    }
+    *reinterpret_cast<uint4*>(drow + n0) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
+
 // dxn[b,:] += inv_temp * sum_{n in chunk} dlogit[b,n] * yn[n,:]   grid (chunks, B), 256 threads
 __global__ void __launch_bounds__(256)
 ce_dxn_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ yn, long long N, int chunk,
@@ -782,4 +831,14 @@ extern "C" int rf_cosine_ce(const void* pooled, int pooled_is_bf16, const void* 
   else
     ce_norm_bwd_kernel<false><<<B, 256, 0, stream>>>(pooled, dxn, dpooled);
   return check_launch("rf_cosine_ce/norm_bwd");
+}
+
+extern "C" int rf_mlm_ce(const float* logits, const int64_t* labels, int M, int V, long long ld, const float* count,
+                         float* loss, void* dlogits_bf16, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(logits && labels && count && loss && dlogits_bf16 && M > 0 && V > 0, "rf_mlm_ce: bad argument");
+  RF_REQUIRE(ld >= V && ld % 8 == 0, "rf_mlm_ce: ld=%lld must be >= V and a multiple of 8", ld);
+  RF_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), stream));
+  mlm_ce_kernel<<<M, 256, 0, stream>>>(logits, labels, V, ld, count, loss, reinterpret_cast<__nv_bfloat16*>(dlogits_bf16));
+  return check_launch("rf_mlm_ce");
 }

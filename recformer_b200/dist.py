@@ -94,10 +94,12 @@ class GradSync:
     for every collective.  Gradients are SUMMED; pass `grad_scale=1/world` to `FusedAdamW.step()`.
     """
 
-    def __init__(self, model, group=None):
+    def __init__(self, model, group=None, passes_per_step: int = 1):
         enc = getattr(model, "longformer", model)
         self.engine = enc._engine
         self.group = group
+        self.passes_per_step = passes_per_step   # encoder backward passes per optimizer step (pretraining: 4)
+        self._seen = {}
         self._works = []
         self._covered = []
         self.engine.grad_hook = self.on_layer
@@ -117,6 +119,9 @@ class GradSync:
 
     def on_layer(self, layer: int) -> None:
         if not self._active():
+            return
+        self._seen[layer] = self._seen.get(layer, 0) + 1
+        if self._seen[layer] < self.passes_per_step:      # gradients of this layer are still being accumulated
             return
         g = self.engine.params.grad
         for a, b in self.layer_ranges(layer):
@@ -140,3 +145,4 @@ class GradSync:
             w.wait()
         self._works.clear()
         self._covered.clear()
+        self._seen.clear()

@@ -377,3 +377,158 @@ class RecformerForSeqRec(nn.Module):
         cand = torch.cat((labels.unsqueeze(-1), neg), dim=-1)
         logits = self.similarity_score(pooler_output, cand)
         return nn.functional.cross_entropy(logits, torch.zeros_like(labels))
+
+
+# --------------------------------------------------------------------------------------------
+# pretraining (ref: recformer/models.py:372-520)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class RecformerPretrainingOutput:
+    """ref: recformer/models.py:57-65."""
+    cl_correct_num: float = 0.0
+    cl_total_num: float = 1e-5
+    loss: Optional[torch.Tensor] = None
+    logits: torch.Tensor = None
+    hidden_states: Optional[Tuple[torch.Tensor]] = None
+    attentions: Optional[Tuple[torch.Tensor]] = None
+    global_attentions: Optional[Tuple[torch.Tensor]] = None
+
+
+class _LMHead(nn.Module):
+    """Parameter container of HF LongformerLMHead (HF:1264-1283): dense, layer_norm, decoder (+ the unused
+    `bias` parameter that transformers 5.5.0 keeps in the state dict)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.layer_norm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.decoder = nn.Linear(config.hidden_size, config.vocab_size)
+        self.bias = nn.Parameter(torch.zeros(config.vocab_size))
+
+
+class _LMHeadCEFunction(torch.autograd.Function):
+    """mean CE(decoder(LN(gelu(dense(rows)))), labels) over the MASKED rows only (the reference scores every
+    position — (B,L,50265) fp32 — and lets ignore_index drop 85 % of it; same loss, ~6.7x less work).
+    All GEMMs run on the tcgen05 kernel; the vocabulary is padded to a multiple of 32 columns."""
+
+    @staticmethod
+    def forward(ctx, rows, labels, Wd, bd, lnw, lnb, Wdec, bdec, eps):
+        M, E = rows.shape
+        V = Wdec.shape[0]
+        Vp = (V + 31) // 32 * 32
+        dev = rows.device
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        x = rows.detach().to(torch.bfloat16).contiguous()
+        Wd16 = Wd.detach().to(torch.bfloat16).contiguous()
+        u, g = torch.empty(M, E, **bf), torch.empty(M, E, **bf)
+        ops.gemm(x, Wd16, out=u, bias=bd.detach().contiguous(), epi=ops.EPI_GELU, out2=g)   # u = gelu', g = gelu
+        g32 = g.float()
+        y = torch.empty(M, E, **bf)
+        stats = torch.empty(M, 2, dtype=torch.float32, device=dev)
+        ops.layernorm_fwd(g32, lnw.detach().contiguous(), lnb.detach().contiguous(), eps, out=y, stats=stats)
+        Wdec16 = torch.zeros(Vp, E, **bf)
+        Wdec16[:V] = Wdec.detach()
+        bpad = torch.zeros(Vp, dtype=torch.float32, device=dev)
+        bpad[:V] = bdec.detach()
+        logits = torch.empty(M, Vp, dtype=torch.float32, device=dev)
+        ops.gemm(y, Wdec16, out=logits, bias=bpad)
+        loss, dlogits = ops.mlm_ce(logits, labels.contiguous(), V)
+        del logits
+        ctx.save_for_backward(x, Wd16, u, g32, stats, y, Wdec16, dlogits, lnw.detach())
+        ctx.V = V
+        return loss.squeeze(0)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, Wd16, u, g32, stats, y, Wdec16, dlogits, lnw = ctx.saved_tensors
+        M, E = x.shape
+        V, Vp = ctx.V, Wdec16.shape[0]
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        dlogits = dlogits * gout.to(torch.bfloat16)            # upstream scale (mlm_weight, grad accumulation, ...)
+        dbpad = torch.zeros(Vp, **f32)
+        ops.colsum(dlogits, dbpad)
+        dWdec = torch.zeros(Vp, E, **f32)
+        ops.gemm(dlogits, y, out=dWdec, a_mn_major=True, b_mn_major=True, accumulate=True)
+        dy = torch.empty(M, E, dtype=torch.bfloat16, device=dev)
+        ops.gemm(dlogits, Wdec16, out=dy, b_mn_major=True)
+        dlnw, dlnb = torch.zeros(E, **f32), torch.zeros(E, **f32)
+        dg = ops.layernorm_bwd(dy, g32, stats, lnw.contiguous(), dlnw, dlnb)
+        dpre = (dg * u).contiguous()
+        dbd = torch.zeros(E, **f32)
+        ops.colsum(dpre, dbd)
+        dWd = torch.zeros(E, E, **f32)
+        ops.gemm(dpre, x, out=dWd, a_mn_major=True, b_mn_major=True, accumulate=True)
+        dx = torch.empty(M, E, dtype=torch.bfloat16, device=dev)
+        ops.gemm(dpre, Wd16, out=dx, b_mn_major=True)
+        return dx.float(), None, dWd, dbd, dlnw, dlnb, dWdec[:V], dbpad[:V], None
+
+
+class RecformerForPretraining(nn.Module):
+    """ref: recformer/models.py:372-520 — two-tower in-batch contrastive loss on the CLS vectors of (history a,
+    target item b) plus mlm_weight * masked-LM loss on the masked copies of both; same forward kwargs, output
+    fields and state_dict keys (`longformer.*`, `lm_head.*`)."""
+
+    def __init__(self, config: RecformerConfig):
+        super().__init__()
+        self.config = config
+        self.longformer = RecformerModel(config)
+        self.lm_head = _LMHead(config)
+        self.lm_head.apply(lambda m: _init_weights(m, config.initializer_range))
+        self.sim = Similarity(config)
+
+    def _encode(self, ids, tag, kw):
+        return self.longformer(ids, attention_mask=kw.get(f"attention_mask_{tag}"),
+                               global_attention_mask=kw.get(f"global_attention_mask_{tag}"),
+                               token_type_ids=kw.get(f"token_type_ids_{tag}"),
+                               item_position_ids=kw.get(f"item_position_ids_{tag}"), return_dict=True)
+
+    def _mlm_loss(self, hidden, labels):
+        flat = labels.reshape(-1)
+        idx = torch.nonzero(flat >= 0).squeeze(1)             # masked positions (one host sync per call)
+        if idx.numel() == 0:
+            return hidden.sum() * 0.0
+        rows = hidden.reshape(-1, hidden.shape[-1]).index_select(0, idx)
+        h = self.lm_head
+        return _LMHeadCEFunction.apply(rows, flat.index_select(0, idx), h.dense.weight, h.dense.bias, h.layer_norm.weight,
+                                       h.layer_norm.bias, h.decoder.weight, h.decoder.bias, self.config.layer_norm_eps)
+
+    def forward(self, input_ids_a=None, attention_mask_a=None, global_attention_mask_a=None, token_type_ids_a=None,
+                item_position_ids_a=None, mlm_input_ids_a=None, mlm_labels_a=None, input_ids_b=None,
+                attention_mask_b=None, global_attention_mask_b=None, token_type_ids_b=None, item_position_ids_b=None,
+                mlm_input_ids_b=None, mlm_labels_b=None, head_mask=None, position_ids=None, inputs_embeds=None,
+                labels=None, output_attentions=None, output_hidden_states=None, return_dict=None):
+        import torch.distributed as dist
+        if head_mask is not None or inputs_embeds is not None or position_ids is not None:
+            raise NotImplementedError("recformer_b200: head_mask / inputs_embeds / position_ids are not supported here")
+        kw = dict(attention_mask_a=attention_mask_a, global_attention_mask_a=global_attention_mask_a,
+                  token_type_ids_a=token_type_ids_a, item_position_ids_a=item_position_ids_a,
+                  attention_mask_b=attention_mask_b, global_attention_mask_b=global_attention_mask_b,
+                  token_type_ids_b=token_type_ids_b, item_position_ids_b=item_position_ids_b)
+        batch_size = input_ids_a.size(0)
+        z1 = self._encode(input_ids_a, "a", kw).pooler_output
+        z2 = self._encode(input_ids_b, "b", kw).pooler_output
+        if dist.is_available() and dist.is_initialized() and self.training and dist.get_world_size() > 1:
+            # ref :475-490 — all ranks' CLS vectors as negatives; only this rank's slot carries gradient.
+            # One collective on the packed (2, B, E) buffer instead of two list all_gathers.
+            world, rank = dist.get_world_size(), dist.get_rank()
+            packed = torch.stack([z1.detach(), z2.detach()]).contiguous()
+            gathered = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
+            dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1))
+            parts1 = [gathered[r, 0] if r != rank else z1 for r in range(world)]
+            parts2 = [gathered[r, 1] if r != rank else z2 for r in range(world)]
+            z1, z2 = torch.cat(parts1, 0), torch.cat(parts2, 0)
+        # (B*W)^2 logits on [B*W, 768] vectors: tiny; plain fp32 torch keeps both towers' gradients exact
+        z1n = z1 / z1.norm(dim=-1, keepdim=True).clamp_min(1e-8)
+        z2n = z2 / z2.norm(dim=-1, keepdim=True).clamp_min(1e-8)
+        cos_sim = (z1n @ z2n.t()) / self.config.temp
+        target = torch.arange(cos_sim.size(0), device=cos_sim.device)
+        loss = nn.functional.cross_entropy(cos_sim, target)
+        correct_num = (torch.argmax(cos_sim, 1) == target).sum()
+        if mlm_input_ids_a is not None and mlm_labels_a is not None:
+            hidden = self._encode(mlm_input_ids_a, "a", kw).last_hidden_state
+            loss = loss + self.config.mlm_weight * self._mlm_loss(hidden, mlm_labels_a)
+        if mlm_input_ids_b is not None and mlm_labels_b is not None:
+            hidden = self._encode(mlm_input_ids_b, "b", kw).last_hidden_state
+            loss = loss + self.config.mlm_weight * self._mlm_loss(hidden, mlm_labels_b)
+        return RecformerPretrainingOutput(loss=loss, logits=cos_sim, cl_correct_num=correct_num, cl_total_num=batch_size)

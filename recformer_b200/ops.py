@@ -292,6 +292,18 @@ def cosine_ce(pooled, yn, labels, temp, want_grad=True, ws=None):
     return loss, dpooled
 
 
+def mlm_ce(logits, labels, vocab):
+    """Masked-LM CE (ignore_index -100) over fp32 logits [M, ld]; returns (loss[1], dlogits bf16 [M, ld])."""
+    _req(logits, torch.float32, "logits"), _req(labels, torch.int64, "labels")
+    M, ld = logits.shape
+    count = (labels >= 0).sum().to(torch.float32).reshape(1)
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    dlogits = torch.empty(M, ld, dtype=torch.bfloat16, device=logits.device)
+    check(_lib.lib().rf_mlm_ce(logits.data_ptr(), labels.data_ptr(), M, vocab, ld, count.data_ptr(), loss.data_ptr(),
+                               dlogits.data_ptr(), _stream()), "rf_mlm_ce")
+    return loss, dlogits
+
+
 def cast_bf16(x, out=None):
     _req(x, torch.float32, "x")
     if out is None:

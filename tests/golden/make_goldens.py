@@ -84,6 +84,31 @@ def case_train(name, cfg_kw, B, L, N, sd_seed=0, batch_seed=0):
             "labels": labels, "loss": loss.item(), "grads": grads}
 
 
+def case_pretrain(name, cfg_kw, B, La, Lb, sd_seed=0, batch_seed=0):
+    """RecformerForPretraining (ref: recformer/models.py:372-520): loss, in-batch contrastive logits and
+    gradient fingerprints from the reference's own autograd (eval(): dropout off; `self.training` False also
+    skips the dist.all_gather branch, which the oracle emulates separately)."""
+    ocfg = O.OracleConfig(**cfg_kw)
+    ref = ref_shim.load_reference()
+    m = ref.RecformerForPretraining(ref_shim.reference_config(ocfg)).eval()
+    sd = O.make_pretrain_state_dict(ocfg, seed=sd_seed)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    batch = O.make_pretrain_batch(ocfg, B, La, Lb, seed=batch_seed)
+    out = m(**batch)
+    out.loss.backward()
+    grads = {}
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        gflat = p.grad.reshape(-1)
+        grads[k] = {"norm": gflat.norm().item(), "head": gflat[:32].clone(), "sum": gflat.double().sum().item()}
+    print(f"{name}: loss {out.loss.item():.6f}, {len(grads)} grads, correct {int(out.cl_correct_num)}")
+    return {"cfg": cfg_kw, "B": B, "La": La, "Lb": Lb, "sd_seed": sd_seed, "batch_seed": batch_seed,
+            "loss": out.loss.item(), "logits": out.logits.detach().clone(), "correct": int(out.cl_correct_num),
+            "grads": grads, "state_keys": sorted(m.state_dict().keys())}
+
+
 def case_ranker():
     ru = ref_shim.load_reference_utils()
     import numpy as np
@@ -136,6 +161,13 @@ def case_tokenizer():
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
+    path = os.path.join(OUT, "reference_goldens.pt")
+    if "--only-pretrain" in sys.argv:      # add the pretraining case to the existing fixture file
+        g = torch.load(path, weights_only=False)
+        g["pretrain_small"] = case_pretrain("pretrain_small", small_cfg(), B=4, La=300, Lb=97)
+        torch.save(g, path)
+        print("updated", path, os.path.getsize(path) / 1e6, "MB")
+        return
     g = {}
     g["fwd_small_ragged"] = case_forward("fwd_small_ragged", small_cfg(), B=3, L=200, ragged=True, N=300, hidden_stride=3)
     g["fwd_small_dense"] = case_forward("fwd_small_dense", small_cfg(), B=2, L=256, ragged=False, N=300, hidden_stride=3)
@@ -147,6 +179,7 @@ def main():
     g["fwd_c1_ragged"] = case_forward("fwd_c1_ragged", dict(), B=4, L=1000, ragged=True, N=1000, hidden_stride=50,
                                       batch_seed=3)
     g["train_small"] = case_train("train_small", small_cfg(), B=3, L=200, N=50)
+    g["pretrain_small"] = case_pretrain("pretrain_small", small_cfg(), B=4, La=300, Lb=97)
     g["ranker"] = case_ranker()
     g["tokenizer"] = case_tokenizer()
     path = os.path.join(OUT, "reference_goldens.pt")

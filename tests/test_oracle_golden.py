@@ -86,3 +86,29 @@ def test_position_ids_and_padding_helpers():
     pl, i2, a2, t2, p2, ip2 = O.pad_to_window_size(cfg, ids, torch.ones_like(ids), torch.zeros_like(ids), None,
                                                    torch.zeros_like(ids))
     assert pl == 59 and i2.shape[1] == 64 and int(i2[0, -1]) == 1 and int(ip2[0, -1]) == 1 and int(a2[0, -1]) == 0
+
+
+def test_pretrain_step_matches_reference(goldens):
+    """RecformerForPretraining (ref: recformer/models.py:372-520): loss, contrastive logits and gradient
+    fingerprints of the oracle restatement vs the unmodified reference."""
+    g = goldens["pretrain_small"]
+    ocfg = O.OracleConfig(**g["cfg"])
+    sd = O.make_pretrain_state_dict(ocfg, seed=g["sd_seed"])
+    for v in sd.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    batch = O.make_pretrain_batch(ocfg, g["B"], g["La"], g["Lb"], seed=g["batch_seed"])
+    loss, cos_sim, correct = O.pretrain_forward(sd, ocfg, batch)
+    assert abs(loss.item() - g["loss"]) < 1e-4
+    assert (cos_sim - g["logits"]).abs().max() < 1e-3
+    assert int(correct) == g["correct"]
+    loss.backward()
+    for k, fp in g["grads"].items():
+        got = sd[k].grad
+        if got is None:
+            assert fp["norm"] < 1e-12, k
+            continue
+        assert abs(got.norm().item() - fp["norm"]) <= 2e-3 * fp["norm"] + 1e-7, k
+        assert (got.reshape(-1)[:32] - fp["head"]).abs().max() <= 2e-3 * fp["head"].abs().max() + 1e-6, k
+    # every parameter key of the reference module exists in the oracle's state dict
+    assert set(g["state_keys"]) - set(sd) == set(), set(g["state_keys"]) - set(sd)
