@@ -667,15 +667,18 @@ static int plan_schedule(int B, long long N, ScoreParams* p) {
     if (s < 1) s = 1;
     if (s > n_tiles) s = n_tiles;
     extra = pairs - static_cast<int>(s) * m_tiles;
-    if (extra > 0 && n_tiles >= 8ll * pairs) {
+    if (extra > 0 && n_tiles >= 4ll * pairs) {
       // a leftover pair restarts its top-k list at every segment and so spends more time inserting than a
       // lock-step pair: it also streams its table range from HBM rather than L2.  Measured (4096 x 1M): giving it ~75 % of a
       // lock-step pair's steps minimises the pass time
       static const int pct = getenv("RF_SCORE_EXTRA_PCT") ? atoi(getenv("RF_SCORE_EXTRA_PCT")) : 75;   // tuning aid
       extra_tiles = n_tiles * extra * pct / (100ll * pairs);
-      if (extra_tiles == 0) extra = 0;
-      main_tiles = n_tiles - extra_tiles;
-      extra_steps = (extra_tiles * m_tiles + extra - 1) / extra;
+      if (extra_tiles == 0) {
+        extra = 0;
+      } else {
+        main_tiles = n_tiles - extra_tiles;
+        extra_steps = (extra_tiles * m_tiles + extra - 1) / extra;
+      }
     } else {
       extra = 0;
     }
