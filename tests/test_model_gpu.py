@@ -256,3 +256,37 @@ def test_pretraining_step_matches_oracle_and_reference(goldens):
         worst = max(worst, (k, err), key=lambda t: t[1])
         assert err < 0.1, (k, err)
     print("pretrain: loss", out.loss.item(), "ref", g["loss"], "worst grad", worst)
+
+
+def test_max_length_4096_single_sequence_matches_oracle():
+    """Edge sizes: the position table's maximum (L = 4096 tokens, ref: recformer/models.py:30 + 4098 positions),
+    B = 1, one layer — forward against the CPU oracle; and the same call twice is bit-identical (eval)."""
+    cfg_kw = dict(vocab_size=1500, num_hidden_layers=1, attention_window=[64], max_position_embeddings=4098,
+                  max_token_num=4096)
+    ocfg, cfg, model, sd = build(cfg_kw, sd_seed=3, seqrec=False)
+    model.eval()
+    batch = O.make_batch(ocfg, 1, 4096, seed=9, ragged=False)
+    with torch.no_grad():
+        out = model(**{k: v.to(DEV) for k, v in batch.items()})
+        out2 = model(**{k: v.to(DEV) for k, v in batch.items()})
+        ref_hidden, ref_pooled = O.model_forward(sd, ocfg, **batch)
+    assert out.last_hidden_state.shape == (1, 4096, 768)
+    assert torch.equal(out.last_hidden_state, out2.last_hidden_state)
+    assert (out.pooler_output.cpu() - ref_pooled).abs().max() < 0.1
+    assert (out.last_hidden_state.cpu() - ref_hidden).abs().max() < 0.15
+
+
+def test_short_and_odd_lengths_match_oracle():
+    """Ragged / tiny inputs: L = 1 (only <s>), L = 5, L = 65 (one token over a window): padded to the window
+    internally (ref: recformer/models.py:210-260), output returned at the original length (HF:1228)."""
+    cfg_kw = dict(vocab_size=1500, num_hidden_layers=2, attention_window=[64, 64], max_position_embeddings=600)
+    ocfg, cfg, model, sd = build(cfg_kw, sd_seed=4, seqrec=False)
+    model.eval()
+    for L in (1, 5, 65):
+        batch = O.make_batch(ocfg, 2, L, seed=L, ragged=False)
+        with torch.no_grad():
+            out = model(**{k: v.to(DEV) for k, v in batch.items()})
+            ref_hidden, ref_pooled = O.model_forward(sd, ocfg, **batch)
+        assert out.last_hidden_state.shape == (2, L, 768)
+        assert (out.last_hidden_state.cpu() - ref_hidden).abs().max() < 0.1, L
+        assert (out.pooler_output.cpu() - ref_pooled).abs().max() < 0.1, L
