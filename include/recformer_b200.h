@@ -243,6 +243,14 @@ int rf_cosine_ce(const void* pooled_bf16_or_f32, int pooled_is_bf16, const void*
                  int B, long long N, int E, float temp, float* loss, float* dpooled_f32, float* ws,
                  rf_stream_t stream);
 long long rf_cosine_ce_ws_bytes(int B, long long N, int E);
+/* Candidate scoring (ref: recformer/models.py:539-545 with `candidates`): logits[b,c] = cos(pooled_b,
+ * table[cand[b,c]]) / temp as fp32 [B,C]; pooled fp32 [B,E] (un-normalised), yn = L2-normalised bf16 table [N,E],
+ * cand int64 [B,C].  rf_cosine_candidates_ce is the sampled-softmax loss of :593-597 (label in column 0,
+ * mean CE against target 0) with its gradient w.r.t. pooled; ws >= B*C*4 + B*E*4 + B*8 + 768 bytes. */
+int rf_cosine_candidates(const float* pooled, const void* yn_bf16, const int64_t* cand, int B, int C, long long N, int E,
+                         float temp, float* logits, rf_stream_t stream);
+int rf_cosine_candidates_ce(const float* pooled, const void* yn_bf16, const int64_t* cand, int B, int C, long long N, int E,
+                            float temp, float* loss, float* dpooled_or_null, void* ws, rf_stream_t stream);
 /* Masked-LM cross entropy of the pretraining head (ref: recformer/models.py:499-510, CrossEntropyLoss with
  * ignore_index -100 over lm_head scores): logits fp32 [M, ld] (vocabulary V <= ld, ld % 8 == 0; padded columns
  * ignored), labels int64 [M]; loss (1 float) = mean over the rows with a valid label of (lse - logit[label]);

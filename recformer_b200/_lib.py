@@ -76,6 +76,9 @@ _SIGS = {
                                c_void_p, c_void_p, c_void_p, c_void_p]),
     "rf_topk_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p]),
+    "rf_cosine_candidates": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_float, c_void_p, c_void_p]),
+    "rf_cosine_candidates_ce": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_float, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
     "rf_mlm_ce": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rf_cosine_ce_ws_bytes": (c_ll, [c_int, c_ll, c_int]),
     "rf_cosine_ce": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_void_p, c_void_p,

@@ -620,6 +620,61 @@ ce_dxn_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict
   }
 }
 
+// ---- candidate scoring (ref: recformer/models.py:539-545 with `candidates`, :593-597 sampled softmax) ----
+// logits[b,c] = (x_b / |x_b|) . yn[cand[b,c]] / temp: one warp per (b, c) gathers a bf16 table row (E = 768).
+__global__ void __launch_bounds__(256)
+cand_logits_kernel(const float* __restrict__ pooled, const __nv_bfloat16* __restrict__ yn,
+                   const int64_t* __restrict__ cand, int C, long long N, float inv_temp, float* __restrict__ logits) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* xr = pooled + static_cast<size_t>(b) * 768;
+  float xv[24];
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float4 a = *reinterpret_cast<const float4*>(xr + (k * 32 + lane) * 8);
+    const float4 c = *reinterpret_cast<const float4*>(xr + (k * 32 + lane) * 8 + 4);
+    xv[k * 8 + 0] = a.x; xv[k * 8 + 1] = a.y; xv[k * 8 + 2] = a.z; xv[k * 8 + 3] = a.w;
+    xv[k * 8 + 4] = c.x; xv[k * 8 + 5] = c.y; xv[k * 8 + 6] = c.z; xv[k * 8 + 7] = c.w;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q += xv[k * 8 + e] * xv[k * 8 + e];
+  }
+  const float scale = inv_temp / fmaxf(sqrtf(warp_sum(q)), 1e-8f);
+  for (int c = blockIdx.x * 8 + warp; c < C; c += gridDim.x * 8) {
+    long long id = cand[static_cast<size_t>(b) * C + c];
+    id = id < 0 ? 0 : (id >= N ? N - 1 : id);
+    const uint4* yr = reinterpret_cast<const uint4*>(yn + id * 768);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const uint4 raw = yr[k * 32 + lane];
+      const float2 y0 = unpack_bf16(raw.x), y1 = unpack_bf16(raw.y), y2 = unpack_bf16(raw.z), y3 = unpack_bf16(raw.w);
+      acc += xv[k * 8 + 0] * y0.x + xv[k * 8 + 1] * y0.y + xv[k * 8 + 2] * y1.x + xv[k * 8 + 3] * y1.y +
+             xv[k * 8 + 4] * y2.x + xv[k * 8 + 5] * y2.y + xv[k * 8 + 6] * y3.x + xv[k * 8 + 7] * y3.y;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) logits[static_cast<size_t>(b) * C + c] = acc * scale;
+  }
+}
+
+// dxn[b,:] = inv_temp * sum_c dlogit[b,c] * yn[cand[b,c],:]   grid (B), 256 threads (3 columns each)
+__global__ void __launch_bounds__(256)
+cand_dxn_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ yn, const int64_t* __restrict__ cand,
+                int C, long long N, float inv_temp, float* __restrict__ dxn) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int c = 0; c < C; ++c) {
+    long long id = cand[static_cast<size_t>(b) * C + c];
+    id = id < 0 ? 0 : (id >= N ? N - 1 : id);
+    const float g = dlogits[static_cast<size_t>(b) * C + c];
+    const __nv_bfloat16* yr = yn + id * 768;
+    a0 += g * __bfloat162float(yr[tid]);
+    a1 += g * __bfloat162float(yr[256 + tid]);
+    a2 += g * __bfloat162float(yr[512 + tid]);
+  }
+  float* o = dxn + static_cast<size_t>(b) * 768;
+  o[tid] = a0 * inv_temp; o[256 + tid] = a1 * inv_temp; o[512 + tid] = a2 * inv_temp;
+}
+
 // dx = (dxn - xh (xh . dxn)) / max(|x|, eps);  grid (B), 256 threads (3 elements each)
 template <bool IN_BF16>
 __global__ void __launch_bounds__(256)
@@ -844,4 +899,43 @@ extern "C" int rf_mlm_ce(const float* logits, const int64_t* labels, int M, int 
   RF_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), stream));
   mlm_ce_kernel<<<M, 256, 0, stream>>>(logits, labels, V, ld, count, loss, reinterpret_cast<__nv_bfloat16*>(dlogits_bf16));
   return check_launch("rf_mlm_ce");
+}
+
+// logits[b,c] = cos(pooled_b, table[cand[b,c]]) / temp over the pre-normalised bf16 table.
+extern "C" int rf_cosine_candidates(const float* pooled, const void* yn, const int64_t* cand, int B, int C, long long N,
+                                    int E, float temp, float* logits, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(pooled && yn && cand && logits && B > 0 && C > 0 && N > 0, "rf_cosine_candidates: bad argument");
+  RF_REQUIRE(E == 768, "rf_cosine_candidates: hidden size %d unsupported (768)", E);
+  int gx = (C + 7) / 8;
+  if (gx > 64) gx = 64;
+  cand_logits_kernel<<<dim3(gx, B), 256, 0, stream>>>(pooled, reinterpret_cast<const __nv_bfloat16*>(yn), cand, C, N,
+                                                       1.0f / temp, logits);
+  return check_launch("rf_cosine_candidates");
+}
+
+// Sampled-softmax CE (ref: recformer/models.py:593-597): loss = mean_b CE(logits[b,:], target 0) with the label in
+// column 0 of `cand`; dpooled = gradient w.r.t. the un-normalised pooled vector.  ws: B*C*4 + B*E*4 + 8*B + 256 bytes.
+extern "C" int rf_cosine_candidates_ce(const float* pooled, const void* yn, const int64_t* cand, int B, int C, long long N,
+                                       int E, float temp, float* loss, float* dpooled, void* ws_, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(pooled && yn && cand && loss && ws_ && B > 0 && C > 0, "rf_cosine_candidates_ce: bad argument");
+  uint8_t* ws = reinterpret_cast<uint8_t*>(ws_);
+  float* logits = reinterpret_cast<float*>(ws);
+  size_t off = (static_cast<size_t>(B) * C * 4 + 255) & ~size_t(255);
+  float* dxn = reinterpret_cast<float*>(ws + off);
+  off += (static_cast<size_t>(B) * E * 4 + 255) & ~size_t(255);
+  int64_t* zeros = reinterpret_cast<int64_t*>(ws + off);
+  int rc = rf_cosine_candidates(pooled, yn, cand, B, C, N, E, temp, logits, stream_);
+  if (rc) return rc;
+  RF_CUDA(cudaMemsetAsync(zeros, 0, static_cast<size_t>(B) * 8, stream));
+  RF_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), stream));
+  ce_row_kernel<<<B, 256, 0, stream>>>(logits, zeros, B, C, loss);
+  rc = check_launch("rf_cosine_candidates_ce/row");
+  if (rc || dpooled == nullptr) return rc;
+  cand_dxn_kernel<<<B, 256, 0, stream>>>(logits, reinterpret_cast<const __nv_bfloat16*>(yn), cand, C, N, 1.0f / temp, dxn);
+  rc = check_launch("rf_cosine_candidates_ce/dxn");
+  if (rc) return rc;
+  ce_norm_bwd_kernel<false><<<B, 256, 0, stream>>>(pooled, dxn, dpooled);
+  return check_launch("rf_cosine_candidates_ce/norm_bwd");
 }

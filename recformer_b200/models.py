@@ -287,6 +287,21 @@ class _CosineCEFunction(torch.autograd.Function):
         return dpooled * g, None, None, None
 
 
+class _CandidateCEFunction(torch.autograd.Function):
+    """Sampled-softmax CE over (label, negatives) candidates (ref: recformer/models.py:593-597)."""
+
+    @staticmethod
+    def forward(ctx, pooled, yn, cand, temp):
+        loss, dpooled = ops.cosine_candidates_ce(pooled.detach().float().contiguous(), yn, cand.contiguous(), temp)
+        ctx.save_for_backward(dpooled)
+        return loss.squeeze(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dpooled,) = ctx.saved_tensors
+        return dpooled * g, None, None, None
+
+
 class Similarity(nn.Module):
     """ref: recformer/models.py:358-369 — cos(x, y) / temp on broadcastable (B,1,E) x (1|B,N,E)."""
 
@@ -335,7 +350,10 @@ class RecformerForSeqRec(nn.Module):
         if candidates is None:
             xn = ops.normalize_rows(pooler_output.detach().contiguous())
             return ops.cosine_logits(xn, self.normalized_items(), self.config.temp)
-        candidate_embeddings = self.item_embedding(candidates)       # (B, C, E) gather (torch plumbing)
+        if candidates.dim() == 2 and pooler_output.is_cuda:          # gather + dot fused: no (B, C, E) tensor
+            return ops.cosine_candidates(pooler_output.detach().float().contiguous(), self.normalized_items(),
+                                         candidates.to(torch.int64).contiguous(), self.config.temp)
+        candidate_embeddings = self.item_embedding(candidates)
         return self.sim(pooler_output.unsqueeze(1), candidate_embeddings)
 
     @torch.no_grad()
@@ -374,9 +392,8 @@ class RecformerForSeqRec(nn.Module):
         # sampled softmax (ref: :593-597) — negatives drawn on the device instead of CPU + H2D
         neg = torch.randint(0, self.config.item_num, (batch_size, self.config.finetune_negative_sample_size),
                             device=labels.device)
-        cand = torch.cat((labels.unsqueeze(-1), neg), dim=-1)
-        logits = self.similarity_score(pooler_output, cand)
-        return nn.functional.cross_entropy(logits, torch.zeros_like(labels))
+        cand = torch.cat((labels.unsqueeze(-1), neg), dim=-1).to(torch.int64)
+        return _CandidateCEFunction.apply(pooler_output, self.normalized_items(), cand, self.config.temp)
 
 
 # --------------------------------------------------------------------------------------------

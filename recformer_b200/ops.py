@@ -292,6 +292,31 @@ def cosine_ce(pooled, yn, labels, temp, want_grad=True, ws=None):
     return loss, dpooled
 
 
+def cosine_candidates(pooled, yn, cand, temp):
+    """logits[b,c] = cos(pooled_b, table[cand[b,c]]) / temp (fp32 [B,C]) over the normalised bf16 table."""
+    _req(pooled, torch.float32, "pooled"), _req(yn, torch.bfloat16, "yn"), _req(cand, torch.int64, "candidates")
+    B, E = pooled.shape
+    C = cand.shape[1]
+    logits = torch.empty(B, C, dtype=torch.float32, device=pooled.device)
+    check(_lib.lib().rf_cosine_candidates(pooled.data_ptr(), yn.data_ptr(), cand.data_ptr(), B, C, yn.shape[0], E, temp,
+                                          logits.data_ptr(), _stream()), "rf_cosine_candidates")
+    return logits
+
+
+def cosine_candidates_ce(pooled, yn, cand, temp, want_grad=True):
+    """Sampled-softmax CE (label in column 0 of cand); returns (loss[1], dpooled fp32 [B,E] or None)."""
+    _req(pooled, torch.float32, "pooled"), _req(yn, torch.bfloat16, "yn"), _req(cand, torch.int64, "candidates")
+    B, E = pooled.shape
+    C = cand.shape[1]
+    ws = torch.empty(B * C * 4 + B * E * 4 + B * 8 + 1024, dtype=torch.uint8, device=pooled.device)
+    loss = torch.empty(1, dtype=torch.float32, device=pooled.device)
+    dpooled = torch.empty(B, E, dtype=torch.float32, device=pooled.device) if want_grad else None
+    check(_lib.lib().rf_cosine_candidates_ce(pooled.data_ptr(), yn.data_ptr(), cand.data_ptr(), B, C, yn.shape[0], E, temp,
+                                             loss.data_ptr(), _ptr(dpooled), ws.data_ptr(), _stream()),
+          "rf_cosine_candidates_ce")
+    return loss, dpooled
+
+
 def mlm_ce(logits, labels, vocab):
     """Masked-LM CE (ignore_index -100) over fp32 logits [M, ld]; returns (loss[1], dlogits bf16 [M, ld])."""
     _req(logits, torch.float32, "logits"), _req(labels, torch.int64, "labels")

@@ -328,6 +328,25 @@ def test_cosine_ce_loss_and_grad():
     assert relerr(dp, pf.grad) < 2e-2
 
 
+def test_candidate_scoring_and_sampled_softmax():
+    """ref: recformer/models.py:539-545 (candidates) and :593-597 (label + sampled negatives, CE against 0)."""
+    B, N, E, C = 9, 3000, 768, 1001
+    pooled = rnd(B, E, seed=1, dtype=torch.float32) * 3
+    table = rnd(N, E, seed=2, dtype=torch.float32)
+    yn = ops.normalize_rows(table)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    cand = torch.randint(0, N, (B, C), device=DEV, generator=g)
+    logits = ops.cosine_candidates(pooled, yn, cand, 0.05)
+    xr = pooled.clone().requires_grad_(True)
+    ref_logits = torch.nn.functional.cosine_similarity(xr[:, None, :], yn.float()[cand], dim=-1) / 0.05
+    assert (logits - ref_logits).abs().max() < 2e-3
+    ref_loss = torch.nn.functional.cross_entropy(ref_logits, torch.zeros(B, dtype=torch.long, device=DEV))
+    ref_loss.backward()
+    loss, dpooled = ops.cosine_candidates_ce(pooled, yn, cand, 0.05)
+    assert abs(loss.item() - ref_loss.item()) < 1e-3
+    assert relerr(dpooled, xr.grad) < 1e-3
+
+
 def test_cast_and_adamw():
     n = 4096 * 3
     p = rnd(n, seed=1, dtype=torch.float32)

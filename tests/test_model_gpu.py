@@ -290,3 +290,44 @@ def test_short_and_odd_lengths_match_oracle():
         assert out.last_hidden_state.shape == (2, L, 768)
         assert (out.last_hidden_state.cpu() - ref_hidden).abs().max() < 0.1, L
         assert (out.pooler_output.cpu() - ref_pooled).abs().max() < 0.1, L
+
+
+def test_sampled_softmax_and_candidates_match_oracle():
+    """The reference's default finetune loss (finetune.py:183 finetune_negative_sample_size=1000): CE over
+    (label, sampled negatives).  Negatives are random, so the check feeds the same candidate matrix to the oracle:
+    candidate logits (no labels) and the loss / pooled-gradient path through the fused kernels."""
+    cfg_kw = dict(vocab_size=1500, num_hidden_layers=1, attention_window=[64], max_position_embeddings=600)
+    ocfg, cfg, model, sd = build(cfg_kw, sd_seed=6)
+    cfg.hidden_dropout_prob = 0.0
+    cfg.attention_probs_dropout_prob = 0.0
+    B, L, N, C = 3, 200, 500, 101
+    batch = O.make_batch(ocfg, B, L, seed=4, ragged=True)
+    items = O.make_item_table(N, 768, seed=1)
+    model.init_item_embedding(items.to(DEV))
+    cand = torch.randint(0, N, (B, C), generator=torch.Generator().manual_seed(8))
+    dev_batch = {k: v.to(DEV) for k, v in batch.items()}
+    model.eval()
+    with torch.no_grad():
+        scores = model(**dev_batch, candidates=cand.to(DEV))
+    ref_scores = O.seqrec_forward(sd, ocfg, batch, items, candidates=cand)
+    assert scores.shape == (B, C) and (scores.cpu() - ref_scores).abs().max() < LOGIT_TOL
+    # loss path: call the fused CE on the model's pooled output with the same candidates as the oracle
+    from recformer_b200.models import _CandidateCEFunction
+    model.train()
+    pooled = model.longformer(**dev_batch).pooler_output
+    loss = _CandidateCEFunction.apply(pooled, model.normalized_items(), cand.to(DEV), cfg.temp)
+    loss.backward()
+    for v in sd.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    ref_loss = O.seqrec_forward(sd, ocfg, batch, items, labels=cand[:, 0], candidates=cand)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 2e-2
+    k = "longformer.encoder.layer.0.output.dense.weight"
+    g, rg = dict(model.named_parameters())[k].grad.cpu(), sd[k].grad
+    assert (g - rg).abs().max() / rg.abs().max() < 0.06
+    # and the public sampled path runs (random negatives on the device)
+    cfg.finetune_negative_sample_size = 50
+    cfg.item_num = N
+    out = model(**dev_batch, labels=torch.tensor([1, 2, 3], device=DEV))
+    assert out.dim() == 0 and torch.isfinite(out)
