@@ -131,6 +131,19 @@ int rf_embed_ln_fwd(const rf_embed_args* a, void* out_bf16, float* out_f32_or_nu
 int rf_embed_ln_bwd(const rf_embed_args* a, const void* dout_bf16, float* d_word, float* d_pos, float* d_type,
                     float* d_item, float* d_gamma, float* d_beta, rf_stream_t stream);
 
+/* Device-side assembly of the tokenizer's batch layout (SURVEY.md §8a Spec T; ref: recformer/tokenization.py:64-152
+ * `encode(items, encode_item=False)` + `padding`) from pre-tokenised items stored as CSR arrays in HBM:
+ * item i owns tokens item_tokens[item_offsets[i] .. item_offsets[i+1]) with token types item_types[..] (1 key,
+ * 2 value); user u's history (oldest first) is user_items[user_offsets[u] .. user_offsets[u+1]).  Writes the five
+ * int64 [B, L] tensors exactly as the reference tokenizer would (most recent item first, at most max_items items,
+ * truncated to max_tokens, right-padded with pad_id / max_item_pos / 3 / 0 / 0) and, if out_len != NULL, each row's
+ * unpadded length.  L must be >= the longest row (use max_tokens for pad_to_max). */
+int rf_assemble_batch(const int64_t* item_offsets, const int32_t* item_tokens, const uint8_t* item_types,
+                      const int64_t* user_offsets, const int64_t* user_items, int B, int L, int max_items,
+                      int max_tokens, int bos_id, int pad_id, int max_item_pos, int64_t* out_ids,
+                      int64_t* out_item_pos, int64_t* out_types, int64_t* out_mask, int64_t* out_global, int32_t* out_len,
+                      rf_stream_t stream);
+
 /* LayerNorm over the last dim (E = 768) of the fp32 residual stream [T,E]; replaces nn.LayerNorm
  * at HF:1070, HF:1129.  The residual stream (pre-LN sums and LN outputs) is kept in fp32 and only
  * rounded to bf16 where it becomes a tensor-core operand: y_bf16 is that operand copy, y_f32 the

@@ -54,6 +54,8 @@ _SIGS = {
     "rf_embed_ln_fwd": (c_int, [P(EmbedArgs), c_void_p, c_void_p, c_void_p, c_void_p]),
     "rf_embed_ln_bwd": (c_int, [P(EmbedArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
+    "rf_assemble_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rf_colsum_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rf_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                  c_void_p]),

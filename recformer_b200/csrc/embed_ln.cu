@@ -560,3 +560,83 @@ extern "C" int rf_adamw_step(float* param, const float* grad, float* exp_avg, fl
       bc1, sqrtf(bc2), grad_scale);
   return check_launch("rf_adamw_step");
 }
+
+// ================================================================================================
+// Device-side batch assembly of the tokenizer's five-tensor layout (SURVEY.md §8a Spec T;
+// ref: recformer/tokenization.py:64-152 `encode` + `padding`) from pre-tokenised items held in HBM
+// as CSR arrays.  One CTA per user: the user's items are taken most-recent-first, at most
+// max_items of them, rows are truncated to max_tokens and right-padded to the output width L with
+// (ids = pad, item position = max_item_pos, token type = 3, masks = 0).  Pure integer work, bit-exact.
+// ================================================================================================
+namespace rf {
+
+__global__ void __launch_bounds__(256)
+assemble_batch_kernel(const int64_t* __restrict__ item_offsets, const int32_t* __restrict__ item_tokens,
+                      const uint8_t* __restrict__ item_types, const int64_t* __restrict__ user_offsets,
+                      const int64_t* __restrict__ user_items, int L, int max_items, int max_tokens, int bos, int pad,
+                      int max_item_pos, int64_t* __restrict__ out_ids, int64_t* __restrict__ out_item_pos,
+                      int64_t* __restrict__ out_types, int64_t* __restrict__ out_mask, int64_t* __restrict__ out_global,
+                      int32_t* __restrict__ out_len) {
+  constexpr int MAXI = 64;                       // max_item_embeddings - 1 <= 63
+  __shared__ int s_start[MAXI + 1];              // first token position of the k-th kept item (k = 0 most recent)
+  __shared__ long long s_src[MAXI];              // offset of that item's tokens in the CSR arrays
+  __shared__ int s_n, s_total;
+  const int u = blockIdx.x, tid = threadIdx.x;
+  const long long u0 = user_offsets[u], u1 = user_offsets[u + 1];
+  if (tid == 0) {
+    const int n = static_cast<int>(min(static_cast<long long>(max_items), u1 - u0));
+    int pos = 1;                                  // position 0 is <s>
+    for (int k = 0; k < n; ++k) {
+      const long long item = user_items[u1 - 1 - k];   // reversed: most recent first
+      const long long a = item_offsets[item], b = item_offsets[item + 1];
+      s_start[k] = pos;
+      s_src[k] = a;
+      pos += static_cast<int>(b - a);
+    }
+    s_start[n] = pos;
+    s_n = n;
+    s_total = min(pos, max_tokens);
+  }
+  __syncthreads();
+  const int n = s_n, total = s_total;
+  if (tid == 0 && out_len != nullptr) out_len[u] = total;
+  for (int p = tid; p < L; p += 256) {
+    long long id = pad, ip = max_item_pos, tt = 3, am = 0, gm = 0;
+    if (p < total) {
+      am = 1;
+      if (p == 0) {
+        id = bos; ip = 0; tt = 0; gm = 1;
+      } else {
+        int lo = 0, hi = n - 1;                   // last k with s_start[k] <= p
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (s_start[mid] <= p) lo = mid; else hi = mid - 1;
+        }
+        const long long src = s_src[lo] + (p - s_start[lo]);
+        id = item_tokens[src];
+        tt = item_types[src];
+        ip = lo + 1;
+      }
+    }
+    const size_t o = static_cast<size_t>(u) * L + p;
+    out_ids[o] = id; out_item_pos[o] = ip; out_types[o] = tt; out_mask[o] = am; out_global[o] = gm;
+  }
+}
+
+}  // namespace rf
+
+extern "C" int rf_assemble_batch(const int64_t* item_offsets, const int32_t* item_tokens, const uint8_t* item_types,
+                                 const int64_t* user_offsets, const int64_t* user_items, int B, int L, int max_items,
+                                 int max_tokens, int bos_id, int pad_id, int max_item_pos, int64_t* out_ids,
+                                 int64_t* out_item_pos, int64_t* out_types, int64_t* out_mask, int64_t* out_global,
+                                 int32_t* out_len, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(item_offsets && item_tokens && item_types && user_offsets && user_items, "rf_assemble_batch: null input");
+  RF_REQUIRE(out_ids && out_item_pos && out_types && out_mask && out_global, "rf_assemble_batch: null output");
+  RF_REQUIRE(B > 0 && L > 0 && max_items >= 1 && max_items <= 63 && max_tokens >= 1,
+             "rf_assemble_batch: bad shape (B=%d L=%d max_items=%d max_tokens=%d)", B, L, max_items, max_tokens);
+  rf::assemble_batch_kernel<<<B, 256, 0, stream>>>(item_offsets, item_tokens, item_types, user_offsets, user_items, L,
+                                                  max_items, max_tokens, bos_id, pad_id, max_item_pos, out_ids,
+                                                  out_item_pos, out_types, out_mask, out_global, out_len);
+  return rf::check_launch("rf_assemble_batch");
+}

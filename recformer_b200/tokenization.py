@@ -83,3 +83,63 @@ class RecformerTokenizer:
 
     def batch_encode(self, item_batch, encode_item=True, pad_to_max=False):
         return self.padding([self.encode(items, encode_item) for items in item_batch], pad_to_max)
+
+
+class DeviceItemStore:
+    """Pre-tokenised items (`{item_id: [input_ids, token_type_ids]}`, ref: finetune.py:239) held on the GPU as CSR
+    arrays; `batch_encode` assembles the tokenizer's five-tensor batch there with one kernel (rf_assemble_batch)
+    instead of Python list loops + a host->device copy of 5 x B x L int64.  Bit-identical to
+    `RecformerTokenizer.batch_encode(..., encode_item=False)`."""
+
+    def __init__(self, config, tokenized_items, device="cuda", bos_token_id: int = 0, pad_token_id: int = 1):
+        import numpy as np
+        self.config, self.device = config, torch.device(device)
+        self.bos_token_id, self.pad_token_id = bos_token_id, pad_token_id
+        self.ids = sorted(tokenized_items)
+        self.index = {item_id: k for k, item_id in enumerate(self.ids)}
+        lens = np.array([len(tokenized_items[i][0]) for i in self.ids], dtype=np.int64)
+        offsets = np.zeros(len(self.ids) + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        tokens = np.concatenate([np.asarray(tokenized_items[i][0], dtype=np.int32) for i in self.ids]) if len(self.ids) else np.zeros(0, np.int32)
+        types = np.concatenate([np.asarray(tokenized_items[i][1], dtype=np.uint8) for i in self.ids]) if len(self.ids) else np.zeros(0, np.uint8)
+        self.offsets = torch.from_numpy(offsets).to(self.device)
+        self.tokens = torch.from_numpy(tokens).to(self.device)
+        self.types = torch.from_numpy(types).to(self.device)
+
+    def batch_encode(self, user_item_ids, pad_to_max: bool = False):
+        """user_item_ids: list (per user) of item ids, oldest first (what `RecformerTokenizer.encode` receives)."""
+        from . import _lib
+        from .ops import check, _stream
+        B = len(user_item_ids)
+        flat = [self.index[i] for items in user_item_ids for i in items]
+        uoff = [0]
+        for items in user_item_ids:
+            uoff.append(uoff[-1] + len(items))
+        u_items = torch.tensor(flat if flat else [0], dtype=torch.int64).pin_memory().to(self.device, non_blocking=True)
+        u_off = torch.tensor(uoff, dtype=torch.int64).pin_memory().to(self.device, non_blocking=True)
+        cfg = self.config
+        max_items, max_tokens = cfg.max_item_embeddings - 1, cfg.max_token_num
+        if pad_to_max:
+            L = max_tokens
+        else:   # the batch maximum is known on the host from the item lengths (no device sync)
+            lens_host = self._host_lengths(user_item_ids, max_items, max_tokens)
+            L = max(lens_host)
+        out = {k: torch.empty(B, L, dtype=torch.int64, device=self.device)
+               for k in ("input_ids", "item_position_ids", "token_type_ids", "attention_mask", "global_attention_mask")}
+        check(_lib.lib().rf_assemble_batch(self.offsets.data_ptr(), self.tokens.data_ptr(), self.types.data_ptr(),
+                                           u_off.data_ptr(), u_items.data_ptr(), B, L, max_items, max_tokens,
+                                           self.bos_token_id, self.pad_token_id, cfg.max_item_embeddings - 1,
+                                           out["input_ids"].data_ptr(), out["item_position_ids"].data_ptr(),
+                                           out["token_type_ids"].data_ptr(), out["attention_mask"].data_ptr(),
+                                           out["global_attention_mask"].data_ptr(), None, _stream()), "rf_assemble_batch")
+        return out
+
+    def _host_lengths(self, user_item_ids, max_items, max_tokens):
+        if not hasattr(self, "_len_host"):
+            off = self.offsets.cpu()
+            self._len_host = (off[1:] - off[:-1]).tolist()
+        out = []
+        for items in user_item_ids:
+            n = 1 + sum(self._len_host[self.index[i]] for i in items[::-1][:max_items])
+            out.append(min(n, max_tokens))
+        return out

@@ -347,6 +347,30 @@ def test_candidate_scoring_and_sampled_softmax():
     assert relerr(dpooled, xr.grad) < 1e-3
 
 
+def test_device_batch_assembly_is_bit_identical_to_tokenizer():
+    """rf_assemble_batch vs RecformerTokenizer.batch_encode(encode_item=False) (ref: tokenization.py:64-152):
+    reversal, 50-item cap, 1024-token truncation, padding values, batch-max and pad_to_max widths."""
+    import recformer_b200 as rb
+    from recformer_b200.tokenization import DeviceItemStore
+    cfg = rb.RecformerConfig(attention_window=[64], num_hidden_layers=1, max_token_num=1024, max_item_embeddings=51)
+    g = torch.Generator().manual_seed(0)
+    items = {}
+    for item_id in range(300):
+        n = int(torch.randint(3, 97, (1,), generator=g))
+        items[item_id * 7 + 3] = [torch.randint(3, 50265, (n,), generator=g).tolist(), torch.randint(1, 3, (n,), generator=g).tolist()]
+    ids = sorted(items)
+    users = []
+    for u, n_items in enumerate((1, 3, 12, 49, 50, 51, 70, 2)):
+        users.append([ids[int(k)] for k in torch.randint(0, len(ids), (n_items,), generator=g)])
+    tok = rb.RecformerTokenizer(cfg)
+    store = DeviceItemStore(cfg, items)
+    for pad_to_max in (False, True):
+        ref = tok.batch_encode([[items[i] for i in u] for u in users], encode_item=False, pad_to_max=pad_to_max)
+        got = store.batch_encode(users, pad_to_max=pad_to_max)
+        for k, v in ref.items():
+            assert torch.equal(got[k].cpu(), torch.tensor(v)), (k, pad_to_max)
+
+
 def test_cast_and_adamw():
     n = 4096 * 3
     p = rnd(n, seed=1, dtype=torch.float32)
