@@ -81,72 +81,56 @@ __device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) {
 // TMEM).  The raw fp32 accumulators are first transposed through a 4 KB 128B-swizzled staging slab
 // in shared memory so that every global access of the epilogue is coalesced: in the second phase
 // lane l owns 8 consecutive columns ((l % 4) * 8) of row 8*s + l/4 for s = 0..3, i.e. each warp
-// instruction touches 8 rows x 64..128 contiguous bytes instead of 32 rows x 16 bytes (the
-// row-per-thread pattern costs 32 LSU wavefronts per instruction and bounded the epilogue).
+// instruction touches 8 rows x 64..128 contiguous bytes instead of 32 rows x 16 bytes.
 // Then: bias / scale / GELU / GELU' / dropout / residual, and the store.
-template <int EPI, bool OUT_F32>
+//
+// The body is STRAIGHT-LINE code: what the epilogue does is fixed by template flags (RES: 0 none, 1 bf16
+// residual, 2 fp32 residual — also used for "accumulate into C"; DROP; SPLITK = red.add stores), rows past M
+// are handled by clamped loads and predicated stores.  With run-time `if (residual) / if (dropout) /
+// continue` the four row steps of a chunk were separate basic blocks and every shared / global load latency
+// was exposed once per step; branch-free, the scheduler overlaps all four.
+template <int EPI, bool OUT_F32, int RES, bool DROP, bool SPLITK>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const GemmParams& p, const float* sb,
                                                uint8_t* stage, int lane, int lcol, int row_base, int col0) {
-  // ---- phase 0: issue the epilogue's global loads (residual / gelu' tile) for all four row steps
-  //      now, so their latency overlaps the shared-memory transposition ----
+  const int cq = lane & 3;               // which 8-column group of the chunk
+  const int c8 = col0 + cq * 8;          // first global column owned by this lane
+  // ---- phase 0: issue the epilogue's global loads (residual / gelu' tile) for all four row steps ----
   uint4 aux_pf[4];
   float4 res_pf[4][2];
-  {
-    const int c8p = col0 + (lane & 3) * 8;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const int row = row_base + s * 8 + (lane >> 2);
-      const bool ok = row < p.M;
-      if (EPI == RF_EPI_DGELU)
-        aux_pf[s] = ok ? *reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.ldaux + c8p) : make_uint4(0, 0, 0, 0);
-      if (EPI != RF_EPI_GELU && p.residual != nullptr && ok) {
-        if (p.residual_f32) {
-          const float* rs = reinterpret_cast<const float*>(p.residual) + static_cast<size_t>(row) * p.ldr + c8p;
-          res_pf[s][0] = *reinterpret_cast<const float4*>(rs);
-          res_pf[s][1] = *reinterpret_cast<const float4*>(rs + 4);
-        } else {
-          res_pf[s][0] = *reinterpret_cast<const float4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
-                                                          static_cast<size_t>(row) * p.ldr + c8p);
-        }
-      }
+  for (int s = 0; s < 4; ++s) {
+    const int rc = min(row_base + s * 8 + (lane >> 2), p.M - 1);
+    if (EPI == RF_EPI_DGELU) aux_pf[s] = *reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(rc) * p.ldaux + c8);
+    if (RES == 2) {
+      const float* rs = reinterpret_cast<const float*>(p.residual) + static_cast<size_t>(rc) * p.ldr + c8;
+      res_pf[s][0] = *reinterpret_cast<const float4*>(rs);
+      res_pf[s][1] = *reinterpret_cast<const float4*>(rs + 4);
+    } else if (RES == 1) {
+      res_pf[s][0] = *reinterpret_cast<const float4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                                      static_cast<size_t>(rc) * p.ldr + c8);
     }
   }
   // ---- phase 1: thread (= row `lane`) writes its 32 fp32 values, 16B units XOR-swizzled by row ----
-  if (!(p.debug_skip_epilogue & 8)) {
+  {
     uint8_t* srow = stage + lane * 128;
 #pragma unroll
     for (int u = 0; u < 8; ++u)
       *reinterpret_cast<uint4*>(srow + ((u ^ (lane & 7)) << 4)) = make_uint4(r[u * 4], r[u * 4 + 1], r[u * 4 + 2], r[u * 4 + 3]);
   }
   __syncwarp();
-  // ---- phase 2: coalesced layout ----
-  const int cq = lane & 3;               // which 8-column group of the chunk
-  const int c8 = col0 + cq * 8;          // first global column owned by this lane
-  float bias8[8];
-  if (p.bias != nullptr) {
-    const float4 b0 = *reinterpret_cast<const float4*>(sb + lcol + cq * 8);
-    const float4 b1 = *reinterpret_cast<const float4*>(sb + lcol + cq * 8 + 4);
-    bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
-    bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
-  } else {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) bias8[e] = 0.f;
-  }
+  // ---- phase 2: coalesced layout (the bias slab is zero-filled when there is no bias) ----
+  const float4 b0 = *reinterpret_cast<const float4*>(sb + lcol + cq * 8);
+  const float4 b1 = *reinterpret_cast<const float4*>(sb + lcol + cq * 8 + 4);
+  const float bias8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   const float sc = (col0 < p.scale_ncols) ? p.scale : 1.0f;   // scale_ncols is a multiple of 32
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
     const int rl = s * 8 + (lane >> 2);
     const int row = row_base + rl;
+    const bool ok = row < p.M;
     const uint8_t* srow = stage + rl * 128;
-    float4 x0, x1;
-    if (p.debug_skip_epilogue & 8) {
-      x0 = make_float4(__uint_as_float(r[s * 8]), __uint_as_float(r[s * 8 + 1]), __uint_as_float(r[s * 8 + 2]), __uint_as_float(r[s * 8 + 3]));
-      x1 = make_float4(__uint_as_float(r[s * 8 + 4]), __uint_as_float(r[s * 8 + 5]), __uint_as_float(r[s * 8 + 6]), __uint_as_float(r[s * 8 + 7]));
-    } else {
-      x0 = *reinterpret_cast<const float4*>(srow + (((2 * cq) ^ (rl & 7)) << 4));
-      x1 = *reinterpret_cast<const float4*>(srow + (((2 * cq + 1) ^ (rl & 7)) << 4));
-    }
-    if (row >= p.M) continue;
+    const float4 x0 = *reinterpret_cast<const float4*>(srow + (((2 * cq) ^ (rl & 7)) << 4));
+    const float4 x1 = *reinterpret_cast<const float4*>(srow + (((2 * cq + 1) ^ (rl & 7)) << 4));
     float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = (v[e] + bias8[e]) * sc;
@@ -155,68 +139,60 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ge
       // C2 <- gelu(u) (operand of the next GEMM); C <- gelu'(u) (all the backward pass needs of u)
       float g[8], d[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        if (p.debug_skip_epilogue & 4) { g[e] = v[e]; d[e] = v[e]; }
-        else gelu_and_grad(v[e], g[e], d[e]);
-      }
+      for (int e = 0; e < 8; ++e) gelu_and_grad(v[e], g[e], d[e]);
       uint4 dv, gv;
       dv.x = pack_bf16(d[0], d[1]); dv.y = pack_bf16(d[2], d[3]); dv.z = pack_bf16(d[4], d[5]); dv.w = pack_bf16(d[6], d[7]);
       gv.x = pack_bf16(g[0], g[1]); gv.y = pack_bf16(g[2], g[3]); gv.z = pack_bf16(g[4], g[5]); gv.w = pack_bf16(g[6], g[7]);
-      if ((p.debug_skip_epilogue & 2) && dv.x != 0x12345678u) continue;
-      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = dv;
-      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + off) = gv;
-      continue;
-    }
-    if (EPI == RF_EPI_DGELU) {   // aux holds gelu'(u) saved by the forward epilogue
-      const uint4 a = aux_pf[s];
-      const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
-      v[0] *= a0.x; v[1] *= a0.y; v[2] *= a1.x; v[3] *= a1.y; v[4] *= a2.x; v[5] *= a2.y; v[6] *= a3.x; v[7] *= a3.y;
-    }
-    if (p.drop_thresh != 0) {
-      const uint64_t grp = (static_cast<uint64_t>(row) * p.N + c8) >> 3;
-      const uint32_t keep = dropout_keep8(p.drop_seed, grp, p.drop_thresh);
+      if (ok) {
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = dv;
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + off) = gv;
+      }
+    } else {
+      if (EPI == RF_EPI_DGELU) {   // aux holds gelu'(u) saved by the forward epilogue
+        const uint4 a = aux_pf[s];
+        const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+        v[0] *= a0.x; v[1] *= a0.y; v[2] *= a1.x; v[3] *= a1.y; v[4] *= a2.x; v[5] *= a2.y; v[6] *= a3.x; v[7] *= a3.y;
+      }
+      if (DROP) {
+        const uint64_t grp = (static_cast<uint64_t>(row) * p.N + c8) >> 3;
+        const uint32_t keep = dropout_keep8(p.drop_seed, grp, p.drop_thresh);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = ((keep >> e) & 1u) ? v[e] * p.drop_scale : 0.0f;
-    }
-    if (p.residual != nullptr) {
-      if (p.residual_f32) {
+        for (int e = 0; e < 8; ++e) v[e] = ((keep >> e) & 1u) ? v[e] * p.drop_scale : 0.0f;
+      }
+      if (RES == 2) {
         const float4 r0 = res_pf[s][0], r1 = res_pf[s][1];
         v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-      } else {
+      } else if (RES == 1) {
         const float4 raw = res_pf[s][0];
         const float2 a0 = unpack_bf16(__float_as_uint(raw.x)), a1 = unpack_bf16(__float_as_uint(raw.y));
         const float2 a2 = unpack_bf16(__float_as_uint(raw.z)), a3 = unpack_bf16(__float_as_uint(raw.w));
         v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y; v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
       }
-    }
-    if (OUT_F32) {
-      float* cf = reinterpret_cast<float*>(p.C) + off;
-      if (p.split_k > 1) {
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cf), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
-                     : "memory");
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cf + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
-                     "f"(v[7])
-                     : "memory");
-      } else if (p.accumulate) {
-        float4 o0 = *reinterpret_cast<float4*>(cf), o1 = *reinterpret_cast<float4*>(cf + 4);
-        o0.x += v[0]; o0.y += v[1]; o0.z += v[2]; o0.w += v[3]; o1.x += v[4]; o1.y += v[5]; o1.z += v[6]; o1.w += v[7];
-        *reinterpret_cast<float4*>(cf) = o0;
-        *reinterpret_cast<float4*>(cf + 4) = o1;
+      if (OUT_F32) {
+        float* cf = reinterpret_cast<float*>(p.C) + off;
+        if (SPLITK) {
+          if (ok) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cf), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+                         : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cf + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
+                         "f"(v[7])
+                         : "memory");
+          }
+        } else if (ok) {
+          *reinterpret_cast<float4*>(cf) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(cf + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
       } else {
-        *reinterpret_cast<float4*>(cf) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(cf + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        uint4 o;
+        o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+        if (ok) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = o;
       }
-    } else {
-      uint4 o;
-      o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-      if ((p.debug_skip_epilogue & 2) && o.x != 0x12345678u) continue;
-      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = o;
     }
   }
   __syncwarp();   // the staging slab is rewritten by the next chunk
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32, int RES, bool DROP, bool SPLITK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using S = GemmSmem<BN>;
@@ -353,7 +329,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint8_t* my_stage = s_stage + (warp - 2) * 4096;
       // stage this tile's bias slab in shared memory (global-load latency off the critical path)
       float* sb = s_bias + acc * BN;
-      if (p.bias != nullptr && etid < BN) sb[etid] = (n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
+      if (etid < BN) sb[etid] = (p.bias != nullptr && n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -374,7 +350,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int lcol = half * (BN / 2) + c * 32;
         const int col0 = n0 + lcol;
         if (col0 >= p.N) continue;  // warp-uniform
-        epilogue_chunk<EPI, OUT_F32>(rbuf[c & 1], p, sb, my_stage, lane, lcol, row_base, col0);
+        epilogue_chunk<EPI, OUT_F32, RES, DROP, SPLITK>(rbuf[c & 1], p, sb, my_stage, lane, lcol, row_base, col0);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -398,6 +374,9 @@ static void fill_params(const rf_gemm_args* a, GemmParams& p) {
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.ldc = a->ldc; p.ldr = a->ldr; p.ldaux = a->ldaux;
   p.accumulate = a->accumulate;
+  if (a->accumulate && a->out_f32 && a->residual == nullptr) {   // C += v  ==  v + (fp32 residual = C), read up front
+    p.residual = a->C; p.residual_f32 = 1; p.ldr = a->ldc;
+  }
   {
     // every K slice must be non-empty: recompute the slice count from the per-slice block count
     const int kb = (a->K + BK - 1) / BK;
@@ -430,7 +409,7 @@ constexpr uint32_t P_BAR_BYTES = (2 * P_STAGES + 4) * 8 + 16;
 constexpr uint32_t P_EPI_STAGE_BYTES = EPI_WARPS * 4096;
 constexpr uint32_t P_SMEM = P_TILE_BYTES + P_EPI_STAGE_BYTES + P_BAR_BYTES + 2 * P_BN * 4 + 1024;
 
-template <bool A_MN, bool B_MN, int EPI, bool OUT_F32>
+template <bool A_MN, bool B_MN, int EPI, bool OUT_F32, int RES, bool DROP, bool SPLITK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -569,7 +548,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row_base = m0 + quad * 32;
       uint8_t* my_stage = s_stage + (warp - 2) * 4096;
       float* sb = s_bias + acc * P_BN;
-      if (p.bias != nullptr && etid < P_BN) sb[etid] = (n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
+      if (etid < P_BN) sb[etid] = (p.bias != nullptr && n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -588,8 +567,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         const int lcol = half * (P_BN / 2) + c * 32;
         const int col0 = n0 + lcol;
-        if (col0 >= p.N || (p.debug_skip_epilogue & 1)) continue;
-        epilogue_chunk<EPI, OUT_F32>(rbuf[c & 1], p, sb, my_stage, lane, lcol, row_base, col0);
+        if (col0 >= p.N || p.debug_skip_epilogue) continue;
+        epilogue_chunk<EPI, OUT_F32, RES, DROP, SPLITK>(rbuf[c & 1], p, sb, my_stage, lane, lcol, row_base, col0);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -603,9 +582,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <bool A_MN, bool B_MN, int EPI, bool OUT_F32>
+template <bool A_MN, bool B_MN, int EPI, bool OUT_F32, int RES, bool DROP, bool SPLITK>
 static int launch_gemm_pair(const rf_gemm_args* a, cudaStream_t stream) {
-  auto kern = gemm_pair_kernel<A_MN, B_MN, EPI, OUT_F32>;
+  auto kern = gemm_pair_kernel<A_MN, B_MN, EPI, OUT_F32, RES, DROP, SPLITK>;
   static bool attr_set = false;
   if (!attr_set) {
     RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
@@ -624,10 +603,10 @@ static int launch_gemm_pair(const rf_gemm_args* a, cudaStream_t stream) {
   return check_launch("rf_gemm_bf16(pair)");
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32, int RES, bool DROP, bool SPLITK>
 static int launch_gemm(const rf_gemm_args* a, cudaStream_t stream) {
   using S = GemmSmem<BN>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, OUT_F32>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, OUT_F32, RES, DROP, SPLITK>;
   static bool attr_set = false;
   if (!attr_set) {
     RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -667,30 +646,58 @@ extern "C" int rf_gemm_bf16(const rf_gemm_args* a, rf_stream_t stream_) {
   // CTA-pair kernel (256 x 256 tiles) whenever there is more than one 128-row slab of output;
   // the single-CTA kernel covers small problems (e.g. one short sequence).
   const bool pair = a->M > 128 && a->N >= 128;
+  // what the (branch-free) epilogue has to do, resolved to template flags
+  const bool drop = a->drop_p > 0.f;
+  int split = 1;
+  {
+    const int kb = (a->K + BK - 1) / BK;
+    int sk = a->split_k > 1 ? a->split_k : 1;
+    if (sk > kb) sk = kb;
+    const int per = (kb + sk - 1) / sk;
+    split = (kb + per - 1) / per;
+  }
+  const bool splitk = split > 1;
+  const bool acc_c = a->accumulate && a->out_f32 && a->residual == nullptr;
+  RF_REQUIRE(!(a->accumulate && a->residual != nullptr), "rf_gemm_bf16: accumulate and residual are exclusive");
+  const int res = (a->residual != nullptr) ? (a->residual_f32 ? 2 : 1) : ((acc_c && !splitk) ? 2 : 0);
+#define RF_GEMM(BNS, AMN, BMN, EPIK, F32, RESK, DROPK, SPLK)                                          \
+  (pair ? launch_gemm_pair<AMN, BMN, EPIK, F32, RESK, DROPK, SPLK>(a, stream)                          \
+        : launch_gemm<BNS, AMN, BMN, EPIK, F32, RESK, DROPK, SPLK>(a, stream))
   if (layout == 0) {
-    if (a->epi == RF_EPI_GELU)
-      return pair ? launch_gemm_pair<false, false, RF_EPI_GELU, false>(a, stream)
-                  : launch_gemm<256, false, false, RF_EPI_GELU, false>(a, stream);
+    if (a->epi == RF_EPI_GELU) {
+      RF_REQUIRE(res == 0 && !drop && !splitk, "rf_gemm_bf16: the GELU epilogue takes neither residual nor dropout");
+      return RF_GEMM(256, false, false, RF_EPI_GELU, false, 0, false, false);
+    }
     RF_REQUIRE(a->epi == RF_EPI_NONE, "rf_gemm_bf16: epilogue %d unsupported for K-major x K-major", a->epi);
-    if (a->out_f32)
-      return pair ? launch_gemm_pair<false, false, RF_EPI_NONE, true>(a, stream)
-                  : launch_gemm<128, false, false, RF_EPI_NONE, true>(a, stream);
-    return pair ? launch_gemm_pair<false, false, RF_EPI_NONE, false>(a, stream)
-                : launch_gemm<256, false, false, RF_EPI_NONE, false>(a, stream);
+    RF_REQUIRE(!splitk, "rf_gemm_bf16: split_k is only instantiated for the wgrad layout");
+    if (a->out_f32) {
+      RF_REQUIRE(res != 1, "rf_gemm_bf16: fp32 output takes an fp32 residual");
+      if (res == 2) return drop ? RF_GEMM(128, false, false, RF_EPI_NONE, true, 2, true, false)
+                                : RF_GEMM(128, false, false, RF_EPI_NONE, true, 2, false, false);
+      return drop ? RF_GEMM(128, false, false, RF_EPI_NONE, true, 0, true, false)
+                  : RF_GEMM(128, false, false, RF_EPI_NONE, true, 0, false, false);
+    }
+    RF_REQUIRE(res == 0 && !drop, "rf_gemm_bf16: residual / dropout need fp32 output in the forward layout");
+    return RF_GEMM(256, false, false, RF_EPI_NONE, false, 0, false, false);
   }
   if (layout == 1) {  // dgrad: dY[M,K] (K-major) x W stored [K,N]
-    RF_REQUIRE(!a->out_f32, "rf_gemm_bf16: fp32 output unsupported for the dgrad layout");
-    if (a->epi == RF_EPI_DGELU)
-      return pair ? launch_gemm_pair<false, true, RF_EPI_DGELU, false>(a, stream)
-                  : launch_gemm<256, false, true, RF_EPI_DGELU, false>(a, stream);
+    RF_REQUIRE(!a->out_f32 && !drop && !splitk, "rf_gemm_bf16: the dgrad layout writes bf16 without dropout / split-K");
+    if (a->epi == RF_EPI_DGELU) {
+      RF_REQUIRE(res == 0, "rf_gemm_bf16: the dGELU epilogue takes no residual");
+      return RF_GEMM(256, false, true, RF_EPI_DGELU, false, 0, false, false);
+    }
     RF_REQUIRE(a->epi == RF_EPI_NONE, "rf_gemm_bf16: epilogue %d unsupported for the dgrad layout", a->epi);
-    return pair ? launch_gemm_pair<false, true, RF_EPI_NONE, false>(a, stream)
-                : launch_gemm<256, false, true, RF_EPI_NONE, false>(a, stream);
+    RF_REQUIRE(res != 2, "rf_gemm_bf16: the dgrad layout takes a bf16 residual");
+    return res == 1 ? RF_GEMM(256, false, true, RF_EPI_NONE, false, 1, false, false)
+                    : RF_GEMM(256, false, true, RF_EPI_NONE, false, 0, false, false);
   }
   if (layout == 3) {  // wgrad: dY^T x X, both stored [K, *]
-    RF_REQUIRE(a->out_f32 && a->epi == RF_EPI_NONE, "rf_gemm_bf16: the wgrad layout writes fp32 without epilogue");
-    return pair ? launch_gemm_pair<true, true, RF_EPI_NONE, true>(a, stream)
-                : launch_gemm<128, true, true, RF_EPI_NONE, true>(a, stream);
+    RF_REQUIRE(a->out_f32 && a->epi == RF_EPI_NONE && !drop && a->residual == nullptr,
+               "rf_gemm_bf16: the wgrad layout writes fp32 without epilogue");
+    if (splitk) return RF_GEMM(128, true, true, RF_EPI_NONE, true, 0, false, true);
+    return res == 2 ? RF_GEMM(128, true, true, RF_EPI_NONE, true, 2, false, false)
+                    : RF_GEMM(128, true, true, RF_EPI_NONE, true, 0, false, false);
   }
+#undef RF_GEMM
   return set_error(RF_ERR_INVALID, "rf_gemm_bf16: layout a_mn_major=1,b_mn_major=0 is not instantiated");
 }
