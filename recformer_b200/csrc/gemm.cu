@@ -677,8 +677,9 @@ extern "C" int rf_gemm_bf16(const rf_gemm_args* a, rf_stream_t stream_) {
       return drop ? RF_GEMM(128, false, false, RF_EPI_NONE, true, 0, true, false)
                   : RF_GEMM(128, false, false, RF_EPI_NONE, true, 0, false, false);
     }
-    RF_REQUIRE(res == 0 && !drop, "rf_gemm_bf16: residual / dropout need fp32 output in the forward layout");
-    return RF_GEMM(256, false, false, RF_EPI_NONE, false, 0, false, false);
+    RF_REQUIRE(res != 2 && !drop, "rf_gemm_bf16: bf16 output takes a bf16 residual and no dropout in the forward layout");
+    return res == 1 ? RF_GEMM(256, false, false, RF_EPI_NONE, false, 1, false, false)
+                    : RF_GEMM(256, false, false, RF_EPI_NONE, false, 0, false, false);
   }
   if (layout == 1) {  // dgrad: dY[M,K] (K-major) x W stored [K,N]
     RF_REQUIRE(!a->out_f32 && !drop && !splitk, "rf_gemm_bf16: the dgrad layout writes bf16 without dropout / split-K");
