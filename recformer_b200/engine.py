@@ -15,6 +15,7 @@ Data layout in HBM
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -246,7 +247,8 @@ class EncoderEngine:
         # of small latency-bound kernels: it runs on a side stream next to the QKV GEMM + band attention.
         self._side: Dict[str, torch.cuda.Stream] = {}
         self._events: Dict[tuple, torch.cuda.Event] = {}
-        self.overlap_global = True
+        self.overlap_global = os.environ.get("RF_DEBUG_NO_OVERLAP") is None
+        self._debug_skip_global = os.environ.get("RF_DEBUG_SKIP_GLOBAL") is not None   # timing experiment only (wrong results)
         self.grad_hook = None      # callable(layer): that layer's gradients are final (dist.GradSync)
 
     # -- helpers -------------------------------------------------------------------------------
@@ -372,7 +374,9 @@ class EncoderEngine:
             k = sv.idx(i)
             x = sv.xin(i)
             w_one = (aw if isinstance(aw, int) else aw[i]) // 2
-            if self.overlap_global:
+            if self._debug_skip_global:
+                pass
+            elif self.overlap_global:
                 # global row (writes ctx row 0 of every sequence) on the side stream, concurrently with the
                 # QKV projection + band attention (which never touch that row when position 0 is global)
                 main, side = torch.cuda.current_stream(device), self.side_stream(device)
@@ -386,7 +390,9 @@ class EncoderEngine:
             ops.gemm(x, W["Wqkv"], out=sv.qkv[k], bias=W["bqkv"], scale=0.125, scale_ncols=E)
             ops.band_attn_fwd(sv.qkv[k], mask, B, Lp, H, w_one, ctx=sv.ctx[k], lse=sv.lse[k], drop_p=sv.drop_attn,
                               drop_seed=self._seed(sv, i, 1))
-            if self.overlap_global:
+            if self._debug_skip_global:
+                pass
+            elif self.overlap_global:
                 main.wait_event(ev_g)
             else:
                 ops.global_attn_fwd(x, mask, W["Wqg"], W["bqg"], W["Wkg"], W["Wvg"], W["bvg"], B, Lp, H, sv.ctx[k],
@@ -451,7 +457,9 @@ class EncoderEngine:
                      split_k=_pick_split(E, E, T))
             ops.gemm(dY, W["Wo"], out=sc.dctx, b_mn_major=True)
             gargs = (x, mask, W["Wqg"], W["bqg"], W["Wkg"], W["Wvg"], W["bvg"], B, Lp, H)
-            if self.overlap_global:
+            if self._debug_skip_global:
+                pass
+            elif self.overlap_global:
                 # weight-gradient half of the global row's backward (needs dctx, not dx) on the side stream,
                 # concurrently with the band-attention backward and the QKV wgrad / dgrad GEMMs
                 main, side = torch.cuda.current_stream(device), self.side_stream(device)
@@ -469,7 +477,9 @@ class EncoderEngine:
                      split_k=_pick_split(3 * E, E, T))
             dx = sc.dx[i % 2]
             ops.gemm(sc.dqkv, W["Wqkv"], out=dx, b_mn_major=True, residual=sc.d_pre)
-            if self.overlap_global:
+            if self._debug_skip_global:
+                pass
+            elif self.overlap_global:
                 main.wait_event(ev_a)
                 ops.global_attn_bwd_dx(*gargs, sv.glob[i], dx, sc.gws, drop_p=sv.drop_attn,
                                        drop_seed=self._seed(sv, i, 2))
