@@ -28,7 +28,9 @@ namespace rf {
 constexpr int GH = 12;    // heads
 constexpr int GE = 768;   // hidden
 constexpr int GD = 64;    // head dim
-constexpr int GBB = 16;   // sequences per batch-block of the weight-product kernels
+constexpr int GBB = 16;   // sequences per batch-block of the column-parallel weight products
+constexpr int RBB = 4;    // sequences per batch-block of the row-parallel ones (12 KB of staging: the kernels of this
+                          // file stay below ~15 KB of shared memory so that they can share an SM with a band-attention CTA)
 
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
@@ -52,7 +54,7 @@ __device__ __forceinline__ float drop_factor(uint64_t seed, uint32_t thresh, flo
 //   MODE_Q  : V = x_cls[b] (bf16);               q_g = (dot + bqg[r]) / 8                -> qg
 //   MODE_OUT: V = m[b, h(r), :];                 ctx[b, 0, r] = dot + bvg[r] * psum[b,h]  (if global)
 //   MODE_DQ : V = du[b, h(r), :];                dq = dot / 8 (0 if no global) -> dqf; dbqg[r] += sum_b dq
-// grid (E / 8, ceil(B / 16)), 256 threads (8 rows of the same head per CTA).
+// grid (E / 8, ceil(B / RBB)), 256 threads (8 rows of the same head per CTA).
 // ---------------------------------------------------------------------------------------------
 enum { MODE_Q = 0, MODE_OUT = 1, MODE_DQ = 2 };
 
@@ -71,12 +73,12 @@ struct RowdotParams {
 
 template <int MODE>
 __global__ void __launch_bounds__(256) global_rowdot_kernel(const RowdotParams p) {
-  __shared__ __align__(16) float vs[GBB][GE];   // 48 KB
+  __shared__ __align__(16) float vs[RBB][GE];   // 12 KB
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = blockIdx.x * 8 + warp;
   const int h = (blockIdx.x * 8) / GD;
-  const int b0 = blockIdx.y * GBB;
-  const int nb = min(GBB, p.B - b0);
+  const int b0 = blockIdx.y * RBB;
+  const int nb = min(RBB, p.B - b0);
   for (int i = tid; i < nb * (GE / 4); i += 256) {
     const int bb = i / (GE / 4), c4 = i % (GE / 4);
     float4 v;
@@ -135,6 +137,7 @@ struct ColmixParams {
   const __nv_bfloat16* dctx;      // A = row 0 of dctx for sequences with a global token
   const uint8_t* mask;
   float* out;                     // [B, H, E]
+  float* out_sum;                 // if non-null: red.add the head's contribution into [B, E] instead (dxcls)
   // dm extras (null otherwise)
   const float* bvg; const float* psum; float* dpsum; float* dbvg; float* doutf;
   int B, L;
@@ -189,54 +192,11 @@ __global__ void __launch_bounds__(64) global_colmix_kernel(const ColmixParams p)
     }
   }
 #pragma unroll
-  for (int bb = 0; bb < GBB; ++bb)
-    if (bb < nb) p.out[(static_cast<size_t>(b0 + bb) * GH + h) * GE + e] = acc[bb];
-}
-
-// dxcls: dx[b, 0, e] += sum_r Wqg[r, e] * dq[b, r]   (all 768 rows: the CLS token's own input gradient)
-// grid (E / 64, ceil(B / 16)), 768 threads = 64 columns x 12 heads; heads reduced through shared memory.
-__global__ void __launch_bounds__(768)
-global_dxcls_kernel(const float* __restrict__ Wqg, const float* __restrict__ dqf, const uint8_t* __restrict__ mask,
-                    int B, int L, __nv_bfloat16* __restrict__ dx) {
-  __shared__ __align__(16) float as[GE][GBB];        // 48 KB: dq of 16 sequences
-  const int tid = threadIdx.x, c = tid & 63, h = tid >> 6;
-  const int e = blockIdx.x * 64 + c, b0 = blockIdx.y * GBB;
-  const int nb = min(GBB, B - b0);
-  float w[GD];     // this thread's 64 weights (head h, column e): loads issued before the staging below
-  {
-    const float* wp = Wqg + static_cast<size_t>(h) * GD * GE + e;
-#pragma unroll
-    for (int d = 0; d < GD; ++d) w[d] = __ldg(wp + static_cast<size_t>(d) * GE);
-  }
-  for (int i = tid; i < GE * GBB; i += 768) {
-    const int r = i / GBB, bb = i % GBB;
-    as[r][bb] = bb < nb ? dqf[static_cast<size_t>(b0 + bb) * GE + r] : 0.f;
-  }
-  __syncthreads();
-  float acc[GBB];
-#pragma unroll
-  for (int bb = 0; bb < GBB; ++bb) acc[bb] = 0.f;
-#pragma unroll
-  for (int d = 0; d < GD; ++d) {
-#pragma unroll
-    for (int q = 0; q < GBB / 4; ++q) {
-      const float4 a = *reinterpret_cast<const float4*>(&as[h * GD + d][q * 4]);
-      acc[q * 4 + 0] += w[d] * a.x; acc[q * 4 + 1] += w[d] * a.y; acc[q * 4 + 2] += w[d] * a.z; acc[q * 4 + 3] += w[d] * a.w;
+  for (int bb = 0; bb < GBB; ++bb) {
+    if (bb < nb) {
+      if (p.out_sum != nullptr) red_add_f32(p.out_sum + static_cast<size_t>(b0 + bb) * GE + e, acc[bb]);
+      else p.out[(static_cast<size_t>(b0 + bb) * GH + h) * GE + e] = acc[bb];
     }
-  }
-  __syncthreads();
-  float* red = &as[0][0];                             // reuse: [12][16][64]
-#pragma unroll
-  for (int bb = 0; bb < GBB; ++bb) red[(h * GBB + bb) * 64 + c] = acc[bb];
-  __syncthreads();
-  for (int i = tid; i < nb * 64; i += 768) {
-    const int bb = i / 64, cc = i % 64;
-    if (!seq_has_global(mask, b0 + bb, L)) continue;
-    float t = 0.f;
-#pragma unroll
-    for (int hh = 0; hh < GH; ++hh) t += red[(hh * GBB + bb) * 64 + cc];
-    __nv_bfloat16* d = dx + static_cast<size_t>(b0 + bb) * L * GE + blockIdx.x * 64 + cc;
-    *d = __float2bfloat16(__bfloat162float(*d) + t);
   }
 }
 
@@ -420,13 +380,13 @@ enum { MIX_ACC = 0, MIX_DX = 1 };
 template <int MODE>
 struct MixCfg {
   static constexpr bool DX = MODE == MIX_DX;
-  static constexpr int TOK = DX ? 64 : 128;
+  static constexpr int TOK = 32;
   static constexpr int STAGES = 3;
   static constexpr uint32_t X_BYTES = TOK * 128;
   static constexpr uint32_t C_BYTES = TOK * 64;
   // MIX_ACC: x tile + one coefficient block;  MIX_DX: dx tile + two coefficient blocks (p', ds)
   static constexpr uint32_t STAGE_BYTES = X_BYTES + (DX ? 2 : 1) * C_BYTES;
-  static constexpr uint32_t RED_BYTES = DX ? 0 : 8 * GH * 64 * 4;
+  static constexpr uint32_t RED_BYTES = DX ? 0 : GH * 64 * 4;          // cross-warp sums via shared-memory atomics
   static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + RED_BYTES + 2 * STAGES * 8 + 1024;
 };
 
@@ -437,6 +397,7 @@ struct MixParams {
   const float* u;     // MIX_DX: [B, H, E]
   float* out;         // MIX_ACC: [B, H, E] (zeroed by the caller): m or du
   __nv_bfloat16* dx;  // MIX_DX
+  const float* dxcls; // MIX_DX: [B, E] fp32 gradient of the CLS token's own input, added into row 0
   int B, L, nblk, items;
 };
 
@@ -448,7 +409,7 @@ global_mix_kernel(const __grid_constant__ CUtensorMap tmX, const MixParams p) {
   constexpr int TOK = C::TOK, STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
-  float* red = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);                 // [8][GH][64] (MIX_ACC)
+  float* red = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);                 // [GH][64] (MIX_ACC)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + C::RED_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -458,6 +419,7 @@ global_mix_kernel(const __grid_constant__ CUtensorMap tmX, const MixParams p) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 8); }
     fence_mbar_init();
   }
+  if (!DX) for (int i = tid; i < GH * 64; i += 288) red[i] = 0.f;
   __syncthreads();
   // stage layout: [x (MIX_ACC) or dx (MIX_DX) tile][coefficient rows 0][coefficient rows 1 (MIX_DX)]
   constexpr uint32_t OFF_C0 = C::X_BYTES, OFF_C1 = OFF_C0 + C::C_BYTES;
@@ -492,15 +454,14 @@ global_mix_kernel(const __grid_constant__ CUtensorMap tmX, const MixParams p) {
     const int b = key / GH, slice = key % GH;
 #pragma unroll
     for (int h = 0; h < (DX ? 1 : GH); ++h) {
-      *reinterpret_cast<float2*>(&red[(warp * GH + h) * 64 + lane * 2]) = make_float2(acc[h][0], acc[h][1]);
+      atomicAdd(&red[h * 64 + lane * 2], acc[h][0]);
+      atomicAdd(&red[h * 64 + lane * 2 + 1], acc[h][1]);
       acc[h][0] = acc[h][1] = 0.f;
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     for (int i = tid; i < GH * 64; i += 256) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) t += red[w * GH * 64 + i];
-      red_add_f32(p.out + (static_cast<size_t>(b) * GH + i / 64) * GE + slice * 64 + (i & 63), t);
+      red_add_f32(p.out + (static_cast<size_t>(b) * GH + i / 64) * GE + slice * 64 + (i & 63), red[i]);
+      red[i] = 0.f;
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
   };
@@ -546,6 +507,10 @@ global_mix_kernel(const __grid_constant__ CUtensorMap tmX, const MixParams p) {
         for (int h = 0; h < GH; ++h) {
           xv.x += pv[h] * dmr[DX ? h : 0][0] + sv[DX ? h : 0] * ur[DX ? h : 0][0];
           xv.y += pv[h] * dmr[DX ? h : 0][1] + sv[DX ? h : 0] * ur[DX ? h : 0][1];
+        }
+        if (j0 + t == 0) {   // the CLS token's own input gradient (zero for sequences without a global token)
+          const float2 c = *reinterpret_cast<const float2*>(p.dxcls + static_cast<size_t>(b) * GE + slice * 64 + lane * 2);
+          xv.x += c.x; xv.y += c.y;
         }
         *reinterpret_cast<uint32_t*>(p.dx + (static_cast<size_t>(b) * p.L + j0 + t) * GE + slice * 64 + lane * 2) =
             pack_bf16(xv.x, xv.y);
@@ -644,7 +609,7 @@ extern "C" int rf_global_attn_fwd(const rf_global_args* a, void* ctx, float* qg,
   {
     RowdotParams r{};
     r.W = a->Wqg; r.bias = a->bqg; r.x = x; r.mask = a->mask012; r.out_f32 = qg; r.B = B; r.L = L;
-    global_rowdot_kernel<MODE_Q><<<dim3(GE / 8, bblocks), 256, 0, stream>>>(r);
+    global_rowdot_kernel<MODE_Q><<<dim3(GE / 8, (B + RBB - 1) / RBB), 256, 0, stream>>>(r);
     if ((rc = check_launch("rf_global_attn_fwd/q"))) return rc;
   }
   {
@@ -667,19 +632,19 @@ extern "C" int rf_global_attn_fwd(const rf_global_args* a, void* ctx, float* qg,
     RowdotParams r{};
     r.W = a->Wvg; r.bias = a->bvg; r.V = mvec; r.psum = psum; r.mask = a->mask012;
     r.ctx = reinterpret_cast<__nv_bfloat16*>(ctx); r.B = B; r.L = L;
-    global_rowdot_kernel<MODE_OUT><<<dim3(GE / 8, bblocks), 256, 0, stream>>>(r);
+    global_rowdot_kernel<MODE_OUT><<<dim3(GE / 8, (B + RBB - 1) / RBB), 256, 0, stream>>>(r);
   }
   return check_launch("rf_global_attn_fwd/out");
 }
 
 extern "C" long long rf_global_attn_bwd_ws_bytes(int B, int L, int H) {
   const long long E = static_cast<long long>(H) * GD;
-  return 4ll * (2ll * B * H * E + B * H + static_cast<long long>(B) * H * L + 2ll * B * E + 16ll * B * L) + 256;
+  return 4ll * (2ll * B * H * E + B * H + static_cast<long long>(B) * H * L + 3ll * B * E + 16ll * B * L) + 256;
 }
 
 namespace {
 struct BwdWs {
-  float *dm, *du, *dst, *dp, *dpsum, *doutf, *dqf;
+  float *dm, *du, *dst, *dp, *dpsum, *doutf, *dqf, *dxcls;
   BwdWs(float* ws, int B, int L) {
     dm = ws;
     du = dm + static_cast<size_t>(B) * GH * GE;
@@ -688,6 +653,7 @@ struct BwdWs {
     dpsum = dp + static_cast<size_t>(B) * GH * L;
     doutf = dpsum + static_cast<size_t>(B) * GH;
     dqf = doutf + static_cast<size_t>(B) * GE;
+    dxcls = dqf + static_cast<size_t>(B) * GE;
   }
 };
 }  // namespace
@@ -702,15 +668,10 @@ extern "C" int rf_global_attn_bwd_dx(const rf_global_args* a, const float* u, co
   RF_REQUIRE(a->H == GH && a->D == GD, "rf_global_attn_bwd_dx: only H=12, D=64 supported (got %d, %d)", a->H, a->D);
   const int B = a->B, L = a->L;
   const BwdWs w(const_cast<float*>(ws), B, L);
-  int rc;
-  {
-    MixParams m{};
-    m.pt = pt; m.dst = w.dst; m.dm = w.dm; m.u = u; m.dx = reinterpret_cast<__nv_bfloat16*>(dx); m.B = B; m.L = L;
-    if ((rc = launch_mix<MIX_DX>(m.dx, m, stream, "rf_global_attn_bwd_dx/dx"))) return rc;
-  }
-  global_dxcls_kernel<<<dim3(GE / 64, (B + GBB - 1) / GBB), 768, 0, stream>>>(a->Wqg, w.dqf, a->mask012, B, L,
-                                                                             reinterpret_cast<__nv_bfloat16*>(dx));
-  return check_launch("rf_global_attn_bwd_dx/dxcls");
+  MixParams m{};
+  m.pt = pt; m.dst = w.dst; m.dm = w.dm; m.u = u; m.dx = reinterpret_cast<__nv_bfloat16*>(dx); m.dxcls = w.dxcls;
+  m.B = B; m.L = L;
+  return launch_mix<MIX_DX>(m.dx, m, stream, "rf_global_attn_bwd_dx/dx");
 }
 
 extern "C" int rf_global_attn_bwd(const rf_global_args* a, const void* dctx, const float* qg, const float* u,
@@ -753,8 +714,16 @@ extern "C" int rf_global_attn_bwd(const rf_global_args* a, const void* dctx, con
     // dq = Wkg[h] du_h / 8 (fp32 copy kept), dbqg += dq
     RowdotParams r{};
     r.W = a->Wkg; r.V = w.du; r.mask = a->mask012; r.out_f32 = w.dqf; r.dbias = dbqg; r.B = B; r.L = L;
-    global_rowdot_kernel<MODE_DQ><<<dim3(GE / 8, bblocks), 256, 0, stream>>>(r);
+    global_rowdot_kernel<MODE_DQ><<<dim3(GE / 8, (B + RBB - 1) / RBB), 256, 0, stream>>>(r);
     if ((rc = check_launch("rf_global_attn_bwd/dq"))) return rc;
+  }
+  {
+    // dxcls[b,:] = Wqg^T dq_b (the CLS token's own input gradient; added into dx row 0 by the dx-update kernel)
+    RF_CUDA(cudaMemsetAsync(w.dxcls, 0, static_cast<size_t>(B) * GE * sizeof(float), stream));
+    ColmixParams c{};
+    c.W = a->Wqg; c.A = w.dqf; c.mask = a->mask012; c.out_sum = w.dxcls; c.B = B; c.L = L;
+    global_colmix_kernel<<<dim3(GE / 64, GH, bblocks), 64, 0, stream>>>(c);
+    if ((rc = check_launch("rf_global_attn_bwd/dxcls"))) return rc;
   }
   global_wgrad_kernel<<<dim3(GH, 3, 3), 256, 0, stream>>>(x, a->mask012, B, L, w.doutf, mvec, qg, w.du, w.dqf, dWvg,
                                                          dWkg, dWqg);
