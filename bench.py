@@ -218,9 +218,8 @@ def train_step(model, opt, batch, world):
         from recformer_b200 import dist as rdist
         _SYNC[id(model)] = rdist.GradSync(model)
     loss.backward()
-    if world > 1:
-        _SYNC[id(model)].finish()
-    opt.step(grad_scale=1.0 / world)
+    tail = _SYNC[id(model)].finish(defer_tail=True) if world > 1 else None
+    opt.step(grad_scale=1.0 / world, wait_other=tail)   # dense / bias segments update while the embedding grads reduce
     return loss
 
 

@@ -128,21 +128,34 @@ class GradSync:
             self._works.append(dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
             self._covered.append((a, b))
 
-    def finish(self) -> None:
+    def finish(self, defer_tail: bool = False):
+        """Reduce what the per-layer calls left (embedding tables; biases / LayerNorm vectors) and wait.
+        With defer_tail=True the big embedding-table range is only LAUNCHED: the returned callable waits for it,
+        so the caller can run the optimizer on everything else meanwhile (FusedAdamW.step(wait_other=...))."""
         if not self._active():
             self._covered.clear()
-            return
+            self._seen.clear()
+            return None
         P = self.engine.params
         g = P.grad
         if g is None:
             raise RuntimeError("GradSync.finish: no gradients (run backward first)")
-        pos = 0
+        gaps, pos = [], 0
         for a, b in sorted(self._covered) + [(P.n_total, P.n_total)]:
             if a > pos:
-                self._works.append(dist.all_reduce(g[pos:a], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                gaps.append((pos, a))
             pos = max(pos, b)
+        gaps.sort(key=lambda r: r[1] - r[0])            # small ranges first, the embedding tables last
+        tail = None
+        for k, (a, b) in enumerate(gaps):
+            w = dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            if defer_tail and k == len(gaps) - 1 and P.n_dense <= a and b <= P.n_decay:
+                tail = w
+            else:
+                self._works.append(w)
         for w in self._works:
             w.wait()
         self._works.clear()
         self._covered.clear()
         self._seen.clear()
+        return (lambda: tail.wait()) if tail is not None else None

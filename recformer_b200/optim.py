@@ -46,7 +46,10 @@ class FusedAdamW:
             P.grad.zero_()
 
     @torch.no_grad()
-    def step(self, grad_scale: float = 1.0):
+    def step(self, grad_scale: float = 1.0, wait_other=None):
+        """wait_other: optional callable (GradSync.finish(defer_tail=True)) that is invoked right before the
+        segment holding the embedding tables is updated — the dense and no-decay segments run while the
+        embedding gradients are still being all-reduced."""
         P = self.engine.params
         if P.grad is None:
             raise RuntimeError("FusedAdamW.step() called before any backward pass")
@@ -56,8 +59,16 @@ class FusedAdamW:
             self._plan()
         self.step_count += 1
         b1, b2 = self.betas
-        for (a, b, decay, shadow) in self._segments:
+        segs = list(self._segments)
+        if wait_other is not None:      # embeddings (+ *_global weights) = the decay segment without a bf16 shadow: last
+            segs.sort(key=lambda sgm: (sgm[2] and not sgm[3]))
+        for (a, b, decay, shadow) in segs:
+            if wait_other is not None and decay and not shadow:
+                wait_other()
+                wait_other = None
             ops.adamw_step(P.flat[a:b], P.grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b],
                            P.shadow[a:b] if shadow else None, self.lr, b1, b2, self.eps,
                            self.weight_decay if decay else 0.0, self.step_count, grad_scale)
+        if wait_other is not None:
+            wait_other()
         P.mark_shadow_fresh()
