@@ -73,6 +73,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + AB_OFF_BAR);
   uint64_t* bar_mma = bar_load + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
+  uint64_t* bar_kv = bar_load + 3;     // dK / dV accumulators ready (dQ is published earlier on bar_mma)
   float* s_delta = reinterpret_cast<float*>(smem + AB_OFF_DELTA);   // [2][128] partial row sums
 
   // 8 warps: TMEM lane quadrant = warp % 4 (rows 32*quad..), `part` = warp / 4 splits every row's
@@ -90,6 +91,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   if (tid == 0) {
     mbar_init(bar_load, 1);
     mbar_init(bar_mma, 1);
+    mbar_init(bar_kv, 1);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -285,6 +287,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     for (int ks = 0; ks < NT / 16; ++ks)
       umma_bf16(tmem + TM_DQ, umma_smem_desc(ads + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
                 umma_smem_desc(ak + ks * 2048, 8192, 1024), idesc_q, ks > 0 ? 1u : 0u);
+    umma_commit(bar_mma);   // dQ is stored while the dK / dV MMAs below still run
     // dV[keys x 64] = P^T dO,  dK[keys x 64] = dS^T Q   (two 128-key halves each)
     constexpr uint32_t idesc_kv = umma_idesc_bf16(128, AB_D, true, true);
 #pragma unroll
@@ -297,13 +300,11 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
                   umma_smem_desc(aq + ks * 2048, 8192, 1024), idesc_kv, ks > 0 ? 1u : 0u);
       }
     }
-    umma_commit(bar_mma);
+    umma_commit(bar_kv);
   }
   __syncwarp();
   mbar_wait(bar_mma, 1);
   tc_fence_after();
-  // every shared-memory operand is dead now: the P region becomes 8 per-warp 4 KB transpose slabs
-  uint8_t* slab = sP + warp * 4096;
 
   // ---- dQ (x 1/sqrt(D): gradient w.r.t. the unscaled projection); part p owns columns 32p..32p+31 ----
   {
@@ -331,6 +332,10 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
       }
     }
   }
+  mbar_wait(bar_kv, 0);
+  tc_fence_after();
+  // every shared-memory operand is dead now: the P region becomes 8 per-warp 4 KB transpose slabs
+  uint8_t* slab = sP + warp * 4096;
   // ---- dK / dV: TMEM lane = key column c = hh*128 + r of the tile.  Each 32-key x 32-dim chunk is
   //      transposed through the warp's slab so that one red.add.v4 instruction covers 4 key rows x
   //      128 contiguous bytes (4 LSU wavefronts) instead of 32 rows x 16 bytes. ----
