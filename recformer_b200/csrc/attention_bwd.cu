@@ -93,7 +93,22 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     mbar_init(bar_mma, 1);
     mbar_init(bar_kv, 1);
     fence_mbar_init();
+    // operand loads first: TMEM allocation and the key-flag set-up (global mask loads) run under their latency
+    mbar_arrive_expect_tx(bar_load, 2 * AB_Q_BYTES + 2 * AB_KV_BYTES);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      tma_load_3d(sQ + c * 8192, &tmQKV64, bar_load, h * AB_D, i0 + c * 64, b);
+      tma_load_3d(sDO + c * 8192, &tmDO, bar_load, h * AB_D, i0 + c * 64, b);
+    }
+#pragma unroll
+    for (int c = 0; c < NK / 64; ++c) {
+      tma_load_3d(sK + c * 8192, &tmQKV64, bar_load, E + h * AB_D, i0 - W + p.shift + c * 64, b);
+      tma_load_3d(sV + c * 8192, &tmQKV64, bar_load, 2 * E + h * AB_D, i0 - W + p.shift + c * 64, b);
+    }
+    tma_load_3d(sK + NK * 128, &tmQKV16, bar_load, E + h * AB_D, 0, b);
+    tma_load_3d(sV + NK * 128, &tmQKV16, bar_load, 2 * E + h * AB_D, 0, b);
   }
+  __syncwarp();
   if (warp == 0) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
@@ -116,19 +131,6 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   constexpr uint32_t TM_DQ = 0, TM_DV = 64, TM_DK = 192;          // phase 2 (dV: 2 x 64, dK: 2 x 64)
 
   if (tid == 0) {
-    mbar_arrive_expect_tx(bar_load, 2 * AB_Q_BYTES + 2 * AB_KV_BYTES);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      tma_load_3d(sQ + c * 8192, &tmQKV64, bar_load, h * AB_D, i0 + c * 64, b);
-      tma_load_3d(sDO + c * 8192, &tmDO, bar_load, h * AB_D, i0 + c * 64, b);
-    }
-#pragma unroll
-    for (int c = 0; c < NK / 64; ++c) {
-      tma_load_3d(sK + c * 8192, &tmQKV64, bar_load, E + h * AB_D, i0 - W + p.shift + c * 64, b);
-      tma_load_3d(sV + c * 8192, &tmQKV64, bar_load, 2 * E + h * AB_D, i0 - W + p.shift + c * 64, b);
-    }
-    tma_load_3d(sK + NK * 128, &tmQKV16, bar_load, E + h * AB_D, 0, b);
-    tma_load_3d(sV + NK * 128, &tmQKV16, bar_load, 2 * E + h * AB_D, 0, b);
     mbar_wait(bar_load, 0);
     tc_fence_after();
     constexpr uint32_t idesc = umma_idesc_bf16(128, NT, false, false);

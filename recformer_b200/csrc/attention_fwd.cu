@@ -86,7 +86,20 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
     mbar_init(bar_load, 1);
     mbar_init(bar_mma, 1);
     fence_mbar_init();
+    // the operand loads are issued first: the TMEM allocation and the key-flag set-up below (global loads
+    // of the mask) then run under their latency
+    mbar_arrive_expect_tx(bar_load, C::Q_BYTES + 2 * C::KV_BYTES);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) tma_load_3d(sQ + c * 8192, &tm64, bar_load, h * HEAD_DIM, i0 + c * 64, b);
+#pragma unroll
+    for (int c = 0; c < NK / 64; ++c) {
+      tma_load_3d(sK + c * 8192, &tm64, bar_load, E + h * HEAD_DIM, i0 - W + p.shift + c * 64, b);
+      tma_load_3d(sV + c * 8192, &tm64, bar_load, 2 * E + h * HEAD_DIM, i0 - W + p.shift + c * 64, b);
+    }
+    tma_load_3d(sK + NK * 128, &tm16, bar_load, E + h * HEAD_DIM, 0, b);
+    tma_load_3d(sV + NK * 128, &tm16, bar_load, 2 * E + h * HEAD_DIM, 0, b);
   }
+  __syncwarp();
   if (warp == 0) {
     tmem_alloc(tmem_slot, C::TMEM_COLS);
     tmem_relinquish();
@@ -108,16 +121,6 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
   const int band_hi = 2 * W - p.hi_cut;   // last in-band column offset of a row
 
   if (tid == 0) {
-    mbar_arrive_expect_tx(bar_load, C::Q_BYTES + 2 * C::KV_BYTES);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) tma_load_3d(sQ + c * 8192, &tm64, bar_load, h * HEAD_DIM, i0 + c * 64, b);
-#pragma unroll
-    for (int c = 0; c < NK / 64; ++c) {
-      tma_load_3d(sK + c * 8192, &tm64, bar_load, E + h * HEAD_DIM, i0 - W + p.shift + c * 64, b);
-      tma_load_3d(sV + c * 8192, &tm64, bar_load, 2 * E + h * HEAD_DIM, i0 - W + p.shift + c * 64, b);
-    }
-    tma_load_3d(sK + NK * 128, &tm16, bar_load, E + h * HEAD_DIM, 0, b);
-    tma_load_3d(sV + NK * 128, &tm16, bar_load, 2 * E + h * HEAD_DIM, 0, b);
     // ---- S = Q K^T ----
     mbar_wait(bar_load, 0);
     tc_fence_after();
