@@ -48,7 +48,9 @@ struct AttnBwdParams {
   const __nv_bfloat16* ctx;   // forward output O (bf16 [B*L, E])
   const float* lse;
   __nv_bfloat16* dqkv;
-  float* dkv;   // fp32 scratch [B*L, 2E]
+  float* dkv;   // fp32 scratch [B*L, 2E] (wide windows: many partial sums per key), or null:
+  float* dkv_cls;   // attention_window 64: dK/dV go straight into dqkv as bf16x2 red.adds (a key receives at most two
+                    // partial sums); only the CLS key, which every tile feeds, is accumulated in fp32 here [B,H,2,64]
   float* dq32;  // fp32 dQ scratch [B*L, E] (wide windows: dQ is accumulated over the window segments) or null
   int B, L, H;
   int shift, hi_cut, use_cls;   // window segment (see attention_fwd.cu)
@@ -355,20 +357,49 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
         *reinterpret_cast<uint4*>(srow + ((u ^ (lane & 7)) << 4)) = make_uint4(v[u * 4], v[u * 4 + 1], v[u * 4 + 2], v[u * 4 + 3]);
     }
     __syncwarp();
+    if (p.dkv != nullptr) {
 #pragma unroll
-    for (int s2 = 0; s2 < 8; ++s2) {
-      const int rl = s2 * 4 + (lane >> 3);          // key row within this warp's 32
-      const int u = lane & 7;                       // 16B unit = 4 floats of the 32-dim chunk
-      const int c = hh * 128 + quad * 32 + rl;      // key column of the tile
-      int j = -1;
-      if (c < NK) j = i0 - W + p.shift + c;
-      else if (c == NK) j = 0;
-      const bool key_ok = (j >= 0 && j < p.L) && (c <= NK) && kflag[c <= NK ? c : 0];
-      const float4 x = *reinterpret_cast<const float4*>(slab + rl * 128 + ((u ^ (rl & 7)) << 4));
-      if (key_ok && p.dkv != nullptr) {
-        float* dst = p.dkv + (static_cast<size_t>(b) * p.L + j) * 2 * E + which * E + h * AB_D + part * 32 + u * 4;
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
-                     : "memory");
+      for (int s2 = 0; s2 < 8; ++s2) {
+        const int rl = s2 * 4 + (lane >> 3);          // key row within this warp's 32
+        const int u = lane & 7;                       // 16B unit = 4 floats of the 32-dim chunk
+        const int c = hh * 128 + quad * 32 + rl;      // key column of the tile
+        int j = -1;
+        if (c < NK) j = i0 - W + p.shift + c;
+        else if (c == NK) j = 0;
+        const bool key_ok = (j >= 0 && j < p.L) && (c <= NK) && kflag[c <= NK ? c : 0];
+        const float4 x = *reinterpret_cast<const float4*>(slab + rl * 128 + ((u ^ (rl & 7)) << 4));
+        if (key_ok) {
+          float* dst = p.dkv + (static_cast<size_t>(b) * p.L + j) * 2 * E + which * E + h * AB_D + part * 32 + u * 4;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
+                       : "memory");
+        }
+      }
+    } else {
+      // bf16 path: lane owns 8 dims (two 16-byte units) of key row rl: one 16-byte bf16x2 red.add per lane,
+      // 8 key rows x 64 contiguous bytes per instruction
+#pragma unroll
+      for (int s2 = 0; s2 < 4; ++s2) {
+        const int rl = s2 * 8 + (lane >> 2);
+        const int uu = lane & 3;
+        const int c = hh * 128 + quad * 32 + rl;
+        int j = -1;
+        if (c < NK) j = i0 - W + p.shift + c;
+        else if (c == NK) j = 0;
+        const bool key_ok = (j >= 0 && j < p.L) && (c <= NK) && kflag[c <= NK ? c : 0];
+        const float4 x0 = *reinterpret_cast<const float4*>(slab + rl * 128 + (((2 * uu) ^ (rl & 7)) << 4));
+        const float4 x1 = *reinterpret_cast<const float4*>(slab + rl * 128 + (((2 * uu + 1) ^ (rl & 7)) << 4));
+        if (key_ok && c == NK) {        // the CLS key: fp32 accumulation over all tiles of the sequence
+          float* dst = p.dkv_cls + ((static_cast<size_t>(b) * p.H + h) * 2 + which) * AB_D + part * 32 + uu * 8;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x0.x), "f"(x0.y), "f"(x0.z), "f"(x0.w)
+                       : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(x1.x), "f"(x1.y), "f"(x1.z), "f"(x1.w)
+                       : "memory");
+        } else if (key_ok) {
+          __nv_bfloat16* dst = p.dqkv + (static_cast<size_t>(b) * p.L + j) * 3 * E + (1 + which) * E + h * AB_D + part * 32 + uu * 8;
+          asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(pack_bf16(x0.x, x0.y)),
+                       "r"(pack_bf16(x0.z, x0.w)), "r"(pack_bf16(x1.x, x1.y)), "r"(pack_bf16(x1.z, x1.w))
+                       : "memory");
+        }
       }
     }
     __syncwarp();
@@ -379,6 +410,18 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
+  }
+}
+
+// dqkv[b, 0, E:3E] = bf16(dkv_cls[b])  for sequences whose position 0 is the global token (bf16 path)
+__global__ void fold_cls_kernel(const float* __restrict__ cls, const uint8_t* __restrict__ mask012, __nv_bfloat16* __restrict__ dqkv,
+                                int L, int H) {
+  const int b = blockIdx.x, E = H * AB_D;
+  if (mask012[static_cast<size_t>(b) * L] != 2) return;
+  for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) {
+    const int which = i / E, hd = i % E, h = hd / AB_D, d = hd % AB_D;
+    dqkv[static_cast<size_t>(b) * L * 3 * E + (1 + which) * E + hd] =
+        __float2bfloat16(cls[((static_cast<size_t>(b) * H + h) * 2 + which) * AB_D + d]);
   }
 }
 
@@ -434,20 +477,23 @@ extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const fl
   const int nseg = (2 * a->w + 1 + 64) / 65;
   RF_REQUIRE(nseg == 1 || a->ws != nullptr, "rf_band_attn_bwd: windows wider than 64 need a workspace");
   float* dq32 = nseg > 1 ? reinterpret_cast<float*>(a->ws) : nullptr;
-  RF_CUDA(cudaMemsetAsync(dkv_scratch, 0, static_cast<size_t>(T) * 2 * E * sizeof(float), stream));
+  const bool bf16_path = nseg == 1;
+  if (bf16_path) {
+    // dK/dV columns of dqkv are accumulated in place: zero them (2-D memset over columns E..3E of every row)
+    RF_CUDA(cudaMemset2DAsync(reinterpret_cast<__nv_bfloat16*>(dqkv) + E, static_cast<size_t>(3) * E * 2, 0,
+                              static_cast<size_t>(2) * E * 2, static_cast<size_t>(T), stream));
+    RF_CUDA(cudaMemsetAsync(dkv_scratch, 0, static_cast<size_t>(B) * a->H * 2 * AB_D * sizeof(float), stream));
+  } else {
+    RF_CUDA(cudaMemsetAsync(dkv_scratch, 0, static_cast<size_t>(T) * 2 * E * sizeof(float), stream));
+  }
   if (dq32) RF_CUDA(cudaMemsetAsync(dq32, 0, static_cast<size_t>(T) * E * sizeof(float), stream));
   AttnBwdParams p;
   p.mask012 = a->mask012; p.lse = lse;
   p.ctx = reinterpret_cast<const __nv_bfloat16*>(ctx);
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
-  p.dkv = dkv_scratch;
+  p.dkv = bf16_path ? nullptr : dkv_scratch;
+  p.dkv_cls = dkv_scratch;
   p.dq32 = dq32;
-  {
-    // profiling aid only: RF_DEBUG_NO_DKV_ATOMICS=1 drops the dK/dV accumulation (wrong results) so
-    // that the cost of the red.add traffic can be measured in isolation
-    static const bool no_atomics = getenv("RF_DEBUG_NO_DKV_ATOMICS") != nullptr;
-    if (no_atomics) p.dkv = nullptr;
-  }
   p.B = a->B; p.L = a->L; p.H = a->H;
   p.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   p.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
@@ -461,6 +507,10 @@ extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const fl
     band_attn_bwd_kernel<<<a->B * a->H * tiles, AB_THREADS, AB_SMEM, stream>>>(*tm64, *tm16, *tmdo, p);
     int rc = check_launch("rf_band_attn_bwd");
     if (rc) return rc;
+  }
+  if (bf16_path) {
+    fold_cls_kernel<<<a->B, 256, 0, stream>>>(dkv_scratch, a->mask012, reinterpret_cast<__nv_bfloat16*>(dqkv), a->L, a->H);
+    return check_launch("rf_band_attn_bwd/fold_cls");
   }
   long long grid = (T * (2 * E / 4) + 255) / 256;
   if (grid > sm_count() * 16) grid = sm_count() * 16;
