@@ -71,9 +71,10 @@ def summarise_rep(rep, dst, topn=12):
             if any(key in cc for key in KEYS) and r[idx] not in ("", "n/a") and "not_issued" not in c and \
                "pct_of_peak_sustained_active" not in c.replace("warps_active", "").replace("issue_active", ""):
                 lines.append(f"  {c:84s} {units[idx]:12s} {r[idx][:40]}")
-        hs = hot.get(name.replace("rf::", ""), hot.get(name, []))
+        norm = lambda n: n.replace("rf::", "").replace("void ", "").replace("(bool)", "").replace("(int)", "").split("(")[0].replace(" ", "")
+        hs = []
         for key, val in hot.items():
-            if key.startswith(name) or name.startswith(key[:60]):
+            if norm(key) == norm(name):
                 hs = val
         if k < len(hs):
             lines.append("  -- SASS hot spots (share of stall samples, instruction, top stall reasons)")
