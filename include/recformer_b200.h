@@ -77,6 +77,12 @@ typedef struct rf_gemm_args {
   float drop_p;
   uint64_t drop_seed;
   int residual_f32;
+  /* Optional extra 64-deep k-block per sequence (dgrad layout, bf16 residual, xk_rows % 256 == 0):
+   *   C[rows of sequence b] += A2[rows, 0:64] * B2[b*64:(b+1)*64, 0:N]
+   * A2 [M,64] bf16, B2 [(M/xk_rows)*64, N] bf16, both row-major and dense; NULL = off. */
+  int xk_rows;
+  const void* A2;
+  const void* B2;
 } rf_gemm_args;
 
 int rf_gemm_bf16(const rf_gemm_args* args, rf_stream_t stream);
@@ -227,6 +233,11 @@ int rf_global_attn_bwd(const rf_global_args* a, const void* dctx_bf16, const flo
                        float* dWqg, float* dbqg, float* dWkg, float* dWvg, float* dbvg, float* ws, rf_stream_t stream);
 int rf_global_attn_bwd_dx(const rf_global_args* a, const float* u, const float* pt, void* dx_bf16, const float* ws,
                           rf_stream_t stream);
+/* Alternative to rf_global_attn_bwd_dx: packs the same token gradients as the operands of the extra
+ * k-block of rf_gemm_bf16 (rf_gemm_args.A2/B2), so that the QKV dgrad GEMM adds them while it
+ * produces dx:  cf [B*L,64] bf16 = (p' | 0 | ds | e_cls | 0),  dmu [B*64,E] bf16 = (dm | 0 | u | dx_cls | 0). */
+int rf_global_attn_bwd_xk(const rf_global_args* a, const float* u, const float* pt, const float* ws, void* cf_bf16,
+                          void* dmu_bf16, rf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Scoring (SURVEY.md §8a Spec S; ref: recformer/models.py:358-369,533-545) and metrics

@@ -20,7 +20,8 @@ class GemmArgs(C.Structure):
                 ("lda", c_int), ("ldb", c_int), ("ldc", c_int), ("ldr", c_int), ("ldaux", c_int),
                 ("a_mn_major", c_int), ("b_mn_major", c_int), ("epi", c_int), ("out_f32", c_int),
                 ("accumulate", c_int), ("split_k", c_int), ("scale", c_float), ("scale_ncols", c_int),
-                ("drop_p", c_float), ("drop_seed", c_u64), ("residual_f32", c_int)]
+                ("drop_p", c_float), ("drop_seed", c_u64), ("residual_f32", c_int),
+                ("xk_rows", c_int), ("A2", c_void_p), ("B2", c_void_p)]
 
 
 class EmbedArgs(C.Structure):
@@ -71,6 +72,7 @@ _SIGS = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p]),
     "rf_global_attn_bwd_dx": (c_int, [P(GlobalArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rf_global_attn_bwd_xk": (c_int, [P(GlobalArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rf_normalize_rows": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "rf_cosine_logits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_void_p]),
     "rf_cosine_topk_ws_bytes": (c_ll, [c_int, c_ll, c_int]),

@@ -43,6 +43,7 @@ struct GemmParams {
   float drop_scale;       // 1/(1-p)
   uint32_t drop_thresh;   // p * 65536, 0 = no dropout
   uint64_t drop_seed;
+  int xk_rows;            // XK: rows of A per batch (one 64-row block of B2 per batch)
 };
 
 template <int BN>
@@ -409,9 +410,14 @@ constexpr uint32_t P_BAR_BYTES = (2 * P_STAGES + 4) * 8 + 16;
 constexpr uint32_t P_EPI_STAGE_BYTES = EPI_WARPS * 4096;
 constexpr uint32_t P_SMEM = P_TILE_BYTES + P_EPI_STAGE_BYTES + P_BAR_BYTES + 2 * P_BN * 4 + 1024;
 
-template <bool A_MN, bool B_MN, int EPI, bool OUT_F32, int RES, bool DROP, bool SPLITK>
+// XK: one extra 64-deep k-block per output tile whose operands come from a second pair of tensors, the A
+// side [M, 64] K-major and the B side batched ([M / xk_rows] blocks of [64, N], N contiguous):
+//   C = A B + A2[rows] B2[batch(rows)]  -- a per-sequence low-rank update riding on the dense GEMM
+// (the global CLS row's token gradients in the QKV dgrad).
+template <bool A_MN, bool B_MN, int EPI, bool OUT_F32, int RES, bool DROP, bool SPLITK, bool XK = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* s_stage = smem + P_TILE_BYTES;
@@ -489,6 +495,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
         }
+        if (XK) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * P_STAGE_BYTES);
+          const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sa = smem + stage * P_STAGE_BYTES;
+          uint8_t* sb = sa + P_A_BYTES;
+          const int xb = (mt * 256) / p.xk_rows;                       // the sequence this 256-row tile lies in
+          tma_load_2d_pair(sa, &tmA2, fb, 0, m0);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) tma_load_2d_pair(sb + c * 8192, &tmB2, fb, n0 + c * 64, xb * 64);
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -515,7 +533,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * P_BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        const int nkb = kb1 - kb0 + (XK ? 1 : 0);
+        for (int it = 0; it < nkb; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t soff = static_cast<uint32_t>(stage) * (P_STAGE_BYTES >> 4);
@@ -523,9 +542,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (elected) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              umma_bf16_pair(d_tmem, ad + k * A_KSTEP, bd + k * B_KSTEP, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_bf16_pair(d_tmem, ad + k * A_KSTEP, bd + k * B_KSTEP, idesc, (it > 0 || k > 0) ? 1u : 0u);
             umma_commit_pair(&empty_bar[stage]);
-            if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[acc]);
+            if (it == nkb - 1) umma_commit_pair(&tfull_bar[acc]);
           }
           __syncwarp();
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
@@ -582,9 +601,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <bool A_MN, bool B_MN, int EPI, bool OUT_F32, int RES, bool DROP, bool SPLITK>
+template <bool A_MN, bool B_MN, int EPI, bool OUT_F32, int RES, bool DROP, bool SPLITK, bool XK = false>
 static int launch_gemm_pair(const rf_gemm_args* a, cudaStream_t stream) {
-  auto kern = gemm_pair_kernel<A_MN, B_MN, EPI, OUT_F32, RES, DROP, SPLITK>;
+  auto kern = gemm_pair_kernel<A_MN, B_MN, EPI, OUT_F32, RES, DROP, SPLITK, XK>;
   static bool attr_set = false;
   if (!attr_set) {
     RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
@@ -594,12 +613,20 @@ static int launch_gemm_pair(const rf_gemm_args* a, cudaStream_t stream) {
   if (!tmA) return RF_ERR_CUDA;
   const CUtensorMap* tmB = B_MN ? get_tmap_2d(a->B, a->K, a->N, a->ldb, 64) : get_tmap_2d(a->B, a->N, a->K, a->ldb, 128);
   if (!tmB) return RF_ERR_CUDA;
+  const CUtensorMap *tmA2 = tmA, *tmB2 = tmB;
+  if (XK) {
+    tmA2 = get_tmap_2d(a->A2, a->M, 64, 64, 128);
+    if (!tmA2) return RF_ERR_CUDA;
+    tmB2 = get_tmap_2d(a->B2, (a->M / a->xk_rows) * 64, a->N, a->N, 64);
+    if (!tmB2) return RF_ERR_CUDA;
+  }
   GemmParams p;
   fill_params(a, p);
+  p.xk_rows = XK ? a->xk_rows : 0;
   const int m_tiles = (a->M + 255) / 256, n_tiles = (a->N + P_BN - 1) / P_BN;
   const int total = m_tiles * n_tiles * p.split_k;
   const int pairs = total < sm_count() / 2 ? total : sm_count() / 2;
-  kern<<<2 * pairs, GEMM_THREADS, P_SMEM, stream>>>(*tmA, *tmB, p);
+  kern<<<2 * pairs, GEMM_THREADS, P_SMEM, stream>>>(*tmA, *tmB, *tmA2, *tmB2, p);
   return check_launch("rf_gemm_bf16(pair)");
 }
 
@@ -642,6 +669,8 @@ extern "C" int rf_gemm_bf16(const rf_gemm_args* a, rf_stream_t stream_) {
   RF_REQUIRE(a->split_k <= 1 || a->out_f32, "rf_gemm_bf16: split_k needs fp32 output");
   RF_REQUIRE(a->epi != RF_EPI_GELU || (a->C2 != nullptr && !a->out_f32), "rf_gemm_bf16: GELU epilogue needs C2, bf16");
   RF_REQUIRE(a->epi != RF_EPI_DGELU || a->aux != nullptr, "rf_gemm_bf16: DGELU epilogue needs aux");
+  RF_REQUIRE(a->A2 == nullptr || (!a->a_mn_major && a->b_mn_major),
+             "rf_gemm_bf16: the extra k-block (A2/B2) is instantiated for the dgrad layout only");
   const int layout = (a->a_mn_major ? 2 : 0) | (a->b_mn_major ? 1 : 0);
   // CTA-pair kernel (256 x 256 tiles) whenever there is more than one 128-row slab of output;
   // the single-CTA kernel covers small problems (e.g. one short sequence).
@@ -689,6 +718,14 @@ extern "C" int rf_gemm_bf16(const rf_gemm_args* a, rf_stream_t stream_) {
     }
     RF_REQUIRE(a->epi == RF_EPI_NONE, "rf_gemm_bf16: epilogue %d unsupported for the dgrad layout", a->epi);
     RF_REQUIRE(res != 2, "rf_gemm_bf16: the dgrad layout takes a bf16 residual");
+    if (a->A2 != nullptr) {
+      RF_REQUIRE(a->B2 != nullptr && pair && res == 1 && a->xk_rows > 0 && a->xk_rows % 256 == 0 &&
+                     a->M % a->xk_rows == 0 && a->N % 8 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(a->A2) | reinterpret_cast<uintptr_t>(a->B2)) & 15) == 0,
+                 "rf_gemm_bf16: the extra k-block needs a bf16 residual, 16-byte aligned A2/B2 and xk_rows %% 256 == 0 "
+                 "dividing M (got M=%d xk_rows=%d)", a->M, a->xk_rows);
+      return launch_gemm_pair<false, true, RF_EPI_NONE, false, 1, false, false, true>(a, stream);
+    }
     return res == 1 ? RF_GEMM(256, false, true, RF_EPI_NONE, false, 1, false, false)
                     : RF_GEMM(256, false, true, RF_EPI_NONE, false, 0, false, false);
   }

@@ -656,7 +656,76 @@ struct BwdWs {
     dxcls = dqf + static_cast<size_t>(B) * GE;
   }
 };
+
+// Packs the token-gradient terms of the CLS row as two bf16 GEMM operands (see rf_global_attn_bwd_xk):
+//   cf [B*L, 64]:  cols 0..11 = p'_h, 16..27 = ds_h, 28 = [token is the CLS], others 0
+//   dmu[B*64, E]:  rows 0..11 = dm_h, 16..27 = u_h,  28 = dx_cls,             others 0
+// One thread per 8 output elements (one 16-byte store).
+__global__ void __launch_bounds__(256)
+global_pack_xk_kernel(const float* __restrict__ pt, const float* __restrict__ dst, const float* __restrict__ dm,
+                      const float* __restrict__ u, const float* __restrict__ dxcls, int B, int L,
+                      __nv_bfloat16* __restrict__ cf, __nv_bfloat16* __restrict__ dmu) {
+  const long long n_cf = static_cast<long long>(B) * L * 8;
+  const long long n_dmu = static_cast<long long>(B) * 64 * (GE / 8);
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = 0.f;
+  __nv_bfloat16* out;
+  if (i < n_cf) {
+    const long long t = i >> 3;
+    const int g = static_cast<int>(i & 7);
+    if (g < 4) {
+      const float* src = ((g < 2) ? pt : dst) + t * 16 + (g & 1) * 8;
+      const float4 a = *reinterpret_cast<const float4*>(src);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+      if ((g & 1) == 0) {
+        const float4 b = *reinterpret_cast<const float4*>(src + 4);
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else if (g == 3) {
+        v[4] = (t % L == 0) ? 1.f : 0.f;
+      }
+    }
+    out = cf + i * 8;
+  } else if (i < n_cf + n_dmu) {
+    const long long r = i - n_cf;
+    const int c8 = static_cast<int>(r % (GE / 8));
+    const int k = static_cast<int>((r / (GE / 8)) & 63);
+    const int b = static_cast<int>(r / (64 * (GE / 8)));
+    const float* src = nullptr;
+    if (k < GH) src = dm + (static_cast<size_t>(b) * GH + k) * GE;
+    else if (k >= 16 && k < 16 + GH) src = u + (static_cast<size_t>(b) * GH + (k - 16)) * GE;
+    else if (k == 28) src = dxcls + static_cast<size_t>(b) * GE;
+    if (src != nullptr) {
+      const float4 a = *reinterpret_cast<const float4*>(src + c8 * 8);
+      const float4 c = *reinterpret_cast<const float4*>(src + c8 * 8 + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    }
+    out = dmu + r * 8;
+  } else {
+    return;
+  }
+  uint4 o;
+  o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(out) = o;
+}
 }  // namespace
+
+extern "C" int rf_global_attn_bwd_xk(const rf_global_args* a, const float* u, const float* pt, const float* ws,
+                                     void* cf, void* dmu, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(a && u && pt && ws && cf && dmu, "rf_global_attn_bwd_xk: null argument");
+  RF_REQUIRE(a->H == GH && a->D == GD, "rf_global_attn_bwd_xk: only H=12, D=64 supported (got %d, %d)", a->H, a->D);
+  RF_REQUIRE(((reinterpret_cast<uintptr_t>(cf) | reinterpret_cast<uintptr_t>(dmu) | reinterpret_cast<uintptr_t>(u)) & 15) == 0,
+             "rf_global_attn_bwd_xk: cf, dmu and u must be 16-byte aligned");
+  const int B = a->B, L = a->L;
+  const BwdWs w(const_cast<float*>(ws), B, L);
+  const long long n = static_cast<long long>(B) * L * 8 + static_cast<long long>(B) * 64 * (GE / 8);
+  global_pack_xk_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      pt, w.dst, w.dm, u, w.dxcls, B, L, reinterpret_cast<__nv_bfloat16*>(cf),
+      reinterpret_cast<__nv_bfloat16*>(dmu));
+  return check_launch("rf_global_attn_bwd_xk/pack");
+}
 
 // Part B of the backward: the gradient the CLS row sends to every token, added into dx; needs the
 // workspace left by rf_global_attn_bwd (dm, ds, dq).  Separate so that part A can run on a side

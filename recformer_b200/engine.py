@@ -232,6 +232,9 @@ class BackwardScratch:
         self.dx = [torch.empty(T, E, **bf) for _ in range(2)]
         self.dkv = torch.empty(T, 2 * E, dtype=torch.float32, device=device)
         self.gws = ops.global_attn_bwd_ws(B, Lp, H, device)
+        # operands of the rank-64 per-sequence update that carries the CLS row's token gradients through the
+        # QKV dgrad GEMM (only when a 256-row output tile never straddles two sequences)
+        self.xk = (torch.empty(T, 64, **bf), torch.empty(B * 64, E, **bf)) if Lp % 256 == 0 and T > 128 else None
 
 
 class EncoderEngine:
@@ -249,6 +252,7 @@ class EncoderEngine:
         self._events: Dict[tuple, torch.cuda.Event] = {}
         self.overlap_global = os.environ.get("RF_DEBUG_NO_OVERLAP") is None
         self._debug_skip_global = os.environ.get("RF_DEBUG_SKIP_GLOBAL") is not None   # timing experiment only (wrong results)
+        self._debug_no_xk = os.environ.get("RF_DEBUG_NO_XK") is not None   # A/B switch: separate dx-update kernel
         self.grad_hook = None      # callable(layer): that layer's gradients are final (dist.GradSync)
 
     # -- helpers -------------------------------------------------------------------------------
@@ -469,6 +473,8 @@ class EncoderEngine:
                 with torch.cuda.stream(side):
                     ops.global_attn_bwd(*gargs, sc.dctx, sv.glob[i], None, G["Wqg"], G["bqg"], G["Wkg"], G["Wvg"],
                                         G["bvg"], ws=sc.gws, drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 2))
+                    if sc.xk is not None and not self._debug_no_xk:
+                        ops.global_attn_bwd_xk(*gargs, sv.glob[i], sc.gws, *sc.xk)
                     ev_a.record(side)
             ops.band_attn_bwd(sv.qkv[i], mask, B, Lp, H, w_one, sv.ctx[i], sv.lse[i], sc.dctx, sc.dqkv, sc.dkv,
                               drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 1))
@@ -476,8 +482,14 @@ class EncoderEngine:
             ops.gemm(sc.dqkv, x, out=G["Wqkv"], a_mn_major=True, b_mn_major=True, accumulate=True,
                      split_k=_pick_split(3 * E, E, T))
             dx = sc.dx[i % 2]
-            ops.gemm(sc.dqkv, W["Wqkv"], out=dx, b_mn_major=True, residual=sc.d_pre)
-            if self._debug_skip_global:
+            fused_dx = self.overlap_global and sc.xk is not None and not self._debug_skip_global and not self._debug_no_xk
+            if fused_dx:
+                # the CLS row's token gradients ride on the dgrad GEMM as one extra per-sequence k-block
+                main.wait_event(ev_a)
+                ops.gemm(sc.dqkv, W["Wqkv"], out=dx, b_mn_major=True, residual=sc.d_pre, xk=(*sc.xk, Lp))
+            else:
+                ops.gemm(sc.dqkv, W["Wqkv"], out=dx, b_mn_major=True, residual=sc.d_pre)
+            if self._debug_skip_global or fused_dx:
                 pass
             elif self.overlap_global:
                 main.wait_event(ev_a)

@@ -40,8 +40,9 @@ def launch_count() -> int:
 # ---------------------------------------------------------------------------------------------
 def gemm(A, B, out=None, *, bias=None, residual=None, aux=None, out2=None, a_mn_major=False, b_mn_major=False,
          epi=EPI_NONE, out_dtype=torch.bfloat16, accumulate=False, split_k=1, scale=1.0, scale_ncols=0,
-         drop_p=0.0, drop_seed=0, M=None, N=None, K=None):
-    """C[M,N] = epilogue(A (*) B).  A: [M,K] (or [K,M] if a_mn_major), B: [N,K] (or [K,N] if b_mn_major)."""
+         drop_p=0.0, drop_seed=0, M=None, N=None, K=None, xk=None):
+    """C[M,N] = epilogue(A (*) B).  A: [M,K] (or [K,M] if a_mn_major), B: [N,K] (or [K,N] if b_mn_major).
+    xk = (A2 [M,64], B2 [M/rows*64, N], rows): extra per-sequence 64-deep k-block (dgrad layout only)."""
     _req(A, torch.bfloat16, "A"), _req(B, torch.bfloat16, "B")
     if M is None:
         M, K_a = (A.shape[1], A.shape[0]) if a_mn_major else (A.shape[0], A.shape[1])
@@ -64,6 +65,12 @@ def gemm(A, B, out=None, *, bias=None, residual=None, aux=None, out2=None, a_mn_
     a.accumulate, a.split_k = int(accumulate), split_k
     a.scale, a.scale_ncols = scale, scale_ncols
     a.drop_p, a.drop_seed = drop_p, drop_seed
+    if xk is not None:
+        A2, B2, rows = xk
+        _req(A2, torch.bfloat16, "A2"), _req(B2, torch.bfloat16, "B2")
+        if tuple(A2.shape) != (M, 64) or tuple(B2.shape) != (M // rows * 64, N):
+            raise ValueError(f"gemm: extra k-block shapes {tuple(A2.shape)}, {tuple(B2.shape)} do not fit M={M} N={N}")
+        a.A2, a.B2, a.xk_rows = A2.data_ptr(), B2.data_ptr(), rows
     check(_lib.lib().rf_gemm_bf16(C.byref(a), _stream()), "rf_gemm_bf16")
     return out
 
@@ -361,6 +368,14 @@ def global_attn_bwd(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, dctx, saved, d
                                         saved["psum"].data_ptr(), _ptr(dx), _ptr(dWqg), _ptr(dbqg), _ptr(dWkg),
                                         _ptr(dWvg), _ptr(dbvg), ws.data_ptr(), _stream()), "rf_global_attn_bwd")
     return ws
+
+
+def global_attn_bwd_xk(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, saved, ws, cf, dmu):
+    """After global_attn_bwd(dx=None): packs the CLS row's token gradients as the two bf16 operands of a
+    rank-64 per-sequence update, dx[b] += cf[b] @ dmu[b] (cf [B*L,64], dmu [B*64,E]), for gemm(..., xk=)."""
+    a = _global_args(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, 0.0, 0)
+    check(_lib.lib().rf_global_attn_bwd_xk(C.byref(a), saved["u"].data_ptr(), saved["pt"].data_ptr(), ws.data_ptr(),
+                                           cf.data_ptr(), dmu.data_ptr(), _stream()), "rf_global_attn_bwd_xk")
 
 
 def global_attn_bwd_dx(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, saved, dx, ws, drop_p=0.0, drop_seed=0):

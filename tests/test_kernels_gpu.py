@@ -81,6 +81,20 @@ def test_gemm_dgrad_layout(M, N, K):
     assert relerr(out, ref) < 1e-2
 
 
+@pytest.mark.parametrize("B,L,N,K", [(2, 256, 768, 2304), (3, 512, 768, 768), (16, 1024, 768, 2304)])
+def test_gemm_dgrad_extra_k_block(B, L, N, K):
+    # dX = dY W + res + per-sequence rank-64 update A2[b] B2[b]: the update rides on the dgrad GEMM as one more k-block
+    M = B * L
+    dY, W, res = rnd(M, K, seed=1), rnd(K, N, seed=2, scale=0.05), rnd(M, N, seed=3)
+    A2, B2 = rnd(M, 64, seed=4), rnd(B * 64, N, seed=5)
+    out = ops.gemm(dY, W, b_mn_major=True, residual=res, xk=(A2, B2, L))
+    ref = dY.float() @ W.float() + res.float()
+    ref += torch.bmm(A2.float().view(B, L, 64), B2.float().view(B, 64, N)).view(M, N)
+    assert relerr(out, ref) < 1e-2
+    with pytest.raises(RuntimeError):        # a 256-row tile must not straddle two sequences
+        ops.gemm(dY, W, b_mn_major=True, residual=res, xk=(A2, rnd(M // 128 * 64, N, seed=6), 128))
+
+
 @pytest.mark.parametrize("T,No,Ki,split", [(64, 128, 128, 1), (1024, 768, 768, 1), (2048, 2304, 768, 4),
                                            (1000 // 8 * 8, 768, 3072, 3)])
 def test_gemm_wgrad_layout(T, No, Ki, split):
@@ -423,7 +437,7 @@ def test_band_attention_bwd(B, L, ragged, w):
         assert err < 2e-2, (name, err)
 
 
-@pytest.mark.parametrize("B,L", [(3, 320), (18, 192)])
+@pytest.mark.parametrize("B,L", [(3, 320), (18, 192), (3, 512)])
 def test_global_attention_bwd(B, L):
     H = 12
     E = H * 64
@@ -456,3 +470,19 @@ def test_global_attention_bwd(B, L):
     for n in ("Wq", "bq", "Wk", "Wv", "bv"):
         assert relerr(grads[n], P[n].grad) < 2e-3, n
     assert P["bk"].grad.abs().max() < 1e-5
+    if L % 256 == 0:
+        # the same token gradients packed as the extra k-block of the QKV dgrad GEMM (engine path for L % 256 == 0)
+        ws = ops.global_attn_bwd_ws(B, L, H, DEV)
+        g2 = {n: torch.zeros_like(t) for n, t in grads.items()}
+        ops.global_attn_bwd(x, mask, Wq, bq, Wk, Wv, bv, B, L, H, dctx, saved, None, g2["Wq"], g2["bq"], g2["Wk"],
+                            g2["Wv"], g2["bv"], ws=ws)
+        cf = torch.empty(B * L, 64, dtype=torch.bfloat16, device=DEV)
+        dmu = torch.empty(B * 64, E, dtype=torch.bfloat16, device=DEV)
+        ops.global_attn_bwd_xk(x, mask, Wq, bq, Wk, Wv, bv, B, L, H, saved, ws, cf, dmu)
+        dqkv, Wqkv = rnd(B * L, 3 * E, seed=11, scale=0.1), rnd(3 * E, E, seed=12, scale=0.03)
+        fused = ops.gemm(dqkv, Wqkv, b_mn_major=True, residual=dx0, xk=(cf, dmu, L))
+        plain = dqkv.float() @ Wqkv.float() + dx0.float()
+        got = fused.float() - plain
+        assert (got - ref_dx).abs().max() < 0.02 * ref_dx.abs().max() + 0.01 * plain.abs().max()
+        upd = torch.bmm(cf.float().view(B, L, 64), dmu.float().view(B, 64, E)).view(B * L, E)
+        assert (upd - ref_dx).abs().max() < 0.02 * ref_dx.abs().max() + 2e-4
