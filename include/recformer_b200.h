@@ -291,6 +291,15 @@ int rf_cast_f32_to_bf16(const float* x, void* y_bf16, long long n, rf_stream_t s
 int rf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16_or_null,
                   long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                   float grad_scale, rf_stream_t stream);
+/* Same update with the per-step scalars read from device memory, hp_dev = {lr, 1 - beta1^t, sqrt(1 - beta2^t),
+ * grad_scale}: the form a captured CUDA graph replays (kernel arguments are frozen at capture). */
+int rf_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16_or_null,
+                      long long n, float beta1, float beta2, float eps, float weight_decay, const float* hp_dev,
+                      rf_stream_t stream);
+/* Dropout masks are Philox draws keyed by (drop_seed argument XOR a library-wide nonce).  The nonce is 0
+ * until this call loads it from device memory (one tiny kernel per translation unit that draws masks);
+ * a captured training step advances *nonce_dev before each replay to draw fresh masks. */
+int rf_set_dropout_nonce(const unsigned long long* nonce_dev, rf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -90,6 +90,9 @@ _SIGS = {
     "rf_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
     "rf_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float,
                               c_float, c_float, c_int, c_float, c_void_p]),
+    "rf_adamw_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float,
+                                  c_float, c_void_p, c_void_p]),
+    "rf_set_dropout_nonce": (c_int, [c_void_p, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -28,6 +28,13 @@ int check_launch(const char* what) {
   return RF_OK;
 }
 
+static nonce_loader_fn g_nonce_loaders[16];
+static int g_n_nonce_loaders = 0;
+int register_nonce_loader(nonce_loader_fn fn) {
+  if (g_n_nonce_loaders < 16) g_nonce_loaders[g_n_nonce_loaders++] = fn;
+  return g_n_nonce_loaders;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -135,4 +142,14 @@ extern "C" {
 const char* rf_last_error(void) { return rf::g_err; }
 int rf_version(void) { return 100; }
 unsigned long long rf_launch_count(void) { return rf::g_launches.load(); }
+int rf_set_dropout_nonce(const unsigned long long* nonce_dev, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(nonce_dev != nullptr, "rf_set_dropout_nonce: null pointer");
+  for (int i = 0; i < rf::g_n_nonce_loaders; ++i) {
+    rf::g_nonce_loaders[i](nonce_dev, stream);
+    const int rc = rf::check_launch("rf_set_dropout_nonce");
+    if (rc) return rc;
+  }
+  return RF_OK;
+}
 }

@@ -22,6 +22,8 @@
 #include "rf_common.h"
 #include "rf_ptx.cuh"
 
+RF_DEFINE_NONCE_LOADER(attn_bwd)
+
 namespace rf {
 
 constexpr int AB_THREADS = 256;

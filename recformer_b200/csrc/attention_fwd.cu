@@ -18,6 +18,8 @@
 #include "rf_common.h"
 #include "rf_ptx.cuh"
 
+RF_DEFINE_NONCE_LOADER(attn_fwd)
+
 namespace rf {
 
 constexpr int ATT_THREADS = 128;

@@ -7,6 +7,8 @@
 #include "rf_common.h"
 #include "rf_ptx.cuh"
 
+RF_DEFINE_NONCE_LOADER(embed_ln)
+
 namespace rf {
 
 constexpr int ROW_THREADS = 256;  // 8 warps = 8 rows per CTA pass
@@ -415,7 +417,11 @@ __global__ void cast_f32_bf16_kernel(const float4* __restrict__ x, uint2* __rest
 
 __global__ void adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
                              float4* __restrict__ v, uint2* __restrict__ shadow, long long n4, float lr, float b1,
-                             float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+                             float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale,
+                             const float* __restrict__ hp) {
+  if (hp != nullptr) {   // per-step scalars from device memory (a captured graph cannot take them as arguments)
+    lr = __ldg(hp); bc1 = __ldg(hp + 1); bc2_sqrt = __ldg(hp + 2); gscale = __ldg(hp + 3);
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
     float* pa = reinterpret_cast<float*>(&pp); float* ga = reinterpret_cast<float*>(&gg);
@@ -557,8 +563,23 @@ extern "C" int rf_adamw_step(float* param, const float* grad, float* exp_avg, fl
   adamw_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(
       reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad), reinterpret_cast<float4*>(exp_avg),
       reinterpret_cast<float4*>(exp_avg_sq), reinterpret_cast<uint2*>(shadow), n4, lr, beta1, beta2, eps, weight_decay,
-      bc1, sqrtf(bc2), grad_scale);
+      bc1, sqrtf(bc2), grad_scale, nullptr);
   return check_launch("rf_adamw_step");
+}
+
+extern "C" int rf_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow,
+                                 long long n, float beta1, float beta2, float eps, float weight_decay,
+                                 const float* hp_dev, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(param && grad && exp_avg && exp_avg_sq && hp_dev && n > 0 && n % 4 == 0, "rf_adamw_step_dev: bad argument");
+  const long long n4 = n / 4;
+  long long grid = (n4 + 255) / 256;
+  if (grid > sm_count() * 16) grid = sm_count() * 16;
+  adamw_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(
+      reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad), reinterpret_cast<float4*>(exp_avg),
+      reinterpret_cast<float4*>(exp_avg_sq), reinterpret_cast<uint2*>(shadow), n4, 0.f, beta1, beta2, eps, weight_decay,
+      1.f, 1.f, 1.f, hp_dev);
+  return check_launch("rf_adamw_step_dev");
 }
 
 // ================================================================================================

@@ -19,6 +19,8 @@
 #include "rf_common.h"
 #include "rf_ptx.cuh"
 
+RF_DEFINE_NONCE_LOADER(gemm)
+
 namespace rf {
 
 constexpr int BM = 128;

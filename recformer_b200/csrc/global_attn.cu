@@ -23,6 +23,8 @@
 #include "rf_common.h"
 #include "rf_ptx.cuh"
 
+RF_DEFINE_NONCE_LOADER(global_attn)
+
 namespace rf {
 
 constexpr int GH = 12;    // heads

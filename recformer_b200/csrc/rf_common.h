@@ -36,4 +36,18 @@ const CUtensorMap* get_tmap_3d(const void* ptr, uint64_t batch, uint64_t rows, u
 
 int sm_count();
 
+// Translation units whose kernels draw dropout masks register a loader for their copy of
+// rf_dropout_nonce (rf_ptx.cuh); rf_set_dropout_nonce() runs every registered loader.
+typedef void (*nonce_loader_fn)(const unsigned long long* dev_src, cudaStream_t stream);
+int register_nonce_loader(nonce_loader_fn fn);
+
 }  // namespace rf
+
+#define RF_DEFINE_NONCE_LOADER(tag)                                                                       \
+  namespace rf {                                                                                          \
+  static __global__ void nonce_load_kernel_##tag(const unsigned long long* src) { rf_dropout_nonce = *src; } \
+  static void nonce_loader_##tag(const unsigned long long* src, cudaStream_t stream) {                    \
+    nonce_load_kernel_##tag<<<1, 1, 0, stream>>>(src);                                                    \
+  }                                                                                                       \
+  static const int nonce_registered_##tag = register_nonce_loader(nonce_loader_##tag);                    \
+  }

@@ -298,7 +298,13 @@ __device__ __forceinline__ float warp_max(float v) {
 // Counter-based RNG for dropout: Philox-4x32-7 keyed by (seed, stream); one call yields 4 x 32
 // random bits for counter `idx`.  Forward and backward regenerate the same mask from the same
 // (seed, element index), so no mask is ever stored.
+//
+// rf_dropout_nonce (one copy per translation unit, loaded from device memory by rf_set_dropout_nonce) is
+// XOR-ed into every seed: the seeds themselves are kernel arguments and therefore frozen into a captured
+// CUDA graph, the nonce is what makes each replay of the graph draw fresh masks.  It is 0 unless set.
+static __device__ unsigned long long rf_dropout_nonce = 0ull;
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t idx) {
+  seed ^= rf_dropout_nonce;
   uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
   uint32_t c0 = static_cast<uint32_t>(idx), c1 = static_cast<uint32_t>(idx >> 32), c2 = 0x9E3779B9u, c3 = 0xBB67AE85u;
 #pragma unroll

@@ -48,6 +48,7 @@ class FlatParams:
         self.flat: Optional[torch.Tensor] = None
         self.grad: Optional[torch.Tensor] = None
         self.shadow: Optional[torch.Tensor] = None
+        self._optimizer_fresh = False
         self.offsets: Dict[str, int] = {}
         self.n_dense = 0
         self.n_decay = 0
@@ -137,12 +138,18 @@ class FlatParams:
 
     def refresh_shadow(self, force: bool = False) -> None:
         sig = sum(self._named[k]._version for k in self._order[: 6 * self.model.config.num_hidden_layers])
+        if self._optimizer_fresh and sig == self._shadow_sig:
+            # the fused AdamW wrote the bf16 shadow together with the fp32 weights: nothing to cast, once
+            self._optimizer_fresh = False
+            return
+        self._optimizer_fresh = False
         if force or sig != self._shadow_sig:
             ops.cast_bf16(self.flat[: self.n_dense], self.shadow)
             self._shadow_sig = sig
 
-    def mark_shadow_fresh(self) -> None:
+    def mark_shadow_fresh(self, by_optimizer: bool = False) -> None:
         self._shadow_sig = sum(self._named[k]._version for k in self._order[: 6 * self.model.config.num_hidden_layers])
+        self._optimizer_fresh = by_optimizer
 
     def prepare_grads(self) -> None:
         """Make every trainable parameter's .grad a view of the flat gradient buffer.  If no

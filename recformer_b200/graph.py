@@ -1,0 +1,93 @@
+"""A finetune step (forward, loss, backward, fused AdamW) captured once as a CUDA graph and replayed.
+
+The step is ~550 kernel launches of 5-150 us each; launched one by one the GPU idles ~2 us between
+consecutive kernels and stalls whenever the Python launch loop falls behind (measured with CUPTI:
+~1 ms of a 14.9 ms step, tools/step_timeline.py).  Replaying the captured graph removes the host from
+the loop.  What a graph freezes are kernel ARGUMENTS, so everything that changes from step to step is
+read from device memory instead:
+  * the batch: copied into static input tensors before each replay;
+  * the dropout masks: every Philox seed is XOR-ed with a nonce the graph loads from device memory
+    (rf_set_dropout_nonce), advanced before each replay;
+  * AdamW's learning rate and bias corrections: rf_adamw_step_dev reads them from a device block.
+The nonce and the optimiser scalars travel in one 24-byte pinned block copied to the device right
+before the launch, so a replay is: fill the static inputs, copy the block, cudaGraphLaunch.  (The copy
+stays outside the graph and rotates over a ring of pinned blocks: the host runs several replays ahead
+of the GPU, a single block baked into the graph would be overwritten before the GPU read it.)
+
+Single-process only (the data-parallel step keeps the eager launch loop with its overlapped NCCL
+all-reduces, recformer_b200.dist.GradSync).
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from . import ops
+
+_NONCE_STRIDE = 0x9E3779B97F4A7C15      # odd 64-bit constant: consecutive steps get far-apart nonces
+_RING = 16
+
+
+class GraphedTrainStep:
+    """step = GraphedTrainStep(model, optimizer, example_batch);  loss = step(batch)
+
+    `model(**batch)` must return the scalar loss (RecformerForSeqRec with labels / candidates).
+    `optimizer` is a recformer_b200.optim.FusedAdamW.  At least one eager step with the same batch
+    shape must have run before (it sizes the engine's workspaces and the optimiser state); the
+    constructor itself does not touch the parameters.  `optimizer.lr` may be changed between calls
+    (schedulers): it is re-read on every replay.  The returned loss is a static device tensor that the
+    next replay overwrites.
+    """
+
+    def __init__(self, model, optimizer, example_batch: Dict[str, torch.Tensor], grad_scale: float = 1.0):
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedTrainStep needs the model on a CUDA device")
+        if optimizer.step_count < 1 or optimizer.exp_avg is None:
+            raise RuntimeError("GraphedTrainStep: run one eager training step first (it allocates the engine "
+                               "workspaces and the optimiser state outside the graph's memory pool)")
+        self.model, self.opt, self.grad_scale = model, optimizer, grad_scale
+        self.static = {k: torch.empty_like(v, device=dev) for k, v in example_batch.items()}
+        for k, v in example_batch.items():
+            self.static[k].copy_(v)
+        # per-step block: [0:4] fp32 optimiser scalars, [4:6] the 64-bit nonce
+        self._ring = [torch.zeros(6, dtype=torch.float32).pin_memory() for _ in range(_RING)]
+        self._ring_f32 = [b.numpy() for b in self._ring]
+        self._ring_i64 = [b[4:6].view(torch.int64).numpy() for b in self._ring]
+        self._ring_done = [None] * _RING
+        self._dev = torch.zeros(6, dtype=torch.float32, device=dev)
+        self._dev_nonce = self._dev[4:6].view(torch.int64)
+        self._replays = 0
+        self.graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(dev)
+        l0 = ops.launch_count()
+        with torch.cuda.graph(self.graph):
+            ops.set_dropout_nonce(self._dev_nonce)
+            loss = model(**self.static)
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step(grad_scale=grad_scale, hp=self._dev[:4])
+            self.loss = loss.detach()
+        optimizer.step_count -= 1          # capture records the launches without executing them
+        self.launches_per_step = ops.launch_count() - l0
+
+    def _send_step_block(self):
+        slot = self._replays % _RING
+        if self._ring_done[slot] is not None:
+            self._ring_done[slot].synchronize()       # the copy that last used this pinned block has run
+        self._ring_f32[slot][:4] = self.opt.step_scalars(self.grad_scale)
+        self._ring_i64[slot][0] = ((self._replays + 1) * _NONCE_STRIDE) & 0x7FFFFFFFFFFFFFFF
+        self._dev.copy_(self._ring[slot], non_blocking=True)
+        ev = self._ring_done[slot] or torch.cuda.Event()
+        ev.record()
+        self._ring_done[slot] = ev
+
+    def __call__(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        for k, v in batch.items():
+            self.static[k].copy_(v, non_blocking=True)
+        self._send_step_block()
+        self._replays += 1
+        self.graph.replay()
+        self.opt.step_count += 1
+        return self.loss

@@ -350,6 +350,20 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, shadow, lr, beta1, beta2, eps, 
                                    _stream()), "rf_adamw_step")
 
 
+def adamw_step_dev(param, grad, exp_avg, exp_avg_sq, shadow, beta1, beta2, eps, weight_decay, hp):
+    """adamw_step with lr / bias corrections / grad_scale read from the device tensor hp (fp32 [>=4])."""
+    _req(hp, torch.float32, "hp")
+    check(_lib.lib().rf_adamw_step_dev(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                       _ptr(shadow), param.numel(), beta1, beta2, eps, weight_decay, hp.data_ptr(),
+                                       _stream()), "rf_adamw_step_dev")
+
+
+def set_dropout_nonce(nonce):
+    """Loads the library-wide dropout nonce from a device int64 tensor (see include/recformer_b200.h)."""
+    _req(nonce, torch.int64, "nonce")
+    check(_lib.lib().rf_set_dropout_nonce(nonce.data_ptr(), _stream()), "rf_set_dropout_nonce")
+
+
 def global_attn_bwd_ws(B, L, H, device):
     nbytes = int(_lib.lib().rf_global_attn_bwd_ws_bytes(B, L, H))
     return torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)

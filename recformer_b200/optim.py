@@ -45,11 +45,20 @@ class FusedAdamW:
         if P.grad is not None:
             P.grad.zero_()
 
+    def step_scalars(self, grad_scale: float = 1.0):
+        """(lr, 1 - beta1^t, sqrt(1 - beta2^t), grad_scale) of the NEXT step: what step(hp=...) reads from
+        device memory when the step is replayed from a CUDA graph (recformer_b200.graph)."""
+        t = self.step_count + 1
+        b1, b2 = self.betas
+        return (float(self.lr), 1.0 - b1 ** t, (1.0 - b2 ** t) ** 0.5, float(grad_scale))
+
     @torch.no_grad()
-    def step(self, grad_scale: float = 1.0, wait_other=None):
+    def step(self, grad_scale: float = 1.0, wait_other=None, hp=None):
         """wait_other: optional callable (GradSync.finish(defer_tail=True)) that is invoked right before the
         segment holding the embedding tables is updated — the dense and no-decay segments run while the
-        embedding gradients are still being all-reduced."""
+        embedding gradients are still being all-reduced.
+        hp: optional fp32 device tensor holding step_scalars(); the kernels then take lr, the bias corrections
+        and grad_scale from it instead of from their arguments (graph capture / replay)."""
         P = self.engine.params
         if P.grad is None:
             raise RuntimeError("FusedAdamW.step() called before any backward pass")
@@ -66,9 +75,14 @@ class FusedAdamW:
             if wait_other is not None and decay and not shadow:
                 wait_other()
                 wait_other = None
+            if hp is not None:
+                ops.adamw_step_dev(P.flat[a:b], P.grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b],
+                                   P.shadow[a:b] if shadow else None, b1, b2, self.eps,
+                                   self.weight_decay if decay else 0.0, hp)
+                continue
             ops.adamw_step(P.flat[a:b], P.grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b],
                            P.shadow[a:b] if shadow else None, self.lr, b1, b2, self.eps,
                            self.weight_decay if decay else 0.0, self.step_count, grad_scale)
         if wait_other is not None:
             wait_other()
-        P.mark_shadow_fresh()
+        P.mark_shadow_fresh(by_optimizer=True)

@@ -331,3 +331,74 @@ def test_sampled_softmax_and_candidates_match_oracle():
     cfg.item_num = N
     out = model(**dev_batch, labels=torch.tensor([1, 2, 3], device=DEV))
     assert out.dim() == 0 and torch.isfinite(out)
+
+
+def _graph_setup(dropout, seed=7):
+    from recformer_b200.optim import FusedAdamW
+    ocfg, cfg, model, sd = build(dict(vocab_size=1500, num_hidden_layers=2, attention_window=[64, 64],
+                                      max_position_embeddings=600), sd_seed=seed)
+    cfg.hidden_dropout_prob = dropout
+    cfg.attention_probs_dropout_prob = dropout
+    model.train()
+    model.longformer.strict_checks = False        # no host synchronisation inside the step (graph capture)
+    model.init_item_embedding(O.make_item_table(50, 768, seed=1).to(DEV))
+    batches = []
+    for s in range(3):
+        b = {k: v.to(DEV) for k, v in O.make_batch(ocfg, 2, 256, seed=20 + s, ragged=True).items()}
+        b["labels"] = torch.tensor([1 + s, 7 + s], device=DEV)
+        batches.append(b)
+    opt = FusedAdamW(model, lr=1e-3, weight_decay=0.01)
+    return model, opt, batches
+
+
+def _eager_step(model, opt, batch):
+    loss = model(**batch)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    return loss.detach().clone()
+
+
+def test_graphed_train_step_matches_eager_steps():
+    """The captured step replays to the same parameters as the kernel-by-kernel loop (no dropout), with a
+    learning-rate change between steps (lr and the AdamW bias corrections are read from device memory)."""
+    from recformer_b200.graph import GraphedTrainStep
+    ref_model, ref_opt, batches = _graph_setup(0.0)
+    model, opt, _ = _graph_setup(0.0)
+    lrs = [1e-3, 5e-4, 2e-3]
+    ref_losses = [_eager_step(ref_model, ref_opt, batches[0])]
+    for lr, b in zip(lrs, batches):
+        ref_opt.lr = lr
+        ref_losses.append(_eager_step(ref_model, ref_opt, b))
+    _eager_step(model, opt, batches[0])            # sizes workspaces + optimiser state
+    step = GraphedTrainStep(model, opt, batches[0])
+    assert step.launches_per_step > 50
+    losses = []
+    for lr, b in zip(lrs, batches):
+        opt.lr = lr
+        losses.append(step(b).clone())
+    assert opt.step_count == ref_opt.step_count == 4
+    # Not bit-equal: gradient sums use atomics, and Adam's first steps move a weight by ~lr * sign(g), so the few
+    # weights whose gradient is pure summation noise differ by O(lr) between ANY two runs.  A wrong learning rate
+    # or bias correction in the replayed step would move every weight: mean |diff| ~ 1e-4..1e-3.
+    for a, r in zip(losses, ref_losses[1:]):
+        assert abs(a.item() - r.item()) < 3e-3 * max(1.0, abs(r.item())), (a.item(), r.item())
+    pa, pr = model.longformer._engine.params.flat, ref_model.longformer._engine.params.flat
+    diff = (pa - pr).abs()
+    assert diff.mean().item() < 2e-5 and diff.max().item() < 2.5 * sum(lrs), (diff.mean().item(), diff.max().item())
+    assert (diff > 1e-4).float().mean().item() < 0.02
+    # the eager path still works on the same model afterwards
+    assert torch.isfinite(_eager_step(model, opt, batches[1]))
+
+
+def test_graphed_train_step_draws_fresh_dropout_masks():
+    from recformer_b200.graph import GraphedTrainStep
+    model, opt, batches = _graph_setup(0.1)
+    _eager_step(model, opt, batches[0])
+    opt.lr = 0.0                                   # parameters frozen: the loss can only move with the masks
+    opt.weight_decay = 0.0
+    step = GraphedTrainStep(model, opt, batches[0])
+    before = model.longformer._engine.params.flat.clone()
+    seen = {round(step(batches[0]).item(), 6) for _ in range(4)}
+    assert len(seen) == 4, seen
+    assert torch.equal(before, model.longformer._engine.params.flat)
