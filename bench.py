@@ -339,12 +339,12 @@ def run_ours(args):
         train_step(model, opt, dev[w % nb], world)
     torch.cuda.synchronize()
 
-    # Single GPU: the whole step (fwd + CE + bwd + AdamW, ~550 launches) is captured once as a CUDA graph and
-    # replayed (recformer_b200.graph); the data-parallel step keeps the eager loop with its overlapped all-reduces.
+    # The whole step (fwd + CE + bwd [+ overlapped gradient all-reduces] + AdamW, ~450 launches) is captured once
+    # as a CUDA graph and replayed (recformer_b200.graph).
     gstep = None
-    if world == 1 and not args.no_graph:
+    if not args.no_graph and (world == 1 or os.environ.get("RF_BENCH_DP_GRAPH", "0") == "1"):
         from recformer_b200.graph import GraphedTrainStep
-        gstep = GraphedTrainStep(model, opt, dev[0])
+        gstep = GraphedTrainStep(model, opt, dev[0], grad_scale=1.0 / world, sync=_SYNC.get(id(model)))
         for w in range(3):
             gstep(dev[w % nb])
         torch.cuda.synchronize()
@@ -422,6 +422,8 @@ def run_ours(args):
                 "roofline": roof, "cpu_baseline": cpu_base, "secondary": secondary}
         print(json.dumps(line), flush=True)
     if world > 1:
+        gstep = None       # a captured graph holds NCCL work: release it before the process group goes away
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
 

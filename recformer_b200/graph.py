@@ -14,8 +14,9 @@ before the launch, so a replay is: fill the static inputs, copy the block, cudaG
 stays outside the graph and rotates over a ring of pinned blocks: the host runs several replays ahead
 of the GPU, a single block baked into the graph would be overwritten before the GPU read it.)
 
-Single-process only (the data-parallel step keeps the eager launch loop with its overlapped NCCL
-all-reduces, recformer_b200.dist.GradSync).
+Data-parallel: pass the step's recformer_b200.dist.GradSync as `sync`; its per-layer asynchronous NCCL
+all-reduces (and the deferred embedding-table tail) are captured with the kernels -- NCCL joins the
+capture through the events torch records between the compute stream and its own.
 """
 from __future__ import annotations
 
@@ -40,7 +41,7 @@ class GraphedTrainStep:
     next replay overwrites.
     """
 
-    def __init__(self, model, optimizer, example_batch: Dict[str, torch.Tensor], grad_scale: float = 1.0):
+    def __init__(self, model, optimizer, example_batch: Dict[str, torch.Tensor], grad_scale: float = 1.0, sync=None):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedTrainStep needs the model on a CUDA device")
@@ -67,7 +68,8 @@ class GraphedTrainStep:
             loss = model(**self.static)
             optimizer.zero_grad()
             loss.backward()
-            optimizer.step(grad_scale=grad_scale, hp=self._dev[:4])
+            tail = sync.finish(defer_tail=True) if sync is not None else None
+            optimizer.step(grad_scale=grad_scale, wait_other=tail, hp=self._dev[:4])
             self.loss = loss.detach()
         optimizer.step_count -= 1          # capture records the launches without executing them
         self.launches_per_step = ops.launch_count() - l0
