@@ -26,7 +26,7 @@ RF_DEFINE_NONCE_LOADER(attn_bwd)
 
 namespace rf {
 
-constexpr int AB_THREADS = 256;
+constexpr int AB_THREADS = 512;
 constexpr int AB_W = 32;
 constexpr int AB_NK = 128 + 2 * AB_W;   // 192
 constexpr int AB_NT = AB_NK + 16;       // 208
@@ -41,7 +41,7 @@ constexpr uint32_t AB_OFF_DS = AB_OFF_P + AB_P_BYTES;
 constexpr uint32_t AB_OFF_FLAG = AB_OFF_DS + AB_P_BYTES;
 constexpr uint32_t AB_OFF_BAR = AB_OFF_FLAG + 208;
 constexpr uint32_t AB_OFF_DELTA = AB_OFF_BAR + 64;
-constexpr uint32_t AB_SMEM = AB_OFF_DELTA + 2 * 128 * 4 + 1024;
+constexpr uint32_t AB_SMEM = AB_OFF_DELTA + 4 * 128 * 4 + 1024;
 static_assert(AB_OFF_V % 1024 == 0 && AB_OFF_P % 1024 == 0, "swizzled tiles need 1024B alignment");
 static_assert(AB_SMEM <= 227 * 1024, "shared memory budget");
 
@@ -78,10 +78,12 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   uint64_t* bar_mma = bar_load + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
   uint64_t* bar_kv = bar_load + 3;     // dK / dV accumulators ready (dQ is published earlier on bar_mma)
-  float* s_delta = reinterpret_cast<float*>(smem + AB_OFF_DELTA);   // [2][128] partial row sums
+  float* s_delta = reinterpret_cast<float*>(smem + AB_OFF_DELTA);   // [4][128] partial row sums
 
-  // 8 warps: TMEM lane quadrant = warp % 4 (rows 32*quad..), `part` = warp / 4 splits every row's
-  // columns between two threads so that 8 warps (not 4) cover the softmax-backward arithmetic.
+  // 16 warps: TMEM lane quadrant = warp % 4 (rows 32*quad..), `part` = warp / 4 splits every row's work
+  // between four threads (the kernel runs one CTA per SM: its warps are all the latency hiding there is):
+  //   softmax backward: parts 0..2 take one 32-column window chunk each, part 3 the CLS column + the zero fill
+  //   delta / dQ: 16 of the 64 head dims each;  dK / dV: part = (dK | dV, low | high 32 dims)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, part = warp >> 2;
   const int tiles_per_seq = (p.L + 127) / 128;
@@ -152,13 +154,13 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   const int r = quad * 32 + lane;       // query row of the tile == TMEM lane
   const int i = i0 + r;
   const bool in_seq = i < p.L;
-  // this thread's half (32 of 64 dims) of the saved context row: loaded while TMA / the first MMAs run
-  uint4 o_raw[4];
+  // this thread's quarter (16 of 64 dims) of the saved context row: loaded while TMA / the first MMAs run
+  uint4 o_raw[2];
   {
     const uint4* op = reinterpret_cast<const uint4*>(p.ctx + (static_cast<size_t>(b) * p.L + (in_seq ? i : 0)) * E +
-                                                     h * AB_D + part * 32);
+                                                     h * AB_D + part * 16);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) o_raw[u] = in_seq ? op[u] : make_uint4(0, 0, 0, 0);
+    for (int u = 0; u < 2; ++u) o_raw[u] = in_seq ? op[u] : make_uint4(0, 0, 0, 0);
   }
   __syncwarp();
   mbar_wait(bar_mma, 0);
@@ -173,9 +175,9 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   const uint64_t rowid = (static_cast<uint64_t>(b) * p.H + h) * p.L + (in_seq ? i : 0);
   constexpr int DGRP = NT / 8;
   const bool g_ok = kflag[NK] != 0;
-  // window chunks of this row block: quad, quad+1 (part 0) and quad+2 + the CLS column (part 1)
-  const int cc_lo = quad + (part == 0 ? 0 : 2);
-  const int cc_hi = quad + (part == 0 ? 2 : 3);
+  // window chunks of this row block: quad + part for parts 0..2; part 3 has the CLS column and the zero chunks
+  const int cc_lo = quad + part;
+  const int cc_hi = part < 3 ? quad + part + 1 : cc_lo;
 
   auto chunk_keep = [&](int cc) -> uint32_t {
     if (p.drop_thresh == 0) return 0xFFFFFFFFu;
@@ -190,13 +192,13 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   };
 
   // ---- delta_i = sum_j P'_ij dP_ij = dO_i . O_i  (O = sum_j P'_ij V_j is the saved forward output):
-  //      each part dots its 32 dims (dO from the swizzled shared-memory tile, O from registers) ----
+  //      each part dots its 16 dims (dO from the swizzled shared-memory tile, O from registers) ----
   float delta = 0.f;
   {
     const uint8_t* drow = sDO + (r >> 6) * 8192 + (r & 63) * 128;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint4 d = *reinterpret_cast<const uint4*>(drow + (((part * 4 + u) ^ (r & 7)) << 4));
+    for (int u = 0; u < 2; ++u) {
+      const uint4 d = *reinterpret_cast<const uint4*>(drow + (((part * 2 + u) ^ (r & 7)) << 4));
       const uint4 o = o_raw[u];
       const float2 d0 = unpack_bf16(d.x), d1 = unpack_bf16(d.y), d2 = unpack_bf16(d.z), d3 = unpack_bf16(d.w);
       const float2 o0 = unpack_bf16(o.x), o1 = unpack_bf16(o.y), o2 = unpack_bf16(o.z), o3 = unpack_bf16(o.w);
@@ -205,7 +207,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     }
   }
   float pg = 0.f, pg_d = 0.f, keep_g = 1.f, dpg = 0.f;
-  if (part == 1) {   // warp-uniform
+  if (part == 3) {   // warp-uniform
     uint32_t gs[16], gd[16];
     tmem_ld16(lane_base + TM_S + NK, gs);
     tmem_ld16(lane_base + TM_DP + NK, gd);
@@ -221,14 +223,14 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   }
   s_delta[part * 128 + r] = delta;
   __syncthreads();
-  delta = row_valid ? s_delta[r] + s_delta[128 + r] : 0.f;   // masked rows may hold non-finite garbage in O / dO
+  // masked rows may hold non-finite garbage in O / dO
+  delta = row_valid ? (s_delta[r] + s_delta[128 + r]) + (s_delta[256 + r] + s_delta[384 + r]) : 0.f;
 
-  // ---- pass B: P' and dS -> shared memory (window chunks as in pass A; the remaining all-zero
-  //      chunks are split by parity) ----
+  // ---- pass B: P' and dS -> shared memory (one window chunk per part 0..2; part 3 fills the all-zero chunks) ----
 #pragma unroll 1
   for (int cc = 0; cc < NK / 32; ++cc) {
     const bool in_win = cc >= quad && cc < quad + 3;
-    const bool mine = in_win ? (cc >= cc_lo && cc < cc_hi) : ((cc & 1) == part);
+    const bool mine = in_win ? (cc >= cc_lo && cc < cc_hi) : (part == 3);
     if (!mine) continue;   // warp-uniform
     uint4 po[4], so[4];
     if (in_win) {
@@ -269,12 +271,13 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   }
   {
     // global chunk = P/dS chunk 3 (columns 192..255): column 192 holds the CLS key, the rest is zero;
-    // part 1 (which owns pg) writes units 0..3, part 0 units 4..7
+    // part 3 (which owns pg) writes units 0..3, part 0 units 4..7
     const float dsg = pg * (keep_g * dpg - delta);
     const uint32_t roff = 3 * 16384 + r * 128;
 #pragma unroll
     for (int uu = 0; uu < 4; ++uu) {
-      const int u = part == 1 ? uu : uu + 4;
+      if (part == 1 || part == 2) continue;   // warp-uniform
+      const int u = part == 3 ? uu : uu + 4;
       const uint32_t o = roff + ((u ^ (r & 7)) << 4);
       *reinterpret_cast<uint4*>(sP + o) = (u == 0) ? make_uint4(pack_bf16(pg_d, 0.f), 0, 0, 0) : make_uint4(0, 0, 0, 0);
       *reinterpret_cast<uint4*>(sDS + o) = (u == 0) ? make_uint4(pack_bf16(dsg, 0.f), 0, 0, 0) : make_uint4(0, 0, 0, 0);
@@ -312,23 +315,23 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   mbar_wait(bar_mma, 1);
   tc_fence_after();
 
-  // ---- dQ (x 1/sqrt(D): gradient w.r.t. the unscaled projection); part p owns columns 32p..32p+31 ----
+  // ---- dQ (x 1/sqrt(D): gradient w.r.t. the unscaled projection); part p owns columns 16p..16p+15 ----
   {
-    uint32_t v[32];
-    tmem_ld32(lane_base + TM_DQ + part * 32, v);
+    uint32_t v[16];
+    tmem_ld16(lane_base + TM_DQ + part * 16, v);
     tmem_ld_wait();
     if (in_seq && p.dq32 != nullptr) {
-      float* orow = p.dq32 + (static_cast<size_t>(b) * p.L + i) * E + h * AB_D + part * 32;
+      float* orow = p.dq32 + (static_cast<size_t>(b) * p.L + i) * E + h * AB_D + part * 16;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
+      for (int j = 0; j < 16; j += 4)
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + j), "f"(__uint_as_float(v[j]) * 0.125f),
                      "f"(__uint_as_float(v[j + 1]) * 0.125f), "f"(__uint_as_float(v[j + 2]) * 0.125f),
                      "f"(__uint_as_float(v[j + 3]) * 0.125f)
                      : "memory");
     } else if (in_seq) {
-      __nv_bfloat16* orow = p.dqkv + (static_cast<size_t>(b) * p.L + i) * 3 * E + h * AB_D + part * 32;
+      __nv_bfloat16* orow = p.dqkv + (static_cast<size_t>(b) * p.L + i) * 3 * E + h * AB_D + part * 16;
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
+      for (int j = 0; j < 16; j += 8) {
         uint4 o;
         o.x = pack_bf16(__uint_as_float(v[j]) * 0.125f, __uint_as_float(v[j + 1]) * 0.125f);
         o.y = pack_bf16(__uint_as_float(v[j + 2]) * 0.125f, __uint_as_float(v[j + 3]) * 0.125f);
@@ -340,15 +343,15 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   }
   mbar_wait(bar_kv, 0);
   tc_fence_after();
-  // every shared-memory operand is dead now: the P region becomes 8 per-warp 4 KB transpose slabs
+  // every shared-memory operand is dead now: the P region becomes 16 per-warp 4 KB transpose slabs
   uint8_t* slab = sP + warp * 4096;
   // ---- dK / dV: TMEM lane = key column c = hh*128 + r of the tile.  Each 32-key x 32-dim chunk is
   //      transposed through the warp's slab so that one red.add.v4 instruction covers 4 key rows x
   //      128 contiguous bytes (4 LSU wavefronts) instead of 32 rows x 16 bytes. ----
+  const int which = part >> 1, dhalf = part & 1;   // this warp: dK (0) or dV (1), dims 32*dhalf .. +31
 #pragma unroll 1
-  for (int t = 0; t < 4; ++t) {       // (hh, which) : which = 0 -> dK, 1 -> dV
-    const int hh = t >> 1, which = t & 1;
-    const uint32_t tcol = (which == 0 ? TM_DK : TM_DV) + hh * 64 + part * 32;
+  for (int hh = 0; hh < 2; ++hh) {    // the two 128-key halves of the tile
+    const uint32_t tcol = (which == 0 ? TM_DK : TM_DV) + hh * 64 + dhalf * 32;
     uint32_t v[32];
     tmem_ld32(lane_base + tcol, v);
     tmem_ld_wait();
@@ -371,7 +374,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
         const bool key_ok = (j >= 0 && j < p.L) && (c <= NK) && kflag[c <= NK ? c : 0];
         const float4 x = *reinterpret_cast<const float4*>(slab + rl * 128 + ((u ^ (rl & 7)) << 4));
         if (key_ok) {
-          float* dst = p.dkv + (static_cast<size_t>(b) * p.L + j) * 2 * E + which * E + h * AB_D + part * 32 + u * 4;
+          float* dst = p.dkv + (static_cast<size_t>(b) * p.L + j) * 2 * E + which * E + h * AB_D + dhalf * 32 + u * 4;
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
                        : "memory");
         }
@@ -391,13 +394,13 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
         const float4 x0 = *reinterpret_cast<const float4*>(slab + rl * 128 + (((2 * uu) ^ (rl & 7)) << 4));
         const float4 x1 = *reinterpret_cast<const float4*>(slab + rl * 128 + (((2 * uu + 1) ^ (rl & 7)) << 4));
         if (key_ok && c == NK) {        // the CLS key: fp32 accumulation over all tiles of the sequence
-          float* dst = p.dkv_cls + ((static_cast<size_t>(b) * p.H + h) * 2 + which) * AB_D + part * 32 + uu * 8;
+          float* dst = p.dkv_cls + ((static_cast<size_t>(b) * p.H + h) * 2 + which) * AB_D + dhalf * 32 + uu * 8;
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x0.x), "f"(x0.y), "f"(x0.z), "f"(x0.w)
                        : "memory");
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(x1.x), "f"(x1.y), "f"(x1.z), "f"(x1.w)
                        : "memory");
         } else if (key_ok) {
-          __nv_bfloat16* dst = p.dqkv + (static_cast<size_t>(b) * p.L + j) * 3 * E + (1 + which) * E + h * AB_D + part * 32 + uu * 8;
+          __nv_bfloat16* dst = p.dqkv + (static_cast<size_t>(b) * p.L + j) * 3 * E + (1 + which) * E + h * AB_D + dhalf * 32 + uu * 8;
           asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(pack_bf16(x0.x, x0.y)),
                        "r"(pack_bf16(x0.z, x0.w)), "r"(pack_bf16(x1.x, x1.y)), "r"(pack_bf16(x1.z, x1.w))
                        : "memory");
