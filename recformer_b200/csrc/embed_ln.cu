@@ -290,16 +290,44 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
   for (int k = 0; k < NV8; ++k)
 #pragma unroll
     for (int e = 0; e < 8; ++e) dg[k][e] = db[k][e] = dbias[k][e] = 0.f;
-  for (int t = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); t < T; t += gridDim.x * (ROW_THREADS / 32)) {
-    const float mean = stats[2 * t], rstd = stats[2 * t + 1];
+  // The next row's loads are issued before the current row is processed (register double buffer): with one
+  // CTA of 8 warps per SM a warp that loads, reduces and stores row after row keeps only 4.5 KB in flight,
+  // and the kernel runs at DRAM latency instead of DRAM bandwidth.
+  const int t_step = gridDim.x * (ROW_THREADS / 32);
+  int t = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  float nx[NV8][8];
+  uint4 ndy[NV8];
+  float2 nst = make_float2(0.f, 1.f);
+  if (t < T) {
+    load_row_f32<NV8>(x + static_cast<size_t>(t) * E, lane, nx);
     const uint4* dr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(t) * E);
+#pragma unroll
+    for (int k = 0; k < NV8; ++k) ndy[k] = dr[k * 32 + lane];
+    nst = *reinterpret_cast<const float2*>(stats + 2 * t);
+  }
+  for (; t < T; t += t_step) {
+    const float mean = nst.x, rstd = nst.y;
     float xh[NV8][8], gy[NV8][8];
-    load_row_f32<NV8>(x + static_cast<size_t>(t) * E, lane, xh);
+    uint4 cdy[NV8];
+#pragma unroll
+    for (int k = 0; k < NV8; ++k) {
+      cdy[k] = ndy[k];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) xh[k][e] = nx[k][e];
+    }
+    if (t + t_step < T) {
+      const int tn = t + t_step;
+      load_row_f32<NV8>(x + static_cast<size_t>(tn) * E, lane, nx);
+      const uint4* dr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(tn) * E);
+#pragma unroll
+      for (int k = 0; k < NV8; ++k) ndy[k] = dr[k * 32 + lane];
+      nst = *reinterpret_cast<const float2*>(stats + 2 * tn);
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < NV8; ++k) {
       const int c = (k * 32 + lane) * 8;
-      const uint4 draw = dr[k * 32 + lane];
+      const uint4 draw = cdy[k];
       const float2 d0 = unpack_bf16(draw.x), d1 = unpack_bf16(draw.y), d2 = unpack_bf16(draw.z), d3 = unpack_bf16(draw.w);
       const float dv[8] = {d0.x, d0.y, d1.x, d1.y, d2.x, d2.y, d3.x, d3.y};
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
