@@ -6,10 +6,11 @@ R=${1:-r01}
 mkdir -p gpurun_out
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/${R}_bench_plain.log 2> gpurun_out/${R}_bench_plain.err || { echo "plain bench failed"; tail -5 gpurun_out/${R}_bench_plain.err; exit 1; }
 tail -1 gpurun_out/${R}_bench_plain.log | cut -c1-300
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2200 --csv --log-file gpurun_out/${R}_launches_bench.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_ncu_launch.log 2>&1; echo "launch list exit $?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2200 --csv --log-file gpurun_out/${R}_launches_bench.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/${R}_ncu_launch.log 2>&1; echo "launch list exit $?"
 timeout 600 python tools/prof_kernels.py gemm_qkv gemm_up_gelu gemm_down_res gemm_dgrad_dgelu gemm_wgrad_up attn_fwd attn_bwd global_fwd global_bwd ln_fwd ln_bwd colsum_3072 score_topk > gpurun_out/${R}_kernel_times.log 2>&1; cat gpurun_out/${R}_kernel_times.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gemm_pair" -s 5 -c 15 -o gpurun_out/${R}_ncu_gemm python tools/prof_kernels.py gemm_qkv gemm_up_gelu gemm_down_res gemm_dgrad_dgelu gemm_wgrad_up > /dev/null 2>&1; echo "ncu gemm exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"band_attn_fwd" -s 1 -c 1 -o gpurun_out/${R}_ncu_attn_fwd python tools/prof_kernels.py attn_fwd > /dev/null 2>&1; echo "ncu attn fwd exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"band_attn_bwd" -s 1 -c 1 -o gpurun_out/${R}_ncu_attn_bwd python tools/prof_kernels.py attn_fwd attn_bwd > /dev/null 2>&1; echo "ncu attn bwd exit $?"
 RF_PROF_ITEMS=250000 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"cosine_pair" -s 1 -c 1 -o gpurun_out/${R}_ncu_score python tools/prof_kernels.py score_topk > /dev/null 2>&1; echo "ncu score exit $?"
-timeout 600 ncu --set full --clock-control none -k regex:"embed_ln_fwd|layernorm_fwd|layernorm_bwd|adamw|global_mix|global_dots" -c 10 -o gpurun_out/${R}_ncu_membound python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-secondary > /dev/null 2>&1; echo "ncu membound exit $?"
+timeout 600 ncu --set full --clock-control none -k regex:"embed_ln_fwd|layernorm_fwd|global_mix|global_dots" -c 6 -o gpurun_out/${R}_ncu_membound python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-secondary --no-graph > /dev/null 2>&1; echo "ncu membound exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"layernorm_bwd|adamw|colsum" -c 6 -o gpurun_out/${R}_ncu_membound_bwd python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-secondary --no-graph > /dev/null 2>&1; echo "ncu membound bwd exit $?"

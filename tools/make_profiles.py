@@ -2,7 +2,7 @@
 
     python tools/make_profiles.py r01
 Writes, per round:
-  profiles/<r>_launches_bench.csv        the ncu launch list of `bench.py --steps 1 --warmup 3` (as captured)
+  profiles/<r>_launches_bench.csv        the ncu launch list of `bench.py --steps 1 --warmup 3 --no-graph` (as captured)
   profiles/<r>_launches_summary.txt      per-kernel totals / shares of that list (cold-cache, serialised)
   profiles/<r>_kernel_times.txt          CUDA-event timings of each hot kernel at the C2 shapes (no profiler)
   profiles/<r>_ncu_<set>.txt             roofline counters + stall reasons + SASS hot spots of the --set full captures
@@ -96,7 +96,7 @@ def summarise_launches(path, dst):
         a = agg.setdefault(r[kn].split("(")[0][:64], [0, 0.0]); a[0] += 1; a[1] += v
     tot = sum(v[1] for v in agg.values())
     out = [f"# per-kernel totals of {os.path.basename(path)}: ncu --metrics gpu__time_duration.sum --clock-control none on",
-           "# `bench.py --steps 1 --warmup 3` (4 training steps + eval leg); cold-cache, serialised launch times",
+           "# `bench.py --steps 1 --warmup 3 --no-graph` (4 training steps + eval leg); cold-cache, serialised launch times",
            f"{'kernel':66s} {'n':>5s} {'total us':>10s} {'avg us':>8s} {'share':>6s}"]
     for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
         out.append(f"{k:66s} {v[0]:5d} {v[1]/1e3:10.1f} {v[1]/1e3/v[0]:8.1f} {100*v[1]/tot:5.1f}%")
