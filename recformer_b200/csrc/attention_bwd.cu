@@ -114,6 +114,21 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     tma_load_3d(sK + NK * 128, &tmQKV16, bar_load, E + h * AB_D, 0, b);
     tma_load_3d(sV + NK * 128, &tmQKV16, bar_load, 2 * E + h * AB_D, 0, b);
   }
+  // Per-row global loads issued right away, next to the TMA loads (they are first used after the S / dP MMAs; issued
+  // any later they arrive after the TMA data and the row waits for them): this thread's quarter (16 of 64 dims) of
+  // the saved context row, the row's log-sum-exp and its mask bytes.
+  const int r = quad * 32 + lane;       // query row of the tile == TMEM lane
+  const int i = i0 + r;
+  const bool in_seq = i < p.L;
+  uint4 o_raw[2];
+  {
+    const uint4* op = reinterpret_cast<const uint4*>(p.ctx + (static_cast<size_t>(b) * p.L + (in_seq ? i : 0)) * E +
+                                                     h * AB_D + part * 16);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) o_raw[u] = in_seq ? op[u] : make_uint4(0, 0, 0, 0);
+  }
+  const float lse = in_seq ? p.lse[(static_cast<size_t>(b) * p.H + h) * p.L + i] : 0.f;
+  const uint8_t m_row = mrow[in_seq ? i : 0], m_cls = mrow[0];
   __syncwarp();
   if (warp == 0) {
     tmem_alloc(tmem_slot, 512);
@@ -151,24 +166,12 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
                 k > 0 ? 1u : 0u);
     umma_commit(bar_mma);
   }
-  const int r = quad * 32 + lane;       // query row of the tile == TMEM lane
-  const int i = i0 + r;
-  const bool in_seq = i < p.L;
-  // this thread's quarter (16 of 64 dims) of the saved context row: loaded while TMA / the first MMAs run
-  uint4 o_raw[2];
-  {
-    const uint4* op = reinterpret_cast<const uint4*>(p.ctx + (static_cast<size_t>(b) * p.L + (in_seq ? i : 0)) * E +
-                                                     h * AB_D + part * 16);
-#pragma unroll
-    for (int u = 0; u < 2; ++u) o_raw[u] = in_seq ? op[u] : make_uint4(0, 0, 0, 0);
-  }
   __syncwarp();
   mbar_wait(bar_mma, 0);
   tc_fence_after();
 
-  const bool is_global_row = (i == 0) && (mrow[0] == 2);
-  const bool row_valid = in_seq && (mrow[in_seq ? i : 0] != 0) && !is_global_row;
-  const float lse = in_seq ? p.lse[(static_cast<size_t>(b) * p.H + h) * p.L + i] : 0.f;
+  const bool is_global_row = (i == 0) && (m_cls == 2);
+  const bool row_valid = in_seq && (m_row != 0) && !is_global_row;
   const uint32_t lane_base = tmem + (static_cast<uint32_t>(quad * 32) << 16);
   const float LOG2E = 1.4426950408889634f;
   const float lse2 = lse * LOG2E;

@@ -101,6 +101,8 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
     tma_load_3d(sK + NK * 128, &tm16, bar_load, E + h * HEAD_DIM, 0, b);
     tma_load_3d(sV + NK * 128, &tm16, bar_load, 2 * E + h * HEAD_DIM, 0, b);
   }
+  // the row's mask bytes are loaded now, next to the TMA loads (first used after the S MMA)
+  const uint8_t m_row = mrow[(i0 + tid) < p.L ? (i0 + tid) : 0], m_cls = mrow[0];
   __syncwarp();
   if (warp == 0) {
     tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -145,7 +147,7 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
   // ---- softmax: thread r owns query row i0 + r (TMEM lane r) ----
   const int r = tid;
   const int i = i0 + r;
-  const bool row_valid = (i < p.L) && (mrow[i < p.L ? i : 0] != 0);
+  const bool row_valid = (i < p.L) && (m_row != 0);
   const uint32_t lane_base = tmem + (static_cast<uint32_t>(warp * 32) << 16);
   constexpr int WIN_CH = 2 * W / 32 + 1;   // 32-column chunks that can hold this warp's band
   const float LOG2E = 1.4426950408889634f;
@@ -252,7 +254,7 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
   tc_fence_after();
 
   const float inv_l = l > 0.0f ? 1.0f / l : 0.0f;
-  const bool is_global_row = (i == 0) && (mrow[0] == 2);
+  const bool is_global_row = (i == 0) && (m_cls == 2);
   const bool do_store = (i < p.L) && !is_global_row;
   __nv_bfloat16* orow = p.ctx + (static_cast<size_t>(b) * p.L + (do_store ? i : 0)) * E + h * HEAD_DIM;
 #pragma unroll
