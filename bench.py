@@ -340,9 +340,9 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     # The whole step (fwd + CE + bwd [+ overlapped gradient all-reduces] + AdamW, ~450 launches) is captured once
-    # as a CUDA graph and replayed (recformer_b200.graph).
+    # as a CUDA graph and replayed (recformer_b200.graph); RF_BENCH_DP_GRAPH=0 keeps eager launches for N > 1.
     gstep, graph_error = None, None
-    if not args.no_graph and (world == 1 or os.environ.get("RF_BENCH_DP_GRAPH", "0") == "1"):
+    if not args.no_graph and (world == 1 or os.environ.get("RF_BENCH_DP_GRAPH", "1") == "1"):
         from recformer_b200.graph import GraphedTrainStep
         try:
             gstep = GraphedTrainStep(model, opt, dev[0], grad_scale=1.0 / world, sync=_SYNC.get(id(model)))
@@ -428,10 +428,16 @@ def run_ours(args):
                 "roofline": roof, "cpu_baseline": cpu_base, "secondary": secondary}
         print(json.dumps(line), flush=True)
     if world > 1:
-        gstep = None       # a captured graph holds NCCL work: release it before the process group goes away
+        # A captured graph keeps NCCL resources alive: destroy_process_group() with the graph still around hung in the
+        # first 2-GPU trial, so the graph is released first; the timer bounds any teardown stall (the line is printed).
+        guard = threading.Timer(60.0, lambda: os._exit(0))
+        guard.daemon = True
+        guard.start()
+        gstep = None
         torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
+        guard.cancel()
 
 
 def main():
