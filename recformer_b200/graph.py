@@ -16,7 +16,9 @@ of the GPU, a single block baked into the graph would be overwritten before the 
 
 Data-parallel: pass the step's recformer_b200.dist.GradSync as `sync`; its per-layer asynchronous NCCL
 all-reduces (and the deferred embedding-table tail) are captured with the kernels -- NCCL joins the
-capture through the events torch records between the compute stream and its own.
+capture through the events torch records between the compute stream and its own.  Drop the GraphedTrainStep
+(it keeps NCCL resources alive) BEFORE torch.distributed.destroy_process_group(): tearing the group down
+under a live graph hangs.  Measured at 2 and 8 GPUs: 15.2 / 15.85 ms per step against 15.9 / 16.5 ms eager.
 """
 from __future__ import annotations
 
