@@ -119,6 +119,45 @@ def test_flat_parameter_plan():
     assert all(v % 8 == 0 for v in o.values())
 
 
+def test_shadow_refresh_skips_the_cast_once_after_the_fused_optimizer(monkeypatch):
+    """FusedAdamW writes the bf16 shadow together with the fp32 weights; the next (forced) refresh must not
+    cast again, the one after that must, and an in-place update of a dense weight always must."""
+    from recformer_b200 import engine as eng
+    cfg = rb.RecformerConfig(attention_window=[64], vocab_size=60, num_hidden_layers=1, max_position_embeddings=70,
+                             max_item_embeddings=51)
+    m = rb.RecformerModel(cfg)
+    fp: FlatParams = m._engine.params
+    fp.flat = torch.zeros(fp.n_total)                      # host stand-ins: only the bookkeeping is under test
+    fp.shadow = torch.zeros(fp.n_dense, dtype=torch.bfloat16)
+    casts = []
+    monkeypatch.setattr(eng.ops, "cast_bf16", lambda src, dst: casts.append(src.numel()))
+    fp.refresh_shadow(force=True)
+    assert casts == [fp.n_dense]
+    fp.refresh_shadow(force=False)                         # nothing changed: no cast
+    assert len(casts) == 1
+    fp.mark_shadow_fresh(by_optimizer=True)
+    fp.refresh_shadow(force=True)                          # training forward right after optimizer.step(): skipped
+    assert len(casts) == 1
+    fp.refresh_shadow(force=True)                          # a second forward without a step: forced again
+    assert len(casts) == 2
+    fp.mark_shadow_fresh(by_optimizer=True)
+    with torch.no_grad():
+        m.encoder.layer[0].attention.self.query.weight.add_(1.0)     # someone else touched a dense weight
+    fp.refresh_shadow(force=False)
+    assert len(casts) == 3
+
+
+def test_adamw_step_scalars_follow_torch_bias_corrections():
+    from recformer_b200.optim import FusedAdamW
+    cfg = rb.RecformerConfig(attention_window=[64], vocab_size=60, num_hidden_layers=1, max_position_embeddings=70,
+                             max_item_embeddings=51)
+    opt = FusedAdamW(rb.RecformerModel(cfg), lr=3e-4, betas=(0.9, 0.999))
+    opt.step_count = 4                                     # the scalars describe the NEXT step (t = 5)
+    lr, bc1, bc2_sqrt, gs = opt.step_scalars(grad_scale=0.125)
+    assert lr == 3e-4 and gs == 0.125
+    assert abs(bc1 - (1 - 0.9 ** 5)) < 1e-12 and abs(bc2_sqrt - (1 - 0.999 ** 5) ** 0.5) < 1e-12
+
+
 def test_split_k_heuristic():
     assert _pick_split(2304, 768, 16384) >= 2       # 27 pair-tiles on 74 CTA pairs -> split
     assert _pick_split(768, 768, 128) == 1           # too few K blocks to split
