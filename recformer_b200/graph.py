@@ -39,8 +39,11 @@ class GraphedTrainStep:
     `optimizer` is a recformer_b200.optim.FusedAdamW.  At least one eager step with the same batch
     shape must have run before (it sizes the engine's workspaces and the optimiser state); the
     constructor itself does not touch the parameters.  `optimizer.lr` may be changed between calls
-    (schedulers): it is re-read on every replay.  The returned loss is a static device tensor that the
-    next replay overwrites.
+    (schedulers): it is re-read on every replay; betas, eps, weight_decay, the dropout probabilities, the
+    batch shape and which parameters are trainable are frozen at capture (build a new GraphedTrainStep after
+    changing any of them).  The returned loss is a static device tensor that the next replay overwrites.
+    The forward must not synchronise with the host: set `model.longformer.strict_checks = False` (the
+    device-side input checks still run; `model.longformer._engine.check_errors()` reads their flags).
     """
 
     def __init__(self, model, optimizer, example_batch: Dict[str, torch.Tensor], grad_scale: float = 1.0, sync=None):
