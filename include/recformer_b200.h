@@ -233,7 +233,7 @@ int rf_global_attn_bwd(const rf_global_args* a, const void* dctx_bf16, const flo
                        float* dWqg, float* dbqg, float* dWkg, float* dWvg, float* dbvg, float* ws, rf_stream_t stream);
 int rf_global_attn_bwd_dx(const rf_global_args* a, const float* u, const float* pt, void* dx_bf16, const float* ws,
                           rf_stream_t stream);
-/* Alternative to rf_global_attn_bwd_dx: packs the same token gradients as the operands of the extra
+/* (autograd of HF:963-1056, token-gradient part.)  Alternative to rf_global_attn_bwd_dx: packs the same token gradients as the operands of the extra
  * k-block of rf_gemm_bf16 (rf_gemm_args.A2/B2), so that the QKV dgrad GEMM adds them while it
  * produces dx:  cf [B*L,64] bf16 = (p' | 0 | ds | e_cls | 0),  dmu [B*64,E] bf16 = (dm | 0 | u | dx_cls | 0). */
 int rf_global_attn_bwd_xk(const rf_global_args* a, const float* u, const float* pt, const float* ws, void* cf_bf16,
@@ -291,12 +291,15 @@ int rf_cast_f32_to_bf16(const float* x, void* y_bf16, long long n, rf_stream_t s
 int rf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16_or_null,
                   long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                   float grad_scale, rf_stream_t stream);
-/* Same update with the per-step scalars read from device memory, hp_dev = {lr, 1 - beta1^t, sqrt(1 - beta2^t),
- * grad_scale}: the form a captured CUDA graph replays (kernel arguments are frozen at capture). */
+/* Same update (ref: optimization.py:7-34, torch.optim.AdamW) with the per-step scalars read from device memory,
+ * hp_dev = {lr, 1 - beta1^t, sqrt(1 - beta2^t), grad_scale}: the form a captured CUDA graph replays (kernel
+ * arguments are frozen at capture; the reference's linear-warmup scheduler changes lr every step). */
 int rf_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16_or_null,
                       long long n, float beta1, float beta2, float eps, float weight_decay, const float* hp_dev,
                       rf_stream_t stream);
-/* Dropout masks are Philox draws keyed by (drop_seed argument XOR a library-wide nonce).  The nonce is 0
+/* Dropout sites: ref: recformer/models.py:134 (embeddings), HF:585,1035 (attention probabilities), HF:1069,1128
+ * (dense outputs); torch draws them from its generator state.  Here the masks are Philox draws keyed by
+ * (drop_seed argument XOR a library-wide nonce).  The nonce is 0
  * until this call loads it from device memory (one tiny kernel per translation unit that draws masks);
  * a captured training step advances *nonce_dev before each replay to draw fresh masks. */
 int rf_set_dropout_nonce(const unsigned long long* nonce_dev, rf_stream_t stream);
