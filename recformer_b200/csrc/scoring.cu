@@ -532,8 +532,9 @@ ce_row_kernel(float* __restrict__ logits, const int64_t* __restrict__ labels, in
 #pragma unroll
   for (int w = 0; w < 8; ++w) l += red[w];
   const long long lab = labels[b];
+  const bool lab_ok = lab >= 0 && lab < N;   // out of range: the loss becomes NaN (torch device-asserts here)
   const float lse = m + logf(l);
-  if (tid == 0) atomicAdd(loss, (lse - row[lab]) / B);
+  if (tid == 0) atomicAdd(loss, lab_ok ? (lse - row[lab]) / B : NAN);
   __syncthreads();
   const float invB = 1.0f / B;
   for (long long n = tid; n < N; n += 256) {
@@ -554,8 +555,9 @@ mlm_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labe
   __nv_bfloat16* drow = dlogits + row_off;
   const long long lab = labels[blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (lab < 0 || lab >= V) {   // ignored row
+  if (lab < 0 || lab >= V) {   // ignore_index (negative) row; a label beyond the vocabulary poisons the loss
     for (long long n = tid * 8; n < ld; n += 256 * 8) *reinterpret_cast<uint4*>(drow + n) = make_uint4(0, 0, 0, 0);
+    if (lab >= V && tid == 0) atomicAdd(loss, NAN);
     return;
   }
   __shared__ float red[8];
@@ -641,6 +643,7 @@ cand_logits_kernel(const float* __restrict__ pooled, const __nv_bfloat16* __rest
   const float scale = inv_temp / fmaxf(sqrtf(warp_sum(q)), 1e-8f);
   for (int c = blockIdx.x * 8 + warp; c < C; c += gridDim.x * 8) {
     long long id = cand[static_cast<size_t>(b) * C + c];
+    const bool id_ok = id >= 0 && id < N;     // out-of-range candidate: NaN logit (never a silent clamp)
     id = id < 0 ? 0 : (id >= N ? N - 1 : id);
     const uint4* yr = reinterpret_cast<const uint4*>(yn + id * 768);
     float acc = 0.f;
@@ -652,7 +655,7 @@ cand_logits_kernel(const float* __restrict__ pooled, const __nv_bfloat16* __rest
              xv[k * 8 + 4] * y2.x + xv[k * 8 + 5] * y2.y + xv[k * 8 + 6] * y3.x + xv[k * 8 + 7] * y3.y;
     }
     acc = warp_sum(acc);
-    if (lane == 0) logits[static_cast<size_t>(b) * C + c] = acc * scale;
+    if (lane == 0) logits[static_cast<size_t>(b) * C + c] = id_ok ? acc * scale : NAN;
   }
 }
 

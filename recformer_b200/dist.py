@@ -96,6 +96,9 @@ class GradSync:
 
     def __init__(self, model, group=None, passes_per_step: int = 1):
         enc = getattr(model, "longformer", model)
+        inside = {id(p) for p in enc.parameters()}
+        # trainable parameters outside the encoder's flat buffer (pretraining lm_head.*): reduced in finish()
+        self.extra_params = [p for p in model.parameters() if id(p) not in inside and p.requires_grad]
         self.engine = enc._engine
         self.group = group
         self.passes_per_step = passes_per_step   # encoder backward passes per optimizer step (pretraining: 4)
@@ -146,6 +149,9 @@ class GradSync:
                 gaps.append((pos, a))
             pos = max(pos, b)
         gaps.sort(key=lambda r: r[1] - r[0])            # small ranges first, the embedding tables last
+        for p in self.extra_params:
+            if p.grad is not None:
+                self._works.append(dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         tail = None
         for k, (a, b) in enumerate(gaps):
             w = dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True)

@@ -96,13 +96,30 @@ class FlatParams:
         self._named = named
 
     # -- storage -------------------------------------------------------------------------------
+    def _aliased(self, device) -> bool:
+        """True when every Parameter object of the module tree is still the one planned AND still a view at its
+        offset of the flat buffer (a replaced module / Parameter, load_state_dict(assign=True) or .to() breaks it)."""
+        if self.flat is None or self.flat.device != torch.device(device):
+            return False
+        base = self.flat.data_ptr()
+        live = dict(self.model.named_parameters())
+        if len(live) != len(self._order):
+            return False
+        for k in self._order:
+            p = live.get(k)
+            if p is None or p is not self._named[k] or p.data_ptr() != base + 4 * self.offsets[k]:
+                return False
+        return True
+
     def ensure(self, device) -> None:
-        first = self._named[self._order[0]]
-        if (self.flat is not None and self.flat.device == first.device == torch.device(device)
-                and first.data_ptr() == self.flat.data_ptr()
-                and self._named[self._order[-1]].data_ptr() ==
-                self.flat.data_ptr() + 4 * self.offsets[self._order[-1]]):
+        if self._aliased(device):
             return
+        live = dict(self.model.named_parameters())
+        if set(live) != set(self._order) or any(live[k].shape != self._named[k].shape for k in self._order):
+            raise RuntimeError("recformer_b200: the module tree's parameters changed shape or name since the engine was "
+                               "planned; rebuild the model")
+        self._named = live                      # adopt replaced Parameter objects (their values are copied below)
+        first = self._named[self._order[0]]
         if first.device != torch.device(device):
             raise RuntimeError(f"recformer_b200: parameters are on {first.device}, inputs on {device}")
         if first.device.type != "cuda":
@@ -135,6 +152,12 @@ class FlatParams:
         for s in shape:
             n *= s
         return base[o:o + n].view(shape)
+
+    def invalidate(self) -> None:
+        """Force the next forward to recast the bf16 shadow (after weights were edited through `.data`, which
+        does not bump the autograd version counters refresh_shadow() keys on)."""
+        self._shadow_sig = None
+        self._optimizer_fresh = False
 
     def refresh_shadow(self, force: bool = False) -> None:
         sig = sum(self._named[k]._version for k in self._order[: 6 * self.model.config.num_hidden_layers])
@@ -251,6 +274,7 @@ class EncoderEngine:
         self.params = FlatParams(model)
         self._free: Dict[tuple, List[SavedActivations]] = {}
         self._bwd: Dict[tuple, BackwardScratch] = {}
+        self._attn_ws: Dict[tuple, Optional[torch.Tensor]] = {}     # wide-window scratch, never freed (graphs hold it)
         self._err = None
         self._call = 0
         # The global (CLS) row only depends on the layer input (forward) / on dctx (backward) and is made
@@ -273,6 +297,14 @@ class EncoderEngine:
         pool = self._free.setdefault(key, [])
         if len(pool) < 4:
             pool.append(sv)
+
+    def attn_ws(self, B: int, Lp: int, w_one: int, device) -> Optional[torch.Tensor]:
+        """Engine-owned band-attention scratch for windows wider than 64, one per (B, Lp, w) and kept for the
+        engine's life: a captured step graph holds its address, and no other engine or stream ever sees it."""
+        key = (B, Lp, w_one, str(device))
+        if key not in self._attn_ws:
+            self._attn_ws[key] = ops.band_attn_ws(B, Lp, self.cfg.num_attention_heads, w_one, device)
+        return self._attn_ws[key]
 
     def side_stream(self, device) -> torch.cuda.Stream:
         key = str(device)
@@ -400,7 +432,7 @@ class EncoderEngine:
                     ev_g.record(side)
             ops.gemm(x, W["Wqkv"], out=sv.qkv[k], bias=W["bqkv"], scale=0.125, scale_ncols=E)
             ops.band_attn_fwd(sv.qkv[k], mask, B, Lp, H, w_one, ctx=sv.ctx[k], lse=sv.lse[k], drop_p=sv.drop_attn,
-                              drop_seed=self._seed(sv, i, 1))
+                              drop_seed=self._seed(sv, i, 1), ws=self.attn_ws(B, Lp, w_one, device))
             if self._debug_skip_global:
                 pass
             elif self.overlap_global:
@@ -484,7 +516,7 @@ class EncoderEngine:
                         ops.global_attn_bwd_xk(*gargs, sv.glob[i], sc.gws, *sc.xk)
                     ev_a.record(side)
             ops.band_attn_bwd(sv.qkv[i], mask, B, Lp, H, w_one, sv.ctx[i], sv.lse[i], sc.dctx, sc.dqkv, sc.dkv,
-                              drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 1))
+                              drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 1), ws=self.attn_ws(B, Lp, w_one, device))
             ops.colsum(sc.dqkv, G["bqkv"])
             ops.gemm(sc.dqkv, x, out=G["Wqkv"], a_mn_major=True, b_mn_major=True, accumulate=True,
                      split_k=_pick_split(3 * E, E, T))

@@ -20,7 +20,9 @@ class Ranker(nn.Module):
         self.ce = nn.CrossEntropyLoss()
 
     def forward(self, scores: torch.Tensor, labels: torch.Tensor) -> List[float]:
-        labels = labels.squeeze()
+        # ref utils.py:83 squeezes; a final batch of ONE user then has a 0-d target and the reference's CE raises
+        # (caught upstream as loss 0.0, utils.py:84-89).  view(-1) keeps the (B,) target for every B.
+        labels = labels.view(-1).long()
         loss = self.ce(scores, labels).item()
         predicts = scores[torch.arange(scores.size(0), device=scores.device), labels].unsqueeze(-1)
         valid_length = (scores > -MAX_VAL).sum(-1).float()

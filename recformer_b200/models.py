@@ -194,7 +194,13 @@ class RecformerModel(nn.Module):
         return self.embeddings.word_embeddings
 
     def set_input_embeddings(self, value):
+        # the engine re-adopts the new Parameter on the next forward (FlatParams.ensure compares identities)
         self.embeddings.word_embeddings = value
+
+    def load_state_dict(self, *a, **kw):
+        out = super().load_state_dict(*a, **kw)
+        self._engine.params.invalidate()        # copy_() under no_grad may not bump the version counters
+        return out
 
     def named_parameters(self, *a, **kw):   # engine views must see the module's own parameters
         return super().named_parameters(*a, **kw)

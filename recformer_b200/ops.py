@@ -157,44 +157,42 @@ def colsum(x, out):
 
 
 # ---------------------------------------------------------------------------------------------
-_ATTN_WS = {}
-
-
 def band_attn_ws(B, L, H, w, device):
-    """Workspace for windows wider than attention_window 64 (cached per shape; None for w == 32)."""
+    """Scratch for windows wider than attention_window 64 (None for w == 32).  The caller OWNS the buffer: the
+    engine keeps one per (B, L, w) for its whole life (a captured CUDA graph bakes the pointer in, so it must
+    never be freed or shared with another engine / stream); direct callers get a fresh allocation per call."""
     nbytes = int(_lib.lib().rf_band_attn_ws_bytes(B, L, H, w))
     if nbytes == 0:
         return None
-    key = (B, L, H, w, str(device))
-    ws = _ATTN_WS.get(key)
-    if ws is None:
-        _ATTN_WS.clear()
-        ws = _ATTN_WS[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
-    return ws
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
-def _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed):
+def _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed, ws=None):
     a = AttnArgs()
     a.qkv, a.mask012 = qkv.data_ptr(), mask012.data_ptr()
     a.B, a.L, a.H, a.D, a.w = B, L, H, 64, w
     a.drop_p, a.drop_seed = drop_p, drop_seed
-    a.ws = _ptr(band_attn_ws(B, L, H, w, qkv.device))
-    return a
+    if ws is None:
+        ws = band_attn_ws(B, L, H, w, qkv.device)
+    elif ws.numel() < int(_lib.lib().rf_band_attn_ws_bytes(B, L, H, w)):
+        raise ValueError("band attention: workspace too small for this shape")
+    a.ws = _ptr(ws)
+    return a, ws
 
 
-def band_attn_fwd(qkv, mask012, B, L, H, w, ctx=None, lse=None, drop_p=0.0, drop_seed=0):
+def band_attn_fwd(qkv, mask012, B, L, H, w, ctx=None, lse=None, drop_p=0.0, drop_seed=0, ws=None):
     _req(qkv, torch.bfloat16, "qkv"), _req(mask012, torch.uint8, "mask012")
     if ctx is None:
         ctx = torch.empty(B * L, H * 64, dtype=torch.bfloat16, device=qkv.device)
     if lse is None:
         lse = torch.empty(B, H, L, dtype=torch.float32, device=qkv.device)
-    a = _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed)
+    a, ws = _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed, ws)
     check(_lib.lib().rf_band_attn_fwd(C.byref(a), ctx.data_ptr(), lse.data_ptr(), _stream()), "rf_band_attn_fwd")
     return ctx, lse
 
 
-def band_attn_bwd(qkv, mask012, B, L, H, w, ctx, lse, dctx, dqkv, dkv_cls, drop_p=0.0, drop_seed=0):
-    a = _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed)
+def band_attn_bwd(qkv, mask012, B, L, H, w, ctx, lse, dctx, dqkv, dkv_cls, drop_p=0.0, drop_seed=0, ws=None):
+    a, ws = _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed, ws)
     check(_lib.lib().rf_band_attn_bwd(C.byref(a), ctx.data_ptr(), lse.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(),
                                       dkv_cls.data_ptr(), _stream()), "rf_band_attn_bwd")
     return dqkv

@@ -1,7 +1,14 @@
 """Fused AdamW over the engine's flat parameter buffer (ref: optimization.py:7-34 builds torch
 AdamW with no weight decay on biases / LayerNorm).  One kernel launch per contiguous parameter
 segment (dense encoder weights — which also get their bf16 shadow refreshed in the same pass —,
-other matrices, no-decay vectors); frozen parameters are skipped."""
+other matrices, no-decay vectors); frozen parameters are skipped.
+
+Trainable parameters of the wrapped model that live OUTSIDE the encoder's flat buffer (the pretraining `lm_head.*`, a
+trainable `item_embedding` made by `init_item_embedding(None)`) are driven by an internal `torch.optim.AdamW` with the
+reference's grouping (no decay on biases / LayerNorm weights, ref: optimization.py:12-22), stepped and zeroed together
+with the fused segments; `dist.GradSync.finish()` all-reduces their gradients too.  Note that `RecformerForSeqRec`
+detaches the item table and the pooled vectors in `similarity_score()` (the table is frozen upstream), so a loss built
+from returned SCORES carries no gradient; the trained paths are `forward(labels=...)`."""
 from __future__ import annotations
 
 from typing import List, Tuple
@@ -20,6 +27,17 @@ class FusedAdamW:
         self.exp_avg = None
         self.exp_avg_sq = None
         self._segments: List[Tuple[int, int, bool, bool]] = []
+        self._plan_sig = None
+        # trainable parameters the flat buffer does not hold
+        inside = {id(p) for p in enc.parameters()}
+        named_extra = [(k, p) for k, p in model.named_parameters() if id(p) not in inside and p.requires_grad]
+        self.extra_params = [p for _, p in named_extra]
+        self._extra_opt = None
+        if named_extra:
+            nd = ("bias", "LayerNorm.weight", "layer_norm.weight")
+            groups = [{"params": [p for k, p in named_extra if not any(t in k for t in nd)], "weight_decay": weight_decay},
+                      {"params": [p for k, p in named_extra if any(t in k for t in nd)], "weight_decay": 0.0}]
+            self._extra_opt = torch.optim.AdamW([g for g in groups if g["params"]], lr=lr, betas=betas, eps=eps)
 
     def _plan(self):
         P = self.engine.params
@@ -40,10 +58,16 @@ class FusedAdamW:
                 segs.append(cur)
         self._segments = [tuple(s) for s in segs]
 
+    def _signature(self):
+        P = self.engine.params
+        return tuple((id(P._named[k]), P._named[k].requires_grad) for k in P._order)
+
     def zero_grad(self, set_to_none: bool = False):
         P = self.engine.params
         if P.grad is not None:
             P.grad.zero_()
+        if self._extra_opt is not None:
+            self._extra_opt.zero_grad(set_to_none=True)
 
     def step_scalars(self, grad_scale: float = 1.0):
         """(lr, 1 - beta1^t, sqrt(1 - beta2^t), grad_scale) of the NEXT step: what step(hp=...) reads from
@@ -65,7 +89,26 @@ class FusedAdamW:
         if self.exp_avg is None or self.exp_avg.data_ptr() == 0 or self.exp_avg.numel() != P.n_total:
             self.exp_avg = torch.zeros_like(P.flat)
             self.exp_avg_sq = torch.zeros_like(P.flat)
+            self._plan_sig = None
+        if hp is None:                   # (a captured step froze its plan; see GraphedTrainStep)
+            sig = self._signature()      # requires_grad flips / replaced Parameters since the last step re-plan
+            if sig != self._plan_sig:
+                self._plan()
+                self._plan_sig = sig
+        elif self._plan_sig is None:
             self._plan()
+            self._plan_sig = self._signature()
+        if self._extra_opt is not None:
+            if hp is not None:
+                raise RuntimeError("FusedAdamW: parameters outside the encoder's flat buffer cannot be stepped from a "
+                                   "captured graph (hp=...); step them eagerly")
+            for g in self._extra_opt.param_groups:
+                g["lr"] = self.lr
+            if grad_scale != 1.0:
+                for p in self.extra_params:
+                    if p.grad is not None:
+                        p.grad.mul_(grad_scale)
+            self._extra_opt.step()
         self.step_count += 1
         b1, b2 = self.betas
         segs = list(self._segments)

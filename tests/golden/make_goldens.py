@@ -61,9 +61,11 @@ def case_forward(name, cfg_kw, B, L, ragged, N, sd_seed=0, batch_seed=0, hidden_
     return g
 
 
-def case_train(name, cfg_kw, B, L, N, sd_seed=0, batch_seed=0):
+def case_train(name, cfg_kw, B, L, N, sd_seed=0, batch_seed=0, n_samples=0):
     """Loss + gradient fingerprints from the reference's own autograd (dropout disabled by
-    eval(): the reference's train-mode RNG stream cannot be reproduced, SURVEY.md §7 hard part 7)."""
+    eval(): the reference's train-mode RNG stream cannot be reproduced, SURVEY.md §7 hard part 7).
+    With n_samples > 0 every gradient tensor additionally stores `n_samples` entries at seeded random
+    flat positions (`sample_idx`, `sample`) plus its abs-max, for element-wise checks of the big tensors."""
     ocfg = O.OracleConfig(**cfg_kw)
     items = O.make_item_table(N, ocfg.hidden_size, seed=1)
     m, _ = build_ref_seqrec(ocfg, sd_seed, items)
@@ -79,6 +81,10 @@ def case_train(name, cfg_kw, B, L, N, sd_seed=0, batch_seed=0):
         grads[k] = {"norm": gflat.norm().item(), "head": gflat[:32].clone(), "sum": gflat.double().sum().item()}
         if gflat.numel() <= 4096:
             grads[k]["full"] = p.grad.clone()
+        if n_samples > 0:
+            rng = __import__("numpy").random.default_rng(len(k) * 7919 + gflat.numel())
+            idx = torch.from_numpy(rng.integers(0, gflat.numel(), size=min(n_samples, gflat.numel())))
+            grads[k].update(sample_idx=idx, sample=gflat[idx].clone(), absmax=gflat.abs().max().item())
     print(f"{name}: loss {loss.item():.6f}, {len(grads)} grads")
     return {"cfg": cfg_kw, "B": B, "L": L, "N": N, "sd_seed": sd_seed, "batch_seed": batch_seed,
             "labels": labels, "loss": loss.item(), "grads": grads}
@@ -168,6 +174,12 @@ def main():
         torch.save(g, path)
         print("updated", path, os.path.getsize(path) / 1e6, "MB")
         return
+    if "--only-train12" in sys.argv:       # add the 12-layer C2-shaped training case (BASELINE configs[1] shape)
+        g = torch.load(path, weights_only=False)
+        g["train_c2_12layer"] = case_train("train_c2_12layer", dict(), B=4, L=1024, N=5000, batch_seed=11, n_samples=512)
+        torch.save(g, path)
+        print("updated", path, os.path.getsize(path) / 1e6, "MB")
+        return
     g = {}
     g["fwd_small_ragged"] = case_forward("fwd_small_ragged", small_cfg(), B=3, L=200, ragged=True, N=300, hidden_stride=3)
     g["fwd_small_dense"] = case_forward("fwd_small_dense", small_cfg(), B=2, L=256, ragged=False, N=300, hidden_stride=3)
@@ -180,6 +192,7 @@ def main():
                                       batch_seed=3)
     g["train_small"] = case_train("train_small", small_cfg(), B=3, L=200, N=50)
     g["pretrain_small"] = case_pretrain("pretrain_small", small_cfg(), B=4, La=300, Lb=97)
+    g["train_c2_12layer"] = case_train("train_c2_12layer", dict(), B=4, L=1024, N=5000, batch_seed=11, n_samples=512)
     g["ranker"] = case_ranker()
     g["tokenizer"] = case_tokenizer()
     path = os.path.join(OUT, "reference_goldens.pt")

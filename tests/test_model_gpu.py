@@ -117,6 +117,39 @@ def test_train_step_matches_reference_gradients(goldens):
     print("worst relative grad-norm error", worst)
 
 
+def test_train_step_12layer_c2_shape_matches_reference(goldens):
+    """The headline configuration's own shape: 12 layers, ragged rows of 1024 tokens, full-softmax CE over 5 000
+    items (BASELINE configs[1], B=4 so that the fp32 CPU reference finishes) — loss and EVERY gradient tensor against
+    the unmodified reference's autograd (tests/golden/make_goldens.py::case_train with 512 seeded samples per tensor)."""
+    g = goldens["train_c2_12layer"]
+    ocfg, cfg, model, sd = build(g["cfg"], g["sd_seed"])
+    cfg.hidden_dropout_prob = 0.0
+    cfg.attention_probs_dropout_prob = 0.0
+    model.train()
+    batch = {k: v.to(DEV) for k, v in O.make_batch(ocfg, g["B"], g["L"], seed=g["batch_seed"], ragged=True).items()}
+    model.init_item_embedding(O.make_item_table(g["N"], 768, seed=1).to(DEV))
+    loss = model(**batch, labels=g["labels"].to(DEV))
+    assert abs(loss.item() - g["loss"]) < 2e-2, (loss.item(), g["loss"])
+    loss.backward()
+    named = dict(model.named_parameters())
+    worst_norm, worst_elem = ("", 0.0), ("", 0.0)
+    for k, ref in g["grads"].items():
+        if ref["norm"] < 1e-6:
+            continue
+        p = named[k]
+        assert p.grad is not None, k
+        gflat = p.grad.reshape(-1).cpu()
+        rel = abs(gflat.norm().item() - ref["norm"]) / ref["norm"]
+        # element-wise: sampled entries against the tensor's own abs-max (bf16 operands, fp32 accumulation)
+        err = (gflat[ref["sample_idx"]] - ref["sample"]).abs().max().item() / ref["absmax"]
+        worst_norm = max(worst_norm, (k, rel), key=lambda t: t[1])
+        worst_elem = max(worst_elem, (k, err), key=lambda t: t[1])
+        assert rel < 0.03, (k, rel)
+        assert err < 0.05, (k, err)
+    print(f"12-layer C2 shape: loss {loss.item():.5f} vs reference {g['loss']:.5f}; worst grad-norm rel err {worst_norm}; "
+          f"worst sampled element err / absmax {worst_elem}")
+
+
 @pytest.mark.parametrize("windows,L", [([64], 300), ([128, 256], 700), ([512], 1100)])
 def test_train_gradients_match_oracle_autograd_dense(windows, L):
     """Full gradient tensors against the oracle's autograd (every parameter); also the wide attention

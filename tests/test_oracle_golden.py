@@ -56,6 +56,33 @@ def test_train_loss_and_grads_match_reference(goldens):
     assert checked >= 45
 
 
+def test_train_12layer_c2_shape_matches_reference(goldens):
+    """BASELINE configs[1] shape (12 layers, 4 ragged rows of 1024 tokens, CE over 5 000 items): the oracle's loss
+    and every gradient tensor (norm, first 32 entries, 512 seeded samples) against the unmodified reference."""
+    g = goldens["train_c2_12layer"]
+    cfg = O.OracleConfig(**g["cfg"])
+    sd = O.make_state_dict(cfg, seed=g["sd_seed"], prefix="longformer.")
+    for v in sd.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    batch = O.make_batch(cfg, g["B"], g["L"], seed=g["batch_seed"], ragged=True)
+    items = O.make_item_table(g["N"], cfg.hidden_size, seed=1)
+    loss = O.seqrec_forward(sd, cfg, batch, items, labels=g["labels"])
+    assert abs(loss.item() - g["loss"]) < 1e-4
+    loss.backward()
+    checked = 0
+    for k, ref in g["grads"].items():
+        grad = sd[k].grad
+        if grad is None:
+            assert ref["norm"] < 1e-6, k
+            continue
+        tol = 1e-5 + 5e-4 * ref["norm"]
+        assert abs(grad.norm().item() - ref["norm"]) < tol, k
+        assert (grad.reshape(-1)[ref["sample_idx"]] - ref["sample"]).abs().max() < 1e-6 + 5e-4 * ref["absmax"], k
+        checked += 1
+    assert checked >= 240
+
+
 def test_ranker_matches_reference(goldens):
     for g in goldens["ranker"]:
         got = O.ranker(g["scores"].float(), g["labels"], ks=(10, 50))
