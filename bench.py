@@ -243,78 +243,188 @@ def time_region(fn, steps, world):
 
 
 def gemm_profile(model, opt, batch, world):
-    """Device time of the dominant kernel (the tcgen05 GEMM) inside one step, via CUDA events around
-    every rf_gemm_bf16 launch on the launching stream."""
+    """Device time of the dominant kernel (the tcgen05 GEMM) inside one kernel-by-kernel step, via CUDA events around
+    every rf_gemm_bf16 launch on the launching stream.  Two un-instrumented eager steps run first so that the profiled
+    step (and the eager step time the GEMM share is quoted against) is a warm one, not the first after graph replays."""
     from recformer_b200 import ops
+    import recformer_b200.engine as eng
+    for _ in range(2):
+        train_step(model, opt, batch, world)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    train_step(model, opt, batch, world)
+    e1.record()
+    torch.cuda.synchronize()
+    eager_ms = e0.elapsed_time(e1)
     real = ops.gemm
     evs = []
 
     def timed(*a, **kw):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
         out = real(*a, **kw)
-        e1.record()
-        evs.append((e0, e1))
+        s1.record()
+        evs.append((s0, s1))
         return out
 
     ops.gemm = timed
-    import recformer_b200.engine as eng
     eng.ops.gemm = timed
     try:
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
         train_step(model, opt, batch, world)
-        e1.record()
         torch.cuda.synchronize()
     finally:
         ops.gemm = real
         eng.ops.gemm = real
     gemm_ms = sum(a.elapsed_time(b) for a, b in evs)
-    return gemm_ms, len(evs), e0.elapsed_time(e1)
+    return gemm_ms, len(evs), eager_ms
 
 
-def eval_topk_bench(device, rank, world, steps, warmup):
-    """configs[3]: 4096 users x 1M items sharded by item id over the ranks, fused top-10."""
+# ------------------------------------------------------------------------------------------------
+# configs[3]: full-catalogue evaluation (4096 users x 1M items, sharded by item id over the ranks)
+# ------------------------------------------------------------------------------------------------
+TABLE_CHUNK = 125_000
+
+
+def raw_table_chunk(c, device):
+    """Rows [c*125000, (c+1)*125000) of the synthetic N(0,1) item table (fp32, un-normalised); seeded per chunk so
+    that every rank / the CPU leg can rebuild any part of the same table."""
+    return torch.randn(TABLE_CHUNK, E, device=device, generator=torch.Generator(device=device).manual_seed(2000 + c))
+
+
+def eval_topk_bench(model, device, rank, world, steps, warmup, cpu_leg):
     from recformer_b200 import dist as rdist
     from recformer_b200 import ops
+    from recformer_b200.metrics import TopKRanker
+    K = 10
     lo, hi = rdist.shard_bounds(EVAL_ITEMS, world, rank)
-    g = torch.Generator(device=device).manual_seed(2)
-    table = torch.empty(hi - lo, E, dtype=torch.bfloat16, device=device)
-    chunk = 125_000
-    for a in range(0, hi - lo, chunk):       # N(0,1) rows, L2-normalised, bf16 (pre-normalised table, Spec S)
-        b = min(hi - lo, a + chunk)
-        ops.normalize_rows(torch.randn(b - a, E, device=device, generator=g), out=table[a:b])
-    users = ops.normalize_rows(torch.randn(EVAL_USERS, E, device=device, generator=torch.Generator(device=device).manual_seed(3)))
-    labels = torch.randint(0, EVAL_ITEMS, (EVAL_USERS,), device=device, generator=torch.Generator(device=device).manual_seed(4))
-
-    def one(_):
-        s, i, l = ops.cosine_topk(users, table, 0.05, k=10, id_base=lo, labels=labels)
-        if world > 1:
-            gs, gi, gl = rdist.all_gather_topk(s, i, l)
-            s, i, l = ops.topk_merge(gs, gi, gl)
-        return s, i, l
-
+    assert lo % TABLE_CHUNK == 0 and hi % TABLE_CHUNK == 0
+    shard = torch.cat([raw_table_chunk(c, device) for c in range(lo // TABLE_CHUNK, hi // TABLE_CHUNK)], 0)
+    model.eval()
+    model.config.item_num = EVAL_ITEMS
+    model.init_item_embedding(shard)                 # ref: recformer/models.py:533-537 (this rank's id range)
+    del shard
+    table = model.normalized_items()                 # L2-normalised bf16 shard, built once per table (Spec S)
+    n_sets = 3
+    users_host = [torch.randn(EVAL_USERS, E, generator=torch.Generator().manual_seed(30 + i)).pin_memory()
+                  for i in range(n_sets)]
+    users_dev = [u.to(device) for u in users_host]
+    # labels: even users get the item the scorer itself ranks (u mod 10)-th (known metric contribution), odd users a
+    # uniform item (rank ~ N/2): Recall@10 -> 0.5, NDCG@10 -> 0.5 * mean_r 1/log2(r+2)
+    def topk(pooled, labels):
+        return rdist.sharded_topk(model, pooled, k=K, labels=labels, id_base=lo)
+    rows = torch.arange(EVAL_USERS, device=device)
+    labels_dev = []
+    for u in users_dev:
+        rnd = torch.randint(0, EVAL_ITEMS, (EVAL_USERS,), device=device, generator=torch.Generator(device=device).manual_seed(4))
+        _, ids, _ = topk(u, rnd)
+        labels_dev.append(torch.where(rows % 2 == 0, ids[rows, rows % K].long(), rnd))
+    labels_host = [l.cpu().pin_memory() for l in labels_dev]
     for w in range(max(3, warmup)):
-        one(w)
-    ms = time_region(one, steps, world)
-    # kernel-only time of the fused scorer on this rank
+        topk(users_dev[w % n_sets], labels_dev[w % n_sets])
+    l0 = ops.launch_count()
+    ms = time_region(lambda i: topk(users_dev[i % n_sets], labels_dev[i % n_sets]), steps, world)
+    launches = (ops.launch_count() - l0) // steps
+    # e2e: pinned host users + labels -> H2D -> public API (normalise, fused top-k, all-gather + merge) -> D2H result
+    res = {}
+
+    def e2e_pass(i):
+        pooled = users_host[i % n_sets].to(device, non_blocking=True)
+        labels = labels_host[i % n_sets].to(device, non_blocking=True)
+        s, ids, l = topk(pooled, labels)
+        res["s"], res["i"], res["l"] = s.cpu(), ids.cpu(), l.cpu()
+
+    e2e_pass(0)
+    ms_e2e = time_region(e2e_pass, steps, world)
+    last = (steps - 1) % n_sets
+    ndcg, recall = TopKRanker([K])(res["s"], res["l"])
+    expect_ndcg = 0.5 * sum(1.0 / torch.log2(torch.tensor(r + 2.0)).item() for r in range(K)) / K
+    # kernel-only time of the fused scorer on this rank: pre-normalised users, pre-allocated scratch and outputs
+    xn = ops.normalize_rows(users_dev[0])
+    ws = ops.cosine_topk_ws(EVAL_USERS, hi - lo, K, device)
+    out = (torch.empty(EVAL_USERS, K, dtype=torch.float32, device=device),
+           torch.empty(EVAL_USERS, K, dtype=torch.int32, device=device), torch.empty(EVAL_USERS, dtype=torch.float32, device=device))
+    kern = lambda: ops.cosine_topk(xn, table, model.config.temp, k=K, id_base=lo, labels=labels_dev[0], ws=ws, out=out)
+    for _ in range(3):
+        kern()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_k = 5
     e0.record()
-    for _ in range(3):
-        ops.cosine_topk(users, table, 0.05, k=10, id_base=lo, labels=labels)
+    for _ in range(n_k):
+        kern()
     e1.record()
     torch.cuda.synchronize()
-    k_ms = e0.elapsed_time(e1) / 3
+    k_ms = e0.elapsed_time(e1) / n_k
     flops = 2.0 * EVAL_USERS * (hi - lo) * E
     _, burst, _, src = peaks()
-    return {"metric": "eval users/sec top-10 over 1M items", "value": EVAL_USERS * steps / (ms / 1e3), "unit": "users/s",
-            "ms_per_pass": ms / steps, "config": {"workload": "BASELINE configs[3]: 4096 users x 1M items bf16 table "
-                                                  f"sharded over {world} GPU(s), cosine top-10 + all-gather merge"},
-            "roofline": {"bound": "tensor", "achieved": flops / (k_ms / 1e3) / 1e12, "peak": burst, "unit": "TFLOP/s",
-                         "frac": flops / (k_ms / 1e3) / 1e12 / burst, "traffic": None, "peak_source": src,
-                         "kernel": "cosine_pair_kernel<TOPK> (tcgen05 cta_group::2, fused top-k epilogue)", "flops_per_launch": flops, "ms_per_launch": k_ms}}
+    traffic, traffic_src = profiled_traffic("cosine_pair_kernel<0>")
+    h2d = users_host[0].numel() * 4 + labels_host[0].numel() * 8
+    d2h = EVAL_USERS * (K * 8 + 4)
+    sec = {"metric": "eval users/sec top-10 over 1M items", "value": EVAL_USERS * steps / (ms / 1e3), "unit": "users/s",
+           "n_gpus": world, "steps": steps, "ms_per_pass": ms / steps, "gpu_launches": int(launches),
+           "config": {"workload": f"BASELINE configs[3]: 4096 users x 1M items (fp32 table -> L2-normalised bf16, {hi - lo} rows "
+                                  f"on this rank, sharded by item id over {world} GPU(s)), cosine/temp top-10 + label score"
+                                  + (", NCCL all-gather + merge" if world > 1 else ""),
+                      "l2": f"table shard {(hi - lo) * E * 2 / 1e6:.0f} MB bf16 > 126 MB L2; 3 rotating user sets"},
+           "e2e": {"value": EVAL_USERS * steps / (ms_e2e / 1e3), "unit": "users/s", "ms_per_pass": ms_e2e / steps,
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "path": "pinned host users fp32 + labels -> H2D -> dist.sharded_topk(model, ...) -> .cpu() of scores/ids/label scores"},
+           "metrics": {"NDCG@10": ndcg, "Recall@10": recall, "expected_by_construction": {"NDCG@10": expect_ndcg, "Recall@10": 0.5},
+                       "note": "even users are labelled with the scorer's own (u mod 10)-th item, odd users uniformly; "
+                               "Spec R from (top-10 scores, label score)"},
+           "roofline": {"bound": "tensor", "achieved": flops / (k_ms / 1e3) / 1e12, "peak": burst, "unit": "TFLOP/s",
+                        "frac": flops / (k_ms / 1e3) / 1e12 / burst, "traffic": traffic if world == 1 else None,
+                        "traffic_source": f"profiles/{traffic_src} (ncu --set full at 4096 x 1M, one GPU)" if traffic_src and world == 1 else None,
+                        "peak_source": f"{src} (burst: kernel timed alone)",
+                        "kernel": "cosine_pair_kernel<TOPK> (tcgen05 cta_group::2, fused top-k epilogue)",
+                        "flops_per_launch": flops, "ms_per_launch": k_ms,
+                        "algorithmic_bytes_per_launch": (hi - lo) * E * 2 + EVAL_USERS * E * 2 + EVAL_USERS * K * 8}}
+    if cpu_leg:
+        sec["cpu_baseline"] = cpu_eval_baseline(users_host[last], labels_host[last], res, device)
+    return sec
+
+
+def cpu_eval_baseline(users, labels, gpu_res, device, n_users=128, chunk=50_000):
+    """The reference's own eval arithmetic on the host cores for a bounded user sample: `Similarity` (cosine / temp,
+    ref: recformer/models.py:358-369) against the whole 1M-row fp32 table in 50k-row slices (its (B,N,H) broadcast
+    cannot be allocated at 1M items), then `Ranker` NDCG/Recall@10 (ref: utils.py:82-107)."""
+    from oracle import recformer_oracle as O
+    from recformer_b200.metrics import TopKRanker
+    torch.set_num_threads(os.cpu_count())
+    table = torch.cat([raw_table_chunk(c, device).cpu() for c in range(EVAL_ITEMS // TABLE_CHUNK)], 0)
+    x, lab = users[:n_users].clone(), labels[:n_users].clone()
+    t0 = time.perf_counter()
+    scores = torch.cat([O.similarity(x.unsqueeze(1), table[a:a + chunk].unsqueeze(0), 0.05) for a in range(0, EVAL_ITEMS, chunk)], 1)
+    m = O.ranker(scores, lab, ks=(10,))
+    dt = time.perf_counter() - t0
+    got = TopKRanker([10])(gpu_res["s"][:n_users], gpu_res["l"][:n_users])
+    top = torch.topk(scores, 10, dim=1)
+    ids_equal = float((top.indices == gpu_res["i"][:n_users].long()).float().mean())
+    return {"value": n_users / dt, "unit": "users/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_users} of {EVAL_USERS} users x 1M items, fp32, Similarity in {chunk}-row slices + Ranker, torch CPU oracle",
+            "NDCG@10": m[0], "Recall@10": m[1], "gpu_NDCG@10_same_users": got[0], "gpu_Recall@10_same_users": got[1],
+            "metrics_equal_4dp": round(m[0], 4) == round(got[0], 4) and round(m[1], 4) == round(got[1], 4),
+            "top10_ids_equal_frac": ids_equal, "max_abs_score_err": float((top.values - gpu_res["s"][:n_users]).abs().max())}
+
+
+def cpu_c1_baseline(n_seqs=2):
+    """BASELINE configs[0] on the host cores: RecformerForSeqRec forward + cosine scoring vs 1k items, fp32 oracle."""
+    from oracle import recformer_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    ocfg = O.OracleConfig()
+    sd = O.make_state_dict(ocfg, seed=0, prefix="longformer.")
+    items = O.make_item_table(1000, E, seed=1)
+    batch = O.make_batch(ocfg, n_seqs, SEQ_LEN, seed=0, ragged=False)
+    best = None
+    with torch.no_grad():
+        for _ in range(2):
+            t0 = time.perf_counter()
+            O.seqrec_forward(sd, ocfg, batch, items)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return {"value": n_seqs / best, "unit": "seqs/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_seqs} of 8 sequences x 1024 tokens, forward + scoring vs 1k items, best of 2, fp32 torch CPU oracle"}
 
 
 def run_ours(args):
@@ -378,7 +488,7 @@ def run_ours(args):
     if sampler:
         sampler.__exit__()
     # ---- roofline of the dominant kernel (tcgen05 GEMM) --------------------------------------
-    gemm_ms, n_gemm, step_ms_prof = gemm_profile(model, opt, dev[0], world)
+    gemm_ms, n_gemm, eager_ms = gemm_profile(model, opt, dev[0], world)
     hbm, burst, sustained, src = peaks()
     flops_step = algorithmic_gemm_flops_per_seq() * B_PER_GPU
     achieved = flops_step / (gemm_ms / 1e3) / 1e12
@@ -388,25 +498,48 @@ def run_ours(args):
                                                    "captured gemm_pair_kernel launches (fwd QKV / GELU / down / dGELU / wgrad)"
                                                    if traffic_src else None),
             "peak_source": f"{src} (sustained: kernel timed inside a long step)",
-            "kernel": "gemm_kernel (tcgen05, all fwd/dgrad/wgrad launches of one step)",
+            "kernel": "gemm_pair_kernel (tcgen05 cta_group::2, all fwd/dgrad/wgrad launches of one step)",
             "flops_per_launch": flops_step / n_gemm, "launches_per_step": n_gemm, "ms_per_launch": gemm_ms / n_gemm,
-            "gemm_share_of_step": gemm_ms / step_ms_prof,
+            "gemm_ms_per_step": gemm_ms, "eager_step_ms": eager_ms, "gemm_share_of_eager_step": gemm_ms / eager_ms,
             "step_tensor_frac": (flops_step + 3 * 4 * 66 * E * NL * SEQ_LEN * B_PER_GPU) / (ms / args.steps / 1e3) / 1e12 / sustained}
+    if gstep is not None:
+        gstep = None                      # release the captured graph (and its NCCL resources) before the other legs
+    if world > 1 and id(model) in _SYNC:
+        model.longformer._engine.grad_hook = None
+    del opt
+    torch.cuda.empty_cache()
+    cpu_legs = rank == 0 and world == 1 and not args.no_cpu_baseline
     secondary = None
     try:
         if args.no_secondary:
             raise RuntimeError("skipped (--no-secondary)")
-        del model, opt
-        torch.cuda.empty_cache()
-        secondary = eval_topk_bench(device, rank, world, max(3, min(args.steps, 10)), args.warmup)
+        secondary = eval_topk_bench(model, device, rank, world, max(3, min(args.steps, 10)), args.warmup, cpu_legs)
     except Exception as ex:  # the primary line must still print
         secondary = {"metric": "eval users/sec top-10 over 1M items", "error": repr(ex)[:300]}
+    del model
+    torch.cuda.empty_cache()
+    extras, checks = {}, None
+    if not args.no_extras:
+        from tools import bench_extras
+        try:
+            extras["pretrain_c3"] = bench_extras.pretrain_bench(device, rank, world, steps=3, sustained_tflops=sustained)
+        except Exception as ex:
+            extras["pretrain_c3"] = {"error": repr(ex)[:300]}
+        if world == 1:
+            try:
+                extras["longseq_c5"] = bench_extras.longseq_bench(device, steps=3, sustained_tflops=sustained)
+            except Exception as ex:
+                extras["longseq_c5"] = {"error": repr(ex)[:300]}
+        if world > 1:
+            from tools import check_multigpu
+            checks = check_multigpu.run_checks(device, rank, world, full=True)
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if cpu_legs:
         rate, cms, cores = cpu_finetune_step_rate(2, 2, 1)
         cpu_base = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": f"2 of {B_PER_GPU} sequences x {SEQ_LEN} tokens per step, 2 timed steps after 1 warm-up, "
                               "fwd+CE(5k items)+bwd+AdamW, fp32 torch CPU oracle"}
+        extras["cpu_baseline_c1_forward"] = cpu_c1_baseline()
     if rank == 0:
         line = {"metric": METRIC, "value": world * B_PER_GPU * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
@@ -418,22 +551,22 @@ def run_ours(args):
                                        "train mode dropout 0.1",
                            "global_batch": world * B_PER_GPU, "seq_len": SEQ_LEN, "parallelism": f"dp{world}",
                            "l2": "per-step working set ~6 GB (activations + weights) >> 126 MB L2; 4 rotating batches",
-                           "launch": "one CUDA graph replay per step" if gstep is not None else
+                           "launch": "one CUDA graph replay per step" if graph_error is None and not args.no_graph and
+                                     (world == 1 or os.environ.get("RF_BENCH_DP_GRAPH", "1") == "1") else
                                      ("eager kernel launches" + (f" (graph capture failed: {graph_error})" if graph_error else ""))},
                 "e2e": {"value": world * B_PER_GPU * args.steps / (ms_e2e / 1e3), "unit": UNIT,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
                         "last_loss": last.get("loss")},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary() if sampler else None,
-                "roofline": roof, "cpu_baseline": cpu_base, "secondary": secondary}
+                "roofline": roof, "cpu_baseline": cpu_base, "secondary": secondary, "extras": extras, "checks": checks}
         print(json.dumps(line), flush=True)
     if world > 1:
         # A captured graph keeps NCCL resources alive: destroy_process_group() with the graph still around hung in the
-        # first 2-GPU trial, so the graph is released first; the timer bounds any teardown stall (the line is printed).
+        # first 2-GPU trial, so the graph is released first (above); the timer bounds any teardown stall.
         guard = threading.Timer(60.0, lambda: os._exit(0))
         guard.daemon = True
         guard.start()
-        gstep = None
         torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
@@ -449,6 +582,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the 1M-item eval leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying the CUDA graph")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C3 pretraining / C5 long-sequence legs and the multi-GPU checks")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -487,6 +487,32 @@ class _LMHeadCEFunction(torch.autograd.Function):
         return dx.float(), None, dWd, dbd, dlnw, dlnb, dWdec[:V], dbpad[:V], None
 
 
+def gather_cls_with_local_grad(z1: torch.Tensor, z2: torch.Tensor, group=None):
+    """ref: recformer/models.py:475-490 — every rank's CLS vectors become in-batch negatives; the gathered copies
+    carry no gradient, so this rank's slot is replaced by the live tensors.  ONE collective on the packed
+    (2, B, E) buffer instead of the reference's two list all_gathers; device-agnostic (NCCL on GPUs, gloo in the
+    CPU tests).  Returns (z1_all, z2_all) of shape (B * world, E), rows ordered by rank."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    packed = torch.stack([z1.detach(), z2.detach()]).contiguous()
+    gathered = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1), group=group)
+    parts1 = [gathered[r, 0] if r != rank else z1 for r in range(world)]
+    parts2 = [gathered[r, 1] if r != rank else z2 for r in range(world)]
+    return torch.cat(parts1, 0), torch.cat(parts2, 0)
+
+
+def contrastive_head(z1: torch.Tensor, z2: torch.Tensor, temp: float):
+    """ref: recformer/models.py:492-497 — cos_sim = sim(z1[:,None], z2[None]) (Spec S), CE against the diagonal.
+    (B*W)^2 logits on [B*W, 768] vectors: fp32 keeps both towers' gradients exact.  Returns (loss, cos_sim, correct)."""
+    z1n = z1 / z1.norm(dim=-1, keepdim=True).clamp_min(1e-8)
+    z2n = z2 / z2.norm(dim=-1, keepdim=True).clamp_min(1e-8)
+    cos_sim = (z1n @ z2n.t()) / temp
+    target = torch.arange(cos_sim.size(0), device=cos_sim.device)
+    loss = nn.functional.cross_entropy(cos_sim, target)
+    return loss, cos_sim, (torch.argmax(cos_sim, 1) == target).sum()
+
+
 class RecformerForPretraining(nn.Module):
     """ref: recformer/models.py:372-520 — two-tower in-batch contrastive loss on the CLS vectors of (history a,
     target item b) plus mlm_weight * masked-LM loss on the masked copies of both; same forward kwargs, output
@@ -532,22 +558,8 @@ class RecformerForPretraining(nn.Module):
         z1 = self._encode(input_ids_a, "a", kw).pooler_output
         z2 = self._encode(input_ids_b, "b", kw).pooler_output
         if dist.is_available() and dist.is_initialized() and self.training and dist.get_world_size() > 1:
-            # ref :475-490 — all ranks' CLS vectors as negatives; only this rank's slot carries gradient.
-            # One collective on the packed (2, B, E) buffer instead of two list all_gathers.
-            world, rank = dist.get_world_size(), dist.get_rank()
-            packed = torch.stack([z1.detach(), z2.detach()]).contiguous()
-            gathered = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
-            dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1))
-            parts1 = [gathered[r, 0] if r != rank else z1 for r in range(world)]
-            parts2 = [gathered[r, 1] if r != rank else z2 for r in range(world)]
-            z1, z2 = torch.cat(parts1, 0), torch.cat(parts2, 0)
-        # (B*W)^2 logits on [B*W, 768] vectors: tiny; plain fp32 torch keeps both towers' gradients exact
-        z1n = z1 / z1.norm(dim=-1, keepdim=True).clamp_min(1e-8)
-        z2n = z2 / z2.norm(dim=-1, keepdim=True).clamp_min(1e-8)
-        cos_sim = (z1n @ z2n.t()) / self.config.temp
-        target = torch.arange(cos_sim.size(0), device=cos_sim.device)
-        loss = nn.functional.cross_entropy(cos_sim, target)
-        correct_num = (torch.argmax(cos_sim, 1) == target).sum()
+            z1, z2 = gather_cls_with_local_grad(z1, z2)            # ref :475-490
+        loss, cos_sim, correct_num = contrastive_head(z1, z2, self.config.temp)
         if mlm_input_ids_a is not None and mlm_labels_a is not None:
             hidden = self._encode(mlm_input_ids_a, "a", kw).last_hidden_state
             loss = loss + self.config.mlm_weight * self._mlm_loss(hidden, mlm_labels_a)

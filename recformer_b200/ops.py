@@ -250,7 +250,14 @@ def cosine_logits(xn, yn, temp, out=None):
     return out
 
 
-def cosine_topk(xn, yn, temp, k=10, id_base=0, labels=None, ws=None):
+def cosine_topk_ws(B, N, k, device):
+    """Scratch of rf_cosine_topk for (B users, N items, k): allocate once and pass as `ws=` to reuse it."""
+    return torch.empty(int(_lib.lib().rf_cosine_topk_ws_bytes(B, N, k)), dtype=torch.uint8, device=device)
+
+
+def cosine_topk(xn, yn, temp, k=10, id_base=0, labels=None, ws=None, out=None):
+    """Fused cosine scoring + top-k.  `ws` (cosine_topk_ws) and `out` = (scores [B,k] fp32, ids [B,k] int32,
+    label_score [B] fp32) may be passed in to run without any allocation."""
     _req(xn, torch.bfloat16, "xn"), _req(yn, torch.bfloat16, "yn")
     B, E = xn.shape
     N = yn.shape[0]
@@ -258,9 +265,15 @@ def cosine_topk(xn, yn, temp, k=10, id_base=0, labels=None, ws=None):
     nbytes = int(_lib.lib().rf_cosine_topk_ws_bytes(B, N, k))
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    scores = torch.empty(B, k, dtype=torch.float32, device=dev)
-    ids = torch.empty(B, k, dtype=torch.int32, device=dev)
-    label_score = torch.empty(B, dtype=torch.float32, device=dev)
+    if out is not None:
+        scores, ids, label_score = out
+        _req(scores, torch.float32, "scores"), _req(ids, torch.int32, "ids"), _req(label_score, torch.float32, "label_score")
+        if tuple(scores.shape) != (B, k) or tuple(ids.shape) != (B, k) or label_score.numel() != B:
+            raise ValueError("cosine_topk: output buffers do not match (B, k)")
+    else:
+        scores = torch.empty(B, k, dtype=torch.float32, device=dev)
+        ids = torch.empty(B, k, dtype=torch.int32, device=dev)
+        label_score = torch.empty(B, dtype=torch.float32, device=dev)
     if labels is not None:
         _req(labels, torch.int64, "labels")
     check(_lib.lib().rf_cosine_topk(xn.data_ptr(), yn.data_ptr(), B, N, E, temp, k, id_base, _ptr(labels),

@@ -137,3 +137,48 @@ def _grad_sync_job(rank, world):
 
 def test_overlapped_grad_sync_covers_buffer_once_world2():
     assert _run(_grad_sync_job) == [(True, 0), (True, 0)]
+
+
+def _contrastive_job(rank, world):
+    """Distributed in-batch contrastive branch (ref: recformer/models.py:475-497): packed all-gather of both towers'
+    CLS vectors, this rank's slot live, CE over the (B*W)^2 logits.  Checked against the oracle's single-process
+    emulation (`pretrain_forward(gathered_z=...)` semantics restated on the pooled vectors): loss, logits, and the
+    gradient — non-zero only through this rank's own slot, and equal to the oracle's autograd through that slot."""
+    from oracle import recformer_oracle as O
+    from recformer_b200.models import contrastive_head, gather_cls_with_local_grad
+    B, E, temp = 5, 768, 0.05
+    g = torch.Generator().manual_seed(11)
+    z1_all = torch.randn(world * B, E, generator=g) + 0.5            # every rank can rebuild all ranks' vectors
+    z2_all = z1_all * 0.7 + 0.7 * torch.randn(world * B, E, generator=g)
+    z1 = z1_all[rank * B:(rank + 1) * B].clone().requires_grad_(True)
+    z2 = z2_all[rank * B:(rank + 1) * B].clone().requires_grad_(True)
+    a1, a2 = gather_cls_with_local_grad(z1, z2)
+    assert a1.shape == (world * B, E) and torch.equal(a1.detach(), z1_all) and torch.equal(a2.detach(), z2_all)
+    loss, cos_sim, correct = contrastive_head(a1, a2, temp)
+    loss.backward()
+    # oracle: live slot inside the gathered (constant) tensors
+    r1 = z1_all[rank * B:(rank + 1) * B].clone().requires_grad_(True)
+    r2 = z2_all[rank * B:(rank + 1) * B].clone().requires_grad_(True)
+    o1 = torch.cat([z1_all[: rank * B], r1, z1_all[(rank + 1) * B:]], 0)
+    o2 = torch.cat([z2_all[: rank * B], r2, z2_all[(rank + 1) * B:]], 0)
+    ref_sim = O.similarity(o1.unsqueeze(1), o2.unsqueeze(0), temp)
+    ref_loss = torch.nn.functional.cross_entropy(ref_sim, torch.arange(world * B))
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 1e-5
+    assert (cos_sim - ref_sim).abs().max() < 1e-4
+    assert int(correct) == int((ref_sim.argmax(1) == torch.arange(world * B)).sum())
+    assert (z1.grad - r1.grad).abs().max() < 1e-6 and (z2.grad - r2.grad).abs().max() < 1e-6
+    assert z1.grad.abs().max() > 0 and z2.grad.abs().max() > 0
+    # summed over ranks (what the DP gradient all-reduce does downstream) the own-slot gradients reproduce the
+    # gradient of the world-sized batch computed in one process
+    full1, full2 = z1_all.clone().requires_grad_(True), z2_all.clone().requires_grad_(True)
+    torch.nn.functional.cross_entropy(O.similarity(full1.unsqueeze(1), full2.unsqueeze(0), temp),
+                                      torch.arange(world * B)).backward()
+    assert (z1.grad - full1.grad[rank * B:(rank + 1) * B]).abs().max() < 1e-6
+    assert (z2.grad - full2.grad[rank * B:(rank + 1) * B]).abs().max() < 1e-6
+    return round(loss.item(), 5)
+
+
+def test_contrastive_allgather_own_slot_gradient_world2():
+    out = _run(_contrastive_job)
+    assert out[0] == out[1]          # the loss is the same on every rank (same gathered batch)

@@ -329,6 +329,83 @@ def test_topk_sharded_merge_matches_unsharded():
     assert torch.equal(ms, ts) and torch.equal(mi, ti) and torch.equal(ml, ls)
 
 
+def test_topk_full_catalogue_4096_users_1m_items_and_metrics():
+    """BASELINE configs[3] at full size: 4096 users x 1 000 000 items, top-10 (+ label score) from the fused scorer
+      * bit-exact (ids AND scores) against the same tensor-core arithmetic written out densely in 50k-item chunks
+        (rf_cosine_logits -> torch.topk), unsharded and as 8 emulated item-id shards merged by rf_topk_merge;
+      * against chunked fp32 torch on the same bf16 inputs (different accumulation order): scores within 2e-4, ids
+        equal wherever the fp32 gap to the neighbouring ranks exceeds 1e-3;
+      * Recall@10 / NDCG@10 of ALL 4096 users from (top-10, label score) (Spec R) equal to the dense-rank definition
+        of the reference Ranker (utils.py:82-107) on the fp32 scores, to 4 decimals; half of the labels are drawn from
+        the reference's own top-20 so that the metrics are non-trivial."""
+    from recformer_b200.metrics import TopKRanker
+    B, N, E, K, S, CH = 4096, 1_000_000, 768, 10, 8, 50_000
+    g = torch.Generator(device=DEV).manual_seed(2)
+    yn = torch.empty(N, E, dtype=torch.bfloat16, device=DEV)
+    for a in range(0, N, 125_000):
+        ops.normalize_rows(torch.randn(125_000, E, device=DEV, generator=g), out=yn[a:a + 125_000])
+    xn = ops.normalize_rows(torch.randn(B, E, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3)))
+    rows = torch.arange(B, device=DEV)
+    # dense chunked references: our tensor-core logits (bit-exact target) and fp32 torch (the reference arithmetic)
+    tc_s, tc_i, fp_s, fp_i = None, None, None, None
+    xf = xn.float()
+
+    def merge(best_s, best_i, logits, base, k):
+        s, i = torch.topk(logits, k, dim=1)
+        i = i + base
+        if best_s is None:
+            return s, i
+        cs, ci = torch.cat([best_s, s], 1), torch.cat([best_i, i], 1)
+        o = torch.argsort(cs, dim=1, descending=True, stable=True)[:, :k]      # earlier (lower-id) chunks win ties
+        return torch.gather(cs, 1, o), torch.gather(ci, 1, o)
+
+    for a in range(0, N, CH):
+        tc = ops.cosine_logits(xn, yn[a:a + CH], 0.05)
+        tc_s, tc_i = merge(tc_s, tc_i, tc, a, K)
+        fp = (xf @ yn[a:a + CH].float().T) / 0.05
+        fp_s, fp_i = merge(fp_s, fp_i, fp, a, 21)
+    # labels: even users from the fp32 reference's top-20 (rank = user index mod 20), odd users uniform
+    labels = torch.randint(0, N, (B,), device=DEV, generator=torch.Generator(device=DEV).manual_seed(4))
+    pick = fp_i[rows, rows % 20]
+    labels = torch.where(rows % 2 == 0, pick, labels)
+    ts, ti, ls = ops.cosine_topk(xn, yn, 0.05, k=K, labels=labels)
+    assert torch.equal(ti.long(), tc_i) and torch.equal(ts, tc_s)
+    # 8 emulated shards (contiguous id ranges, as dist.shard_bounds assigns them) + merge == unsharded, bit for bit
+    ps, pi, pl = [], [], []
+    for r in range(S):
+        lo, hi = r * (N // S), (r + 1) * (N // S)
+        s_, i_, l_ = ops.cosine_topk(xn, yn[lo:hi], 0.05, k=K, id_base=lo, labels=labels)
+        ps.append(s_), pi.append(i_), pl.append(l_)
+    ms, mi, ml = ops.topk_merge(torch.stack(ps), torch.stack(pi), torch.stack(pl))
+    assert torch.equal(ms, ts) and torch.equal(mi, ti) and torch.equal(ml, ls)
+    # fp32 torch on the same inputs
+    assert (ts - fp_s[:, :K]).abs().max().item() < 2e-4
+    gap_up = torch.cat([torch.full((B, 1), 1e9, device=DEV), fp_s[:, :K - 1] - fp_s[:, 1:K]], 1)
+    gap_dn = fp_s[:, :K] - fp_s[:, 1:K + 1]
+    clear = (gap_up > 1e-3) & (gap_dn > 1e-3)
+    assert clear.float().mean().item() > 0.9
+    assert torch.equal(ti.long()[clear], fp_i[:, :K][clear])
+    # metrics over all users: dense-rank definition on the fp32 scores vs Spec R on the fused output
+    lab_fp = torch.empty(B, device=DEV)
+    rank = torch.zeros(B, device=DEV)
+    for a in range(0, N, CH):
+        fp = (xf @ yn[a:a + CH].float().T) / 0.05
+        own = (labels >= a) & (labels < a + CH)
+        lab_fp[own] = fp[rows[own], labels[own] - a]
+    for a in range(0, N, CH):
+        fp = (xf @ yn[a:a + CH].float().T) / 0.05
+        rank += (fp > lab_fp[:, None]).sum(-1).float()
+    ind = (rank < K).float()
+    want = [((1 / torch.log2(rank + 2)) * ind).mean().item(), ind.mean().item()]
+    got = TopKRanker([K])(ts, ls)
+    print(f"4096 x 1M: NDCG@10 {got[0]:.6f} (dense fp32 {want[0]:.6f}), Recall@10 {got[1]:.6f} ({want[1]:.6f}), "
+          f"clear-gap ranks {clear.float().mean().item():.4f}, max |score - fp32| {(ts - fp_s[:, :K]).abs().max().item():.2e}")
+    assert round(got[0], 4) == round(want[0], 4) and round(got[1], 4) == round(want[1], 4), (got, want)
+    assert 0.2 < got[1] < 0.3
+    got_m = TopKRanker([K])(ms, ml)
+    assert got_m == got
+
+
 def test_cosine_ce_loss_and_grad():
     B, N, E = 16, 5000, 768
     pooled = rnd(B, E, seed=1)

@@ -435,3 +435,63 @@ def test_graphed_train_step_draws_fresh_dropout_masks():
     seen = {round(step(batches[0]).item(), 6) for _ in range(4)}
     assert len(seen) == 4, seen
     assert torch.equal(before, model.longformer._engine.params.flat)
+
+
+def test_graph_replay_survives_other_shapes_on_wide_windows():
+    """the wide-window band-attention scratch is baked into a captured step graph, so it must stay alive and
+    private while other shapes run between replays.  Capture a step with attention_window 128, run eval forwards of
+    other shapes (they allocate their own scratch), replay, and compare with the same steps run eagerly."""
+    from recformer_b200.graph import GraphedTrainStep
+    from recformer_b200.optim import FusedAdamW
+
+    def setup():
+        ocfg, cfg, model, sd = build(dict(vocab_size=1500, num_hidden_layers=2, attention_window=[128, 128],
+                                          max_position_embeddings=1100), sd_seed=8)
+        cfg.hidden_dropout_prob = cfg.attention_probs_dropout_prob = 0.0
+        model.train()
+        model.longformer.strict_checks = False
+        model.init_item_embedding(O.make_item_table(50, 768, seed=1).to(DEV))
+        bs = []
+        for s in range(2):
+            b = {k: v.to(DEV) for k, v in O.make_batch(ocfg, 2, 512, seed=50 + s, ragged=True).items()}
+            b["labels"] = torch.tensor([3 + s, 9 + s], device=DEV)
+            bs.append(b)
+        other = [{k: v.to(DEV) for k, v in O.make_batch(ocfg, B, L, seed=60, ragged=True).items()} for B, L in ((3, 1024), (1, 256))]
+        return ocfg, model, FusedAdamW(model, lr=1e-4), bs, other
+
+    _, ref_model, ref_opt, bs, _ = setup()
+    ref = [_eager_step(ref_model, ref_opt, b).item() for b in (bs[0], bs[0], bs[1], bs[0])]
+    _, model, opt, bs, other = setup()
+    _eager_step(model, opt, bs[0])
+    step = GraphedTrainStep(model, opt, bs[0])
+    got = []
+    for b in (bs[0], bs[1], bs[0]):
+        got.append(step(b).item())
+        model.eval()
+        with torch.no_grad():
+            for o in other:                       # other (B, L) shapes between replays
+                model(**o)
+        model.train()
+        torch.cuda.synchronize()
+    for a, r in zip(got, ref[1:]):
+        assert abs(a - r) < 3e-3 * max(1.0, abs(r)), (got, ref)
+    eng = model.longformer._engine
+    assert len(eng._attn_ws) >= 3 and all(v is not None for v in eng._attn_ws.values())
+
+
+def test_multigpu_result_equality_checks():
+    """tools/check_multigpu.py under torchrun on 2 GPUs (skipped on single-GPU boxes; bench.py --gpus N runs the same
+    checks and reports them in its JSON line): sharded top-k == unsharded, DP gradients == single-GPU gradients of the
+    concatenated batch, contrastive all-gather == world-sized batch."""
+    import json, os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "check_multigpu.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    res = json.loads(line)["check_multigpu"]
+    assert res["topk"]["sharded_topk_equals_unsharded"] and res["dp"]["dp_grads_equal_single_gpu"]
+    assert res["contrastive"]["contrastive_allgather_equals_world_batch"]
