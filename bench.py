@@ -309,16 +309,19 @@ def eval_topk_bench(model, device, rank, world, steps, warmup, cpu_leg):
     users_host = [torch.randn(EVAL_USERS, E, generator=torch.Generator().manual_seed(30 + i)).pin_memory()
                   for i in range(n_sets)]
     users_dev = [u.to(device) for u in users_host]
-    # labels: even users get the item the scorer itself ranks (u mod 10)-th (known metric contribution), odd users a
-    # uniform item (rank ~ N/2): Recall@10 -> 0.5, NDCG@10 -> 0.5 * mean_r 1/log2(r+2)
+    # labels: even users get one of the scorer's own top-10 items -- the rank (1..8) whose score is best separated from
+    # both neighbours, so that the fp32 CPU leg (which ranks the un-rounded fp32 table) agrees on it --, odd users a
+    # uniform item (rank ~ N/2): Recall@10 = 0.5
     def topk(pooled, labels):
         return rdist.sharded_topk(model, pooled, k=K, labels=labels, id_base=lo)
     rows = torch.arange(EVAL_USERS, device=device)
     labels_dev = []
     for u in users_dev:
         rnd = torch.randint(0, EVAL_ITEMS, (EVAL_USERS,), device=device, generator=torch.Generator(device=device).manual_seed(4))
-        _, ids, _ = topk(u, rnd)
-        labels_dev.append(torch.where(rows % 2 == 0, ids[rows, rows % K].long(), rnd))
+        s, ids, _ = topk(u, rnd)
+        gaps = torch.minimum(s[:, :-2] - s[:, 1:-1], s[:, 1:-1] - s[:, 2:])
+        pick = gaps.argmax(-1) + 1
+        labels_dev.append(torch.where(rows % 2 == 0, ids[rows, pick].long(), rnd))
     labels_host = [l.cpu().pin_memory() for l in labels_dev]
     for w in range(max(3, warmup)):
         topk(users_dev[w % n_sets], labels_dev[w % n_sets])
@@ -338,7 +341,6 @@ def eval_topk_bench(model, device, rank, world, steps, warmup, cpu_leg):
     ms_e2e = time_region(e2e_pass, steps, world)
     last = (steps - 1) % n_sets
     ndcg, recall = TopKRanker([K])(res["s"], res["l"])
-    expect_ndcg = 0.5 * sum(1.0 / torch.log2(torch.tensor(r + 2.0)).item() for r in range(K)) / K
     # kernel-only time of the fused scorer on this rank: pre-normalised users, pre-allocated scratch and outputs
     xn = ops.normalize_rows(users_dev[0])
     ws = ops.cosine_topk_ws(EVAL_USERS, hi - lo, K, device)
@@ -370,9 +372,9 @@ def eval_topk_bench(model, device, rank, world, steps, warmup, cpu_leg):
            "e2e": {"value": EVAL_USERS * steps / (ms_e2e / 1e3), "unit": "users/s", "ms_per_pass": ms_e2e / steps,
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "path": "pinned host users fp32 + labels -> H2D -> dist.sharded_topk(model, ...) -> .cpu() of scores/ids/label scores"},
-           "metrics": {"NDCG@10": ndcg, "Recall@10": recall, "expected_by_construction": {"NDCG@10": expect_ndcg, "Recall@10": 0.5},
-                       "note": "even users are labelled with the scorer's own (u mod 10)-th item, odd users uniformly; "
-                               "Spec R from (top-10 scores, label score)"},
+           "metrics": {"NDCG@10": ndcg, "Recall@10": recall, "note": "even users are labelled with one of the scorer's own top-10 items (rank 1..8 with the widest score gap "
+                               "to its neighbours), odd users uniformly, so Recall@10 = 0.5 by construction; Spec R from "
+                               "(top-10 scores, label score); cpu_baseline re-derives both metrics with the reference Ranker"},
            "roofline": {"bound": "tensor", "achieved": flops / (k_ms / 1e3) / 1e12, "peak": burst, "unit": "TFLOP/s",
                         "frac": flops / (k_ms / 1e3) / 1e12 / burst, "traffic": traffic if world == 1 else None,
                         "traffic_source": f"profiles/{traffic_src} (ncu --set full at 4096 x 1M, one GPU)" if traffic_src and world == 1 else None,

@@ -118,7 +118,7 @@ def test_band_attention_backward_regenerates_the_forward_dropout_mask():
     p = torch.nan_to_num(torch.softmax(s, -1), nan=0.0).masked_fill(~valid[:, None, :, None], 0.0)
     ref_ctx = ((p * keepb * KEEP_SCALE) @ v).transpose(1, 2).reshape(B, L, E)
     got = ctx.view(B, L, E).float()
-    assert (got[:, 1:] - ref_ctx[:, 1:]).abs().max() < 2e-2
+    assert (got[:, 1:] - ref_ctx[:, 1:]).abs().max() < 3e-2          # P' = p/(1-p) is rounded to bf16 before PV
     # ... and the backward kernel (which regenerates the mask) must match autograd through that same mask
     dctx = rnd(B * L, E, seed=7)
     dqkv = torch.full((B * L, 3 * E), float("nan"), dtype=torch.bfloat16, device=DEV)

@@ -144,8 +144,8 @@ def test_train_step_12layer_c2_shape_matches_reference(goldens):
         err = (gflat[ref["sample_idx"]] - ref["sample"]).abs().max().item() / ref["absmax"]
         worst_norm = max(worst_norm, (k, rel), key=lambda t: t[1])
         worst_elem = max(worst_elem, (k, err), key=lambda t: t[1])
-        assert rel < 0.03, (k, rel)
-        assert err < 0.05, (k, err)
+        assert rel < 0.01, (k, rel)          # measured worst: 0.4 % (query_global.bias of layer 1)
+        assert err < 0.04, (k, err)          # measured worst: 2.1 % of the tensor's abs-max
     print(f"12-layer C2 shape: loss {loss.item():.5f} vs reference {g['loss']:.5f}; worst grad-norm rel err {worst_norm}; "
           f"worst sampled element err / absmax {worst_elem}")
 
