@@ -5,6 +5,7 @@
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "rf_common.h"
 
@@ -33,6 +34,14 @@ static int g_n_nonce_loaders = 0;
 int register_nonce_loader(nonce_loader_fn fn) {
   if (g_n_nonce_loaders < 16) g_nonce_loaders[g_n_nonce_loaders++] = fn;
   return g_n_nonce_loaders;
+}
+
+// cudaFuncSetAttribute is per DEVICE: true exactly once per (flag, current device)
+bool first_use_on_device(std::atomic<unsigned long long>* seen) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  return (seen->fetch_or(bit) & bit) == 0;
 }
 
 int sm_count() {
@@ -96,7 +105,11 @@ static const CUtensorMap* lookup_or_encode(MapKey key, int rank) {
     return nullptr;
   }
   if (g_maps.size() > 8192) {  // unbounded growth guard for callers that keep reallocating
-    for (auto& kv : g_maps) delete kv.second;
+    // Another thread may still hold a pointer it obtained before this eviction (the lock is released before
+    // the launch that copies the map into kernel parameters): evicted maps are RETIRED, never freed
+    // (128 B each, at most one generation of 8192 per eviction).
+    static std::vector<CUtensorMap*> retired;
+    for (auto& kv : g_maps) retired.push_back(kv.second);
     g_maps.clear();
   }
   CUtensorMap* m = new CUtensorMap;

@@ -11,10 +11,13 @@
 //   dV = P^T dO        A = P  (MN-major view of the same P buffer), B = dO (MN-major)
 //   dK = dS^T Q        A = dS (MN-major view),                       B = Q  (MN-major)
 // so no operand is ever transposed in memory.  dQ (scaled back by 1/sqrt(D)) is written as bf16
-// into dqkv; dK/dV tiles (keys of neighbouring tiles overlap, and every tile contributes to the
-// CLS key) are accumulated with red.add.f32 into an fp32 scratch [B*L, 2E] that a small kernel
-// then folds into the K/V columns of dqkv.  The global query row receives no band gradient (its
-// band output is overwritten by the global row, HF:615-626).
+// into dqkv.  dK/dV tiles overlap between neighbouring query tiles: at attention_window 64 a key receives at most
+// two partial sums, which go straight into the bf16 gradient with 16-byte red.add.noftz.v4.bf16x2 (only the CLS
+// key, which every tile feeds, is accumulated in fp32 and folded in by a tiny kernel); wide windows (several
+// segments per key) accumulate dK/dV and dQ in fp32 scratch that a fold kernel converts.  The global query row
+// receives no band gradient (its band output is overwritten by the global row, HF:615-626).
+// Key validity is a bit mask per tile (band position by shifts: no per-element shared-memory flag loads), and the
+// dropout masks are regenerated from ABSOLUTE (row, key) coordinates (rf_ptx.cuh), independent of the tiling.
 #include <cuda_bf16.h>
 #include <math.h>
 #include <stdlib.h>
@@ -39,7 +42,7 @@ constexpr uint32_t AB_OFF_V = AB_OFF_K + AB_KV_BYTES;          // 26624 = 26 KiB
 constexpr uint32_t AB_OFF_P = AB_OFF_V + AB_KV_BYTES;
 constexpr uint32_t AB_OFF_DS = AB_OFF_P + AB_P_BYTES;
 constexpr uint32_t AB_OFF_FLAG = AB_OFF_DS + AB_P_BYTES;
-constexpr uint32_t AB_OFF_BAR = AB_OFF_FLAG + 208;
+constexpr uint32_t AB_OFF_BAR = AB_OFF_FLAG + 64;     // key-valid bit words (7 used)
 constexpr uint32_t AB_OFF_DELTA = AB_OFF_BAR + 64;
 constexpr uint32_t AB_SMEM = AB_OFF_DELTA + 4 * 128 * 4 + 1024;
 static_assert(AB_OFF_V % 1024 == 0 && AB_OFF_P % 1024 == 0, "swizzled tiles need 1024B alignment");
@@ -73,7 +76,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   uint8_t* sV = smem + AB_OFF_V;
   uint8_t* sP = smem + AB_OFF_P;
   uint8_t* sDS = smem + AB_OFF_DS;
-  uint8_t* kflag = smem + AB_OFF_FLAG;
+  uint32_t* kbits = reinterpret_cast<uint32_t*>(smem + AB_OFF_FLAG);
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + AB_OFF_BAR);
   uint64_t* bar_mma = bar_load + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
@@ -93,6 +96,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   const int i0 = tile * 128;
   const int E = p.H * AB_D;
   const uint8_t* mrow = p.mask012 + static_cast<size_t>(b) * p.L;
+  const int key0 = i0 - W + p.shift;             // absolute key index of tile column 0
 
   if (tid == 0) {
     mbar_init(bar_load, 1);
@@ -108,8 +112,8 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     }
 #pragma unroll
     for (int c = 0; c < NK / 64; ++c) {
-      tma_load_3d(sK + c * 8192, &tmQKV64, bar_load, E + h * AB_D, i0 - W + p.shift + c * 64, b);
-      tma_load_3d(sV + c * 8192, &tmQKV64, bar_load, 2 * E + h * AB_D, i0 - W + p.shift + c * 64, b);
+      tma_load_3d(sK + c * 8192, &tmQKV64, bar_load, E + h * AB_D, key0 + c * 64, b);
+      tma_load_3d(sV + c * 8192, &tmQKV64, bar_load, 2 * E + h * AB_D, key0 + c * 64, b);
     }
     tma_load_3d(sK + NK * 128, &tmQKV16, bar_load, E + h * AB_D, 0, b);
     tma_load_3d(sV + NK * 128, &tmQKV16, bar_load, 2 * E + h * AB_D, 0, b);
@@ -134,15 +138,14 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  for (int c = tid; c < NT; c += AB_THREADS) {
-    uint8_t f = 0;
-    if (c < NK) {
-      const int j = i0 - W + p.shift + c;
-      f = (j >= 0 && j < p.L && mrow[j] == 1) ? 1 : 0;
-    } else if (c == NK) {
-      f = (p.use_cls && mrow[0] == 2) ? 1 : 0;
-    }
-    kflag[c] = f;
+  // key-valid bits of the NK band columns (bit c: key is in range, not padding, not global); word 7 bit 0 = CLS column
+  if (warp < NK / 32) {
+    const int j = key0 + warp * 32 + lane;
+    const bool inr = j >= 0 && j < p.L;
+    const uint32_t word = __ballot_sync(0xffffffffu, inr && (mrow[inr ? j : 0] == 1));
+    if (lane == 0) kbits[warp] = word;
+  } else if (warp == NK / 32 && lane == 0) {
+    kbits[7] = (p.use_cls && mrow[0] == 2) ? 1u : 0u;
   }
   tc_fence_before();
   __syncthreads();
@@ -176,22 +179,19 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   const float LOG2E = 1.4426950408889634f;
   const float lse2 = lse * LOG2E;
   const uint64_t rowid = (static_cast<uint64_t>(b) * p.H + h) * p.L + (in_seq ? i : 0);
-  constexpr int DGRP = NT / 8;
-  const bool g_ok = kflag[NK] != 0;
+  const uint64_t rowbase = rowid * attn_drop_groups(p.L);
+  const bool g_ok = kbits[7] != 0;
   // window chunks of this row block: quad + part for parts 0..2; part 3 has the CLS column and the zero chunks
   const int cc_lo = quad + part;
   const int cc_hi = part < 3 ? quad + part + 1 : cc_lo;
 
-  auto chunk_keep = [&](int cc) -> uint32_t {
-    if (p.drop_thresh == 0) return 0xFFFFFFFFu;
-    uint32_t km = 0;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int c0 = cc * 32 + u * 8;
-      if (c0 + 7 >= r && c0 <= r + 2 * W)
-        km |= dropout_keep8(p.drop_seed, rowid * DGRP + (c0 >> 3), p.drop_thresh) << (u * 8);
-    }
-    return km;
+  // live columns of a 32-column chunk for this row: key-valid bits AND band position [r, r + 2W - hi_cut]
+  const int band_hi = 2 * W - p.hi_cut;
+  auto chunk_live = [&](int cc) -> uint32_t {
+    const int lo = r - cc * 32, hi = r + band_hi - cc * 32;
+    const uint32_t mlo = lo <= 0 ? 0xFFFFFFFFu : (lo >= 32 ? 0u : (0xFFFFFFFFu << lo));
+    const uint32_t mhi = hi >= 31 ? 0xFFFFFFFFu : (hi < 0 ? 0u : (0xFFFFFFFFu >> (31 - hi)));
+    return row_valid ? (kbits[cc] & mlo & mhi) : 0u;
   };
 
   // ---- delta_i = sum_j P'_ij dP_ij = dO_i . O_i  (O = sum_j P'_ij V_j is the saved forward output):
@@ -218,8 +218,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     pg = (row_valid && g_ok) ? exp2f(__uint_as_float(gs[0]) * LOG2E - lse2) : 0.f;   // undropped
     pg_d = pg;
     if (p.drop_thresh != 0) {
-      const uint32_t keep = dropout_keep8(p.drop_seed, rowid * DGRP + (NK >> 3), p.drop_thresh);
-      keep_g = (keep & 1u) ? p.drop_scale : 0.f;
+      keep_g = attn_keep_cls(p.drop_seed, rowbase, p.drop_thresh, p.drop_scale);
       pg_d = pg * keep_g;
     }
     dpg = __uint_as_float(gd[0]);
@@ -241,13 +240,13 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
       tmem_ld32(lane_base + TM_S + cc * 32, sv);
       tmem_ld32(lane_base + TM_DP + cc * 32, dv);
       tmem_ld_wait();
-      const uint32_t keepm = chunk_keep(cc);
+      const uint32_t live = chunk_live(cc);
+      const uint32_t keepm = (p.drop_thresh != 0 && live != 0)
+                                 ? attn_keep32(p.drop_seed, rowbase, key0 + cc * 32, p.drop_thresh, live) : 0xFFFFFFFFu;
       float pr[32], ds[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const int c = cc * 32 + j;
-        const bool ok = row_valid && kflag[c] && (c >= r) && (c <= r + 2 * W - p.hi_cut);
-        const float pu = ok ? exp2f(__uint_as_float(sv[j]) * LOG2E - lse2) : 0.f;
+        const float pu = ((live >> j) & 1u) ? exp2f(__uint_as_float(sv[j]) * LOG2E - lse2) : 0.f;
         const float kp = ((keepm >> j) & 1u) ? p.drop_scale : 0.f;
         pr[j] = pu * kp;                                           // P' feeds dV
         ds[j] = pu * (kp * __uint_as_float(dv[j]) - delta);        // softmax backward
@@ -372,9 +371,9 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
         const int u = lane & 7;                       // 16B unit = 4 floats of the 32-dim chunk
         const int c = hh * 128 + quad * 32 + rl;      // key column of the tile
         int j = -1;
-        if (c < NK) j = i0 - W + p.shift + c;
+        if (c < NK) j = key0 + c;
         else if (c == NK) j = 0;
-        const bool key_ok = (j >= 0 && j < p.L) && (c <= NK) && kflag[c <= NK ? c : 0];
+        const bool key_ok = (c < NK) ? ((kbits[c >> 5] >> (c & 31)) & 1u) != 0 : (c == NK && g_ok);
         const float4 x = *reinterpret_cast<const float4*>(slab + rl * 128 + ((u ^ (rl & 7)) << 4));
         if (key_ok) {
           float* dst = p.dkv + (static_cast<size_t>(b) * p.L + j) * 2 * E + which * E + h * AB_D + dhalf * 32 + u * 4;
@@ -391,9 +390,9 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
         const int uu = lane & 3;
         const int c = hh * 128 + quad * 32 + rl;
         int j = -1;
-        if (c < NK) j = i0 - W + p.shift + c;
+        if (c < NK) j = key0 + c;
         else if (c == NK) j = 0;
-        const bool key_ok = (j >= 0 && j < p.L) && (c <= NK) && kflag[c <= NK ? c : 0];
+        const bool key_ok = (c < NK) ? ((kbits[c >> 5] >> (c & 31)) & 1u) != 0 : (c == NK && g_ok);
         const float4 x0 = *reinterpret_cast<const float4*>(slab + rl * 128 + (((2 * uu) ^ (rl & 7)) << 4));
         const float4 x1 = *reinterpret_cast<const float4*>(slab + rl * 128 + (((2 * uu + 1) ^ (rl & 7)) << 4));
         if (key_ok && c == NK) {        // the CLS key: fp32 accumulation over all tiles of the sequence
@@ -469,10 +468,9 @@ extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const fl
   RF_REQUIRE(a->w >= 32 && a->w % 32 == 0 && a->w <= 256,
              "rf_band_attn_bwd: one-sided window %d unsupported (multiples of 32 up to 256)", a->w);
   RF_REQUIRE(a->B > 0 && a->L >= 16 && a->H > 0, "rf_band_attn_bwd: bad shape");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_seen{0};   // one bit per device
+  if (first_use_on_device(&attr_seen)) {
     RF_CUDA(cudaFuncSetAttribute(band_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
-    attr_set = true;
   }
   const int E = a->H * AB_D;
   const uint64_t L = a->L, B = a->B;
@@ -481,7 +479,7 @@ extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const fl
   const CUtensorMap* tm16 = get_tmap_3d(a->qkv, B, L, 3 * E, 3 * E, L * 3 * E, 16);
   const CUtensorMap* tmdo = get_tmap_3d(dctx, B, L, E, E, L * E, 64);
   if (!tm64 || !tm16 || !tmdo) return RF_ERR_CUDA;
-  // window segments: the same decomposition (and per-segment dropout seeds) as the forward pass
+  // window segments of 65 key offsets (the forward pass may segment differently: dropout masks are absolute)
   const int nseg = (2 * a->w + 1 + 64) / 65;
   RF_REQUIRE(nseg == 1 || a->ws != nullptr, "rf_band_attn_bwd: windows wider than 64 need a workspace");
   float* dq32 = nseg > 1 ? reinterpret_cast<float*>(a->ws) : nullptr;
@@ -511,7 +509,7 @@ extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const fl
     p.shift = lo + 32;
     p.hi_cut = hi > a->w ? hi - a->w : 0;
     p.use_cls = k == 0;
-    p.drop_seed = nseg == 1 ? a->drop_seed : a->drop_seed + 0x9E3779B97F4A7C15ull * k;
+    p.drop_seed = a->drop_seed;     // masks are keyed on absolute (row, key): the same seed for every segment
     band_attn_bwd_kernel<<<a->B * a->H * tiles, AB_THREADS, AB_SMEM, stream>>>(*tm64, *tm16, *tmdo, p);
     int rc = check_launch("rf_band_attn_bwd");
     if (rc) return rc;

@@ -1,14 +1,19 @@
 // Banded (sliding-window) attention forward with a global CLS key column, sm_100a.
 //
-// One CTA = one (batch, head, 128-query tile).  Keys j in [i0-W, i0+127+W] (NK = 128+2W rows)
-// plus the sequence's first 16 rows (row 0 = the global CLS key) are TMA-loaded once
-// (128B-swizzled, out-of-range rows zero-filled by TMA), then
+// One CTA = one (batch, head, 128-query tile), templated on the one-sided window W in {32, 64, 128}
+// (attention_window 64 / 128 / 256 in ONE pass; attention_window 512 = two W=128 segments merged through
+// their log-sum-exps).  Keys j in [i0-W, i0+127+W] (NK = 128+2W rows) plus the sequence's first 16 rows
+// (row 0 = the global CLS key) are TMA-loaded once (128B-swizzled, out-of-range rows zero-filled by TMA), then
 //   S[128 x (NK+16)] = Q K^T          tcgen05.mma, fp32 accumulator in TMEM
-//   softmax over the band + CLS column in fp32, one thread per query row (tcgen05.ld); the
-//   band / padding / global masks are predicates on (row, column), never materialised
-//   P (bf16) -> shared memory in the K-major UMMA layout (aliasing the dead Q/K tiles)
+//   softmax over the band + CLS column in fp32.  TWO threads per query row (warps w and w+4 share TMEM lane
+//   quadrant w): each reads its half of the row's 2W+32 window columns from TMEM ONCE into registers
+//   (tcgen05.ld x16), masks them with a per-row bit mask (key-valid bits of the tile AND the band position,
+//   built with shifts: no per-element shared-memory flag loads), and the two halves exchange max / sum through
+//   shared memory;  P (bf16) -> shared memory in the K-major UMMA layout (aliasing the dead Q/K tiles)
 //   O[128 x 64] = P V                 tcgen05.mma (V is the MN-major B operand, no transpose)
-//   O / rowsum -> bf16 context; log-sum-exp saved for the backward pass.
+//   O / rowsum -> bf16 context (32 head dims per thread); log-sum-exp saved for the backward pass.
+// Dropout masks are keyed on ABSOLUTE coordinates (row, key >> 3), so the backward kernel regenerates them
+// whatever its own tiling / window segmentation is.
 // Semantics: SURVEY.md §8a Spec A / HF:481-639.  Global keys are removed from the band and
 // re-enter through the extra column (HF:523,558-568); padded query rows produce zeros (HF:578);
 // the global query row (position 0 when mask012==2) is left to rf_global_attn_fwd (HF:963-1056).
@@ -22,7 +27,7 @@ RF_DEFINE_NONCE_LOADER(attn_fwd)
 
 namespace rf {
 
-constexpr int ATT_THREADS = 128;
+constexpr int ATT_THREADS = 256;
 constexpr int HEAD_DIM = 64;
 
 template <int W>
@@ -30,16 +35,20 @@ struct AttnFwdCfg {
   static constexpr int NK = 128 + 2 * W;       // band key rows
   static constexpr int NT = NK + 16;           // + global chunk
   static constexpr int PCH = (NT + 63) / 64;   // 64-key P chunks
+  static constexpr int WIN_CH = 2 * W / 32 + 1;   // 32-column chunks a row quadrant's band can touch
+  static constexpr int UNITS = WIN_CH;            // 16-column units per thread (two threads per row)
   static constexpr uint32_t Q_BYTES = 128 * 128;
   static constexpr uint32_t KV_BYTES = NT * 128;
   static constexpr uint32_t P_BYTES = PCH * 16384;
   static constexpr uint32_t REGION_A = (Q_BYTES + KV_BYTES > P_BYTES) ? (Q_BYTES + KV_BYTES) : P_BYTES;
   static constexpr uint32_t OFF_V = REGION_A;
-  static constexpr uint32_t OFF_FLAG = OFF_V + KV_BYTES;
-  static constexpr uint32_t OFF_BAR = OFF_FLAG + ((NT + 15) / 16) * 16;
+  static constexpr uint32_t OFF_BITS = OFF_V + KV_BYTES;            // key-valid bit words
+  static constexpr uint32_t OFF_RED = OFF_BITS + 64;                // [2][2][128] floats: max / sum exchange
+  static constexpr uint32_t OFF_BAR = OFF_RED + 4 * 128 * 4;
   static constexpr uint32_t TOTAL = OFF_BAR + 64 + 1024;
   static constexpr uint32_t TMEM_COLS = (NT <= 256) ? 256 : 512;
   static_assert(NT <= 512, "window too large for the single-shot kernel");
+  static_assert(NT <= 14 * 32, "key-valid bit words");
   static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
@@ -48,8 +57,8 @@ struct AttnFwdParams {
   __nv_bfloat16* ctx;
   float* lse;
   int B, L, H;
-  // window segment (windows wider than 2*W+1 keys are covered by several launches whose outputs are merged
-  // through their log-sum-exps): keys are shifted by `shift` rows, the top `hi_cut` offsets of the band are
+  // window segment (windows wider than the kernel's 2W+1 keys are covered by several launches whose outputs are
+  // merged through their log-sum-exps): keys are shifted by `shift` rows, the top `hi_cut` offsets of the band are
   // cut, the CLS column is only part of segment 0, and an empty row reports lse = -inf instead of 0
   int shift, hi_cut, use_cls, lse_neg_inf;
   float drop_scale;
@@ -62,20 +71,22 @@ __global__ void __launch_bounds__(ATT_THREADS)
 band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
                      const AttnFwdParams p) {
   using C = AttnFwdCfg<W>;
-  constexpr int NK = C::NK, NT = C::NT;
+  constexpr int NK = C::NK, NT = C::NT, UNITS = C::UNITS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sQ = smem;
   uint8_t* sK = smem + C::Q_BYTES;
   uint8_t* sP = smem;  // aliases Q/K once S has been computed
   uint8_t* sV = smem + C::OFF_V;
-  uint8_t* kflag = smem + C::OFF_FLAG;
+  uint32_t* kbits = reinterpret_cast<uint32_t*>(smem + C::OFF_BITS);
+  float* s_red = reinterpret_cast<float*>(smem + C::OFF_RED);
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* bar_mma = bar_load + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, part = warp >> 2;
   const int tiles_per_seq = (p.L + 127) / 128;
   const int tile = blockIdx.x % tiles_per_seq;
   const int h = (blockIdx.x / tiles_per_seq) % p.H;
@@ -83,40 +94,42 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
   const int i0 = tile * 128;
   const int E = p.H * HEAD_DIM;
   const uint8_t* mrow = p.mask012 + static_cast<size_t>(b) * p.L;
+  const int key0 = i0 - W + p.shift;             // absolute key index of tile column 0
 
   if (tid == 0) {
     mbar_init(bar_load, 1);
     mbar_init(bar_mma, 1);
     fence_mbar_init();
-    // the operand loads are issued first: the TMEM allocation and the key-flag set-up below (global loads
+    // the operand loads are issued first: the TMEM allocation and the key-bit set-up below (global loads
     // of the mask) then run under their latency
     mbar_arrive_expect_tx(bar_load, C::Q_BYTES + 2 * C::KV_BYTES);
 #pragma unroll
     for (int c = 0; c < 2; ++c) tma_load_3d(sQ + c * 8192, &tm64, bar_load, h * HEAD_DIM, i0 + c * 64, b);
 #pragma unroll
     for (int c = 0; c < NK / 64; ++c) {
-      tma_load_3d(sK + c * 8192, &tm64, bar_load, E + h * HEAD_DIM, i0 - W + p.shift + c * 64, b);
-      tma_load_3d(sV + c * 8192, &tm64, bar_load, 2 * E + h * HEAD_DIM, i0 - W + p.shift + c * 64, b);
+      tma_load_3d(sK + c * 8192, &tm64, bar_load, E + h * HEAD_DIM, key0 + c * 64, b);
+      tma_load_3d(sV + c * 8192, &tm64, bar_load, 2 * E + h * HEAD_DIM, key0 + c * 64, b);
     }
     tma_load_3d(sK + NK * 128, &tm16, bar_load, E + h * HEAD_DIM, 0, b);
     tma_load_3d(sV + NK * 128, &tm16, bar_load, 2 * E + h * HEAD_DIM, 0, b);
   }
   // the row's mask bytes are loaded now, next to the TMA loads (first used after the S MMA)
-  const uint8_t m_row = mrow[(i0 + tid) < p.L ? (i0 + tid) : 0], m_cls = mrow[0];
+  const int r = quad * 32 + lane;       // query row of the tile == TMEM lane
+  const int i = i0 + r;
+  const uint8_t m_row = mrow[i < p.L ? i : 0], m_cls = mrow[0];
   __syncwarp();
   if (warp == 0) {
     tmem_alloc(tmem_slot, C::TMEM_COLS);
     tmem_relinquish();
   }
-  for (int c = tid; c < NT; c += ATT_THREADS) {
-    uint8_t f = 0;
-    if (c < NK) {
-      const int j = i0 - W + p.shift + c;
-      f = (j >= 0 && j < p.L && mrow[j] == 1) ? 1 : 0;
-    } else if (c == NK) {
-      f = (p.use_cls && mrow[0] == 2) ? 1 : 0;
-    }
-    kflag[c] = f;
+  // key-valid bits of the NK band columns (bit c: key is in range, not padding, not global)
+#pragma unroll 1
+  for (int cb = warp * 32; cb < NK; cb += ATT_THREADS) {
+    const int j = key0 + cb + lane;
+    const bool inr = j >= 0 && j < p.L;
+    const bool f = inr && (mrow[inr ? j : 0] == 1);
+    const uint32_t word = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) kbits[cb >> 5] = word;
   }
   tc_fence_before();
   __syncthreads();
@@ -140,100 +153,97 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
     }
     umma_commit(bar_mma);
   }
+  // per-row band masks of this thread's 16-column units (independent of S: computed while the MMA runs)
+  const bool row_valid = (i < p.L) && (m_row != 0);
+  const int ubase = quad * 2 + part * UNITS;       // first 16-column unit of this thread (tile column / 16)
+  uint32_t wmask[UNITS];
+#pragma unroll
+  for (int u = 0; u < UNITS; ++u) {
+    const int c0 = (ubase + u) * 16;
+    const uint32_t kw = (kbits[c0 >> 5] >> (c0 & 31)) & 0xFFFFu;
+    const int lo = r - c0, hi = r + band_hi - c0;
+    const uint32_t mlo = lo <= 0 ? 0xFFFFu : (lo >= 16 ? 0u : ((0xFFFFu << lo) & 0xFFFFu));
+    const uint32_t mhi = hi >= 15 ? 0xFFFFu : (hi < 0 ? 0u : (0xFFFFu >> (15 - hi)));
+    wmask[u] = row_valid ? (kw & mlo & mhi) : 0u;
+  }
+  const bool g_ok = p.use_cls && (m_cls == 2);
   __syncwarp();
   mbar_wait(bar_mma, 0);
   tc_fence_after();
 
-  // ---- softmax: thread r owns query row i0 + r (TMEM lane r) ----
-  const int r = tid;
-  const int i = i0 + r;
-  const bool row_valid = (i < p.L) && (m_row != 0);
-  const uint32_t lane_base = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  constexpr int WIN_CH = 2 * W / 32 + 1;   // 32-column chunks that can hold this warp's band
+  // ---- softmax: threads (quad, part 0) and (quad, part 1) share query row i0 + r (TMEM lane r) ----
+  const uint32_t lane_base = tmem + (static_cast<uint32_t>(quad * 32) << 16);
   const float LOG2E = 1.4426950408889634f;
-
-  float m = -INFINITY;
-  {
-#pragma unroll 1
-    for (int cc = warp; cc < warp + WIN_CH; ++cc) {
-      uint32_t v[32];
-      tmem_ld32(lane_base + cc * 32, v);
-      tmem_ld_wait();
+  uint32_t sv[UNITS][16];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = cc * 32 + j;
-        const bool ok = kflag[c] && (c >= r) && (c <= r + band_hi);
-        m = ok ? fmaxf(m, __uint_as_float(v[j])) : m;
-      }
-    }
-  }
+  for (int u = 0; u < UNITS; ++u) tmem_ld16(lane_base + (ubase + u) * 16, sv[u]);
   uint32_t g16[16];
-  tmem_ld16(lane_base + NK, g16);
+  if (part == 1) tmem_ld16(lane_base + NK, g16);   // warp-uniform
   tmem_ld_wait();
-  const float sg = __uint_as_float(g16[0]);
-  const bool g_ok = kflag[NK] != 0;
-  if (g_ok) m = fmaxf(m, sg);
-  if (!row_valid || m == -INFINITY) m = 0.0f;   // fully masked row: every p below is forced to 0
+  float m = -INFINITY;
+#pragma unroll
+  for (int u = 0; u < UNITS; ++u)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float s = ((wmask[u] >> j) & 1u) ? __uint_as_float(sv[u][j]) : -INFINITY;
+      sv[u][j] = __float_as_uint(s);
+      m = fmaxf(m, s);
+    }
+  float sg = -INFINITY;
+  if (part == 1 && g_ok && row_valid) sg = __uint_as_float(g16[0]);
+  m = fmaxf(m, sg);
+  s_red[part * 128 + r] = m;
+  __syncthreads();
+  m = fmaxf(s_red[r], s_red[128 + r]);
+  if (m == -INFINITY) m = 0.0f;   // fully masked row: every p below is exp2(-inf) = 0
   const float m2 = m * LOG2E;
 
+  const uint64_t rowid = (static_cast<uint64_t>(b) * p.H + h) * p.L + (i < p.L ? i : 0);
+  const uint64_t rowbase = rowid * attn_drop_groups(p.L);
   float l = 0.0f;
+#pragma unroll
+  for (int u = 0; u < UNITS; ++u) {
+    float pr[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float e = exp2f(__uint_as_float(sv[u][j]) * LOG2E - m2);
+      l += e;
+      pr[j] = e;
+    }
+    if (p.drop_thresh != 0 && wmask[u] != 0) {
+      const uint32_t keep = attn_keep16(p.drop_seed, rowbase, key0 + (ubase + u) * 16, p.drop_thresh);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pr[j] = ((keep >> j) & 1u) ? pr[j] * p.drop_scale : 0.0f;
+    }
+    const int c0 = (ubase + u) * 16;
+    uint8_t* prow = sP + (c0 >> 6) * 16384 + r * 128;
+    const int u16 = (c0 & 63) >> 3;     // first of the two 16-byte units inside the 64-key chunk
+    *reinterpret_cast<uint4*>(prow + (((u16) ^ (r & 7)) << 4)) =
+        make_uint4(pack_bf16(pr[0], pr[1]), pack_bf16(pr[2], pr[3]), pack_bf16(pr[4], pr[5]), pack_bf16(pr[6], pr[7]));
+    *reinterpret_cast<uint4*>(prow + (((u16 + 1) ^ (r & 7)) << 4)) =
+        make_uint4(pack_bf16(pr[8], pr[9]), pack_bf16(pr[10], pr[11]), pack_bf16(pr[12], pr[13]), pack_bf16(pr[14], pr[15]));
+  }
+  // zero fill: the 16-column units of the band columns outside this row quadrant's window (split by parity)
 #pragma unroll 1
-  for (int cc = 0; cc < NK / 32; ++cc) {
-    uint4 out[4];
-    if (cc >= warp && cc < warp + WIN_CH) {   // warp-uniform
-      uint32_t v[32];
-      tmem_ld32(lane_base + cc * 32, v);
-      tmem_ld_wait();
-      float pr[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = cc * 32 + j;
-        const bool ok = row_valid && kflag[c] && (c >= r) && (c <= r + band_hi);
-        const float e = ok ? exp2f(__uint_as_float(v[j]) * LOG2E - m2) : 0.0f;
-        l += e;
-        pr[j] = e;
-      }
-      if (p.drop_thresh != 0) {
-        // keep-mask keyed on (row, 8-column group of the tile): one Philox call per 8 probabilities
-        const uint64_t rowid = (static_cast<uint64_t>(b) * p.H + h) * p.L + i;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c0 = cc * 32 + u * 8;
-          if (c0 + 7 >= r && c0 <= r + 2 * W) {
-            const uint32_t keep = dropout_keep8(p.drop_seed, rowid * (NT / 8) + (c0 >> 3), p.drop_thresh);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) pr[u * 8 + e] = ((keep >> e) & 1u) ? pr[u * 8 + e] * p.drop_scale : 0.0f;
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        out[u].x = pack_bf16(pr[u * 8 + 0], pr[u * 8 + 1]);
-        out[u].y = pack_bf16(pr[u * 8 + 2], pr[u * 8 + 3]);
-        out[u].z = pack_bf16(pr[u * 8 + 4], pr[u * 8 + 5]);
-        out[u].w = pack_bf16(pr[u * 8 + 6], pr[u * 8 + 7]);
-      }
-    } else {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) out[u] = make_uint4(0, 0, 0, 0);
-    }
-    uint8_t* prow = sP + (cc >> 1) * 16384 + r * 128;
-    const int ubase = (cc & 1) * 4;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(prow + (((ubase + u) ^ (r & 7)) << 4)) = out[u];
+  for (int uu = part; uu < NK / 16; uu += 2) {
+    if (uu >= quad * 2 && uu < quad * 2 + 2 * UNITS) continue;   // warp-uniform
+    const int c0 = uu * 16;
+    uint8_t* prow = sP + (c0 >> 6) * 16384 + r * 128;
+    const int u16 = (c0 & 63) >> 3;
+    *reinterpret_cast<uint4*>(prow + ((u16 ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(prow + (((u16 + 1) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
   }
-  {
-    float pg = (row_valid && g_ok) ? exp2f(sg * LOG2E - m2) : 0.0f;
+  if (part == 1) {
+    // global chunk: tile column NK holds the CLS key (absolute key 0), columns NK+1.. are zero
+    float pg = exp2f(sg * LOG2E - m2);
     l += pg;
-    if (p.drop_thresh != 0) {
-      const uint64_t rowid = (static_cast<uint64_t>(b) * p.H + h) * p.L + i;
-      const uint32_t keep = dropout_keep8(p.drop_seed, rowid * (NT / 8) + (NK >> 3), p.drop_thresh);
-      pg = (keep & 1u) ? pg * p.drop_scale : 0.0f;
-    }
-    uint8_t* prow = sP + (NK / 64) * 16384 + r * 128;
-    *reinterpret_cast<uint4*>(prow + ((0 ^ (r & 7)) << 4)) = make_uint4(pack_bf16(pg, 0.0f), 0, 0, 0);
-    *reinterpret_cast<uint4*>(prow + ((1 ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+    if (p.drop_thresh != 0) pg *= attn_keep_cls(p.drop_seed, rowbase, p.drop_thresh, p.drop_scale);
+    uint8_t* prow = sP + (NK >> 6) * 16384 + r * 128;
+    const int u16 = (NK & 63) >> 3;
+    *reinterpret_cast<uint4*>(prow + ((u16 ^ (r & 7)) << 4)) = make_uint4(pack_bf16(pg, 0.0f), 0, 0, 0);
+    *reinterpret_cast<uint4*>(prow + (((u16 + 1) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
   }
+  s_red[256 + part * 128 + r] = l;
 
   // ---- O = P V ----
   fence_proxy_async_smem();
@@ -249,18 +259,19 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
                 umma_smem_desc(av + ks * 2048, 8192, 1024), idesc2, ks > 0 ? 1u : 0u);
     umma_commit(bar_mma);
   }
-  __syncwarp();
-  mbar_wait(bar_mma, 1);
-  tc_fence_after();
-
+  l = s_red[256 + r] + s_red[384 + r];
   const float inv_l = l > 0.0f ? 1.0f / l : 0.0f;
   const bool is_global_row = (i == 0) && (m_cls == 2);
   const bool do_store = (i < p.L) && !is_global_row;
-  __nv_bfloat16* orow = p.ctx + (static_cast<size_t>(b) * p.L + (do_store ? i : 0)) * E + h * HEAD_DIM;
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
+  __nv_bfloat16* orow = p.ctx + (static_cast<size_t>(b) * p.L + (do_store ? i : 0)) * E + h * HEAD_DIM + part * 32;
+  if (part == 0 && i < p.L)
+    p.lse[(static_cast<size_t>(b) * p.H + h) * p.L + i] = (l > 0.0f) ? (m + logf(l)) : (p.lse_neg_inf ? -INFINITY : 0.0f);
+  __syncwarp();
+  mbar_wait(bar_mma, 1);
+  tc_fence_after();
+  {
     uint32_t v[32];
-    tmem_ld32(lane_base + half * 32, v);   // warp-collective: executed by every lane
+    tmem_ld32(lane_base + part * 32, v);   // warp-collective: executed by every lane
     tmem_ld_wait();
     if (do_store) {
 #pragma unroll
@@ -270,12 +281,10 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
         o.y = pack_bf16(__uint_as_float(v[j + 2]) * inv_l, __uint_as_float(v[j + 3]) * inv_l);
         o.z = pack_bf16(__uint_as_float(v[j + 4]) * inv_l, __uint_as_float(v[j + 5]) * inv_l);
         o.w = pack_bf16(__uint_as_float(v[j + 6]) * inv_l, __uint_as_float(v[j + 7]) * inv_l);
-        *reinterpret_cast<uint4*>(orow + half * 32 + j) = o;
+        *reinterpret_cast<uint4*>(orow + j) = o;
       }
     }
   }
-  if (i < p.L)
-    p.lse[(static_cast<size_t>(b) * p.H + h) * p.L + i] = (l > 0.0f) ? (m + logf(l)) : (p.lse_neg_inf ? -INFINITY : 0.0f);
 
   tc_fence_before();
   __syncthreads();
@@ -341,28 +350,33 @@ attn_merge_kernel(float* __restrict__ acc, float* __restrict__ lse_acc, const __
 
 struct AttnSegment { int shift, hi_cut, use_cls; };
 
-// Segments of a band of half-width w for the W = 32 kernels (65 key offsets each): offsets [-w + 65k, -w + 65k + 64]
-// clipped to [-w, w]; the kernel's own band is centred, so segment k is run with keys shifted by its centre.
-static int attn_segments(int w, AttnSegment* seg) {
-  const int n = (2 * w + 1 + 64) / 65;
+// Native half-width of the forward kernel used for a band of half-width w: the widest of {32, 64, 128} that
+// does not exceed w.
+static int fwd_native_w(int w) { return w >= 128 ? 128 : (w >= 64 ? 64 : 32); }
+
+// Segments of a band of half-width w for a kernel of native half-width wk (2*wk+1 key offsets each): offsets
+// [-w + (2wk+1)k, -w + (2wk+1)k + 2wk] clipped to [-w, w]; the kernel's own band is centred, so segment k is run
+// with keys shifted by its centre.
+static int attn_segments(int w, int wk, AttnSegment* seg) {
+  const int span = 2 * wk + 1;
+  const int n = (2 * w + 1 + span - 1) / span;
   for (int k = 0; k < n; ++k) {
-    const int lo = -w + 65 * k, hi = lo + 64;
-    seg[k].shift = lo + 32;
+    const int lo = -w + span * k, hi = lo + 2 * wk;
+    seg[k].shift = lo + wk;
     seg[k].hi_cut = hi > w ? hi - w : 0;
     seg[k].use_cls = k == 0;
   }
   return n;
 }
 
-static int launch_attn_fwd32(const rf_attn_args* a, void* ctx, float* lse, const AttnSegment& sg, int lse_neg_inf,
-                             uint64_t seed, cudaStream_t stream) {
-  constexpr int W = 32;
+template <int W>
+static int launch_attn_fwd(const rf_attn_args* a, void* ctx, float* lse, const AttnSegment& sg, int lse_neg_inf,
+                           cudaStream_t stream) {
   using C = AttnFwdCfg<W>;
   auto kern = band_attn_fwd_kernel<W>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_seen{0};   // one bit per device
+  if (first_use_on_device(&attr_seen)) {
     RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
-    attr_set = true;
   }
   const int E = a->H * HEAD_DIM;
   const CUtensorMap* tm64 = get_tmap_3d(a->qkv, a->B, a->L, 3 * E, 3 * E, static_cast<uint64_t>(a->L) * 3 * E, 64);
@@ -376,10 +390,17 @@ static int launch_attn_fwd32(const rf_attn_args* a, void* ctx, float* lse, const
   p.shift = sg.shift; p.hi_cut = sg.hi_cut; p.use_cls = sg.use_cls; p.lse_neg_inf = lse_neg_inf;
   p.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   p.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
-  p.drop_seed = seed;
+  p.drop_seed = a->drop_seed;
   const int tiles = (a->L + 127) / 128;
   kern<<<a->B * a->H * tiles, ATT_THREADS, C::TOTAL, stream>>>(*tm64, *tm16, p);
   return check_launch("rf_band_attn_fwd");
+}
+
+static int launch_attn_fwd_w(int wk, const rf_attn_args* a, void* ctx, float* lse, const AttnSegment& sg, int lse_neg_inf,
+                             cudaStream_t stream) {
+  if (wk == 128) return launch_attn_fwd<128>(a, ctx, lse, sg, lse_neg_inf, stream);
+  if (wk == 64) return launch_attn_fwd<64>(a, ctx, lse, sg, lse_neg_inf, stream);
+  return launch_attn_fwd<32>(a, ctx, lse, sg, lse_neg_inf, stream);
 }
 
 }  // namespace rf
@@ -387,7 +408,8 @@ static int launch_attn_fwd32(const rf_attn_args* a, void* ctx, float* lse, const
 extern "C" long long rf_band_attn_ws_bytes(int B, int L, int H, int w) {
   if (w <= 32) return 0;
   const long long T = static_cast<long long>(B) * L, E = static_cast<long long>(H) * rf::HEAD_DIM;
-  // forward: fp32 accumulator [T,E] + bf16 segment output [T,E] + 2 x lse [B,H,L];  backward: fp32 dQ scratch [T,E]
+  // forward (segmented windows only): fp32 accumulator [T,E] + bf16 segment output [T,E] + 2 x lse [B,H,L];
+  // backward: fp32 dQ scratch [T,E] (aliases the forward accumulator)
   return T * E * 4 + T * E * 2 + 2ll * B * H * L * 4 + 256;
 }
 
@@ -399,10 +421,12 @@ extern "C" int rf_band_attn_fwd(const rf_attn_args* a, void* ctx, float* lse, rf
   RF_REQUIRE(a->B > 0 && a->L >= 16 && a->H > 0, "rf_band_attn_fwd: bad shape B=%d L=%d H=%d", a->B, a->L, a->H);
   RF_REQUIRE(a->w >= 32 && a->w % 32 == 0 && a->w <= 256,
              "rf_band_attn_fwd: one-sided window %d unsupported (multiples of 32 up to 256)", a->w);
+  RF_REQUIRE(a->L <= ATTN_MAX_L, "rf_band_attn_fwd: sequence length %d exceeds %d", a->L, ATTN_MAX_L);
   AttnSegment seg[16];
-  const int nseg = attn_segments(a->w, seg);
-  if (nseg == 1) return launch_attn_fwd32(a, ctx, lse, seg[0], 0, a->drop_seed, stream);
-  RF_REQUIRE(a->ws != nullptr, "rf_band_attn_fwd: windows wider than 64 need a workspace (rf_band_attn_ws_bytes)");
+  const int wk = fwd_native_w(a->w);
+  const int nseg = attn_segments(a->w, wk, seg);
+  if (nseg == 1) return launch_attn_fwd_w(wk, a, ctx, lse, seg[0], 0, stream);
+  RF_REQUIRE(a->ws != nullptr, "rf_band_attn_fwd: this window needs a workspace (rf_band_attn_ws_bytes)");
   const size_t T = static_cast<size_t>(a->B) * a->L, E = static_cast<size_t>(a->H) * HEAD_DIM;
   uint8_t* ws = reinterpret_cast<uint8_t*>(a->ws);
   float* acc = reinterpret_cast<float*>(ws);
@@ -411,7 +435,7 @@ extern "C" int rf_band_attn_fwd(const rf_attn_args* a, void* ctx, float* lse, rf
   float* lse_acc = lse_part + static_cast<size_t>(a->B) * a->H * a->L;
   const long long total = static_cast<long long>(T) * a->H * 8;
   for (int k = 0; k < nseg; ++k) {
-    int rc = launch_attn_fwd32(a, part, lse_part, seg[k], 1, a->drop_seed + 0x9E3779B97F4A7C15ull * k, stream);
+    int rc = launch_attn_fwd_w(wk, a, part, lse_part, seg[k], 1, stream);
     if (rc) return rc;
     attn_merge_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
         acc, lse_acc, part, lse_part, a->mask012, reinterpret_cast<__nv_bfloat16*>(ctx), lse, a->B, a->L, a->H, k == 0,

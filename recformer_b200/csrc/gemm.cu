@@ -606,10 +606,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <bool A_MN, bool B_MN, int EPI, bool OUT_F32, int RES, bool DROP, bool SPLITK, bool XK = false>
 static int launch_gemm_pair(const rf_gemm_args* a, cudaStream_t stream) {
   auto kern = gemm_pair_kernel<A_MN, B_MN, EPI, OUT_F32, RES, DROP, SPLITK, XK>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_seen{0};   // one bit per device
+  if (first_use_on_device(&attr_seen)) {
     RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
-    attr_set = true;
   }
   const CUtensorMap* tmA = A_MN ? get_tmap_2d(a->A, a->K, a->M, a->lda, 64) : get_tmap_2d(a->A, a->M, a->K, a->lda, 128);
   if (!tmA) return RF_ERR_CUDA;
@@ -636,10 +635,9 @@ template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32, int RES, bool DRO
 static int launch_gemm(const rf_gemm_args* a, cudaStream_t stream) {
   using S = GemmSmem<BN>;
   auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, OUT_F32, RES, DROP, SPLITK>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_seen{0};   // one bit per device
+  if (first_use_on_device(&attr_seen)) {
     RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
   }
   const CUtensorMap* tmA = A_MN ? get_tmap_2d(a->A, a->K, a->M, a->lda, 64) : get_tmap_2d(a->A, a->M, a->K, a->lda, BM);
   if (!tmA) return RF_ERR_CUDA;

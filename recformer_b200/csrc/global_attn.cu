@@ -579,10 +579,9 @@ template <int MODE>
 static int launch_mix(const __nv_bfloat16* tile_src, MixParams& p, cudaStream_t stream, const char* what) {
   using C = MixCfg<MODE>;
   auto kern = global_mix_kernel<MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_seen{0};   // one bit per device
+  if (first_use_on_device(&attr_seen)) {
     RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_set = true;
   }
   const uint64_t B = p.B, L = p.L;
   const CUtensorMap* tmx = get_tmap_3d(tile_src, B, L, GE, GE, L * GE, C::TOK);

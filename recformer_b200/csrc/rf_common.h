@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/recformer_b200.h"
 
 namespace rf {
@@ -35,6 +37,8 @@ const CUtensorMap* get_tmap_3d(const void* ptr, uint64_t batch, uint64_t rows, u
                                uint64_t batch_stride_elems, uint32_t box_rows);
 
 int sm_count();
+// true exactly once per (flag, current CUDA device): guards the per-device cudaFuncSetAttribute calls
+bool first_use_on_device(std::atomic<unsigned long long>* seen);
 
 // Translation units whose kernels draw dropout masks register a loader for their copy of
 // rf_dropout_nonce (rf_ptx.cuh); rf_set_dropout_nonce() runs every registered loader.

@@ -331,4 +331,36 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t grp, u
   return m;
 }
 
+// ---- attention-probability dropout: masks keyed on ABSOLUTE (row, key) coordinates ---------------------------
+// keep(row, key j) = bit (j' & 7) of dropout_keep8(seed, row * attn_drop_groups(L) + (j' >> 3)), j' = j + ATTN_DROP_BIAS
+// (the bias keeps tile columns left of the sequence start non-negative).  The forward and backward kernels tile and
+// segment the band differently; with absolute coordinates each regenerates the same bits for the columns it holds.
+constexpr int ATTN_DROP_BIAS = 1024;       // multiple of 8; > the widest reach of a tile left of key 0
+constexpr int ATTN_MAX_L = 1 << 20;
+__device__ __forceinline__ uint64_t attn_drop_groups(int L) { return static_cast<uint64_t>((L + 2 * ATTN_DROP_BIAS) / 8 + 2); }
+// keep bits of 16 consecutive keys starting at absolute key j0 (any alignment)
+__device__ __forceinline__ uint32_t attn_keep16(uint64_t seed, uint64_t rowbase, int j0, uint32_t thresh) {
+  const int jb = j0 + ATTN_DROP_BIAS;
+  const int g0 = jb >> 3, sh = jb & 7;
+  uint32_t bits = dropout_keep8(seed, rowbase + g0, thresh) | (dropout_keep8(seed, rowbase + g0 + 1, thresh) << 8);
+  if (sh != 0) bits |= dropout_keep8(seed, rowbase + g0 + 2, thresh) << 16;
+  return (bits >> sh) & 0xFFFFu;
+}
+// keep bits of 32 consecutive keys starting at absolute key j0; `live` = bit mask of the columns that matter (8-key
+// groups without a live column are not generated)
+__device__ __forceinline__ uint32_t attn_keep32(uint64_t seed, uint64_t rowbase, int j0, uint32_t thresh, uint32_t live) {
+  const int jb = j0 + ATTN_DROP_BIAS;
+  const int g0 = jb >> 3, sh = jb & 7;
+  const uint64_t live64 = static_cast<uint64_t>(live) << sh;
+  uint64_t bits = 0;
+#pragma unroll
+  for (int g = 0; g < 5; ++g)
+    if ((live64 >> (8 * g)) & 0xFFull) bits |= static_cast<uint64_t>(dropout_keep8(seed, rowbase + g0 + g, thresh)) << (8 * g);
+  return static_cast<uint32_t>(bits >> sh);
+}
+// dropout factor (scale or 0) of the global CLS key column = absolute key 0
+__device__ __forceinline__ float attn_keep_cls(uint64_t seed, uint64_t rowbase, uint32_t thresh, float scale) {
+  return (dropout_keep8(seed, rowbase + (ATTN_DROP_BIAS >> 3), thresh) & 1u) ? scale : 0.0f;
+}
+
 }  // namespace rf

@@ -754,13 +754,12 @@ static int plan_schedule(int B, long long N, ScoreParams* p) {
 }
 
 static int launch_cosine(int mode, const void* xn, const void* yn, ScoreParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_seen{0};   // one bit per device
+  if (first_use_on_device(&attr_seen)) {
     RF_CUDA(cudaFuncSetAttribute(cosine_mma_kernel<SC_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
     RF_CUDA(cudaFuncSetAttribute(cosine_mma_kernel<SC_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
     RF_CUDA(cudaFuncSetAttribute(cosine_pair_kernel<SC_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
     RF_CUDA(cudaFuncSetAttribute(cosine_pair_kernel<SC_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
-    attr_set = true;
   }
   if (use_pair(p.B)) {
     const CUtensorMap* tmA = get_tmap_2d(xn, p.B, p.K, p.K, 128);

@@ -78,12 +78,13 @@ def _band_allowed(mask012, L, w):
 def _probe_band_keep(mask, allowed, B, L, H, w, seed):
     """Reads the (dropped, scaled) probability matrix A[b,h,i,j] out of rf_band_attn_fwd: with q = 0 the softmax is
     uniform over the allowed keys, and one-hot value rows v_j = e_(j mod 64) make ctx[i, d] the sum of A[i, j] over
-    the allowed keys with j mod 64 = d.  Three passes (keys with even / odd j // 64, and the global CLS key) leave
-    at most ONE such key per (i, d): the only band keys 64 apart are j = i-32 and i+32, which differ in j // 64."""
+    the allowed keys with j mod 64 = d.  One pass per residue of (j // 64) modulo the number of 64-key blocks a band can
+    touch, plus one for the global CLS key, leaves at most ONE allowed key per (i, d) in every pass."""
     E = H * 64
     j = torch.arange(L, device=DEV)
     A = torch.zeros(B, H, L, L, device=DEV)
-    for cls in (((j // 64) % 2 == 0) & (j != 0), ((j // 64) % 2 == 1) & (j != 0), j == 0):
+    ncls = (2 * w) // 64 + 2           # a band of 2w+1 keys touches at most this many 64-key blocks
+    for cls in [((j // 64) % ncls == c) & (j != 0) for c in range(ncls)] + [j == 0]:
         qkv = torch.zeros(B, L, 3, H, 64, device=DEV)
         qkv[:, :, 2] = (torch.nn.functional.one_hot(j % 64, 64).float() * cls[:, None].float())[None, :, None, :]
         ctx, _ = ops.band_attn_fwd(qkv.view(B * L, 3 * E).to(torch.bfloat16), mask, B, L, H, w, drop_p=P_DROP, drop_seed=seed)
@@ -92,12 +93,15 @@ def _probe_band_keep(mask, allowed, B, L, H, w, seed):
     return A
 
 
-def test_band_attention_backward_regenerates_the_forward_dropout_mask():
-    B, L, H, w, seed = 2, 256, 12, 32, 0xABCDEF01
+@pytest.mark.parametrize("L,w", [(256, 32), (256, 64), (320, 96), (512, 128)])
+def test_band_attention_backward_regenerates_the_forward_dropout_mask(L, w):
+    """w = 32: one forward / one backward pass; 64 and 128: single-pass forward kernels, 65-offset backward segments;
+    96: TWO forward segments whose key origin is not 8-aligned (the absolute-coordinate mask bits are re-aligned)."""
+    B, H, seed = 2, 12, 0xABCDEF01
     E = H * 64
     mask = torch.ones(B, L, dtype=torch.uint8, device=DEV)
     mask[:, 0] = 2
-    mask[1, 200:] = 0
+    mask[1, L - 56:] = 0
     allowed, valid = _band_allowed(mask.long(), L, w)
     A = _probe_band_keep(mask, allowed, B, L, H, w, seed)
     n_allowed = allowed.sum(-1).clamp_min(1).float()                                            # (B, L)

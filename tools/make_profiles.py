@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
-KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg ", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.max ", "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg ", "sm__cycles_elapsed.avg ", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active_realtime.avg.pct", "sm__inst_executed_pipe_tensor", "smsp__inst_executed.sum ",
         "smsp__issue_active.avg.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "l1tex__throughput.avg.pct", "dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum ",
@@ -71,6 +71,18 @@ def summarise_rep(rep, dst, topn=12):
             if any(key in cc for key in KEYS) and r[idx] not in ("", "n/a") and "not_issued" not in c and \
                "pct_of_peak_sustained_active" not in c.replace("warps_active", "").replace("issue_active", ""):
                 lines.append(f"  {c:84s} {units[idx]:12s} {r[idx][:40]}")
+        # tcgen05 tensor-pipe utilisation.  `sm__pipe_tensor_cycles_active_realtime...pct` under-reports UTCHMMA work
+        # by ~5x on sm_100a (it read 3.5-18 % on GEMMs that CUDA events put at 0.86-1.34 PFLOP/s).  The sub-pipe cycle
+        # counter is exact: it equals (UTCHMMA instructions per SM) x (cycles per instruction at the dense bf16 rate,
+        # 8192 FLOP/clk/SM) x 4 (it aggregates the SM's four sub-partitions), so active share = counter / 4 / elapsed.
+        try:
+            hm = float(r[h.index("TPC.TriageCompute.sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg")])
+            el = float(r[h.index("sm__cycles_elapsed.max")])
+            ghz = float(r[h.index("sm__cycles_elapsed.max.per_second")])
+            lines.append(f"  {'DERIVED tensor pipe (UTCHMMA) active = hmma_cycles_active_realtime.avg / 4 / sm__cycles_elapsed.max':84s} "
+                         f"{'%':12s} {100 * hm / 4 / el:.1f}   (= {hm / 4 * 8192 * 148 * ghz / el / 1e3:.0f} TFLOP/s at {ghz:.2f} GHz)")
+        except (ValueError, IndexError):
+            pass
         norm = lambda n: n.replace("rf::", "").replace("void ", "").replace("(bool)", "").replace("(int)", "").split("(")[0].replace(" ", "")
         hs = []
         for key, val in hot.items():
@@ -136,4 +148,26 @@ for f in sorted(os.listdir(G)):
 for t in traffic.values():
     t["dram_bytes"] /= t["n"]; t["time_us"] /= t["n"]
 json.dump(traffic, open(os.path.join(P, R + "_traffic.json"), "w"), indent=1, sort_keys=True)
+# SASS evidence: tcgen05 / TMEM / TMA mnemonics per kernel of the shipped library (cuobjdump, no GPU needed)
+lib = os.path.join(ROOT, "recformer_b200", "librecformer_b200.so")
+if os.path.exists(lib):
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    counts, cur = {}, None
+    pats = ("UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "HMMA.", "RED.E", "ATOM")
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0][:90]
+            counts[cur] = dict.fromkeys(pats, 0)
+        elif cur:
+            for pat in pats:
+                if pat in line: counts[cur][pat] += 1
+    out = [f"# cuobjdump -sass recformer_b200/librecformer_b200.so: instruction counts per kernel ({R}); UTCHMMA = tcgen05.mma,",
+           "# LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG/UBLKCP = TMA, UTCBAR = tcgen05.commit, HMMA. = legacy mma.sync (none expected)",
+           f"{'kernel':92s} " + " ".join(f"{x:>8s}" for x in pats)]
+    for k, v in sorted(counts.items()):
+        out.append(f"{k:92s} " + " ".join(f"{v[x]:8d}" for x in pats))
+    tot = {x: sum(v[x] for v in counts.values()) for x in pats}
+    out.append(f"{'TOTAL':92s} " + " ".join(f"{tot[x]:8d}" for x in pats))
+    open(os.path.join(P, R + "_sass_counts.txt"), "w").write("\n".join(out) + "\n")
 print(sorted(os.listdir(P)))

@@ -53,6 +53,59 @@ FLOPS = {"gemm_qkv": 2 * T * 3 * E * E, "gemm_up_gelu": 2 * T * F * E, "gemm_dow
          "gemm_dgrad_dgelu": 2 * T * F * E, "gemm_wgrad_up": 2 * T * F * E, "gemm_wgrad_qkv": 2 * T * 3 * E * E}
 BYTES = {"attn_fwd": T * 4 * E * 2, "attn_bwd": T * 8 * E * 2, "ln_fwd": T * E * (4 + 2 + 4), "ln_bwd": T * E * (2 + 4 + 2 + 2),
          "colsum_3072": T * F * 2}
+# embeddings + LN (fwd / bwd) and the fused AdamW at the C2 shapes
+_emb = {}
+def _embed_setup():
+    if _emb: return _emb
+    V, P_ = 50265, 4098
+    _emb["tabs"] = [rf(V, E, sc=0.02), rf(P_, E, sc=0.02), rf(4, E, sc=0.02), rf(51, E, sc=0.02), 1 + rf(E, sc=0.1), rf(E, sc=0.1)]
+    ids = torch.randint(3, V, (B, L), device=dev, generator=g); ids[:, 0] = 0
+    _emb["ids"], _emb["tt"] = ids, torch.randint(1, 3, (B, L), device=dev, generator=g)
+    _emb["ip"] = (torch.arange(L, device=dev)[None, :] // 60 + 1).expand(B, L).clamp(max=50).contiguous()
+    _emb["err"] = torch.zeros(1, dtype=torch.int32, device=dev)
+    _emb["pos"], _ = ops.prepare_inputs(ids, torch.ones_like(ids), None, L, 1, _emb["err"])
+    _emb["grads"] = [torch.zeros_like(t) for t in _emb["tabs"]]
+    _emb["out"] = torch.empty(T, E, dtype=torch.bfloat16, device=dev); _emb["out32"] = torch.empty(T, E, device=dev)
+    return _emb
+def _embed_fwd():
+    e = _embed_setup()
+    ops.embed_ln_fwd(e["ids"], e["tt"], e["ip"], e["pos"], *e["tabs"], L, 1, 1e-5, e["err"], drop_p=0.1, drop_seed=9, out=e["out"], out32=e["out32"])
+def _embed_bwd():
+    e = _embed_setup()
+    ops.embed_ln_bwd(dx, e["ids"], e["tt"], e["ip"], e["pos"], *e["tabs"], L, 1, 1e-5, *e["grads"], drop_p=0.1, drop_seed=9)
+CASES["embed_fwd"], CASES["embed_bwd"] = _embed_fwd, _embed_bwd
+BYTES["embed_fwd"] = T * (E * 4 + E * 2 + E * 4 + 32)        # word row fp32 + bf16 out + fp32 out + ids
+BYTES["embed_bwd"] = T * (E * 2 + E * 4 + E * 4 + 32)        # dout + recomputed word row + fp32 word-grad row RMW (atomics)
+_ad = {}
+def _adamw():
+    if not _ad:
+        n = 85 * 1024 * 1024      # the dense encoder segment of the flat buffer (85 M parameters)
+        _ad["p"], _ad["g"] = rf(n, sc=0.02), rf(n, sc=0.001)
+        _ad["m"], _ad["v"] = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+        _ad["s"] = torch.empty(n, dtype=torch.bfloat16, device=dev)
+    ops.adamw_step(_ad["p"], _ad["g"], _ad["m"], _ad["v"], _ad["s"], 5e-5, 0.9, 0.999, 1e-8, 0.01, 3)
+CASES["adamw"] = _adamw
+BYTES["adamw"] = 85 * 1024 * 1024 * (4 * 4 + 3 * 4 + 2)       # read p,g,m,v; write p,m,v + bf16 shadow
+# wide windows at the C5 shape (2 x 4096 tokens)
+_wd = {}
+def _wide(w, bwd):
+    Bw, Lw = 2, 4096
+    if "qkv" not in _wd:
+        _wd["qkv"] = rb(Bw * Lw, 3 * E); _wd["mask"] = torch.ones(Bw, Lw, dtype=torch.uint8, device=dev); _wd["mask"][:, 0] = 2
+        _wd["mask"][1, 3900:] = 0
+        _wd["ctx"] = torch.empty(Bw * Lw, E, dtype=torch.bfloat16, device=dev); _wd["lse"] = torch.empty(Bw, H, Lw, device=dev)
+        _wd["dctx"] = rb(Bw * Lw, E, sc=0.01); _wd["dqkv"] = torch.empty(Bw * Lw, 3 * E, dtype=torch.bfloat16, device=dev)
+        _wd["scr"] = torch.empty(Bw * Lw, 2 * E, device=dev)
+    ws = _wd.setdefault(("ws", w), ops.band_attn_ws(Bw, Lw, H, w, dev))
+    if bwd:
+        ops.band_attn_bwd(_wd["qkv"], _wd["mask"], Bw, Lw, H, w, _wd["ctx"], _wd["lse"], _wd["dctx"], _wd["dqkv"], _wd["scr"], ws=ws)
+    else:
+        ops.band_attn_fwd(_wd["qkv"], _wd["mask"], Bw, Lw, H, w, ctx=_wd["ctx"], lse=_wd["lse"], ws=ws)
+for _w in (64, 128, 256):
+    CASES[f"attn_fwd_w{2 * _w}"] = (lambda w=_w: _wide(w, False))
+    CASES[f"attn_bwd_w{2 * _w}"] = (lambda w=_w: _wide(w, True))
+    BYTES[f"attn_fwd_w{2 * _w}"] = 2 * 4096 * 4 * E * 2
+    BYTES[f"attn_bwd_w{2 * _w}"] = 2 * 4096 * 8 * E * 2
 CASES["attn_bwd_nodrop"] = lambda: ops.band_attn_bwd(qkv, mask, B, L, H, 32, ctx, lse, dctx, dqkv, scratch)
 CASES["attn_fwd_nodrop"] = lambda: ops.band_attn_fwd(qkv, mask, B, L, H, 32, ctx=ctx, lse=lse)
 BYTES["attn_bwd_nodrop"] = BYTES["attn_bwd"]; BYTES["attn_fwd_nodrop"] = BYTES["attn_fwd"]
