@@ -257,6 +257,13 @@ long long rf_cosine_topk_ws_bytes(int B, long long N, int k);
 int rf_cosine_topk(const void* xn_bf16, const void* yn_bf16, int B, long long N, int E, float temp, int k,
                    int id_base, const int64_t* labels_or_null, float* topk_scores, int32_t* topk_ids,
                    float* label_score, void* ws, rf_stream_t stream);
+/* Same, written as ONE packed fp32 buffer [B, 2k+1] = k scores | k ids (int32 bit patterns) | label score per user:
+ * the unit a rank contributes to the all-gather of sharded scoring (one collective, no pack kernel). */
+int rf_cosine_topk_packed(const void* xn_bf16, const void* yn_bf16, int B, long long N, int E, float temp, int k,
+                          int id_base, const int64_t* labels_or_null, float* packed, void* ws, rf_stream_t stream);
+/* Merge of `parts` packed buffers [parts, B, 2k+1] (the all-gather result) into the global top-k. */
+int rf_topk_merge_packed(const float* packed, int parts, int B, int k, float* out_scores, int32_t* out_ids,
+                         float* out_label_score, rf_stream_t stream);
 /* Merge `parts` lists of k (score,id) per user (e.g. the all-gathered per-GPU top-k) into the
  * global top-k; label scores are max-reduced over parts. */
 int rf_topk_merge(const float* scores, const int32_t* ids, const float* label_scores, int parts, int B, int k,
@@ -297,6 +304,12 @@ int rf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_av
 int rf_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16_or_null,
                       long long n, float beta1, float beta2, float eps, float weight_decay, const float* hp_dev,
                       rf_stream_t stream);
+/* Same update reading the gradient as bf16 — the wire format of the data-parallel gradient all-reduce
+ * (recformer_b200.dist.GradSync; the reference's DeepSpeed stage-2 path reduces fp16 gradients,
+ * ref: lightning_pretrain.py:143).  hp_dev may be NULL (then lr / step / grad_scale arguments are used). */
+int rf_adamw_step_bf16grad(float* param, const void* grad_bf16, float* exp_avg, float* exp_avg_sq, void* shadow_bf16_or_null,
+                           long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                           float grad_scale, const float* hp_dev_or_null, rf_stream_t stream);
 /* Dropout sites: ref: recformer/models.py:134 (embeddings), HF:585,1035 (attention probabilities), HF:1069,1128
  * (dense outputs); torch draws them from its generator state.  Here the masks are Philox draws keyed by
  * (drop_seed argument XOR a library-wide nonce).  The nonce is 0

@@ -78,6 +78,9 @@ _SIGS = {
     "rf_cosine_topk_ws_bytes": (c_ll, [c_int, c_ll, c_int]),
     "rf_cosine_topk": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rf_cosine_topk_packed": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_int, c_int, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
+    "rf_topk_merge_packed": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rf_topk_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p]),
     "rf_cosine_candidates": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_float, c_void_p, c_void_p]),
@@ -92,6 +95,8 @@ _SIGS = {
                               c_float, c_float, c_int, c_float, c_void_p]),
     "rf_adamw_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float,
                                   c_float, c_void_p, c_void_p]),
+    "rf_adamw_step_bf16grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float,
+                                       c_float, c_float, c_int, c_float, c_void_p, c_void_p]),
     "rf_set_dropout_nonce": (c_int, [c_void_p, c_void_p]),
 }
 

@@ -443,7 +443,8 @@ __global__ void cast_f32_bf16_kernel(const float4* __restrict__ x, uint2* __rest
   }
 }
 
-__global__ void adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+template <bool G_BF16>
+__global__ void adamw_kernel(float4* __restrict__ p, const void* __restrict__ g_, float4* __restrict__ m,
                              float4* __restrict__ v, uint2* __restrict__ shadow, long long n4, float lr, float b1,
                              float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale,
                              const float* __restrict__ hp) {
@@ -451,7 +452,14 @@ __global__ void adamw_kernel(float4* __restrict__ p, const float4* __restrict__ 
     lr = __ldg(hp); bc1 = __ldg(hp + 1); bc2_sqrt = __ldg(hp + 2); gscale = __ldg(hp + 3);
   }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+    float4 pp = p[i], gg, mm = m[i], vv = v[i];
+    if (G_BF16) {   // gradients as they come off the bf16 all-reduce of data-parallel training
+      const uint2 raw = reinterpret_cast<const uint2*>(g_)[i];
+      const float2 lo = unpack_bf16(raw.x), hi = unpack_bf16(raw.y);
+      gg = make_float4(lo.x, lo.y, hi.x, hi.y);
+    } else {
+      gg = reinterpret_cast<const float4*>(g_)[i];
+    }
     float* pa = reinterpret_cast<float*>(&pp); float* ga = reinterpret_cast<float*>(&gg);
     float* ma = reinterpret_cast<float*>(&mm); float* va = reinterpret_cast<float*>(&vv);
 #pragma unroll
@@ -588,11 +596,29 @@ extern "C" int rf_adamw_step(float* param, const float* grad, float* exp_avg, fl
   const long long n4 = n / 4;
   long long grid = (n4 + 255) / 256;
   if (grid > sm_count() * 16) grid = sm_count() * 16;
-  adamw_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(
-      reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad), reinterpret_cast<float4*>(exp_avg),
+  adamw_kernel<false><<<static_cast<int>(grid), 256, 0, stream>>>(
+      reinterpret_cast<float4*>(param), grad, reinterpret_cast<float4*>(exp_avg),
       reinterpret_cast<float4*>(exp_avg_sq), reinterpret_cast<uint2*>(shadow), n4, lr, beta1, beta2, eps, weight_decay,
       bc1, sqrtf(bc2), grad_scale, nullptr);
   return check_launch("rf_adamw_step");
+}
+
+extern "C" int rf_adamw_step_bf16grad(float* param, const void* grad_bf16, float* exp_avg, float* exp_avg_sq, void* shadow,
+                                      long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                      int step, float grad_scale, const float* hp_dev, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(param && grad_bf16 && exp_avg && exp_avg_sq && n > 0 && n % 4 == 0 && (hp_dev || step >= 1),
+             "rf_adamw_step_bf16grad: bad argument");
+  const long long n4 = n / 4;
+  long long grid = (n4 + 255) / 256;
+  if (grid > sm_count() * 16) grid = sm_count() * 16;
+  const float bc1 = hp_dev ? 1.f : 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2 = hp_dev ? 1.f : 1.f - powf(beta2, static_cast<float>(step));
+  adamw_kernel<true><<<static_cast<int>(grid), 256, 0, stream>>>(
+      reinterpret_cast<float4*>(param), grad_bf16, reinterpret_cast<float4*>(exp_avg),
+      reinterpret_cast<float4*>(exp_avg_sq), reinterpret_cast<uint2*>(shadow), n4, lr, beta1, beta2, eps, weight_decay,
+      bc1, sqrtf(bc2), grad_scale, hp_dev);
+  return check_launch("rf_adamw_step_bf16grad");
 }
 
 extern "C" int rf_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow,
@@ -603,8 +629,8 @@ extern "C" int rf_adamw_step_dev(float* param, const float* grad, float* exp_avg
   const long long n4 = n / 4;
   long long grid = (n4 + 255) / 256;
   if (grid > sm_count() * 16) grid = sm_count() * 16;
-  adamw_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(
-      reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad), reinterpret_cast<float4*>(exp_avg),
+  adamw_kernel<false><<<static_cast<int>(grid), 256, 0, stream>>>(
+      reinterpret_cast<float4*>(param), grad, reinterpret_cast<float4*>(exp_avg),
       reinterpret_cast<float4*>(exp_avg_sq), reinterpret_cast<uint2*>(shadow), n4, 0.f, beta1, beta2, eps, weight_decay,
       1.f, 1.f, 1.f, hp_dev);
   return check_launch("rf_adamw_step_dev");

@@ -50,6 +50,8 @@ struct ScoreParams {
   float* ws_scores;               // [parts][B][k]   part = (slice or S + extra pair) * 2 + column half
   int32_t* ws_ids;                // [parts][B][k]
   float* ws_label;                // [parts][B]
+  unsigned int* ws_thr;           // [B + 1]: per user row, max over all parts of their current k-th best score (order-
+                                  //          preserving uint encoding, 0 = nothing yet); slot B absorbs rows past B
   float* logits;                  // DENSE: [B][N]
 };
 
@@ -59,14 +61,46 @@ enum { SC_TOPK = 0, SC_DENSE = 1 };
 // ([q][thread], conflict-free); only the current k-th best score (`thr`) is kept in a register, so
 // the common case — no column of a 32-column accumulator chunk beats thr — costs one max per
 // column and a single warp vote.
+//
+// Cross-part pruning.  A user row's items are swept by several parts (item-tile slices x column halves, leftover
+// pairs), each with its own list.  A part whose list is full publishes its k-th best score t (atomicMax on an order-
+// preserving encoding): that part alone holds k items scoring >= t, so no item scoring < t can be in the row's global
+// top-k.  Every part therefore also rejects candidates below the published maximum g — with `>=`, not `>`: an item
+// that TIES with g may still win its place by the lower-id rule.  Without this every part pays the full warm-up of a
+// young list (k (1 + ln(n/k)) inserts for its n items); with it the row pays roughly one warm-up in total, which is
+// what makes a 125k-item shard (8-GPU sharding of the 1M table) cost little more per item than the whole table.
 struct TopkState {
   float* scratch;   // this thread's column of its warp's [32][32] fp32 chunk slab
   float* ts;        // &list_scores[0][thread]
   int* ti;          // &list_ids[0][thread]
-  float thr;
+  float thr;        // k-th best score of THIS part's list (-inf until the list is full)
+  float eff;        // strict rejection threshold: max(thr, largest float below the published g)
+  float gprev;      // largest float below g
+  float published;  // last value of thr this thread published
+  unsigned int* gthr;
   float label_score;
   long long label_local;   // label id relative to this table shard, or -1
 };
+
+__device__ __forceinline__ unsigned int f2ord(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned int u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+constexpr unsigned int ORD_NEG_INF = 0x007FFFFFu;   // f2ord(-inf); anything <= is "no threshold yet"
+
+// once per item tile: pick up what the other parts have published, publish our own k-th best if it rose
+__device__ __forceinline__ void topk_sync_threshold(TopkState& st) {
+  if (st.thr > st.published) {
+    atomicMax(st.gthr, f2ord(st.thr));
+    st.published = st.thr;
+  }
+  const unsigned int u = *reinterpret_cast<volatile unsigned int*>(st.gthr);
+  st.gprev = (u <= ORD_NEG_INF) ? -INFINITY : ord2f(u - 1);
+  st.eff = fmaxf(st.thr, st.gprev);
+}
 
 constexpr int SC_LIST_STRIDE = SC_EPI_WARPS * 32;
 
@@ -98,7 +132,7 @@ __device__ __forceinline__ void topk_chunk(const uint32_t (&r)[32], TopkState& s
   const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * p.inv_temp;   // == max_j (r[j] * inv_temp): rounding is monotonic
   const long long rel = st.label_local - col0;
   const bool partial = col0 + 32 > p.N;                                // warp-uniform
-  const bool mine = (mx > st.thr) || (rel >= 0 && rel < 32) || partial;
+  const bool mine = (mx > st.eff) || (rel >= 0 && rel < 32) || partial;
   if (!__any_sync(0xffffffffu, mine)) return;
   // slow path: bit mask of the columns that beat the current k-th best, then one insertion per set bit
   // (a straight-line predicated insert per column costs ~10x more: the threshold only moves on a hit)
@@ -109,7 +143,7 @@ __device__ __forceinline__ void topk_chunk(const uint32_t (&r)[32], TopkState& s
     for (int j = 0; j < 32; ++j) {
       const float s = __uint_as_float(r[j]) * p.inv_temp;
       if (j == rel && j < nvalid) st.label_score = s;
-      hits |= (s > st.thr && j < nvalid) ? (1u << j) : 0u;
+      hits |= (s > st.eff && j < nvalid) ? (1u << j) : 0u;
     }
   }
   if (__any_sync(0xffffffffu, hits != 0)) {
@@ -122,7 +156,10 @@ __device__ __forceinline__ void topk_chunk(const uint32_t (&r)[32], TopkState& s
       const int j = __ffs(hits) - 1;
       hits &= hits - 1;
       const float s = st.scratch[j * 32] * p.inv_temp;
-      if (s > st.thr) st.thr = topk_insert(st.ts, st.ti, p.k, s, id0 + j);   // thr may have risen since the mask was built
+      if (s > st.eff) {   // the threshold may have risen since the mask was built
+        st.thr = topk_insert(st.ts, st.ti, p.k, s, id0 + j);
+        st.eff = fmaxf(st.thr, st.gprev);
+      }
     }
   }
   __syncwarp();
@@ -143,7 +180,8 @@ __device__ __forceinline__ void topk_state_init(TopkState& st, uint8_t* list_sme
   st.ts = reinterpret_cast<float*>(list_smem) + etid;
   st.ti = reinterpret_cast<int*>(list_smem + SC_MAXK * SC_LIST_STRIDE * 4) + etid;
   for (int q = 0; q < SC_MAXK; ++q) { st.ts[q * SC_LIST_STRIDE] = -INFINITY; st.ti[q * SC_LIST_STRIDE] = 0x7fffffff; }
-  st.thr = -INFINITY;
+  st.thr = st.eff = st.gprev = st.published = -INFINITY;
+  st.gthr = p.ws_thr + (row_ok ? row : p.B);
   st.label_score = -INFINITY;
   st.label_local = -1;
   if (p.labels != nullptr && row_ok) {
@@ -247,6 +285,7 @@ cosine_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * SC_BN + half * (SC_BN / 2);
       uint32_t rbuf[2][32];
       tmem_ld32(tbase, rbuf[0]);
+      if (MODE == SC_TOPK) topk_sync_threshold(st);
 #pragma unroll
       for (int c = 0; c < SC_BN / 2 / 32; ++c) {
         tmem_ld_wait();
@@ -405,6 +444,7 @@ cosine_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * SC_BN + half * (SC_BN / 2);
         uint32_t rbuf[2][32];
         tmem_ld32(tbase, rbuf[0]);
+        if (MODE == SC_TOPK) topk_sync_threshold(st);
 #pragma unroll
         for (int c = 0; c < SC_BN / 2 / 32; ++c) {
           tmem_ld_wait();
@@ -435,7 +475,10 @@ cosine_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 __global__ void topk_merge_kernel(const float* __restrict__ scores, const int32_t* __restrict__ ids,
                                   const float* __restrict__ label_scores, int parts, int B, int k,
                                   float* __restrict__ out_scores, int32_t* __restrict__ out_ids,
-                                  float* __restrict__ out_label) {
+                                  float* __restrict__ out_label, int in_ld, int in_part_stride, int out_ld, int out_label_ld) {
+  // inputs: list q of (part s, row b) at scores[s * in_part_stride + b * in_ld + q] (ids likewise, label scores at
+  // label_scores[s * in_part_stride + b * in_ld]); outputs with row strides out_ld / out_label_ld.  The dense
+  // [parts][B][k] layout is in_ld = k, in_part_stride = B * k; a packed (B, 2k+1) row = k scores | k ids | label.
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float ts[SC_MAXK]; int ti[SC_MAXK];
@@ -443,9 +486,11 @@ __global__ void topk_merge_kernel(const float* __restrict__ scores, const int32_
   for (int i = 0; i < SC_MAXK; ++i) { ts[i] = -INFINITY; ti[i] = 0x7fffffff; }
   float lab = -INFINITY;
   for (int s = 0; s < parts; ++s) {
-    const float* ps = scores + (static_cast<size_t>(s) * B + b) * k;
-    const int32_t* pi = ids + (static_cast<size_t>(s) * B + b) * k;
-    if (label_scores) lab = fmaxf(lab, label_scores[static_cast<size_t>(s) * B + b]);
+    const float* ps = scores + static_cast<size_t>(s) * in_part_stride + static_cast<size_t>(b) * in_ld;
+    const int32_t* pi = ids + static_cast<size_t>(s) * in_part_stride + static_cast<size_t>(b) * in_ld;
+    if (label_scores)
+      lab = fmaxf(lab, in_ld == k ? label_scores[static_cast<size_t>(s) * B + b]
+                                  : label_scores[static_cast<size_t>(s) * in_part_stride + static_cast<size_t>(b) * in_ld]);
     for (int q0 = 0; q0 < k; ++q0) {
       float cs = ps[q0]; int ci = pi[q0];
       if (!(cs > -INFINITY)) break;   // -inf = list not full, NaN = part never written for this row
@@ -462,8 +507,8 @@ __global__ void topk_merge_kernel(const float* __restrict__ scores, const int32_
   }
 #pragma unroll
   for (int q = 0; q < SC_MAXK; ++q)
-    if (q < k) { out_scores[static_cast<size_t>(b) * k + q] = ts[q]; out_ids[static_cast<size_t>(b) * k + q] = ti[q]; }
-  if (out_label) out_label[b] = lab;
+    if (q < k) { out_scores[static_cast<size_t>(b) * out_ld + q] = ts[q]; out_ids[static_cast<size_t>(b) * out_ld + q] = ti[q]; }
+  if (out_label) out_label[static_cast<size_t>(b) * out_label_ld] = lab;
 }
 
 // y[n,:] = x[n,:] / max(|x[n,:]|, 1e-8) as bf16; one warp per row (E = 768).
@@ -815,14 +860,14 @@ extern "C" int rf_cosine_logits(const void* xn, const void* yn, float* logits, i
 
 extern "C" long long rf_cosine_topk_ws_bytes(int B, long long N, int k) {
   const long long parts = 2ll * plan_schedule(B, N, nullptr);
-  return parts * B * (static_cast<long long>(k) * 8 + 4) + 256;
+  return parts * B * (static_cast<long long>(k) * 8 + 4) + (static_cast<long long>(B) + 1) * 4 + 256;
 }
 
-extern "C" int rf_cosine_topk(const void* xn, const void* yn, int B, long long N, int E, float temp, int k,
-                              int id_base, const int64_t* labels, float* topk_scores, int32_t* topk_ids,
-                              float* label_score, void* ws, rf_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+static int cosine_topk_impl(const void* xn, const void* yn, int B, long long N, int E, float temp, int k, int id_base,
+                            const int64_t* labels, float* topk_scores, int32_t* topk_ids, float* label_score, int out_ld,
+                            int label_ld, void* ws, cudaStream_t stream) {
   RF_REQUIRE(xn && yn && topk_scores && topk_ids && ws && B > 0 && N > 0, "rf_cosine_topk: bad argument");
+  RF_REQUIRE(static_cast<long long>(B) * (2 * k + 1) < 2147483647ll, "rf_cosine_topk: B * k too large");
   RF_REQUIRE(k >= 1 && k <= SC_MAXK, "rf_cosine_topk: k=%d out of range [1,%d]", k, SC_MAXK);
   RF_REQUIRE(E % 8 == 0, "rf_cosine_topk: E must be a multiple of 8");
   RF_REQUIRE(N + id_base < 2147483647ll, "rf_cosine_topk: item ids must fit int32");
@@ -836,12 +881,41 @@ extern "C" int rf_cosine_topk(const void* xn, const void* yn, int B, long long N
   p.ws_label = reinterpret_cast<float*>(p.ws_ids + cnt);
   // a leftover pair only writes the rows of the user tiles it visited: every other (part, row) slot keeps
   // this NaN pattern, which the merge skips
+  p.ws_thr = reinterpret_cast<unsigned int*>(p.ws_label + static_cast<size_t>(parts) * B);
   RF_CUDA(cudaMemsetAsync(ws, 0xFF, cnt * 8 + static_cast<size_t>(parts) * B * 4, stream));
+  RF_CUDA(cudaMemsetAsync(p.ws_thr, 0, (static_cast<size_t>(B) + 1) * 4, stream));     // 0 = no threshold published yet
   int rc = launch_cosine(SC_TOPK, xn, yn, p, stream);
   if (rc) return rc;
-  topk_merge_kernel<<<(B + 127) / 128, 128, 0, stream>>>(p.ws_scores, p.ws_ids, p.ws_label, parts, B, k,
-                                                        topk_scores, topk_ids, label_score);
+  topk_merge_kernel<<<(B + 127) / 128, 128, 0, stream>>>(p.ws_scores, p.ws_ids, p.ws_label, parts, B, k, topk_scores,
+                                                        topk_ids, label_score, k, B * k, out_ld, label_ld);
   return check_launch("rf_cosine_topk/merge");
+}
+
+extern "C" int rf_cosine_topk(const void* xn, const void* yn, int B, long long N, int E, float temp, int k,
+                              int id_base, const int64_t* labels, float* topk_scores, int32_t* topk_ids,
+                              float* label_score, void* ws, rf_stream_t stream_) {
+  RF_REQUIRE(topk_scores && topk_ids, "rf_cosine_topk: bad argument");
+  return cosine_topk_impl(xn, yn, B, N, E, temp, k, id_base, labels, topk_scores, topk_ids, label_score, k, 1, ws,
+                          reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int rf_cosine_topk_packed(const void* xn, const void* yn, int B, long long N, int E, float temp, int k,
+                                     int id_base, const int64_t* labels, float* packed, void* ws, rf_stream_t stream_) {
+  RF_REQUIRE(packed, "rf_cosine_topk_packed: bad argument");
+  const int ld = 2 * k + 1;
+  return cosine_topk_impl(xn, yn, B, N, E, temp, k, id_base, labels, packed, reinterpret_cast<int32_t*>(packed) + k,
+                          packed + 2 * k, ld, ld, ws, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int rf_topk_merge_packed(const float* packed, int parts, int B, int k, float* out_scores, int32_t* out_ids,
+                                    float* out_label_score, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(packed && out_scores && out_ids && parts > 0 && B > 0, "rf_topk_merge_packed: bad argument");
+  RF_REQUIRE(k >= 1 && k <= SC_MAXK, "rf_topk_merge_packed: k=%d out of range [1,%d]", k, SC_MAXK);
+  const int ld = 2 * k + 1;
+  topk_merge_kernel<<<(B + 127) / 128, 128, 0, stream>>>(packed, reinterpret_cast<const int32_t*>(packed) + k, packed + 2 * k,
+                                                        parts, B, k, out_scores, out_ids, out_label_score, ld, B * ld, k, 1);
+  return check_launch("rf_topk_merge_packed");
 }
 
 extern "C" int rf_topk_merge(const float* scores, const int32_t* ids, const float* label_scores, int parts, int B,
@@ -851,7 +925,7 @@ extern "C" int rf_topk_merge(const float* scores, const int32_t* ids, const floa
   RF_REQUIRE(scores && ids && out_scores && out_ids && parts > 0 && B > 0, "rf_topk_merge: bad argument");
   RF_REQUIRE(k >= 1 && k <= SC_MAXK, "rf_topk_merge: k=%d out of range [1,%d]", k, SC_MAXK);
   topk_merge_kernel<<<(B + 127) / 128, 128, 0, stream>>>(scores, ids, label_scores, parts, B, k, out_scores, out_ids,
-                                                        out_label_score);
+                                                        out_label_score, k, B * k, k, 1);
   return check_launch("rf_topk_merge");
 }
 

@@ -58,13 +58,18 @@ def all_gather_topk(scores, ids, label_score, group=None):
 def sharded_topk(model, pooled: torch.Tensor, k: int = 10, labels: Optional[torch.Tensor] = None,
                  id_base: int = 0, group=None):
     """Global top-k when `model.item_embedding` holds only this rank's shard (ids offset by
-    id_base).  One all-gather + local merge; identical on every rank."""
+    id_base).  Three launches + one collective: the fused scorer writes this rank's packed (B, 2k+1) result
+    (rf_cosine_topk_packed), ONE all-gather exchanges it, rf_topk_merge_packed reads the gathered buffer in place;
+    the result is identical on every rank and bit-identical to the unsharded run."""
     from . import ops
-    s, i, l = model.topk(pooled, k=k, labels=labels, id_base=id_base)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return s, i, l
-    gs, gi, gl = all_gather_topk(s, i, l, group)
-    return ops.topk_merge(gs, gi, gl)
+        return model.topk(pooled, k=k, labels=labels, id_base=id_base)
+    xn = ops.normalize_rows(pooled.contiguous())
+    packed = ops.cosine_topk_packed(xn, model.normalized_items(), model.config.temp, k=k, id_base=id_base, labels=labels)
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out.view(-1), packed.view(-1), group=group)
+    return ops.topk_merge_packed(out, k)
 
 
 def allreduce_gradients(model, group=None, average: bool = True) -> None:
@@ -92,9 +97,15 @@ class GradSync:
     current stream and runs it on its own stream, next to the remaining backward kernels.  `finish()`
     reduces what is left (embedding tables, biases, LayerNorm vectors), and makes the current stream wait
     for every collective.  Gradients are SUMMED; pass `grad_scale=1/world` to `FusedAdamW.step()`.
+
+    Wire format: on CUDA the gradients travel as bf16 (`wire_dtype`, default) — each range is cast into a flat bf16
+    buffer right before its all-reduce, which halves the bytes on NVLink and the time the NCCL kernels compete with
+    the backward GEMMs; the fused AdamW then reads the reduced bf16 gradients directly (`engine.params.grad_wire`).
+    The reference's own data-parallel path reduces fp16 gradients (DeepSpeed stage 2, ref: lightning_pretrain.py:143).
+    `wire_dtype=torch.float32` all-reduces the fp32 gradient buffer in place (CPU / gloo tests).
     """
 
-    def __init__(self, model, group=None, passes_per_step: int = 1):
+    def __init__(self, model, group=None, passes_per_step: int = 1, wire_dtype=None):
         enc = getattr(model, "longformer", model)
         inside = {id(p) for p in enc.parameters()}
         # trainable parameters outside the encoder's flat buffer (pretraining lm_head.*): reduced in finish()
@@ -105,6 +116,8 @@ class GradSync:
         self._seen = {}
         self._works = []
         self._covered = []
+        self.wire_dtype = wire_dtype
+        self._comm = None
         self.engine.grad_hook = self.on_layer
 
     def _active(self) -> bool:
@@ -120,6 +133,29 @@ class GradSync:
         g1 = P.offsets[p + "attention.self.value_global.weight"] + named[p + "attention.self.value_global.weight"].numel()
         return [(d0, d1), (g0, g1)]
 
+    def _wire(self, g: torch.Tensor):
+        """The buffer that travels: the fp32 gradient buffer itself, or its flat bf16 twin (allocated once)."""
+        dt = self.wire_dtype if self.wire_dtype is not None else (torch.bfloat16 if g.is_cuda else torch.float32)
+        if dt == torch.float32:
+            self.engine.params.grad_wire = None
+            return None
+        if self._comm is None or self._comm.numel() != g.numel() or self._comm.device != g.device:
+            self._comm = torch.empty(g.numel(), dtype=torch.bfloat16, device=g.device)
+        return self._comm
+
+    def _reduce_range(self, g: torch.Tensor, a: int, b: int):
+        comm = self._wire(g)
+        if comm is None:
+            return dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        from . import ops
+        ops.cast_bf16(g[a:b], comm[a:b])
+        return dist.all_reduce(comm[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def gradient(self) -> torch.Tensor:
+        """The reduced (summed) flat gradient as fp32, whatever the wire format (checks / tests)."""
+        P = self.engine.params
+        return P.grad_wire.float() if getattr(P, "grad_wire", None) is not None else P.grad
+
     def on_layer(self, layer: int) -> None:
         if not self._active():
             return
@@ -128,7 +164,7 @@ class GradSync:
             return
         g = self.engine.params.grad
         for a, b in self.layer_ranges(layer):
-            self._works.append(dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._works.append(self._reduce_range(g, a, b))
             self._covered.append((a, b))
 
     def finish(self, defer_tail: bool = False):
@@ -138,6 +174,7 @@ class GradSync:
         if not self._active():
             self._covered.clear()
             self._seen.clear()
+            self.engine.params.grad_wire = None
             return None
         P = self.engine.params
         g = P.grad
@@ -154,7 +191,7 @@ class GradSync:
                 self._works.append(dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         tail = None
         for k, (a, b) in enumerate(gaps):
-            w = dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            w = self._reduce_range(g, a, b)
             if defer_tail and k == len(gaps) - 1 and P.n_dense <= a and b <= P.n_decay:
                 tail = w
             else:
@@ -164,4 +201,5 @@ class GradSync:
         self._works.clear()
         self._covered.clear()
         self._seen.clear()
+        P.grad_wire = self._comm if self._wire(g) is not None else None     # what FusedAdamW.step() reads
         return (lambda: tail.wait()) if tail is not None else None

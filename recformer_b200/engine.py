@@ -47,6 +47,7 @@ class FlatParams:
         self.model = model
         self.flat: Optional[torch.Tensor] = None
         self.grad: Optional[torch.Tensor] = None
+        self.grad_wire: Optional[torch.Tensor] = None   # bf16 twin holding the all-reduced gradients (dist.GradSync)
         self.shadow: Optional[torch.Tensor] = None
         self._optimizer_fresh = False
         self.offsets: Dict[str, int] = {}

@@ -282,6 +282,38 @@ def cosine_topk(xn, yn, temp, k=10, id_base=0, labels=None, ws=None, out=None):
     return scores, ids, label_score
 
 
+def cosine_topk_packed(xn, yn, temp, k=10, id_base=0, labels=None, ws=None, out=None):
+    """cosine_topk written as one packed fp32 [B, 2k+1] buffer (k scores | k ids as int32 bits | label score): the
+    unit each rank contributes to the all-gather of sharded scoring."""
+    _req(xn, torch.bfloat16, "xn"), _req(yn, torch.bfloat16, "yn")
+    B, N = xn.shape[0], yn.shape[0]
+    nbytes = int(_lib.lib().rf_cosine_topk_ws_bytes(B, N, k))
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=xn.device)
+    if out is None:
+        out = torch.empty(B, 2 * k + 1, dtype=torch.float32, device=xn.device)
+    if labels is not None:
+        _req(labels, torch.int64, "labels")
+    check(_lib.lib().rf_cosine_topk_packed(xn.data_ptr(), yn.data_ptr(), B, N, xn.shape[1], temp, k, id_base, _ptr(labels),
+                                           out.data_ptr(), ws.data_ptr(), _stream()), "rf_cosine_topk_packed")
+    return out
+
+
+def topk_merge_packed(packed, k):
+    """packed: [parts, B, 2k+1] (all-gathered cosine_topk_packed buffers) -> (scores [B,k], ids [B,k], label [B])."""
+    _req(packed, torch.float32, "packed")
+    parts, B, ld = packed.shape
+    if ld != 2 * k + 1:
+        raise ValueError("topk_merge_packed: last dimension must be 2k+1")
+    dev = packed.device
+    out_s = torch.empty(B, k, dtype=torch.float32, device=dev)
+    out_i = torch.empty(B, k, dtype=torch.int32, device=dev)
+    out_l = torch.empty(B, dtype=torch.float32, device=dev)
+    check(_lib.lib().rf_topk_merge_packed(packed.data_ptr(), parts, B, k, out_s.data_ptr(), out_i.data_ptr(),
+                                          out_l.data_ptr(), _stream()), "rf_topk_merge_packed")
+    return out_s, out_i, out_l
+
+
 def topk_merge(scores, ids, label_scores=None):
     """scores/ids: [parts, B, k]; label_scores: [parts, B] or None."""
     parts, B, k = scores.shape
@@ -367,6 +399,15 @@ def adamw_step_dev(param, grad, exp_avg, exp_avg_sq, shadow, beta1, beta2, eps, 
     check(_lib.lib().rf_adamw_step_dev(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                        _ptr(shadow), param.numel(), beta1, beta2, eps, weight_decay, hp.data_ptr(),
                                        _stream()), "rf_adamw_step_dev")
+
+
+def adamw_step_bf16grad(param, grad_bf16, exp_avg, exp_avg_sq, shadow, lr, beta1, beta2, eps, weight_decay, step,
+                        grad_scale=1.0, hp=None):
+    """AdamW update from bf16 gradients (the wire format of dist.GradSync); hp as in adamw_step_dev or None."""
+    _req(grad_bf16, torch.bfloat16, "grad")
+    check(_lib.lib().rf_adamw_step_bf16grad(param.data_ptr(), grad_bf16.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                            _ptr(shadow), param.numel(), lr, beta1, beta2, eps, weight_decay, step,
+                                            grad_scale, _ptr(hp), _stream()), "rf_adamw_step_bf16grad")
 
 
 def set_dropout_nonce(nonce):

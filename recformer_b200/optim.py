@@ -114,10 +114,16 @@ class FusedAdamW:
         segs = list(self._segments)
         if wait_other is not None:      # embeddings (+ *_global weights) = the decay segment without a bf16 shadow: last
             segs.sort(key=lambda sgm: (sgm[2] and not sgm[3]))
+        wire = P.grad_wire          # bf16 all-reduced gradients of this step (dist.GradSync), else None
         for (a, b, decay, shadow) in segs:
             if wait_other is not None and decay and not shadow:
                 wait_other()
                 wait_other = None
+            if wire is not None:
+                ops.adamw_step_bf16grad(P.flat[a:b], wire[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b],
+                                        P.shadow[a:b] if shadow else None, self.lr, b1, b2, self.eps,
+                                        self.weight_decay if decay else 0.0, self.step_count, grad_scale, hp=hp)
+                continue
             if hp is not None:
                 ops.adamw_step_dev(P.flat[a:b], P.grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b],
                                    P.shadow[a:b] if shadow else None, b1, b2, self.eps,
@@ -128,4 +134,5 @@ class FusedAdamW:
                            self.weight_decay if decay else 0.0, self.step_count, grad_scale)
         if wait_other is not None:
             wait_other()
+        P.grad_wire = None            # consumed: a later step without a GradSync must not read stale gradients
         P.mark_shadow_fresh(by_optimizer=True)

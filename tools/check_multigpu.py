@@ -50,9 +50,15 @@ def check_sharded_topk(device, rank, world, users=512, items=200_000, k=10):
     s, i, l = ops.cosine_topk(xn, shard, 0.05, k=k, id_base=lo, labels=labels)
     gs, gi, gl = rdist.all_gather_topk(s, i, l)
     ms, mi, ml = ops.topk_merge(gs, gi, gl)
+    # the production path: packed per-rank result -> one all-gather -> merge of the gathered buffer in place
+    packed = ops.cosine_topk_packed(xn, shard, 0.05, k=k, id_base=lo, labels=labels)
+    gathered = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=device)
+    dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1))
+    ps, pi, pl = ops.topk_merge_packed(gathered, k)
+    same_packed = torch.equal(ps, ms) and torch.equal(pi, mi) and torch.equal(pl, ml)
     full = build_table(0, items, rows, E, device)
     ts, ti, tl = ops.cosine_topk(xn, full, 0.05, k=k, labels=labels)
-    ok = torch.tensor([int(torch.equal(ms, ts) and torch.equal(mi, ti) and torch.equal(ml, tl))], device=device)
+    ok = torch.tensor([int(same_packed and torch.equal(ms, ts) and torch.equal(mi, ti) and torch.equal(ml, tl))], device=device)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     return {"sharded_topk_equals_unsharded": bool(ok.item()), "users": users, "items": items, "ranks": world}
 
@@ -109,7 +115,7 @@ def check_dp_gradients(device, rank, world, per_rank=2, L=256):
     loss.backward()
     sync.finish()
     model.longformer._engine.grad_hook = None
-    got = P.grad / world
+    got = sync.gradient() / world       # bf16 on the wire by default: compared within bf16 rounding below
     err = ((got - ref).abs().max() / ref.abs().max()).item()
     nerr = abs(got.norm().item() - ref.norm().item()) / ref.norm().item()
     t = torch.tensor([err, nerr], device=device)

@@ -1,11 +1,21 @@
 #!/bin/bash
-# 8-GPU box: full bench at N=8 (train + sharded eval), NCCL channel sweep on the training leg, pretraining at N=8
-mkdir -p gpurun_out
-run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $2 "${@:3}"; }
-timeout 600 env python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29601 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/bench_n8.log 2> gpurun_out/bench_n8.err
-echo "== N=8 exit $?"; tail -1 gpurun_out/bench_n8.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('train', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'gemm', d['roofline']['achieved'], 'eval', d['secondary'].get('value'), d['secondary'].get('ms_per_pass'), d['secondary'].get('error'))"
-for ch in 4 8 16; do
-  NCCL_MAX_NCHANNELS=$ch timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 2961$ch bench.py --gpus 8 --steps 10 --warmup 3 --no-secondary --no-cpu-baseline > gpurun_out/bench_n8_ch$ch.log 2>/dev/null
-  echo "NCCL_MAX_NCHANNELS=$ch"; tail -1 gpurun_out/bench_n8_ch$ch.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('  train', d['value'], d['ms_per_step'], 'gemm', d['roofline']['achieved'])"
-done
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29640 tools/bench_pretrain.py 2>/dev/null | tail -1 | tee gpurun_out/r01_pretrain_n8.jsonl
+# 2-GPU validation: scoring tests + shard timing on one GPU, multi-GPU equality checks, bench at N=1 and N=2 on the same box
+cd /root/repo; mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_kernels_gpu.py -q -p no:cacheprovider --tb=short -k "topk or cast_and_adamw" > gpurun_out/t_score.log 2>&1; echo "== scoring tests exit $?: $(tail -1 gpurun_out/t_score.log)"; grep -E "^E  |FAILED|^ERROR" gpurun_out/t_score.log | head
+RF_PROF_ITEMS=125000 timeout 300 python tools/prof_kernels.py score_topk 2>&1 | sed 's/score_topk/score_topk_125k_shard/'
+timeout 300 python tools/prof_kernels.py score_topk 2>&1 | tail -1
+TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+timeout 600 $TR --nproc-per-node 2 --master-port 29541 tools/check_multigpu.py --full > gpurun_out/check_n2.log 2>&1; echo "== check_multigpu exit $?"; grep check_multigpu gpurun_out/check_n2.log | cut -c1-1500
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_n1.log 2> gpurun_out/bench_n1.err; echo "== bench n1 exit $?"
+timeout 900 $TR --nproc-per-node 2 --master-port 29542 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.log 2> gpurun_out/bench_n2.err; echo "== bench n2 exit $?"; tail -3 gpurun_out/bench_n2.err
+python - <<'PY'
+import json
+for f in ("bench_n1", "bench_n2"):
+    try:
+        d = json.loads([l for l in open(f"gpurun_out/{f}.log") if l.startswith("{")][-1])
+        s = d.get("secondary") or {}
+        print(f, "train", round(d["value"], 1), "ms", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"], 1), "| eval", round(s.get("value", 0)), "ms", s.get("ms_per_pass"), "e2e", round((s.get("e2e") or {}).get("value", 0)))
+        print("   checks", json.dumps(d.get("checks"))[:1200]); print("   c3", json.dumps((d.get("extras") or {}).get("pretrain_c3"))[:400])
+    except Exception as ex:
+        print(f, "unreadable", ex)
+PY
