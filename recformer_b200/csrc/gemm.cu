@@ -46,6 +46,7 @@ struct GemmParams {
   uint32_t drop_thresh;   // p * 65536, 0 = no dropout
   uint64_t drop_seed;
   int xk_rows;            // XK: rows of A per batch (one 64-row block of B2 per batch)
+  int* tile_counter;      // pair kernel: dynamic tile scheduler (zero between launches, see gemm_pair_kernel)
 };
 
 template <int BN>
@@ -408,9 +409,21 @@ constexpr int P_BN = 256;        // pair tile N
 constexpr int P_STAGES = 5;
 constexpr uint32_t P_A_BYTES = 128 * BK * 2, P_B_BYTES = 128 * BK * 2, P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
 constexpr uint32_t P_TILE_BYTES = P_STAGES * P_STAGE_BYTES;
-constexpr uint32_t P_BAR_BYTES = (2 * P_STAGES + 4) * 8 + 16;
+constexpr int P_SCHED = 4;       // depth of the tile-id ring of the dynamic scheduler
+constexpr uint32_t P_BAR_BYTES = (2 * P_STAGES + 4) * 8 + 16 + 2 * P_SCHED * 8 + P_SCHED * 4;
 constexpr uint32_t P_EPI_STAGE_BYTES = EPI_WARPS * 4096;
 constexpr uint32_t P_SMEM = P_TILE_BYTES + P_EPI_STAGE_BYTES + P_BAR_BYTES + 2 * P_BN * 4 + 1024;
+
+// Tile scheduling is DYNAMIC: the leader's producer thread draws the next tile index from a global counter
+// (atomicAdd) and publishes it through a 4-deep ring of tile ids in the shared memory of BOTH CTAs (a
+// st.shared::cluster + release/acquire mbarrier hand-over); every role reads its tiles from that ring.  With the
+// former static schedule (tile = pair, pair + npairs, ...) a pair whose SMs were still occupied when the grid was
+// launched — by a kernel of another stream: the side-stream global-attention row, NCCL's all-reduce kernels in
+// data-parallel training — started late and ran its whole share AFTER the others had finished, doubling the GEMM's
+// duration; now the resident pairs drain the tile list and a late pair finds it (nearly) empty.  The counter is one
+// of 256 zero-initialised device words picked round-robin by the host; the pair that draws the last sentinel
+// (value total_tiles + npairs - 1: every pair draws exactly one) resets it to zero for its next use.
+__device__ int g_gemm_tile_counters[256];
 
 // XK: one extra 64-deep k-block per output tile whose operands come from a second pair of tensors, the A
 // side [M, 64] K-major and the B side batched ([M / xk_rows] blocks of [64, N], N contiguous):
@@ -428,12 +441,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + P_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* sched_full = reinterpret_cast<uint64_t*>(tmem_slot + 4);
+  uint64_t* sched_empty = sched_full + P_SCHED;      // the LEADER's copy is the live one
+  volatile int* s_tile = reinterpret_cast<volatile int*>(sched_empty + P_SCHED);
   float* s_bias = reinterpret_cast<float*>(smem + P_TILE_BYTES + P_EPI_STAGE_BYTES + P_BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int npairs = gridDim.x >> 1;
 
   const int m_tiles = (p.M + 255) / 256;
   const int n_tiles = (p.N + P_BN - 1) / P_BN;
@@ -441,6 +457,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int k_per_split = (k_blocks_total + p.split_k - 1) / p.split_k;
   const int total_tiles = m_tiles * n_tiles * p.split_k;
 
+  // the scheduler thread draws its first tile before anything else: the atomic's round trip to L2 (~1 us) then
+  // overlaps the barrier / TMEM set-up and the cluster sync below instead of delaying the first TMA load
+  int first_draw = 0;
+  if (threadIdx.x == 0 && leader && p.tile_counter != nullptr) first_draw = atomicAdd(p.tile_counter, 1);
   if (threadIdx.x == 0) {
     for (int s = 0; s < P_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);     // leader's copy is the live one: expect_tx covers both CTAs' slabs
@@ -450,12 +470,29 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull_bar[s], 1);                // multicast tcgen05.commit
       mbar_init(&tempty_bar[s], 2 * EPI_WARPS);   // leader's copy: epilogue warps of both CTAs
     }
+    for (int s = 0; s < P_SCHED; ++s) {
+      mbar_init(&sched_full[s], 1);                    // the scheduler's publish (one arrive per CTA)
+      mbar_init(&sched_empty[s], 2 * EPI_WARPS + 2);   // readers: 16 epilogue warps, the MMA warp, the peer's producer
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
     tmem_alloc_pair(tmem_slot, 512);
     tmem_relinquish_pair();
   }
+  // ring readers: wait for slot `rs`, read the tile id, report the read to the leader's sched_empty barrier
+  int rs = 0;
+  uint32_t rph = 0;
+  auto read_tile = [&]() -> int {     // executed by whole warps (or by the peer's single producer thread)
+    mbar_wait_cluster(&sched_full[rs], rph);
+    return s_tile[rs];
+  };
+  auto release_tile = [&]() {         // one thread per reader, after the tile id has been consumed
+    mbar_arrive_cluster(mapa_u32(smem_u32(&sched_empty[rs]), 0));
+  };
+  auto advance_ring = [&]() {
+    if (++rs == P_SCHED) { rs = 0; rph ^= 1; }
+  };
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -468,7 +505,36 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tma_prefetch_desc(&tmB);
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < total_tiles; tile += npairs) {
+      // leader: draw the next tile and publish it to both CTAs; peer: read it from the ring
+      int static_next = static_cast<int>(blockIdx.x >> 1);
+      bool have_first = true;
+      auto next_tile = [&]() -> int {
+        if (!leader) {
+          const int t = read_tile();
+          if (t >= 0) release_tile();      // (always true: orders the read before the arrive)
+          advance_ring();
+          return t;
+        }
+        mbar_wait(&sched_empty[rs], rph ^ 1);
+        int t;
+        if (p.tile_counter != nullptr) {
+          t = have_first ? first_draw : atomicAdd(p.tile_counter, 1);
+          have_first = false;
+          if (t == total_tiles + npairs - 1) atomicExch(p.tile_counter, 0);   // last sentinel of this launch
+        } else {                        // RF_GEMM_STATIC_SCHEDULE=1 (A/B aid): the former static round-robin
+          t = static_next;
+          static_next += npairs;
+        }
+        s_tile[rs] = t;
+        st_shared_cluster_u32(mapa_u32(smem_u32(const_cast<int*>(&s_tile[rs])), 1), static_cast<uint32_t>(t));
+        mbar_arrive(&sched_full[rs]);
+        mbar_arrive_cluster_release(mapa_u32(smem_u32(&sched_full[rs]), 1));
+        advance_ring();
+        return t;
+      };
+      int tile = next_tile();
+      while (tile < total_tiles) {
+        const int tile_next = next_tile();      // drawn one tile ahead: its latency hides under this tile's loads
         const int nt = tile % n_tiles;
         const int rest = tile / n_tiles;
         const int mt = rest % m_tiles;
@@ -509,6 +575,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int c = 0; c < 2; ++c) tma_load_2d_pair(sb + c * 8192, &tmB2, fb, n0 + c * 64, xb * 64);
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
         }
+        tile = tile_next;
       }
     }
   } else if (warp == 1) {
@@ -528,7 +595,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = pair; tile < total_tiles; tile += npairs) {
+      for (;;) {
+        const int tile = read_tile();
+        __syncwarp();
+        if (lane == 0 && tile >= 0) release_tile();
+        advance_ring();
+        if (tile >= total_tiles) break;
         const int sp = (tile / n_tiles) / m_tiles;
         const int kb0 = sp * k_per_split;
         const int kb1 = min(kb0 + k_per_split, k_blocks_total);
@@ -562,7 +634,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int CH = P_BN / 2 / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = pair; tile < total_tiles; tile += npairs) {
+    for (;;) {
+      const int tile = read_tile();
+      __syncwarp();
+      if (lane == 0 && tile >= 0) release_tile();
+      advance_ring();
+      if (tile >= total_tiles) break;
       const int nt = tile % n_tiles;
       const int mt = (tile / n_tiles) % m_tiles;
       const int m0 = mt * 256 + static_cast<int>(rank) * 128, n0 = nt * P_BN;
@@ -603,6 +680,25 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// One of the 256 scheduler counters of the current device, round-robin: launches that could be in flight at the
+// same time (different streams) get different words; each launch leaves its word at zero.
+static int* next_tile_counter() {
+  static int* base[64] = {nullptr};
+  static std::atomic<unsigned> seq{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (base[dev] == nullptr) {
+    void* ptr = nullptr;
+    if (cudaGetSymbolAddress(&ptr, g_gemm_tile_counters) != cudaSuccess) {
+      set_error(RF_ERR_CUDA, "rf_gemm_bf16: cudaGetSymbolAddress(g_gemm_tile_counters) failed");
+      return nullptr;
+    }
+    base[dev] = reinterpret_cast<int*>(ptr);
+  }
+  return base[dev] + (seq.fetch_add(1, std::memory_order_relaxed) & 255u);
+}
+
 template <bool A_MN, bool B_MN, int EPI, bool OUT_F32, int RES, bool DROP, bool SPLITK, bool XK = false>
 static int launch_gemm_pair(const rf_gemm_args* a, cudaStream_t stream) {
   auto kern = gemm_pair_kernel<A_MN, B_MN, EPI, OUT_F32, RES, DROP, SPLITK, XK>;
@@ -627,6 +723,9 @@ static int launch_gemm_pair(const rf_gemm_args* a, cudaStream_t stream) {
   const int m_tiles = (a->M + 255) / 256, n_tiles = (a->N + P_BN - 1) / P_BN;
   const int total = m_tiles * n_tiles * p.split_k;
   const int pairs = total < sm_count() / 2 ? total : sm_count() / 2;
+  static const bool static_sched = getenv("RF_GEMM_STATIC_SCHEDULE") != nullptr;
+  p.tile_counter = static_sched ? nullptr : next_tile_counter();
+  if (!static_sched && !p.tile_counter) return RF_ERR_CUDA;
   kern<<<2 * pairs, GEMM_THREADS, P_SMEM, stream>>>(*tmA, *tmB, *tmA2, *tmB2, p);
   return check_launch("rf_gemm_bf16(pair)");
 }

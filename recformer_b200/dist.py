@@ -105,7 +105,7 @@ class GradSync:
     `wire_dtype=torch.float32` all-reduces the fp32 gradient buffer in place (CPU / gloo tests).
     """
 
-    def __init__(self, model, group=None, passes_per_step: int = 1, wire_dtype=None):
+    def __init__(self, model, group=None, passes_per_step: int = 1, wire_dtype=None, bucket_layers: int = 4):
         enc = getattr(model, "longformer", model)
         inside = {id(p) for p in enc.parameters()}
         # trainable parameters outside the encoder's flat buffer (pretraining lm_head.*): reduced in finish()
@@ -117,20 +117,29 @@ class GradSync:
         self._works = []
         self._covered = []
         self.wire_dtype = wire_dtype
+        # Layers are reduced in buckets of `bucket_layers` (their dense / *_global ranges are contiguous in the flat
+        # buffer): measured on 2 B200s, the 298 MB bf16 payload takes 0.61 ms as one NCCL all-reduce but 1.50 ms as 26
+        # per-layer calls (launch latency + small-message efficiency), and that time is spent on SMs the backward
+        # GEMMs want.  Four layers per bucket = 3 buckets + the embedding / vector tail.
+        self.bucket_layers = max(1, int(bucket_layers))
         self._comm = None
+        # RF_DP_SYNC_AT_END=1 (A/B aid): no per-layer overlap, one cast + one all-reduce of the whole buffer in finish()
+        import os
+        self.at_end = os.environ.get("RF_DP_SYNC_AT_END") is not None
         self.engine.grad_hook = self.on_layer
 
     def _active(self) -> bool:
         return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
 
-    def layer_ranges(self, layer: int):
+    def layer_ranges(self, layer: int, last_layer: Optional[int] = None):
+        """The two contiguous flat-buffer ranges (dense weights, *_global weights) of layers layer..last_layer."""
         P = self.engine.params
-        p = f"encoder.layer.{layer}."
+        p, q = f"encoder.layer.{layer}.", f"encoder.layer.{layer if last_layer is None else last_layer}."
         named = P._named
         d0 = P.offsets[p + "attention.self.query.weight"]
-        d1 = P.offsets[p + "output.dense.weight"] + named[p + "output.dense.weight"].numel()
+        d1 = P.offsets[q + "output.dense.weight"] + named[q + "output.dense.weight"].numel()
         g0 = P.offsets[p + "attention.self.query_global.weight"]
-        g1 = P.offsets[p + "attention.self.value_global.weight"] + named[p + "attention.self.value_global.weight"].numel()
+        g1 = P.offsets[q + "attention.self.value_global.weight"] + named[q + "attention.self.value_global.weight"].numel()
         return [(d0, d1), (g0, g1)]
 
     def _wire(self, g: torch.Tensor):
@@ -157,13 +166,16 @@ class GradSync:
         return P.grad_wire.float() if getattr(P, "grad_wire", None) is not None else P.grad
 
     def on_layer(self, layer: int) -> None:
-        if not self._active():
+        if not self._active() or self.at_end:
             return
         self._seen[layer] = self._seen.get(layer, 0) + 1
         if self._seen[layer] < self.passes_per_step:      # gradients of this layer are still being accumulated
             return
+        if layer % self.bucket_layers != 0:               # the backward visits layers top-down: a bucket is complete
+            return                                        # when its lowest layer is
+        n_layers = self.engine.cfg.num_hidden_layers
         g = self.engine.params.grad
-        for a, b in self.layer_ranges(layer):
+        for a, b in self.layer_ranges(layer, min(layer + self.bucket_layers, n_layers) - 1):
             self._works.append(self._reduce_range(g, a, b))
             self._covered.append((a, b))
 

@@ -124,7 +124,7 @@ def _grad_sync_job(rank, world):
     P = eng.params
     P.grad = torch.arange(P.n_total, dtype=torch.float32) % 7 + rank      # rank-dependent stand-in gradients
     expect = (torch.arange(P.n_total, dtype=torch.float32) % 7) * world + sum(range(world))
-    sync = rdist.GradSync(model)
+    sync = rdist.GradSync(model, bucket_layers=1)
     assert eng.grad_hook is not None
     for layer in reversed(range(3)):           # what engine.backward() does as each layer finishes
         eng.grad_hook(layer)
@@ -137,6 +137,31 @@ def _grad_sync_job(rank, world):
 
 def test_overlapped_grad_sync_covers_buffer_once_world2():
     assert _run(_grad_sync_job) == [(True, 0), (True, 0)]
+
+
+def _grad_sync_bucket_job(rank, world):
+    """Bucketed GradSync (2 layers per bucket on a 5-layer model: buckets {4}, {2,3}, {0,1}) still covers every
+    element exactly once, with 2 collectives per bucket."""
+    import recformer_b200 as rb
+    from recformer_b200 import dist as rdist
+    cfg = rb.RecformerConfig(attention_window=[64] * 5, vocab_size=120, num_hidden_layers=5, max_position_embeddings=80)
+    model = rb.RecformerForSeqRec(cfg)
+    eng = model.longformer._engine
+    P = eng.params
+    P.grad = torch.arange(P.n_total, dtype=torch.float32) % 5 + 2 * rank
+    expect = (torch.arange(P.n_total, dtype=torch.float32) % 5) * world + 2 * sum(range(world))
+    sync = rdist.GradSync(model, bucket_layers=2)
+    counts = []
+    for layer in reversed(range(5)):
+        eng.grad_hook(layer)
+        counts.append(len(sync._covered))
+    sync.finish()
+    return bool(torch.equal(P.grad, expect)), counts
+
+
+def test_bucketed_grad_sync_world2():
+    out = _run(_grad_sync_bucket_job)
+    assert out[0] == (True, [2, 2, 4, 4, 6]) and out[1] == out[0]
 
 
 def _contrastive_job(rank, world):

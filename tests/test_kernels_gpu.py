@@ -514,7 +514,7 @@ def test_band_attention_bwd(B, L, ragged, w):
         assert err < 2e-2, (name, err)
 
 
-@pytest.mark.parametrize("B,L", [(3, 320), (18, 192), (3, 512)])
+@pytest.mark.parametrize("B,L", [(3, 320), (18, 192), (3, 512), (3, 128), (6, 128), (6, 256), (4, 64)])
 def test_global_attention_bwd(B, L):
     H = 12
     E = H * 64

@@ -63,11 +63,11 @@ def check_sharded_topk(device, rank, world, users=512, items=200_000, k=10):
     return {"sharded_topk_equals_unsharded": bool(ok.item()), "users": users, "items": items, "ranks": world}
 
 
-def _small_model(device, pretraining=False):
+def _small_model(device, pretraining=False, init_range=0.02):
     import recformer_b200 as rb
     cfg = rb.RecformerConfig(attention_window=[64, 64], vocab_size=1500, num_hidden_layers=2, max_position_embeddings=600,
                              max_item_embeddings=51, max_token_num=512, hidden_dropout_prob=0.0,
-                             attention_probs_dropout_prob=0.0, item_num=300)
+                             attention_probs_dropout_prob=0.0, item_num=300, initializer_range=init_range)
     torch.manual_seed(1234)                      # identical initial weights on every rank
     model = (rb.RecformerForPretraining if pretraining else rb.RecformerForSeqRec)(cfg)
     with torch.no_grad():                        # HF init leaves biases 0 / LN affine (1, 0): randomise them too
@@ -125,7 +125,11 @@ def check_dp_gradients(device, rank, world, per_rank=2, L=256):
 
 
 def check_contrastive(device, rank, world, per_rank=3):
-    model, cfg = _small_model(device, pretraining=True)
+    # N(0, 0.12) weights: at the default 0.02 the CLS vectors of a random-init encoder are collinear (cos 0.993-0.9997,
+    # measured with the CPU oracle) and the contrastive gradient is a difference of nearly equal terms -- even the
+    # full-batch single-GPU gradient then sits 15-25 % (of a tensor's abs-max) from the fp32 oracle; at 0.12 the
+    # cosines are ~0.6 and the comparison below is well conditioned
+    model, cfg = _small_model(device, pretraining=True, init_range=0.12)
     a = _batch(cfg, per_rank * world, 256, seed=91, device=device)
     b = _batch(cfg, per_rank * world, 96, seed=92, device=device)
     kw = lambda sl: dict(**{k + "_a": v[sl] for k, v in a.items()}, **{k + "_b": v[sl] for k, v in b.items()})

@@ -1,7 +1,7 @@
 #!/bin/bash
 # 2-GPU validation: scoring tests + shard timing on one GPU, multi-GPU equality checks, bench at N=1 and N=2 on the same box
 cd /root/repo; mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_kernels_gpu.py -q -p no:cacheprovider --tb=short -k "topk or cast_and_adamw" > gpurun_out/t_score.log 2>&1; echo "== scoring tests exit $?: $(tail -1 gpurun_out/t_score.log)"; grep -E "^E  |FAILED|^ERROR" gpurun_out/t_score.log | head
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_model_gpu.py -q -p no:cacheprovider --tb=short -x > gpurun_out/t_score.log 2>&1; echo "== scoring tests exit $?: $(tail -1 gpurun_out/t_score.log)"; grep -E "^E  |FAILED|^ERROR" gpurun_out/t_score.log | head
 RF_PROF_ITEMS=125000 timeout 300 python tools/prof_kernels.py score_topk 2>&1 | sed 's/score_topk/score_topk_125k_shard/'
 timeout 300 python tools/prof_kernels.py score_topk 2>&1 | tail -1
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
