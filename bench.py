@@ -532,6 +532,10 @@ def run_ours(args):
                 extras["longseq_c5"] = bench_extras.longseq_bench(device, steps=3, sustained_tflops=sustained)
             except Exception as ex:
                 extras["longseq_c5"] = {"error": repr(ex)[:300]}
+            try:
+                extras["encode_all_items"] = bench_extras.encode_items_bench(device, sustained_tflops=sustained)
+            except Exception as ex:
+                extras["encode_all_items"] = {"error": repr(ex)[:300]}
         if world > 1:
             from tools import check_multigpu
             checks = check_multigpu.run_checks(device, rank, world, full=True)

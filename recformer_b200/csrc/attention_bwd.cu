@@ -90,20 +90,17 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, part = warp >> 2;
   const int tiles_per_seq = (p.L + 127) / 128;
-  const int tile = blockIdx.x % tiles_per_seq;
-  const int h = (blockIdx.x / tiles_per_seq) % p.H;
-  const int b = blockIdx.x / (tiles_per_seq * p.H);
-  const int i0 = tile * 128;
+  const int total_tiles = p.B * p.H * tiles_per_seq;
   const int E = p.H * AB_D;
-  const uint8_t* mrow = p.mask012 + static_cast<size_t>(b) * p.L;
-  const int key0 = i0 - W + p.shift;             // absolute key index of tile column 0
+  constexpr uint32_t TM_S = 0, TM_DP = 256;                       // phase 1
+  constexpr uint32_t TM_DQ = 0, TM_DV = 64, TM_DK = 192;          // phase 2 (dV: 2 x 64, dK: 2 x 64)
 
-  if (tid == 0) {
-    mbar_init(bar_load, 1);
-    mbar_init(bar_mma, 1);
-    mbar_init(bar_kv, 1);
-    fence_mbar_init();
-    // operand loads first: TMEM allocation and the key-flag set-up (global mask loads) run under their latency
+  // PERSISTENT: one CTA per SM walks the (b, h, tile) list.  The operand loads of the NEXT tile are issued as soon as
+  // the current tile's last MMAs have retired (every shared-memory operand is dead then), so they land while the dK / dV
+  // epilogue drains TMEM; barriers and the 512 TMEM columns are set up once per CTA.
+  auto issue_loads = [&](int t) {     // thread 0 only
+    const int tile = t % tiles_per_seq, h = (t / tiles_per_seq) % p.H, b = t / (tiles_per_seq * p.H);
+    const int i0 = tile * 128, key0 = i0 - W + p.shift;
     mbar_arrive_expect_tx(bar_load, 2 * AB_Q_BYTES + 2 * AB_KV_BYTES);
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -117,10 +114,30 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     }
     tma_load_3d(sK + NK * 128, &tmQKV16, bar_load, E + h * AB_D, 0, b);
     tma_load_3d(sV + NK * 128, &tmQKV16, bar_load, 2 * E + h * AB_D, 0, b);
+  };
+  if (tid == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    mbar_init(bar_kv, 1);
+    fence_mbar_init();
+    if (static_cast<int>(blockIdx.x) < total_tiles) issue_loads(blockIdx.x);
   }
-  // Per-row global loads issued right away, next to the TMA loads (they are first used after the S / dP MMAs; issued
-  // any later they arrive after the TMA data and the row waits for them): this thread's quarter (16 of 64 dims) of
-  // the saved context row, the row's log-sum-exp and its mask bytes.
+  __syncwarp();
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  uint32_t it = 0;      // tiles processed by this CTA: parity of the once-per-tile barriers
+#pragma unroll 1
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+  const int tile = t % tiles_per_seq;
+  const int h = (t / tiles_per_seq) % p.H;
+  const int b = t / (tiles_per_seq * p.H);
+  const int i0 = tile * 128;
+  const uint8_t* mrow = p.mask012 + static_cast<size_t>(b) * p.L;
+  const int key0 = i0 - W + p.shift;             // absolute key index of tile column 0
+  // Per-row global loads issued right away (they are first used after the S / dP MMAs): this thread's quarter
+  // (16 of 64 dims) of the saved context row, the row's log-sum-exp and its mask bytes.
   const int r = quad * 32 + lane;       // query row of the tile == TMEM lane
   const int i = i0 + r;
   const bool in_seq = i < p.L;
@@ -133,11 +150,6 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   }
   const float lse = in_seq ? p.lse[(static_cast<size_t>(b) * p.H + h) * p.L + i] : 0.f;
   const uint8_t m_row = mrow[in_seq ? i : 0], m_cls = mrow[0];
-  __syncwarp();
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
   // key-valid bits of the NK band columns (bit c: key is in range, not padding, not global); word 7 bit 0 = CLS column
   if (warp < NK / 32) {
     const int j = key0 + warp * 32 + lane;
@@ -151,11 +163,9 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  constexpr uint32_t TM_S = 0, TM_DP = 256;                       // phase 1
-  constexpr uint32_t TM_DQ = 0, TM_DV = 64, TM_DK = 192;          // phase 2 (dV: 2 x 64, dK: 2 x 64)
 
   if (tid == 0) {
-    mbar_wait(bar_load, 0);
+    mbar_wait(bar_load, it & 1);
     tc_fence_after();
     constexpr uint32_t idesc = umma_idesc_bf16(128, NT, false, false);
     const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK), ado = smem_u32(sDO), av = smem_u32(sV);
@@ -343,8 +353,25 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
       }
     }
   }
-  mbar_wait(bar_kv, 0);
+  mbar_wait(bar_kv, it & 1);
   tc_fence_after();
+  // every MMA of this tile has retired: Q / dO / K / V are dead -> start the next tile's loads under the epilogue below
+  if (t + static_cast<int>(gridDim.x) < total_tiles) {
+    const int tn = t + gridDim.x;
+    if (tid == 0) issue_loads(tn);
+    // ... and pull the next tile's per-row data (saved context quarter, log-sum-exp) into L2: those plain loads sit on
+    // the next iteration's critical path (their DRAM latency was the top stall of the one-shot kernel)
+    const int hn = (tn / tiles_per_seq) % p.H, bn = tn / (tiles_per_seq * p.H);
+    const int in_ = (tn % tiles_per_seq) * 128 + r;
+    if (in_ < p.L) {
+      const void* pc = p.ctx + (static_cast<size_t>(bn) * p.L + in_) * E + hn * AB_D + part * 16;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pc));
+      if (part == 0) {
+        const void* pl = p.lse + (static_cast<size_t>(bn) * p.H + hn) * p.L + in_;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pl));
+      }
+    }
+  }
   // every shared-memory operand is dead now: the P region becomes 16 per-warp 4 KB transpose slabs
   uint8_t* slab = sP + warp * 4096;
   // ---- dK / dV: TMEM lane = key column c = hh*128 + r of the tile.  Each 32-key x 32-dim chunk is
@@ -413,11 +440,10 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
+  __syncthreads();     // TMEM, the transpose slabs, kbits and s_delta are rewritten by the next tile
+  tc_fence_after();
+  }   // tile loop
+  if (warp == 0) tmem_dealloc(*tmem_slot, 512);
 }
 
 // dqkv[b, 0, E:3E] = bf16(dkv_cls[b])  for sequences whose position 0 is the global token (bf16 path)
@@ -510,7 +536,8 @@ extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const fl
     p.hi_cut = hi > a->w ? hi - a->w : 0;
     p.use_cls = k == 0;
     p.drop_seed = a->drop_seed;     // masks are keyed on absolute (row, key): the same seed for every segment
-    band_attn_bwd_kernel<<<a->B * a->H * tiles, AB_THREADS, AB_SMEM, stream>>>(*tm64, *tm16, *tmdo, p);
+    const int total = a->B * a->H * tiles;
+    band_attn_bwd_kernel<<<total < sm_count() ? total : sm_count(), AB_THREADS, AB_SMEM, stream>>>(*tm64, *tm16, *tmdo, p);
     int rc = check_launch("rf_band_attn_bwd");
     if (rc) return rc;
   }

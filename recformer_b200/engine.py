@@ -276,6 +276,7 @@ class EncoderEngine:
         self._free: Dict[tuple, List[SavedActivations]] = {}
         self._bwd: Dict[tuple, BackwardScratch] = {}
         self._attn_ws: Dict[tuple, Optional[torch.Tensor]] = {}     # wide-window scratch, never freed (graphs hold it)
+        self._dout_cls: Dict[tuple, torch.Tensor] = {}              # all-zero upstream-gradient buffers (CLS-only backward)
         self._err = None
         self._call = 0
         # The global (CLS) row only depends on the layer input (forward) / on dctx (backward) and is made
@@ -461,6 +462,20 @@ class EncoderEngine:
         return sv.x[nl] if sv.per_layer else sv.x[nl % 2]
 
     # -- backward ------------------------------------------------------------------------------
+    def backward_from_pooled(self, sv: SavedActivations, d_pooled: torch.Tensor) -> None:
+        """Backward when only the CLS rows carry gradient (RecformerPooler 'cls', ref: recformer/models.py:160-171):
+        d_pooled [B, E].  The [B*Lp, E] bf16 upstream gradient is a persistent all-zero buffer of the engine whose B CLS
+        rows are filled in and cleared again afterwards, instead of a fresh 25 MB memset + strided copy per step."""
+        key = (sv.B, sv.Lp, str(d_pooled.device))
+        buf = self._dout_cls.get(key)
+        if buf is None:
+            buf = self._dout_cls[key] = torch.zeros(sv.B * sv.Lp, self.cfg.hidden_size, dtype=torch.bfloat16,
+                                                    device=d_pooled.device)
+        rows = buf.view(sv.B, sv.Lp, -1)[:, 0]
+        rows.copy_(d_pooled)
+        self.backward(sv, buf)
+        rows.zero_()
+
     def backward(self, sv: SavedActivations, dout: torch.Tensor) -> None:
         """dout: bf16 [B*Lp, E] gradient w.r.t. the final hidden states.  Accumulates into .grad."""
         cfg, P = self.cfg, self.params

@@ -163,6 +163,28 @@ class _EncoderFunction(torch.autograd.Function):
         return None, None, None, None
 
 
+class _EncoderPooledFunction(torch.autograd.Function):
+    """The encoder when only the 'cls' pooler output is consumed (RecformerForSeqRec / the contrastive towers): returns
+    the [B, E] CLS rows, so neither the 50 MB fp32 copy of the hidden states nor a per-step zero-filled upstream
+    gradient is materialised."""
+
+    @staticmethod
+    def forward(ctx, hook, model, inputs):
+        eng = model._engine
+        sv = eng.forward(*inputs, training=model.training, save=True)
+        pooled = eng.hidden(sv).view(sv.B, sv.Lp, model.config.hidden_size)[:, 0].clone()
+        ctx.model, ctx.sv = model, sv
+        return pooled
+
+    @staticmethod
+    def backward(ctx, d_pooled):
+        eng = ctx.model._engine
+        eng.backward_from_pooled(ctx.sv, d_pooled)
+        eng.release(ctx.sv)
+        ctx.sv = None
+        return None, None, None
+
+
 class RecformerModel(nn.Module):
     """ref: recformer/models.py:174-356 — same constructor checks, forward kwargs and outputs."""
 
@@ -260,6 +282,32 @@ class RecformerModel(nn.Module):
         if not return_dict:
             return (hidden, pooled)
         return RecformerModelOutput(last_hidden_state=hidden, pooler_output=pooled)
+
+    def forward_pooled(self, input_ids, attention_mask=None, global_attention_mask=None, token_type_ids=None,
+                       position_ids=None, item_position_ids=None) -> torch.Tensor:
+        """`forward(...).pooler_output` for the 'cls' pooler without materialising `last_hidden_state` (same checks,
+        same values; what RecformerForSeqRec and the pretraining towers consume)."""
+        if self.pooler.pooler_type != "cls":
+            return self(input_ids, attention_mask=attention_mask, global_attention_mask=global_attention_mask,
+                        token_type_ids=token_type_ids, position_ids=position_ids, item_position_ids=item_position_ids,
+                        return_dict=True).pooler_output
+        if not input_ids.is_cuda:
+            raise RuntimeError("recformer_b200 runs on CUDA only (no CPU fallback): move inputs to the GPU")
+        if item_position_ids is None:
+            raise ValueError("item_position_ids is required (ref: recformer/models.py:132 indexes it unconditionally)")
+        to64 = lambda t: None if t is None else t.to(torch.int64).contiguous()
+        inputs = (to64(input_ids), to64(attention_mask), to64(global_attention_mask), to64(token_type_ids),
+                  to64(item_position_ids), to64(position_ids))
+        eng = self._engine
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            pooled = _EncoderPooledFunction.apply(self._grad_hook(input_ids.device), self, inputs)
+        else:
+            sv = eng.forward(*inputs, training=self.training, save=False)
+            pooled = eng.hidden(sv).view(sv.B, sv.Lp, self.config.hidden_size)[:, 0].clone()
+            eng.release(sv)
+        if self.strict_checks:
+            eng.check_errors()
+        return pooled
 
     # raw bf16 access for fused consumers (scoring) that do not need fp32 copies
     def encode_pooled_bf16(self, **batch) -> torch.Tensor:
@@ -383,13 +431,19 @@ class RecformerForSeqRec(nn.Module):
                 candidates: Optional[torch.Tensor] = None,
                 labels: Optional[torch.Tensor] = None):
         batch_size = input_ids.size(0)
-        outputs = self.longformer(input_ids, attention_mask=attention_mask,
-                                  global_attention_mask=global_attention_mask, head_mask=head_mask,
-                                  token_type_ids=token_type_ids, position_ids=position_ids,
-                                  item_position_ids=item_position_ids, inputs_embeds=inputs_embeds,
-                                  output_attentions=output_attentions, output_hidden_states=output_hidden_states,
-                                  return_dict=True)
-        pooler_output = outputs.pooler_output
+        if head_mask is None and inputs_embeds is None and not output_attentions and not output_hidden_states:
+            # only the CLS rows are consumed (ref :565-579 reads outputs.pooler_output)
+            pooler_output = self.longformer.forward_pooled(input_ids, attention_mask=attention_mask,
+                                                           global_attention_mask=global_attention_mask,
+                                                           token_type_ids=token_type_ids, position_ids=position_ids,
+                                                           item_position_ids=item_position_ids)
+        else:                       # unsupported kwargs raise inside RecformerModel.forward, as documented there
+            pooler_output = self.longformer(input_ids, attention_mask=attention_mask,
+                                            global_attention_mask=global_attention_mask, head_mask=head_mask,
+                                            token_type_ids=token_type_ids, position_ids=position_ids,
+                                            item_position_ids=item_position_ids, inputs_embeds=inputs_embeds,
+                                            output_attentions=output_attentions,
+                                            output_hidden_states=output_hidden_states, return_dict=True).pooler_output
         if labels is None:
             return self.similarity_score(pooler_output, candidates)
         if self.config.finetune_negative_sample_size <= 0:      # full softmax
@@ -555,8 +609,11 @@ class RecformerForPretraining(nn.Module):
                   attention_mask_b=attention_mask_b, global_attention_mask_b=global_attention_mask_b,
                   token_type_ids_b=token_type_ids_b, item_position_ids_b=item_position_ids_b)
         batch_size = input_ids_a.size(0)
-        z1 = self._encode(input_ids_a, "a", kw).pooler_output
-        z2 = self._encode(input_ids_b, "b", kw).pooler_output
+        pooled = lambda ids, tag: self.longformer.forward_pooled(
+            ids, attention_mask=kw.get(f"attention_mask_{tag}"), global_attention_mask=kw.get(f"global_attention_mask_{tag}"),
+            token_type_ids=kw.get(f"token_type_ids_{tag}"), item_position_ids=kw.get(f"item_position_ids_{tag}"))
+        z1 = pooled(input_ids_a, "a")
+        z2 = pooled(input_ids_b, "b")
         if dist.is_available() and dist.is_initialized() and self.training and dist.get_world_size() > 1:
             z1, z2 = gather_cls_with_local_grad(z1, z2)            # ref :475-490
         loss, cos_sim, correct_num = contrastive_head(z1, z2, self.config.temp)

@@ -251,6 +251,9 @@ def test_encode_all_items_matches_oracle():
     sel = [k for k, i in enumerate(ids) if 30 <= i < 70]
     assert shard.shape[0] == len(sel)
     assert (shard.cpu() - ref[sel]).abs().max() < 2e-2
+    # device-side batch assembly (DeviceItemStore / rf_assemble_batch) gives bit-identical rows to the host tokenizer path
+    fast = encode_all_items(model, tok, items, batch_size=16, item_store=True)
+    assert torch.equal(fast, table)
 
 
 def test_pretraining_step_matches_oracle_and_reference(goldens):

@@ -107,3 +107,44 @@ def longseq_bench(device, windows=(64, 128, 256, 512), steps=3, warmup=3, B=2, L
         del model, batch
         torch.cuda.empty_cache()
     return out
+
+
+def encode_items_bench(device, n_items=8192, batch_size=512, sustained_tflops=None):
+    """SURVEY.md §8f-1 — `encode_all_items` (ref: finetune.py:38-63; run once per stage-1 epoch, :304-307): one-item
+    sequences of 20..96 tokens (padded to the batch max, then to the 64-token window), 12 layers, CLS pooled, rows also
+    written as the L2-normalised bf16 shard.  Timed with the device-side batch assembly and with the reference's host
+    tokenizer loop."""
+    import time
+    import numpy as np
+    import recformer_b200 as rb
+    from recformer_b200.items import encode_all_items
+    from recformer_b200.tokenization import DeviceItemStore
+    cfg = rb.RecformerConfig(attention_window=[64] * NL, max_token_num=1024, max_item_embeddings=51, max_attr_num=3,
+                             max_attr_length=32)
+    model = rb.RecformerModel(cfg).to(device).eval()
+    model.strict_checks = False
+    tok = rb.RecformerTokenizer(cfg)
+    rng = np.random.default_rng(0)
+    items = {}
+    for i in range(n_items):
+        n = int(rng.integers(20, 97))
+        items[i] = [rng.integers(3, 50265, size=n).tolist(), rng.integers(1, 3, size=n).tolist()]
+    norm = torch.empty(n_items, E, dtype=torch.bfloat16, device=device)
+    store = DeviceItemStore(cfg, items, device=device)
+    out = {}
+    for name, kw in (("device_assembly", dict(item_store=store)), ("host_tokenizer", dict())):
+        encode_all_items(model, tok, items, batch_size=batch_size, normalized_out=norm, id_range=(0, 2 * batch_size), **kw)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        encode_all_items(model, tok, items, batch_size=batch_size, normalized_out=norm, **kw)
+        torch.cuda.synchronize()
+        out[name + "_items_per_s"] = n_items / (time.perf_counter() - t0)
+    tokens = n_items * 128                      # every batch pads to 97..128 tokens -> 128 after window padding
+    flops = (DENSE_FLOP_PER_TOKEN_LAYER + 4 * 66 * E) * NL * tokens
+    out.update(workload=f"encode_all_items: {n_items} one-item sequences (20-96 tokens), batch {batch_size}, 12 layers, forward only",
+               algorithmic_tflops=flops * out["device_assembly_items_per_s"] / n_items / 1e12)
+    if sustained_tflops:
+        out["tensor_roof_frac"] = out["algorithmic_tflops"] / sustained_tflops
+    del model, store
+    torch.cuda.empty_cache()
+    return out
