@@ -205,9 +205,12 @@ int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx_bf16, const float* l
  * never applied to all L tokens (SURVEY.md §7 hard part 3):
  *   q_g = (Wqg x_cls + bqg)/sqrt(D);  u_h = Wkg[h]^T q_g[h];  s_j = u_h . x_j  (b_kg cancels in
  *   the softmax);  p = softmax_{valid j}(s);  m_h = sum_j p_j x_j;  out[h] = Wvg[h] m_h + bvg[h].
- * Writes row 0 of every sequence in ctx.  Saved for backward: qg [B,E], u [B,H,E], p [B,H,L],
- * pt [B,L,16] = dropout(p) transposed (token-major, 12 heads + 4 pad; 16-byte aligned), mvec [B,H,E],
- * psum [B,H] = sum_j dropout(p)_j (all fp32). */
+ * Writes row 0 of every sequence in ctx.  One pass over x (scores + online softmax + p'-weighted sum per 128-token
+ * chunk, merged by a small kernel).  Saved for backward (all fp32): qg [B,E], u [B,H,E], p [B,H,L] = the RAW scores
+ * s_hj (-inf for padded keys; the backward recomputes the probabilities from them and the log-sum-exp), mvec [B,H,E],
+ * psum [2,B,H] = (sum_j dropout(p)_j, log-sum-exp of the row).  pt [B,L,16] (token-major dropout(p), 12 heads + 4 pad;
+ * 16-byte aligned) is NOT written here any more: the backward fills it.  ws: rf_global_attn_fwd_ws_bytes() scratch
+ * (chunk partials), 16-byte aligned. */
 typedef struct rf_global_args {
   const void* x;  /* bf16 [B*L,E] layer input */
   const uint8_t* mask012;
@@ -219,8 +222,9 @@ typedef struct rf_global_args {
   uint64_t drop_seed;
 } rf_global_args;
 
+long long rf_global_attn_fwd_ws_bytes(int B, int L, int H);
 int rf_global_attn_fwd(const rf_global_args* a, void* ctx_bf16, float* qg, float* u, float* p, float* pt, float* mvec,
-                       float* psum, rf_stream_t stream);
+                       float* psum, float* ws, rf_stream_t stream);
 /* Backward of the CLS row: reads dctx row 0; accumulates (+=) fp32 dWqg,dbqg,dWkg,dWvg,dbvg (any
  * may be NULL; dbkg is identically zero) and ADDS the dense gradient the row sends to every
  * token (through s_j and m_h) into dx (bf16 [B*L,E]).  ws: rf_global_attn_bwd_ws_bytes().

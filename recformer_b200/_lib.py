@@ -65,8 +65,9 @@ _SIGS = {
     "rf_band_attn_ws_bytes": (c_ll, [c_int, c_int, c_int, c_int]),
     "rf_band_attn_fwd": (c_int, [P(AttnArgs), c_void_p, c_void_p, c_void_p]),
     "rf_band_attn_bwd": (c_int, [P(AttnArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rf_global_attn_fwd_ws_bytes": (c_ll, [c_int, c_int, c_int]),
     "rf_global_attn_fwd": (c_int, [P(GlobalArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                   c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_void_p]),
     "rf_global_attn_bwd_ws_bytes": (c_ll, [c_int, c_int, c_int]),
     "rf_global_attn_bwd": (c_int, [P(GlobalArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

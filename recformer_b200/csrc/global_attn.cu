@@ -571,6 +571,295 @@ global_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restri
   for (int d = 0; d < GD; ++d) dW[static_cast<size_t>(h * GD + d) * GE + e] += acc[d];
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused token passes (round 2).  The forward used to stream x twice (scores, then the p'-weighted sum) with a
+// softmax kernel in between, the backward three times (dp, softmax backward, du), all on CUDA cores
+// (2 x 12 x 768 MACs per token: ~27 M warp instructions per pass, issue-bound at ~55 us).  Both are now ONE pass
+// each, with the two contractions on the tensor cores (legacy mma.sync m16n8k16: the N dimension is the 12 heads,
+// far too narrow for a tcgen05 tile):
+//   CTA = (sequence, 64-token chunk).  The x tile [64 x 768] bf16 is staged once in shared memory (cp.async).
+//   phase A  S[64 x 16] = X . V^T, V = the 12 per-sequence vectors (u forward, dm backward; fp32, fed as a
+//            bf16 hi + lo pair so the scores keep fp32-grade vectors); 8 warps = 4 token tiles x 2 K halves.
+//   softmax  forward: chunk-local max / sums per head, weights e * keep -> P' [16 x 64] bf16; raw scores saved.
+//            backward: p recomputed from the saved score and lse; delta_h = dm_h . m_h + dpsum_h psum_h (closed form:
+//            no reduction over tokens); ds = p (keep scale (dm.x + dpsum) - delta) -> DS [16 x 64] bf16, pt / dst rows.
+//   phase B  [16 x 768] = P' . X (or DS . X): each warp owns 96 columns; B fragments by ldmatrix.trans from the tile.
+//   The chunk partials (max, sum, dropped sum, vector) are merged by a tiny kernel (forward: rescaled by the chunk
+//   maxima -> m_h, psum_h, lse_h; backward: plain sum -> du_h).
+// ---------------------------------------------------------------------------------------------
+constexpr int GP_THREADS = 256;
+constexpr int GP_TOK = 64;                       // tokens per CTA
+constexpr int GP_XLD = GE + 8;                   // padded row (1552 B = 97 x 16 B: conflict-free ldmatrix)
+constexpr int GP_PLD = GP_TOK + 8;               // padded P' / DS row (144 B)
+constexpr uint32_t GP_OFF_S = GP_TOK * GP_XLD * 2;                    // partial scores [2][64][16] fp32
+constexpr uint32_t GP_OFF_P = GP_OFF_S + 2 * GP_TOK * 16 * 4;         // P' / DS tile [16][72] bf16
+constexpr uint32_t GP_SMEM = GP_OFF_P + 16 * GP_PLD * 2;
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// fp32 pair -> bf16x2 "hi" and the bf16x2 rounding remainder "lo"
+__device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16(x, y);
+  const float2 h = unpack_bf16(hi);
+  lo = pack_bf16(x - h.x, y - h.y);
+}
+
+struct PassParams {
+  const __nv_bfloat16* x;     // [B*L, E]
+  const uint8_t* mask;
+  const float* vecs;          // fwd: u [B,H,E];  bwd: dm [B,H,E]
+  float* s;                   // [B,H,L] raw scores (fwd: written, -inf for padded keys;  bwd: read)
+  float* cmax; float* csum; float* csumd; float* cm;     // chunk partials, per (b, chunk, h)
+  // backward
+  const float* dpsum; const float* psum; const float* lse; const float* mvec;
+  float* pt; float* dst;      // [B, L, 16] token-major coefficient rows (p' and ds)
+  int B, L, C;
+  float drop_scale; uint32_t drop_thresh; uint64_t drop_seed;
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(GP_THREADS) global_pass_kernel(const PassParams p) {
+  extern __shared__ __align__(16) uint8_t gp_smem[];
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(gp_smem);
+  float* sS = reinterpret_cast<float*>(gp_smem + GP_OFF_S);
+  __nv_bfloat16* sP = reinterpret_cast<__nv_bfloat16*>(gp_smem + GP_OFF_P);
+  const int b = blockIdx.y, c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = p.L, j0 = c * GP_TOK;
+  const int g = lane >> 2, t4 = lane & 3;
+
+  // ---- stage the x tile (rows past L are clamped: their columns of P' / DS are zero) ----
+  for (int i = tid; i < GP_TOK * (GE / 8); i += GP_THREADS) {
+    const int r = i / (GE / 8), ch = i % (GE / 8);
+    const int j = min(j0 + r, L - 1);
+    const __nv_bfloat16* src = p.x + (static_cast<size_t>(b) * L + j) * GE + ch * 8;
+    const uint32_t dst = smem_u32(xs + r * GP_XLD + ch * 8);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  // backward: delta_h of the heads this warp normalises (needs only saved vectors: overlaps the tile load)
+  const int hA = warp, hB = warp + 8;            // softmax stage: warp handles heads warp and warp + 8 (if < 12)
+  float deltaA = 0.f, deltaB = 0.f;
+  if (BWD) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int h = q ? hB : hA;
+      if (h < GH) {
+        const float* dmv = p.vecs + (static_cast<size_t>(b) * GH + h) * GE;
+        const float* mv = p.mvec + (static_cast<size_t>(b) * GH + h) * GE;
+        float d = 0.f;
+        for (int e = lane; e < GE; e += 32) d += __ldg(dmv + e) * __ldg(mv + e);
+        d = warp_sum(d) + p.dpsum[b * GH + h] * p.psum[b * GH + h];
+        if (q) deltaB = d; else deltaA = d;
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // ---- phase A: S[64 x 16] = X V^T; warp = (token tile mt, K half kh) ----
+  {
+    const int mt = warp & 3, kh = warp >> 2;
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const uint32_t a_base = smem_u32(xs + (mt * 16 + (lane & 15)) * GP_XLD + (lane >> 4) * 8);
+    // B fragment rows: n = g of n-tile 0 -> head g; n-tile 1 -> head 8 + g (heads 12..15 do not exist: zero)
+    const float* v0 = p.vecs + (static_cast<size_t>(b) * GH + g) * GE;
+    const float* v1 = p.vecs + (static_cast<size_t>(b) * GH + 8 + (g < 4 ? g : 0)) * GE;
+    const bool have1 = g < 4;
+#pragma unroll 4
+    for (int ks = 0; ks < 24; ++ks) {
+      const int k0 = kh * 384 + ks * 16;
+      uint32_t a[4];
+      ldmatrix_x4(a_base + k0 * 2, a);
+      const float2 f00 = __ldg(reinterpret_cast<const float2*>(v0 + k0 + 2 * t4));
+      const float2 f01 = __ldg(reinterpret_cast<const float2*>(v0 + k0 + 8 + 2 * t4));
+      float2 f10 = make_float2(0.f, 0.f), f11 = make_float2(0.f, 0.f);
+      if (have1) {
+        f10 = __ldg(reinterpret_cast<const float2*>(v1 + k0 + 2 * t4));
+        f11 = __ldg(reinterpret_cast<const float2*>(v1 + k0 + 8 + 2 * t4));
+      }
+      uint32_t h0, l0, h1, l1;
+      split_bf16x2(f00.x, f00.y, h0, l0); split_bf16x2(f01.x, f01.y, h1, l1);
+      mma_bf16_16816(acc[0], a, h0, h1);
+      mma_bf16_16816(acc[0], a, l0, l1);
+      split_bf16x2(f10.x, f10.y, h0, l0); split_bf16x2(f11.x, f11.y, h1, l1);
+      mma_bf16_16816(acc[1], a, h0, h1);
+      mma_bf16_16816(acc[1], a, l0, l1);
+    }
+    float* o = sS + kh * (GP_TOK * 16);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      *reinterpret_cast<float2*>(o + (mt * 16 + g) * 16 + nt * 8 + 2 * t4) = make_float2(acc[nt][0], acc[nt][1]);
+      *reinterpret_cast<float2*>(o + (mt * 16 + g + 8) * 16 + nt * 8 + 2 * t4) = make_float2(acc[nt][2], acc[nt][3]);
+    }
+  }
+  __syncthreads();
+
+  // ---- softmax stage: warp handles heads hA (and hB if < 12); lane handles tokens lane and lane + 32 ----
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int h = q ? hB : hA;
+    if (h >= 16) continue;
+    if (h >= GH) {                 // padding rows 12..15 of the P' / DS operand
+      sP[h * GP_PLD + lane] = __float2bfloat16(0.f);
+      sP[h * GP_PLD + lane + 32] = __float2bfloat16(0.f);
+      continue;
+    }
+    const uint64_t row = (static_cast<uint64_t>(b) * GH + h) * L;
+    float sc[2], kf[2];
+    bool valid[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int tok = lane + 32 * u, j = j0 + tok;
+      valid[u] = j < L && p.mask[static_cast<size_t>(b) * L + (j < L ? j : 0)] != 0;
+      sc[u] = sS[tok * 16 + h] + sS[GP_TOK * 16 + tok * 16 + h];
+      kf[u] = drop_factor(p.drop_seed, p.drop_thresh, p.drop_scale, row + (j < L ? j : 0));
+    }
+    if (!BWD) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        sc[u] = valid[u] ? sc[u] : -INFINITY;
+        if (j0 + lane + 32 * u < L) p.s[row + j0 + lane + 32 * u] = sc[u];
+        m = fmaxf(m, sc[u]);
+      }
+      m = warp_max(m);
+      float l = 0.f, ld = 0.f;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float e = valid[u] ? __expf(sc[u] - m) : 0.f;
+        const float wd = e * kf[u];
+        l += e; ld += wd;
+        sP[h * GP_PLD + lane + 32 * u] = __float2bfloat16(wd);
+      }
+      l = warp_sum(l); ld = warp_sum(ld);
+      if (lane == 0) {
+        const size_t pi = (static_cast<size_t>(b) * p.C + c) * GH + h;
+        p.cmax[pi] = m; p.csum[pi] = l; p.csumd[pi] = ld;
+      }
+    } else {
+      const float dps = p.dpsum[b * GH + h], lse = p.lse[b * GH + h];
+      const float delta = q ? deltaB : deltaA;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = j0 + lane + 32 * u;
+        float pd = 0.f, ds = 0.f;
+        if (valid[u]) {
+          const float pr = __expf(p.s[row + j] - lse);
+          pd = pr * kf[u];
+          ds = pr * (kf[u] * (sc[u] + dps) - delta);
+        }
+        if (j < L) {
+          p.pt[(static_cast<size_t>(b) * L + j) * 16 + h] = pd;
+          p.dst[(static_cast<size_t>(b) * L + j) * 16 + h] = ds;
+        }
+        sP[h * GP_PLD + lane + 32 * u] = __float2bfloat16(ds);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B: [16 heads x 768] = P' X; warp owns columns [96 warp, 96 warp + 96) ----
+  {
+    float acc[12][4];
+#pragma unroll
+    for (int n = 0; n < 12; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+    const uint32_t a_base = smem_u32(sP + (lane & 15) * GP_PLD + (lane >> 4) * 8);
+    // ldmatrix.x4.trans over [16 tokens x 16 columns]: lanes 0-15 address token rows of the first 8 columns,
+    // lanes 16-31 the same rows of the next 8 -> {b0, b1} of n-tile 2i and {b0, b1} of n-tile 2i + 1
+    const uint32_t b_base = smem_u32(xs + (lane & 15) * GP_XLD + warp * 96 + (lane >> 4) * 8);
+#pragma unroll
+    for (int ks = 0; ks < GP_TOK / 16; ++ks) {
+      uint32_t a[4];
+      ldmatrix_x4(a_base + ks * 32, a);
+#pragma unroll
+      for (int np = 0; np < 6; ++np) {
+        uint32_t bb[4];
+        ldmatrix_x4_trans(b_base + (ks * 16 * GP_XLD + np * 16) * 2, bb);
+        mma_bf16_16816(acc[2 * np], a, bb[0], bb[1]);
+        mma_bf16_16816(acc[2 * np + 1], a, bb[2], bb[3]);
+      }
+    }
+    const size_t pbase = (static_cast<size_t>(b) * p.C + c) * GH;
+#pragma unroll
+    for (int n = 0; n < 12; ++n) {
+      const int col = warp * 96 + n * 8 + 2 * t4;
+      *reinterpret_cast<float2*>(p.cm + (pbase + g) * GE + col) = make_float2(acc[n][0], acc[n][1]);
+      if (g < 4) *reinterpret_cast<float2*>(p.cm + (pbase + 8 + g) * GE + col) = make_float2(acc[n][2], acc[n][3]);
+    }
+  }
+}
+
+// backward chunk partials -> du[b,h,:] = sum over chunks.  grid (H, B), 256 threads (3 columns each)
+__global__ void __launch_bounds__(256)
+global_sum_partials_kernel(const float* __restrict__ cm, int C, float* __restrict__ out) {
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 4
+  for (int c = 0; c < C; ++c) {
+    const float* v = cm + ((static_cast<size_t>(b) * C + c) * GH + h) * GE;
+    a0 += v[tid]; a1 += v[256 + tid]; a2 += v[512 + tid];
+  }
+  float* o = out + (static_cast<size_t>(b) * GH + h) * GE;
+  o[tid] = a0; o[256 + tid] = a1; o[512 + tid] = a2;
+}
+
+// chunk partials -> m_h = sum_j p'_hj x_j, psum_h = sum_j p'_hj, lse_h.  grid (H, B), 256 threads (3 columns each)
+__global__ void __launch_bounds__(256)
+global_merge_kernel(const float* __restrict__ cmax, const float* __restrict__ csum, const float* __restrict__ csumd,
+                    const float* __restrict__ cm, int C, float* __restrict__ mvec, float* __restrict__ psum,
+                    float* __restrict__ lse) {
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const size_t base = (static_cast<size_t>(b) * C) * GH + h;
+  __shared__ float s_r[64], s_z[3];
+  if (tid < 32) {                      // chunk rescale factors first (C <= 64), so that the column loop below is
+    float m = -INFINITY;               // a stream of independent loads
+    for (int c = tid; c < C; c += 32) m = fmaxf(m, cmax[base + static_cast<size_t>(c) * GH]);
+    m = warp_max(m);
+    float z = 0.f, zd = 0.f;
+    for (int c = tid; c < C; c += 32) {
+      const size_t pi = base + static_cast<size_t>(c) * GH;
+      const float mc = cmax[pi];
+      const float r = (mc > -INFINITY) ? __expf(mc - m) : 0.f;
+      s_r[c] = r;
+      z += csum[pi] * r; zd += csumd[pi] * r;
+    }
+    z = warp_sum(z); zd = warp_sum(zd);
+    if (tid == 0) { s_z[0] = z; s_z[1] = zd; s_z[2] = m; }
+  }
+  __syncthreads();
+  const float Z = s_z[0], Zd = s_z[1], M = s_z[2];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 4
+  for (int c = 0; c < C; ++c) {
+    const float* v = cm + (base + static_cast<size_t>(c) * GH) * GE;
+    const float r = s_r[c];
+    a0 += v[tid] * r; a1 += v[256 + tid] * r; a2 += v[512 + tid] * r;
+  }
+  const float inv = Z > 0.f ? 1.f / Z : 0.f;
+  float* o = mvec + (static_cast<size_t>(b) * GH + h) * GE;
+  o[tid] = a0 * inv; o[256 + tid] = a1 * inv; o[512 + tid] = a2 * inv;
+  if (tid == 0) {
+    psum[b * GH + h] = Zd * inv;
+    lse[b * GH + h] = Z > 0.f ? M + logf(Z) : 0.f;
+  }
+}
+
 }  // namespace rf
 
 using namespace rf;
@@ -593,12 +882,18 @@ static int launch_mix(const __nv_bfloat16* tile_src, MixParams& p, cudaStream_t 
   return check_launch(what);
 }
 
+extern "C" long long rf_global_attn_fwd_ws_bytes(int B, int L, int H) {
+  const long long C = (L + GP_TOK - 1) / GP_TOK;
+  return 4ll * B * C * H * (3 + static_cast<long long>(H) * GD) + 256;
+}
+
 extern "C" int rf_global_attn_fwd(const rf_global_args* a, void* ctx, float* qg, float* u, float* p, float* pt,
-                                  float* mvec, float* psum, rf_stream_t stream_) {
+                                  float* mvec, float* psum, float* ws, rf_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  RF_REQUIRE(a && ctx && qg && u && p && pt && mvec && psum, "rf_global_attn_fwd: null argument");
+  RF_REQUIRE(a && ctx && qg && u && p && pt && mvec && psum && ws, "rf_global_attn_fwd: null argument");
+  RF_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "rf_global_attn_fwd: ws must be 16-byte aligned");
   RF_REQUIRE(a->H == GH && a->D == GD, "rf_global_attn_fwd: only H=12, D=64 supported (got %d, %d)", a->H, a->D);
-  RF_REQUIRE(a->B > 0 && a->L > 0, "rf_global_attn_fwd: bad shape");
+  RF_REQUIRE(a->B > 0 && a->L > 0 && a->L <= 64 * GP_TOK, "rf_global_attn_fwd: bad shape (L <= %d)", 64 * GP_TOK);
   RF_REQUIRE((reinterpret_cast<uintptr_t>(pt) & 15) == 0, "rf_global_attn_fwd: pt must be 16-byte aligned");
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a->x);
   const int B = a->B, L = a->L;
@@ -606,7 +901,6 @@ extern "C" int rf_global_attn_fwd(const rf_global_args* a, void* ctx, float* qg,
   const uint32_t thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   const float scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
   int rc;
-  RF_CUDA(cudaMemsetAsync(mvec, 0, static_cast<size_t>(B) * GH * GE * sizeof(float), stream));
   {
     RowdotParams r{};
     r.W = a->Wqg; r.bias = a->bqg; r.x = x; r.mask = a->mask012; r.out_f32 = qg; r.B = B; r.L = L;
@@ -619,15 +913,24 @@ extern "C" int rf_global_attn_fwd(const rf_global_args* a, void* ctx, float* qg,
     global_colmix_kernel<<<dim3(GE / 64, GH, bblocks), 64, 0, stream>>>(c);
     if ((rc = check_launch("rf_global_attn_fwd/u"))) return rc;
   }
-  global_dots_kernel<0><<<dim3((L + 63) / 64, B), 256, 0, stream>>>(x, a->mask012, u, nullptr, L, scale, thresh,
-                                                                   a->drop_seed, p);
-  if ((rc = check_launch("rf_global_attn_fwd/scores"))) return rc;
-  global_softmax_kernel<<<B * GH, 256, 0, stream>>>(p, L, scale, thresh, a->drop_seed, pt, psum);
-  if ((rc = check_launch("rf_global_attn_fwd/softmax"))) return rc;
   {
-    MixParams m{};
-    m.pt = pt; m.out = mvec; m.B = B; m.L = L;
-    if ((rc = launch_mix<MIX_ACC>(x, m, stream, "rf_global_attn_fwd/mix"))) return rc;
+    // one pass over x: scores (saved), online softmax, p'-weighted sum -> chunk partials in the workspace
+    const int C = (L + GP_TOK - 1) / GP_TOK;
+    float* w = ws;
+    PassParams q{};
+    q.x = x; q.mask = a->mask012; q.vecs = u; q.s = p; q.B = B; q.L = L; q.C = C;
+    q.cmax = w; q.csum = q.cmax + static_cast<size_t>(B) * C * GH; q.csumd = q.csum + static_cast<size_t>(B) * C * GH;
+    q.cm = q.csumd + static_cast<size_t>(B) * C * GH;
+    q.drop_scale = scale; q.drop_thresh = thresh; q.drop_seed = a->drop_seed;
+    static std::atomic<unsigned long long> attr_seen{0};   // one bit per device
+    if (first_use_on_device(&attr_seen)) {
+      RF_CUDA(cudaFuncSetAttribute(global_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GP_SMEM));
+    }
+    global_pass_kernel<false><<<dim3(C, B), GP_THREADS, GP_SMEM, stream>>>(q);
+    if ((rc = check_launch("rf_global_attn_fwd/pass"))) return rc;
+    global_merge_kernel<<<dim3(GH, B), 256, 0, stream>>>(q.cmax, q.csum, q.csumd, q.cm, C, mvec, psum,
+                                                        psum + static_cast<size_t>(B) * GH);
+    if ((rc = check_launch("rf_global_attn_fwd/merge"))) return rc;
   }
   {
     RowdotParams r{};
@@ -640,12 +943,13 @@ extern "C" int rf_global_attn_fwd(const rf_global_args* a, void* ctx, float* qg,
 
 extern "C" long long rf_global_attn_bwd_ws_bytes(int B, int L, int H) {
   const long long E = static_cast<long long>(H) * GD;
-  return 4ll * (2ll * B * H * E + B * H + static_cast<long long>(B) * H * L + 3ll * B * E + 16ll * B * L) + 256;
+  const long long C = (L + 63) / 64;       // chunk partials of the fused token pass (GP_TOK = 64)
+  return 4ll * (2ll * B * H * E + B * H + static_cast<long long>(B) * H * L + 3ll * B * E + 16ll * B * L + B * C * H * E) + 256;
 }
 
 namespace {
 struct BwdWs {
-  float *dm, *du, *dst, *dp, *dpsum, *doutf, *dqf, *dxcls;
+  float *dm, *du, *dst, *dp, *dpsum, *doutf, *dqf, *dxcls, *part;
   BwdWs(float* ws, int B, int L) {
     dm = ws;
     du = dm + static_cast<size_t>(B) * GH * GE;
@@ -655,6 +959,7 @@ struct BwdWs {
     doutf = dpsum + static_cast<size_t>(B) * GH;
     dqf = doutf + static_cast<size_t>(B) * GE;
     dxcls = dqf + static_cast<size_t>(B) * GE;
+    part = dxcls + static_cast<size_t>(B) * GE;           // [B, C, H, E] chunk partials of du
   }
 };
 
@@ -760,7 +1065,6 @@ extern "C" int rf_global_attn_bwd(const rf_global_args* a, const void* dctx, con
   const uint32_t thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   const float scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
   int rc;
-  RF_CUDA(cudaMemsetAsync(w.du, 0, static_cast<size_t>(B) * GH * GE * sizeof(float), stream));
   {
     // dm[b,h,:] = Wvg[h]^T dout_h; dpsum = bvg[h].dout_h; dbvg += dout_h psum; fp32 copy of dout
     ColmixParams c{};
@@ -769,16 +1073,23 @@ extern "C" int rf_global_attn_bwd(const rf_global_args* a, const void* dctx, con
     global_colmix_kernel<<<dim3(GE / 64, GH, bblocks), 64, 0, stream>>>(c);
     if ((rc = check_launch("rf_global_attn_bwd/dm"))) return rc;
   }
-  global_dots_kernel<1><<<dim3((L + 63) / 64, B), 256, 0, stream>>>(x, a->mask012, w.dm, w.dpsum, L, scale, thresh,
-                                                                   a->drop_seed, w.dp);
-  if ((rc = check_launch("rf_global_attn_bwd/dp"))) return rc;
-  global_bwd_ds_kernel<<<B * GH, 256, 0, stream>>>(p, w.dp, L, w.dst);
-  if ((rc = check_launch("rf_global_attn_bwd/ds"))) return rc;
   {
-    // du[b,h,:] = sum_j ds_hj x_j
-    MixParams m{};
-    m.pt = w.dst; m.out = w.du; m.B = B; m.L = L;
-    if ((rc = launch_mix<MIX_ACC>(x, m, stream, "rf_global_attn_bwd/du"))) return rc;
+    // one pass over x: p recomputed from the saved scores / lse, softmax backward with the closed-form delta,
+    // du += ds x, and the coefficient rows pt (= p') / dst (= ds) of the dx update
+    PassParams q{};
+    q.x = x; q.mask = a->mask012; q.vecs = w.dm; q.s = const_cast<float*>(p); q.B = B; q.L = L;
+    q.C = (L + GP_TOK - 1) / GP_TOK;
+    q.dpsum = w.dpsum; q.psum = psum; q.lse = psum + static_cast<size_t>(B) * GH; q.mvec = mvec;
+    q.pt = const_cast<float*>(pt); q.dst = w.dst; q.cm = w.part;
+    q.drop_scale = scale; q.drop_thresh = thresh; q.drop_seed = a->drop_seed;
+    static std::atomic<unsigned long long> attr_seen{0};   // one bit per device
+    if (first_use_on_device(&attr_seen)) {
+      RF_CUDA(cudaFuncSetAttribute(global_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GP_SMEM));
+    }
+    global_pass_kernel<true><<<dim3(q.C, B), GP_THREADS, GP_SMEM, stream>>>(q);
+    if ((rc = check_launch("rf_global_attn_bwd/pass"))) return rc;
+    global_sum_partials_kernel<<<dim3(GH, B), 256, 0, stream>>>(w.part, q.C, w.du);
+    if ((rc = check_launch("rf_global_attn_bwd/du"))) return rc;
   }
   {
     // dq = Wkg[h] du_h / 8 (fp32 copy kept), dbqg += dq

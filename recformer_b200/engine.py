@@ -228,10 +228,7 @@ class SavedActivations:
         self.g = [torch.empty(T, F, **bf) for _ in range(n)]
         self.pre2 = [torch.empty(T, E, **f32) for _ in range(n)]
         self.stats2 = [torch.empty(T, 2, **f32) for _ in range(n)]
-        self.glob = [{"qg": torch.empty(B, E, **f32), "u": torch.empty(B, H, E, **f32),
-                      "p": torch.empty(B, H, Lp, **f32), "pt": torch.empty(B, Lp, 16, **f32),
-                      "mvec": torch.empty(B, H, E, **f32),
-                      "psum": torch.empty(B, H, **f32)} for _ in range(n)]
+        self.glob = [ops.global_attn_saved(B, Lp, H, device) for _ in range(n)]
         self.pos_ids = None
         self.mask012 = None
         self.inputs = None

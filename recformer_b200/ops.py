@@ -207,21 +207,27 @@ def _global_args(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, drop_p, drop_seed
     return a
 
 
+def global_attn_saved(B, L, H, device):
+    """Buffers rf_global_attn_fwd saves for the backward (+ its chunk-partial scratch "ws")."""
+    E = H * 64
+    f32 = dict(dtype=torch.float32, device=device)
+    nws = int(_lib.lib().rf_global_attn_fwd_ws_bytes(B, L, H))
+    return {"qg": torch.empty(B, E, **f32), "u": torch.empty(B, H, E, **f32),
+            "p": torch.empty(B, H, L, **f32),            # raw scores s_hj (the backward recomputes p from them)
+            "pt": torch.empty(B, L, 16, **f32),          # token-major dropout(p): written by the backward
+            "mvec": torch.empty(B, H, E, **f32),
+            "psum": torch.empty(2, B, H, **f32),         # [0] = sum_j dropout(p), [1] = log-sum-exp
+            "ws": torch.empty((nws + 3) // 4, **f32)}
+
+
 def global_attn_fwd(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, ctx, saved=None, drop_p=0.0, drop_seed=0):
     """Writes row 0 of every sequence of ctx; returns the tensors saved for backward."""
-    E = H * 64
-    dev = x.device
     if saved is None:
-        saved = {"qg": torch.empty(B, E, dtype=torch.float32, device=dev),
-                 "u": torch.empty(B, H, E, dtype=torch.float32, device=dev),
-                 "p": torch.empty(B, H, L, dtype=torch.float32, device=dev),
-                 "pt": torch.empty(B, L, 16, dtype=torch.float32, device=dev),
-                 "mvec": torch.empty(B, H, E, dtype=torch.float32, device=dev),
-                 "psum": torch.empty(B, H, dtype=torch.float32, device=dev)}
+        saved = global_attn_saved(B, L, H, x.device)
     a = _global_args(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, drop_p, drop_seed)
     check(_lib.lib().rf_global_attn_fwd(C.byref(a), ctx.data_ptr(), saved["qg"].data_ptr(), saved["u"].data_ptr(),
                                         saved["p"].data_ptr(), saved["pt"].data_ptr(), saved["mvec"].data_ptr(),
-                                        saved["psum"].data_ptr(), _stream()), "rf_global_attn_fwd")
+                                        saved["psum"].data_ptr(), saved["ws"].data_ptr(), _stream()), "rf_global_attn_fwd")
     return saved
 
 

@@ -272,7 +272,10 @@ def test_global_attention_fwd(B, L):
     ref = (p @ vg).reshape(B, E)
     got = ctx.view(B, L, E)[:, 0].float()
     assert (got - ref).abs().max() < 1e-2
-    assert (saved["p"] - p[:, :, 0]).abs().max() < 1e-4
+    # saved for the backward: the raw scores and the row's log-sum-exp reproduce the probabilities
+    rec = torch.exp(saved["p"] - saved["psum"][1][:, :, None])
+    assert (rec - p[:, :, 0]).abs().max() < 1e-4
+    assert (saved["psum"][0] - 1.0).abs().max() < 1e-5          # no dropout: sum_j p'_j = 1
 
 
 # ------------------------------------------------------------------------------------- scoring
@@ -545,7 +548,7 @@ def test_global_attention_bwd(B, L):
     got_dx = dx.float() - dx0.float()
     assert (got_dx - ref_dx).abs().max() < 0.02 * ref_dx.abs().max() + 2e-4   # bf16 read-modify-write of dx
     for n in ("Wq", "bq", "Wk", "Wv", "bv"):
-        assert relerr(grads[n], P[n].grad) < 2e-3, n
+        assert relerr(grads[n], P[n].grad) < 5e-3, n      # ds is a bf16 tensor-core operand of the du contraction
     assert P["bk"].grad.abs().max() < 1e-5
     if L % 256 == 0:
         # the same token gradients packed as the extra k-block of the QKV dgrad GEMM (engine path for L % 256 == 0)

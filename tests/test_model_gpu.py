@@ -251,9 +251,11 @@ def test_encode_all_items_matches_oracle():
     sel = [k for k, i in enumerate(ids) if 30 <= i < 70]
     assert shard.shape[0] == len(sel)
     assert (shard.cpu() - ref[sel]).abs().max() < 2e-2
-    # device-side batch assembly (DeviceItemStore / rf_assemble_batch) gives bit-identical rows to the host tokenizer path
+    # device-side batch assembly (DeviceItemStore / rf_assemble_batch): the same batches (bit-identical layouts, see
+    # test_device_batch_assembly_is_bit_identical_to_tokenizer), so the same rows up to the run-to-run jitter of the
+    # global-row reductions
     fast = encode_all_items(model, tok, items, batch_size=16, item_store=True)
-    assert torch.equal(fast, table)
+    assert (fast - table).abs().max().item() < 1e-3
 
 
 def test_pretraining_step_matches_oracle_and_reference(goldens):
