@@ -679,25 +679,34 @@ __global__ void __launch_bounds__(GP_THREADS) global_pass_kernel(const PassParam
     const float* v0 = p.vecs + (static_cast<size_t>(b) * GH + g) * GE;
     const float* v1 = p.vecs + (static_cast<size_t>(b) * GH + 8 + (g < 4 ? g : 0)) * GE;
     const bool have1 = g < 4;
-#pragma unroll 4
-    for (int ks = 0; ks < 24; ++ks) {
+    // the vector fragments are plain global loads (L1 / L2 hits): fetched TWO k-steps ahead of their use
+    auto fetch = [&](int ks, float2 (&f)[4]) {
       const int k0 = kh * 384 + ks * 16;
-      uint32_t a[4];
-      ldmatrix_x4(a_base + k0 * 2, a);
-      const float2 f00 = __ldg(reinterpret_cast<const float2*>(v0 + k0 + 2 * t4));
-      const float2 f01 = __ldg(reinterpret_cast<const float2*>(v0 + k0 + 8 + 2 * t4));
-      float2 f10 = make_float2(0.f, 0.f), f11 = make_float2(0.f, 0.f);
-      if (have1) {
-        f10 = __ldg(reinterpret_cast<const float2*>(v1 + k0 + 2 * t4));
-        f11 = __ldg(reinterpret_cast<const float2*>(v1 + k0 + 8 + 2 * t4));
+      f[0] = __ldg(reinterpret_cast<const float2*>(v0 + k0 + 2 * t4));
+      f[1] = __ldg(reinterpret_cast<const float2*>(v0 + k0 + 8 + 2 * t4));
+      f[2] = have1 ? __ldg(reinterpret_cast<const float2*>(v1 + k0 + 2 * t4)) : make_float2(0.f, 0.f);
+      f[3] = have1 ? __ldg(reinterpret_cast<const float2*>(v1 + k0 + 8 + 2 * t4)) : make_float2(0.f, 0.f);
+    };
+    float2 fa[4], fb[4];
+    fetch(0, fa);
+    fetch(1, fb);
+#pragma unroll 1
+    for (int ks = 0; ks < 24; ks += 2) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float2 (&f)[4] = half ? fb : fa;
+        const int k0 = kh * 384 + (ks + half) * 16;
+        uint32_t a[4];
+        ldmatrix_x4(a_base + k0 * 2, a);
+        uint32_t h0, l0, h1, l1, h2, l2, h3, l3;
+        split_bf16x2(f[0].x, f[0].y, h0, l0); split_bf16x2(f[1].x, f[1].y, h1, l1);
+        split_bf16x2(f[2].x, f[2].y, h2, l2); split_bf16x2(f[3].x, f[3].y, h3, l3);
+        if (ks + half + 2 < 24) fetch(ks + half + 2, f);       // refill this buffer for two steps later
+        mma_bf16_16816(acc[0], a, h0, h1);
+        mma_bf16_16816(acc[0], a, l0, l1);
+        mma_bf16_16816(acc[1], a, h2, h3);
+        mma_bf16_16816(acc[1], a, l2, l3);
       }
-      uint32_t h0, l0, h1, l1;
-      split_bf16x2(f00.x, f00.y, h0, l0); split_bf16x2(f01.x, f01.y, h1, l1);
-      mma_bf16_16816(acc[0], a, h0, h1);
-      mma_bf16_16816(acc[0], a, l0, l1);
-      split_bf16x2(f10.x, f10.y, h0, l0); split_bf16x2(f11.x, f11.y, h1, l1);
-      mma_bf16_16816(acc[1], a, h0, h1);
-      mma_bf16_16816(acc[1], a, l0, l1);
     }
     float* o = sS + kh * (GP_TOK * 16);
 #pragma unroll
