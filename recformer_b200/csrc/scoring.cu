@@ -471,44 +471,66 @@ cosine_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 1) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
 }
 
-// Merge `parts` sorted lists of k (score, id) per user -> global top-k (score desc, id asc).
-__global__ void topk_merge_kernel(const float* __restrict__ scores, const int32_t* __restrict__ ids,
-                                  const float* __restrict__ label_scores, int parts, int B, int k,
-                                  float* __restrict__ out_scores, int32_t* __restrict__ out_ids,
-                                  float* __restrict__ out_label, int in_ld, int in_part_stride, int out_ld, int out_label_ld) {
-  // inputs: list q of (part s, row b) at scores[s * in_part_stride + b * in_ld + q] (ids likewise, label scores at
-  // label_scores[s * in_part_stride + b * in_ld]); outputs with row strides out_ld / out_label_ld.  The dense
-  // [parts][B][k] layout is in_ld = k, in_part_stride = B * k; a packed (B, 2k+1) row = k scores | k ids | label.
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  float ts[SC_MAXK]; int ti[SC_MAXK];
-#pragma unroll
-  for (int i = 0; i < SC_MAXK; ++i) { ts[i] = -INFINITY; ti[i] = 0x7fffffff; }
-  float lab = -INFINITY;
-  for (int s = 0; s < parts; ++s) {
-    const float* ps = scores + static_cast<size_t>(s) * in_part_stride + static_cast<size_t>(b) * in_ld;
-    const int32_t* pi = ids + static_cast<size_t>(s) * in_part_stride + static_cast<size_t>(b) * in_ld;
-    if (label_scores)
-      lab = fmaxf(lab, in_ld == k ? label_scores[static_cast<size_t>(s) * B + b]
-                                  : label_scores[static_cast<size_t>(s) * in_part_stride + static_cast<size_t>(b) * in_ld]);
-    for (int q0 = 0; q0 < k; ++q0) {
-      float cs = ps[q0]; int ci = pi[q0];
-      if (!(cs > -INFINITY)) break;   // -inf = list not full, NaN = part never written for this row
-#pragma unroll
-      for (int q = 0; q < SC_MAXK; ++q) {
-        if (q < k) {
-          const bool sw = (cs > ts[q]) || (cs == ts[q] && ci < ti[q]);
-          const float t_s = ts[q]; const int t_i = ti[q];
-          ts[q] = sw ? cs : t_s; ti[q] = sw ? ci : t_i;
-          cs = sw ? t_s : cs; ci = sw ? t_i : ci;
-        }
+// Merge `parts` lists of k (score, id) per user -> global top-k (score desc, id asc).  ONE WARP PER USER ROW: lane q
+// holds entry q of the running sorted list; candidates are streamed 32 at a time (coalesced), a ballot picks those that
+// beat the current k-th entry, and each is inserted cooperatively (position = number of better entries by ballot/popc,
+// the tail shifts by one shuffle).  The former thread-per-row version walked parts x k candidates through a serial
+// register insertion in 32 CTAs: 106 us for 28 parts x 4096 users — 14 % of a 125k-item shard's pass.
+// inputs: list q of (part s, row b) at scores[s * in_part_stride + b * in_ld + q] (ids likewise, label scores at
+// label_scores[s * B + b] for the dense layout, at [s * in_part_stride + b * in_ld] for packed rows); outputs with row
+// strides out_ld / out_label_ld.  Dense [parts][B][k]: in_ld = k, in_part_stride = B * k; a packed (B, 2k+1) row =
+// k scores | k ids | label.
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(const float* __restrict__ scores, const int32_t* __restrict__ ids,
+                  const float* __restrict__ label_scores, int parts, int B, int k,
+                  float* __restrict__ out_scores, int32_t* __restrict__ out_ids,
+                  float* __restrict__ out_label, int in_ld, int in_part_stride, int out_ld, int out_label_ld) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;                                   // warp-uniform
+  float ts = -INFINITY;
+  int ti = 0x7fffffff;
+  const int total = parts * k;
+  for (int base = 0; base < total; base += 32) {
+    const int idx = base + lane;
+    const bool in = idx < total;
+    const int sp = in ? idx / k : 0, q0 = in ? idx % k : 0;
+    const size_t off = static_cast<size_t>(sp) * in_part_stride + static_cast<size_t>(b) * in_ld + q0;
+    const float cs = in ? scores[off] : -INFINITY;
+    const int ci = in ? ids[off] : 0x7fffffff;
+    const float thr_s = __shfl_sync(0xffffffffu, ts, k - 1);
+    const int thr_i = __shfl_sync(0xffffffffu, ti, k - 1);
+    // -inf = list slot never filled, NaN = part never written for this row: neither is a candidate
+    const bool cand = in && (cs > -INFINITY) && (cs > thr_s || (cs == thr_s && ci < thr_i));
+    unsigned m = __ballot_sync(0xffffffffu, cand);
+    while (m != 0) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const float c_s = __shfl_sync(0xffffffffu, cs, src);
+      const int c_i = __shfl_sync(0xffffffffu, ci, src);
+      const bool better = lane < k && (ts > c_s || (ts == c_s && ti < c_i));
+      const int pos = __popc(__ballot_sync(0xffffffffu, better));
+      const float up_s = __shfl_up_sync(0xffffffffu, ts, 1);
+      const int up_i = __shfl_up_sync(0xffffffffu, ti, 1);
+      if (pos < k) {
+        if (lane == pos) { ts = c_s; ti = c_i; }
+        else if (lane > pos && lane < k) { ts = up_s; ti = up_i; }
       }
     }
   }
-#pragma unroll
-  for (int q = 0; q < SC_MAXK; ++q)
-    if (q < k) { out_scores[static_cast<size_t>(b) * out_ld + q] = ts[q]; out_ids[static_cast<size_t>(b) * out_ld + q] = ti[q]; }
-  if (out_label) out_label[static_cast<size_t>(b) * out_label_ld] = lab;
+  if (lane < k) {
+    out_scores[static_cast<size_t>(b) * out_ld + lane] = ts;
+    out_ids[static_cast<size_t>(b) * out_ld + lane] = ti;
+  }
+  if (out_label != nullptr) {
+    float lab = -INFINITY;
+    if (label_scores != nullptr)
+      for (int sp = lane; sp < parts; sp += 32)
+        lab = fmaxf(lab, in_ld == k ? label_scores[static_cast<size_t>(sp) * B + b]
+                                    : label_scores[static_cast<size_t>(sp) * in_part_stride + static_cast<size_t>(b) * in_ld]);
+    lab = warp_max(lab);
+    if (lane == 0) out_label[static_cast<size_t>(b) * out_label_ld] = lab;
+  }
 }
 
 // y[n,:] = x[n,:] / max(|x[n,:]|, 1e-8) as bf16; one warp per row (E = 768).
@@ -863,6 +885,22 @@ extern "C" long long rf_cosine_topk_ws_bytes(int B, long long N, int k) {
   return parts * B * (static_cast<long long>(k) * 8 + 4) + (static_cast<long long>(B) + 1) * 4 + 256;
 }
 
+// seed the shared thresholds with the k-th best score of a merged top-k (here: of the first SEED_ITEMS items)
+__global__ void topk_seed_threshold_kernel(const float* __restrict__ scores, int B, int k, int ld, unsigned int* __restrict__ thr) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float s = scores[static_cast<size_t>(b) * ld + k - 1];
+  thr[b] = (s > -INFINITY) ? f2ord(s) : 0u;
+}
+
+// Threshold seeding (8-GPU sharding makes the per-GPU table short: a 125k-item shard is swept by ~9 parts that each
+// see ~14k items per row, and a list that young takes a hit in nearly every 32-column chunk of a warp).  A cheap
+// pre-pass finds the exact top-k of the first SEED_ITEMS items (the same kernels on a 16-tile table, ~25 us) and
+// publishes its k-th best score as every row's initial shared threshold: the main sweep then starts with a top-
+// (k / SEED_ITEMS) quantile threshold instead of -inf.  Exact: the k-th best of a subset never exceeds the global one.
+constexpr long long SC_SEED_ITEMS = 4096;
+constexpr long long SC_SEED_MIN_N = 16 * SC_SEED_ITEMS;
+
 static int cosine_topk_impl(const void* xn, const void* yn, int B, long long N, int E, float temp, int k, int id_base,
                             const int64_t* labels, float* topk_scores, int32_t* topk_ids, float* label_score, int out_ld,
                             int label_ld, void* ws, cudaStream_t stream) {
@@ -882,11 +920,36 @@ static int cosine_topk_impl(const void* xn, const void* yn, int B, long long N, 
   // a leftover pair only writes the rows of the user tiles it visited: every other (part, row) slot keeps
   // this NaN pattern, which the merge skips
   p.ws_thr = reinterpret_cast<unsigned int*>(p.ws_label + static_cast<size_t>(parts) * B);
-  RF_CUDA(cudaMemsetAsync(ws, 0xFF, cnt * 8 + static_cast<size_t>(parts) * B * 4, stream));
   RF_CUDA(cudaMemsetAsync(p.ws_thr, 0, (static_cast<size_t>(B) + 1) * 4, stream));     // 0 = no threshold published yet
-  int rc = launch_cosine(SC_TOPK, xn, yn, p, stream);
+  int rc;
+  // Measured (4096 users; 125k / 250k / 1M items): the pre-pass costs 88 us and the main sweep gains nothing — the
+  // shard's deficit was the serial merge kernel (106 us) and a fixed ~140 us, not list warm-up — so seeding is OFF unless
+  // RF_SCORE_SEED=1 asks for it.
+  static const bool seed = getenv("RF_SCORE_SEED") != nullptr;
+  if (N >= SC_SEED_MIN_N && seed) {
+    // pre-pass over the first SEED_ITEMS items; its merged top-k lands in the caller's output buffers (overwritten by
+    // the real result below), its k-th best score seeds ws_thr
+    ScoreParams q{};
+    q.B = B; q.N = SC_SEED_ITEMS; q.K = E; q.inv_temp = p.inv_temp; q.k = k; q.id_base = id_base;
+    const int qparts = 2 * plan_schedule(B, SC_SEED_ITEMS, &q);
+    RF_REQUIRE(qparts <= parts, "rf_cosine_topk: internal: seed pass needs more parts than the main pass");
+    const size_t qcnt = static_cast<size_t>(qparts) * B * k;
+    q.ws_scores = reinterpret_cast<float*>(ws);
+    q.ws_ids = reinterpret_cast<int32_t*>(q.ws_scores + qcnt);
+    q.ws_label = reinterpret_cast<float*>(q.ws_ids + qcnt);
+    q.ws_thr = p.ws_thr;
+    RF_CUDA(cudaMemsetAsync(ws, 0xFF, qcnt * 8 + static_cast<size_t>(qparts) * B * 4, stream));
+    if ((rc = launch_cosine(SC_TOPK, xn, yn, q, stream))) return rc;
+    topk_merge_kernel<<<(B + 7) / 8, 256, 0, stream>>>(q.ws_scores, q.ws_ids, nullptr, qparts, B, k, topk_scores,
+                                                          topk_ids, nullptr, k, B * k, out_ld, label_ld);
+    if ((rc = check_launch("rf_cosine_topk/seed-merge"))) return rc;
+    topk_seed_threshold_kernel<<<(B + 127) / 128, 128, 0, stream>>>(topk_scores, B, k, out_ld, p.ws_thr);
+    if ((rc = check_launch("rf_cosine_topk/seed"))) return rc;
+  }
+  RF_CUDA(cudaMemsetAsync(ws, 0xFF, cnt * 8 + static_cast<size_t>(parts) * B * 4, stream));
+  rc = launch_cosine(SC_TOPK, xn, yn, p, stream);
   if (rc) return rc;
-  topk_merge_kernel<<<(B + 127) / 128, 128, 0, stream>>>(p.ws_scores, p.ws_ids, p.ws_label, parts, B, k, topk_scores,
+  topk_merge_kernel<<<(B + 7) / 8, 256, 0, stream>>>(p.ws_scores, p.ws_ids, p.ws_label, parts, B, k, topk_scores,
                                                         topk_ids, label_score, k, B * k, out_ld, label_ld);
   return check_launch("rf_cosine_topk/merge");
 }
@@ -913,7 +976,7 @@ extern "C" int rf_topk_merge_packed(const float* packed, int parts, int B, int k
   RF_REQUIRE(packed && out_scores && out_ids && parts > 0 && B > 0, "rf_topk_merge_packed: bad argument");
   RF_REQUIRE(k >= 1 && k <= SC_MAXK, "rf_topk_merge_packed: k=%d out of range [1,%d]", k, SC_MAXK);
   const int ld = 2 * k + 1;
-  topk_merge_kernel<<<(B + 127) / 128, 128, 0, stream>>>(packed, reinterpret_cast<const int32_t*>(packed) + k, packed + 2 * k,
+  topk_merge_kernel<<<(B + 7) / 8, 256, 0, stream>>>(packed, reinterpret_cast<const int32_t*>(packed) + k, packed + 2 * k,
                                                         parts, B, k, out_scores, out_ids, out_label_score, ld, B * ld, k, 1);
   return check_launch("rf_topk_merge_packed");
 }
@@ -924,7 +987,7 @@ extern "C" int rf_topk_merge(const float* scores, const int32_t* ids, const floa
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   RF_REQUIRE(scores && ids && out_scores && out_ids && parts > 0 && B > 0, "rf_topk_merge: bad argument");
   RF_REQUIRE(k >= 1 && k <= SC_MAXK, "rf_topk_merge: k=%d out of range [1,%d]", k, SC_MAXK);
-  topk_merge_kernel<<<(B + 127) / 128, 128, 0, stream>>>(scores, ids, label_scores, parts, B, k, out_scores, out_ids,
+  topk_merge_kernel<<<(B + 7) / 8, 256, 0, stream>>>(scores, ids, label_scores, parts, B, k, out_scores, out_ids,
                                                         out_label_score, k, B * k, k, 1);
   return check_launch("rf_topk_merge");
 }
