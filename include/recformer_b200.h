@@ -314,6 +314,12 @@ int rf_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* ex
 int rf_adamw_step_bf16grad(float* param, const void* grad_bf16, float* exp_avg, float* exp_avg_sq, void* shadow_bf16_or_null,
                            long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                            float grad_scale, const float* hp_dev_or_null, rf_stream_t stream);
+/* rf_adamw_step (hp_dev == NULL) / rf_adamw_step_dev (hp_dev != NULL) that additionally overwrites the fp32 gradient it
+ * has just consumed with zeros — the `optimizer.zero_grad()` of the reference loop (ref: finetune.py:126) folded into
+ * the update, so a captured step needs no separate memset of the flat gradient buffer. */
+int rf_adamw_step_zero(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16_or_null,
+                       long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                       float grad_scale, const float* hp_dev_or_null, rf_stream_t stream);
 /* Dropout sites: ref: recformer/models.py:134 (embeddings), HF:585,1035 (attention probabilities), HF:1069,1128
  * (dense outputs); torch draws them from its generator state.  Here the masks are Philox draws keyed by
  * (drop_seed argument XOR a library-wide nonce).  The nonce is 0

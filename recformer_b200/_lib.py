@@ -98,6 +98,8 @@ _SIGS = {
                                   c_float, c_void_p, c_void_p]),
     "rf_adamw_step_bf16grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float,
                                        c_float, c_float, c_int, c_float, c_void_p, c_void_p]),
+    "rf_adamw_step_zero": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float,
+                                   c_float, c_float, c_int, c_float, c_void_p, c_void_p]),
     "rf_set_dropout_nonce": (c_int, [c_void_p, c_void_p]),
 }
 

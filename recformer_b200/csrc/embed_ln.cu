@@ -118,6 +118,64 @@ __device__ __forceinline__ void embed_row_stats(const EmbedDev& a, int id, int p
   rstd = rsqrtf(warp_sum(q) / a.E + a.eps);
 }
 
+// Raw (unvalidated) ids of one token: loaded one to two work items ahead of their use so that the dependent
+// row gathers never wait for them.
+struct TokIds { int id, pid, tt, ip; };
+
+__device__ __forceinline__ TokIds embed_load_ids(const EmbedDev& a, int b, int l) {
+  TokIds r;
+  if (l < a.L) {
+    const size_t s = static_cast<size_t>(b) * a.L + l;
+    r.id = static_cast<int>(__ldg(a.ids + s));
+    r.tt = a.tt ? static_cast<int>(__ldg(a.tt + s)) : 0;
+    r.ip = static_cast<int>(__ldg(a.ip + s));
+  } else {  // window padding (ref: recformer/models.py:238-258)
+    r.id = a.pad; r.tt = 0; r.ip = a.pad;
+  }
+  r.pid = __ldg(a.pos + static_cast<size_t>(b) * a.Lp + l);
+  return r;
+}
+
+__device__ __forceinline__ bool embed_clamp_ids(const EmbedDev& a, TokIds& r) {
+  const bool bad = r.id < 0 || r.id >= a.vocab || r.pid < 0 || r.pid >= a.max_pos || r.tt < 0 || r.tt >= a.type_size ||
+                   r.ip < 0 || r.ip >= a.max_item;
+  r.id = min(max(r.id, 0), a.vocab - 1);
+  r.pid = min(max(r.pid, 0), a.max_pos - 1);
+  r.tt = min(max(r.tt, 0), a.type_size - 1);
+  r.ip = min(max(r.ip, 0), a.max_item - 1);
+  return bad;
+}
+
+// Work decomposition of the backward kernel: a work item is (sequence group, position l); the warps of a CTA take
+// the sequences of the group at the SAME position, so that phase B (below) can sum their position-row gradients in
+// registers.  Each CTA owns a contiguous range of work items (consecutive positions: the id loads of the next item
+// hit the same cache lines, and a CTA touches few item-position rows).
+// warp -> (sequence, position) of work item w.  `seqs` (the largest power of two <= min(B, warps)) sequences share a
+// CTA; the remaining factor of the CTA's warps covers consecutive positions.
+struct EmbedMap {
+  int seqs, posn, lblocks, items;
+  __host__ __device__ __forceinline__ void locate(int w, int warp, int& b, int& l) const {
+    const int g = w / lblocks, lb = w - g * lblocks;
+    b = g * seqs + (warp & (seqs - 1));
+    l = lb * posn + warp / seqs;
+  }
+};
+
+__host__ __device__ __forceinline__ EmbedMap embed_map(int B, int Lp, int warps) {
+  EmbedMap m;
+  m.seqs = 1;
+  while (m.seqs * 2 <= B && m.seqs * 2 <= warps) m.seqs *= 2;
+  m.posn = warps / m.seqs;
+  m.lblocks = (Lp + m.posn - 1) / m.posn;
+  m.items = ((B + m.seqs - 1) / m.seqs) * m.lblocks;
+  return m;
+}
+
+// Forward: one warp per token, the 8 warps of a CTA on 8 consecutive tokens.  Measured alternatives (ncu, C2 shape,
+// 30.4 us for this one): warps on the same position of 8 / 16 sequences so that the position row is shared (36 us: the
+// 3 MB-strided output rows), token-type / item-position tables in shared memory (38 us: every CTA first pulls the same
+// 165 KB through L2) — the kernel moves 16.7 KB of L2 traffic per token for 7.7 KB of compulsory bytes and sits at
+// the L2 fabric's ~7.5 TB/s.
 template <int NV4>
 __global__ void __launch_bounds__(ROW_THREADS) embed_ln_fwd_kernel(const EmbedDev a, __nv_bfloat16* __restrict__ out,
                                                                    float* __restrict__ out32, int* err_flag) {
@@ -151,9 +209,11 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_ln_fwd_kernel(const EmbedDe
   }
 }
 
+// Fallback backward (small tables do not fit shared memory): one warp per token, every table updated by global
+// red.adds — 4 x 768 atomics per token, of which the token-type / item-position ones pile onto a handful of rows.
 template <int NV4>
 __global__ void __launch_bounds__(ROW_THREADS)
-embed_ln_bwd_kernel(const EmbedDev a, const __nv_bfloat16* __restrict__ dout, float* d_word, float* d_pos,
+embed_ln_bwd_atomic_kernel(const EmbedDev a, const __nv_bfloat16* __restrict__ dout, float* d_word, float* d_pos,
                     float* d_type, float* d_item, float* d_gamma, float* d_beta) {
   const int lane = threadIdx.x & 31;
   const int T = a.B * a.Lp;
@@ -213,6 +273,240 @@ embed_ln_bwd_kernel(const EmbedDev a, const __nv_bfloat16* __restrict__ dout, fl
     if (d_gamma) red_add_v4(d_gamma + v * 4, dg[k].x, dg[k].y, dg[k].z, dg[k].w);
     if (d_beta) red_add_v4(d_beta + v * 4, db[k].x, db[k].y, db[k].z, db[k].w);
   }
+}
+
+// Backward with CTA-level aggregation of the small tables.  Same work decomposition as the forward (the warps of a
+// CTA take up to 8 sequences at the same position).  Per work item:
+//   phase A (warp = token): recompute the row statistics, dx = LayerNorm backward of the (dropout-masked) upstream
+//     gradient, red.add dx into the word-gradient row (the only table whose rows are mostly distinct), park dx in a
+//     shared-memory slab;
+//   phase B (thread = 4 columns): walk the parked rows; position rows are summed in registers while consecutive rows
+//     carry the same position id (left-aligned batches: all sequences of the group) and flushed with ONE red.add;
+//     token-type and item-position rows are accumulated into shared-memory copies of the two tables that the column's
+//     owner updates without atomics.
+// The shared tables are flushed once per CTA at the end (item rows only if touched).  Global atomics per token drop
+// from 4 x 768 to ~1.2 x 768; the former kernel spent its 145 us in the L2 atomic units (12.6 M red.v4 per step,
+// 16 384 of them onto each word of the 3 token-type rows).
+struct EmbedBwdSmem {
+  static constexpr int STAGE_FLOATS = (ROW_THREADS / 32) * 768;
+  static size_t bytes(int type_size, int max_item) {
+    return (2 * STAGE_FLOATS + static_cast<size_t>(type_size + max_item) * 768) * 4 + 2 * (ROW_THREADS / 32) * 16 +
+           static_cast<size_t>(max_item) * 4 + 16;
+  }
+};
+
+template <int NV4>
+__global__ void __launch_bounds__(ROW_THREADS, 1)
+embed_ln_bwd_kernel(const EmbedDev a, const __nv_bfloat16* __restrict__ dout, float* d_word, float* d_pos,
+                    float* d_type, float* d_item, float* d_gamma, float* d_beta) {
+  constexpr int E = NV4 * 128, WARPS = ROW_THREADS / 32;
+  extern __shared__ float4 embed_smem[];
+  float4* stage = embed_smem;                                   // [2][WARPS][E / 4]
+  float4* tab_type = stage + 2 * WARPS * (E / 4);               // [type_size][E / 4]
+  float4* tab_item = tab_type + a.type_size * (E / 4);          // [max_item][E / 4]
+  int4* keys = reinterpret_cast<int4*>(tab_item + a.max_item * (E / 4));   // [2][WARPS] (pid, tt, ip, valid)
+  int* touched = reinterpret_cast<int*>(keys + 2 * WARPS);      // [max_item]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (a.type_size + a.max_item) * (E / 4); i += ROW_THREADS)
+    tab_type[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < a.max_item; i += ROW_THREADS) touched[i] = 0;
+  __syncthreads();
+
+  const EmbedMap mp = embed_map(a.B, a.Lp, ROW_THREADS / 32);
+  const int per = (mp.items + gridDim.x - 1) / gridDim.x;
+  const int w0 = blockIdx.x * per, w1 = min(mp.items, w0 + per);
+  auto ids_of = [&](int w) -> TokIds {
+    TokIds r{a.pad, a.pad, 0, a.pad};
+    if (w < w1) {
+      int b, l;
+      mp.locate(w, warp, b, l);
+      if (b < a.B && l < a.Lp) r = embed_load_ids(a, b, l);
+    }
+    return r;
+  };
+  float4 dg[NV4], db[NV4];
+#pragma unroll
+  for (int k = 0; k < NV4; ++k) dg[k] = db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  TokIds cur = ids_of(w0), nxt = ids_of(w0 + 1);
+  const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
+  const float4* word4 = reinterpret_cast<const float4*>(a.word);
+  // The two DRAM-latency loads of an item (its random word row, its upstream-gradient row) are issued one item ahead,
+  // before phase B and the barrier of the current item, and held in registers.
+  auto tok_of = [&](int w) -> int {      // token index of this warp's row of item w, or -1
+    if (w >= w1) return -1;
+    int b, l;
+    mp.locate(w, warp, b, l);
+    return (b < a.B && l < a.Lp) ? b * a.Lp + l : -1;
+  };
+  float4 wrow[NV4];
+  uint2 drow[NV4];
+  {
+    const int idc = min(max(cur.id, 0), a.vocab - 1);
+    const int t0 = max(tok_of(w0), 0);
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) {
+      wrow[k] = __ldg(word4 + static_cast<size_t>(idc) * (E / 4) + k * 32 + lane);
+      drow[k] = reinterpret_cast<const uint2*>(dout + static_cast<size_t>(t0) * E)[k * 32 + lane];
+    }
+  }
+  for (int w = w0; w < w1; ++w) {
+    const int buf = (w - w0) & 1;
+    const TokIds nn = ids_of(w + 2);
+    float4 wnext[NV4];
+    uint2 dnext[NV4];
+    {
+      const int idn = min(max(nxt.id, 0), a.vocab - 1);
+      const int tn = max(tok_of(w + 1), 0);
+#pragma unroll
+      for (int k = 0; k < NV4; ++k) {
+        wnext[k] = __ldg(word4 + static_cast<size_t>(idn) * (E / 4) + k * 32 + lane);
+        dnext[k] = reinterpret_cast<const uint2*>(dout + static_cast<size_t>(tn) * E)[k * 32 + lane];
+      }
+    }
+    int b, l;
+    mp.locate(w, warp, b, l);
+    const bool valid = b < a.B && l < a.Lp;     // warp-uniform
+    // ---------------- phase A ----------------
+    if (valid) {
+      const int t = b * a.Lp + l;
+      embed_clamp_ids(a, cur);
+      float4 x[NV4];
+      float mean, rstd;
+      {
+        const float4* pw = reinterpret_cast<const float4*>(a.posw + static_cast<size_t>(cur.pid) * E);
+        const float4* tw = reinterpret_cast<const float4*>(a.type + static_cast<size_t>(cur.tt) * E);
+        const float4* iw = reinterpret_cast<const float4*>(a.item + static_cast<size_t>(cur.ip) * E);
+        float sx = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV4; ++k) {
+          const int v = k * 32 + lane;
+          const float4 a0 = wrow[k], a1 = __ldg(pw + v), a2 = __ldg(tw + v), a3 = __ldg(iw + v);
+          x[k].x = ((a0.x + a1.x) + a2.x) + a3.x;
+          x[k].y = ((a0.y + a1.y) + a2.y) + a3.y;
+          x[k].z = ((a0.z + a1.z) + a2.z) + a3.z;
+          x[k].w = ((a0.w + a1.w) + a2.w) + a3.w;
+          sx += (x[k].x + x[k].y) + (x[k].z + x[k].w);
+        }
+        mean = warp_sum(sx) / E;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV4; ++k) {
+          const float dx = x[k].x - mean, dy = x[k].y - mean, dz = x[k].z - mean, dw = x[k].w - mean;
+          q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        }
+        rstd = rsqrtf(warp_sum(q) / E + a.eps);
+      }
+      float4 gy[NV4];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV4; ++k) {
+        const int v = k * 32 + lane;
+        const uint2 raw = drow[k];
+        float2 lo = unpack_bf16(raw.x), hi = unpack_bf16(raw.y);
+        float4 dy = make_float4(lo.x, lo.y, hi.x, hi.y);
+        if (a.drop_thresh != 0) {
+          const uint32_t keep = dropout_keep4(a.drop_seed, static_cast<uint64_t>(t) * (E / 4) + v, a.drop_thresh);
+          dy.x = (keep & 1u) ? dy.x * a.drop_scale : 0.f; dy.y = (keep & 2u) ? dy.y * a.drop_scale : 0.f;
+          dy.z = (keep & 4u) ? dy.z * a.drop_scale : 0.f; dy.w = (keep & 8u) ? dy.w * a.drop_scale : 0.f;
+        }
+        const float4 xh = make_float4((x[k].x - mean) * rstd, (x[k].y - mean) * rstd, (x[k].z - mean) * rstd,
+                                      (x[k].w - mean) * rstd);
+        x[k] = xh;
+        dg[k].x += dy.x * xh.x; dg[k].y += dy.y * xh.y; dg[k].z += dy.z * xh.z; dg[k].w += dy.w * xh.w;
+        db[k].x += dy.x; db[k].y += dy.y; db[k].z += dy.z; db[k].w += dy.w;
+        const float4 g = __ldg(g4 + v);
+        gy[k] = make_float4(dy.x * g.x, dy.y * g.y, dy.z * g.z, dy.w * g.w);
+        s1 += (gy[k].x + gy[k].y) + (gy[k].z + gy[k].w);
+        s2 += (gy[k].x * xh.x + gy[k].y * xh.y) + (gy[k].z * xh.z + gy[k].w * xh.w);
+      }
+      s1 = warp_sum(s1) / E;
+      s2 = warp_sum(s2) / E;
+      float4* srow = stage + (buf * WARPS + warp) * (E / 4);
+#pragma unroll
+      for (int k = 0; k < NV4; ++k) {
+        const int v = k * 32 + lane;
+        const float4 dx = make_float4(rstd * (gy[k].x - s1 - x[k].x * s2), rstd * (gy[k].y - s1 - x[k].y * s2),
+                                      rstd * (gy[k].z - s1 - x[k].z * s2), rstd * (gy[k].w - s1 - x[k].w * s2));
+        // nn.Embedding(padding_idx=pad) never accumulates a gradient into the pad row
+        // (ref: recformer/models.py:89,104-106)
+        if (d_word && cur.id != a.pad) red_add_v4(d_word + static_cast<size_t>(cur.id) * E + v * 4, dx.x, dx.y, dx.z, dx.w);
+        srow[v] = dx;
+      }
+    }
+    if (lane == 0) keys[buf * WARPS + warp] = make_int4(cur.pid, cur.tt, cur.ip, valid ? 1 : 0);
+    __syncthreads();
+    // ---------------- phase B ----------------
+    if (threadIdx.x < E / 4) {
+      const int j = threadIdx.x;
+      float4 accp = make_float4(0.f, 0.f, 0.f, 0.f);
+      int curp = -1;
+#pragma unroll 1
+      for (int r = 0; r < WARPS; ++r) {
+        const int4 key = keys[buf * WARPS + r];
+        if (!key.w) continue;
+        const float4 v = stage[(buf * WARPS + r) * (E / 4) + j];
+        if (d_pos && key.x != a.pad) {
+          if (key.x != curp) {
+            if (curp >= 0) red_add_v4(d_pos + static_cast<size_t>(curp) * E + j * 4, accp.x, accp.y, accp.z, accp.w);
+            accp = make_float4(0.f, 0.f, 0.f, 0.f);
+            curp = key.x;
+          }
+          accp.x += v.x; accp.y += v.y; accp.z += v.z; accp.w += v.w;
+        }
+        if (d_type) {
+          float4 c = tab_type[key.y * (E / 4) + j];
+          c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
+          tab_type[key.y * (E / 4) + j] = c;
+        }
+        if (d_item) {
+          float4 c = tab_item[key.z * (E / 4) + j];
+          c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
+          tab_item[key.z * (E / 4) + j] = c;
+          if (j == 0) touched[key.z] = 1;
+        }
+      }
+      if (curp >= 0) red_add_v4(d_pos + static_cast<size_t>(curp) * E + j * 4, accp.x, accp.y, accp.z, accp.w);
+    }
+    // no second barrier: the next item parks its rows in the other slab, and the slab used now is only rewritten
+    // two items later, i.e. after the next barrier
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) { wrow[k] = wnext[k]; drow[k] = dnext[k]; }
+    cur = nxt;
+    nxt = nn;
+  }
+  __syncthreads();
+  // ---- flush: LayerNorm weight / bias gradients (8 warps -> 1 through the first slab), then the shared tables ----
+  float* red = reinterpret_cast<float*>(stage);
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    float* dst = which == 0 ? d_gamma : d_beta;
+    if (dst == nullptr) continue;    // uniform
+#pragma unroll
+    for (int k = 0; k < NV4; ++k)
+      reinterpret_cast<float4*>(red + warp * E)[k * 32 + lane] = which == 0 ? dg[k] : db[k];
+    __syncthreads();
+    if (threadIdx.x < E / 4) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < WARPS; ++r) {
+        const float4 v = reinterpret_cast<const float4*>(red + r * E)[threadIdx.x];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      red_add_v4(dst + threadIdx.x * 4, t.x, t.y, t.z, t.w);
+    }
+    __syncthreads();
+  }
+  if (d_type)
+    for (int i = threadIdx.x; i < a.type_size * (E / 4); i += ROW_THREADS) {
+      const float4 v = tab_type[i];
+      red_add_v4(d_type + static_cast<size_t>(i) * 4, v.x, v.y, v.z, v.w);
+    }
+  if (d_item)
+    for (int i = threadIdx.x; i < a.max_item * (E / 4); i += ROW_THREADS) {
+      if (!touched[i / (E / 4)]) continue;
+      const float4 v = tab_item[i];
+      red_add_v4(d_item + static_cast<size_t>(i) * 4, v.x, v.y, v.z, v.w);
+    }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -443,8 +737,8 @@ __global__ void cast_f32_bf16_kernel(const float4* __restrict__ x, uint2* __rest
   }
 }
 
-template <bool G_BF16>
-__global__ void adamw_kernel(float4* __restrict__ p, const void* __restrict__ g_, float4* __restrict__ m,
+template <bool G_BF16, bool ZERO_G = false>
+__global__ void adamw_kernel(float4* __restrict__ p, const void* g_, float4* __restrict__ m,
                              float4* __restrict__ v, uint2* __restrict__ shadow, long long n4, float lr, float b1,
                              float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale,
                              const float* __restrict__ hp) {
@@ -459,6 +753,9 @@ __global__ void adamw_kernel(float4* __restrict__ p, const void* __restrict__ g_
       gg = make_float4(lo.x, lo.y, hi.x, hi.y);
     } else {
       gg = reinterpret_cast<const float4*>(g_)[i];
+      // the step consumed this gradient: leave zeros behind, so that a captured training step needs no separate
+      // 600 MB memset of the flat gradient buffer (rf_adamw_step_zero)
+      if (ZERO_G) reinterpret_cast<float4*>(const_cast<void*>(g_))[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float* pa = reinterpret_cast<float*>(&pp); float* ga = reinterpret_cast<float*>(&gg);
     float* ma = reinterpret_cast<float*>(&mm); float* va = reinterpret_cast<float*>(&vv);
@@ -487,6 +784,13 @@ static EmbedDev make_embed_dev(const rf_embed_args* a) {
   d.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
   d.drop_seed = a->drop_seed;
   return d;
+}
+
+// grid of the embedding kernels: one CTA per work item (see EmbedMap), capped at `per_sm` CTAs per SM
+static int embed_grid(const rf_embed_args* a, int warps, int per_sm) {
+  const long long items = embed_map(a->B, a->Lp, warps).items;
+  const long long cap = static_cast<long long>(sm_count()) * per_sm;
+  return static_cast<int>(items < cap ? (items > 0 ? items : 1) : cap);
 }
 
 static int row_grid(int T) {
@@ -529,9 +833,19 @@ extern "C" int rf_embed_ln_bwd(const rf_embed_args* a, const void* dout, float* 
   RF_REQUIRE(a && dout, "rf_embed_ln_bwd: null argument");
   RF_REQUIRE(a->E == 768, "rf_embed_ln_bwd: hidden size %d unsupported (768)", a->E);
   const EmbedDev d = make_embed_dev(a);
-  const int grid = min(row_grid(a->B * a->Lp), sm_count() * 2);
-  embed_ln_bwd_kernel<6><<<grid, ROW_THREADS, 0, stream>>>(d, reinterpret_cast<const __nv_bfloat16*>(dout), d_word,
-                                                          d_pos, d_type, d_item, d_gamma, d_beta);
+  const size_t smem = EmbedBwdSmem::bytes(a->type_size, a->max_item);
+  if (smem <= 227 * 1024) {
+    auto kern = embed_ln_bwd_kernel<6>;
+    static std::atomic<unsigned long long> attr_seen{0};   // one bit per device
+    if (first_use_on_device(&attr_seen))
+      RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    kern<<<embed_grid(a, ROW_THREADS / 32, 1), ROW_THREADS, smem, stream>>>(d, reinterpret_cast<const __nv_bfloat16*>(dout), d_word, d_pos,
+                                                         d_type, d_item, d_gamma, d_beta);
+  } else {
+    const int grid = min(row_grid(a->B * a->Lp), sm_count() * 2);
+    embed_ln_bwd_atomic_kernel<6><<<grid, ROW_THREADS, 0, stream>>>(d, reinterpret_cast<const __nv_bfloat16*>(dout),
+                                                                   d_word, d_pos, d_type, d_item, d_gamma, d_beta);
+  }
   return check_launch("rf_embed_ln_bwd");
 }
 
@@ -634,6 +948,24 @@ extern "C" int rf_adamw_step_dev(float* param, const float* grad, float* exp_avg
       reinterpret_cast<float4*>(exp_avg_sq), reinterpret_cast<uint2*>(shadow), n4, 0.f, beta1, beta2, eps, weight_decay,
       1.f, 1.f, 1.f, hp_dev);
   return check_launch("rf_adamw_step_dev");
+}
+
+extern "C" int rf_adamw_step_zero(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow, long long n,
+                                  float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                                  float grad_scale, const float* hp_dev, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && n % 4 == 0 && (hp_dev || step >= 1),
+             "rf_adamw_step_zero: bad argument");
+  const long long n4 = n / 4;
+  long long grid = (n4 + 255) / 256;
+  if (grid > sm_count() * 16) grid = sm_count() * 16;
+  const float bc1 = hp_dev ? 1.f : 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2 = hp_dev ? 1.f : 1.f - powf(beta2, static_cast<float>(step));
+  adamw_kernel<false, true><<<static_cast<int>(grid), 256, 0, stream>>>(
+      reinterpret_cast<float4*>(param), grad, reinterpret_cast<float4*>(exp_avg),
+      reinterpret_cast<float4*>(exp_avg_sq), reinterpret_cast<uint2*>(shadow), n4, lr, beta1, beta2, eps, weight_decay,
+      bc1, sqrtf(bc2), grad_scale, hp_dev);
+  return check_launch("rf_adamw_step_zero");
 }
 
 // ================================================================================================

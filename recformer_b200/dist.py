@@ -133,14 +133,7 @@ class GradSync:
 
     def layer_ranges(self, layer: int, last_layer: Optional[int] = None):
         """The two contiguous flat-buffer ranges (dense weights, *_global weights) of layers layer..last_layer."""
-        P = self.engine.params
-        p, q = f"encoder.layer.{layer}.", f"encoder.layer.{layer if last_layer is None else last_layer}."
-        named = P._named
-        d0 = P.offsets[p + "attention.self.query.weight"]
-        d1 = P.offsets[q + "output.dense.weight"] + named[q + "output.dense.weight"].numel()
-        g0 = P.offsets[p + "attention.self.query_global.weight"]
-        g1 = P.offsets[q + "attention.self.value_global.weight"] + named[q + "attention.self.value_global.weight"].numel()
-        return [(d0, d1), (g0, g1)]
+        return self.engine.params.layer_ranges(layer, last_layer)
 
     def _wire(self, g: torch.Tensor):
         """The buffer that travels: the fp32 gradient buffer itself, or its flat bf16 twin (allocated once)."""

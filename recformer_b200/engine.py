@@ -154,6 +154,16 @@ class FlatParams:
             n *= s
         return base[o:o + n].view(shape)
 
+    def layer_ranges(self, layer: int, last_layer: Optional[int] = None):
+        """The two contiguous flat-buffer ranges (six dense weights, three *_global weights) of layers layer..last_layer."""
+        p, q = f"encoder.layer.{layer}.", f"encoder.layer.{layer if last_layer is None else last_layer}."
+        named = self._named
+        d0 = self.offsets[p + "attention.self.query.weight"]
+        d1 = self.offsets[q + "output.dense.weight"] + named[q + "output.dense.weight"].numel()
+        g0 = self.offsets[p + "attention.self.query_global.weight"]
+        g1 = self.offsets[q + "attention.self.value_global.weight"] + named[q + "attention.self.value_global.weight"].numel()
+        return [(d0, d1), (g0, g1)]
+
     def invalidate(self) -> None:
         """Force the next forward to recast the bf16 shadow (after weights were edited through `.data`, which
         does not bump the autograd version counters refresh_shadow() keys on)."""
@@ -283,7 +293,15 @@ class EncoderEngine:
         self.overlap_global = os.environ.get("RF_DEBUG_NO_OVERLAP") is None
         self._debug_skip_global = os.environ.get("RF_DEBUG_SKIP_GLOBAL") is not None   # timing experiment only (wrong results)
         self._debug_no_xk = os.environ.get("RF_DEBUG_NO_XK") is not None   # A/B switch: separate dx-update kernel
-        self.grad_hook = None      # callable(layer): that layer's gradients are final (dist.GradSync)
+        self.grad_hook = None      # callable(layer): that layer's gradients are final (dist.GradSync, FusedAdamW overlap)
+        # Second side stream ("aux"): work nobody on the backward's critical path waits for — the bias-gradient column
+        # sums of dU / dqkv and, when FusedAdamW.begin_overlap() armed it, the AdamW update of finished layers.  These
+        # are small-footprint HBM-bound kernels (<= 40 registers, <= 8 KB of shared memory) that fit on an SM NEXT to a
+        # resident persistent GEMM CTA, so they use the HBM bandwidth the tensor-bound GEMMs leave idle.
+        self._aux: Dict[str, torch.cuda.Stream] = {}
+        # Off by default: on a stream of the SAME priority as the main one this work delays the CTAs of the persistent
+        # kernels (13.57 vs 13.35 ms per step); GraphedTrainStep captures on a high-priority stream and switches it on.
+        self.overlap_aux = False
 
     # -- helpers -------------------------------------------------------------------------------
     def _acquire(self, B, Lp, device, per_layer) -> SavedActivations:
@@ -308,8 +326,28 @@ class EncoderEngine:
     def side_stream(self, device) -> torch.cuda.Stream:
         key = str(device)
         if key not in self._side:
-            self._side[key] = torch.cuda.Stream(device=device)
+            # high priority: the main stream waits for this chain of small kernels once per layer and direction
+            self._side[key] = torch.cuda.Stream(device=device, priority=int(os.environ.get("RF_SIDE_PRIO", "-1")))
         return self._side[key]
+
+    def aux_stream(self, device) -> torch.cuda.Stream:
+        key = str(device)
+        if key not in self._aux:
+            self._aux[key] = torch.cuda.Stream(device=device, priority=0)      # lowest: runs in what the others leave
+        return self._aux[key]
+
+    def fork_aux(self, device, name: str, layer: int, fn) -> torch.cuda.Event:
+        """Run fn() on the aux stream after everything enqueued so far on the current stream; returns the event that
+        marks its completion (the caller waits on it before it overwrites what fn reads, and at the end of the pass)."""
+        main, aux = torch.cuda.current_stream(device), self.aux_stream(device)
+        ev = self.event(device, name, layer)
+        ev.record(main)
+        aux.wait_event(ev)
+        with torch.cuda.stream(aux):
+            fn()
+            done = self.event(device, name + ".done", layer)
+            done.record(aux)
+        return done
 
     def event(self, device, name: str, layer: int) -> torch.cuda.Event:
         key = (str(device), name, layer)
@@ -490,6 +528,8 @@ class EncoderEngine:
         pd = sv.drop_hidden
         aw = cfg.attention_window
         d_out = dout
+        use_aux = self.overlap_aux
+        dU_free = dqkv_free = None      # aux-stream events: the column sums that still read sc.dU / sc.dqkv
         for i in reversed(range(cfg.num_hidden_layers)):
             W, G = self._layer_weights(i), self._layer_grads(i)
             x = sv.x[i]
@@ -501,8 +541,13 @@ class EncoderEngine:
             dY = sc.d_pre_drop if pd > 0 else sc.d_pre
             ops.gemm(dY, sv.g[i], out=G["W2"], a_mn_major=True, b_mn_major=True, accumulate=True,
                      split_k=_pick_split(E, F, T))
+            if dU_free is not None:
+                torch.cuda.current_stream(device).wait_event(dU_free)
             ops.gemm(dY, W["W2"], out=sc.dU, b_mn_major=True, epi=ops.EPI_DGELU, aux=sv.u[i])
-            ops.colsum(sc.dU, G["b1"])
+            if use_aux:
+                dU_free = self.fork_aux(device, "dU", i, lambda: ops.colsum(sc.dU, G["b1"]))
+            else:
+                ops.colsum(sc.dU, G["b1"])
             ops.gemm(sc.dU, sv.h1[i], out=G["W1"], a_mn_major=True, b_mn_major=True, accumulate=True,
                      split_k=_pick_split(F, E, T))
             ops.gemm(sc.dU, W["W1"], out=sc.dh1, b_mn_major=True, residual=sc.d_pre)
@@ -528,9 +573,14 @@ class EncoderEngine:
                     if sc.xk is not None and not self._debug_no_xk:
                         ops.global_attn_bwd_xk(*gargs, sv.glob[i], sc.gws, *sc.xk)
                     ev_a.record(side)
+            if dqkv_free is not None:
+                torch.cuda.current_stream(device).wait_event(dqkv_free)
             ops.band_attn_bwd(sv.qkv[i], mask, B, Lp, H, w_one, sv.ctx[i], sv.lse[i], sc.dctx, sc.dqkv, sc.dkv,
                               drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 1), ws=self.attn_ws(B, Lp, w_one, device))
-            ops.colsum(sc.dqkv, G["bqkv"])
+            if use_aux:
+                dqkv_free = self.fork_aux(device, "dqkv", i, lambda: ops.colsum(sc.dqkv, G["bqkv"]))
+            else:
+                ops.colsum(sc.dqkv, G["bqkv"])
             ops.gemm(sc.dqkv, x, out=G["Wqkv"], a_mn_major=True, b_mn_major=True, accumulate=True,
                      split_k=_pick_split(3 * E, E, T))
             dx = sc.dx[i % 2]
@@ -553,6 +603,9 @@ class EncoderEngine:
             d_out = dx
             if self.grad_hook is not None:
                 self.grad_hook(i)
+        for ev in (dU_free, dqkv_free):       # join the aux stream: the bias gradients are final when backward() returns
+            if ev is not None:
+                torch.cuda.current_stream(device).wait_event(ev)
         e = "embeddings."
         named = P._named
         gview = lambda k: P.view(k, P.grad) if named[k].requires_grad else None

@@ -416,6 +416,14 @@ def adamw_step_bf16grad(param, grad_bf16, exp_avg, exp_avg_sq, shadow, lr, beta1
                                             grad_scale, _ptr(hp), _stream()), "rf_adamw_step_bf16grad")
 
 
+def adamw_step_zero(param, grad, exp_avg, exp_avg_sq, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
+                    hp=None):
+    """adamw_step / adamw_step_dev (hp given) that also leaves zeros in the fp32 gradient it consumed."""
+    check(_lib.lib().rf_adamw_step_zero(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                        _ptr(shadow), param.numel(), lr, beta1, beta2, eps, weight_decay, step,
+                                        grad_scale, _ptr(hp), _stream()), "rf_adamw_step_zero")
+
+
 def set_dropout_nonce(nonce):
     """Loads the library-wide dropout nonce from a device int64 tensor (see include/recformer_b200.h)."""
     _req(nonce, torch.int64, "nonce")

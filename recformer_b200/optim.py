@@ -28,6 +28,7 @@ class FusedAdamW:
         self.exp_avg_sq = None
         self._segments: List[Tuple[int, int, bool, bool]] = []
         self._plan_sig = None
+        self._ov = None        # state of an update overlapped with the backward pass (begin_overlap)
         # trainable parameters the flat buffer does not hold
         inside = {id(p) for p in enc.parameters()}
         named_extra = [(k, p) for k, p in model.named_parameters() if id(p) not in inside and p.requires_grad]
@@ -76,13 +77,8 @@ class FusedAdamW:
         b1, b2 = self.betas
         return (float(self.lr), 1.0 - b1 ** t, (1.0 - b2 ** t) ** 0.5, float(grad_scale))
 
-    @torch.no_grad()
-    def step(self, grad_scale: float = 1.0, wait_other=None, hp=None):
-        """wait_other: optional callable (GradSync.finish(defer_tail=True)) that is invoked right before the
-        segment holding the embedding tables is updated — the dense and no-decay segments run while the
-        embedding gradients are still being all-reduced.
-        hp: optional fp32 device tensor holding step_scalars(); the kernels then take lr, the bias corrections
-        and grad_scale from it instead of from their arguments (graph capture / replay)."""
+    # -- internals -----------------------------------------------------------------------------
+    def _ensure_state(self, frozen_plan: bool) -> None:
         P = self.engine.params
         if P.grad is None:
             raise RuntimeError("FusedAdamW.step() called before any backward pass")
@@ -90,7 +86,7 @@ class FusedAdamW:
             self.exp_avg = torch.zeros_like(P.flat)
             self.exp_avg_sq = torch.zeros_like(P.flat)
             self._plan_sig = None
-        if hp is None:                   # (a captured step froze its plan; see GraphedTrainStep)
+        if not frozen_plan:              # (a captured step froze its plan; see GraphedTrainStep)
             sig = self._signature()      # requires_grad flips / replaced Parameters since the last step re-plan
             if sig != self._plan_sig:
                 self._plan()
@@ -98,6 +94,95 @@ class FusedAdamW:
         elif self._plan_sig is None:
             self._plan()
             self._plan_sig = self._signature()
+
+    def _update(self, a: int, b: int, decay: bool, shadow: bool, t: int, grad_scale: float, hp, zero: bool) -> None:
+        """One launch over the flat range [a, b)."""
+        P = self.engine.params
+        b1, b2 = self.betas
+        wd = self.weight_decay if decay else 0.0
+        sh = P.shadow[a:b] if shadow else None
+        wire = P.grad_wire          # bf16 all-reduced gradients of this step (dist.GradSync), else None
+        if wire is not None:
+            ops.adamw_step_bf16grad(P.flat[a:b], wire[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b], sh, self.lr, b1, b2,
+                                    self.eps, wd, t, grad_scale, hp=hp)
+        elif zero:
+            ops.adamw_step_zero(P.flat[a:b], P.grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b], sh, self.lr, b1, b2,
+                                self.eps, wd, t, grad_scale, hp=hp)
+        elif hp is not None:
+            ops.adamw_step_dev(P.flat[a:b], P.grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b], sh, b1, b2, self.eps,
+                               wd, hp)
+        else:
+            ops.adamw_step(P.flat[a:b], P.grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b], sh, self.lr, b1, b2,
+                           self.eps, wd, t, grad_scale)
+
+    # -- update overlapped with the backward pass ------------------------------------------------
+    @torch.no_grad()
+    def begin_overlap(self, grad_scale: float = 1.0, hp=None, zero_grads: bool = False, passes: int = 1) -> None:
+        """Call between the forward and `loss.backward()` of a step whose gradients are complete after this backward
+        (no accumulation across calls, no gradient clipping, single GPU): as soon as the engine has enqueued a layer's
+        backward, that layer's dense and *_global weights are updated on the engine's aux stream, next to the backward
+        kernels of the layers below (AdamW is HBM-bound and small enough to share an SM with a resident GEMM CTA; the
+        GEMMs are tensor-bound).  `step()` afterwards updates what is left (embeddings, biases, LayerNorm vectors) and
+        joins the aux stream.  The result is bit-identical to a plain `step()`: same kernels on the same inputs.
+        zero_grads: every update also clears the gradient range it consumed (no zero_grad() memset next step).
+        passes: encoder backward passes per step (a layer is final after the last one)."""
+        if self.engine.params.grad_wire is not None:
+            raise RuntimeError("FusedAdamW.begin_overlap: gradients come from an all-reduce (GradSync); not supported")
+        P = self.engine.params
+        P.prepare_grads()
+        self._ensure_state(frozen_plan=hp is not None)
+        self._ov = {"gs": float(grad_scale), "hp": hp, "zero": bool(zero_grads), "covered": [], "seen": {},
+                    "passes": int(passes), "prev": self.engine.grad_hook, "t": self.step_count + 1, "last": None}
+        self.engine.grad_hook = self._on_layer
+
+    def _on_layer(self, layer: int) -> None:
+        ov = self._ov
+        if ov["prev"] is not None:
+            ov["prev"](layer)
+        ov["seen"][layer] = ov["seen"].get(layer, 0) + 1
+        if ov["seen"][layer] < ov["passes"]:
+            return
+        eng = self.engine
+        device = eng.params.flat.device
+
+        def run():
+            for r0, r1 in eng.params.layer_ranges(layer):
+                for (a, b, decay, shadow) in self._segments:
+                    lo, hi = max(a, r0), min(b, r1)
+                    if lo < hi:
+                        self._update(lo, hi, decay, shadow, ov["t"], ov["gs"], ov["hp"], ov["zero"])
+                        ov["covered"].append((lo, hi))
+
+        ov["last"] = eng.fork_aux(device, "opt", layer, run)
+
+    @staticmethod
+    def _subtract(a: int, b: int, covered):
+        """[a, b) minus the (disjoint) covered ranges."""
+        out, pos = [], a
+        for lo, hi in sorted(covered):
+            if hi <= pos or lo >= b:
+                continue
+            if lo > pos:
+                out.append((pos, lo))
+            pos = max(pos, hi)
+        if pos < b:
+            out.append((pos, b))
+        return out
+
+    @torch.no_grad()
+    def step(self, grad_scale: float = 1.0, wait_other=None, hp=None, zero_grads: bool = False):
+        """wait_other: optional callable (GradSync.finish(defer_tail=True)) that is invoked right before the
+        segment holding the embedding tables is updated — the dense and no-decay segments run while the
+        embedding gradients are still being all-reduced.
+        hp: optional fp32 device tensor holding step_scalars(); the kernels then take lr, the bias corrections
+        and grad_scale from it instead of from their arguments (graph capture / replay).
+        zero_grads: the update also clears the fp32 gradients it consumed (see begin_overlap)."""
+        P = self.engine.params
+        ov, self._ov = self._ov, None
+        if ov is not None:
+            self.engine.grad_hook = ov["prev"]
+            grad_scale, hp, zero_grads = ov["gs"], ov["hp"], ov["zero"]
+        self._ensure_state(frozen_plan=hp is not None)
         if self._extra_opt is not None:
             if hp is not None:
                 raise RuntimeError("FusedAdamW: parameters outside the encoder's flat buffer cannot be stepped from a "
@@ -110,29 +195,25 @@ class FusedAdamW:
                         p.grad.mul_(grad_scale)
             self._extra_opt.step()
         self.step_count += 1
-        b1, b2 = self.betas
         segs = list(self._segments)
         if wait_other is not None:      # embeddings (+ *_global weights) = the decay segment without a bf16 shadow: last
             segs.sort(key=lambda sgm: (sgm[2] and not sgm[3]))
-        wire = P.grad_wire          # bf16 all-reduced gradients of this step (dist.GradSync), else None
+        covered = ov["covered"] if ov is not None else []
         for (a, b, decay, shadow) in segs:
             if wait_other is not None and decay and not shadow:
                 wait_other()
                 wait_other = None
-            if wire is not None:
-                ops.adamw_step_bf16grad(P.flat[a:b], wire[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b],
-                                        P.shadow[a:b] if shadow else None, self.lr, b1, b2, self.eps,
-                                        self.weight_decay if decay else 0.0, self.step_count, grad_scale, hp=hp)
-                continue
-            if hp is not None:
-                ops.adamw_step_dev(P.flat[a:b], P.grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b],
-                                   P.shadow[a:b] if shadow else None, b1, b2, self.eps,
-                                   self.weight_decay if decay else 0.0, hp)
-                continue
-            ops.adamw_step(P.flat[a:b], P.grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b],
-                           P.shadow[a:b] if shadow else None, self.lr, b1, b2, self.eps,
-                           self.weight_decay if decay else 0.0, self.step_count, grad_scale)
+            for lo, hi in (self._subtract(a, b, covered) if covered else [(a, b)]):
+                self._update(lo, hi, decay, shadow, self.step_count, grad_scale, hp, zero_grads and P.grad_wire is None)
         if wait_other is not None:
             wait_other()
+        if ov is not None and ov["last"] is not None:      # join the aux stream: every parameter is updated on return
+            torch.cuda.current_stream(P.flat.device).wait_event(ov["last"])
         P.grad_wire = None            # consumed: a later step without a GradSync must not read stale gradients
         P.mark_shadow_fresh(by_optimizer=True)
+
+    def untouched_ranges(self):
+        """Flat ranges no update ever writes (frozen parameters): what a step that relies on zero_grads=True still has
+        to clear itself."""
+        self._ensure_state(frozen_plan=False)
+        return self._subtract(0, self.engine.params.n_total, [(a, b) for (a, b, _, _) in self._segments])

@@ -429,6 +429,43 @@ def test_graphed_train_step_matches_eager_steps():
     assert torch.isfinite(_eager_step(model, opt, batches[1]))
 
 
+def test_overlapped_adamw_is_bit_identical_to_plain_step():
+    """FusedAdamW.begin_overlap(): per-layer updates launched from the engine's layer hook on the aux stream + the rest in
+    step() must cover every trainable element exactly once — same parameters, moments and bf16 shadow, bit for bit, as
+    one plain step() on the same gradients; with zero_grads the consumed gradients are cleared, frozen ones kept."""
+    model, opt, batches = _graph_setup(0.0)
+    _eager_step(model, opt, batches[0])
+    eng = model.longformer._engine
+    P = eng.params
+    frozen = model.longformer.embeddings.word_embeddings.weight
+    frozen.requires_grad_(False)                      # a frozen range in the middle of a segment
+    loss = model(**batches[1])
+    opt.zero_grad()
+    loss.backward()
+    torch.cuda.synchronize()
+    snap = [t.clone() for t in (P.flat, P.grad, opt.exp_avg, opt.exp_avg_sq, P.shadow)]
+    opt.lr = 7e-4
+    opt.step(grad_scale=0.5)
+    torch.cuda.synchronize()
+    want = [t.clone() for t in (P.flat, opt.exp_avg, opt.exp_avg_sq, P.shadow)]
+    for dst, src in zip((P.flat, P.grad, opt.exp_avg, opt.exp_avg_sq, P.shadow), snap):
+        dst.copy_(src)
+    opt.step_count -= 1
+    opt.begin_overlap(grad_scale=0.5, zero_grads=True)
+    for layer in reversed(range(model.config.num_hidden_layers)):
+        eng.grad_hook(layer)                          # what engine.backward() calls after each layer
+    opt.step()
+    torch.cuda.synchronize()
+    assert eng.grad_hook is None and opt.step_count == 2
+    for got, ref, name in zip((P.flat, opt.exp_avg, opt.exp_avg_sq, P.shadow), want, ("param", "m", "v", "shadow")):
+        assert torch.equal(got, ref), name
+    o = P.offsets["embeddings.word_embeddings.weight"]
+    n = frozen.numel()
+    assert torch.equal(P.grad[o:o + n], snap[1][o:o + n])               # frozen: gradient left alone
+    assert P.grad[:o].abs().max().item() == 0.0 and P.grad[o + n:].abs().max().item() == 0.0
+    assert opt.untouched_ranges() == [(o, o + n)]
+
+
 def test_graphed_train_step_draws_fresh_dropout_masks():
     from recformer_b200.graph import GraphedTrainStep
     model, opt, batches = _graph_setup(0.1)
