@@ -27,7 +27,7 @@ constexpr int SC_EPI_WARPS = 8, SC_THREADS = 64 + 32 * SC_EPI_WARPS;
 constexpr int SC_MAXK = 16;
 constexpr uint32_t SC_A_BYTES = SC_BM * SC_BK * 2, SC_B_BYTES = SC_BN * SC_BK * 2;
 constexpr uint32_t SC_STAGE_BYTES = SC_A_BYTES + SC_B_BYTES;
-constexpr uint32_t SC_LIST_ONLY_BYTES = SC_MAXK * SC_EPI_WARPS * 32 * 8;   // per-thread top-k lists: [q][thread] score + id
+constexpr uint32_t SC_LIST_ONLY_BYTES = SC_MAXK * SC_EPI_WARPS * 32 * 8;   // per-row top-k lists: scores, then ids
 constexpr uint32_t SC_LIST_BYTES = SC_LIST_ONLY_BYTES + SC_EPI_WARPS * 4096;   // + per-warp [32 cols][32 rows] fp32 chunk slab
 constexpr uint32_t SC_SMEM = SC_STAGES * SC_STAGE_BYTES + SC_LIST_BYTES + (2 * SC_STAGES + 4) * 8 + 16 + 1024;
 // CTA-pair variant: 256 users x 256 items per tile, each CTA stages its 128 user rows and its
@@ -69,10 +69,22 @@ enum { SC_TOPK = 0, SC_DENSE = 1 };
 // that TIES with g may still win its place by the lower-id rule.  Without this every part pays the full warm-up of a
 // young list (k (1 + ln(n/k)) inserts for its n items); with it the row pays roughly one warm-up in total, which is
 // what makes a 125k-item shard (8-GPU sharding of the 1M table) cost little more per item than the whole table.
+//
+// List layout and the two insert paths.  A warp's 32 rows keep their sorted lists in one shared-memory block, entry q of
+// row t at word t * 16 + (q ^ (t >> 1)): conflict-free both when every lane touches entry q of its OWN row (banks
+// (t & 1) * 16 + (q ^ (t >> 1)) are all different) and when lanes 0..k-1 touch the k entries of ONE row.  A chunk that
+// produced hits inserts them either
+//   * per lane (SIMT): every lane with hits runs a compare-and-shift insertion on its own row — the warp pays
+//     max-over-lanes(hits) x ~90 instructions of a dependent shared-memory chain, or
+//   * cooperatively: the warp takes the hits one by one, lane q holds entry q of the hit's row, one ballot gives the
+//     insertion position, one shuffle shifts the tail (~20 instructions per hit, total-over-lanes of them).
+// The chunk picks whichever is cheaper from the hit counts (one redux each).  Young lists (first tiles of a part, or
+// the short item range a shard of an 8-GPU run sees) have many hits per lane: SIMT; afterwards a chunk typically has
+// a handful of hits spread over different lanes, where the SIMT path idles 31 lanes per insertion: cooperative.
 struct TopkState {
-  float* scratch;   // this thread's column of its warp's [32][32] fp32 chunk slab
-  float* ts;        // &list_scores[0][thread]
-  int* ti;          // &list_ids[0][thread]
+  float* slab;      // this warp's [32 cols][32 rows] fp32 chunk slab
+  float* ls;        // this warp's list scores [32 rows][16 entries] (swizzled, see list_slot)
+  int* li;          // ... and ids
   float thr;        // k-th best score of THIS part's list (-inf until the list is full)
   float eff;        // strict rejection threshold: max(thr, largest float below the published g)
   float gprev;      // largest float below g
@@ -81,6 +93,8 @@ struct TopkState {
   float label_score;
   long long label_local;   // label id relative to this table shard, or -1
 };
+
+__device__ __forceinline__ int list_slot(int t, int q) { return t * SC_MAXK + (q ^ (t >> 1)); }
 
 __device__ __forceinline__ unsigned int f2ord(float f) {
   const unsigned int b = __float_as_uint(f);
@@ -102,24 +116,45 @@ __device__ __forceinline__ void topk_sync_threshold(TopkState& st) {
   st.eff = fmaxf(st.thr, st.gprev);
 }
 
-constexpr int SC_LIST_STRIDE = SC_EPI_WARPS * 32;
-
-__device__ __forceinline__ float topk_insert(float* ts, int* ti, int k, float s, int id) {
+// per-lane insertion into the lane's own row; returns the new k-th best
+__device__ __forceinline__ float topk_insert_own(const TopkState& st, int lane, int k, float s, int id) {
   // descending insertion; strict '>' keeps the earlier (lower) id ahead on equal scores
   int q = k - 1;
-  while (q > 0 && s > ts[(q - 1) * SC_LIST_STRIDE]) {
-    ts[q * SC_LIST_STRIDE] = ts[(q - 1) * SC_LIST_STRIDE];
-    ti[q * SC_LIST_STRIDE] = ti[(q - 1) * SC_LIST_STRIDE];
+  while (q > 0) {
+    const float prev = st.ls[list_slot(lane, q - 1)];
+    if (!(s > prev)) break;
+    st.ls[list_slot(lane, q)] = prev;
+    st.li[list_slot(lane, q)] = st.li[list_slot(lane, q - 1)];
     --q;
   }
-  ts[q * SC_LIST_STRIDE] = s;
-  ti[q * SC_LIST_STRIDE] = id;
-  return ts[(k - 1) * SC_LIST_STRIDE];
+  st.ls[list_slot(lane, q)] = s;
+  st.li[list_slot(lane, q)] = id;
+  return st.ls[list_slot(lane, k - 1)];
+}
+
+// warp-cooperative insertion of (s, id) into row L's list (all arguments warp-uniform); returns the new k-th best
+__device__ __forceinline__ float topk_insert_coop(const TopkState& st, int lane, int k, int L, float s, int id) {
+  float e_s = -INFINITY;
+  int e_i = 0x7fffffff;
+  if (lane < SC_MAXK) { e_s = st.ls[list_slot(L, lane)]; e_i = st.li[list_slot(L, lane)]; }
+  const bool ahead = lane < k && (e_s > s || (e_s == s && e_i < id));     // a prefix of the sorted list
+  const int pos = __popc(__ballot_sync(0xffffffffu, ahead));
+  const float up_s = __shfl_up_sync(0xffffffffu, e_s, 1);
+  const int up_i = __shfl_up_sync(0xffffffffu, e_i, 1);
+  float n_s = e_s;
+  int n_i = e_i;
+  if (lane == pos) { n_s = s; n_i = id; }
+  else if (lane > pos) { n_s = up_s; n_i = up_i; }
+  if (lane >= pos && lane < k) { st.ls[list_slot(L, lane)] = n_s; st.li[list_slot(L, lane)] = n_i; }
+  const float thr_new = __shfl_sync(0xffffffffu, n_s, k - 1);
+  __syncwarp();
+  return thr_new;
 }
 
 // One 32-row x 32-column accumulator chunk (thread = user row) of the TOPK epilogue.
 __device__ __forceinline__ void topk_chunk(const uint32_t (&r)[32], TopkState& st, const ScoreParams& p,
                                            long long col0) {
+  const int lane = threadIdx.x & 31;
   // fast reject: max over the chunk (4 independent chains), one multiply, one vote
   float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
 #pragma unroll
@@ -132,33 +167,60 @@ __device__ __forceinline__ void topk_chunk(const uint32_t (&r)[32], TopkState& s
   const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * p.inv_temp;   // == max_j (r[j] * inv_temp): rounding is monotonic
   const long long rel = st.label_local - col0;
   const bool partial = col0 + 32 > p.N;                                // warp-uniform
-  const bool mine = (mx > st.eff) || (rel >= 0 && rel < 32) || partial;
-  if (!__any_sync(0xffffffffu, mine)) return;
-  // slow path: bit mask of the columns that beat the current k-th best, then one insertion per set bit
-  // (a straight-line predicated insert per column costs ~10x more: the threshold only moves on a hit)
   const int nvalid = partial ? static_cast<int>(p.N - col0) : 32;
+  const bool has_label = rel >= 0 && rel < nvalid;
+  const bool mine = (mx > st.eff) || has_label;
+  if (!__any_sync(0xffffffffu, mine)) return;
+  // slow path.  Bit mask of the columns that MAY beat the threshold: the raw accumulator against a threshold lowered
+  // by a few ulps (one compare per column, no multiply); the exact test s * inv_temp > eff is repeated on each
+  // candidate at insertion time — the threshold may have risen by then anyway.
   uint32_t hits = 0;
-  if (mine) {
+  if (mx > st.eff) {
+    float raw = __fdividef(st.eff, p.inv_temp);
+    raw = raw - fabsf(raw) * 4e-6f - 1e-30f;          // (-inf stays -inf)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float s = __uint_as_float(r[j]) * p.inv_temp;
-      if (j == rel && j < nvalid) st.label_score = s;
-      hits |= (s > st.eff && j < nvalid) ? (1u << j) : 0u;
-    }
+    for (int j = 0; j < 32; ++j) hits |= (__uint_as_float(r[j]) > raw) ? (1u << j) : 0u;
+    if (partial) hits &= (1u << nvalid) - 1u;
   }
-  if (__any_sync(0xffffffffu, hits != 0)) {
-    // the chunk's values go through this thread's column of the warp's scratch slab so that a hit can be
-    // fetched by its (dynamic) column index
+  // the chunk's values go through the warp's slab so that a hit (or the label column) can be fetched by its
+  // dynamic column index, by any lane
 #pragma unroll
-    for (int j = 0; j < 32; ++j) st.scratch[j * 32] = __uint_as_float(r[j]);
-    const int id0 = p.id_base + static_cast<int>(col0);
-    while (hits != 0) {
-      const int j = __ffs(hits) - 1;
-      hits &= hits - 1;
-      const float s = st.scratch[j * 32] * p.inv_temp;
-      if (s > st.eff) {   // the threshold may have risen since the mask was built
-        st.thr = topk_insert(st.ts, st.ti, p.k, s, id0 + j);
-        st.eff = fmaxf(st.thr, st.gprev);
+  for (int j = 0; j < 32; ++j) st.slab[j * 32 + lane] = __uint_as_float(r[j]);
+  __syncwarp();
+  if (has_label) st.label_score = st.slab[static_cast<int>(rel) * 32 + lane] * p.inv_temp;
+  const int nh = __popc(hits);
+  const int total = __reduce_add_sync(0xffffffffu, nh);
+  const int id0 = p.id_base + static_cast<int>(col0);
+  if (total != 0) {
+    const int most = __reduce_max_sync(0xffffffffu, nh);
+    if (total > 4 * most) {
+      // ---- per-lane insertions ----
+      while (hits != 0) {
+        const int j = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const float s = st.slab[j * 32 + lane] * p.inv_temp;
+        if (s > st.eff) {
+          st.thr = topk_insert_own(st, lane, p.k, s, id0 + j);
+          st.eff = fmaxf(st.thr, st.gprev);
+        }
+      }
+    } else {
+      // ---- cooperative insertions, hit by hit ----
+      uint32_t lanes = __ballot_sync(0xffffffffu, hits != 0);
+      while (lanes != 0) {
+        const int L = __ffs(lanes) - 1;
+        lanes &= lanes - 1;
+        uint32_t m = __shfl_sync(0xffffffffu, hits, L);
+        while (m != 0) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1;
+          const float s = st.slab[j * 32 + L] * p.inv_temp;
+          const float eff_l = __shfl_sync(0xffffffffu, st.eff, L);
+          if (s > eff_l) {
+            const float thr_new = topk_insert_coop(st, lane, p.k, L, s, id0 + j);
+            if (lane == L) { st.thr = thr_new; st.eff = fmaxf(thr_new, st.gprev); }
+          }
+        }
       }
     }
   }
@@ -176,10 +238,13 @@ __device__ __forceinline__ void dense_chunk(const uint32_t (&r)[32], const Score
 
 __device__ __forceinline__ void topk_state_init(TopkState& st, uint8_t* list_smem, int etid, const ScoreParams& p, int row,
                                                 bool row_ok) {
-  st.scratch = reinterpret_cast<float*>(list_smem + SC_LIST_ONLY_BYTES) + (etid >> 5) * 1024 + (etid & 31);
-  st.ts = reinterpret_cast<float*>(list_smem) + etid;
-  st.ti = reinterpret_cast<int*>(list_smem + SC_MAXK * SC_LIST_STRIDE * 4) + etid;
-  for (int q = 0; q < SC_MAXK; ++q) { st.ts[q * SC_LIST_STRIDE] = -INFINITY; st.ti[q * SC_LIST_STRIDE] = 0x7fffffff; }
+  const int ewarp = etid >> 5, lane = etid & 31;
+  st.slab = reinterpret_cast<float*>(list_smem + SC_LIST_ONLY_BYTES) + ewarp * 1024;
+  st.ls = reinterpret_cast<float*>(list_smem) + ewarp * 32 * SC_MAXK;
+  st.li = reinterpret_cast<int*>(list_smem + SC_EPI_WARPS * 32 * SC_MAXK * 4) + ewarp * 32 * SC_MAXK;
+  __syncwarp();     // (re-initialisation: cooperative reads of the previous segment's lists are over)
+  for (int q = 0; q < SC_MAXK; ++q) { st.ls[list_slot(lane, q)] = -INFINITY; st.li[list_slot(lane, q)] = 0x7fffffff; }
+  __syncwarp();
   st.thr = st.eff = st.gprev = st.published = -INFINITY;
   st.gthr = p.ws_thr + (row_ok ? row : p.B);
   st.label_score = -INFINITY;
@@ -191,9 +256,10 @@ __device__ __forceinline__ void topk_state_init(TopkState& st, uint8_t* list_sme
 }
 
 __device__ __forceinline__ void topk_state_flush(const TopkState& st, const ScoreParams& p, int part, int row) {
+  const int lane = threadIdx.x & 31;
   float* os = p.ws_scores + (static_cast<size_t>(part) * p.B + row) * p.k;
   int32_t* oi = p.ws_ids + (static_cast<size_t>(part) * p.B + row) * p.k;
-  for (int q = 0; q < p.k; ++q) { os[q] = st.ts[q * SC_LIST_STRIDE]; oi[q] = st.ti[q * SC_LIST_STRIDE]; }
+  for (int q = 0; q < p.k; ++q) { os[q] = st.ls[list_slot(lane, q)]; oi[q] = st.li[list_slot(lane, q)]; }
   p.ws_label[static_cast<size_t>(part) * p.B + row] = st.label_score;
 }
 
