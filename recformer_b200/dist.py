@@ -126,6 +126,7 @@ class GradSync:
         # RF_DP_SYNC_AT_END=1 (A/B aid): no per-layer overlap, one cast + one all-reduce of the whole buffer in finish()
         import os
         self.at_end = os.environ.get("RF_DP_SYNC_AT_END") is not None
+        self.bucket_hook = None     # callable(ranges, works): a bucket's all-reduces were launched (FusedAdamW overlap)
         self.engine.grad_hook = self.on_layer
 
     def _active(self) -> bool:
@@ -168,9 +169,12 @@ class GradSync:
             return                                        # when its lowest layer is
         n_layers = self.engine.cfg.num_hidden_layers
         g = self.engine.params.grad
-        for a, b in self.layer_ranges(layer, min(layer + self.bucket_layers, n_layers) - 1):
-            self._works.append(self._reduce_range(g, a, b))
-            self._covered.append((a, b))
+        ranges = self.layer_ranges(layer, min(layer + self.bucket_layers, n_layers) - 1)
+        works = [self._reduce_range(g, a, b) for a, b in ranges]
+        self._works += works
+        self._covered += ranges
+        if self.bucket_hook is not None:
+            self.bucket_hook(ranges, works)
 
     def finish(self, defer_tail: bool = False):
         """Reduce what the per-layer calls left (embedding tables; biases / LayerNorm vectors) and wait.

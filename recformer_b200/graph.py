@@ -81,8 +81,14 @@ class GraphedTrainStep:
         # the critical chain's CTAs before those of the aux stream (priority 0: bias-gradient column sums, overlapped
         # AdamW), which then only fill what the chain leaves.  Measured (same box, ms per step): plain 13.35, aux work at
         # equal priority 13.57 (it delays the persistent kernels' CTAs), with priorities 13.21.
-        # (Data-parallel steps keep the default priority and no aux work: NCCL's stream would be the low-priority one.)
-        prio = int(os.environ.get("RF_GRAPH_PRIO", "-1")) if sync is None else 0
+        # Data-parallel steps: same priorities (NCCL's own stream, like the aux stream, has the default = lowest one: the
+        # collectives fill what the backward leaves, and finish in the clear at its end); the update of a layer bucket
+        # follows that bucket's all-reduce on the aux stream (FusedAdamW.begin_overlap(sync=...)).  RF_DP_PLAIN=1 (A/B
+        # aid) restores the default-priority capture without aux work.
+        dp_plain = sync is not None and os.environ.get("RF_DP_PLAIN") is not None
+        self.dp_overlap = sync is not None and not dp_plain and os.environ.get("RF_GRAPH_NO_OVERLAP") is None \
+            and not optimizer.extra_params
+        prio = 0 if dp_plain else int(os.environ.get("RF_GRAPH_PRIO", "-1"))
         cap_stream = torch.cuda.Stream(device=dev, priority=prio)
         aux_before = enc._engine.overlap_aux
         enc._engine.overlap_aux = prio < 0 and os.environ.get("RF_DEBUG_NO_AUX") is None
@@ -95,6 +101,11 @@ class GraphedTrainStep:
                     P.grad[a:b].zero_()
                 loss.backward()
                 optimizer.step()
+            elif sync is not None and self.dp_overlap:
+                optimizer.zero_grad()
+                optimizer.begin_overlap(grad_scale=grad_scale, hp=self._dev[:4], sync=sync)
+                loss.backward()
+                optimizer.step(wait_other=sync.finish(defer_tail=True))
             else:
                 optimizer.zero_grad()
                 loss.backward()

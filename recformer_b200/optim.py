@@ -95,13 +95,15 @@ class FusedAdamW:
             self._plan()
             self._plan_sig = self._signature()
 
-    def _update(self, a: int, b: int, decay: bool, shadow: bool, t: int, grad_scale: float, hp, zero: bool) -> None:
+    def _update(self, a: int, b: int, decay: bool, shadow: bool, t: int, grad_scale: float, hp, zero: bool,
+                wire=None) -> None:
         """One launch over the flat range [a, b)."""
         P = self.engine.params
         b1, b2 = self.betas
         wd = self.weight_decay if decay else 0.0
         sh = P.shadow[a:b] if shadow else None
-        wire = P.grad_wire          # bf16 all-reduced gradients of this step (dist.GradSync), else None
+        if wire is None:
+            wire = P.grad_wire      # bf16 all-reduced gradients of this step (dist.GradSync), else None
         if wire is not None:
             ops.adamw_step_bf16grad(P.flat[a:b], wire[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b], sh, self.lr, b1, b2,
                                     self.eps, wd, t, grad_scale, hp=hp)
@@ -117,7 +119,8 @@ class FusedAdamW:
 
     # -- update overlapped with the backward pass ------------------------------------------------
     @torch.no_grad()
-    def begin_overlap(self, grad_scale: float = 1.0, hp=None, zero_grads: bool = False, passes: int = 1) -> None:
+    def begin_overlap(self, grad_scale: float = 1.0, hp=None, zero_grads: bool = False, passes: int = 1,
+                      sync=None) -> None:
         """Call between the forward and `loss.backward()` of a step whose gradients are complete after this backward
         (no accumulation across calls, no gradient clipping, single GPU): as soon as the engine has enqueued a layer's
         backward, that layer's dense and *_global weights are updated on the engine's aux stream, next to the backward
@@ -125,15 +128,48 @@ class FusedAdamW:
         GEMMs are tensor-bound).  `step()` afterwards updates what is left (embeddings, biases, LayerNorm vectors) and
         joins the aux stream.  The result is bit-identical to a plain `step()`: same kernels on the same inputs.
         zero_grads: every update also clears the gradient range it consumed (no zero_grad() memset next step).
-        passes: encoder backward passes per step (a layer is final after the last one)."""
-        if self.engine.params.grad_wire is not None:
-            raise RuntimeError("FusedAdamW.begin_overlap: gradients come from an all-reduce (GradSync); not supported")
+        passes: encoder backward passes per step (a layer is final after the last one).
+        sync: the step's dist.GradSync (data-parallel).  The updates then follow the all-reduce of each layer bucket
+        instead of each layer's backward: the aux stream waits for the bucket's collectives and updates the bucket's
+        ranges from the reduced bf16 wire gradients while the backward of the layers below is still running; pass
+        grad_scale = 1 / world."""
         P = self.engine.params
+        if P.grad_wire is not None:
+            raise RuntimeError("FusedAdamW.begin_overlap: a previous GradSync.finish() was never consumed by step()")
         P.prepare_grads()
         self._ensure_state(frozen_plan=hp is not None)
         self._ov = {"gs": float(grad_scale), "hp": hp, "zero": bool(zero_grads), "covered": [], "seen": {},
-                    "passes": int(passes), "prev": self.engine.grad_hook, "t": self.step_count + 1, "last": None}
-        self.engine.grad_hook = self._on_layer
+                    "passes": int(passes), "prev": self.engine.grad_hook, "t": self.step_count + 1, "last": None,
+                    "sync": sync}
+        if sync is None:
+            self.engine.grad_hook = self._on_layer
+        else:
+            if zero_grads:
+                raise RuntimeError("FusedAdamW.begin_overlap: zero_grads is for fp32 gradients, not the all-reduced wire")
+            sync.bucket_hook = self._on_bucket
+
+    def _on_bucket(self, ranges, works) -> None:
+        """dist.GradSync launched the all-reduces of a layer bucket (flat `ranges`)."""
+        ov = self._ov
+        if not ov["sync"]._active():
+            return
+        eng = self.engine
+        device = eng.params.flat.device
+        wire = ov["sync"]._wire(eng.params.grad)
+        aux = eng.aux_stream(device)
+        with torch.cuda.stream(aux):
+            for w in works:
+                w.wait()                       # the aux stream waits for the collectives (not the host)
+            for r0, r1 in ranges:
+                for (a, b, decay, shadow) in self._segments:
+                    lo, hi = max(a, r0), min(b, r1)
+                    if lo < hi:
+                        self._update(lo, hi, decay, shadow, ov["t"], ov["gs"], ov["hp"], False,
+                                     wire=wire if wire is not None else None)
+                        ov["covered"].append((lo, hi))
+            done = eng.event(device, "opt.bucket.done", len(ov["covered"]))
+            done.record(aux)
+        ov["last"] = done
 
     def _on_layer(self, layer: int) -> None:
         ov = self._ov
@@ -180,7 +216,10 @@ class FusedAdamW:
         P = self.engine.params
         ov, self._ov = self._ov, None
         if ov is not None:
-            self.engine.grad_hook = ov["prev"]
+            if ov["sync"] is None:
+                self.engine.grad_hook = ov["prev"]
+            else:
+                ov["sync"].bucket_hook = None
             grad_scale, hp, zero_grads = ov["gs"], ov["hp"], ov["zero"]
         self._ensure_state(frozen_plan=hp is not None)
         if self._extra_opt is not None:

@@ -154,10 +154,71 @@ def check_contrastive(device, rank, world, per_rank=3):
             "logits_shape": list(out.logits.shape), "ranks": world}
 
 
+def check_dp_step(device, rank, world, per_rank=2, L=256, steps=3):
+    """Data-parallel optimiser step: the captured step whose AdamW updates follow each layer bucket's all-reduce on the
+    aux stream (FusedAdamW.begin_overlap(sync=...)) against the plain eager sequence backward -> GradSync.finish() ->
+    FusedAdamW.step(), from identical weights on identical batches; and the replicas stay bit-identical across ranks."""
+    from recformer_b200 import dist as rdist
+    from recformer_b200.graph import GraphedTrainStep
+    from recformer_b200.optim import FusedAdamW
+    out = []
+    batches = None
+    for mode in ("eager", "graph"):
+        model, cfg = _small_model(device)
+        model.longformer.strict_checks = False
+        model.init_item_embedding(torch.randn(cfg.item_num, 768, generator=torch.Generator().manual_seed(5)).to(device))
+        if batches is None:
+            batches = []
+            for s in range(steps + 1):
+                full = _batch(cfg, per_rank * world, L, seed=300 + s, device=device)
+                labels = torch.randint(0, cfg.item_num, (per_rank * world,), generator=torch.Generator().manual_seed(400 + s)).to(device)
+                sl = slice(rank * per_rank, (rank + 1) * per_rank)
+                b = {k: v[sl].contiguous() for k, v in full.items()}
+                b["labels"] = labels[sl].contiguous()
+                batches.append(b)
+        opt = FusedAdamW(model, lr=1e-3, weight_decay=0.01)
+        sync = rdist.GradSync(model, bucket_layers=1)
+
+        def eager(b):
+            loss = model(**b)
+            opt.zero_grad()
+            loss.backward()
+            opt.step(grad_scale=1.0 / world, wait_other=sync.finish(defer_tail=True))
+
+        eager(batches[0])
+        if mode == "eager":
+            for b in batches[1:]:
+                eager(b)
+        else:
+            step = GraphedTrainStep(model, opt, batches[0], grad_scale=1.0 / world, sync=sync)
+            assert step.dp_overlap
+            for b in batches[1:]:
+                step(b)
+            torch.cuda.synchronize()
+            del step
+        torch.cuda.synchronize()
+        model.longformer._engine.grad_hook = None
+        out.append(model.longformer._engine.params.flat.clone())
+    diff = (out[0] - out[1]).abs()
+    # replicas: every rank must hold exactly the same parameters
+    mine = out[1].clone()
+    dist.broadcast(mine, src=0)
+    same = torch.tensor([int(torch.equal(mine, out[1]))], device=device)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    t = torch.tensor([diff.mean().item(), (diff > 1e-4).float().mean().item()], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # tolerance as in tests/test_model_gpu.py::test_graphed_train_step_matches_eager_steps (atomics in the gradient sums
+    # + Adam's sign-like first steps: a wrong update rule moves every weight by ~lr)
+    return {"dp_overlapped_step_equals_plain": bool(t[0].item() < 2e-5 and t[1].item() < 0.02),
+            "replicas_bit_identical": bool(same.item()), "mean_abs_diff": float(t[0].item()),
+            "frac_diff_gt_1e-4": float(t[1].item()), "ranks": world}
+
+
 def run_checks(device, rank, world, full=False):
     res = {}
     for name, fn in (("topk", lambda: check_sharded_topk(device, rank, world)),
                      ("dp", lambda: check_dp_gradients(device, rank, world)),
+                     ("dp_step", lambda: check_dp_step(device, rank, world)),
                      ("contrastive", lambda: check_contrastive(device, rank, world))):
         try:
             res[name] = fn()
