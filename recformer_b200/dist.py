@@ -169,6 +169,9 @@ class GradSync:
             return                                        # when its lowest layer is
         n_layers = self.engine.cfg.num_hidden_layers
         g = self.engine.params.grad
+        aux_done = getattr(self.engine, "aux_done", None)
+        if aux_done is not None:        # weight gradients computed on the engine's aux stream: final before they travel
+            torch.cuda.current_stream(g.device).wait_event(aux_done)
         ranges = self.layer_ranges(layer, min(layer + self.bucket_layers, n_layers) - 1)
         works = [self._reduce_range(g, a, b) for a, b in ranges]
         self._works += works

@@ -261,12 +261,14 @@ class BackwardScratch:
         E, F, H = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
         T = B * Lp
         bf = dict(dtype=torch.bfloat16, device=device)
-        self.d_pre = torch.empty(T, E, **bf)
-        self.d_pre_drop = torch.empty(T, E, **bf)
-        self.dU = torch.empty(T, F, **bf)
+        # Everything the aux stream reads (weight-gradient GEMMs, bias column sums) exists once per LayerNorm site and
+        # layer parity: the main stream may be up to two layers ahead of the aux stream before it has to wait.
+        self.d_pre = [[torch.empty(T, E, **bf) for _ in range(2)] for _ in range(2)]         # [site][parity]
+        self.d_pre_drop = [[torch.empty(T, E, **bf) for _ in range(2)] for _ in range(2)]
+        self.dU = [torch.empty(T, F, **bf) for _ in range(2)]
         self.dh1 = torch.empty(T, E, **bf)
         self.dctx = torch.empty(T, E, **bf)
-        self.dqkv = torch.empty(T, 3 * E, **bf)
+        self.dqkv = [torch.empty(T, 3 * E, **bf) for _ in range(2)]
         self.dx = [torch.empty(T, E, **bf) for _ in range(2)]
         self.dkv = torch.empty(T, 2 * E, dtype=torch.float32, device=device)
         self.gws = ops.global_attn_bwd_ws(B, Lp, H, device)
@@ -302,6 +304,12 @@ class EncoderEngine:
         # Off by default: on a stream of the SAME priority as the main one this work delays the CTAs of the persistent
         # kernels (13.57 vs 13.35 ms per step); GraphedTrainStep captures on a high-priority stream and switches it on.
         self.overlap_aux = False
+        # RF_WGRAD_AUX=1 (experiment, with overlap_aux): the four weight-gradient GEMMs of a layer also go to the aux stream —
+        # nothing on the backward's dependency chain reads them, so they could fill the tails of the chain's kernels.
+        # Measured: no gain (13.17-13.35 vs 13.23-13.30 ms per step, SM clock 1725 vs 1800-1820 MHz): the step runs at
+        # the board's power cap, and keeping more SMs busy is paid back in clock.
+        self.wgrad_aux = os.environ.get("RF_WGRAD_AUX") is not None
+        self.aux_done = None       # latest aux-stream event of the running backward (dist.GradSync waits on it)
 
     # -- helpers -------------------------------------------------------------------------------
     def _acquire(self, B, Lp, device, per_layer) -> SavedActivations:
@@ -528,42 +536,60 @@ class EncoderEngine:
         pd = sv.drop_hidden
         aw = cfg.attention_window
         d_out = dout
+        main = torch.cuda.current_stream(device)
         use_aux = self.overlap_aux
-        dU_free = dqkv_free = None      # aux-stream events: the column sums that still read sc.dU / sc.dqkv
+        wg_aux = use_aux and self.wgrad_aux
+        aux_marks = {}                  # layer -> aux-stream event after that layer's last aux-stream kernel
+        self.aux_done = None
+
+        def on_aux(name, layer, fn):
+            self.aux_done = self.fork_aux(device, name, layer, fn)
+
         for i in reversed(range(cfg.num_hidden_layers)):
             W, G = self._layer_weights(i), self._layer_grads(i)
             x = sv.x[i]
             w_one = (aw if isinstance(aw, int) else aw[i]) // 2
+            par = i & 1
+            if aux_marks.get(i + 2) is not None:     # this parity's scratch was last read by the aux stream two layers up
+                main.wait_event(aux_marks[i + 2])
+            d_pre2, d_pre1 = sc.d_pre[0][par], sc.d_pre[1][par]
+            dY2 = sc.d_pre_drop[0][par] if pd > 0 else d_pre2
+            dY1 = sc.d_pre_drop[1][par] if pd > 0 else d_pre1
+            dU, dqkv = sc.dU[par], sc.dqkv[par]
+
+            def wgrad(name, dy, act, out, M, N):
+                fn = lambda: ops.gemm(dy, act, out=out, a_mn_major=True, b_mn_major=True, accumulate=True,
+                                      split_k=_pick_split(M, N, T))
+                if wg_aux:
+                    on_aux(name, i, fn)
+                else:
+                    fn()
+
             # ---- output block: LN2 <- dense(W2) <- gelu <- dense(W1) ----
-            dpd = sc.d_pre_drop if pd > 0 else None
-            ops.layernorm_bwd(d_out, sv.pre2[i], sv.stats2[i], W["ln2w"], G["ln2w"], G["ln2b"], dx=sc.d_pre,
-                              dx_dropped=dpd, drop_p=pd, drop_seed=self._seed(sv, i, 4), d_bias=G["b2"])
-            dY = sc.d_pre_drop if pd > 0 else sc.d_pre
-            ops.gemm(dY, sv.g[i], out=G["W2"], a_mn_major=True, b_mn_major=True, accumulate=True,
-                     split_k=_pick_split(E, F, T))
-            if dU_free is not None:
-                torch.cuda.current_stream(device).wait_event(dU_free)
-            ops.gemm(dY, W["W2"], out=sc.dU, b_mn_major=True, epi=ops.EPI_DGELU, aux=sv.u[i])
+            ops.layernorm_bwd(d_out, sv.pre2[i], sv.stats2[i], W["ln2w"], G["ln2w"], G["ln2b"], dx=d_pre2,
+                              dx_dropped=dY2 if pd > 0 else None, drop_p=pd, drop_seed=self._seed(sv, i, 4),
+                              d_bias=G["b2"])
+            wgrad("wgW2", dY2, sv.g[i], G["W2"], E, F)
+            ops.gemm(dY2, W["W2"], out=dU, b_mn_major=True, epi=ops.EPI_DGELU, aux=sv.u[i])
             if use_aux:
-                dU_free = self.fork_aux(device, "dU", i, lambda: ops.colsum(sc.dU, G["b1"]))
+                on_aux("dU", i, lambda: ops.colsum(dU, G["b1"]))
             else:
-                ops.colsum(sc.dU, G["b1"])
-            ops.gemm(sc.dU, sv.h1[i], out=G["W1"], a_mn_major=True, b_mn_major=True, accumulate=True,
-                     split_k=_pick_split(F, E, T))
-            ops.gemm(sc.dU, W["W1"], out=sc.dh1, b_mn_major=True, residual=sc.d_pre)
+                ops.colsum(dU, G["b1"])
+            wgrad("wgW1", dU, sv.h1[i], G["W1"], F, E)
+            ops.gemm(dU, W["W1"], out=sc.dh1, b_mn_major=True, residual=d_pre2)
             # ---- attention block: LN1 <- dense(Wo) <- attention <- dense(Wqkv) ----
-            ops.layernorm_bwd(sc.dh1, sv.pre1[i], sv.stats1[i], W["ln1w"], G["ln1w"], G["ln1b"], dx=sc.d_pre,
-                              dx_dropped=dpd, drop_p=pd, drop_seed=self._seed(sv, i, 3), d_bias=G["bo"])
-            ops.gemm(dY, sv.ctx[i], out=G["Wo"], a_mn_major=True, b_mn_major=True, accumulate=True,
-                     split_k=_pick_split(E, E, T))
-            ops.gemm(dY, W["Wo"], out=sc.dctx, b_mn_major=True)
+            ops.layernorm_bwd(sc.dh1, sv.pre1[i], sv.stats1[i], W["ln1w"], G["ln1w"], G["ln1b"], dx=d_pre1,
+                              dx_dropped=dY1 if pd > 0 else None, drop_p=pd, drop_seed=self._seed(sv, i, 3),
+                              d_bias=G["bo"])
+            wgrad("wgWo", dY1, sv.ctx[i], G["Wo"], E, E)
+            ops.gemm(dY1, W["Wo"], out=sc.dctx, b_mn_major=True)
             gargs = (x, mask, W["Wqg"], W["bqg"], W["Wkg"], W["Wvg"], W["bvg"], B, Lp, H)
             if self._debug_skip_global:
                 pass
             elif self.overlap_global:
                 # weight-gradient half of the global row's backward (needs dctx, not dx) on the side stream,
                 # concurrently with the band-attention backward and the QKV wgrad / dgrad GEMMs
-                main, side = torch.cuda.current_stream(device), self.side_stream(device)
+                side = self.side_stream(device)
                 ev_d, ev_a = self.event(device, "dctx", i), self.event(device, "gA", i)
                 ev_d.record(main)
                 side.wait_event(ev_d)
@@ -573,24 +599,21 @@ class EncoderEngine:
                     if sc.xk is not None and not self._debug_no_xk:
                         ops.global_attn_bwd_xk(*gargs, sv.glob[i], sc.gws, *sc.xk)
                     ev_a.record(side)
-            if dqkv_free is not None:
-                torch.cuda.current_stream(device).wait_event(dqkv_free)
-            ops.band_attn_bwd(sv.qkv[i], mask, B, Lp, H, w_one, sv.ctx[i], sv.lse[i], sc.dctx, sc.dqkv, sc.dkv,
+            ops.band_attn_bwd(sv.qkv[i], mask, B, Lp, H, w_one, sv.ctx[i], sv.lse[i], sc.dctx, dqkv, sc.dkv,
                               drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 1), ws=self.attn_ws(B, Lp, w_one, device))
             if use_aux:
-                dqkv_free = self.fork_aux(device, "dqkv", i, lambda: ops.colsum(sc.dqkv, G["bqkv"]))
+                on_aux("dqkv", i, lambda: ops.colsum(dqkv, G["bqkv"]))
             else:
-                ops.colsum(sc.dqkv, G["bqkv"])
-            ops.gemm(sc.dqkv, x, out=G["Wqkv"], a_mn_major=True, b_mn_major=True, accumulate=True,
-                     split_k=_pick_split(3 * E, E, T))
+                ops.colsum(dqkv, G["bqkv"])
+            wgrad("wgWqkv", dqkv, x, G["Wqkv"], 3 * E, E)
             dx = sc.dx[i % 2]
             fused_dx = self.overlap_global and sc.xk is not None and not self._debug_skip_global and not self._debug_no_xk
             if fused_dx:
                 # the CLS row's token gradients ride on the dgrad GEMM as one extra per-sequence k-block
                 main.wait_event(ev_a)
-                ops.gemm(sc.dqkv, W["Wqkv"], out=dx, b_mn_major=True, residual=sc.d_pre, xk=(*sc.xk, Lp))
+                ops.gemm(dqkv, W["Wqkv"], out=dx, b_mn_major=True, residual=d_pre1, xk=(*sc.xk, Lp))
             else:
-                ops.gemm(sc.dqkv, W["Wqkv"], out=dx, b_mn_major=True, residual=sc.d_pre)
+                ops.gemm(dqkv, W["Wqkv"], out=dx, b_mn_major=True, residual=d_pre1)
             if self._debug_skip_global or fused_dx:
                 pass
             elif self.overlap_global:
@@ -601,11 +624,11 @@ class EncoderEngine:
                 ops.global_attn_bwd(*gargs, sc.dctx, sv.glob[i], dx, G["Wqg"], G["bqg"], G["Wkg"], G["Wvg"], G["bvg"],
                                     ws=sc.gws, drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 2))
             d_out = dx
+            aux_marks[i] = self.aux_done
             if self.grad_hook is not None:
                 self.grad_hook(i)
-        for ev in (dU_free, dqkv_free):       # join the aux stream: the bias gradients are final when backward() returns
-            if ev is not None:
-                torch.cuda.current_stream(device).wait_event(ev)
+        if self.aux_done is not None:         # join the aux stream: every gradient is final when backward() returns
+            main.wait_event(self.aux_done)
         e = "embeddings."
         named = P._named
         gview = lambda k: P.view(k, P.grad) if named[k].requires_grad else None

@@ -1,16 +1,11 @@
 #!/bin/bash
 cd /root/repo; mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_kernels_gpu.py -q -p no:cacheprovider --tb=short -k "topk or candidate or cosine or score" 2>&1 | tail -4 | cut -c1-300
-timeout 900 python -m pytest tests/test_model_gpu.py -q -p no:cacheprovider --tb=short -k "recall" 2>&1 | tail -2 | cut -c1-300
-for ni in 31250 125000 250000 1000000; do
-RF_PROF_ITEMS=$ni timeout 300 python tools/prof_kernels.py score_topk 2>&1 | tail -1 | sed "s/score_topk/items_$ni/"
-done
-RF_PROF_ITEMS=125000 timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none --csv --log-file gpurun_out/score_launches.csv python tools/prof_kernels.py score_topk > /dev/null 2>&1
-python - <<'PY'
-import csv
-rows=list(csv.reader(open('gpurun_out/score_launches.csv',errors='replace')))
-h=[i for i,r in enumerate(rows) if 'Kernel Name' in r][0]
-kn,mn,mv=rows[h].index('Kernel Name'),rows[h].index('Metric Name'),rows[h].index('Metric Value')
-for r in rows[h+1:][-8:]:
-    if len(r)>mv: print(r[kn].split('(')[0][-50:], r[mn], r[mv])
-PY
+timeout 900 python -m pytest tests/test_model_gpu.py tests/test_dropin_gpu.py tests/test_dropout_gpu.py -q -p no:cacheprovider --tb=short -x 2>&1 | tail -4 | cut -c1-400
+run() { # name, env...
+  name=$1; shift
+  env "$@" timeout 600 python bench.py --steps 20 --warmup 5 --no-extras --no-cpu-baseline --no-secondary > gpurun_out/q_$name.log 2> gpurun_out/q_$name.err; tail -1 gpurun_out/q_$name.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$name', round(d['value'],1), round(d['ms_per_step'],3), round(d['e2e']['value'],1), d['clocks']['sm_mhz'], round(d['roofline']['frac'],3))"
+}
+run wg_main RF_DEBUG_NO_WGRAD_AUX=1
+run wg_aux A=1
+run wg_main2 RF_DEBUG_NO_WGRAD_AUX=1
+run wg_aux2 A=1

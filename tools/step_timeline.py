@@ -10,7 +10,9 @@ import torch
 import bench
 from recformer_b200.optim import FusedAdamW
 
-steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+graph = "--graph" in sys.argv
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+steps = int(args[0]) if args else 2
 dev = torch.device("cuda", 0)
 model, cfg = bench.build_model(dev)
 model.train()
@@ -20,9 +22,18 @@ for w in range(4):
     bench.train_step(model, opt, batches[w % 2], 1)
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
+if graph:      # the captured step the bench times (python tools/step_timeline.py 2 --graph)
+    from recformer_b200.graph import GraphedTrainStep
+    gstep = GraphedTrainStep(model, opt, batches[0])
+    for w in range(3):
+        gstep(batches[w % 2])
+    torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for i in range(steps):
-        bench.train_step(model, opt, batches[i % 2], 1)
+        if graph:
+            gstep(batches[i % 2])
+        else:
+            bench.train_step(model, opt, batches[i % 2], 1)
     torch.cuda.synchronize()
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 ks = []
