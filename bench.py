@@ -312,8 +312,21 @@ def eval_topk_bench(model, device, rank, world, steps, warmup, cpu_leg):
     # labels: even users get one of the scorer's own top-10 items -- the rank (1..8) whose score is best separated from
     # both neighbours, so that the fp32 CPU leg (which ranks the un-rounded fp32 table) agrees on it --, odd users a
     # uniform item (rank ~ N/2): Recall@10 = 0.5
+    # multi-GPU: the exchange of the per-rank top-k is fused into the scorer (peer-memory stores + one symmetric-memory
+    # barrier, recformer_b200.dist.PeerTopkExchange); RF_BENCH_NCCL_TOPK=1, or a box without symmetric memory, uses
+    # the NCCL all-gather path
+    exchange, exchange_kind = None, "single GPU"
+    if world > 1:
+        exchange_kind = "NCCL all-gather + merge"
+        if os.environ.get("RF_BENCH_NCCL_TOPK") is None:
+            try:
+                exchange = rdist.PeerTopkExchange(EVAL_USERS, K, device)
+                exchange_kind = "peer-memory stores from the scorer's merge kernel + symmetric-memory barrier + merge"
+            except Exception as ex:
+                sys.stderr.write(f"[bench] PeerTopkExchange unavailable ({ex!r}); using the NCCL all-gather\n")
+
     def topk(pooled, labels):
-        return rdist.sharded_topk(model, pooled, k=K, labels=labels, id_base=lo)
+        return rdist.sharded_topk(model, pooled, k=K, labels=labels, id_base=lo, exchange=exchange)
     rows = torch.arange(EVAL_USERS, device=device)
     labels_dev = []
     for u in users_dev:
@@ -367,7 +380,7 @@ def eval_topk_bench(model, device, rank, world, steps, warmup, cpu_leg):
            "n_gpus": world, "steps": steps, "ms_per_pass": ms / steps, "gpu_launches": int(launches),
            "config": {"workload": f"BASELINE configs[3]: 4096 users x 1M items (fp32 table -> L2-normalised bf16, {hi - lo} rows "
                                   f"on this rank, sharded by item id over {world} GPU(s)), cosine/temp top-10 + label score"
-                                  + (", NCCL all-gather + merge" if world > 1 else ""),
+                                  + (", " + exchange_kind if world > 1 else ""),
                       "l2": f"table shard {(hi - lo) * E * 2 / 1e6:.0f} MB bf16 > 126 MB L2; 3 rotating user sets"},
            "e2e": {"value": EVAL_USERS * steps / (ms_e2e / 1e3), "unit": "users/s", "ms_per_pass": ms_e2e / steps,
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -266,6 +266,16 @@ int rf_cosine_topk(const void* xn_bf16, const void* yn_bf16, int B, long long N,
 int rf_cosine_topk_packed(const void* xn_bf16, const void* yn_bf16, int B, long long N, int E, float temp, int k,
                           int id_base, const int64_t* labels_or_null, float* packed, void* ws, rf_stream_t stream);
 /* Merge of `parts` packed buffers [parts, B, 2k+1] (the all-gather result) into the global top-k. */
+/* rf_cosine_topk_packed whose result is not written locally but STORED INTO EVERY RANK'S gathered buffer over NVLink peer
+ * memory — the all-gather of sharded scoring (ref: finetune.py:66-96 scores one table on one GPU; SURVEY.md §8e shards it)
+ * fused into the merge kernel's epilogue.  peer_gathered[r] (host array of `world` device addresses, r = 0..world-1) is
+ * rank r's (world, B, 2k+1) fp32 buffer as mapped into THIS process (torch symmetric memory `buffer_ptrs`, CUDA IPC or any
+ * other peer mapping); this rank's rows go to block `rank` of each.  The caller synchronises the ranks afterwards (a
+ * symmetric-memory barrier on the same stream) and runs rf_topk_merge_packed on its own gathered buffer.  2k+1 <= 32. */
+#define RF_MAX_PEERS 16
+int rf_cosine_topk_bcast(const void* xn_bf16, const void* yn_bf16, int B, long long N, int E, float temp, int k,
+                         int id_base, const int64_t* labels_or_null, const unsigned long long* peer_gathered, int world,
+                         int rank, void* workspace, rf_stream_t stream);
 int rf_topk_merge_packed(const float* packed, int parts, int B, int k, float* out_scores, int32_t* out_ids,
                          float* out_label_score, rf_stream_t stream);
 /* Merge `parts` lists of k (score,id) per user (e.g. the all-gathered per-GPU top-k) into the

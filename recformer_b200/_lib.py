@@ -81,6 +81,8 @@ _SIGS = {
                                c_void_p, c_void_p, c_void_p, c_void_p]),
     "rf_cosine_topk_packed": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p]),
+    "rf_cosine_topk_bcast": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_int, c_int, c_void_p, c_void_p,
+                                     c_int, c_int, c_void_p, c_void_p]),
     "rf_topk_merge_packed": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rf_topk_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p]),

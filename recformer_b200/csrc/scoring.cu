@@ -546,11 +546,20 @@ cosine_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // label_scores[s * B + b] for the dense layout, at [s * in_part_stride + b * in_ld] for packed rows); outputs with row
 // strides out_ld / out_label_ld.  Dense [parts][B][k]: in_ld = k, in_part_stride = B * k; a packed (B, 2k+1) row =
 // k scores | k ids | label.
+// Fan-out of the merged rows into the symmetric "gathered" buffers of all ranks (rf_cosine_topk_bcast): base[r] is
+// rank r's (world, B, 2k+1) buffer mapped into this process (NVLink peer memory), slot = this rank's (B, 2k+1) block in it.
+struct MergeFanout {
+  float* base[RF_MAX_PEERS];
+  int n;
+  long long slot;      // element offset of this rank's block
+};
+
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const float* __restrict__ scores, const int32_t* __restrict__ ids,
                   const float* __restrict__ label_scores, int parts, int B, int k,
                   float* __restrict__ out_scores, int32_t* __restrict__ out_ids,
-                  float* __restrict__ out_label, int in_ld, int in_part_stride, int out_ld, int out_label_ld) {
+                  float* __restrict__ out_label, int in_ld, int in_part_stride, int out_ld, int out_label_ld,
+                  const MergeFanout fan = MergeFanout{}) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= B) return;                                   // warp-uniform
@@ -584,19 +593,27 @@ topk_merge_kernel(const float* __restrict__ scores, const int32_t* __restrict__ 
       }
     }
   }
+  float lab = -INFINITY;
+  if (label_scores != nullptr)
+    for (int sp = lane; sp < parts; sp += 32)
+      lab = fmaxf(lab, in_ld == k ? label_scores[static_cast<size_t>(sp) * B + b]
+                                  : label_scores[static_cast<size_t>(sp) * in_part_stride + static_cast<size_t>(b) * in_ld]);
+  lab = warp_max(lab);
+  if (fan.n > 0) {
+    // one packed row (k scores | k ids | label score) per user, stored straight into every rank's gathered buffer:
+    // lane q < k carries score q, lane k + q id q, lane 2k the label score — one coalesced (2k+1)-word store per peer
+    const int ld = 2 * k + 1;
+    const float id_bits = __int_as_float(__shfl_sync(0xffffffffu, ti, lane >= k ? lane - k : 0));
+    const float word = lane < k ? ts : (lane < 2 * k ? id_bits : lab);
+    if (lane < ld)
+      for (int r = 0; r < fan.n; ++r) fan.base[r][fan.slot + static_cast<long long>(b) * ld + lane] = word;
+    return;
+  }
   if (lane < k) {
     out_scores[static_cast<size_t>(b) * out_ld + lane] = ts;
     out_ids[static_cast<size_t>(b) * out_ld + lane] = ti;
   }
-  if (out_label != nullptr) {
-    float lab = -INFINITY;
-    if (label_scores != nullptr)
-      for (int sp = lane; sp < parts; sp += 32)
-        lab = fmaxf(lab, in_ld == k ? label_scores[static_cast<size_t>(sp) * B + b]
-                                    : label_scores[static_cast<size_t>(sp) * in_part_stride + static_cast<size_t>(b) * in_ld]);
-    lab = warp_max(lab);
-    if (lane == 0) out_label[static_cast<size_t>(b) * out_label_ld] = lab;
-  }
+  if (out_label != nullptr && lane == 0) out_label[static_cast<size_t>(b) * out_label_ld] = lab;
 }
 
 // y[n,:] = x[n,:] / max(|x[n,:]|, 1e-8) as bf16; one warp per row (E = 768).
@@ -951,26 +968,10 @@ extern "C" long long rf_cosine_topk_ws_bytes(int B, long long N, int k) {
   return parts * B * (static_cast<long long>(k) * 8 + 4) + (static_cast<long long>(B) + 1) * 4 + 256;
 }
 
-// seed the shared thresholds with the k-th best score of a merged top-k (here: of the first SEED_ITEMS items)
-__global__ void topk_seed_threshold_kernel(const float* __restrict__ scores, int B, int k, int ld, unsigned int* __restrict__ thr) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const float s = scores[static_cast<size_t>(b) * ld + k - 1];
-  thr[b] = (s > -INFINITY) ? f2ord(s) : 0u;
-}
-
-// Threshold seeding (8-GPU sharding makes the per-GPU table short: a 125k-item shard is swept by ~9 parts that each
-// see ~14k items per row, and a list that young takes a hit in nearly every 32-column chunk of a warp).  A cheap
-// pre-pass finds the exact top-k of the first SEED_ITEMS items (the same kernels on a 16-tile table, ~25 us) and
-// publishes its k-th best score as every row's initial shared threshold: the main sweep then starts with a top-
-// (k / SEED_ITEMS) quantile threshold instead of -inf.  Exact: the k-th best of a subset never exceeds the global one.
-constexpr long long SC_SEED_ITEMS = 4096;
-constexpr long long SC_SEED_MIN_N = 16 * SC_SEED_ITEMS;
-
 static int cosine_topk_impl(const void* xn, const void* yn, int B, long long N, int E, float temp, int k, int id_base,
                             const int64_t* labels, float* topk_scores, int32_t* topk_ids, float* label_score, int out_ld,
-                            int label_ld, void* ws, cudaStream_t stream) {
-  RF_REQUIRE(xn && yn && topk_scores && topk_ids && ws && B > 0 && N > 0, "rf_cosine_topk: bad argument");
+                            int label_ld, void* ws, cudaStream_t stream, const MergeFanout* fan = nullptr) {
+  RF_REQUIRE(xn && yn && topk_scores && (topk_ids || fan) && ws && B > 0 && N > 0, "rf_cosine_topk: bad argument");
   RF_REQUIRE(static_cast<long long>(B) * (2 * k + 1) < 2147483647ll, "rf_cosine_topk: B * k too large");
   RF_REQUIRE(k >= 1 && k <= SC_MAXK, "rf_cosine_topk: k=%d out of range [1,%d]", k, SC_MAXK);
   RF_REQUIRE(E % 8 == 0, "rf_cosine_topk: E must be a multiple of 8");
@@ -987,36 +988,16 @@ static int cosine_topk_impl(const void* xn, const void* yn, int B, long long N, 
   // this NaN pattern, which the merge skips
   p.ws_thr = reinterpret_cast<unsigned int*>(p.ws_label + static_cast<size_t>(parts) * B);
   RF_CUDA(cudaMemsetAsync(p.ws_thr, 0, (static_cast<size_t>(B) + 1) * 4, stream));     // 0 = no threshold published yet
+  // (Seeding the shared thresholds from a pre-pass over the first 4096 items was measured: the pre-pass costs 88 us and
+  // the main sweep gains nothing, because with 32 rows per warp a chunk is only skipped once the threshold sits near the
+  // 1e-4 quantile.)
   int rc;
-  // Measured (4096 users; 125k / 250k / 1M items): the pre-pass costs 88 us and the main sweep gains nothing — the
-  // shard's deficit was the serial merge kernel (106 us) and a fixed ~140 us, not list warm-up — so seeding is OFF unless
-  // RF_SCORE_SEED=1 asks for it.
-  static const bool seed = getenv("RF_SCORE_SEED") != nullptr;
-  if (N >= SC_SEED_MIN_N && seed) {
-    // pre-pass over the first SEED_ITEMS items; its merged top-k lands in the caller's output buffers (overwritten by
-    // the real result below), its k-th best score seeds ws_thr
-    ScoreParams q{};
-    q.B = B; q.N = SC_SEED_ITEMS; q.K = E; q.inv_temp = p.inv_temp; q.k = k; q.id_base = id_base;
-    const int qparts = 2 * plan_schedule(B, SC_SEED_ITEMS, &q);
-    RF_REQUIRE(qparts <= parts, "rf_cosine_topk: internal: seed pass needs more parts than the main pass");
-    const size_t qcnt = static_cast<size_t>(qparts) * B * k;
-    q.ws_scores = reinterpret_cast<float*>(ws);
-    q.ws_ids = reinterpret_cast<int32_t*>(q.ws_scores + qcnt);
-    q.ws_label = reinterpret_cast<float*>(q.ws_ids + qcnt);
-    q.ws_thr = p.ws_thr;
-    RF_CUDA(cudaMemsetAsync(ws, 0xFF, qcnt * 8 + static_cast<size_t>(qparts) * B * 4, stream));
-    if ((rc = launch_cosine(SC_TOPK, xn, yn, q, stream))) return rc;
-    topk_merge_kernel<<<(B + 7) / 8, 256, 0, stream>>>(q.ws_scores, q.ws_ids, nullptr, qparts, B, k, topk_scores,
-                                                          topk_ids, nullptr, k, B * k, out_ld, label_ld);
-    if ((rc = check_launch("rf_cosine_topk/seed-merge"))) return rc;
-    topk_seed_threshold_kernel<<<(B + 127) / 128, 128, 0, stream>>>(topk_scores, B, k, out_ld, p.ws_thr);
-    if ((rc = check_launch("rf_cosine_topk/seed"))) return rc;
-  }
   RF_CUDA(cudaMemsetAsync(ws, 0xFF, cnt * 8 + static_cast<size_t>(parts) * B * 4, stream));
   rc = launch_cosine(SC_TOPK, xn, yn, p, stream);
   if (rc) return rc;
   topk_merge_kernel<<<(B + 7) / 8, 256, 0, stream>>>(p.ws_scores, p.ws_ids, p.ws_label, parts, B, k, topk_scores,
-                                                        topk_ids, label_score, k, B * k, out_ld, label_ld);
+                                                        topk_ids, label_score, k, B * k, out_ld, label_ld,
+                                                        fan ? *fan : MergeFanout{});
   return check_launch("rf_cosine_topk/merge");
 }
 
@@ -1034,6 +1015,24 @@ extern "C" int rf_cosine_topk_packed(const void* xn, const void* yn, int B, long
   const int ld = 2 * k + 1;
   return cosine_topk_impl(xn, yn, B, N, E, temp, k, id_base, labels, packed, reinterpret_cast<int32_t*>(packed) + k,
                           packed + 2 * k, ld, ld, ws, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int rf_cosine_topk_bcast(const void* xn, const void* yn, int B, long long N, int E, float temp, int k,
+                                    int id_base, const int64_t* labels, const unsigned long long* peer_gathered, int world,
+                                    int rank, void* ws, rf_stream_t stream_) {
+  RF_REQUIRE(peer_gathered && world >= 1 && world <= RF_MAX_PEERS && rank >= 0 && rank < world,
+             "rf_cosine_topk_bcast: bad peer list (world=%d, rank=%d, at most %d peers)", world, rank, RF_MAX_PEERS);
+  RF_REQUIRE(2 * k + 1 <= 32, "rf_cosine_topk_bcast: k=%d too large for one packed row per warp", k);
+  MergeFanout fan{};
+  fan.n = world;
+  fan.slot = static_cast<long long>(rank) * B * (2 * k + 1);
+  for (int r = 0; r < world; ++r) {
+    RF_REQUIRE(peer_gathered[r] != 0 && (peer_gathered[r] & 3) == 0, "rf_cosine_topk_bcast: null / misaligned peer buffer %d", r);
+    fan.base[r] = reinterpret_cast<float*>(static_cast<uintptr_t>(peer_gathered[r]));
+  }
+  // the merged rows never land in a local (B, 2k+1) buffer: the merge kernel's only stores are the peer stores
+  return cosine_topk_impl(xn, yn, B, N, E, temp, k, id_base, labels, fan.base[rank], nullptr, nullptr, 2 * k + 1, 2 * k + 1,
+                          ws, reinterpret_cast<cudaStream_t>(stream_), &fan);
 }
 
 extern "C" int rf_topk_merge_packed(const float* packed, int parts, int B, int k, float* out_scores, int32_t* out_ids,

@@ -56,7 +56,7 @@ def all_gather_topk(scores, ids, label_score, group=None):
 
 
 def sharded_topk(model, pooled: torch.Tensor, k: int = 10, labels: Optional[torch.Tensor] = None,
-                 id_base: int = 0, group=None):
+                 id_base: int = 0, group=None, exchange: Optional["PeerTopkExchange"] = None):
     """Global top-k when `model.item_embedding` holds only this rank's shard (ids offset by
     id_base).  Three launches + one collective: the fused scorer writes this rank's packed (B, 2k+1) result
     (rf_cosine_topk_packed), ONE all-gather exchanges it, rf_topk_merge_packed reads the gathered buffer in place;
@@ -64,12 +64,56 @@ def sharded_topk(model, pooled: torch.Tensor, k: int = 10, labels: Optional[torc
     from . import ops
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return model.topk(pooled, k=k, labels=labels, id_base=id_base)
+    if exchange is not None:      # peer-memory exchange fused into the scorer (see PeerTopkExchange)
+        return exchange.topk(model, pooled, labels=labels, id_base=id_base)
     xn = ops.normalize_rows(pooled.contiguous())
     packed = ops.cosine_topk_packed(xn, model.normalized_items(), model.config.temp, k=k, id_base=id_base, labels=labels)
     world = dist.get_world_size(group)
     out = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
     dist.all_gather_into_tensor(out.view(-1), packed.view(-1), group=group)
     return ops.topk_merge_packed(out, k)
+
+
+class PeerTopkExchange:
+    """The all-gather of sharded scoring fused into the scorer: every rank owns a symmetric (world, B, 2k+1) buffer (torch
+    symmetric memory: each rank's allocation is mapped into every process of the node over NVLink / NVSwitch); the merge
+    kernel that finishes a rank's shard stores its packed rows straight into block `rank` of ALL ranks' buffers
+    (rf_cosine_topk_bcast), one symmetric-memory barrier publishes them, and rf_topk_merge_packed reads the local
+    buffer.  No pack kernel, no NCCL launch: scorer -> barrier -> merge.  Two buffers alternate, so a pass may overwrite
+    the buffer of the pass before last without a second barrier (every rank has passed the barrier in between, i.e. has
+    merged the older one).
+
+        ex = PeerTopkExchange(B, k, device)          # collective: every rank of the group calls it
+        scores, ids, label_scores = ex.topk(model, pooled, labels=labels, id_base=lo)
+    """
+
+    def __init__(self, B: int, k: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.B, self.k = B, k
+        self.bufs, self.handles = [], []
+        for _ in range(2):
+            t = symm_mem.empty(self.world * B * (2 * k + 1), dtype=torch.float32, device=device)
+            h = symm_mem.rendezvous(t, self.group)
+            self.bufs.append(t.view(self.world, B, 2 * k + 1))
+            self.handles.append(h)
+        self.peer_ptrs = [[int(p) for p in h.buffer_ptrs] for h in self.handles]
+        self._pass = 0
+        self._ws = None
+
+    def topk(self, model, pooled: torch.Tensor, labels: Optional[torch.Tensor] = None, id_base: int = 0):
+        from . import ops
+        if pooled.shape[0] != self.B:
+            raise ValueError(f"PeerTopkExchange was built for {self.B} users, got {pooled.shape[0]}")
+        j = self._pass & 1
+        self._pass += 1
+        xn = ops.normalize_rows(pooled.contiguous())
+        self._ws = ops.cosine_topk_bcast(xn, model.normalized_items(), model.config.temp, self.peer_ptrs[j], self.rank,
+                                         k=self.k, id_base=id_base, labels=labels, ws=self._ws)
+        self.handles[j].barrier(channel=j)          # on the current stream: all ranks' rows have landed everywhere
+        return ops.topk_merge_packed(self.bufs[j], self.k)
 
 
 def allreduce_gradients(model, group=None, average: bool = True) -> None:

@@ -305,6 +305,22 @@ def cosine_topk_packed(xn, yn, temp, k=10, id_base=0, labels=None, ws=None, out=
     return out
 
 
+def cosine_topk_bcast(xn, yn, temp, peer_ptrs, rank, k=10, id_base=0, labels=None, ws=None):
+    """cosine_topk_packed whose merged rows are stored into block `rank` of EVERY rank's gathered (world, B, 2k+1) buffer
+    (peer_ptrs: their device addresses as mapped into this process, e.g. symmetric-memory buffer_ptrs)."""
+    _req(xn, torch.bfloat16, "xn"), _req(yn, torch.bfloat16, "yn")
+    B, N = xn.shape[0], yn.shape[0]
+    nbytes = int(_lib.lib().rf_cosine_topk_ws_bytes(B, N, k))
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=xn.device)
+    if labels is not None:
+        _req(labels, torch.int64, "labels")
+    arr = (C.c_ulonglong * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    check(_lib.lib().rf_cosine_topk_bcast(xn.data_ptr(), yn.data_ptr(), B, N, xn.shape[1], temp, k, id_base, _ptr(labels),
+                                          arr, len(peer_ptrs), rank, ws.data_ptr(), _stream()), "rf_cosine_topk_bcast")
+    return ws
+
+
 def topk_merge_packed(packed, k):
     """packed: [parts, B, 2k+1] (all-gathered cosine_topk_packed buffers) -> (scores [B,k], ids [B,k], label [B])."""
     _req(packed, torch.float32, "packed")

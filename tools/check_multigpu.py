@@ -56,11 +56,30 @@ def check_sharded_topk(device, rank, world, users=512, items=200_000, k=10):
     dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1))
     ps, pi, pl = ops.topk_merge_packed(gathered, k)
     same_packed = torch.equal(ps, ms) and torch.equal(pi, mi) and torch.equal(pl, ml)
+    # the fused exchange: the scorer's merge kernel stores into every rank's symmetric buffer, barrier, merge
+    peer = {"peer_exchange": "unavailable"}
+    try:
+        ex = rdist.PeerTopkExchange(users, k, device)
+        same_peer = True
+        for _ in range(3):            # three passes: both buffers, and a reuse
+            ex._ws = ops.cosine_topk_bcast(xn, shard, 0.05, ex.peer_ptrs[ex._pass & 1], rank, k=k, id_base=lo, labels=labels,
+                                           ws=ex._ws)
+            j = ex._pass & 1
+            ex._pass += 1
+            ex.handles[j].barrier(channel=j)
+            es, ei, el = ops.topk_merge_packed(ex.bufs[j], k)
+            same_peer = same_peer and torch.equal(es, ms) and torch.equal(ei, mi) and torch.equal(el, ml)
+        peer = {"peer_exchange_equals_nccl": bool(same_peer)}
+    except Exception as exn:
+        peer = {"peer_exchange_error": repr(exn)[:200]}
     full = build_table(0, items, rows, E, device)
     ts, ti, tl = ops.cosine_topk(xn, full, 0.05, k=k, labels=labels)
-    ok = torch.tensor([int(same_packed and torch.equal(ms, ts) and torch.equal(mi, ti) and torch.equal(ml, tl))], device=device)
+    ok = torch.tensor([int(same_packed and torch.equal(ms, ts) and torch.equal(mi, ti) and torch.equal(ml, tl)),
+                       int(peer.get("peer_exchange_equals_nccl", True))], device=device)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-    return {"sharded_topk_equals_unsharded": bool(ok.item()), "users": users, "items": items, "ranks": world}
+    if "peer_exchange_equals_nccl" in peer:
+        peer["peer_exchange_equals_nccl"] = bool(ok[1].item())
+    return {"sharded_topk_equals_unsharded": bool(ok[0].item()), "users": users, "items": items, "ranks": world, **peer}
 
 
 def _small_model(device, pretraining=False, init_range=0.02):
