@@ -41,6 +41,11 @@ for e in ev:
     tr = e.time_range
     ks.append((tr.start, tr.end, e.name, getattr(e, "device_index", 0), getattr(e, "stream", None)))
 ks.sort()
+if "--dump" in sys.argv:     # every device event (start us, duration us, name) for offline reading
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/timeline_events.tsv", "w") as f:
+        for s_, e_, n_, *_ in ks:
+            f.write(f"{s_ - ks[0][0]:.2f}\t{e_ - s_:.2f}\t{n_[:90]}\n")
 t0, t1 = ks[0][0], max(k[1] for k in ks)
 print(f"{len(ks)} device events over {(t1 - t0) / 1e3:.3f} ms ({steps} steps -> {(t1 - t0) / 1e3 / steps:.3f} ms/step)")
 # union busy time
