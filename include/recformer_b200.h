@@ -102,6 +102,22 @@ int rf_prepare_inputs(const int64_t* input_ids, const int64_t* attention_mask, c
                       rf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Padding-aware execution.  The reference runs every layer over all B*L positions of a right-padded batch
+ * (ref: recformer/tokenization.py:110-152 pads to the batch maximum, ref: recformer/models.py:274-356 computes them);
+ * what it computes on padded positions never reaches a real token (keys are masked, everything else is row-wise) and
+ * their gradients are exactly zero.  rf_row_tile_flags marks the 256-row tiles of the token axis that hold at least one
+ * real token (L % 256 == 0) and lists the 128-row attention query tiles inside them; rf_set_row_activity makes that
+ * the launch context of the CALLING THREAD: until it is cleared (tile_flags = NULL), rf_gemm_bf16 (CTA-pair kernel with
+ * M == rows, or the weight-gradient layout with K == rows), rf_layernorm_fwd/bwd, rf_colsum_bf16, rf_embed_ln_fwd/bwd
+ * and rf_band_attn_fwd/bwd launched with a matching row count skip the padding-only tiles (outputs of skipped rows are
+ * left untouched; reductions over rows leave them out).  Results on real tokens are unchanged.
+ * ------------------------------------------------------------------------------------------ */
+int rf_row_tile_flags(const uint8_t* mask012, int B, int L, uint8_t* tile_flags /* [B*L/256] */,
+                      int32_t* qtile_list /* [B*L/128] */, int32_t* n_qtiles /* [1] */, rf_stream_t stream);
+int rf_set_row_activity(const uint8_t* tile_flags_or_null, long long rows, const int32_t* qtile_list,
+                        const int32_t* n_qtiles);
+
+/* ------------------------------------------------------------------------------------------
  * RecformerEmbeddings (ref: recformer/models.py:108-138): 4-table gather-sum, LayerNorm,
  * dropout — one kernel, one warp per token, 128-bit loads, warp-shuffle statistics.
  *   out[t,:] = dropout(LN(word[ids[t]] + pos[pid[t]] + type[tt[t]] + item[ip[t]]))   (bf16)

@@ -52,6 +52,8 @@ _SIGS = {
     "rf_gemm_bf16": (c_int, [P(GemmArgs), c_void_p]),
     "rf_prepare_inputs": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
+    "rf_row_tile_flags": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rf_set_row_activity": (c_int, [c_void_p, c_ll, c_void_p, c_void_p]),
     "rf_embed_ln_fwd": (c_int, [P(EmbedArgs), c_void_p, c_void_p, c_void_p, c_void_p]),
     "rf_embed_ln_bwd": (c_int, [P(EmbedArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),

@@ -44,6 +44,10 @@ bool first_use_on_device(std::atomic<unsigned long long>* seen) {
   return (seen->fetch_or(bit) & bit) == 0;
 }
 
+static thread_local RowActivity g_activity{nullptr, 0, nullptr, nullptr};
+const RowActivity& row_activity() { return g_activity; }
+void set_row_activity(const RowActivity& a) { g_activity = a; }
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -165,4 +169,17 @@ int rf_set_dropout_nonce(const unsigned long long* nonce_dev, rf_stream_t stream
   }
   return RF_OK;
 }
+}
+
+namespace rf { void set_row_activity(const RowActivity& a); }
+
+extern "C" int rf_set_row_activity(const uint8_t* tile_flags, long long rows, const int32_t* qtile_list,
+                                   const int32_t* n_qtiles) {
+  if (tile_flags == nullptr) {
+    rf::set_row_activity(rf::RowActivity{nullptr, 0, nullptr, nullptr});
+    return RF_OK;
+  }
+  RF_REQUIRE(rows > 0 && rows % 256 == 0 && qtile_list && n_qtiles, "rf_set_row_activity: rows must be a positive multiple of 256");
+  rf::set_row_activity(rf::RowActivity{tile_flags, rows, qtile_list, n_qtiles});
+  return RF_OK;
 }

@@ -62,6 +62,9 @@ struct AttnBwdParams {
   float drop_scale;
   uint32_t drop_thresh;
   uint64_t drop_seed;
+  // row activity (rf_set_row_activity): the persistent CTAs walk the compact list of active query tiles x heads
+  const int32_t* qtiles;      // [n] entries b * tiles_per_seq + tile, or null = every tile
+  const int32_t* n_qtiles;    // device scalar n
 };
 
 __global__ void __launch_bounds__(AB_THREADS)
@@ -90,7 +93,20 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, part = warp >> 2;
   const int tiles_per_seq = (p.L + 127) / 128;
-  const int total_tiles = p.B * p.H * tiles_per_seq;
+  const int total_tiles = p.qtiles != nullptr ? *p.n_qtiles * p.H : p.B * p.H * tiles_per_seq;
+  // work item t -> (sequence b, head h, query tile): dense enumeration, or through the list of active query tiles
+  auto decode = [&](int t, int& tile, int& h, int& b) {
+    if (p.qtiles != nullptr) {
+      const int q = p.qtiles[t / p.H];
+      h = t % p.H;
+      tile = q % tiles_per_seq;
+      b = q / tiles_per_seq;
+    } else {
+      tile = t % tiles_per_seq;
+      h = (t / tiles_per_seq) % p.H;
+      b = t / (tiles_per_seq * p.H);
+    }
+  };
   const int E = p.H * AB_D;
   constexpr uint32_t TM_S = 0, TM_DP = 256;                       // phase 1
   constexpr uint32_t TM_DQ = 0, TM_DV = 64, TM_DK = 192;          // phase 2 (dV: 2 x 64, dK: 2 x 64)
@@ -99,7 +115,8 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   // the current tile's last MMAs have retired (every shared-memory operand is dead then), so they land while the dK / dV
   // epilogue drains TMEM; barriers and the 512 TMEM columns are set up once per CTA.
   auto issue_loads = [&](int t) {     // thread 0 only
-    const int tile = t % tiles_per_seq, h = (t / tiles_per_seq) % p.H, b = t / (tiles_per_seq * p.H);
+    int tile, h, b;
+    decode(t, tile, h, b);
     const int i0 = tile * 128, key0 = i0 - W + p.shift;
     mbar_arrive_expect_tx(bar_load, 2 * AB_Q_BYTES + 2 * AB_KV_BYTES);
 #pragma unroll
@@ -130,9 +147,8 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   uint32_t it = 0;      // tiles processed by this CTA: parity of the once-per-tile barriers
 #pragma unroll 1
   for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-  const int tile = t % tiles_per_seq;
-  const int h = (t / tiles_per_seq) % p.H;
-  const int b = t / (tiles_per_seq * p.H);
+  int tile, h, b;
+  decode(t, tile, h, b);
   const int i0 = tile * 128;
   const uint8_t* mrow = p.mask012 + static_cast<size_t>(b) * p.L;
   const int key0 = i0 - W + p.shift;             // absolute key index of tile column 0
@@ -361,8 +377,9 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     if (tid == 0) issue_loads(tn);
     // ... and pull the next tile's per-row data (saved context quarter, log-sum-exp) into L2: those plain loads sit on
     // the next iteration's critical path (their DRAM latency was the top stall of the one-shot kernel)
-    const int hn = (tn / tiles_per_seq) % p.H, bn = tn / (tiles_per_seq * p.H);
-    const int in_ = (tn % tiles_per_seq) * 128 + r;
+    int tilen, hn, bn;
+    decode(tn, tilen, hn, bn);
+    const int in_ = tilen * 128 + r;
     if (in_ < p.L) {
       const void* pc = p.ctx + (static_cast<size_t>(bn) * p.L + in_) * E + hn * AB_D + part * 16;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(pc));
@@ -537,6 +554,12 @@ extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const fl
     p.use_cls = k == 0;
     p.drop_seed = a->drop_seed;     // masks are keyed on absolute (row, key): the same seed for every segment
     const int total = a->B * a->H * tiles;
+    {
+      const RowActivity& ra = row_activity();
+      const bool on = ra.flags != nullptr && ra.rows == static_cast<long long>(a->B) * a->L && a->L % 256 == 0;
+      p.qtiles = on ? ra.qtiles : nullptr;
+      p.n_qtiles = on ? ra.n_qtiles : nullptr;
+    }
     band_attn_bwd_kernel<<<total < sm_count() ? total : sm_count(), AB_THREADS, AB_SMEM, stream>>>(*tm64, *tm16, *tmdo, p);
     int rc = check_launch("rf_band_attn_bwd");
     if (rc) return rc;

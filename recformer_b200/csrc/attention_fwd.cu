@@ -64,6 +64,7 @@ struct AttnFwdParams {
   float drop_scale;
   uint32_t drop_thresh;
   uint64_t drop_seed;
+  const uint8_t* row_active;   // rf_set_row_activity: one flag per 256 token rows (L % 256 == 0), or null
 };
 
 template <int W>
@@ -92,6 +93,8 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
   const int h = (blockIdx.x / tiles_per_seq) % p.H;
   const int b = blockIdx.x / (tiles_per_seq * p.H);
   const int i0 = tile * 128;
+  // a query tile inside a padding-only 256-row tile: nobody reads its output rows (before any barrier / TMEM set-up)
+  if (p.row_active != nullptr && p.row_active[(static_cast<size_t>(b) * p.L + i0) >> 8] == 0) return;
   const int E = p.H * HEAD_DIM;
   const uint8_t* mrow = p.mask012 + static_cast<size_t>(b) * p.L;
   const int key0 = i0 - W + p.shift;             // absolute key index of tile column 0
@@ -391,6 +394,11 @@ static int launch_attn_fwd(const rf_attn_args* a, void* ctx, float* lse, const A
   p.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   p.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
   p.drop_seed = a->drop_seed;
+  {
+    const RowActivity& ra = row_activity();
+    p.row_active = (ra.flags != nullptr && ra.rows == static_cast<long long>(a->B) * a->L && a->L % 256 == 0) ? ra.flags
+                                                                                                              : nullptr;
+  }
   const int tiles = (a->L + 127) / 128;
   kern<<<a->B * a->H * tiles, ATT_THREADS, C::TOTAL, stream>>>(*tm64, *tm16, p);
   return check_launch("rf_band_attn_fwd");

@@ -13,6 +13,13 @@ namespace rf {
 
 constexpr int ROW_THREADS = 256;  // 8 warps = 8 rows per CTA pass
 
+// row activity (rf_set_row_activity): one flag per 256 token rows; a row kernel skips rows of padding-only tiles
+__device__ __forceinline__ bool row_on(const uint8_t* active, int t) { return active == nullptr || active[t >> 8] != 0; }
+static const uint8_t* active_flags_for(long long rows) {
+  const RowActivity& ra = row_activity();
+  return (ra.flags != nullptr && ra.rows == rows) ? ra.flags : nullptr;
+}
+
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -56,6 +63,35 @@ __global__ void prepare_inputs_kernel(const int64_t* __restrict__ ids, const int
     running += __popc(bal);
   }
   if (__any_sync(0xffffffffu, bad_global) && lane == 0) atomicOr(err_flag, 1);
+}
+
+// rf_row_tile_flags: which 256-row tiles of the [B*L] token axis hold at least one real token, and the compact list of
+// the 128-row attention query tiles inside them.  One CTA; warp w takes tiles w, w + 8, ...
+__global__ void __launch_bounds__(256) row_tile_flags_kernel(const uint8_t* __restrict__ mask012, int n_tiles,
+                                                            uint8_t* __restrict__ flags, int32_t* __restrict__ qtiles,
+                                                            int32_t* __restrict__ n_qtiles) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = warp; t < n_tiles; t += 8) {
+    const unsigned long long v = reinterpret_cast<const unsigned long long*>(mask012 + static_cast<size_t>(t) * 256)[lane];
+    const bool any = __any_sync(0xffffffffu, v != 0ull);
+    if (lane == 0) flags[t] = any ? 1 : 0;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int count = 0;
+    for (int t0 = 0; t0 < n_tiles; t0 += 32) {
+      const int t = t0 + lane;
+      const bool on = t < n_tiles && flags[t] != 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, on);
+      if (on) {
+        const int at = count + __popc(bal & ((1u << lane) - 1u));
+        qtiles[2 * at] = 2 * t;
+        qtiles[2 * at + 1] = 2 * t + 1;
+      }
+      count += __popc(bal);
+    }
+    if (lane == 0) *n_qtiles = 2 * count;
+  }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -178,10 +214,12 @@ __host__ __device__ __forceinline__ EmbedMap embed_map(int B, int Lp, int warps)
 // the L2 fabric's ~7.5 TB/s.
 template <int NV4>
 __global__ void __launch_bounds__(ROW_THREADS) embed_ln_fwd_kernel(const EmbedDev a, __nv_bfloat16* __restrict__ out,
-                                                                   float* __restrict__ out32, int* err_flag) {
+                                                                   float* __restrict__ out32, int* err_flag,
+                                                                   const uint8_t* __restrict__ active) {
   const int lane = threadIdx.x & 31;
   const int T = a.B * a.Lp;
   for (int t = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); t < T; t += gridDim.x * (ROW_THREADS / 32)) {
+    if (!row_on(active, t)) continue;
     int id, pid, tt, ip;
     bool bad;
     embed_token_ids(a, t, id, pid, tt, ip, bad);
@@ -214,13 +252,14 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_ln_fwd_kernel(const EmbedDe
 template <int NV4>
 __global__ void __launch_bounds__(ROW_THREADS)
 embed_ln_bwd_atomic_kernel(const EmbedDev a, const __nv_bfloat16* __restrict__ dout, float* d_word, float* d_pos,
-                    float* d_type, float* d_item, float* d_gamma, float* d_beta) {
+                    float* d_type, float* d_item, float* d_gamma, float* d_beta, const uint8_t* __restrict__ active) {
   const int lane = threadIdx.x & 31;
   const int T = a.B * a.Lp;
   float4 dg[NV4], db[NV4];
 #pragma unroll
   for (int k = 0; k < NV4; ++k) dg[k] = db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int t = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); t < T; t += gridDim.x * (ROW_THREADS / 32)) {
+    if (!row_on(active, t)) continue;
     int id, pid, tt, ip;
     bool bad;
     embed_token_ids(a, t, id, pid, tt, ip, bad);
@@ -298,7 +337,7 @@ struct EmbedBwdSmem {
 template <int NV4>
 __global__ void __launch_bounds__(ROW_THREADS, 1)
 embed_ln_bwd_kernel(const EmbedDev a, const __nv_bfloat16* __restrict__ dout, float* d_word, float* d_pos,
-                    float* d_type, float* d_item, float* d_gamma, float* d_beta) {
+                    float* d_type, float* d_item, float* d_gamma, float* d_beta, const uint8_t* __restrict__ active) {
   constexpr int E = NV4 * 128, WARPS = ROW_THREADS / 32;
   extern __shared__ float4 embed_smem[];
   float4* stage = embed_smem;                                   // [2][WARPS][E / 4]
@@ -336,7 +375,7 @@ embed_ln_bwd_kernel(const EmbedDev a, const __nv_bfloat16* __restrict__ dout, fl
     if (w >= w1) return -1;
     int b, l;
     mp.locate(w, warp, b, l);
-    return (b < a.B && l < a.Lp) ? b * a.Lp + l : -1;
+    return (b < a.B && l < a.Lp && row_on(active, b * a.Lp + l)) ? b * a.Lp + l : -1;
   };
   float4 wrow[NV4];
   uint2 drow[NV4];
@@ -365,7 +404,7 @@ embed_ln_bwd_kernel(const EmbedDev a, const __nv_bfloat16* __restrict__ dout, fl
     }
     int b, l;
     mp.locate(w, warp, b, l);
-    const bool valid = b < a.B && l < a.Lp;     // warp-uniform
+    const bool valid = b < a.B && l < a.Lp && row_on(active, b * a.Lp + l);     // warp-uniform
     // ---------------- phase A ----------------
     if (valid) {
       const int t = b * a.Lp + l;
@@ -527,10 +566,11 @@ template <int NV8>
 __global__ void __launch_bounds__(ROW_THREADS)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      __nv_bfloat16* __restrict__ y, float* __restrict__ y32, float* __restrict__ stats, int T,
-                     float eps) {
+                     float eps, const uint8_t* __restrict__ active) {
   constexpr int E = NV8 * 256;
   const int lane = threadIdx.x & 31;
   for (int t = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5); t < T; t += gridDim.x * (ROW_THREADS / 32)) {
+    if (!row_on(active, t)) continue;
     float v[NV8][8];
     load_row_f32<NV8>(x + static_cast<size_t>(t) * E, lane, v);
     float s = 0.f;
@@ -575,7 +615,8 @@ __global__ void __launch_bounds__(ROW_THREADS)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
                      const float* __restrict__ stats, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
                      __nv_bfloat16* __restrict__ dx_dropped, float drop_scale, uint32_t drop_thresh,
-                     uint64_t drop_seed, float* d_gamma, float* d_beta, float* d_bias, int T) {
+                     uint64_t drop_seed, float* d_gamma, float* d_beta, float* d_bias, int T,
+                     const uint8_t* __restrict__ active) {
   constexpr int E = NV8 * 256;
   const int lane = threadIdx.x & 31;
   __shared__ float red[ROW_THREADS / 32][E];
@@ -592,7 +633,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
   float nx[NV8][8];
   uint4 ndy[NV8];
   float2 nst = make_float2(0.f, 1.f);
-  if (t < T) {
+  if (t < T && row_on(active, t)) {
     load_row_f32<NV8>(x + static_cast<size_t>(t) * E, lane, nx);
     const uint4* dr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(t) * E);
 #pragma unroll
@@ -609,7 +650,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
 #pragma unroll
       for (int e = 0; e < 8; ++e) xh[k][e] = nx[k][e];
     }
-    if (t + t_step < T) {
+    if (t + t_step < T && row_on(active, t + t_step)) {
       const int tn = t + t_step;
       load_row_f32<NV8>(x + static_cast<size_t>(tn) * E, lane, nx);
       const uint4* dr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(tn) * E);
@@ -617,6 +658,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
       for (int k = 0; k < NV8; ++k) ndy[k] = dr[k * 32 + lane];
       nst = *reinterpret_cast<const float2*>(stats + 2 * tn);
     }
+    if (!row_on(active, t)) continue;      // padding-only tile: nothing was loaded for this row, nothing is written
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < NV8; ++k) {
@@ -686,7 +728,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
 // column sums of a bf16 [T,N] matrix (bias gradients): out[n] += sum_t x[t,n]
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* out, int T, int N,
-                                                          int ld, int rows_per_cta) {
+                                                          int ld, int rows_per_cta, const uint8_t* __restrict__ active) {
   // CTA = one 256-column slab (lane -> 8 columns) x rows_per_cta rows (warp w takes rows w, w+8, ...);
   // warps are reduced in shared memory, then one red.add per column per CTA.
   __shared__ float red[8][256];
@@ -700,7 +742,9 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
     for (; t + 24 < t1; t += 32) {   // 4 independent loads in flight
       uint4 raw[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) raw[q] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(t + q * 8) * ld + c);
+      for (int q = 0; q < 4; ++q)
+        raw[q] = row_on(active, t + q * 8) ? *reinterpret_cast<const uint4*>(x + static_cast<size_t>(t + q * 8) * ld + c)
+                                           : make_uint4(0, 0, 0, 0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float2 a0 = unpack_bf16(raw[q].x), a1 = unpack_bf16(raw[q].y), a2 = unpack_bf16(raw[q].z), a3 = unpack_bf16(raw[q].w);
@@ -709,6 +753,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
       }
     }
     for (; t < t1; t += 8) {
+      if (!row_on(active, t)) continue;
       const uint4 raw = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * ld + c);
       const float2 a0 = unpack_bf16(raw.x), a1 = unpack_bf16(raw.y), a2 = unpack_bf16(raw.z), a3 = unpack_bf16(raw.w);
       acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y;
@@ -816,14 +861,24 @@ extern "C" int rf_prepare_inputs(const int64_t* input_ids, const int64_t* attent
   return check_launch("rf_prepare_inputs");
 }
 
+extern "C" int rf_row_tile_flags(const uint8_t* mask012, int B, int L, uint8_t* tile_flags, int32_t* qtile_list,
+                                 int32_t* n_qtiles, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(mask012 && tile_flags && qtile_list && n_qtiles, "rf_row_tile_flags: null argument");
+  RF_REQUIRE(B > 0 && L > 0 && L % 256 == 0, "rf_row_tile_flags: L=%d must be a multiple of 256", L);
+  RF_REQUIRE((reinterpret_cast<uintptr_t>(mask012) & 7) == 0, "rf_row_tile_flags: mask must be 8-byte aligned");
+  row_tile_flags_kernel<<<1, 256, 0, stream>>>(mask012, B * (L / 256), tile_flags, qtile_list, n_qtiles);
+  return check_launch("rf_row_tile_flags");
+}
+
 extern "C" int rf_embed_ln_fwd(const rf_embed_args* a, void* out, float* out32, int* err_flag, rf_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   RF_REQUIRE(a && (out || out32), "rf_embed_ln_fwd: null argument");
   RF_REQUIRE(a->E == 768, "rf_embed_ln_fwd: hidden size %d unsupported (768)", a->E);
   RF_REQUIRE(a->B > 0 && a->L > 0 && a->Lp >= a->L, "rf_embed_ln_fwd: bad shape");
   const EmbedDev d = make_embed_dev(a);
-  embed_ln_fwd_kernel<6><<<row_grid(a->B * a->Lp), ROW_THREADS, 0, stream>>>(d, reinterpret_cast<__nv_bfloat16*>(out),
-                                                                           out32, err_flag);
+  embed_ln_fwd_kernel<6><<<row_grid(a->B * a->Lp), ROW_THREADS, 0, stream>>>(
+      d, reinterpret_cast<__nv_bfloat16*>(out), out32, err_flag, active_flags_for(static_cast<long long>(a->B) * a->Lp));
   return check_launch("rf_embed_ln_fwd");
 }
 
@@ -839,12 +894,14 @@ extern "C" int rf_embed_ln_bwd(const rf_embed_args* a, const void* dout, float* 
     static std::atomic<unsigned long long> attr_seen{0};   // one bit per device
     if (first_use_on_device(&attr_seen))
       RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    kern<<<embed_grid(a, ROW_THREADS / 32, 1), ROW_THREADS, smem, stream>>>(d, reinterpret_cast<const __nv_bfloat16*>(dout), d_word, d_pos,
-                                                         d_type, d_item, d_gamma, d_beta);
+    kern<<<embed_grid(a, ROW_THREADS / 32, 1), ROW_THREADS, smem, stream>>>(
+        d, reinterpret_cast<const __nv_bfloat16*>(dout), d_word, d_pos, d_type, d_item, d_gamma, d_beta,
+        active_flags_for(static_cast<long long>(a->B) * a->Lp));
   } else {
     const int grid = min(row_grid(a->B * a->Lp), sm_count() * 2);
-    embed_ln_bwd_atomic_kernel<6><<<grid, ROW_THREADS, 0, stream>>>(d, reinterpret_cast<const __nv_bfloat16*>(dout),
-                                                                   d_word, d_pos, d_type, d_item, d_gamma, d_beta);
+    embed_ln_bwd_atomic_kernel<6><<<grid, ROW_THREADS, 0, stream>>>(
+        d, reinterpret_cast<const __nv_bfloat16*>(dout), d_word, d_pos, d_type, d_item, d_gamma, d_beta,
+        active_flags_for(static_cast<long long>(a->B) * a->Lp));
   }
   return check_launch("rf_embed_ln_bwd");
 }
@@ -856,7 +913,7 @@ extern "C" int rf_layernorm_fwd(const float* x, const float* gamma, const float*
   RF_REQUIRE(E == 768, "rf_layernorm_fwd: hidden size %d unsupported (768)", E);
   RF_REQUIRE(T > 0, "rf_layernorm_fwd: T=%d", T);
   layernorm_fwd_kernel<3><<<row_grid(T), ROW_THREADS, 0, stream>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y),
-                                                                  y32, stats, T, eps);
+                                                                  y32, stats, T, eps, active_flags_for(T));
   return check_launch("rf_layernorm_fwd");
 }
 
@@ -872,7 +929,7 @@ extern "C" int rf_layernorm_bwd(const void* dy, const float* x, const float* sta
   layernorm_bwd_kernel<3><<<grid, ROW_THREADS, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), x, stats, gamma,
       reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(dx_dropped), scale, thresh, drop_seed,
-      d_gamma, d_beta, d_bias, T);
+      d_gamma, d_beta, d_bias, T, active_flags_for(T));
   return check_launch("rf_layernorm_bwd");
 }
 
@@ -885,7 +942,8 @@ extern "C" int rf_colsum_bf16(const void* x, float* out, int T, int N, int ld, r
   if (gy > T) gy = T;
   const int rows = (T + gy - 1) / gy;
   gy = (T + rows - 1) / rows;
-  colsum_bf16_kernel<<<dim3(gx, gy), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, T, N, ld, rows);
+  colsum_bf16_kernel<<<dim3(gx, gy), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, T, N, ld, rows,
+                                                      active_flags_for(T));
   return check_launch("rf_colsum_bf16");
 }
 

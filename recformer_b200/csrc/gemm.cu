@@ -47,6 +47,9 @@ struct GemmParams {
   uint64_t drop_seed;
   int xk_rows;            // XK: rows of A per batch (one 64-row block of B2 per batch)
   int* tile_counter;      // pair kernel: dynamic tile scheduler (zero between launches, see gemm_pair_kernel)
+  // pair kernel, row activity (rf_set_row_activity): one flag per 256 rows of the token axis; 0 = padding only.
+  const uint8_t* m_active;   // token axis = M (forward / dgrad): output tiles of inactive row tiles are skipped
+  const uint8_t* k_active;   // token axis = K (wgrad): inactive 64-token k-blocks are skipped (their dY rows are zero)
 };
 
 template <int BN>
@@ -425,6 +428,17 @@ constexpr uint32_t P_SMEM = P_TILE_BYTES + P_EPI_STAGE_BYTES + P_BAR_BYTES + 2 *
 // (value total_tiles + npairs - 1: every pair draws exactly one) resets it to zero for its next use.
 __device__ int g_gemm_tile_counters[256];
 
+// wgrad with row activity: k-block kb (64 tokens) belongs to the 256-token tile kb >> 2
+__device__ __forceinline__ bool kb_active(const uint8_t* k_active, int kb) {
+  return k_active == nullptr || k_active[kb >> 2] != 0;
+}
+__device__ __forceinline__ int count_active_kb(const uint8_t* k_active, int kb0, int kb1) {
+  if (k_active == nullptr) return kb1 - kb0;
+  int n = 0;
+  for (int kb = kb0; kb < kb1; ++kb) n += k_active[kb >> 2] != 0 ? 1 : 0;
+  return n;
+}
+
 // XK: one extra 64-deep k-block per output tile whose operands come from a second pair of tensors, the A
 // side [M, 64] K-major and the B side batched ([M / xk_rows] blocks of [64, N], N contiguous):
 //   C = A B + A2[rows] B2[batch(rows)]  -- a per-sequence low-rank update riding on the dense GEMM
@@ -543,7 +557,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n0 = nt * P_BN + static_cast<int>(rank) * 128;      // this CTA's half of the B tile
         const int kb0 = sp * k_per_split;
         const int kb1 = min(kb0 + k_per_split, k_blocks_total);
+        if (p.m_active != nullptr && p.m_active[mt] == 0) { tile = tile_next; continue; }   // padding-only row tile
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (!kb_active(p.k_active, kb)) continue;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * P_STAGE_BYTES);
           const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's barrier
@@ -604,10 +620,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int sp = (tile / n_tiles) / m_tiles;
         const int kb0 = sp * k_per_split;
         const int kb1 = min(kb0 + k_per_split, k_blocks_total);
+        if (p.m_active != nullptr && p.m_active[(tile / n_tiles) % m_tiles] == 0) continue;
+        const int nkb = count_active_kb(p.k_active, kb0, kb1) + (XK ? 1 : 0);
+        if (nkb == 0) continue;                       // wgrad slice made of padding only: nothing to add
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * P_BN;
-        const int nkb = kb1 - kb0 + (XK ? 1 : 0);
         for (int it = 0; it < nkb; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -642,6 +660,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (tile >= total_tiles) break;
       const int nt = tile % n_tiles;
       const int mt = (tile / n_tiles) % m_tiles;
+      if (p.m_active != nullptr && p.m_active[mt] == 0) continue;
+      if (p.k_active != nullptr) {
+        const int sp = (tile / n_tiles) / m_tiles;
+        const int kb0 = sp * k_per_split;
+        if (count_active_kb(p.k_active, kb0, min(kb0 + k_per_split, k_blocks_total)) == 0) continue;
+      }
       const int m0 = mt * 256 + static_cast<int>(rank) * 128, n0 = nt * P_BN;
       const int row_base = m0 + quad * 32;
       uint8_t* my_stage = s_stage + (warp - 2) * 4096;
@@ -723,6 +747,12 @@ static int launch_gemm_pair(const rf_gemm_args* a, cudaStream_t stream) {
   const int m_tiles = (a->M + 255) / 256, n_tiles = (a->N + P_BN - 1) / P_BN;
   const int total = m_tiles * n_tiles * p.split_k;
   const int pairs = total < sm_count() / 2 ? total : sm_count() / 2;
+  {
+    const RowActivity& ra = row_activity();
+    const bool wgrad_layout = A_MN && B_MN;
+    p.m_active = (ra.flags != nullptr && !wgrad_layout && ra.rows == a->M) ? ra.flags : nullptr;
+    p.k_active = (ra.flags != nullptr && wgrad_layout && ra.rows == a->K) ? ra.flags : nullptr;
+  }
   static const bool static_sched = getenv("RF_GEMM_STATIC_SCHEDULE") != nullptr;
   p.tile_counter = static_sched ? nullptr : next_tile_counter();
   if (!static_sched && !p.tile_counter) return RF_ERR_CUDA;
@@ -744,6 +774,8 @@ static int launch_gemm(const rf_gemm_args* a, cudaStream_t stream) {
   if (!tmB) return RF_ERR_CUDA;
   GemmParams p;
   fill_params(a, p);
+  p.m_active = p.k_active = nullptr;       // the single-CTA kernel (small problems) takes no row activity
+  p.tile_counter = nullptr;
   const int m_tiles = (a->M + BM - 1) / BM, n_tiles = (a->N + BN - 1) / BN;
   const int total = m_tiles * n_tiles * p.split_k;
   const int grid = total < sm_count() ? total : sm_count();

@@ -36,6 +36,16 @@ const CUtensorMap* get_tmap_2d(const void* ptr, uint64_t rows, uint64_t cols, ui
 const CUtensorMap* get_tmap_3d(const void* ptr, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                                uint64_t batch_stride_elems, uint32_t box_rows);
 
+// Launch context "row activity" (rf_set_row_activity): when set, the token-major kernels of the encoder skip the
+// 256-row tiles whose flag is 0 (tiles made of padding only).  Thread-local, consulted at launch time.
+struct RowActivity {
+  const uint8_t* flags;        // [rows / 256], device; nullptr = everything active
+  long long rows;              // B * L of the activation matrices the flags describe
+  const int32_t* qtiles;       // compact list of the active 128-row query tiles (b * (L / 128) + tile), device
+  const int32_t* n_qtiles;     // its length, device
+};
+const RowActivity& row_activity();
+
 int sm_count();
 // true exactly once per (flag, current CUDA device): guards the per-device cudaFuncSetAttribute calls
 bool first_use_on_device(std::atomic<unsigned long long>* seen);

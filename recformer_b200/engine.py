@@ -225,20 +225,28 @@ class SavedActivations:
         bf = dict(dtype=torch.bfloat16, device=device)
         f32 = dict(dtype=torch.float32, device=device)
         self.B, self.Lp, self.per_layer = B, Lp, per_layer
-        self.x = [torch.empty(T, E, **bf) for _ in range(nl + 1 if per_layer else 2)]      # bf16 operand copy
-        self.x32 = [torch.empty(T, E, **f32) for _ in range(2)]                             # fp32 residual stream
-        self.h1_32 = torch.empty(T, E, **f32)
-        self.qkv = [torch.empty(T, 3 * E, **bf) for _ in range(n)]
-        self.lse = [torch.empty(B, H, Lp, **f32) for _ in range(n)]
-        self.ctx = [torch.empty(T, E, **bf) for _ in range(n)]
-        self.pre1 = [torch.empty(T, E, **f32) for _ in range(n)]
-        self.stats1 = [torch.empty(T, 2, **f32) for _ in range(n)]
-        self.h1 = [torch.empty(T, E, **bf) for _ in range(n)]
-        self.u = [torch.empty(T, F, **bf) for _ in range(n)]       # gelu'(pre-activation), saved for backward
-        self.g = [torch.empty(T, F, **bf) for _ in range(n)]
-        self.pre2 = [torch.empty(T, E, **f32) for _ in range(n)]
-        self.stats2 = [torch.empty(T, 2, **f32) for _ in range(n)]
+        self.x = [torch.zeros(T, E, **bf) for _ in range(nl + 1 if per_layer else 2)]      # bf16 operand copy
+        self.x32 = [torch.zeros(T, E, **f32) for _ in range(2)]                             # fp32 residual stream
+        self.h1_32 = torch.zeros(T, E, **f32)
+        self.qkv = [torch.zeros(T, 3 * E, **bf) for _ in range(n)]
+        self.lse = [torch.zeros(B, H, Lp, **f32) for _ in range(n)]
+        self.ctx = [torch.zeros(T, E, **bf) for _ in range(n)]
+        self.pre1 = [torch.zeros(T, E, **f32) for _ in range(n)]
+        self.stats1 = [torch.zeros(T, 2, **f32) for _ in range(n)]
+        self.h1 = [torch.zeros(T, E, **bf) for _ in range(n)]
+        self.u = [torch.zeros(T, F, **bf) for _ in range(n)]       # gelu'(pre-activation), saved for backward
+        self.g = [torch.zeros(T, F, **bf) for _ in range(n)]
+        self.pre2 = [torch.zeros(T, E, **f32) for _ in range(n)]
+        self.stats2 = [torch.zeros(T, 2, **f32) for _ in range(n)]
         self.glob = [ops.global_attn_saved(B, Lp, H, device) for _ in range(n)]
+        # padding-aware execution (include/recformer_b200.h, rf_set_row_activity): 256-row tiles that hold a real token.
+        # Buffers above are zero-initialised because rows of skipped tiles are never written: whatever a kernel reads
+        # from them (keys of a masked neighbour tile under a zero probability) must at least be finite.
+        self.activity, self.skip = None, False
+        if Lp % 256 == 0:
+            self.activity = (torch.zeros(T // 256, dtype=torch.uint8, device=device),
+                             torch.zeros(T // 128, dtype=torch.int32, device=device),
+                             torch.zeros(1, dtype=torch.int32, device=device))
         self.pos_ids = None
         self.mask012 = None
         self.inputs = None
@@ -263,18 +271,18 @@ class BackwardScratch:
         bf = dict(dtype=torch.bfloat16, device=device)
         # Everything the aux stream reads (weight-gradient GEMMs, bias column sums) exists once per LayerNorm site and
         # layer parity: the main stream may be up to two layers ahead of the aux stream before it has to wait.
-        self.d_pre = [[torch.empty(T, E, **bf) for _ in range(2)] for _ in range(2)]         # [site][parity]
-        self.d_pre_drop = [[torch.empty(T, E, **bf) for _ in range(2)] for _ in range(2)]
-        self.dU = [torch.empty(T, F, **bf) for _ in range(2)]
-        self.dh1 = torch.empty(T, E, **bf)
-        self.dctx = torch.empty(T, E, **bf)
-        self.dqkv = [torch.empty(T, 3 * E, **bf) for _ in range(2)]
-        self.dx = [torch.empty(T, E, **bf) for _ in range(2)]
-        self.dkv = torch.empty(T, 2 * E, dtype=torch.float32, device=device)
+        self.d_pre = [[torch.zeros(T, E, **bf) for _ in range(2)] for _ in range(2)]         # [site][parity]
+        self.d_pre_drop = [[torch.zeros(T, E, **bf) for _ in range(2)] for _ in range(2)]
+        self.dU = [torch.zeros(T, F, **bf) for _ in range(2)]
+        self.dh1 = torch.zeros(T, E, **bf)
+        self.dctx = torch.zeros(T, E, **bf)
+        self.dqkv = [torch.zeros(T, 3 * E, **bf) for _ in range(2)]
+        self.dx = [torch.zeros(T, E, **bf) for _ in range(2)]
+        self.dkv = torch.zeros(T, 2 * E, dtype=torch.float32, device=device)
         self.gws = ops.global_attn_bwd_ws(B, Lp, H, device)
         # operands of the rank-64 per-sequence update that carries the CLS row's token gradients through the
         # QKV dgrad GEMM (only when a 256-row output tile never straddles two sequences)
-        self.xk = (torch.empty(T, 64, **bf), torch.empty(B * 64, E, **bf)) if Lp % 256 == 0 and T > 128 else None
+        self.xk = (torch.zeros(T, 64, **bf), torch.zeros(B * 64, E, **bf)) if Lp % 256 == 0 and T > 128 else None
 
 
 class EncoderEngine:
@@ -295,6 +303,7 @@ class EncoderEngine:
         self.overlap_global = os.environ.get("RF_DEBUG_NO_OVERLAP") is None
         self._debug_skip_global = os.environ.get("RF_DEBUG_SKIP_GLOBAL") is not None   # timing experiment only (wrong results)
         self._debug_no_xk = os.environ.get("RF_DEBUG_NO_XK") is not None   # A/B switch: separate dx-update kernel
+        self.tile_skip = os.environ.get("RF_NO_TILE_SKIP") is None     # padding-aware execution (forward(skip_padding=True))
         self.grad_hook = None      # callable(layer): that layer's gradients are final (dist.GradSync, FusedAdamW overlap)
         # Second side stream ("aux"): work nobody on the backward's critical path waits for — the bias-gradient column
         # sums of dU / dqkv and, when FusedAdamW.begin_overlap() armed it, the AdamW update of finished layers.  These
@@ -430,7 +439,12 @@ class EncoderEngine:
 
     # -- forward -------------------------------------------------------------------------------
     def forward(self, input_ids, attention_mask, global_attention_mask, token_type_ids, item_position_ids,
-                position_ids=None, training: bool = False, save: bool = False) -> SavedActivations:
+                position_ids=None, training: bool = False, save: bool = False,
+                skip_padding: bool = False) -> SavedActivations:
+        """skip_padding: the caller only consumes rows of real tokens (the CLS rows, gathered masked rows) and feeds
+        back zero gradient for padded positions: 256-row tiles made of padding only are skipped by every token-major
+        kernel of the pass and of its backward (rf_set_row_activity); their rows of the hidden states keep whatever an
+        earlier pass left there.  Needs Lp % 256 == 0, otherwise ignored."""
         cfg, P = self.cfg, self.params
         device = input_ids.device
         P.ensure(device)
@@ -449,6 +463,20 @@ class EncoderEngine:
             pos = torch.nn.functional.pad(position_ids.to(torch.int32), (0, Lp - L), value=cfg.pad_token_id).contiguous()
         sv.pos_ids, sv.mask012 = pos, mask
         sv.inputs = (input_ids, token_type_ids, item_position_ids)
+        sv.skip = bool(skip_padding) and self.tile_skip and sv.activity is not None
+        if sv.skip:
+            ops.row_tile_flags(mask, B, Lp, *sv.activity)
+            ops.set_row_activity(sv.activity[0], B * Lp, sv.activity[1], sv.activity[2])
+        try:
+            self._forward_layers(sv, input_ids, token_type_ids, item_position_ids, pos, mask, err, device)
+        finally:
+            ops.set_row_activity(None)
+        return sv
+
+    def _forward_layers(self, sv, input_ids, token_type_ids, item_position_ids, pos, mask, err, device) -> None:
+        cfg, P = self.cfg, self.params
+        B, Lp = sv.B, sv.Lp
+        E, H = cfg.hidden_size, cfg.num_attention_heads
         e = "embeddings."
         ops.embed_ln_fwd(input_ids, token_type_ids, item_position_ids, pos,
                          P.view(e + "word_embeddings.weight"), P.view(e + "position_embeddings.weight"),
@@ -494,7 +522,6 @@ class EncoderEngine:
                      drop_seed=self._seed(sv, i, 4))
             ops.layernorm_fwd(sv.pre2[k], W["ln2w"], W["ln2b"], cfg.layer_norm_eps, out=sv.xout(i),
                               out32=sv.x32[(i + 1) % 2], stats=sv.stats2[k])
-        return sv
 
     def hidden(self, sv: SavedActivations) -> torch.Tensor:
         """fp32 [B*Lp, E] final hidden states (the residual-stream copy of the last LayerNorm)."""
@@ -521,6 +548,14 @@ class EncoderEngine:
 
     def backward(self, sv: SavedActivations, dout: torch.Tensor) -> None:
         """dout: bf16 [B*Lp, E] gradient w.r.t. the final hidden states.  Accumulates into .grad."""
+        if sv.skip:
+            ops.set_row_activity(sv.activity[0], sv.B * sv.Lp, sv.activity[1], sv.activity[2])
+        try:
+            self._backward(sv, dout)
+        finally:
+            ops.set_row_activity(None)
+
+    def _backward(self, sv: SavedActivations, dout: torch.Tensor) -> None:
         cfg, P = self.cfg, self.params
         assert sv.per_layer, "forward was not run with save=True"
         B, Lp = sv.B, sv.Lp

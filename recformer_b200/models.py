@@ -171,7 +171,7 @@ class _EncoderPooledFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hook, model, inputs):
         eng = model._engine
-        sv = eng.forward(*inputs, training=model.training, save=True)
+        sv = eng.forward(*inputs, training=model.training, save=True, skip_padding=True)   # only CLS rows leave / return
         pooled = eng.hidden(sv).view(sv.B, sv.Lp, model.config.hidden_size)[:, 0].clone()
         ctx.model, ctx.sv = model, sv
         return pooled
@@ -302,7 +302,7 @@ class RecformerModel(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             pooled = _EncoderPooledFunction.apply(self._grad_hook(input_ids.device), self, inputs)
         else:
-            sv = eng.forward(*inputs, training=self.training, save=False)
+            sv = eng.forward(*inputs, training=self.training, save=False, skip_padding=True)
             pooled = eng.hidden(sv).view(sv.B, sv.Lp, self.config.hidden_size)[:, 0].clone()
             eng.release(sv)
         if self.strict_checks:
@@ -317,7 +317,7 @@ class RecformerModel(nn.Module):
         ids = batch["input_ids"]
         sv = eng.forward(to64(ids), to64(batch.get("attention_mask")), to64(batch.get("global_attention_mask")),
                          to64(batch.get("token_type_ids")), to64(batch["item_position_ids"]),
-                         to64(batch.get("position_ids")), training=False, save=False)
+                         to64(batch.get("position_ids")), training=False, save=False, skip_padding=True)
         pooled = eng.hidden_bf16(sv).view(sv.B, sv.Lp, -1)[:, 0].contiguous()
         eng.release(sv)
         return pooled

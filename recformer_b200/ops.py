@@ -105,6 +105,21 @@ def _embed_args(input_ids, token_type_ids, item_position_ids, pos_ids, word, pos
     return a
 
 
+def row_tile_flags(mask012, B, L, flags, qtiles, n_qtiles):
+    """flags[u8, B*L/256] = 256-row tile holds a real token; qtiles[i32, B*L/128] / n_qtiles[i32, 1] = active query tiles."""
+    check(_lib.lib().rf_row_tile_flags(mask012.data_ptr(), B, L, flags.data_ptr(), qtiles.data_ptr(), n_qtiles.data_ptr(),
+                                       _stream()), "rf_row_tile_flags")
+
+
+def set_row_activity(flags=None, rows=0, qtiles=None, n_qtiles=None):
+    """Launch context of this host thread: token-major kernels skip padding-only 256-row tiles; None clears it."""
+    if flags is None:
+        check(_lib.lib().rf_set_row_activity(None, 0, None, None), "rf_set_row_activity")
+    else:
+        check(_lib.lib().rf_set_row_activity(flags.data_ptr(), rows, qtiles.data_ptr(), n_qtiles.data_ptr()),
+              "rf_set_row_activity")
+
+
 def embed_ln_fwd(input_ids, token_type_ids, item_position_ids, pos_ids, word, posw, typew, itemw, gamma, beta, Lp,
                  padding_idx, eps, err_flag, drop_p=0.0, drop_seed=0, out=None, out32=None):
     for t, n in ((word, "word"), (posw, "pos"), (typew, "type"), (itemw, "item"), (gamma, "gamma"), (beta, "beta")):

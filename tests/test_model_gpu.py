@@ -371,6 +371,54 @@ def test_sampled_softmax_and_candidates_match_oracle():
     assert out.dim() == 0 and torch.isfinite(out)
 
 
+def test_padding_tile_skipping_leaves_real_tokens_unchanged():
+    """Padding-aware execution (rf_set_row_activity): with rows of 1024 tokens of which some are shorter than 768 / 512,
+    whole 256-row tiles are skipped by every token-major kernel.  The pooled CLS vectors must be BIT-identical to the
+    run that computes every padded position (the forward is deterministic), the loss too, and the gradients equal up
+    to the summation order of the atomics (the padded rows' contributions are exact zeros either way)."""
+    ocfg, cfg, model, sd = build(dict(vocab_size=1500, num_hidden_layers=3, attention_window=[64, 64, 64],
+                                      max_position_embeddings=1100), sd_seed=3)
+    cfg.hidden_dropout_prob = 0.0
+    cfg.attention_probs_dropout_prob = 0.0
+    model.init_item_embedding(O.make_item_table(200, 768, seed=1).to(DEV))
+    batch = {k: v.to(DEV) for k, v in O.make_batch(ocfg, 5, 1024, seed=11, ragged=True).items()}
+    lens = [1024, 300, 700, 515, 130]
+    for b, n in enumerate(lens):           # explicit lengths: tiles 1..3 of row 1, tile 3 of rows 2 and 3, ... are padding
+        batch["attention_mask"][b, n:] = 0
+        batch["input_ids"][b, n:] = cfg.pad_token_id
+        batch["token_type_ids"][b, n:] = 3
+        batch["item_position_ids"][b, n:] = cfg.max_item_embeddings - 1
+    labels = torch.tensor([1, 5, 9, 60, 199], device=DEV)
+    eng = model.longformer._engine
+    P = eng.params
+    out = {}
+    for skip in (False, True):
+        eng.tile_skip = skip
+        model.eval()
+        with torch.no_grad():
+            pooled = model.longformer.forward_pooled(**batch).clone()
+        model.train()
+        if P.grad is not None:
+            P.grad.zero_()
+        loss = model(**batch, labels=labels)
+        loss.backward()
+        torch.cuda.synchronize()
+        out[skip] = (pooled, loss.detach().clone(), P.grad.clone())
+    eng.tile_skip = True
+    assert eng._bwd and any(sv.activity is not None for pool in eng._free.values() for sv in pool)
+    assert torch.equal(out[True][0], out[False][0])
+    assert torch.equal(out[True][1], out[False][1])
+    ga, gb = out[True][2], out[False][2]
+    assert (ga - gb).abs().max().item() <= 2e-3 * gb.abs().max().item(), (ga - gb).abs().max().item()
+    assert abs(ga.norm().item() - gb.norm().item()) <= 1e-4 * gb.norm().item()
+    # and the skipped run agrees with the fp32 oracle like any other
+    ref = O.seqrec_forward(sd, ocfg, {k: v.cpu() for k, v in batch.items()}, O.make_item_table(200, 768, seed=1))
+    model.eval()
+    with torch.no_grad():
+        got = model(**batch)
+    assert (got.cpu() - ref).abs().max().item() < 2e-2
+
+
 def _graph_setup(dropout, seed=7):
     from recformer_b200.optim import FusedAdamW
     ocfg, cfg, model, sd = build(dict(vocab_size=1500, num_hidden_layers=2, attention_window=[64, 64],
