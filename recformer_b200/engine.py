@@ -313,11 +313,13 @@ class EncoderEngine:
         # Off by default: on a stream of the SAME priority as the main one this work delays the CTAs of the persistent
         # kernels (13.57 vs 13.35 ms per step); GraphedTrainStep captures on a high-priority stream and switches it on.
         self.overlap_aux = False
-        # RF_WGRAD_AUX=1 (experiment, with overlap_aux): the four weight-gradient GEMMs of a layer also go to the aux stream —
-        # nothing on the backward's dependency chain reads them, so they could fill the tails of the chain's kernels.
-        # Measured: no gain (13.17-13.35 vs 13.23-13.30 ms per step, SM clock 1725 vs 1800-1820 MHz): the step runs at
-        # the board's power cap, and keeping more SMs busy is paid back in clock.
-        self.wgrad_aux = os.environ.get("RF_WGRAD_AUX") is not None
+        # With overlap_aux the four weight-gradient GEMMs of a layer also go to the aux stream: nothing on the backward's
+        # dependency chain reads them, and their (dynamically scheduled) CTAs fill the last, partly empty wave of the
+        # chain's GEMMs.  Measured with every row tile active: no gain (13.17-13.35 vs 13.23-13.30 ms; the step runs at
+        # the board's power cap and busier SMs are paid back in clock, 1725 vs 1800 MHz); with padding tiles skipped the
+        # N = 768 GEMMs have 144-192 tiles on 74 CTA pairs, i.e. long tails: 12.72-12.79 vs 12.91-12.97 ms.
+        # RF_NO_WGRAD_AUX=1 keeps them on the main stream.
+        self.wgrad_aux = os.environ.get("RF_NO_WGRAD_AUX") is None
         self.aux_done = None       # latest aux-stream event of the running backward (dist.GradSync waits on it)
 
     # -- helpers -------------------------------------------------------------------------------

@@ -144,7 +144,7 @@ class _EncoderFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hook, model, L, inputs):
         eng = model._engine
-        sv = eng.forward(*inputs, training=model.training, save=True)
+        sv = eng.forward(*inputs, training=model.training, save=True, skip_padding=model.padding_rows_unused)
         B, Lp, E = sv.B, sv.Lp, model.config.hidden_size
         hidden = eng.hidden(sv).view(B, Lp, E)[:, :L].clone()   # fp32 residual stream of the last layer
         ctx.model, ctx.sv, ctx.L = model, sv, L
@@ -210,6 +210,11 @@ class RecformerModel(nn.Module):
         object.__setattr__(self, "_engine", EncoderEngine(self))
         object.__setattr__(self, "_hook", None)
         self.strict_checks = True
+        # True: whoever calls forward() never reads `last_hidden_state` at padded positions and never sends gradient to
+        # them (the pretraining heads: CLS rows + gathered masked rows) — the encoder may then skip 256-row tiles made of
+        # padding only (engine.forward(skip_padding=True)); those rows of the returned hidden states are undefined.
+        # False (default): every position is computed, as in the reference (ref: recformer/models.py:274-356).
+        self.padding_rows_unused = False
 
     # HF-compatible accessors used by the reference scripts (finetune.py:272-275)
     def get_input_embeddings(self):
@@ -269,7 +274,7 @@ class RecformerModel(nn.Module):
         if needs_grad:
             hidden = _EncoderFunction.apply(self._grad_hook(input_ids.device), self, L, inputs)
         else:
-            sv = eng.forward(*inputs, training=self.training, save=False)
+            sv = eng.forward(*inputs, training=self.training, save=False, skip_padding=self.padding_rows_unused)
             hidden = eng.hidden(sv).view(B, sv.Lp, E)[:, :L].clone()
             eng.release(sv)
         if self.strict_checks:
@@ -576,6 +581,7 @@ class RecformerForPretraining(nn.Module):
         super().__init__()
         self.config = config
         self.longformer = RecformerModel(config)
+        self.longformer.padding_rows_unused = True      # this class consumes CLS rows and masked (real-token) rows only
         self.lm_head = _LMHead(config)
         self.lm_head.apply(lambda m: _init_weights(m, config.initializer_range))
         self.sim = Similarity(config)
