@@ -203,6 +203,10 @@ typedef struct rf_attn_args {
   float drop_p;
   uint64_t drop_seed;
   void* ws; /* workspace of rf_band_attn_ws_bytes() bytes; required when w > 32, else may be NULL */
+  void* keepbits; /* optional, w == 32 with drop_p > 0: [B, H, L] x 16 bytes (16-byte aligned).  rf_band_attn_fwd saves
+                     the dropout keep bits of every row's window there and rf_band_attn_bwd reads them back instead of
+                     regenerating the Philox stream (a third of its softmax-backward instructions).  NULL (or any other
+                     window): both passes regenerate the masks from (drop_seed, row, key) as before. */
 } rf_attn_args;
 
 /* Workspace for windows wider than attention_window 64 (w > 32): the band is covered by ceil((2w+1)/65)

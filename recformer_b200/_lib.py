@@ -35,7 +35,7 @@ class EmbedArgs(C.Structure):
 
 class AttnArgs(C.Structure):
     _fields_ = [("qkv", c_void_p), ("mask012", c_void_p), ("B", c_int), ("L", c_int), ("H", c_int), ("D", c_int),
-                ("w", c_int), ("drop_p", c_float), ("drop_seed", c_u64), ("ws", c_void_p)]
+                ("w", c_int), ("drop_p", c_float), ("drop_seed", c_u64), ("ws", c_void_p), ("keepbits", c_void_p)]
 
 
 class GlobalArgs(C.Structure):

@@ -20,6 +20,9 @@ LIB = os.path.join(HERE, "librecformer_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# development aid: extra -D flags (e.g. RF_NVCC_DEFINES="-DRF_KTIMING" enables the in-kernel phase clocks read by
+# tools/ktiming.py); part of the build digest, so switching it rebuilds
+NVCC_FLAGS += os.environ.get("RF_NVCC_DEFINES", "").split()
 
 
 def _sources():

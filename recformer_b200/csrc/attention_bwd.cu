@@ -62,11 +62,31 @@ struct AttnBwdParams {
   float drop_scale;
   uint32_t drop_thresh;
   uint64_t drop_seed;
+  const uint4* keepbits;      // [B, H, L] x 16 B: the forward's dropout keep bits (attention_window 64 only), or null = regenerate
   // row activity (rf_set_row_activity): the persistent CTAs walk the compact list of active query tiles x heads
   const int32_t* qtiles;      // [n] entries b * tiles_per_seq + tile, or null = every tile
   const int32_t* n_qtiles;    // device scalar n
 };
 
+#ifdef RF_KTIMING
+__device__ long long g_kt_bwd[4][16][16];     // [warp 0 / 5 / 10 / 15][tile][stamp]
+#define KT(k) do { if (lane == 0 && (warp % 5) == 0 && blockIdx.x == 5 && it < 16) g_kt_bwd[warp / 5][it][k] = clock64(); } while (0)
+#else
+#define KT(k) do {} while (0)
+#endif
+
+// PERSISTENT, one CTA per SM.  Each CTA owns a CONTIGUOUS run of the (b, h, tile) list in which the query tile is the
+// fastest index, so consecutive work items are neighbouring tiles of one (sequence, head):
+//  * the 64 keys that two neighbouring tiles share ([i0 + 96, i0 + 160) = tile columns 128..191 of the first = columns
+//    0..63 of the second; the same TMEM lanes of the second key half / the first key half, i.e. the SAME THREADS of the
+//    dK / dV epilogue) are carried in registers from one tile to the next and stored once, with plain 16-byte stores;
+//    only the first / last tile of a run, whose neighbour belongs to another CTA, uses red.add on the shared keys.
+//    (Before: every key of every tile went through red.global.add.v4.bf16x2 — 128 warp-level REDs per tile at
+//    ~41 cycles each were 27 % of the tile time.)
+//  * the CLS key's gradient is accumulated in registers over the tiles of a (sequence, head) and flushed once;
+//  * the next tile's operands are TMA-loaded as soon as the current tile's last MMA has retired, its key-valid bits
+//    are built from mask bytes loaded a tile ahead (no global-load latency between tiles), its context / LSE rows are
+//    L2-prefetched; barriers and the 512 TMEM columns are set up once per CTA.
 __global__ void __launch_bounds__(AB_THREADS)
 band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_constant__ CUtensorMap tmQKV16,
                      const __grid_constant__ CUtensorMap tmDO, const AttnBwdParams p) {
@@ -79,11 +99,11 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   uint8_t* sV = smem + AB_OFF_V;
   uint8_t* sP = smem + AB_OFF_P;
   uint8_t* sDS = smem + AB_OFF_DS;
-  uint32_t* kbits = reinterpret_cast<uint32_t*>(smem + AB_OFF_FLAG);
+  uint32_t* kbits_all = reinterpret_cast<uint32_t*>(smem + AB_OFF_FLAG);   // [2][8]: double-buffered per tile
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + AB_OFF_BAR);
   uint64_t* bar_mma = bar_load + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
-  uint64_t* bar_kv = bar_load + 3;     // dK / dV accumulators ready (dQ is published earlier on bar_mma)
+  uint64_t* bar_kv = bar_load + 3;     // all dK / dV accumulators ready = every MMA of the tile retired (dQ: bar_mma)
   float* s_delta = reinterpret_cast<float*>(smem + AB_OFF_DELTA);   // [4][128] partial row sums
 
   // 16 warps: TMEM lane quadrant = warp % 4 (rows 32*quad..), `part` = warp / 4 splits every row's work
@@ -93,255 +113,371 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, part = warp >> 2;
   const int tiles_per_seq = (p.L + 127) / 128;
-  const int total_tiles = p.qtiles != nullptr ? *p.n_qtiles * p.H : p.B * p.H * tiles_per_seq;
-  // work item t -> (sequence b, head h, query tile): dense enumeration, or through the list of active query tiles
-  auto decode = [&](int t, int& tile, int& h, int& b) {
+  const int n_q = p.qtiles != nullptr ? *p.n_qtiles : 0;
+  const int total_tiles = p.qtiles != nullptr ? n_q * p.H : p.B * p.H * tiles_per_seq;
+  const int t_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * total_tiles / gridDim.x);
+  const int t_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * total_tiles / gridDim.x);
+  // work item t -> (sequence b, head h, query tile), the tile index fastest: dense enumeration, or head-major over the
+  // list of active query tiles (which is sorted by sequence, then tile).  Positions are decoded once and then ADVANCED
+  // (the divisions of a full decode per tile were ~1 500 cycles on every warp's critical path).
+  struct Pos { int tile, h, b, idx; };
+  auto decode = [&](int t) -> Pos {
+    Pos o;
     if (p.qtiles != nullptr) {
-      const int q = p.qtiles[t / p.H];
-      h = t % p.H;
-      tile = q % tiles_per_seq;
-      b = q / tiles_per_seq;
+      o.h = t / n_q;
+      o.idx = t - o.h * n_q;
+      const int q = p.qtiles[o.idx];
+      o.tile = q % tiles_per_seq;
+      o.b = q / tiles_per_seq;
     } else {
-      tile = t % tiles_per_seq;
-      h = (t / tiles_per_seq) % p.H;
-      b = t / (tiles_per_seq * p.H);
+      o.idx = 0;
+      o.tile = t % tiles_per_seq;
+      o.h = (t / tiles_per_seq) % p.H;
+      o.b = t / (tiles_per_seq * p.H);
     }
+    return o;
+  };
+  auto advance = [&](const Pos& c) -> Pos {
+    Pos o = c;
+    if (p.qtiles != nullptr) {
+      if (++o.idx == n_q) { o.idx = 0; ++o.h; }
+      const int q = p.qtiles[o.idx];
+      o.tile = q % tiles_per_seq;
+      o.b = q / tiles_per_seq;
+    } else if (++o.tile == tiles_per_seq) {
+      o.tile = 0;
+      if (++o.h == p.H) { o.h = 0; ++o.b; }
+    }
+    return o;
   };
   const int E = p.H * AB_D;
   constexpr uint32_t TM_S = 0, TM_DP = 256;                       // phase 1
   constexpr uint32_t TM_DQ = 0, TM_DV = 64, TM_DK = 192;          // phase 2 (dV: 2 x 64, dK: 2 x 64)
+  const bool carry_enabled = p.dkv == nullptr;    // bf16 path (attention_window 64); wide windows accumulate in fp32 scratch
 
-  // PERSISTENT: one CTA per SM walks the (b, h, tile) list.  The operand loads of the NEXT tile are issued as soon as
-  // the current tile's last MMAs have retired (every shared-memory operand is dead then), so they land while the dK / dV
-  // epilogue drains TMEM; barriers and the 512 TMEM columns are set up once per CTA.
-  auto issue_loads = [&](int t) {     // thread 0 only
-    int tile, h, b;
-    decode(t, tile, h, b);
+  // TMA loads of a tile's operands, in three groups (0: Q + dO and the expect_tx arrival, 1: K, 2: V; -1 = all) so
+  // that three lightly loaded warps can share the ~1 100 cycles of issue; complete_tx of a group may precede the
+  // expect_tx (the transaction count goes negative, the phase cannot complete before the arrival).
+  auto issue_loads = [&](const Pos& q, int group) {     // one thread per group
+    const int tile = q.tile, h = q.h, b = q.b;
     const int i0 = tile * 128, key0 = i0 - W + p.shift;
-    mbar_arrive_expect_tx(bar_load, 2 * AB_Q_BYTES + 2 * AB_KV_BYTES);
+    if (group <= 0) {
+      mbar_arrive_expect_tx(bar_load, 2 * AB_Q_BYTES + 2 * AB_KV_BYTES);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      tma_load_3d(sQ + c * 8192, &tmQKV64, bar_load, h * AB_D, i0 + c * 64, b);
-      tma_load_3d(sDO + c * 8192, &tmDO, bar_load, h * AB_D, i0 + c * 64, b);
+      for (int c = 0; c < 2; ++c) {
+        tma_load_3d(sQ + c * 8192, &tmQKV64, bar_load, h * AB_D, i0 + c * 64, b);
+        tma_load_3d(sDO + c * 8192, &tmDO, bar_load, h * AB_D, i0 + c * 64, b);
+      }
     }
+    if (group < 0 || group == 1) {
 #pragma unroll
-    for (int c = 0; c < NK / 64; ++c) {
-      tma_load_3d(sK + c * 8192, &tmQKV64, bar_load, E + h * AB_D, key0 + c * 64, b);
-      tma_load_3d(sV + c * 8192, &tmQKV64, bar_load, 2 * E + h * AB_D, key0 + c * 64, b);
+      for (int c = 0; c < NK / 64; ++c) tma_load_3d(sK + c * 8192, &tmQKV64, bar_load, E + h * AB_D, key0 + c * 64, b);
+      tma_load_3d(sK + NK * 128, &tmQKV16, bar_load, E + h * AB_D, 0, b);
     }
-    tma_load_3d(sK + NK * 128, &tmQKV16, bar_load, E + h * AB_D, 0, b);
-    tma_load_3d(sV + NK * 128, &tmQKV16, bar_load, 2 * E + h * AB_D, 0, b);
+    if (group < 0 || group == 2) {
+#pragma unroll
+      for (int c = 0; c < NK / 64; ++c) tma_load_3d(sV + c * 8192, &tmQKV64, bar_load, 2 * E + h * AB_D, key0 + c * 64, b);
+      tma_load_3d(sV + NK * 128, &tmQKV16, bar_load, 2 * E + h * AB_D, 0, b);
+    }
   };
+  // The mask byte that decides one key-valid bit of tile (b, tile): warps 0..5 = band columns, warp 6 lane 0 = the CLS
+  // key.  One unconditional byte load from a clamped address (`ok` says whether it counts), so that nothing but the
+  // load itself sits at the issue point: the value is consumed a tile phase later (store_kbits).
+  auto kbyte_addr = [&](int b, int tile, bool& ok) -> const uint8_t* {
+    const uint8_t* mrow = p.mask012 + static_cast<size_t>(b) * p.L;
+    const int j = tile * 128 - W + p.shift + warp * 32 + lane;
+    const bool band = warp < NK / 32;
+    ok = band ? (j >= 0 && j < p.L) : (warp == NK / 32 && lane == 0);
+    return mrow + ((band && ok) ? j : 0);
+  };
+  auto store_kbits = [&](uint32_t* kb, uint32_t kbyte, bool ok) {     // whole warps 0..6
+    if (warp < NK / 32) {
+      const uint32_t word = __ballot_sync(0xffffffffu, ok && kbyte == 1u);
+      if (lane == 0) kb[warp] = word;
+    } else if (warp == NK / 32 && lane == 0) {
+      kb[7] = (p.use_cls && kbyte == 2u) ? 1u : 0u;
+    }
+  };
+
+  // Per-thread global data of a tile (pulled into L2 a tile ahead, loaded at the top of the tile, first used after
+  // the S / dP MMAs have been issued): two 16-byte pieces of the saved context tile, read coalesced — lane = (row
+  // within a group of 4, 16-byte unit), 4 full lines per warp instruction — for delta_i = dO_i . O_i; this thread's
+  // row: log-sum-exp, mask bytes and the dropout keep bits the forward saved.
+  struct RowData { uint4 o[2]; float lse; uint32_t m_row, m_cls; uint4 kb; };
+  const int r = quad * 32 + lane;       // query row of the tile == TMEM lane
+  auto load_rows = [&](const Pos& q) -> RowData {
+    RowData d;
+    const int i0 = q.tile * 128;
+    const uint8_t* mrow = p.mask012 + static_cast<size_t>(q.b) * p.L;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int rr = (warp * 2 + u) * 4 + (lane >> 3);
+      d.o[u] = (i0 + rr < p.L) ? *reinterpret_cast<const uint4*>(p.ctx + (static_cast<size_t>(q.b) * p.L + i0 + rr) * E +
+                                                                 q.h * AB_D + (lane & 7) * 8)
+                               : make_uint4(0, 0, 0, 0);
+    }
+    const int i = i0 + r;
+    const bool in_seq = i < p.L;
+    const size_t rowid = (static_cast<size_t>(q.b) * p.H + q.h) * p.L + (in_seq ? i : 0);
+    d.lse = in_seq ? p.lse[rowid] : 0.f;
+    d.m_row = mrow[in_seq ? i : 0];
+    d.m_cls = mrow[0];
+    d.kb = (p.keepbits != nullptr && in_seq) ? p.keepbits[rowid] : make_uint4(0, 0, 0, 0);
+    return d;
+  };
+
   if (tid == 0) {
     mbar_init(bar_load, 1);
     mbar_init(bar_mma, 1);
     mbar_init(bar_kv, 1);
     fence_mbar_init();
-    if (static_cast<int>(blockIdx.x) < total_tiles) issue_loads(blockIdx.x);
+    if (t_begin < t_end) issue_loads(decode(t_begin), -1);
   }
   __syncwarp();
   if (warp == 0) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  uint32_t it = 0;      // tiles processed by this CTA: parity of the once-per-tile barriers
-#pragma unroll 1
-  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-  int tile, h, b;
-  decode(t, tile, h, b);
-  const int i0 = tile * 128;
-  const uint8_t* mrow = p.mask012 + static_cast<size_t>(b) * p.L;
-  const int key0 = i0 - W + p.shift;             // absolute key index of tile column 0
-  // Per-row global loads issued right away (they are first used after the S / dP MMAs): this thread's quarter
-  // (16 of 64 dims) of the saved context row, the row's log-sum-exp and its mask bytes.
-  const int r = quad * 32 + lane;       // query row of the tile == TMEM lane
-  const int i = i0 + r;
-  const bool in_seq = i < p.L;
-  uint4 o_raw[2];
-  {
-    const uint4* op = reinterpret_cast<const uint4*>(p.ctx + (static_cast<size_t>(b) * p.L + (in_seq ? i : 0)) * E +
-                                                     h * AB_D + part * 16);
-#pragma unroll
-    for (int u = 0; u < 2; ++u) o_raw[u] = in_seq ? op[u] : make_uint4(0, 0, 0, 0);
-  }
-  const float lse = in_seq ? p.lse[(static_cast<size_t>(b) * p.H + h) * p.L + i] : 0.f;
-  const uint8_t m_row = mrow[in_seq ? i : 0], m_cls = mrow[0];
-  // key-valid bits of the NK band columns (bit c: key is in range, not padding, not global); word 7 bit 0 = CLS column
-  if (warp < NK / 32) {
-    const int j = key0 + warp * 32 + lane;
-    const bool inr = j >= 0 && j < p.L;
-    const uint32_t word = __ballot_sync(0xffffffffu, inr && (mrow[inr ? j : 0] == 1));
-    if (lane == 0) kbits[warp] = word;
-  } else if (warp == NK / 32 && lane == 0) {
-    kbits[7] = (p.use_cls && mrow[0] == 2) ? 1u : 0u;
+  Pos cur = decode(t_begin < t_end ? t_begin : 0);
+  if (t_begin < t_end && warp <= NK / 32) {
+    bool ok;
+    const uint8_t* ka = kbyte_addr(cur.b, cur.tile, ok);
+    store_kbits(kbits_all, *ka, ok);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (tid == 0) {
-    mbar_wait(bar_load, it & 1);
+  // Control warp = warp 15 (quad 3, part 3): the lightest compute share in both phases (zero fill only in the softmax
+  // backward, no second key half in the dK / dV epilogue), so the serial issue work (45 MMAs, 12 TMA loads per tile)
+  // delays nobody else.
+  const bool ctrl = warp == 15;
+  // MMA issue: the control warp stays converged, the descriptors are warp-uniform 64-bit values (tile bases built once, the
+  // k-step / chunk offsets added in the 16-byte-granular address field), only the tcgen05 instructions are
+  // predicated on the elected lane
+  const bool elected = elect_one();
+  const uint64_t dQ_k = umma_smem_desc(smem_u32(sQ), 16, 1024), dK_k = umma_smem_desc(smem_u32(sK), 16, 1024);
+  const uint64_t dDO_k = umma_smem_desc(smem_u32(sDO), 16, 1024), dV_k = umma_smem_desc(smem_u32(sV), 16, 1024);
+  const uint64_t dDS_k = umma_smem_desc(smem_u32(sDS), 16, 1024);
+  const uint64_t dK_mn = umma_smem_desc(smem_u32(sK), 8192, 1024), dQ_mn = umma_smem_desc(smem_u32(sQ), 8192, 1024);
+  const uint64_t dDO_mn = umma_smem_desc(smem_u32(sDO), 8192, 1024);
+  const uint64_t dP_mn = umma_smem_desc(smem_u32(sP), 16384, 1024), dDS_mn = umma_smem_desc(smem_u32(sDS), 16384, 1024);
+
+  float carry[32];      // quad 0/1: the shared 64 keys' partial dK / dV of the previous tile; quad 2 (lane 0): the CLS key's sum
+#pragma unroll
+  for (int j = 0; j < 32; ++j) carry[j] = 0.f;
+  bool carry_in = false;
+  uint32_t it = 0;      // tiles processed by this CTA: parity of the once-per-tile barriers
+#pragma unroll 1
+  for (int t = t_begin; t < t_end; ++t, ++it) {
+  KT(0);
+  const int tile = cur.tile, h = cur.h, b = cur.b;
+  const bool has_next = t + 1 < t_end;
+  Pos nxt = cur;
+  if (has_next) nxt = advance(cur);
+  const int tile_n = nxt.tile, h_n = nxt.h, b_n = nxt.b;
+  const bool same_bh_next = has_next && b_n == b && h_n == h;
+  const bool carry_out = carry_enabled && same_bh_next && tile_n == tile + 1;
+  KT(12);
+  const uint32_t* kbits = kbits_all + (it & 1) * 8;
+  const int i0 = tile * 128;
+  const uint8_t* mrow = p.mask012 + static_cast<size_t>(b) * p.L;
+  const int key0 = i0 - W + p.shift;             // absolute key index of tile column 0
+  const int i = i0 + r;
+  const bool in_seq = i < p.L;
+  RowData rd = load_rows(cur);
+  uint32_t kbyte_n = 0;     // the mask byte behind one key-valid bit of the NEXT tile (turned into bits after this tile's last MMA)
+  bool kbyte_ok = false;
+  if (has_next && warp <= NK / 32)      // (volatile: the compiler must not sink the load down to its first use)
+    asm volatile("ld.global.u8 %0, [%1];" : "=r"(kbyte_n) : "l"(kbyte_addr(b_n, tile_n, kbyte_ok)));
+  const uint64_t rowid = (static_cast<uint64_t>(b) * p.H + h) * p.L + (in_seq ? i : 0);
+  const uint64_t rowbase = rowid * attn_drop_groups(p.L);
+  KT(1);
+
+  mbar_wait(bar_load, it & 1);       // every warp: dO is needed for delta below
+  if (ctrl) {
+    KT(2);
     tc_fence_after();
     constexpr uint32_t idesc = umma_idesc_bf16(128, NT, false, false);
-    const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK), ado = smem_u32(sDO), av = smem_u32(sV);
+    if (elected) {
 #pragma unroll
-    for (int k = 0; k < AB_D / 16; ++k)
-      umma_bf16(tmem + TM_S, umma_smem_desc(aq + k * 32, 16, 1024), umma_smem_desc(ak + k * 32, 16, 1024), idesc,
-                k > 0 ? 1u : 0u);
+      for (int k = 0; k < AB_D / 16; ++k) umma_bf16(tmem + TM_S, dQ_k + k * 2, dK_k + k * 2, idesc, k > 0 ? 1u : 0u);
 #pragma unroll
-    for (int k = 0; k < AB_D / 16; ++k)
-      umma_bf16(tmem + TM_DP, umma_smem_desc(ado + k * 32, 16, 1024), umma_smem_desc(av + k * 32, 16, 1024), idesc,
-                k > 0 ? 1u : 0u);
-    umma_commit(bar_mma);
+      for (int k = 0; k < AB_D / 16; ++k) umma_bf16(tmem + TM_DP, dDO_k + k * 2, dV_k + k * 2, idesc, k > 0 ? 1u : 0u);
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
   }
-  __syncwarp();
+  // The registers loaded above become visible to the compiler HERE: without this fence ptxas schedules their first
+  // consumers (bf16 unpacks, the lse scaling) right behind the loads, i.e. in front of the MMA issue, and the
+  // global-load latency lands on the critical path of every tile.
+  asm volatile("" : "+r"(rd.o[0].x), "+r"(rd.o[0].y), "+r"(rd.o[0].z), "+r"(rd.o[0].w), "+r"(rd.o[1].x), "+r"(rd.o[1].y),
+                    "+r"(rd.o[1].z), "+r"(rd.o[1].w), "+f"(rd.lse), "+r"(rd.m_row), "+r"(rd.m_cls), "+r"(rd.kb.x),
+                    "+r"(rd.kb.y), "+r"(rd.kb.z), "+r"(rd.kb.w));
+  const float lse = rd.lse;
+  const uint32_t m_row = rd.m_row, m_cls = rd.m_cls;
+  const uint4 kb_row = rd.kb;
+  float keep_g = 1.f;        // dropout factor of the CLS column (part 3 uses it)
+  if (part == 3 && p.drop_thresh != 0)
+    keep_g = p.keepbits != nullptr ? (((kb_row.w >> 16) & 1u) ? p.drop_scale : 0.f)
+                                   : attn_keep_cls(p.drop_seed, rowbase, p.drop_thresh, p.drop_scale);
+  // ---- delta_i = sum_j P'_ij dP_ij = dO_i . O_i  (O = sum_j P'_ij V_j is the saved forward output), computed under
+  //      the S / dP MMAs: 8 dims per lane (dO from the swizzled shared-memory tile), 8 lanes per row ----
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int rr = (warp * 2 + u) * 4 + (lane >> 3);
+    const uint4 d = *reinterpret_cast<const uint4*>(sDO + (rr >> 6) * 8192 + (rr & 63) * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+    const uint4 o = rd.o[u];
+    const float2 d0 = unpack_bf16(d.x), d1 = unpack_bf16(d.y), d2 = unpack_bf16(d.z), d3 = unpack_bf16(d.w);
+    const float2 o0 = unpack_bf16(o.x), o1 = unpack_bf16(o.y), o2 = unpack_bf16(o.z), o3 = unpack_bf16(o.w);
+    float dl = d0.x * o0.x + d0.y * o0.y + d1.x * o1.x + d1.y * o1.y + d2.x * o2.x + d2.y * o2.y + d3.x * o3.x + d3.y * o3.y;
+    dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+    dl += __shfl_xor_sync(0xffffffffu, dl, 2);
+    dl += __shfl_xor_sync(0xffffffffu, dl, 4);
+    if ((lane & 7) == 0) s_delta[rr] = dl;
+  }
   mbar_wait(bar_mma, 0);
   tc_fence_after();
+  KT(3);
 
   const bool is_global_row = (i == 0) && (m_cls == 2);
   const bool row_valid = in_seq && (m_row != 0) && !is_global_row;
   const uint32_t lane_base = tmem + (static_cast<uint32_t>(quad * 32) << 16);
   const float LOG2E = 1.4426950408889634f;
   const float lse2 = lse * LOG2E;
-  const uint64_t rowid = (static_cast<uint64_t>(b) * p.H + h) * p.L + (in_seq ? i : 0);
-  const uint64_t rowbase = rowid * attn_drop_groups(p.L);
   const bool g_ok = kbits[7] != 0;
-  // window chunks of this row block: quad + part for parts 0..2; part 3 has the CLS column and the zero chunks
-  const int cc_lo = quad + part;
-  const int cc_hi = part < 3 ? quad + part + 1 : cc_lo;
+  const int band_hi = 2 * W - p.hi_cut;      // a row's live columns: key-valid bits AND band position [r, r + band_hi]
 
-  // live columns of a 32-column chunk for this row: key-valid bits AND band position [r, r + 2W - hi_cut]
-  const int band_hi = 2 * W - p.hi_cut;
-  auto chunk_live = [&](int cc) -> uint32_t {
-    const int lo = r - cc * 32, hi = r + band_hi - cc * 32;
-    const uint32_t mlo = lo <= 0 ? 0xFFFFFFFFu : (lo >= 32 ? 0u : (0xFFFFFFFFu << lo));
-    const uint32_t mhi = hi >= 31 ? 0xFFFFFFFFu : (hi < 0 ? 0u : (0xFFFFFFFFu >> (31 - hi)));
-    return row_valid ? (kbits[cc] & mlo & mhi) : 0u;
-  };
-
-  // ---- delta_i = sum_j P'_ij dP_ij = dO_i . O_i  (O = sum_j P'_ij V_j is the saved forward output):
-  //      each part dots its 16 dims (dO from the swizzled shared-memory tile, O from registers) ----
-  float delta = 0.f;
-  {
-    const uint8_t* drow = sDO + (r >> 6) * 8192 + (r & 63) * 128;
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const uint4 d = *reinterpret_cast<const uint4*>(drow + (((part * 2 + u) ^ (r & 7)) << 4));
-      const uint4 o = o_raw[u];
-      const float2 d0 = unpack_bf16(d.x), d1 = unpack_bf16(d.y), d2 = unpack_bf16(d.z), d3 = unpack_bf16(d.w);
-      const float2 o0 = unpack_bf16(o.x), o1 = unpack_bf16(o.y), o2 = unpack_bf16(o.z), o3 = unpack_bf16(o.w);
-      delta += d0.x * o0.x + d0.y * o0.y + d1.x * o1.x + d1.y * o1.y + d2.x * o2.x + d2.y * o2.y + d3.x * o3.x +
-               d3.y * o3.y;
-    }
-  }
-  float pg = 0.f, pg_d = 0.f, keep_g = 1.f, dpg = 0.f;
-  if (part == 3) {   // warp-uniform
-    uint32_t gs[16], gd[16];
-    tmem_ld16(lane_base + TM_S + NK, gs);
-    tmem_ld16(lane_base + TM_DP + NK, gd);
+  float pg = 0.f, pg_d = 0.f, dpg = 0.f;
+  if (part == 3) {   // warp-uniform: the CLS column
+    uint32_t gs[8], gd[8];
+    tmem_ld8(lane_base + TM_S + NK, gs);
+    tmem_ld8(lane_base + TM_DP + NK, gd);
     tmem_ld_wait();
     pg = (row_valid && g_ok) ? exp2f(__uint_as_float(gs[0]) * LOG2E - lse2) : 0.f;   // undropped
-    pg_d = pg;
-    if (p.drop_thresh != 0) {
-      keep_g = attn_keep_cls(p.drop_seed, rowbase, p.drop_thresh, p.drop_scale);
-      pg_d = pg * keep_g;
-    }
+    pg_d = pg * keep_g;
     dpg = __uint_as_float(gd[0]);
   }
-  s_delta[part * 128 + r] = delta;
   __syncthreads();
+  KT(4);
   // masked rows may hold non-finite garbage in O / dO
-  delta = row_valid ? (s_delta[r] + s_delta[128 + r]) + (s_delta[256 + r] + s_delta[384 + r]) : 0.f;
+  const float delta = row_valid ? s_delta[r] : 0.f;
 
-  // ---- pass B: P' and dS -> shared memory (one window chunk per part 0..2; part 3 fills the all-zero chunks) ----
-#pragma unroll 1
-  for (int cc = 0; cc < NK / 32; ++cc) {
-    const bool in_win = cc >= quad && cc < quad + 3;
-    const bool mine = in_win ? (cc >= cc_lo && cc < cc_hi) : (part == 3);
-    if (!mine) continue;   // warp-uniform
-    uint4 po[4], so[4];
-    if (in_win) {
-      uint32_t sv[32], dv[32];
-      tmem_ld32(lane_base + TM_S + cc * 32, sv);
-      tmem_ld32(lane_base + TM_DP + cc * 32, dv);
-      tmem_ld_wait();
-      const uint32_t live = chunk_live(cc);
-      const uint32_t keepm = (p.drop_thresh != 0 && live != 0)
-                                 ? attn_keep32(p.drop_seed, rowbase, key0 + cc * 32, p.drop_thresh, live) : 0xFFFFFFFFu;
-      float pr[32], ds[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float pu = ((live >> j) & 1u) ? exp2f(__uint_as_float(sv[j]) * LOG2E - lse2) : 0.f;
-        const float kp = ((keepm >> j) & 1u) ? p.drop_scale : 0.f;
-        pr[j] = pu * kp;                                           // P' feeds dV
-        ds[j] = pu * (kp * __uint_as_float(dv[j]) - delta);        // softmax backward
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        po[u] = make_uint4(pack_bf16(pr[u * 8], pr[u * 8 + 1]), pack_bf16(pr[u * 8 + 2], pr[u * 8 + 3]),
-                           pack_bf16(pr[u * 8 + 4], pr[u * 8 + 5]), pack_bf16(pr[u * 8 + 6], pr[u * 8 + 7]));
-        so[u] = make_uint4(pack_bf16(ds[u * 8], ds[u * 8 + 1]), pack_bf16(ds[u * 8 + 2], ds[u * 8 + 3]),
-                           pack_bf16(ds[u * 8 + 4], ds[u * 8 + 5]), pack_bf16(ds[u * 8 + 6], ds[u * 8 + 7]));
-      }
-    } else {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) po[u] = so[u] = make_uint4(0, 0, 0, 0);
-    }
-    const uint32_t roff = (cc >> 1) * 16384 + r * 128;
-    const int ubase = (cc & 1) * 4;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t o = roff + (((ubase + u) ^ (r & 7)) << 4);
-      *reinterpret_cast<uint4*>(sP + o) = po[u];
-      *reinterpret_cast<uint4*>(sDS + o) = so[u];
-    }
-  }
+  // ---- pass B: P' and dS -> shared memory.  The 96 window columns [32 quad, 32 quad + 96) of a row quadrant are split
+  //      evenly between the four parts: 24 columns (three 8-key groups) each ----
   {
-    // global chunk = P/dS chunk 3 (columns 192..255): column 192 holds the CLS key, the rest is zero;
-    // part 3 (which owns pg) writes units 0..3, part 0 units 4..7
-    const float dsg = pg * (keep_g * dpg - delta);
-    const uint32_t roff = 3 * 16384 + r * 128;
+    const int c0 = quad * 32 + part * 24;                 // first tile column of this thread's piece
+    uint32_t sv[24], dv[24];
+    {
+      uint32_t a16[16], a8[8], b16[16], b8[8];
+      tmem_ld16(lane_base + TM_S + c0, a16);
+      tmem_ld8(lane_base + TM_S + c0 + 16, a8);
+      tmem_ld16(lane_base + TM_DP + c0, b16);
+      tmem_ld8(lane_base + TM_DP + c0 + 16, b8);
+      tmem_ld_wait();
 #pragma unroll
-    for (int uu = 0; uu < 4; ++uu) {
-      if (part == 1 || part == 2) continue;   // warp-uniform
-      const int u = part == 3 ? uu : uu + 4;
-      const uint32_t o = roff + ((u ^ (r & 7)) << 4);
+      for (int j = 0; j < 16; ++j) { sv[j] = a16[j]; dv[j] = b16[j]; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sv[16 + j] = a8[j]; dv[16 + j] = b8[j]; }
+    }
+    uint32_t live;
+    {
+      const int wi = c0 >> 5, sh = c0 & 31;
+      const uint64_t kw = (static_cast<uint64_t>(kbits[wi + 1]) << 32) | kbits[wi];     // wi + 1 <= 6 (unused word: masked off)
+      const int lo = r - c0, hi = r + band_hi - c0;
+      const uint32_t mlo = lo <= 0 ? 0xFFFFFFu : (lo >= 24 ? 0u : ((0xFFFFFFu << lo) & 0xFFFFFFu));
+      const uint32_t mhi = hi >= 23 ? 0xFFFFFFu : (hi < 0 ? 0u : (0xFFFFFFu >> (23 - hi)));
+      live = row_valid ? (static_cast<uint32_t>(kw >> sh) & mlo & mhi) : 0u;
+    }
+    uint32_t keepm = 0xFFFFFFu;
+    if (p.drop_thresh != 0) {
+      if (p.keepbits != nullptr) {
+        // the forward saved the row's keep bits: u16 x 8 = [unit 0, 1, 2, -, unit 3, 4, 5, CLS], unit = 16 window columns
+        const uint64_t lo64 = static_cast<uint64_t>(kb_row.x) | (static_cast<uint64_t>(kb_row.y & 0xFFFFu) << 32) |
+                              (static_cast<uint64_t>(kb_row.z & 0xFFFFu) << 48);
+        const uint32_t hi32 = (kb_row.z >> 16) | (kb_row.w << 16);
+        keepm = part == 0 ? static_cast<uint32_t>(lo64)
+              : part == 1 ? static_cast<uint32_t>(lo64 >> 24)
+              : part == 2 ? (static_cast<uint32_t>(lo64 >> 48) | (hi32 << 16))
+                          : (hi32 >> 8);
+      } else if (live != 0) {
+        keepm = attn_keep32(p.drop_seed, rowbase, key0 + c0, p.drop_thresh, live);
+      }
+    }
+    uint32_t po[12], so[12];
+#pragma unroll
+    for (int j = 0; j < 24; j += 2) {
+      float pr[2], ds[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float pu = ((live >> (j + e)) & 1u) ? exp2f(__uint_as_float(sv[j + e]) * LOG2E - lse2) : 0.f;
+        const float kp = ((keepm >> (j + e)) & 1u) ? p.drop_scale : 0.f;
+        pr[e] = pu * kp;                                               // P' feeds dV
+        ds[e] = pu * (kp * __uint_as_float(dv[j + e]) - delta);        // softmax backward
+      }
+      po[j >> 1] = pack_bf16(pr[0], pr[1]);
+      so[j >> 1] = pack_bf16(ds[0], ds[1]);
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int c = c0 + u * 8;
+      const uint32_t o = (c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4);
+      *reinterpret_cast<uint4*>(sP + o) = make_uint4(po[u * 4], po[u * 4 + 1], po[u * 4 + 2], po[u * 4 + 3]);
+      *reinterpret_cast<uint4*>(sDS + o) = make_uint4(so[u * 4], so[u * 4 + 1], so[u * 4 + 2], so[u * 4 + 3]);
+    }
+    // zero fill of the 96 band columns outside the window (twelve 8-column units, three per part) ...
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int k = part * 3 + u;
+      const int cu = k < 4 * quad ? k : k + 12;           // 8-column unit of the tile
+      const uint32_t o = (cu >> 3) * 16384 + r * 128 + (((cu & 7) ^ (r & 7)) << 4);
+      *reinterpret_cast<uint4*>(sP + o) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sDS + o) = make_uint4(0, 0, 0, 0);
+    }
+    // ... and the global chunk = P/dS chunk 3 (columns 192..255): column 192 holds the CLS key, the rest is zero;
+    // part 3 (which owns pg) writes units 0, 1, parts 0..2 units 2..7
+    const float dsg = pg * (keep_g * dpg - delta);
+#pragma unroll
+    for (int uu = 0; uu < 2; ++uu) {
+      const int u = ((part + 1) & 3) * 2 + uu;
+      const uint32_t o = 3 * 16384 + r * 128 + ((u ^ (r & 7)) << 4);
       *reinterpret_cast<uint4*>(sP + o) = (u == 0) ? make_uint4(pack_bf16(pg_d, 0.f), 0, 0, 0) : make_uint4(0, 0, 0, 0);
       *reinterpret_cast<uint4*>(sDS + o) = (u == 0) ? make_uint4(pack_bf16(dsg, 0.f), 0, 0, 0) : make_uint4(0, 0, 0, 0);
     }
   }
 
+  KT(5);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) {
+  KT(6);
+  if (ctrl) {
     tc_fence_after();
-    const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK), ado = smem_u32(sDO), ap = smem_u32(sP), ads = smem_u32(sDS);
-    // dQ[128 x 64] = dS[128 x 208] K[208 x 64]
     constexpr uint32_t idesc_q = umma_idesc_bf16(128, AB_D, false, true);
-#pragma unroll
-    for (int ks = 0; ks < NT / 16; ++ks)
-      umma_bf16(tmem + TM_DQ, umma_smem_desc(ads + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                umma_smem_desc(ak + ks * 2048, 8192, 1024), idesc_q, ks > 0 ? 1u : 0u);
-    umma_commit(bar_mma);   // dQ is stored while the dK / dV MMAs below still run
-    // dV[keys x 64] = P^T dO,  dK[keys x 64] = dS^T Q   (two 128-key halves each)
     constexpr uint32_t idesc_kv = umma_idesc_bf16(128, AB_D, true, true);
+    if (elected) {
+      // dQ[128 x 64] = dS[128 x 208] K[208 x 64]   (dS chunk of 64 keys = +16384 B, k-step = +32 B; K rows: +2048 B)
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
+      for (int ks = 0; ks < NT / 16; ++ks)
+        umma_bf16(tmem + TM_DQ, dDS_k + ((ks >> 2) * 1024 + (ks & 3) * 2), dK_mn + ks * 128, idesc_q, ks > 0 ? 1u : 0u);
+      umma_commit(bar_mma);   // dQ is stored while the dK / dV MMAs below still run
+      // dV[keys x 64] = P^T dO,  dK[keys x 64] = dS^T Q   (two 128-key halves each)
 #pragma unroll
-      for (int ks = 0; ks < 128 / 16; ++ks) {
-        umma_bf16(tmem + TM_DV + hh * 64, umma_smem_desc(ap + hh * 32768 + ks * 2048, 16384, 1024),
-                  umma_smem_desc(ado + ks * 2048, 8192, 1024), idesc_kv, ks > 0 ? 1u : 0u);
-        umma_bf16(tmem + TM_DK + hh * 64, umma_smem_desc(ads + hh * 32768 + ks * 2048, 16384, 1024),
-                  umma_smem_desc(aq + ks * 2048, 8192, 1024), idesc_kv, ks > 0 ? 1u : 0u);
+      for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+        for (int ks = 0; ks < 128 / 16; ++ks) {
+          umma_bf16(tmem + TM_DV + hh * 64, dP_mn + (hh * 2048 + ks * 128), dDO_mn + ks * 128, idesc_kv, ks > 0 ? 1u : 0u);
+          umma_bf16(tmem + TM_DK + hh * 64, dDS_mn + (hh * 2048 + ks * 128), dQ_mn + ks * 128, idesc_kv, ks > 0 ? 1u : 0u);
+        }
       }
+      umma_commit(bar_kv);
     }
-    umma_commit(bar_kv);
+    __syncwarp();
   }
-  __syncwarp();
   mbar_wait(bar_mma, 1);
   tc_fence_after();
+  KT(7);
 
   // ---- dQ (x 1/sqrt(D): gradient w.r.t. the unscaled projection); part p owns columns 16p..16p+15 ----
   {
@@ -357,50 +493,113 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
                      "f"(__uint_as_float(v[j + 3]) * 0.125f)
                      : "memory");
     } else if (in_seq) {
-      __nv_bfloat16* orow = p.dqkv + (static_cast<size_t>(b) * p.L + i) * 3 * E + h * AB_D + part * 16;
+      // bf16 path: this thread's 16 dims are one full 32-byte sector of the row (the four parts complete the 128-byte
+      // line): a single 256-bit store
+      uint32_t o[8];
 #pragma unroll
-      for (int j = 0; j < 16; j += 8) {
-        uint4 o;
-        o.x = pack_bf16(__uint_as_float(v[j]) * 0.125f, __uint_as_float(v[j + 1]) * 0.125f);
-        o.y = pack_bf16(__uint_as_float(v[j + 2]) * 0.125f, __uint_as_float(v[j + 3]) * 0.125f);
-        o.z = pack_bf16(__uint_as_float(v[j + 4]) * 0.125f, __uint_as_float(v[j + 5]) * 0.125f);
-        o.w = pack_bf16(__uint_as_float(v[j + 6]) * 0.125f, __uint_as_float(v[j + 7]) * 0.125f);
-        *reinterpret_cast<uint4*>(orow + j) = o;
-      }
+      for (int j = 0; j < 8; ++j) o[j] = pack_bf16(__uint_as_float(v[2 * j]) * 0.125f, __uint_as_float(v[2 * j + 1]) * 0.125f);
+      st_global_v8(p.dqkv + (static_cast<size_t>(b) * p.L + i) * 3 * E + h * AB_D + part * 16, o);
     }
   }
+  KT(8);
+  // Once every MMA of this tile has retired, Q / dO / K / V are dead: the next tile's loads are issued (lane 0 of
+  // warps 3, 7, 11: quadrant 3 has no second key half to store), its key-valid bits built from the bytes loaded at the
+  // top of this tile, and its per-row global data (saved context rows, log-sum-exps, keep bits) pulled into L2.
+  auto next_tile_setup = [&]() {
+    if (!has_next) return;
+    if (quad == 3 && part < 3 && lane == 0) issue_loads(nxt, part);
+    __syncwarp();
+    asm volatile("" : "+r"(kbyte_n));      // (first use of the byte loaded at the top of the tile: see the fence above)
+    if (warp <= NK / 32) store_kbits(kbits_all + ((it + 1) & 1) * 8, kbyte_n, kbyte_ok);
+    const size_t row0 = (static_cast<size_t>(b_n) * p.H + h_n) * p.L + tile_n * 128;
+    if (tid < 128) {
+      if (tile_n * 128 + tid < p.L)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.ctx + (static_cast<size_t>(b_n) * p.L + tile_n * 128 + tid) * E + h_n * AB_D));
+    } else if (tid < 132) {
+      if (tile_n * 128 + (tid - 128) * 32 < p.L) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.lse + row0 + (tid - 128) * 32));
+    } else if (tid < 148 && p.keepbits != nullptr) {
+      if (tile_n * 128 + (tid - 132) * 8 < p.L) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.keepbits + row0 + (tid - 132) * 8));
+    }
+  };
+  // (Publishing the first key half's accumulators early and draining them under the second half's MMAs was measured
+  // slower: the tcgen05.ld traffic delays the MMAs, which are shared-memory-bandwidth bound at N = 64.)
   mbar_wait(bar_kv, it & 1);
   tc_fence_after();
-  // every MMA of this tile has retired: Q / dO / K / V are dead -> start the next tile's loads under the epilogue below
-  if (t + static_cast<int>(gridDim.x) < total_tiles) {
-    const int tn = t + gridDim.x;
-    if (tid == 0) issue_loads(tn);
-    // ... and pull the next tile's per-row data (saved context quarter, log-sum-exp) into L2: those plain loads sit on
-    // the next iteration's critical path (their DRAM latency was the top stall of the one-shot kernel)
-    int tilen, hn, bn;
-    decode(tn, tilen, hn, bn);
-    const int in_ = tilen * 128 + r;
-    if (in_ < p.L) {
-      const void* pc = p.ctx + (static_cast<size_t>(bn) * p.L + in_) * E + hn * AB_D + part * 16;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(pc));
-      if (part == 0) {
-        const void* pl = p.lse + (static_cast<size_t>(bn) * p.H + hn) * p.L + in_;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pl));
-      }
-    }
-  }
+  KT(9);
+  next_tile_setup();
+  KT(13);
   // every shared-memory operand is dead now: the P region becomes 16 per-warp 4 KB transpose slabs
   uint8_t* slab = sP + warp * 4096;
   // ---- dK / dV: TMEM lane = key column c = hh*128 + r of the tile.  Each 32-key x 32-dim chunk is
-  //      transposed through the warp's slab so that one red.add.v4 instruction covers 4 key rows x
-  //      128 contiguous bytes (4 LSU wavefronts) instead of 32 rows x 16 bytes. ----
+  //      bf16 path: straight from registers (below); fp32 path: through the warp's transpose slab. ----
   const int which = part >> 1, dhalf = part & 1;   // this warp: dK (0) or dV (1), dims 32*dhalf .. +31
 #pragma unroll 1
   for (int hh = 0; hh < 2; ++hh) {    // the two 128-key halves of the tile
+    if (carry_enabled && hh == 1 && quad == 3) continue;          // tile columns 224..255: nothing there
     const uint32_t tcol = (which == 0 ? TM_DK : TM_DV) + hh * 64 + dhalf * 32;
     uint32_t v[32];
     tmem_ld32(lane_base + tcol, v);
     tmem_ld_wait();
+    bool use_red = true;          // warp-uniform: may another CTA (or a non-adjacent tile) add to these keys?
+    if (carry_enabled) {
+      if (hh == 0) {
+        if (quad < 2) {           // keys shared with the previous tile
+          if (carry_in) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + carry[j]);
+            use_red = false;
+          }
+        } else {
+          use_red = false;        // keys [i0 + 32, i0 + 96): only this tile's queries see them
+        }
+      } else if (quad < 2) {      // keys shared with the next tile
+        if (carry_out) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) carry[j] = __uint_as_float(v[j]);
+          continue;               // stored by the next tile
+        }
+      } else {                    // quad 2: lane 0 = the CLS key column (the other lanes hold zeros)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) carry[j] += __uint_as_float(v[j]);
+        if (!same_bh_next) {      // last tile of this (sequence, head) in this CTA's run: flush, fp32
+          if (lane == 0 && p.use_cls) {
+            float* dst = p.dkv_cls + ((static_cast<size_t>(b) * p.H + h) * 2 + which) * AB_D + dhalf * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(carry[j]), "f"(carry[j + 1]),
+                           "f"(carry[j + 2]), "f"(carry[j + 3])
+                           : "memory");
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) carry[j] = 0.f;
+        }
+        continue;
+      }
+    }
+    if (p.dkv == nullptr) {
+      // bf16 path (band keys only: the CLS column went into `carry` above): this thread = key row c, its 32 dims are
+      // 64 contiguous bytes of the gradient row: two 256-bit stores, or four bf16x2 red.adds on keys another CTA shares
+      const int c = hh * 128 + quad * 32 + lane;      // < NK here
+      if ((kbits[c >> 5] >> (c & 31)) & 1u) {
+        __nv_bfloat16* dst = p.dqkv + (static_cast<size_t>(b) * p.L + key0 + c) * 3 * E + (1 + which) * E + h * AB_D + dhalf * 32;
+        uint32_t o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        if (use_red) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst + 2 * j), "r"(o[j]), "r"(o[j + 1]),
+                         "r"(o[j + 2]), "r"(o[j + 3])
+                         : "memory");
+        } else {
+          st_global_v8(dst, o);
+          st_global_v8(dst + 16, o + 8);
+        }
+      }
+      continue;
+    }
+    // fp32 path (wide windows): the 32-key x 32-dim chunk is transposed through the warp's slab so that one red.add.v4
+    // instruction covers 4 key rows x 128 contiguous bytes (4 LSU wavefronts) instead of 32 rows x 16 bytes
     {
       uint8_t* srow = slab + lane * 128;
 #pragma unroll
@@ -408,57 +607,32 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
         *reinterpret_cast<uint4*>(srow + ((u ^ (lane & 7)) << 4)) = make_uint4(v[u * 4], v[u * 4 + 1], v[u * 4 + 2], v[u * 4 + 3]);
     }
     __syncwarp();
-    if (p.dkv != nullptr) {
 #pragma unroll
-      for (int s2 = 0; s2 < 8; ++s2) {
-        const int rl = s2 * 4 + (lane >> 3);          // key row within this warp's 32
-        const int u = lane & 7;                       // 16B unit = 4 floats of the 32-dim chunk
-        const int c = hh * 128 + quad * 32 + rl;      // key column of the tile
-        int j = -1;
-        if (c < NK) j = key0 + c;
-        else if (c == NK) j = 0;
-        const bool key_ok = (c < NK) ? ((kbits[c >> 5] >> (c & 31)) & 1u) != 0 : (c == NK && g_ok);
-        const float4 x = *reinterpret_cast<const float4*>(slab + rl * 128 + ((u ^ (rl & 7)) << 4));
-        if (key_ok) {
-          float* dst = p.dkv + (static_cast<size_t>(b) * p.L + j) * 2 * E + which * E + h * AB_D + dhalf * 32 + u * 4;
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
-                       : "memory");
-        }
-      }
-    } else {
-      // bf16 path: lane owns 8 dims (two 16-byte units) of key row rl: one 16-byte bf16x2 red.add per lane,
-      // 8 key rows x 64 contiguous bytes per instruction
-#pragma unroll
-      for (int s2 = 0; s2 < 4; ++s2) {
-        const int rl = s2 * 8 + (lane >> 2);
-        const int uu = lane & 3;
-        const int c = hh * 128 + quad * 32 + rl;
-        int j = -1;
-        if (c < NK) j = key0 + c;
-        else if (c == NK) j = 0;
-        const bool key_ok = (c < NK) ? ((kbits[c >> 5] >> (c & 31)) & 1u) != 0 : (c == NK && g_ok);
-        const float4 x0 = *reinterpret_cast<const float4*>(slab + rl * 128 + (((2 * uu) ^ (rl & 7)) << 4));
-        const float4 x1 = *reinterpret_cast<const float4*>(slab + rl * 128 + (((2 * uu + 1) ^ (rl & 7)) << 4));
-        if (key_ok && c == NK) {        // the CLS key: fp32 accumulation over all tiles of the sequence
-          float* dst = p.dkv_cls + ((static_cast<size_t>(b) * p.H + h) * 2 + which) * AB_D + dhalf * 32 + uu * 8;
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x0.x), "f"(x0.y), "f"(x0.z), "f"(x0.w)
-                       : "memory");
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(x1.x), "f"(x1.y), "f"(x1.z), "f"(x1.w)
-                       : "memory");
-        } else if (key_ok) {
-          __nv_bfloat16* dst = p.dqkv + (static_cast<size_t>(b) * p.L + j) * 3 * E + (1 + which) * E + h * AB_D + dhalf * 32 + uu * 8;
-          asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(pack_bf16(x0.x, x0.y)),
-                       "r"(pack_bf16(x0.z, x0.w)), "r"(pack_bf16(x1.x, x1.y)), "r"(pack_bf16(x1.z, x1.w))
-                       : "memory");
-        }
+    for (int s2 = 0; s2 < 8; ++s2) {
+      const int rl = s2 * 4 + (lane >> 3);          // key row within this warp's 32
+      const int u = lane & 7;                       // 16B unit = 4 floats of the 32-dim chunk
+      const int c = hh * 128 + quad * 32 + rl;      // key column of the tile
+      int j = -1;
+      if (c < NK) j = key0 + c;
+      else if (c == NK) j = 0;
+      const bool key_ok = (c < NK) ? ((kbits[c >> 5] >> (c & 31)) & 1u) != 0 : (c == NK && g_ok);
+      const float4 x = *reinterpret_cast<const float4*>(slab + rl * 128 + ((u ^ (rl & 7)) << 4));
+      if (key_ok) {
+        float* dst = p.dkv + (static_cast<size_t>(b) * p.L + j) * 2 * E + which * E + h * AB_D + dhalf * 32 + u * 4;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
+                     : "memory");
       }
     }
     __syncwarp();
   }
+  carry_in = carry_out;
+  cur = nxt;
 
+  KT(10);
   tc_fence_before();
-  __syncthreads();     // TMEM, the transpose slabs, kbits and s_delta are rewritten by the next tile
+  __syncthreads();     // TMEM, the transpose slabs, the other kbits buffer and s_delta are rewritten by the next tile
   tc_fence_after();
+  KT(11);
   }   // tile loop
   if (warp == 0) tmem_dealloc(*tmem_slot, 512);
 }
@@ -503,6 +677,12 @@ __global__ void fold_dkv_kernel(const float4* __restrict__ dkv, __nv_bfloat16* _
 
 using namespace rf;
 
+#ifdef RF_KTIMING
+extern "C" int rf_debug_ktiming_bwd(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_kt_bwd, sizeof(g_kt_bwd)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const float* lse, const void* dctx,
                                 void* dqkv, float* dkv_scratch, rf_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -511,6 +691,7 @@ extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const fl
   RF_REQUIRE(a->w >= 32 && a->w % 32 == 0 && a->w <= 256,
              "rf_band_attn_bwd: one-sided window %d unsupported (multiples of 32 up to 256)", a->w);
   RF_REQUIRE(a->B > 0 && a->L >= 16 && a->H > 0, "rf_band_attn_bwd: bad shape");
+  RF_REQUIRE((reinterpret_cast<uintptr_t>(dqkv) & 31) == 0, "rf_band_attn_bwd: dqkv must be 32-byte aligned (256-bit stores)");
   static std::atomic<unsigned long long> attr_seen{0};   // one bit per device
   if (first_use_on_device(&attr_seen)) {
     RF_CUDA(cudaFuncSetAttribute(band_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
@@ -546,6 +727,7 @@ extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const fl
   p.B = a->B; p.L = a->L; p.H = a->H;
   p.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   p.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
+  p.keepbits = (bf16_path && a->drop_p > 0.f) ? reinterpret_cast<const uint4*>(a->keepbits) : nullptr;
   const int tiles = (a->L + 127) / 128;
   for (int k = 0; k < nseg; ++k) {
     const int lo = -a->w + 65 * k, hi = lo + 64;

@@ -65,7 +65,15 @@ struct AttnFwdParams {
   uint32_t drop_thresh;
   uint64_t drop_seed;
   const uint8_t* row_active;   // rf_set_row_activity: one flag per 256 token rows (L % 256 == 0), or null
+  uint2* keepbits;             // W = 32 with dropout: [B, H, L] x 16 B, the keep bits of every row's window for the backward, or null
 };
+
+#ifdef RF_KTIMING
+__device__ long long g_kt_fwd[16][12];
+#define KT(k) do { if (threadIdx.x == 0 && blockIdx.x >= 592 && blockIdx.x < 608) g_kt_fwd[blockIdx.x - 592][k] = clock64(); } while (0)
+#else
+#define KT(k) do {} while (0)
+#endif
 
 template <int W>
 __global__ void __launch_bounds__(ATT_THREADS)
@@ -86,6 +94,7 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
 
   const int tid = threadIdx.x;
+  KT(0);
   const int warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, part = warp >> 2;
   const int tiles_per_seq = (p.L + 127) / 128;
@@ -139,10 +148,12 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int band_hi = 2 * W - p.hi_cut;   // last in-band column offset of a row
+  KT(1);
 
   if (tid == 0) {
     // ---- S = Q K^T ----
     mbar_wait(bar_load, 0);
+    KT(2);
     tc_fence_after();
     const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK);
 #pragma unroll
@@ -173,6 +184,7 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
   __syncwarp();
   mbar_wait(bar_mma, 0);
   tc_fence_after();
+  KT(3);
 
   // ---- softmax: threads (quad, part 0) and (quad, part 1) share query row i0 + r (TMEM lane r) ----
   const uint32_t lane_base = tmem + (static_cast<uint32_t>(quad * 32) << 16);
@@ -196,7 +208,9 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
   if (part == 1 && g_ok && row_valid) sg = __uint_as_float(g16[0]);
   m = fmaxf(m, sg);
   s_red[part * 128 + r] = m;
+  KT(4);
   __syncthreads();
+  KT(5);
   m = fmaxf(s_red[r], s_red[128 + r]);
   if (m == -INFINITY) m = 0.0f;   // fully masked row: every p below is exp2(-inf) = 0
   const float m2 = m * LOG2E;
@@ -204,9 +218,11 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
   const uint64_t rowid = (static_cast<uint64_t>(b) * p.H + h) * p.L + (i < p.L ? i : 0);
   const uint64_t rowbase = rowid * attn_drop_groups(p.L);
   float l = 0.0f;
+  uint32_t kb[UNITS];
 #pragma unroll
   for (int u = 0; u < UNITS; ++u) {
     float pr[16];
+    kb[u] = 0;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float e = exp2f(__uint_as_float(sv[u][j]) * LOG2E - m2);
@@ -215,6 +231,7 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
     }
     if (p.drop_thresh != 0 && wmask[u] != 0) {
       const uint32_t keep = attn_keep16(p.drop_seed, rowbase, key0 + (ubase + u) * 16, p.drop_thresh);
+      kb[u] = keep;
 #pragma unroll
       for (int j = 0; j < 16; ++j) pr[j] = ((keep >> j) & 1u) ? pr[j] * p.drop_scale : 0.0f;
     }
@@ -236,22 +253,34 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
     *reinterpret_cast<uint4*>(prow + ((u16 ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(prow + (((u16 + 1) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
   }
+  uint32_t kb_cls = 0;
   if (part == 1) {
     // global chunk: tile column NK holds the CLS key (absolute key 0), columns NK+1.. are zero
     float pg = exp2f(sg * LOG2E - m2);
     l += pg;
-    if (p.drop_thresh != 0) pg *= attn_keep_cls(p.drop_seed, rowbase, p.drop_thresh, p.drop_scale);
+    if (p.drop_thresh != 0) {
+      const float kg = attn_keep_cls(p.drop_seed, rowbase, p.drop_thresh, p.drop_scale);
+      kb_cls = kg != 0.0f ? 1u : 0u;
+      pg *= kg;
+    }
     uint8_t* prow = sP + (NK >> 6) * 16384 + r * 128;
     const int u16 = (NK & 63) >> 3;
     *reinterpret_cast<uint4*>(prow + ((u16 ^ (r & 7)) << 4)) = make_uint4(pack_bf16(pg, 0.0f), 0, 0, 0);
     *reinterpret_cast<uint4*>(prow + (((u16 + 1) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
   }
   s_red[256 + part * 128 + r] = l;
+  if (W == 32 && p.keepbits != nullptr && i < p.L) {
+    // u16 x 8 per row: [unit 0, 1, 2, -, unit 3, 4, 5, CLS] (unit = 16 window columns); this thread's half
+    if constexpr (UNITS == 3)
+      p.keepbits[((static_cast<size_t>(b) * p.H + h) * p.L + i) * 2 + part] = make_uint2(kb[0] | (kb[1] << 16), kb[2] | (kb_cls << 16));
+  }
 
   // ---- O = P V ----
+  KT(6);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  KT(7);
   if (tid == 0) {
     tc_fence_after();
     const uint32_t ap = smem_u32(sP), av = smem_u32(sV);
@@ -272,6 +301,7 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
   __syncwarp();
   mbar_wait(bar_mma, 1);
   tc_fence_after();
+  KT(8);
   {
     uint32_t v[32];
     tmem_ld32(lane_base + part * 32, v);   // warp-collective: executed by every lane
@@ -289,12 +319,15 @@ band_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_cons
     }
   }
 
+  KT(9);
   tc_fence_before();
   __syncthreads();
+  KT(10);
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, C::TMEM_COLS);
   }
+  KT(11);
 }
 
 // Running merge of window segments: acc / lse_acc hold the softmax-weighted output and log-sum-exp of the
@@ -394,6 +427,7 @@ static int launch_attn_fwd(const rf_attn_args* a, void* ctx, float* lse, const A
   p.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   p.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
   p.drop_seed = a->drop_seed;
+  p.keepbits = (W == 32 && a->w == 32 && a->drop_p > 0.f) ? reinterpret_cast<uint2*>(a->keepbits) : nullptr;
   {
     const RowActivity& ra = row_activity();
     p.row_active = (ra.flags != nullptr && ra.rows == static_cast<long long>(a->B) * a->L && a->L % 256 == 0) ? ra.flags
@@ -412,6 +446,12 @@ static int launch_attn_fwd_w(int wk, const rf_attn_args* a, void* ctx, float* ls
 }
 
 }  // namespace rf
+
+#ifdef RF_KTIMING
+extern "C" int rf_debug_ktiming_fwd(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, rf::g_kt_fwd, sizeof(rf::g_kt_fwd)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" long long rf_band_attn_ws_bytes(int B, int L, int H, int w) {
   if (w <= 32) return 0;

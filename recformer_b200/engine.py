@@ -214,6 +214,9 @@ class FlatParams:
                 p.grad = gv
 
 
+_SAVE_KEEPBITS = os.environ.get("RF_NO_KEEPBITS") is None      # A/B aid: regenerate the attention dropout masks instead
+
+
 class SavedActivations:
     """Everything one forward pass keeps for its backward (or, in eval, reusable scratch)."""
 
@@ -231,6 +234,8 @@ class SavedActivations:
         self.qkv = [torch.zeros(T, 3 * E, **bf) for _ in range(n)]
         self.lse = [torch.zeros(B, H, Lp, **f32) for _ in range(n)]
         self.ctx = [torch.zeros(T, E, **bf) for _ in range(n)]
+        # attention-probability dropout keep bits (16 B per row and head), saved by the forward for the backward
+        self.keepbits = [ops.band_attn_keepbits(B, Lp, H, device) if per_layer and _SAVE_KEEPBITS else None for _ in range(n)]
         self.pre1 = [torch.zeros(T, E, **f32) for _ in range(n)]
         self.stats1 = [torch.zeros(T, 2, **f32) for _ in range(n)]
         self.h1 = [torch.zeros(T, E, **bf) for _ in range(n)]
@@ -507,7 +512,8 @@ class EncoderEngine:
                     ev_g.record(side)
             ops.gemm(x, W["Wqkv"], out=sv.qkv[k], bias=W["bqkv"], scale=0.125, scale_ncols=E)
             ops.band_attn_fwd(sv.qkv[k], mask, B, Lp, H, w_one, ctx=sv.ctx[k], lse=sv.lse[k], drop_p=sv.drop_attn,
-                              drop_seed=self._seed(sv, i, 1), ws=self.attn_ws(B, Lp, w_one, device))
+                              drop_seed=self._seed(sv, i, 1), ws=self.attn_ws(B, Lp, w_one, device),
+                              keepbits=sv.keepbits[k])
             if self._debug_skip_global:
                 pass
             elif self.overlap_global:
@@ -637,7 +643,8 @@ class EncoderEngine:
                         ops.global_attn_bwd_xk(*gargs, sv.glob[i], sc.gws, *sc.xk)
                     ev_a.record(side)
             ops.band_attn_bwd(sv.qkv[i], mask, B, Lp, H, w_one, sv.ctx[i], sv.lse[i], sc.dctx, dqkv, sc.dkv,
-                              drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 1), ws=self.attn_ws(B, Lp, w_one, device))
+                              drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 1), ws=self.attn_ws(B, Lp, w_one, device),
+                              keepbits=sv.keepbits[i])
             if use_aux:
                 on_aux("dqkv", i, lambda: ops.colsum(dqkv, G["bqkv"]))
             else:

@@ -182,7 +182,13 @@ def band_attn_ws(B, L, H, w, device):
     return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
-def _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed, ws=None):
+def band_attn_keepbits(B, L, H, device):
+    """Buffer for the attention-probability dropout keep bits of one layer (attention_window 64 only): written by
+    band_attn_fwd(keepbits=...), read back by band_attn_bwd(keepbits=...) instead of regenerating the Philox stream."""
+    return torch.empty(B * H * L * 4, dtype=torch.int32, device=device)
+
+
+def _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed, ws=None, keepbits=None):
     a = AttnArgs()
     a.qkv, a.mask012 = qkv.data_ptr(), mask012.data_ptr()
     a.B, a.L, a.H, a.D, a.w = B, L, H, 64, w
@@ -192,22 +198,26 @@ def _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed, ws=None):
     elif ws.numel() < int(_lib.lib().rf_band_attn_ws_bytes(B, L, H, w)):
         raise ValueError("band attention: workspace too small for this shape")
     a.ws = _ptr(ws)
+    if keepbits is not None:
+        if keepbits.dtype != torch.int32 or keepbits.numel() < B * H * L * 4 or keepbits.data_ptr() % 16:
+            raise ValueError("band attention: keepbits must be a 16-byte aligned int32 tensor of B*H*L*4 elements")
+        a.keepbits = keepbits.data_ptr() if (w == 32 and drop_p > 0.0) else None
     return a, ws
 
 
-def band_attn_fwd(qkv, mask012, B, L, H, w, ctx=None, lse=None, drop_p=0.0, drop_seed=0, ws=None):
+def band_attn_fwd(qkv, mask012, B, L, H, w, ctx=None, lse=None, drop_p=0.0, drop_seed=0, ws=None, keepbits=None):
     _req(qkv, torch.bfloat16, "qkv"), _req(mask012, torch.uint8, "mask012")
     if ctx is None:
         ctx = torch.empty(B * L, H * 64, dtype=torch.bfloat16, device=qkv.device)
     if lse is None:
         lse = torch.empty(B, H, L, dtype=torch.float32, device=qkv.device)
-    a, ws = _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed, ws)
+    a, ws = _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed, ws, keepbits)
     check(_lib.lib().rf_band_attn_fwd(C.byref(a), ctx.data_ptr(), lse.data_ptr(), _stream()), "rf_band_attn_fwd")
     return ctx, lse
 
 
-def band_attn_bwd(qkv, mask012, B, L, H, w, ctx, lse, dctx, dqkv, dkv_cls, drop_p=0.0, drop_seed=0, ws=None):
-    a, ws = _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed, ws)
+def band_attn_bwd(qkv, mask012, B, L, H, w, ctx, lse, dctx, dqkv, dkv_cls, drop_p=0.0, drop_seed=0, ws=None, keepbits=None):
+    a, ws = _attn_args(qkv, mask012, B, L, H, w, drop_p, drop_seed, ws, keepbits)
     check(_lib.lib().rf_band_attn_bwd(C.byref(a), ctx.data_ptr(), lse.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(),
                                       dkv_cls.data_ptr(), _stream()), "rf_band_attn_bwd")
     return dqkv

@@ -238,3 +238,35 @@ def test_embedding_backward_regenerates_the_forward_dropout_mask():
     torch.nn.functional.layer_norm(pre, (E,), gamma, beta, 1e-5).backward(dm)
     ref_type = torch.zeros_like(tabs[2]).index_add_(0, tt, pre.grad)
     assert relerr(gt[2], ref_type) < 5e-3
+
+
+@pytest.mark.parametrize("L,ragged", [(256, False), (1024, True)])
+def test_band_attention_saved_keep_bits_equal_the_regenerated_mask(L, ragged):
+    """attention_window 64: the forward can save each row's dropout keep bits (rf_attn_args.keepbits) and the backward
+    reads them back instead of regenerating the Philox stream — both backward passes must produce the SAME gradients
+    bit for bit, and a backward pass fed with inverted bits must not (the bits are really used)."""
+    B, H, w, seed = 3, 12, 32, 0x1234567
+    E = H * 64
+    mask = torch.ones(B, L, dtype=torch.uint8, device=DEV)
+    mask[:, 0] = 2
+    if ragged:
+        mask[1, L - 200:] = 0
+        mask[2, 300:] = 0
+    qkv = rnd(B * L, 3 * E, seed=11)
+    qkv[:, :E] *= 0.35
+    dctx = rnd(B * L, E, seed=12)
+    kb = ops.band_attn_keepbits(B, L, H, DEV)
+    kb.fill_(-1)
+    ctx0, lse0 = ops.band_attn_fwd(qkv, mask, B, L, H, w, drop_p=P_DROP, drop_seed=seed)
+    ctx1, lse1 = ops.band_attn_fwd(qkv, mask, B, L, H, w, drop_p=P_DROP, drop_seed=seed, keepbits=kb)
+    # (row 0 of a sequence is the global row: the band kernel leaves it to rf_global_attn_fwd)
+    assert torch.equal(ctx0.view(B, L, E)[:, 1:], ctx1.view(B, L, E)[:, 1:]) and torch.equal(lse0[:, :, 1:], lse1[:, :, 1:])
+    scratch = torch.empty(B * L, 2 * E, dtype=torch.float32, device=DEV)
+    g0 = torch.full((B * L, 3 * E), float("nan"), dtype=torch.bfloat16, device=DEV)
+    g1 = torch.full_like(g0, float("nan"))
+    ops.band_attn_bwd(qkv, mask, B, L, H, w, ctx0, lse0, dctx, g0, scratch, drop_p=P_DROP, drop_seed=seed)
+    ops.band_attn_bwd(qkv, mask, B, L, H, w, ctx0, lse0, dctx, g1, scratch, drop_p=P_DROP, drop_seed=seed, keepbits=kb)
+    assert torch.equal(g0.view(torch.int16), g1.view(torch.int16))
+    g2 = torch.full_like(g0, float("nan"))
+    ops.band_attn_bwd(qkv, mask, B, L, H, w, ctx0, lse0, dctx, g2, scratch, drop_p=P_DROP, drop_seed=seed, keepbits=~kb)
+    assert relerr(g2[:, 2 * E:], g0[:, 2 * E:].float()) > 0.1
