@@ -62,7 +62,8 @@ struct AttnBwdParams {
   float drop_scale;
   uint32_t drop_thresh;
   uint64_t drop_seed;
-  const uint4* keepbits;      // [B, H, L] x 16 B: the forward's dropout keep bits (attention_window 64 only), or null = regenerate
+  const uint32_t* keepbits;   // [B, H, L, 4]: the forward's dropout keep bits (attention_window 64 only: thread (row, part) reads
+                              // word `part` = its 24 window columns, bit 24 of word 3 = the CLS column), or null = regenerate
   // row activity (rf_set_row_activity): the persistent CTAs walk the compact list of active query tiles x heads
   const int32_t* qtiles;      // [n] entries b * tiles_per_seq + tile, or null = every tile
   const int32_t* n_qtiles;    // device scalar n
@@ -203,7 +204,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   // the S / dP MMAs have been issued): two 16-byte pieces of the saved context tile, read coalesced — lane = (row
   // within a group of 4, 16-byte unit), 4 full lines per warp instruction — for delta_i = dO_i . O_i; this thread's
   // row: log-sum-exp, mask bytes and the dropout keep bits the forward saved.
-  struct RowData { uint4 o[2]; float lse; uint32_t m_row, m_cls; uint4 kb; };
+  struct RowData { uint4 o[2]; float lse; uint32_t m_row, m_cls, kb; };
   const int r = quad * 32 + lane;       // query row of the tile == TMEM lane
   auto load_rows = [&](const Pos& q) -> RowData {
     RowData d;
@@ -222,7 +223,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     d.lse = in_seq ? p.lse[rowid] : 0.f;
     d.m_row = mrow[in_seq ? i : 0];
     d.m_cls = mrow[0];
-    d.kb = (p.keepbits != nullptr && in_seq) ? p.keepbits[rowid] : make_uint4(0, 0, 0, 0);
+    d.kb = (p.keepbits != nullptr && in_seq) ? p.keepbits[rowid * 4 + part] : 0u;
     return d;
   };
 
@@ -313,14 +314,13 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   // consumers (bf16 unpacks, the lse scaling) right behind the loads, i.e. in front of the MMA issue, and the
   // global-load latency lands on the critical path of every tile.
   asm volatile("" : "+r"(rd.o[0].x), "+r"(rd.o[0].y), "+r"(rd.o[0].z), "+r"(rd.o[0].w), "+r"(rd.o[1].x), "+r"(rd.o[1].y),
-                    "+r"(rd.o[1].z), "+r"(rd.o[1].w), "+f"(rd.lse), "+r"(rd.m_row), "+r"(rd.m_cls), "+r"(rd.kb.x),
-                    "+r"(rd.kb.y), "+r"(rd.kb.z), "+r"(rd.kb.w));
+                    "+r"(rd.o[1].z), "+r"(rd.o[1].w), "+f"(rd.lse), "+r"(rd.m_row), "+r"(rd.m_cls), "+r"(rd.kb));
   const float lse = rd.lse;
   const uint32_t m_row = rd.m_row, m_cls = rd.m_cls;
-  const uint4 kb_row = rd.kb;
+  const uint32_t kb_row = rd.kb;
   float keep_g = 1.f;        // dropout factor of the CLS column (part 3 uses it)
   if (part == 3 && p.drop_thresh != 0)
-    keep_g = p.keepbits != nullptr ? (((kb_row.w >> 16) & 1u) ? p.drop_scale : 0.f)
+    keep_g = p.keepbits != nullptr ? (((kb_row >> 24) & 1u) ? p.drop_scale : 0.f)
                                    : attn_keep_cls(p.drop_seed, rowbase, p.drop_thresh, p.drop_scale);
   // ---- delta_i = sum_j P'_ij dP_ij = dO_i . O_i  (O = sum_j P'_ij V_j is the saved forward output), computed under
   //      the S / dP MMAs: 8 dims per lane (dO from the swizzled shared-memory tile), 8 lanes per row ----
@@ -393,14 +393,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     uint32_t keepm = 0xFFFFFFu;
     if (p.drop_thresh != 0) {
       if (p.keepbits != nullptr) {
-        // the forward saved the row's keep bits: u16 x 8 = [unit 0, 1, 2, -, unit 3, 4, 5, CLS], unit = 16 window columns
-        const uint64_t lo64 = static_cast<uint64_t>(kb_row.x) | (static_cast<uint64_t>(kb_row.y & 0xFFFFu) << 32) |
-                              (static_cast<uint64_t>(kb_row.z & 0xFFFFu) << 48);
-        const uint32_t hi32 = (kb_row.z >> 16) | (kb_row.w << 16);
-        keepm = part == 0 ? static_cast<uint32_t>(lo64)
-              : part == 1 ? static_cast<uint32_t>(lo64 >> 24)
-              : part == 2 ? (static_cast<uint32_t>(lo64 >> 48) | (hi32 << 16))
-                          : (hi32 >> 8);
+        keepm = kb_row;       // the forward saved this thread's 24 keep bits
       } else if (live != 0) {
         keepm = attn_keep32(p.drop_seed, rowbase, key0 + c0, p.drop_thresh, live);
       }
@@ -518,7 +511,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
     } else if (tid < 132) {
       if (tile_n * 128 + (tid - 128) * 32 < p.L) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.lse + row0 + (tid - 128) * 32));
     } else if (tid < 148 && p.keepbits != nullptr) {
-      if (tile_n * 128 + (tid - 132) * 8 < p.L) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.keepbits + row0 + (tid - 132) * 8));
+      if (tile_n * 128 + (tid - 132) * 8 < p.L) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.keepbits + (row0 + (tid - 132) * 8) * 4));
     }
   };
   // (Publishing the first key half's accumulators early and draining them under the second half's MMAs was measured
@@ -727,7 +720,7 @@ extern "C" int rf_band_attn_bwd(const rf_attn_args* a, const void* ctx, const fl
   p.B = a->B; p.L = a->L; p.H = a->H;
   p.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   p.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
-  p.keepbits = (bf16_path && a->drop_p > 0.f) ? reinterpret_cast<const uint4*>(a->keepbits) : nullptr;
+  p.keepbits = (bf16_path && a->drop_p > 0.f) ? reinterpret_cast<const uint32_t*>(a->keepbits) : nullptr;
   const int tiles = (a->L + 127) / 128;
   for (int k = 0; k < nseg; ++k) {
     const int lo = -a->w + 65 * k, hi = lo + 64;

@@ -30,12 +30,12 @@ for name, fn, sym in (("fwd", lambda: ops.band_attn_fwd(qkv, mask, B, L, H, 32, 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     flush.zero_(); e0.record(); fn(); e1.record(); torch.cuda.synchronize()
     print(f"== {name}: {e0.elapsed_time(e1) * 1e3:.1f} us (dropout {drop})")
-    if name == "bwd":
+    if True:
         buf = (C.c_longlong * (4 * 16 * 16))()
         f = getattr(lib, sym)
         f.argtypes = [C.c_void_p]; f.restype = C.c_int
         assert f(C.cast(buf, C.c_void_p)) == 0
-        order = [0, 12, 1, 2, 3, 4, 5, 6, 7, 8, 9, 13, 10, 11]
+        order = [0, 12, 1, 2, 3, 4, 5, 6, 7, 8, 9, 13, 10, 11] if name == "bwd" else list(range(11))
         base = [buf[i * 16 + 0] for i in range(16)]       # warp 0 stamp 0 of each tile
         for w in range(4):
             print(f"  warp {w * 5}: stamps relative to warp 0's tile start, order {order}")
