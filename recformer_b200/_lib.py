@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librecformer_b200.so")
+# RF_LIB_PATH: development aid (A/B runs of two builds on the same box); the product always loads the in-tree library
+LIB_PATH = os.environ.get("RF_LIB_PATH") or os.path.join(HERE, "librecformer_b200.so")
 
 c_void_p, c_int, c_float, c_ll, c_u64 = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_uint64
 

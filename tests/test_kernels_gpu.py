@@ -71,6 +71,40 @@ def test_gemm_gelu_dual_and_dgelu():
     assert relerr(dU, (dY.float() @ W2.float()) * uref.grad) < 2e-2
 
 
+@pytest.mark.parametrize("M", [57 * 256, 57 * 256 - 100, 51 * 256])
+def test_gemm_step_shapes_ragged_row_counts(M):
+    """The four FFN GEMMs of a training step at the row counts a ragged batch leaves after padding-tile skipping (57 /
+    51 row tiles, one of them partial): every epilogue / operand layout of the chain is compared with fp32 torch."""
+    E, F = 768, 3072
+    x, W1, b1 = rnd(M, E, seed=1), rnd(F, E, seed=2, scale=0.05), rnd(F, seed=3, dtype=torch.float32)
+    g = torch.empty(M, F, dtype=torch.bfloat16, device=DEV)
+    d = ops.gemm(x, W1, bias=b1, epi=ops.EPI_GELU, out2=g)                              # K-major B, GELU dual store
+    uref = (x.float() @ W1.float().T + b1).requires_grad_(True)
+    gref = torch.nn.functional.gelu(uref)
+    gref.sum().backward()
+    assert relerr(g, gref) < 1e-2 and relerr(d, uref.grad) < 1e-2
+    W2, b2, res32 = rnd(E, F, seed=4, scale=0.05), rnd(E, seed=5, dtype=torch.float32), rnd(M, E, seed=6, dtype=torch.float32)
+    out32 = ops.gemm(g, W2, bias=b2, residual=res32, out_dtype=torch.float32)           # K-major B, fp32 residual, K = 3072
+    assert relerr(out32, g.float() @ W2.float().T + b2 + res32) < 1e-4
+    dY = rnd(M, E, seed=7)
+    dU = ops.gemm(dY, W2, b_mn_major=True, epi=ops.EPI_DGELU, aux=d)                    # MN-major B, dGELU, N = 3072
+    assert relerr(dU, (dY.float() @ W2.float()) * d.float()) < 2e-2
+    res = rnd(M, E, seed=8)
+    dx = ops.gemm(dU, W1, b_mn_major=True, residual=res)                                # MN-major B, bf16 residual, N = 768
+    assert relerr(dx, dU.float() @ W1.float() + res.float()) < 1e-2
+
+
+def test_gemm_extra_k_block_14_sequences():
+    B, L, N, K = 14, 1024, 768, 2304          # 56 row tiles x 3 column tiles
+    M = B * L
+    dY, W, res = rnd(M, K, seed=1), rnd(K, N, seed=2, scale=0.05), rnd(M, N, seed=3)
+    A2, B2 = rnd(M, 64, seed=4), rnd(B * 64, N, seed=5)
+    out = ops.gemm(dY, W, b_mn_major=True, residual=res, xk=(A2, B2, L))
+    ref = dY.float() @ W.float() + res.float()
+    ref += torch.bmm(A2.float().view(B, L, 64), B2.float().view(B, 64, N)).view(M, N)
+    assert relerr(out, ref) < 1e-2
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (384, 768, 2304), (200, 3072, 768)])
 def test_gemm_dgrad_layout(M, N, K):
     # dX[M,N] = dY[M,K] @ W[K,N]  with W stored row-major [K,N] (nn.Linear weight [out,in])
