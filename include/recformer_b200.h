@@ -83,6 +83,10 @@ typedef struct rf_gemm_args {
   int xk_rows;
   const void* A2;
   const void* B2;
+  /* Optional, with drop_p > 0 and N % 8 == 0: the epilogue also SAVES the dropout mask it draws, one byte per 8
+   * consecutive columns (bit e = column 8g + e kept), [M, N/8] row-major; rf_layernorm_bwd(drop_mask = ...) reads it
+   * back instead of regenerating the Philox stream.  NULL = off. */
+  void* drop_mask;
 } rf_gemm_args;
 
 int rf_gemm_bf16(const rf_gemm_args* args, rf_stream_t stream);
@@ -181,7 +185,8 @@ int rf_layernorm_fwd(const float* x_f32, const float* gamma, const float* beta, 
                      float* stats, int T, int E, float eps, rf_stream_t stream);
 int rf_layernorm_bwd(const void* dy_bf16, const float* x_f32, const float* stats, const float* gamma, void* dx_bf16,
                      void* dx_dropped_bf16, float drop_p, uint64_t drop_seed, float* d_gamma, float* d_beta,
-                     float* d_bias, int T, int E, rf_stream_t stream);
+                     float* d_bias, int T, int E, const uint8_t* drop_mask /* [T, E/8] saved by rf_gemm_bf16, or NULL =
+                     regenerate from drop_seed */, rf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Longformer sliding-window attention with a global CLS token (SURVEY.md §8a Spec A;

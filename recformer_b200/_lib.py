@@ -22,7 +22,7 @@ class GemmArgs(C.Structure):
                 ("a_mn_major", c_int), ("b_mn_major", c_int), ("epi", c_int), ("out_f32", c_int),
                 ("accumulate", c_int), ("split_k", c_int), ("scale", c_float), ("scale_ncols", c_int),
                 ("drop_p", c_float), ("drop_seed", c_u64), ("residual_f32", c_int),
-                ("xk_rows", c_int), ("A2", c_void_p), ("B2", c_void_p)]
+                ("xk_rows", c_int), ("A2", c_void_p), ("B2", c_void_p), ("drop_mask", c_void_p)]
 
 
 class EmbedArgs(C.Structure):
@@ -64,7 +64,7 @@ _SIGS = {
     "rf_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                  c_void_p]),
     "rf_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_u64,
-                                 c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "rf_band_attn_ws_bytes": (c_ll, [c_int, c_int, c_int, c_int]),
     "rf_band_attn_fwd": (c_int, [P(AttnArgs), c_void_p, c_void_p, c_void_p]),
     "rf_band_attn_bwd": (c_int, [P(AttnArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

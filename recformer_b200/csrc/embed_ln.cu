@@ -616,7 +616,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
                      const float* __restrict__ stats, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
                      __nv_bfloat16* __restrict__ dx_dropped, float drop_scale, uint32_t drop_thresh,
                      uint64_t drop_seed, float* d_gamma, float* d_beta, float* d_bias, int T,
-                     const uint8_t* __restrict__ active) {
+                     const uint8_t* __restrict__ active, const uint8_t* __restrict__ drop_mask) {
   constexpr int E = NV8 * 256;
   const int lane = threadIdx.x & 31;
   __shared__ float red[ROW_THREADS / 32][E];
@@ -632,21 +632,30 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
   int t = blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
   float nx[NV8][8];
   uint4 ndy[NV8];
+  uint8_t nmk[NV8];      // saved dropout mask bytes of the row (one per 8 columns), when the GEMM epilogue kept them
+#pragma unroll
+  for (int k = 0; k < NV8; ++k) nmk[k] = 0xFF;
   float2 nst = make_float2(0.f, 1.f);
   if (t < T && row_on(active, t)) {
     load_row_f32<NV8>(x + static_cast<size_t>(t) * E, lane, nx);
     const uint4* dr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(t) * E);
 #pragma unroll
     for (int k = 0; k < NV8; ++k) ndy[k] = dr[k * 32 + lane];
+    if (drop_mask != nullptr) {
+#pragma unroll
+      for (int k = 0; k < NV8; ++k) nmk[k] = drop_mask[static_cast<size_t>(t) * (E / 8) + k * 32 + lane];
+    }
     nst = *reinterpret_cast<const float2*>(stats + 2 * t);
   }
   for (; t < T; t += t_step) {
     const float mean = nst.x, rstd = nst.y;
     float xh[NV8][8], gy[NV8][8];
     uint4 cdy[NV8];
+    uint8_t cmk[NV8];
 #pragma unroll
     for (int k = 0; k < NV8; ++k) {
       cdy[k] = ndy[k];
+      cmk[k] = nmk[k];
 #pragma unroll
       for (int e = 0; e < 8; ++e) xh[k][e] = nx[k][e];
     }
@@ -656,6 +665,10 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
       const uint4* dr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(tn) * E);
 #pragma unroll
       for (int k = 0; k < NV8; ++k) ndy[k] = dr[k * 32 + lane];
+      if (drop_mask != nullptr) {
+#pragma unroll
+        for (int k = 0; k < NV8; ++k) nmk[k] = drop_mask[static_cast<size_t>(tn) * (E / 8) + k * 32 + lane];
+      }
       nst = *reinterpret_cast<const float2*>(stats + 2 * tn);
     }
     if (!row_on(active, t)) continue;      // padding-only tile: nothing was loaded for this row, nothing is written
@@ -691,7 +704,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
       oxr[k * 32 + lane] = ov;
       if (dx_dropped != nullptr) {
         const uint64_t grp = (static_cast<uint64_t>(t) * E + (k * 32 + lane) * 8) >> 3;
-        const uint32_t keep = drop_thresh ? dropout_keep8(drop_seed, grp, drop_thresh) : 0xFFu;
+        const uint32_t keep = !drop_thresh ? 0xFFu : (drop_mask != nullptr ? cmk[k] : dropout_keep8(drop_seed, grp, drop_thresh));
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = ((keep >> e) & 1u) ? o[e] * drop_scale : 0.f;
         ov.x = pack_bf16(o[0], o[1]); ov.y = pack_bf16(o[2], o[3]); ov.z = pack_bf16(o[4], o[5]); ov.w = pack_bf16(o[6], o[7]);
@@ -919,7 +932,7 @@ extern "C" int rf_layernorm_fwd(const float* x, const float* gamma, const float*
 
 extern "C" int rf_layernorm_bwd(const void* dy, const float* x, const float* stats, const float* gamma, void* dx,
                                 void* dx_dropped, float drop_p, uint64_t drop_seed, float* d_gamma, float* d_beta,
-                                float* d_bias, int T, int E, rf_stream_t stream_) {
+                                float* d_bias, int T, int E, const uint8_t* drop_mask, rf_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   RF_REQUIRE(dy && x && stats && gamma && dx, "rf_layernorm_bwd: null argument");
   RF_REQUIRE(E == 768, "rf_layernorm_bwd: hidden size %d unsupported (768)", E);
@@ -929,7 +942,7 @@ extern "C" int rf_layernorm_bwd(const void* dy, const float* x, const float* sta
   layernorm_bwd_kernel<3><<<grid, ROW_THREADS, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), x, stats, gamma,
       reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(dx_dropped), scale, thresh, drop_seed,
-      d_gamma, d_beta, d_bias, T, active_flags_for(T));
+      d_gamma, d_beta, d_bias, T, active_flags_for(T), thresh != 0 ? drop_mask : nullptr);
   return check_launch("rf_layernorm_bwd");
 }
 

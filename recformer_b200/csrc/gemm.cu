@@ -45,6 +45,7 @@ struct GemmParams {
   float drop_scale;       // 1/(1-p)
   uint32_t drop_thresh;   // p * 65536, 0 = no dropout
   uint64_t drop_seed;
+  uint8_t* drop_mask;     // optional [M, N/8]: the dropout mask the epilogue draws, saved for rf_layernorm_bwd
   int xk_rows;            // XK: rows of A per batch (one 64-row block of B2 per batch)
   int* tile_counter;      // pair kernel: dynamic tile scheduler (zero between launches, see gemm_pair_kernel)
   // pair kernel, row activity (rf_set_row_activity): one flag per 256 rows of the token axis; 0 = padding only.
@@ -162,6 +163,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ge
       if (DROP) {
         const uint64_t grp = (static_cast<uint64_t>(row) * p.N + c8) >> 3;
         const uint32_t keep = dropout_keep8(p.drop_seed, grp, p.drop_thresh);
+        if (p.drop_mask != nullptr && ok) p.drop_mask[grp] = static_cast<uint8_t>(keep);
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = ((keep >> e) & 1u) ? v[e] * p.drop_scale : 0.0f;
       }
@@ -395,6 +397,7 @@ static void fill_params(const rf_gemm_args* a, GemmParams& p) {
   p.drop_thresh = a->drop_p > 0.f ? static_cast<uint32_t>(a->drop_p * 65536.0f) : 0u;
   p.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
   p.drop_seed = a->drop_seed;
+  p.drop_mask = (a->drop_p > 0.f && a->N % 8 == 0) ? reinterpret_cast<uint8_t*>(a->drop_mask) : nullptr;
   static const int noepi = getenv("RF_DEBUG_GEMM_NOEPI") ? atoi(getenv("RF_DEBUG_GEMM_NOEPI")) : 0;
   p.debug_skip_epilogue = noepi;
 }

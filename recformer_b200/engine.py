@@ -214,7 +214,8 @@ class FlatParams:
                 p.grad = gv
 
 
-_SAVE_KEEPBITS = os.environ.get("RF_NO_KEEPBITS") is None      # A/B aid: regenerate the attention dropout masks instead
+# A/B aid: RF_NO_KEEPBITS=1 makes every backward kernel regenerate its dropout mask instead of reading the saved bits
+_SAVE_KEEPBITS = os.environ.get("RF_NO_KEEPBITS", "0") != "1"
 
 
 class SavedActivations:
@@ -236,6 +237,11 @@ class SavedActivations:
         self.ctx = [torch.zeros(T, E, **bf) for _ in range(n)]
         # attention-probability dropout keep bits (16 B per row and head), saved by the forward for the backward
         self.keepbits = [ops.band_attn_keepbits(B, Lp, H, device) if per_layer and _SAVE_KEEPBITS else None for _ in range(n)]
+        # hidden-dropout masks of the two residual GEMMs (one byte per 8 columns), saved for the LayerNorm backward
+        self.mask1 = [torch.zeros(T, E // 8, dtype=torch.uint8, device=device) if per_layer and _SAVE_KEEPBITS else None
+                      for _ in range(n)]
+        self.mask2 = [torch.zeros(T, E // 8, dtype=torch.uint8, device=device) if per_layer and _SAVE_KEEPBITS else None
+                      for _ in range(n)]
         self.pre1 = [torch.zeros(T, E, **f32) for _ in range(n)]
         self.stats1 = [torch.zeros(T, 2, **f32) for _ in range(n)]
         self.h1 = [torch.zeros(T, E, **bf) for _ in range(n)]
@@ -522,12 +528,12 @@ class EncoderEngine:
                 ops.global_attn_fwd(x, mask, W["Wqg"], W["bqg"], W["Wkg"], W["Wvg"], W["bvg"], B, Lp, H, sv.ctx[k],
                                     saved=sv.glob[k], drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 2))
             ops.gemm(sv.ctx[k], W["Wo"], out=sv.pre1[k], bias=W["bo"], residual=sv.x32[i % 2],
-                     drop_p=sv.drop_hidden, drop_seed=self._seed(sv, i, 3))
+                     drop_p=sv.drop_hidden, drop_seed=self._seed(sv, i, 3), drop_mask=sv.mask1[k])
             ops.layernorm_fwd(sv.pre1[k], W["ln1w"], W["ln1b"], cfg.layer_norm_eps, out=sv.h1[k], out32=sv.h1_32,
                               stats=sv.stats1[k])
             ops.gemm(sv.h1[k], W["W1"], out=sv.u[k], bias=W["b1"], epi=ops.EPI_GELU, out2=sv.g[k])
             ops.gemm(sv.g[k], W["W2"], out=sv.pre2[k], bias=W["b2"], residual=sv.h1_32, drop_p=sv.drop_hidden,
-                     drop_seed=self._seed(sv, i, 4))
+                     drop_seed=self._seed(sv, i, 4), drop_mask=sv.mask2[k])
             ops.layernorm_fwd(sv.pre2[k], W["ln2w"], W["ln2b"], cfg.layer_norm_eps, out=sv.xout(i),
                               out32=sv.x32[(i + 1) % 2], stats=sv.stats2[k])
 
@@ -611,7 +617,7 @@ class EncoderEngine:
             # ---- output block: LN2 <- dense(W2) <- gelu <- dense(W1) ----
             ops.layernorm_bwd(d_out, sv.pre2[i], sv.stats2[i], W["ln2w"], G["ln2w"], G["ln2b"], dx=d_pre2,
                               dx_dropped=dY2 if pd > 0 else None, drop_p=pd, drop_seed=self._seed(sv, i, 4),
-                              d_bias=G["b2"])
+                              d_bias=G["b2"], drop_mask=sv.mask2[i])
             wgrad("wgW2", dY2, sv.g[i], G["W2"], E, F)
             ops.gemm(dY2, W["W2"], out=dU, b_mn_major=True, epi=ops.EPI_DGELU, aux=sv.u[i])
             if use_aux:
@@ -623,7 +629,7 @@ class EncoderEngine:
             # ---- attention block: LN1 <- dense(Wo) <- attention <- dense(Wqkv) ----
             ops.layernorm_bwd(sc.dh1, sv.pre1[i], sv.stats1[i], W["ln1w"], G["ln1w"], G["ln1b"], dx=d_pre1,
                               dx_dropped=dY1 if pd > 0 else None, drop_p=pd, drop_seed=self._seed(sv, i, 3),
-                              d_bias=G["bo"])
+                              d_bias=G["bo"], drop_mask=sv.mask1[i])
             wgrad("wgWo", dY1, sv.ctx[i], G["Wo"], E, E)
             ops.gemm(dY1, W["Wo"], out=sc.dctx, b_mn_major=True)
             gargs = (x, mask, W["Wqg"], W["bqg"], W["Wkg"], W["Wvg"], W["bvg"], B, Lp, H)

@@ -40,7 +40,7 @@ def launch_count() -> int:
 # ---------------------------------------------------------------------------------------------
 def gemm(A, B, out=None, *, bias=None, residual=None, aux=None, out2=None, a_mn_major=False, b_mn_major=False,
          epi=EPI_NONE, out_dtype=torch.bfloat16, accumulate=False, split_k=1, scale=1.0, scale_ncols=0,
-         drop_p=0.0, drop_seed=0, M=None, N=None, K=None, xk=None):
+         drop_p=0.0, drop_seed=0, M=None, N=None, K=None, xk=None, drop_mask=None):
     """C[M,N] = epilogue(A (*) B).  A: [M,K] (or [K,M] if a_mn_major), B: [N,K] (or [K,N] if b_mn_major).
     xk = (A2 [M,64], B2 [M/rows*64, N], rows): extra per-sequence 64-deep k-block (dgrad layout only)."""
     _req(A, torch.bfloat16, "A"), _req(B, torch.bfloat16, "B")
@@ -65,6 +65,10 @@ def gemm(A, B, out=None, *, bias=None, residual=None, aux=None, out2=None, a_mn_
     a.accumulate, a.split_k = int(accumulate), split_k
     a.scale, a.scale_ncols = scale, scale_ncols
     a.drop_p, a.drop_seed = drop_p, drop_seed
+    if drop_mask is not None and drop_p > 0.0:      # uint8 [M, N/8]: the epilogue saves the mask it draws
+        if drop_mask.dtype != torch.uint8 or drop_mask.numel() < a.M * (a.N // 8):
+            raise ValueError("gemm: drop_mask must be a uint8 tensor of M * N / 8 elements")
+        a.drop_mask = drop_mask.data_ptr()
     if xk is not None:
         A2, B2, rows = xk
         _req(A2, torch.bfloat16, "A2"), _req(B2, torch.bfloat16, "B2")
@@ -154,14 +158,14 @@ def layernorm_fwd(x, gamma, beta, eps, out=None, out32=None, stats=None):
 
 
 def layernorm_bwd(dy, x, stats, gamma, d_gamma, d_beta, dx=None, dx_dropped=None, drop_p=0.0, drop_seed=0,
-                  d_bias=None):
+                  d_bias=None, drop_mask=None):
     _req(x, torch.float32, "x")
     T, E = x.shape
     if dx is None:
         dx = torch.empty(T, E, dtype=torch.bfloat16, device=x.device)
     check(_lib.lib().rf_layernorm_bwd(dy.data_ptr(), x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), dx.data_ptr(),
                                       _ptr(dx_dropped), drop_p, drop_seed, _ptr(d_gamma), _ptr(d_beta), _ptr(d_bias),
-                                      T, E, _stream()), "rf_layernorm_bwd")
+                                      T, E, _ptr(drop_mask), _stream()), "rf_layernorm_bwd")
     return dx
 
 

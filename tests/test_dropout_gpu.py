@@ -62,6 +62,23 @@ def test_gemm_epilogue_dropout_mask_is_the_one_layernorm_bwd_regenerates(T):
     xf = pre_p.clone().requires_grad_(True)
     torch.nn.functional.layer_norm(xf, (E,), gamma, beta, 1e-5).backward(dy.float())
     assert relerr(dbias, (xf.grad * fwd_keep * KEEP_SCALE).sum(0)) < 2e-3
+    # the epilogue can also SAVE its mask (one byte per 8 columns) for the backward to read back: same forward
+    # output, bit-identical backward, and the saved bits are really used (inverted bits give another result)
+    saved = torch.zeros(T, E // 8, dtype=torch.uint8, device=DEV)
+    pre_m = ops.gemm(A, W, bias=bias, residual=res, drop_p=P_DROP, drop_seed=seed, out_dtype=torch.float32, drop_mask=saved)
+    assert torch.equal(pre_m, pre_p)
+    bits = ((saved[:, :, None] >> torch.arange(8, device=DEV, dtype=torch.uint8)) & 1).bool().view(T, E)
+    assert torch.equal(bits[live], fwd_keep[live])
+    dx2 = torch.empty_like(dx)
+    dxd2 = torch.full_like(dxd, float("nan"))
+    dbias2 = torch.zeros_like(dbias)
+    ops.layernorm_bwd(dy, pre_p, stats, gamma, torch.zeros_like(dg), torch.zeros_like(db), dx=dx2, dx_dropped=dxd2,
+                      drop_p=P_DROP, drop_seed=seed + 99, d_bias=dbias2, drop_mask=saved)      # the seed is not consulted
+    assert torch.equal(dxd2.view(torch.int16), dxd.view(torch.int16)) and torch.equal(dx2.view(torch.int16), dx.view(torch.int16))
+    assert relerr(dbias2, dbias) < 1e-5
+    ops.layernorm_bwd(dy, pre_p, stats, gamma, torch.zeros_like(dg), torch.zeros_like(db), dx=dx2, dx_dropped=dxd2,
+                      drop_p=P_DROP, drop_seed=seed, d_bias=dbias2, drop_mask=~saved)
+    assert (dxd2.float() != 0).ne(bwd_keep)[live].float().mean().item() > 0.9
     # and a different seed gives a different mask (the comparison above is not vacuous)
     other = ops.gemm(A, W, bias=bias, residual=res, drop_p=P_DROP, drop_seed=seed + 1, out_dtype=torch.float32)
     assert ((other - res).abs() > 0.5 * dense_0.abs()).ne(fwd_keep).float().mean().item() > 0.1

@@ -32,6 +32,7 @@ Wg = [rf(E, E, sc=0.03) for _ in range(3)]; bg = [rf(E, sc=0.1) for _ in range(2
 gW = [torch.zeros(E, E, device=dev) for _ in range(3)]; gb = [torch.zeros(E, device=dev) for _ in range(2)]
 dx = rb(T, E, sc=0.01)
 cs = torch.zeros(F, device=dev)
+dmask = torch.randint(0, 256, (T, E // 8), dtype=torch.uint8, device=dev)
 state = {}
 
 CASES = {
@@ -45,13 +46,14 @@ CASES = {
     "attn_bwd": lambda: ops.band_attn_bwd(qkv, mask, B, L, H, 32, ctx, lse, dctx, dqkv, scratch, drop_p=0.1, drop_seed=3),
     "ln_fwd": lambda: ops.layernorm_fwd(pre, gamma, beta, 1e-5, out=h1, out32=h32, stats=stats),
     "ln_bwd": lambda: ops.layernorm_bwd(dY, pre, stats, gamma, dg, db, dx=dpre, dx_dropped=dpre2, drop_p=0.1, drop_seed=5, d_bias=dbias),
+    "ln_bwd_mask": lambda: ops.layernorm_bwd(dY, pre, stats, gamma, dg, db, dx=dpre, dx_dropped=dpre2, drop_p=0.1, drop_seed=5, d_bias=dbias, drop_mask=dmask),
     "colsum_3072": lambda: ops.colsum(dU, cs),
     "global_fwd": lambda: state.__setitem__("sv", ops.global_attn_fwd(x, mask, Wg[0], bg[0], Wg[1], Wg[2], bg[1], B, L, H, ctx, saved=state.get("sv"), drop_p=0.1, drop_seed=7)),
     "global_bwd": lambda: state.__setitem__("ws", ops.global_attn_bwd(x, mask, Wg[0], bg[0], Wg[1], Wg[2], bg[1], B, L, H, dctx, state["sv"], dx, gW[0], gb[0], gW[1], gW[2], gb[1], ws=state.get("ws"), drop_p=0.1, drop_seed=7)),
 }
 FLOPS = {"gemm_qkv": 2 * T * 3 * E * E, "gemm_up_gelu": 2 * T * F * E, "gemm_down_res": 2 * T * F * E,
          "gemm_dgrad_dgelu": 2 * T * F * E, "gemm_wgrad_up": 2 * T * F * E, "gemm_wgrad_qkv": 2 * T * 3 * E * E}
-BYTES = {"attn_fwd": T * 4 * E * 2, "attn_bwd": T * 8 * E * 2, "ln_fwd": T * E * (4 + 2 + 4), "ln_bwd": T * E * (2 + 4 + 2 + 2),
+BYTES = {"attn_fwd": T * 4 * E * 2, "attn_bwd": T * 8 * E * 2, "ln_fwd": T * E * (4 + 2 + 4), "ln_bwd": T * E * (2 + 4 + 2 + 2), "ln_bwd_mask": T * E * (2 + 4 + 2 + 2),
          "colsum_3072": T * F * 2}
 # embeddings + LN (fwd / bwd) and the fused AdamW at the C2 shapes
 _emb = {}
