@@ -283,7 +283,6 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   KT(12);
   const uint32_t* kbits = kbits_all + (it & 1) * 8;
   const int i0 = tile * 128;
-  const uint8_t* mrow = p.mask012 + static_cast<size_t>(b) * p.L;
   const int key0 = i0 - W + p.shift;             // absolute key index of tile column 0
   const int i = i0 + r;
   const bool in_seq = i < p.L;

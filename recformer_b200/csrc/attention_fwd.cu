@@ -816,7 +816,7 @@ static int launch_attn_fwd_w(int wk, const rf_attn_args* a, void* ctx, float* ls
   if (wk == 32) return launch_attn_fwd_persist(a, ctx, lse, sg, lse_neg_inf, stream);
   if (wk == 128) return launch_attn_fwd<128>(a, ctx, lse, sg, lse_neg_inf, stream);
   if (wk == 64) return launch_attn_fwd<64>(a, ctx, lse, sg, lse_neg_inf, stream);
-  return launch_attn_fwd<32>(a, ctx, lse, sg, lse_neg_inf, stream);
+  return set_error(RF_ERR_INVALID, "rf_band_attn_fwd: no kernel for native half-width %d", wk);
 }
 
 }  // namespace rf

@@ -33,6 +33,7 @@ gW = [torch.zeros(E, E, device=dev) for _ in range(3)]; gb = [torch.zeros(E, dev
 dx = rb(T, E, sc=0.01)
 cs = torch.zeros(F, device=dev)
 dmask = torch.randint(0, 256, (T, E // 8), dtype=torch.uint8, device=dev)
+kbits = ops.band_attn_keepbits(B, L, H, dev)
 state = {}
 
 CASES = {
@@ -42,8 +43,10 @@ CASES = {
     "gemm_dgrad_dgelu": lambda: ops.gemm(dY, W2, out=dU, b_mn_major=True, epi=ops.EPI_DGELU, aux=u),
     "gemm_wgrad_up": lambda: ops.gemm(dU, x, out=dW1, a_mn_major=True, b_mn_major=True, accumulate=True, split_k=2),
     "gemm_wgrad_qkv": lambda: ops.gemm(qkv, x, out=dWqkv, a_mn_major=True, b_mn_major=True, accumulate=True, split_k=4),
-    "attn_fwd": lambda: ops.band_attn_fwd(qkv, mask, B, L, H, 32, ctx=ctx, lse=lse, drop_p=0.1, drop_seed=3),
-    "attn_bwd": lambda: ops.band_attn_bwd(qkv, mask, B, L, H, 32, ctx, lse, dctx, dqkv, scratch, drop_p=0.1, drop_seed=3),
+    # as the engine runs them: the forward saves the dropout keep bits, the backward reads them back
+    "attn_fwd": lambda: ops.band_attn_fwd(qkv, mask, B, L, H, 32, ctx=ctx, lse=lse, drop_p=0.1, drop_seed=3, keepbits=kbits),
+    "attn_bwd": lambda: ops.band_attn_bwd(qkv, mask, B, L, H, 32, ctx, lse, dctx, dqkv, scratch, drop_p=0.1, drop_seed=3, keepbits=kbits),
+    "attn_bwd_regen": lambda: ops.band_attn_bwd(qkv, mask, B, L, H, 32, ctx, lse, dctx, dqkv, scratch, drop_p=0.1, drop_seed=3),
     "ln_fwd": lambda: ops.layernorm_fwd(pre, gamma, beta, 1e-5, out=h1, out32=h32, stats=stats),
     "ln_bwd": lambda: ops.layernorm_bwd(dY, pre, stats, gamma, dg, db, dx=dpre, dx_dropped=dpre2, drop_p=0.1, drop_seed=5, d_bias=dbias),
     "ln_bwd_mask": lambda: ops.layernorm_bwd(dY, pre, stats, gamma, dg, db, dx=dpre, dx_dropped=dpre2, drop_p=0.1, drop_seed=5, d_bias=dbias, drop_mask=dmask),
@@ -110,7 +113,7 @@ for _w in (64, 128, 256):
     BYTES[f"attn_bwd_w{2 * _w}"] = 2 * 4096 * 8 * E * 2
 CASES["attn_bwd_nodrop"] = lambda: ops.band_attn_bwd(qkv, mask, B, L, H, 32, ctx, lse, dctx, dqkv, scratch)
 CASES["attn_fwd_nodrop"] = lambda: ops.band_attn_fwd(qkv, mask, B, L, H, 32, ctx=ctx, lse=lse)
-BYTES["attn_bwd_nodrop"] = BYTES["attn_bwd"]; BYTES["attn_fwd_nodrop"] = BYTES["attn_fwd"]
+BYTES["attn_bwd_nodrop"] = BYTES["attn_bwd_regen"] = BYTES["attn_bwd"]; BYTES["attn_fwd_nodrop"] = BYTES["attn_fwd"]
 if any(a.startswith("score") for a in sys.argv[1:]):
     NU, NI = 4096, int(os.environ.get("RF_PROF_ITEMS", "1000000"))
     tab = torch.empty(NI, E, dtype=torch.bfloat16, device=dev)
