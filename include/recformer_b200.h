@@ -34,7 +34,8 @@ typedef struct CUstream_st* rf_stream_t; /* == cudaStream_t */
 #define RF_ERR_CUDA (-2)    /* CUDA runtime / driver error       */
 
 const char* rf_last_error(void);
-int rf_version(void);
+int rf_version(void); /* 102: rf_attn_args.keepbits, rf_gemm_args.drop_mask, rf_layernorm_bwd(..., drop_mask) added;
+                         structs only ever grow at the end: zero-initialise them */
 /* Number of kernels launched by this library in the calling process so far (bench.py reports
  * the per-step delta as `gpu_launches`). */
 unsigned long long rf_launch_count(void);

@@ -157,7 +157,7 @@ const CUtensorMap* get_tmap_3d(const void* ptr, uint64_t batch, uint64_t rows, u
 
 extern "C" {
 const char* rf_last_error(void) { return rf::g_err; }
-int rf_version(void) { return 100; }
+int rf_version(void) { return 102; }   // 102: rf_attn_args.keepbits, rf_gemm_args.drop_mask, rf_layernorm_bwd(drop_mask)
 unsigned long long rf_launch_count(void) { return rf::g_launches.load(); }
 int rf_set_dropout_nonce(const unsigned long long* nonce_dev, rf_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

@@ -418,24 +418,33 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
       *reinterpret_cast<uint4*>(sP + o) = make_uint4(po[u * 4], po[u * 4 + 1], po[u * 4 + 2], po[u * 4 + 3]);
       *reinterpret_cast<uint4*>(sDS + o) = make_uint4(so[u * 4], so[u * 4 + 1], so[u * 4 + 2], so[u * 4 + 3]);
     }
-    // zero fill of the 96 band columns outside the window (twelve 8-column units, three per part) ...
+    // Zero fill of the 96 band columns outside the window (twelve 8-column units, three per part) and of the global
+    // chunk = P/dS chunk 3 (columns 192..255: column 192 holds the CLS key, the rest is zero).  A thread writes the same
+    // window columns of its row every tile, so in the bf16 path — where nothing else ever touches the P / dS buffers —
+    // the fill is needed for the CTA's first tile only; the fp32 path reuses the P buffer as transpose slabs.
+    if (!carry_enabled || it == 0) {
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      const int k = part * 3 + u;
-      const int cu = k < 4 * quad ? k : k + 12;           // 8-column unit of the tile
-      const uint32_t o = (cu >> 3) * 16384 + r * 128 + (((cu & 7) ^ (r & 7)) << 4);
-      *reinterpret_cast<uint4*>(sP + o) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(sDS + o) = make_uint4(0, 0, 0, 0);
+      for (int u = 0; u < 3; ++u) {
+        const int k = part * 3 + u;
+        const int cu = k < 4 * quad ? k : k + 12;           // 8-column unit of the tile
+        const uint32_t o = (cu >> 3) * 16384 + r * 128 + (((cu & 7) ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(sP + o) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sDS + o) = make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int uu = 0; uu < 2; ++uu) {      // units 1..7 of the global chunk: part 3 takes 1, parts 0..2 units 2..7
+        const int u = ((part + 1) & 3) * 2 + uu;
+        if (u == 0) continue;
+        const uint32_t o = 3 * 16384 + r * 128 + ((u ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(sP + o) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sDS + o) = make_uint4(0, 0, 0, 0);
+      }
     }
-    // ... and the global chunk = P/dS chunk 3 (columns 192..255): column 192 holds the CLS key, the rest is zero;
-    // part 3 (which owns pg) writes units 0, 1, parts 0..2 units 2..7
-    const float dsg = pg * (keep_g * dpg - delta);
-#pragma unroll
-    for (int uu = 0; uu < 2; ++uu) {
-      const int u = ((part + 1) & 3) * 2 + uu;
-      const uint32_t o = 3 * 16384 + r * 128 + ((u ^ (r & 7)) << 4);
-      *reinterpret_cast<uint4*>(sP + o) = (u == 0) ? make_uint4(pack_bf16(pg_d, 0.f), 0, 0, 0) : make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(sDS + o) = (u == 0) ? make_uint4(pack_bf16(dsg, 0.f), 0, 0, 0) : make_uint4(0, 0, 0, 0);
+    if (part == 3) {     // the CLS column itself (unit 0 of the global chunk), every tile
+      const float dsg = pg * (keep_g * dpg - delta);
+      const uint32_t o = 3 * 16384 + r * 128 + ((r & 7) << 4);
+      *reinterpret_cast<uint4*>(sP + o) = make_uint4(pack_bf16(pg_d, 0.f), 0, 0, 0);
+      *reinterpret_cast<uint4*>(sDS + o) = make_uint4(pack_bf16(dsg, 0.f), 0, 0, 0);
     }
   }
 

@@ -1,10 +1,7 @@
-#!/bin/bash
-cd /root/repo; mkdir -p gpurun_out
-run() { # name, env...
-  name=$1; shift
-  env "$@" timeout 600 python bench.py --steps 20 --warmup 5 --no-extras --no-cpu-baseline --no-secondary > gpurun_out/q_$name.log 2> gpurun_out/q_$name.err; tail -1 gpurun_out/q_$name.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$name', round(d['value'],1), round(d['ms_per_step'],3), round(d['e2e']['value'],1), d['clocks']['sm_mhz'], round(d['roofline']['frac'],3), d['roofline'].get('rows_processed',{}).get('profiled_batch'))" || tail -5 gpurun_out/q_$name.err
-}
-run skip A=1
-run skip_wgaux RF_WGRAD_AUX=1
-run skip2 A=1
-run skip_wgaux2 RF_WGRAD_AUX=1
+cd /root/repo
+run() { name=$1; shift; env "$@" timeout 600 python bench.py --steps 30 --warmup 5 --no-extras --no-cpu-baseline --no-secondary 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$name', round(d['value'],1), round(d['ms_per_step'],3), d['clocks']['sm_mhz'])"; }
+run default A=1
+run side-2 RF_SIDE_PRIO=-2
+run side-3 RF_SIDE_PRIO=-3
+run default A=1
+run side-2 RF_SIDE_PRIO=-2
