@@ -125,7 +125,7 @@ band_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV64, const __grid_c
   auto decode = [&](int t) -> Pos {
     Pos o;
     if (p.qtiles != nullptr) {
-      o.h = t / n_q;
+      o.h = n_q > 0 ? t / n_q : 0;
       o.idx = t - o.h * n_q;
       const int q = p.qtiles[o.idx];
       o.tile = q % tiles_per_seq;

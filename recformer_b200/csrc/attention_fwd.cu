@@ -366,7 +366,7 @@ band_attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm64, const __g
   auto decode = [&](int t) -> Pos {
     Pos o;
     if (pp.qtiles != nullptr) {
-      o.h = t / n_q;
+      o.h = n_q > 0 ? t / n_q : 0;
       o.idx = t - o.h * n_q;
       const int q = pp.qtiles[o.idx];
       o.tile = q % tiles_per_seq;
