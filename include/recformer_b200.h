@@ -261,6 +261,11 @@ long long rf_global_attn_bwd_ws_bytes(int B, int L, int H);
 int rf_global_attn_bwd(const rf_global_args* a, const void* dctx_bf16, const float* qg, const float* u,
                        const float* p, const float* pt, const float* mvec, const float* psum, void* dx_bf16,
                        float* dWqg, float* dbqg, float* dWkg, float* dWvg, float* dbvg, float* ws, rf_stream_t stream);
+/* The three *_global weight-gradient outer products of rf_global_attn_bwd as a separate launch (autograd of
+ * HF:963-1056, weight part): call rf_global_attn_bwd with dWqg = dWkg = dWvg = NULL, then this with the same ws —
+ * nothing on the backward's critical path waits for it. */
+int rf_global_attn_bwd_wgrad(const rf_global_args* a, const float* qg, const float* mvec, const float* ws, float* dWqg,
+                             float* dWkg, float* dWvg, rf_stream_t stream);
 int rf_global_attn_bwd_dx(const rf_global_args* a, const float* u, const float* pt, void* dx_bf16, const float* ws,
                           rf_stream_t stream);
 /* (autograd of HF:963-1056, token-gradient part.)  Alternative to rf_global_attn_bwd_dx: packs the same token gradients as the operands of the extra

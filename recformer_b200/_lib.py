@@ -76,6 +76,7 @@ _SIGS = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p]),
     "rf_global_attn_bwd_dx": (c_int, [P(GlobalArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rf_global_attn_bwd_wgrad": (c_int, [P(GlobalArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rf_global_attn_bwd_xk": (c_int, [P(GlobalArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rf_normalize_rows": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "rf_cosine_logits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_void_p]),

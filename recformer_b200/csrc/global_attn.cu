@@ -1115,9 +1115,26 @@ extern "C" int rf_global_attn_bwd(const rf_global_args* a, const void* dctx, con
     global_colmix_kernel<<<dim3(GE / 64, GH, bblocks), 64, 0, stream>>>(c);
     if ((rc = check_launch("rf_global_attn_bwd/dxcls"))) return rc;
   }
-  global_wgrad_kernel<<<dim3(GH, 3, 3), 256, 0, stream>>>(x, a->mask012, B, L, w.doutf, mvec, qg, w.du, w.dqf, dWvg,
-                                                         dWkg, dWqg);
-  if ((rc = check_launch("rf_global_attn_bwd/wgrad"))) return rc;
+  // the three weight-gradient outer products feed only the optimiser: with dWqg == dWkg == dWvg == NULL they are left
+  // to rf_global_attn_bwd_wgrad (same ws), which the engine launches AFTER the token-gradient operands the main stream
+  // waits for (rf_global_attn_bwd_xk), so the 16-40 us they take are off the backward's critical chain
+  if (dWvg != nullptr || dWkg != nullptr || dWqg != nullptr) {
+    RF_REQUIRE(dWvg && dWkg && dWqg, "rf_global_attn_bwd: pass all three *_global weight gradients or none");
+    global_wgrad_kernel<<<dim3(GH, 3, 3), 256, 0, stream>>>(x, a->mask012, B, L, w.doutf, mvec, qg, w.du, w.dqf, dWvg,
+                                                           dWkg, dWqg);
+    if ((rc = check_launch("rf_global_attn_bwd/wgrad"))) return rc;
+  }
   if (dx != nullptr) return rf_global_attn_bwd_dx(a, u, pt, dx, ws, stream_);
   return RF_OK;
+}
+
+extern "C" int rf_global_attn_bwd_wgrad(const rf_global_args* a, const float* qg, const float* mvec, const float* ws,
+                                        float* dWqg, float* dWkg, float* dWvg, rf_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  RF_REQUIRE(a && qg && mvec && ws && dWqg && dWkg && dWvg, "rf_global_attn_bwd_wgrad: null argument");
+  RF_REQUIRE(a->H == GH && a->D == GD, "rf_global_attn_bwd_wgrad: only H=12, D=64 supported (got %d, %d)", a->H, a->D);
+  const BwdWs w(const_cast<float*>(ws), a->B, a->L);
+  global_wgrad_kernel<<<dim3(GH, 3, 3), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->x), a->mask012, a->B, a->L,
+                                                         w.doutf, mvec, qg, w.du, w.dqf, dWvg, dWkg, dWqg);
+  return check_launch("rf_global_attn_bwd_wgrad");
 }

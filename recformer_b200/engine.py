@@ -218,6 +218,9 @@ class FlatParams:
 _SAVE_KEEPBITS = os.environ.get("RF_NO_KEEPBITS", "0") != "1"
 
 
+_GLOBAL_WGRAD_INLINE = os.environ.get("RF_GLOBAL_WGRAD_INLINE", "0") == "1"     # A/B aid: the former launch order
+
+
 class SavedActivations:
     """Everything one forward pass keeps for its backward (or, in eval, reusable scratch)."""
 
@@ -614,6 +617,7 @@ class EncoderEngine:
                 else:
                     fn()
 
+            ev_w = None
             # ---- output block: LN2 <- dense(W2) <- gelu <- dense(W1) ----
             ops.layernorm_bwd(d_out, sv.pre2[i], sv.stats2[i], W["ln2w"], G["ln2w"], G["ln2b"], dx=d_pre2,
                               dx_dropped=dY2 if pd > 0 else None, drop_p=pd, drop_seed=self._seed(sv, i, 4),
@@ -643,11 +647,19 @@ class EncoderEngine:
                 ev_d.record(main)
                 side.wait_event(ev_d)
                 with torch.cuda.stream(side):
-                    ops.global_attn_bwd(*gargs, sc.dctx, sv.glob[i], None, G["Wqg"], G["bqg"], G["Wkg"], G["Wvg"],
+                    # the three *_global weight gradients feed only the optimiser: they are launched AFTER the operands
+                    # the main stream waits for (ev_a), off the critical chain; ev_w joins them at the end of the layer
+                    late = not _GLOBAL_WGRAD_INLINE
+                    ops.global_attn_bwd(*gargs, sc.dctx, sv.glob[i], None, None if late else G["Wqg"], G["bqg"],
+                                        None if late else G["Wkg"], None if late else G["Wvg"],
                                         G["bvg"], ws=sc.gws, drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 2))
                     if sc.xk is not None and not self._debug_no_xk:
                         ops.global_attn_bwd_xk(*gargs, sv.glob[i], sc.gws, *sc.xk)
                     ev_a.record(side)
+                    if late:
+                        ops.global_attn_bwd_wgrad(*gargs, sv.glob[i], sc.gws, G["Wqg"], G["Wkg"], G["Wvg"])
+                        ev_w = self.event(device, "gW", i)
+                        ev_w.record(side)
             ops.band_attn_bwd(sv.qkv[i], mask, B, Lp, H, w_one, sv.ctx[i], sv.lse[i], sc.dctx, dqkv, sc.dkv,
                               drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 1), ws=self.attn_ws(B, Lp, w_one, device),
                               keepbits=sv.keepbits[i])
@@ -675,6 +687,8 @@ class EncoderEngine:
                                     ws=sc.gws, drop_p=sv.drop_attn, drop_seed=self._seed(sv, i, 2))
             d_out = dx
             aux_marks[i] = self.aux_done
+            if ev_w is not None:               # this layer's *_global weight gradients (long finished: launched a layer ago)
+                main.wait_event(ev_w)
             if self.grad_hook is not None:
                 self.grad_hook(i)
         if self.aux_done is not None:         # join the aux stream: every gradient is final when backward() returns

@@ -495,6 +495,14 @@ def global_attn_bwd(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, dctx, saved, d
     return ws
 
 
+def global_attn_bwd_wgrad(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, saved, ws, dWqg, dWkg, dWvg):
+    """After global_attn_bwd(..., dWqg=None, dWkg=None, dWvg=None): the three *_global weight gradients (same ws)."""
+    a = _global_args(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, 0.0, 0)
+    check(_lib.lib().rf_global_attn_bwd_wgrad(C.byref(a), saved["qg"].data_ptr(), saved["mvec"].data_ptr(), ws.data_ptr(),
+                                              dWqg.data_ptr(), dWkg.data_ptr(), dWvg.data_ptr(), _stream()),
+          "rf_global_attn_bwd_wgrad")
+
+
 def global_attn_bwd_xk(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, saved, ws, cf, dmu):
     """After global_attn_bwd(dx=None): packs the CLS row's token gradients as the two bf16 operands of a
     rank-64 per-sequence update, dx[b] += cf[b] @ dmu[b] (cf [B*L,64], dmu [B*64,E]), for gemm(..., xk=)."""

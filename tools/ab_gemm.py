@@ -21,6 +21,9 @@ dW1 = torch.zeros(F, E, dtype=torch.float32, device=dev)
 CASES = {
     "qkv": (lambda: ops.gemm(x, Wqkv, out=qkv, bias=bqkv, scale=0.125, scale_ncols=E), 3 * E * E),
     "wo_res_drop": (lambda: ops.gemm(x, Wo, out=pre, bias=bo, residual=res32, drop_p=0.1, drop_seed=1), E * E),
+    "wo_res_nodrop": (lambda: ops.gemm(x, Wo, out=pre, bias=bo, residual=res32), E * E),
+    "wo_bf16_plain": (lambda: ops.gemm(x, Wo, out=dx, bias=bo), E * E),
+    "down_res_nodrop": (lambda: ops.gemm(gl, W2, out=pre, bias=b2, residual=res32), F * E),
     "up_gelu": (lambda: ops.gemm(x, W1, out=u, bias=b1, epi=ops.EPI_GELU, out2=gl), F * E),
     "down_res_drop": (lambda: ops.gemm(gl, W2, out=pre, bias=b2, residual=res32, drop_p=0.1, drop_seed=1), F * E),
     "dgrad_down_dgelu": (lambda: ops.gemm(dY, W2, out=dU, b_mn_major=True, epi=ops.EPI_DGELU, aux=u), F * E),
