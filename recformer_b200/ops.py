@@ -483,7 +483,8 @@ def global_attn_bwd_ws(B, L, H, device):
 def global_attn_bwd(x, mask012, Wqg, bqg, Wkg, Wvg, bvg, B, L, H, dctx, saved, dx, dWqg, dbqg, dWkg, dWvg, dbvg,
                     ws=None, drop_p=0.0, drop_seed=0):
     """Accumulates the *_global weight grads and, if dx is given, adds the CLS row's dense gradient into dx
-    (bf16 [B*L,E]).  With dx=None call global_attn_bwd_dx afterwards (same ws)."""
+    (bf16 [B*L,E]).  With dx=None call global_attn_bwd_dx afterwards (same ws); with dWqg = dWkg = dWvg = None the
+    three weight-gradient outer products are left to global_attn_bwd_wgrad (same ws)."""
     nbytes = int(_lib.lib().rf_global_attn_bwd_ws_bytes(B, L, H))
     if ws is None or ws.numel() * ws.element_size() < nbytes:
         ws = global_attn_bwd_ws(B, L, H, x.device)

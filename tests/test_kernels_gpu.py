@@ -584,6 +584,17 @@ def test_global_attention_bwd(B, L):
     for n in ("Wq", "bq", "Wk", "Wv", "bv"):
         assert relerr(grads[n], P[n].grad) < 5e-3, n      # ds is a bf16 tensor-core operand of the du contraction
     assert P["bk"].grad.abs().max() < 1e-5
+    # the engine's launch order: weight-gradient outer products as their own launch (rf_global_attn_bwd_wgrad) after the
+    # rest of the chain — same kernel on the same workspace, so the gradients are bit-identical to the inline form
+    ws3 = ops.global_attn_bwd_ws(B, L, H, DEV)
+    g3 = {n: torch.zeros_like(t) for n, t in grads.items()}
+    ops.global_attn_bwd(x, mask, Wq, bq, Wk, Wv, bv, B, L, H, dctx, saved, None, None, g3["bq"], None, None, g3["bv"], ws=ws3)
+    assert all(g3[n].abs().max() == 0 for n in ("Wq", "Wk", "Wv"))
+    ops.global_attn_bwd_wgrad(x, mask, Wq, bq, Wk, Wv, bv, B, L, H, saved, ws3, g3["Wq"], g3["Wk"], g3["Wv"])
+    for n in ("Wq", "Wk", "Wv"):
+        assert torch.equal(g3[n], grads[n]), n
+    for n in ("bq", "bv"):                       # (bias gradients are accumulated with float atomics: order may differ)
+        assert relerr(g3[n], grads[n]) < 1e-5, n
     if L % 256 == 0:
         # the same token gradients packed as the extra k-block of the QKV dgrad GEMM (engine path for L % 256 == 0)
         ws = ops.global_attn_bwd_ws(B, L, H, DEV)
