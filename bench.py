@@ -52,7 +52,7 @@ def profiled_traffic(kernel_substr):
     try:
         files = sorted(f for f in os.listdir(pdir) if f.endswith("_traffic.json"))
         d = json.load(open(os.path.join(pdir, files[-1])))
-        sel = [v for k, v in d.items() if kernel_substr in k]
+        sel = [v for k, v in d.items() if kernel_substr in k and "[" not in k]      # "[...]" = captures at other sizes
         if not sel:
             return None, None
         n = sum(v["n"] for v in sel)

@@ -141,6 +141,8 @@ for f in sorted(os.listdir(G)):
         mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6, "second": 1e6}
         for r in raw[2:]:
             name = re.sub(r"\(CUtensorMap.*", "", r[ik])
+            if "shard" in f:          # a capture at another problem size must not be averaged into the full-size entry
+                name += " [125k-item shard]"
             t = traffic.setdefault(name, {"dram_bytes": 0.0, "time_us": 0.0, "n": 0, "source": f})
             t["dram_bytes"] += float(r[ir]) * mult[ur] + float(r[iw]) * mult[uw]
             t["time_us"] += float(r[it]) * mult[ut]
