@@ -11,6 +11,7 @@ import bench
 from recformer_b200.optim import FusedAdamW
 
 graph = "--graph" in sys.argv
+e2e = "--e2e" in sys.argv          # with --graph: pinned host batches in, loss.item() out every step (bench.py's e2e loop)
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 steps = int(args[0]) if args else 2
 dev = torch.device("cuda", 0)
@@ -30,7 +31,9 @@ if graph:      # the captured step the bench times (python tools/step_timeline.p
     torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for i in range(steps):
-        if graph:
+        if graph and e2e:
+            float(gstep(host[i % 2]).item())
+        elif graph:
             gstep(batches[i % 2])
         else:
             bench.train_step(model, opt, batches[i % 2], 1)
