@@ -194,8 +194,11 @@ int rf_layernorm_bwd(const void* dy_bf16, const float* x_f32, const float* stats
  * HF:481-639 + helpers HF:641-961).  qkv is the fused projection output [B*L, 3*E] bf16 with
  * q already scaled by 1/sqrt(D); mask012 is the merged mask (ref: recformer/models.py:262-272)
  * as uint8 [B,L]: 0 padding, 1 local, 2 global.  Only position 0 may be global (the
- * tokenizer's layout, ref: recformer/tokenization.py:97-99).  One CTA per (batch, head,
- * 128-query tile): TMA loads, QK^T and PV on tcgen05 with TMEM accumulators, fp32 softmax.
+ * tokenizer's layout, ref: recformer/tokenization.py:97-99).  Work unit = (batch, head,
+ * 128-query tile): TMA loads, QK^T and PV on tcgen05 with TMEM accumulators, fp32 softmax;
+ * attention_window 64 runs persistent kernels (one CTA per SM walks a contiguous run of tiles,
+ * forward and backward), wider windows one CTA per tile (forward) / 65-offset segments (backward).
+ * ctx and dqkv must be 32-byte aligned (256-bit stores).
  *   ctx  [B*L, E] bf16: attention output of every NON-global query (row 0 of each sequence
  *        is written by rf_global_attn_fwd); padded query rows are exactly zero (HF:578).
  *   lse  [B,H,L] fp32: log-sum-exp of each query row (saved for backward).
