@@ -25,8 +25,33 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(handle, name), f"{name} declared in include/recformer_b200.h but not exported"
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     lib = _lib.lib()
-    assert lib.rf_version() >= 100
+    assert lib.rf_version() >= 102
     assert lib.rf_launch_count() == 0
+
+
+def _header_struct_fields(header, name):
+    """Field names of `typedef struct <name> {...} <name>;` in declaration order (comments stripped)."""
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), header, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for piece in decl.split(","):                       # "int M, N, K" -> M, N, K
+            fields.append(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", piece)[-1])
+    return fields
+
+
+@pytest.mark.parametrize("cname,ctype", [("rf_gemm_args", "GemmArgs"), ("rf_attn_args", "AttnArgs"),
+                                         ("rf_global_args", "GlobalArgs"), ("rf_embed_args", "EmbedArgs")])
+def test_ctypes_structs_mirror_the_header(cname, ctype):
+    """The ctypes mirrors in _lib.py must list exactly the header's fields, in order (structs only ever grow at the end;
+    a field added on one side only would shift every later argument)."""
+    header = open(os.path.join(ROOT, "include", "recformer_b200.h")).read()
+    if re.search(r"typedef struct %s \{" % cname, header) is None:
+        pytest.skip(f"{cname} is not a struct of this header")
+    assert _header_struct_fields(header, cname) == [f[0] for f in getattr(_lib, ctype)._fields_]
 
 
 def test_argument_validation_errors_without_gpu():
