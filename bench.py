@@ -181,25 +181,25 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 def build_model(device):
     import recformer_b200 as rb
-    from oracle import recformer_oracle as O   # synthetic weights / batches only (shared generators)
+    from tools import synthetic as S           # seeded weights / batches (neutral ground: not the oracle)
     cfg = rb.RecformerConfig(attention_window=[64] * NL, max_token_num=SEQ_LEN, max_item_embeddings=51,
                              max_attr_num=3, max_attr_length=32, item_num=N_ITEMS)
     model = rb.RecformerForSeqRec(cfg)
-    sd = O.make_state_dict(O.OracleConfig(), seed=0, prefix="longformer.")
+    sd = S.make_state_dict(S.SynthConfig(), seed=0, prefix="longformer.")
     model.load_state_dict(sd, strict=True)
     model = model.to(device)
-    model.init_item_embedding(O.make_item_table(N_ITEMS, E, seed=1).to(device))
+    model.init_item_embedding(S.make_item_table(N_ITEMS, E, seed=1).to(device))
     model.longformer.strict_checks = False     # device-side input validation stays on; no per-step host sync
     return model, cfg
 
 
 def make_batches(n, device, rank):
-    from oracle import recformer_oracle as O
-    ocfg = O.OracleConfig()
+    from tools import synthetic as S
+    ocfg = S.SynthConfig()
     host, dev = [], []
     g = torch.Generator().manual_seed(1234 + rank)
     for i in range(n):
-        b = O.make_batch(ocfg, B_PER_GPU, SEQ_LEN, seed=1000 * rank + i, ragged=True)
+        b = S.make_batch(ocfg, B_PER_GPU, SEQ_LEN, seed=1000 * rank + i, ragged=True)
         b["labels"] = torch.randint(0, N_ITEMS, (B_PER_GPU,), generator=g)
         host.append({k: v.pin_memory() for k, v in b.items()})
         dev.append({k: v.to(device) for k, v in b.items()})

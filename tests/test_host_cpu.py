@@ -220,3 +220,42 @@ def test_ranker_and_topk_ranker_match_reference(goldens):
         top = torch.topk(s, 50, dim=-1).values
         tk = rb.TopKRanker([10, 50])(top, s[torch.arange(s.shape[0]), lab])
         assert np.allclose(tk, g["metrics"][:4], atol=1e-6)
+
+
+def _imports_of(path):
+    """(function name or '<module>', imported module) pairs of one source file, from its AST."""
+    import ast
+    tree = ast.parse(open(path).read())
+    out = []
+
+    def walk(node, scope):
+        for child in ast.iter_child_nodes(node):
+            s = child.name if isinstance(child, (ast.FunctionDef, ast.AsyncFunctionDef)) else scope
+            if isinstance(child, ast.Import):
+                out.extend((scope, a.name) for a in child.names)
+            elif isinstance(child, ast.ImportFrom):
+                out.extend((scope, (child.module or "") + "." + a.name) for a in child.names)
+            walk(child, s)
+
+    walk(tree, "<module>")
+    return out
+
+
+def test_only_the_checker_legs_import_the_oracle():
+    """The oracle is test infrastructure: the product package and the neutral input generators never import it, and in
+    bench.py only the cpu_baseline / --impl reference functions do (the product arm builds its inputs from
+    tools/synthetic.py)."""
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    product = glob.glob(os.path.join(root, "recformer_b200", "**", "*.py"), recursive=True) + \
+        glob.glob(os.path.join(root, "recformer", "**", "*.py"), recursive=True) + [os.path.join(root, "tools", "synthetic.py")]
+    assert len(product) > 10
+    for path in product:
+        bad = [m for _, m in _imports_of(path) if m.split(".")[0] == "oracle"]
+        assert not bad, (path, bad)
+    assert not [m for _, m in _imports_of(os.path.join(root, "tools", "synthetic.py")) if m.startswith("recformer")]
+    allowed = {"cpu_finetune_step_rate", "cpu_eval_baseline", "cpu_c1_baseline"}
+    users = {scope for scope, m in _imports_of(os.path.join(root, "bench.py")) if m.split(".")[0] == "oracle"}
+    assert users and users <= allowed, users
+    for tool in glob.glob(os.path.join(root, "tools", "*.py")):
+        assert not [m for _, m in _imports_of(tool) if m.split(".")[0] == "oracle"], tool

@@ -2,7 +2,7 @@
   configs[2]  pretraining step (MLM + in-batch contrastive, batch 64/GPU, data-parallel)  -> pretrain_bench
   configs[4]  long-sequence stress (2 x 4096 tokens, attention_window 64 -> 512, fwd+bwd) -> longseq_bench
 bench.py carries their results as extra keys of its JSON line; tools/bench_pretrain.py / bench_longseq.py print them
-stand-alone.  Synthetic weights / batches come from the shared generators in oracle/ (no arithmetic from there)."""
+stand-alone.  Synthetic weights / batches come from the seeded generators in tools/synthetic.py (not from the oracle)."""
 from __future__ import annotations
 
 import torch
@@ -34,8 +34,8 @@ def pretrain_bench(device, rank, world, steps=3, warmup=3, B=64, LA=1024, LB=128
     import recformer_b200 as rb
     from recformer_b200 import dist as rdist
     from recformer_b200.optim import FusedAdamW
-    from oracle import recformer_oracle as O
-    ocfg = O.OracleConfig()
+    from tools import synthetic as O
+    ocfg = O.SynthConfig()
     cfg = rb.RecformerConfig(attention_window=[64] * NL, max_token_num=LA, max_item_embeddings=51, max_attr_num=3,
                              max_attr_length=32)
     model = rb.RecformerForPretraining(cfg)
@@ -81,14 +81,14 @@ def pretrain_bench(device, rank, world, steps=3, warmup=3, B=64, LA=1024, LB=128
 
 def longseq_bench(device, windows=(64, 128, 256, 512), steps=3, warmup=3, B=2, L=4096, sustained_tflops=None):
     import recformer_b200 as rb
-    from oracle import recformer_oracle as O
+    from tools import synthetic as O
     out = []
     for window in windows:
         cfg = rb.RecformerConfig(attention_window=[window] * NL, max_token_num=L, hidden_dropout_prob=0.0,
                                  attention_probs_dropout_prob=0.0)
         model = rb.RecformerModel(cfg).to(device).train()
         model.strict_checks = False
-        batch = {k: v.to(device) for k, v in O.make_batch(O.OracleConfig(attention_window=[window] * NL), B, L, seed=1,
+        batch = {k: v.to(device) for k, v in O.make_batch(O.SynthConfig(attention_window=[window] * NL), B, L, seed=1,
                                                           ragged=True).items()}
 
         def step(_):
