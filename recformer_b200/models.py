@@ -117,8 +117,13 @@ class RecformerPooler(nn.Module):
         if self.pooler_type == "cls":
             return hidden_states[:, 0]
         if self.pooler_type == "avg":
-            am = attention_mask[:, : hidden_states.shape[1]].to(hidden_states.dtype)
-            return (hidden_states * am.unsqueeze(-1)).sum(1) / am.sum(-1).unsqueeze(-1)
+            # the reference multiplies by the MERGED mask (0 padding / 1 local / 2 global, ref: recformer/models.py:310-312,
+            # 342), so the CLS row counts twice in numerator and denominator.  Rows with mask 0 are zeroed by selection,
+            # not by the product: with padding_rows_unused the encoder leaves them undefined (possibly non-finite).
+            am = attention_mask[:, : hidden_states.shape[1]]
+            h = hidden_states.masked_fill((am == 0).unsqueeze(-1), 0.0)
+            am = am.to(hidden_states.dtype)
+            return (h * am.unsqueeze(-1)).sum(1) / am.sum(-1).unsqueeze(-1)
         raise NotImplementedError
 
 

@@ -419,6 +419,59 @@ def test_padding_tile_skipping_leaves_real_tokens_unchanged():
     assert (got.cpu() - ref).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("skip", [False, True])
+def test_avg_pooler_matches_oracle(skip):
+    """SURVEY 8a a11, pooler_type 'avg' (ref: recformer/models.py:166-167): the mean over the MERGED mask (CLS weighted
+    2) of last_hidden_state, forward and gradient against fp32 oracle autograd.  With `padding_rows_unused` the encoder
+    skips 256-row tiles of padding and leaves those rows undefined: the pooler must not let them through."""
+    kw = dict(vocab_size=1500, num_hidden_layers=2, attention_window=[64, 64], max_position_embeddings=1100)
+    ocfg = O.OracleConfig(pooler_type="avg", **kw)
+    cfg = rb.RecformerConfig(pooler_type="avg", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **kw)
+    sd = O.make_state_dict(ocfg, seed=5)
+    model = rb.RecformerModel(cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).train()
+    model.padding_rows_unused = skip
+    batch = O.make_batch(ocfg, 3, 1024, seed=2, ragged=True)
+    for b, n in enumerate([1024, 200, 600]):         # rows 1 and 2 end with whole tiles of padding
+        batch["attention_mask"][b, n:] = 0
+        batch["input_ids"][b, n:] = ocfg.pad_token_id
+        batch["token_type_ids"][b, n:] = 3
+        batch["item_position_ids"][b, n:] = ocfg.max_item_embeddings - 1
+    w = torch.from_numpy(np.random.default_rng(0).standard_normal((3, 768), dtype=np.float32))
+    dbatch = {k: v.to(DEV) for k, v in batch.items()}
+    eng = model._engine
+    for attempt in range(2 if skip else 1):
+        if attempt == 1:                               # second pass over poisoned buffers: what skipped tiles leave behind
+            for pool in eng._free.values():
+                for sv in pool:
+                    for t in sv.x32:
+                        t.fill_(float("nan"))
+            eng.params.grad.zero_()
+        pooled = model(**dbatch).pooler_output
+        (pooled * w.to(DEV)).sum().backward()
+        torch.cuda.synchronize()
+    if skip:
+        assert any(sv.activity is not None for pool in eng._free.values() for sv in pool)   # tiles really were skipped
+    for v in sd.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    _, ref = O.model_forward(sd, ocfg, **batch)
+    (ref * w).sum().backward()
+    assert torch.isfinite(pooled).all()
+    err = (pooled.detach().cpu() - ref.detach()).abs().max().item()
+    print(f"avg pooler (skip={skip}): pooled max-abs err {err:.4f}")
+    assert err < 2e-2, err
+    named = dict(model.named_parameters())
+    for k in ("encoder.layer.1.output.dense.weight", "encoder.layer.0.attention.self.query.weight",
+              "embeddings.LayerNorm.weight"):
+        g, r = named[k].grad.cpu(), sd[k].grad
+        assert torch.isfinite(g).all(), k
+        rel = (g - r).abs().max().item() / r.abs().max().item()
+        assert rel < 0.08, (k, rel)
+        assert abs(g.norm().item() - r.norm().item()) < 0.05 * r.norm().item(), k
+
+
 def _graph_setup(dropout, seed=7):
     from recformer_b200.optim import FusedAdamW
     ocfg, cfg, model, sd = build(dict(vocab_size=1500, num_hidden_layers=2, attention_window=[64, 64],
