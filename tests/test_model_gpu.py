@@ -426,7 +426,9 @@ def test_avg_pooler_matches_oracle(skip):
     skips 256-row tiles of padding and leaves those rows undefined: the pooler must not let them through."""
     kw = dict(vocab_size=1500, num_hidden_layers=2, attention_window=[64, 64], max_position_embeddings=1100)
     ocfg = O.OracleConfig(pooler_type="avg", **kw)
-    cfg = rb.RecformerConfig(pooler_type="avg", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **kw)
+    cfg = rb.RecformerConfig(pooler_type="avg", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                             max_token_num=ocfg.max_token_num, max_item_embeddings=ocfg.max_item_embeddings,
+                             max_attr_num=3, max_attr_length=32, **kw)
     sd = O.make_state_dict(ocfg, seed=5)
     model = rb.RecformerModel(cfg)
     model.load_state_dict(sd, strict=True)
