@@ -222,6 +222,24 @@ def test_ranker_and_topk_ranker_match_reference(goldens):
         assert np.allclose(tk, g["metrics"][:4], atol=1e-6)
 
 
+def test_ranker_final_batch_of_one_user():
+    """A last eval batch of ONE user (len(dataset) % batch_size == 1): the reference squeezes the (1,1) labels to a 0-d
+    target, its CE raises and is caught as loss 0.0 while NDCG / Recall / MRR / AUC are still computed (ref:
+    utils.py:83-107).  Here the target stays (1,), so the ranking metrics equal the reference's and the loss is the real
+    CE instead of the 0.0 placeholder."""
+    s = torch.tensor([[0.3, 2.0, -1.0, 0.9, 0.1, 1.5]])
+    for lab, rank in ((1, 0), (3, 2), (2, 5)):
+        labels = torch.tensor([[lab]])
+        got = rb.Ranker([1, 3])(s, labels)
+        want = [1 / np.log2(rank + 2) * (rank < 1), float(rank < 1), 1 / np.log2(rank + 2) * (rank < 3), float(rank < 3),
+                1 / (rank + 1), 1 - rank / 6]
+        assert np.allclose(got[:6], want, atol=1e-6), (lab, got)
+        assert np.isclose(got[6], torch.nn.functional.cross_entropy(s, torch.tensor([lab])).item(), atol=1e-6)
+        assert rb.Ranker([1, 3])(s, torch.tensor([lab]))[:6] == got[:6]        # (B,) labels are accepted too
+        tk = rb.TopKRanker([1, 3])(torch.topk(s, 3).values, s[:, lab])
+        assert np.allclose(tk, want[:4], atol=1e-6)
+
+
 def _imports_of(path):
     """(function name or '<module>', imported module) pairs of one source file, from its AST."""
     import ast
