@@ -34,7 +34,8 @@ Tensor = torch.Tensor
 # product arm and the tools can build their inputs without importing this checker; re-exported under the old names.
 # ----------------------------------------------------------------------------------------------
 from tools.synthetic import (SynthConfig as OracleConfig, MASK_TOKEN_ID, state_dict_keys, make_state_dict,  # noqa: E402,F401
-                             make_batch, make_item_table, lm_head_keys, make_pretrain_state_dict, make_pretrain_batch)
+                             make_batch, make_item_table, lm_head_keys, make_pretrain_state_dict, make_pretrain_batch,
+                             classifier_keys, make_fraud_state_dict)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -230,6 +231,47 @@ def seqrec_forward(sd, cfg: OracleConfig, batch: Dict[str, Tensor], item_embeddi
         return F.cross_entropy(logits, labels)
     logits = similarity_score(pooled, item_embedding, cfg.temp, candidates)
     return F.cross_entropy(logits, torch.zeros_like(labels))
+
+
+# ----------------------------------------------------------------------------------------------
+# binary classification head (ref: recformer/models.py:601-713; caller finetune_classification.py)
+# ----------------------------------------------------------------------------------------------
+def focal_loss(inputs: Tensor, targets: Tensor, alpha: Optional[float] = 1, gamma: float = 2,
+               pos_weight: Optional[Tensor] = None) -> Tensor:
+    """ref: recformer/models.py:611-631 — p = sigmoid(x); p_t = p t + (1-p)(1-t); loss = alpha_t (1-p_t)^gamma BCE(x, t)
+    with alpha_t = alpha t + (1-alpha)(1-t) (skipped when alpha is None); mean over the batch."""
+    p = torch.sigmoid(inputs)
+    # BCE with logits and pos_weight w: -(w t log p + (1-t) log(1-p)), written with logsigmoid for stability
+    w = 1.0 if pos_weight is None else pos_weight
+    ce = -(w * targets * F.logsigmoid(inputs) + (1 - targets) * F.logsigmoid(-inputs))
+    p_t = p * targets + (1 - p) * (1 - targets)
+    out = (1 - p_t) ** gamma * ce
+    if alpha is not None:
+        out = (alpha * targets + (1 - alpha) * (1 - targets)) * out
+    return out.mean()
+
+
+def fraud_head(sd: Dict[str, Tensor], pooled: Tensor) -> Tensor:
+    """ref: recformer/models.py:643-651,697-699 in eval mode (the three dropouts are identities): Linear/ReLU ->
+    Linear/ReLU -> Linear -> squeeze(-1).  Returns logits (B,)."""
+    h = torch.relu(F.linear(pooled, sd["classifier.0.weight"], sd["classifier.0.bias"]))
+    h = torch.relu(F.linear(h, sd["classifier.3.weight"], sd["classifier.3.bias"]))
+    return F.linear(h, sd["classifier.6.weight"], sd["classifier.6.bias"]).squeeze(-1)
+
+
+def bce_with_logits(logits: Tensor, labels: Tensor, pos_weight: float = 1.0) -> Tensor:
+    """ref: recformer/models.py:702-708 — nn.BCEWithLogitsLoss(pos_weight=w)(logits, labels.float()):
+    mean of -(w t log sigmoid(x) + (1 - t) log sigmoid(-x))."""
+    t = labels.float()
+    return -(pos_weight * t * F.logsigmoid(logits) + (1 - t) * F.logsigmoid(-logits)).mean()
+
+
+def fraud_forward(sd: Dict[str, Tensor], cfg: OracleConfig, batch: Dict[str, Tensor], labels: Optional[Tensor] = None,
+                  pos_weight: float = 1.0):
+    """ref: recformer/models.py:677-713 — encoder -> pooled -> head; returns (loss or None, logits (B,))."""
+    _, pooled = model_forward(sd, cfg, prefix="longformer.", **batch)
+    logits = fraud_head(sd, pooled)
+    return (None if labels is None else bce_with_logits(logits, labels, pos_weight)), logits
 
 
 # ----------------------------------------------------------------------------------------------

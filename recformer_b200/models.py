@@ -467,6 +467,89 @@ class RecformerForSeqRec(nn.Module):
 
 
 # --------------------------------------------------------------------------------------------
+# binary classification head on the CLS vector (ref: recformer/models.py:601-713; the caller finetune_classification.py)
+# --------------------------------------------------------------------------------------------
+class FocalLoss(nn.Module):
+    """ref: recformer/models.py:601-631 — mean of alpha_t * (1 - p_t)^gamma * BCE-with-logits(inputs, targets)."""
+
+    def __init__(self, alpha=1, gamma=2, pos_weight=None):
+        super().__init__()
+        self.alpha = alpha
+        self.gamma = gamma
+        self.pos_weight = pos_weight
+
+    def forward(self, inputs, targets):
+        probs = torch.sigmoid(inputs)
+        ce = nn.functional.binary_cross_entropy_with_logits(inputs, targets, pos_weight=self.pos_weight, reduction="none")
+        p_t = probs * targets + (1 - probs) * (1 - targets)
+        loss = (1 - p_t) ** self.gamma * ce
+        if self.alpha is not None:
+            loss = (self.alpha * targets + (1 - self.alpha) * (1 - targets)) * loss
+        return loss.mean()
+
+
+class RecformerForFraudDetection(nn.Module):
+    """ref: recformer/models.py:633-713 — dropout + a 768 -> 384 -> 192 -> 1 ReLU MLP on the encoder's pooled output,
+    BCE-with-logits (config.pos_weight) against 0/1 labels.  The encoder pass is the CUDA engine (CLS-only entry when
+    the pooler is 'cls': forward_pooled); the head works on (B, 768) vectors — a few MFLOP — and stays plain torch, its
+    parameters live outside the encoder's flat buffer (FusedAdamW steps them through its `extra_params` optimizer)."""
+
+    def __init__(self, config: RecformerConfig):
+        super().__init__()
+        self.config = config
+        self.longformer = RecformerModel(config)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob if hasattr(config, "hidden_dropout_prob") else 0.1)
+        E = config.hidden_size
+        self.classifier = nn.Sequential(nn.Linear(E, E // 2), nn.ReLU(), nn.Dropout(0.2),
+                                        nn.Linear(E // 2, E // 4), nn.ReLU(), nn.Dropout(0.2),
+                                        nn.Linear(E // 4, 1))
+        self.classifier.apply(lambda m: _init_weights(m, config.initializer_range))       # HF post_init (ref :659)
+        # a plain attribute, not a buffer: absent from the state dict, as in the reference (ref :656)
+        self.pos_weight = torch.tensor(config.pos_weight) if hasattr(config, "pos_weight") else torch.tensor(1.0)
+
+    def init_item_embedding(self, embeddings: Optional[torch.Tensor] = None):
+        self.item_embedding = nn.Embedding(num_embeddings=self.config.item_num, embedding_dim=self.config.hidden_size)
+        if embeddings is not None:
+            self.item_embedding = nn.Embedding.from_pretrained(embeddings, freeze=True)
+            print("Initalize item embeddings from vectors.")
+
+    def forward(self,
+                input_ids: Optional[torch.Tensor] = None,
+                attention_mask: Optional[torch.Tensor] = None,
+                global_attention_mask: Optional[torch.Tensor] = None,
+                head_mask: Optional[torch.Tensor] = None,
+                token_type_ids: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.Tensor] = None,
+                item_position_ids: Optional[torch.Tensor] = None,
+                inputs_embeds: Optional[torch.Tensor] = None,
+                output_attentions: Optional[bool] = None,
+                output_hidden_states: Optional[bool] = None,
+                return_dict: Optional[bool] = None,
+                labels: Optional[torch.Tensor] = None):
+        return_dict = return_dict if return_dict is not None else self.config.use_return_dict
+        if head_mask is None and inputs_embeds is None and not output_attentions and not output_hidden_states:
+            pooler_output = self.longformer.forward_pooled(input_ids, attention_mask=attention_mask,
+                                                           global_attention_mask=global_attention_mask,
+                                                           token_type_ids=token_type_ids, position_ids=position_ids,
+                                                           item_position_ids=item_position_ids)
+        else:                       # unsupported kwargs raise inside RecformerModel.forward, as documented there
+            pooler_output = self.longformer(input_ids, attention_mask=attention_mask,
+                                            global_attention_mask=global_attention_mask, head_mask=head_mask,
+                                            token_type_ids=token_type_ids, position_ids=position_ids,
+                                            item_position_ids=item_position_ids, inputs_embeds=inputs_embeds,
+                                            output_attentions=output_attentions,
+                                            output_hidden_states=output_hidden_states, return_dict=True).pooler_output
+        logits = self.classifier(self.dropout(pooler_output)).squeeze(-1)            # (B,)
+        loss = None
+        if labels is not None:
+            loss = nn.functional.binary_cross_entropy_with_logits(logits, labels.float(),
+                                                                  pos_weight=self.pos_weight.to(logits.device))
+        if not return_dict:
+            return (loss, logits)
+        return {"loss": loss, "logits": logits}
+
+
+# --------------------------------------------------------------------------------------------
 # pretraining (ref: recformer/models.py:372-520; SURVEY.md §8f-2)
 # --------------------------------------------------------------------------------------------
 @dataclass

@@ -115,6 +115,47 @@ def case_pretrain(name, cfg_kw, B, La, Lb, sd_seed=0, batch_seed=0):
             "grads": grads, "state_keys": sorted(m.state_dict().keys())}
 
 
+def case_fraud(name, cfg_kw, B, L, sd_seed=0, batch_seed=0, pos_weight=3.0):
+    """RecformerForFraudDetection + FocalLoss (ref: recformer/models.py:601-713): logits, BCE(pos_weight) loss and
+    gradient fingerprints from the reference's own autograd (eval(): its three dropouts off), plus FocalLoss values
+    on seeded logits / targets for three (alpha, gamma, pos_weight) settings."""
+    import numpy as np
+    ocfg = O.OracleConfig(**cfg_kw)
+    ref = ref_shim.load_reference()
+    rcfg = ref_shim.reference_config(ocfg)
+    rcfg.pos_weight = pos_weight
+    m = ref.RecformerForFraudDetection(rcfg).eval()
+    sd = O.make_fraud_state_dict(ocfg, seed=sd_seed)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    batch = O.make_batch(ocfg, B, L, seed=batch_seed, ragged=True)
+    labels = torch.from_numpy(np.random.default_rng(9).integers(0, 2, size=B))
+    out = m(**batch, labels=labels)
+    out["loss"].backward()
+    grads = {}
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        gflat = p.grad.reshape(-1)
+        grads[k] = {"norm": gflat.norm().item(), "head": gflat[:32].clone(), "sum": gflat.double().sum().item()}
+        if gflat.numel() <= 4096:
+            grads[k]["full"] = p.grad.clone()
+    tup = m(**batch, labels=labels, return_dict=False)
+    assert isinstance(tup, tuple) and torch.equal(tup[1], out["logits"])
+    rng = np.random.default_rng(21)
+    x = torch.from_numpy(rng.standard_normal(64).astype(np.float32) * 3)
+    t = torch.from_numpy(rng.integers(0, 2, size=64).astype(np.float32))
+    focal = []
+    for alpha, gamma, pw in ((1, 2, None), (0.6, 2, None), (None, 1.5, 2.5)):
+        f = ref.FocalLoss(alpha=alpha, gamma=gamma, pos_weight=None if pw is None else torch.tensor(pw))
+        focal.append({"alpha": alpha, "gamma": gamma, "pos_weight": pw, "value": f(x, t).item()})
+    print(f"{name}: loss {out['loss'].item():.6f}, logits {out['logits'].tolist()}, {len(grads)} grads, focal "
+          f"{[round(f['value'], 5) for f in focal]}")
+    return {"cfg": cfg_kw, "B": B, "L": L, "sd_seed": sd_seed, "batch_seed": batch_seed, "pos_weight": pos_weight,
+            "labels": labels, "loss": out["loss"].item(), "logits": out["logits"].detach().clone(), "grads": grads,
+            "state_keys": sorted(m.state_dict().keys()), "focal_x": x, "focal_t": t, "focal": focal}
+
+
 def case_ranker():
     ru = ref_shim.load_reference_utils()
     import numpy as np
@@ -174,6 +215,12 @@ def main():
         torch.save(g, path)
         print("updated", path, os.path.getsize(path) / 1e6, "MB")
         return
+    if "--only-fraud" in sys.argv:         # add the classification-head case (RecformerForFraudDetection, FocalLoss)
+        g = torch.load(path, weights_only=False)
+        g["fraud_small"] = case_fraud("fraud_small", small_cfg(), B=4, L=300)
+        torch.save(g, path)
+        print("updated", path, os.path.getsize(path) / 1e6, "MB")
+        return
     if "--only-train12" in sys.argv:       # add the 12-layer C2-shaped training case (BASELINE configs[1] shape)
         g = torch.load(path, weights_only=False)
         g["train_c2_12layer"] = case_train("train_c2_12layer", dict(), B=4, L=1024, N=5000, batch_seed=11, n_samples=512)
@@ -193,6 +240,7 @@ def main():
     g["train_small"] = case_train("train_small", small_cfg(), B=3, L=200, N=50)
     g["pretrain_small"] = case_pretrain("pretrain_small", small_cfg(), B=4, La=300, Lb=97)
     g["train_c2_12layer"] = case_train("train_c2_12layer", dict(), B=4, L=1024, N=5000, batch_seed=11, n_samples=512)
+    g["fraud_small"] = case_fraud("fraud_small", small_cfg(), B=4, L=300)
     g["ranker"] = case_ranker()
     g["tokenizer"] = case_tokenizer()
     path = os.path.join(OUT, "reference_goldens.pt")

@@ -474,6 +474,82 @@ def test_avg_pooler_matches_oracle(skip):
         assert abs(g.norm().item() - r.norm().item()) < 0.05 * r.norm().item(), k
 
 
+def _check_fraud_head_grads(pooled, g, got):
+    """Gradients of BCE(pos_weight)(head(pooled), labels) w.r.t. the six classifier tensors by fp32 CPU autograd through
+    the oracle head, against `got` (name -> gradient)."""
+    sdh = {k: v.clone().requires_grad_(True)
+           for k, v in O.make_fraud_state_dict(O.OracleConfig(**g["cfg"]), seed=g["sd_seed"]).items() if k.startswith("classifier.")}
+    O.bce_with_logits(O.fraud_head(sdh, pooled), g["labels"], g["pos_weight"]).backward()
+    assert len(got) == 6
+    for k, v in sdh.items():
+        err = (got[k] - v.grad).abs().max().item()
+        assert err <= 1e-3 * v.grad.abs().max().item() + 1e-7, (k, err, v.grad.abs().max().item())
+
+
+def test_fraud_detection_head_matches_reference(goldens):
+    """RecformerForFraudDetection (ref: recformer/models.py:633-713; caller finetune_classification.py): logits, BCE
+    (pos_weight) loss and gradients of the drop-in (CUDA encoder + torch head) against the fixture made by the
+    unmodified reference, the return conventions, and one FusedAdamW step reaching the head's parameters."""
+    from recformer_b200.optim import FusedAdamW
+    g = goldens["fraud_small"]
+    ocfg = O.OracleConfig(**g["cfg"])
+    cfg = rb.RecformerConfig(attention_window=list(ocfg.attention_window), vocab_size=ocfg.vocab_size,
+                             num_hidden_layers=ocfg.num_hidden_layers, max_position_embeddings=ocfg.max_position_embeddings,
+                             max_token_num=ocfg.max_token_num, max_item_embeddings=ocfg.max_item_embeddings,
+                             max_attr_num=3, max_attr_length=32, pos_weight=g["pos_weight"])
+    model = rb.RecformerForFraudDetection(cfg)
+    model.load_state_dict(O.make_fraud_state_dict(ocfg, seed=g["sd_seed"]), strict=True)
+    model = model.to(DEV).eval()                       # the fixture was made with dropout off
+    batch = {k: v.to(DEV) for k, v in O.make_batch(ocfg, g["B"], g["L"], seed=g["batch_seed"], ragged=True).items()}
+    labels = g["labels"].to(DEV)
+    with torch.no_grad():
+        out0 = model(**batch)
+    assert out0["loss"] is None and out0["logits"].shape == (g["B"],)
+    out = model(**batch, labels=labels)
+    lerr = (out["logits"].detach().cpu() - g["logits"]).abs().max().item()
+    print(f"fraud head: logits max-abs err {lerr:.5f}, loss {out['loss'].item():.5f} vs {g['loss']:.5f}")
+    assert lerr < LOGIT_TOL and (out0["logits"] - out["logits"].detach()).abs().max().item() < 1e-5
+    assert abs(out["loss"].item() - g["loss"]) < 1e-2
+    tup = model(**batch, labels=labels, return_dict=False)
+    assert isinstance(tup, tuple) and (tup[1].detach() - out["logits"].detach()).abs().max().item() < 1e-5
+    out["loss"].backward()
+    torch.cuda.synchronize()
+    named = dict(model.named_parameters())
+    worst = 0.0
+    for k, fp in g["grads"].items():
+        got = named[k].grad
+        if fp["norm"] < 1e-6:          # softmax-invariant biases, the last layer's local q/k/v: rounding noise upstream
+            assert got is None or got.abs().max().item() < 1e-5, k
+            continue
+        got = got.float().cpu()
+        assert abs(got.norm().item() - fp["norm"]) < 0.06 * fp["norm"] + 1e-7, (k, got.norm().item(), fp["norm"])
+        if "full" in fp and not k.startswith("classifier."):
+            rel = (got - fp["full"]).abs().max().item() / fp["full"].abs().max().item()
+            worst = max(worst, rel)
+            assert rel < 0.12, (k, rel)
+    print(f"fraud head: worst small-tensor encoder gradient error {worst:.4f} of abs-max")
+    # The head's own gradients element-wise: its ReLU gates flip under bf16-level changes of the pooled vector (one unit
+    # switching in one of four rows moves a bias gradient by ~20 % of the tensor's abs-max), so they are compared with
+    # the oracle head evaluated on the drop-in's OWN pooled output, where fp32 torch on both sides must agree closely.
+    with torch.no_grad():
+        pooled = model.longformer.forward_pooled(**batch).float().cpu()
+    _check_fraud_head_grads(pooled, g, {k: p.grad.float().cpu() for k, p in named.items() if k.startswith("classifier.")})
+    # one optimizer step: the head lives outside the flat buffer and must move too
+    model.train()
+    opt = FusedAdamW(model, lr=1e-3, weight_decay=0.01)
+    assert len(opt.extra_params) == 6
+    before = {k: named[k].detach().clone() for k in ("classifier.0.weight", "classifier.6.bias",
+                                                     "longformer.encoder.layer.0.output.dense.weight")}
+    loss = model(**batch, labels=labels)["loss"]
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    torch.cuda.synchronize()
+    for k, b in before.items():
+        assert not torch.equal(b, named[k].detach()), k
+    assert torch.isfinite(loss).item()
+
+
 def _graph_setup(dropout, seed=7):
     from recformer_b200.optim import FusedAdamW
     ocfg, cfg, model, sd = build(dict(vocab_size=1500, num_hidden_layers=2, attention_window=[64, 64],

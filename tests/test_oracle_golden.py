@@ -139,3 +139,47 @@ def test_pretrain_step_matches_reference(goldens):
         assert (got.reshape(-1)[:32] - fp["head"]).abs().max() <= 2e-3 * fp["head"].abs().max() + 1e-6, k
     # every parameter key of the reference module exists in the oracle's state dict
     assert set(g["state_keys"]) - set(sd) == set(), set(g["state_keys"]) - set(sd)
+
+
+def test_fraud_head_and_focal_loss_match_reference(goldens):
+    """RecformerForFraudDetection / FocalLoss (ref: recformer/models.py:601-713): logits, BCE(pos_weight) loss and
+    gradient fingerprints of the oracle restatement vs the unmodified reference; FocalLoss of the oracle AND of the
+    drop-in class (plain torch, runs on CPU) vs the reference's values."""
+    g = goldens["fraud_small"]
+    ocfg = O.OracleConfig(**g["cfg"])
+    sd = O.make_fraud_state_dict(ocfg, seed=g["sd_seed"])
+    for v in sd.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    batch = O.make_batch(ocfg, g["B"], g["L"], seed=g["batch_seed"], ragged=True)
+    loss, logits = O.fraud_forward(sd, ocfg, batch, labels=g["labels"], pos_weight=g["pos_weight"])
+    assert abs(loss.item() - g["loss"]) < 1e-5
+    assert (logits - g["logits"]).abs().max() < 1e-5
+    loss.backward()
+    checked = 0
+    for k, fp in g["grads"].items():
+        got = sd[k].grad
+        if got is None:
+            assert fp["norm"] < 1e-9, k
+            continue
+        tol = 1e-6 + 5e-4 * fp["norm"]
+        assert abs(got.norm().item() - fp["norm"]) < tol, k
+        assert (got.reshape(-1)[:32] - fp["head"]).abs().max() < tol, k
+        if "full" in fp:
+            assert (got - fp["full"]).abs().max() < tol, k
+        checked += 1
+    assert checked >= 50
+    assert set(g["state_keys"]) - set(sd) == set(), set(g["state_keys"]) - set(sd)
+    import recformer_b200 as rb
+    for f in g["focal"]:
+        pw = None if f["pos_weight"] is None else torch.tensor(f["pos_weight"])
+        assert abs(O.focal_loss(g["focal_x"], g["focal_t"], f["alpha"], f["gamma"], pw).item() - f["value"]) < 1e-6
+        assert abs(rb.FocalLoss(f["alpha"], f["gamma"], pw)(g["focal_x"], g["focal_t"]).item() - f["value"]) < 1e-6
+    # the drop-in's parameter layout is the reference's (pos_weight is an attribute, not a buffer)
+    cfg = rb.RecformerConfig(attention_window=list(ocfg.attention_window), vocab_size=ocfg.vocab_size,
+                             num_hidden_layers=ocfg.num_hidden_layers, max_position_embeddings=ocfg.max_position_embeddings,
+                             max_item_embeddings=ocfg.max_item_embeddings, pos_weight=g["pos_weight"])
+    m = rb.RecformerForFraudDetection(cfg)
+    assert sorted(m.state_dict().keys()) == g["state_keys"]
+    assert float(m.pos_weight) == g["pos_weight"]
+    m.load_state_dict({k: v.detach() for k, v in sd.items()}, strict=True)

@@ -207,3 +207,24 @@ def make_pretrain_batch(cfg: SynthConfig, B: int, La: int, Lb: int, seed: int = 
         out[f"mlm_input_ids_{tag}"] = torch.from_numpy(mlm_ids)
         out[f"mlm_labels_{tag}"] = torch.from_numpy(labels)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# binary classification head (ref: recformer/models.py:633-660: classifier = 768 -> 384 -> 192 -> 1 Sequential)
+# ----------------------------------------------------------------------------------------------
+def classifier_keys(cfg: SynthConfig) -> List[tuple]:
+    E = cfg.hidden_size
+    return [("classifier.0.weight", (E // 2, E), "w"), ("classifier.0.bias", (E // 2,), "b"),
+            ("classifier.3.weight", (E // 4, E // 2), "w"), ("classifier.3.bias", (E // 4,), "b"),
+            ("classifier.6.weight", (1, E // 4), "w"), ("classifier.6.bias", (1,), "b")]
+
+
+def make_fraud_state_dict(cfg: SynthConfig, seed: int = 0, head_std: float = 0.05) -> Dict[str, Tensor]:
+    """Encoder weights under `longformer.` + a seeded classifier head.  The head's matrices are N(0, 0.05) rather than
+    HF's 0.02 so that the logits (three small layers deep) are O(0.1-1) and a parity check on them has teeth."""
+    sd = make_state_dict(cfg, seed=seed, prefix="longformer.")
+    rng = np.random.default_rng(seed + 5000)
+    for key, shape, kind in classifier_keys(cfg):
+        std = head_std if kind == "w" else 0.05
+        sd[key] = torch.from_numpy(rng.standard_normal(shape, dtype=np.float32) * np.float32(std))
+    return sd
