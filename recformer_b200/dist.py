@@ -3,8 +3,11 @@
 The hot path shards in two ways:
   * full-catalogue scoring: the item table is sharded by contiguous item-id ranges; each rank
     runs the fused cosine-GEMM + top-k on its shard and the per-rank (k scores, k ids, label
-    score) are exchanged with ONE all-gather, then merged locally (rf_topk_merge);
-  * data-parallel training: replicas; the flat fp32 gradient buffer is all-reduced in one call.
+    score) are exchanged with ONE all-gather, then merged locally (rf_topk_merge) — or, with a
+    PeerTopkExchange, stored by the scorer straight into every rank's symmetric buffer over NVLink peer
+    memory (no NCCL launch: scorer -> barrier -> merge);
+  * data-parallel training: replicas; the flat gradient buffer is all-reduced in one call
+    (allreduce_gradients) or in layer buckets overlapped with the backward pass (GradSync, bf16 wire format).
 """
 from __future__ import annotations
 
