@@ -63,6 +63,43 @@ def test_argument_validation_errors_without_gpu():
     assert lib.rf_cosine_topk(None, None, 1, 1, 768, 0.05, 10, 0, None, None, None, None, None, None) == -1
 
 
+def test_header_is_plain_c_and_binds_from_a_c_program(tmp_path):
+    """The drop-in boundary is a C ABI: include/recformer_b200.h must compile as C (no C++ / torch types) and a C
+    program must be able to bind the library with nothing but dlopen — what a non-Python host of the reference would do
+    (INTEGRATION.md).  No compute call is made (there is no GPU here): version, argument validation, error string."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    src = tmp_path / "bind.c"
+    src.write_text(r"""
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+#include "recformer_b200.h"
+int main(int argc, char** argv) {
+  void* h = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);
+  if (!h) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 2; }
+  int (*version)(void) = (int (*)(void))dlsym(h, "rf_version");
+  const char* (*last_error)(void) = (const char* (*)(void))dlsym(h, "rf_last_error");
+  int (*gemm)(const rf_gemm_args*, rf_stream_t) = (int (*)(const rf_gemm_args*, rf_stream_t))dlsym(h, "rf_gemm_bf16");
+  if (!version || !last_error || !gemm) return 3;
+  rf_gemm_args a;
+  memset(&a, 0, sizeof a);
+  int rc = gemm(&a, (rf_stream_t)0);
+  printf("%d %d %s\n", version(), rc, last_error());
+  return 0;
+}
+""")
+    exe = tmp_path / "bind"
+    flags = ["-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", cuda_inc]
+    subprocess.run(["gcc", *flags, "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "recformer_b200.h")], check=True)
+    subprocess.run(["gcc", *flags, str(src), "-o", str(exe), "-ldl"], check=True)
+    out = subprocess.run([str(exe), _lib.LIB_PATH], check=True, capture_output=True, text=True).stdout.split(None, 2)
+    assert int(out[0]) >= 102 and int(out[1]) == -1 and "empty problem" in out[2], out
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/librecformer_b200.so")
