@@ -2,7 +2,8 @@
 // attention_window 64); wider windows run it once per window segment (shifted keys, see attention_fwd.cu)
 // with the FINAL log-sum-exp / context of the merged forward, accumulating dQ in an fp32 scratch.
 //
-// One CTA = one (batch, head, 128-query tile), the same tiling as the forward kernel:
+// One work item = one (batch, head, 128-query tile), the same tiling as the forward kernel; the kernel is PERSISTENT
+// (one CTA per SM walks a contiguous run of work items, see band_attn_bwd_kernel below).  Per work item:
 //   S  = Q K^T,  dP = dO V^T                      tcgen05.mma -> TMEM (2 x 208 columns)
 //   delta = rowsum(dO o O) (= sum_j P'_j dP_j, taken from the saved context instead of a first pass
 //   over the probabilities),  P = exp(S - lse),  dS = P (dP - delta)    fp32, thread = query row
@@ -12,12 +13,15 @@
 //   dK = dS^T Q        A = dS (MN-major view),                       B = Q  (MN-major)
 // so no operand is ever transposed in memory.  dQ (scaled back by 1/sqrt(D)) is written as bf16
 // into dqkv.  dK/dV tiles overlap between neighbouring query tiles: at attention_window 64 a key receives at most
-// two partial sums, which go straight into the bf16 gradient with 16-byte red.add.noftz.v4.bf16x2 (only the CLS
-// key, which every tile feeds, is accumulated in fp32 and folded in by a tiny kernel); wide windows (several
-// segments per key) accumulate dK/dV and dQ in fp32 scratch that a fold kernel converts.  The global query row
-// receives no band gradient (its band output is overwritten by the global row, HF:615-626).
-// Key validity is a bit mask per tile (band position by shifts: no per-element shared-memory flag loads), and the
-// dropout masks are regenerated from ABSOLUTE (row, key) coordinates (rf_ptx.cuh), independent of the tiling.
+// two partial sums.  Inside a CTA's run the shared keys are carried in registers to the next tile and stored once with
+// plain 16-byte stores; only at the ends of a run do they go into the bf16 gradient with 16-byte
+// red.add.noftz.v4.bf16x2 (the CLS key, which every tile feeds, is summed in registers per (sequence, head), then
+// accumulated in fp32 and folded in by a tiny kernel); wide windows (several segments per key) accumulate dK/dV and
+// dQ in fp32 scratch that a fold kernel converts.  The global query row receives no band gradient (its band output is
+// overwritten by the global row, HF:615-626).
+// Key validity is a bit mask per tile (band position by shifts: no per-element shared-memory flag loads).  Dropout:
+// the keep bits the forward saved (rf_attn_args.keepbits, one word per thread) are read back; without them the masks
+// are regenerated from ABSOLUTE (row, key) coordinates (rf_ptx.cuh), independent of the tiling — bit-identical.
 #include <cuda_bf16.h>
 #include <math.h>
 #include <stdlib.h>
